@@ -1,0 +1,215 @@
+"""ctypes binding of include/filo_b200.h.  Fails loudly when the CUDA library is missing (no fallback)."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfilo_b200.so")
+
+FN_LAST, FN_RATE, FN_INCREASE, FN_DELTA, FN_SUM_OVER_TIME, FN_AVG_OVER_TIME, FN_COUNT_OVER_TIME, \
+    FN_MIN_OVER_TIME, FN_MAX_OVER_TIME, FN_TIMESTAMP = range(10)
+AGG_NONE, AGG_SUM, AGG_AVG, AGG_MIN, AGG_MAX, AGG_COUNT, AGG_TOPK, AGG_BOTTOMK = range(8)
+SCHEMA_CUMULATIVE = 1
+Q_PARTIAL = 1
+OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CORRUPT_VECTOR, ERR_UNSUPPORTED, ERR_QUERY_LIMIT, ERR_BAD_QUERY, ERR_OOM = 0, -1, -2, -3, -4, -5, -6, -7
+
+EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_last_error", "filo_load_series", "filo_synth_table",
+           "filo_table_set_groups", "filo_table_get_info", "filo_table_read_record", "filo_table_free",
+           "filo_num_windows", "filo_query", "filo_query_device", "filo_present_partials"]
+
+
+class Cfg(C.Structure):
+    _fields_ = [("inclusive_range", C.c_int32), ("group_by_cardinality_limit", C.c_int32),
+                ("min_step_ms", C.c_int64), ("max_data_per_shard_query", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("bytes_scanned", C.c_int64), ("samples_scanned", C.c_int64), ("kernel_ns", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class TableInfo(C.Structure):
+    _fields_ = [("n_series", C.c_int64), ("n_chunks", C.c_int64), ("n_samples", C.c_int64), ("arena_bytes", C.c_int64),
+                ("algorithmic_bytes", C.c_int64), ("max_rows_per_series", C.c_int32), ("max_chunks_per_series", C.c_int32),
+                ("n_groups", C.c_int32), ("schema_flags", C.c_int32)]
+
+
+class SynthSpec(C.Structure):
+    _fields_ = [("n_series", C.c_int64), ("rows_per_series", C.c_int32), ("rows_per_chunk", C.c_int32),
+                ("t0_ms", C.c_int64), ("interval_ms", C.c_int32), ("ts_jitter_ms", C.c_int32),
+                ("value_kind", C.c_int32), ("value_enc", C.c_int32), ("reset_period", C.c_int32),
+                ("nan_per_million", C.c_int32), ("n_groups", C.c_int32), ("schema_flags", C.c_int32),
+                ("seed", C.c_uint64), ("series_id_base", C.c_int64), ("sin_table", C.c_void_p)]
+
+
+class FiloError(RuntimeError):
+    """Mirrors how the JNI shim surfaces a non-zero status: RuntimeException(message)."""
+
+    def __init__(self, code, msg):
+        super().__init__("filo_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libfilo_b200.so is not built (%s). Run `python -m filodb_b200.build`; there is no CPU fallback." % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _sig(_lib)
+    return _lib
+
+
+def _sig(L):
+    i32, i64, vp = C.c_int32, C.c_int64, C.c_void_p
+    L.filo_ctx_create.restype = i32; L.filo_ctx_create.argtypes = [i32, C.POINTER(Cfg), C.POINTER(vp)]
+    L.filo_ctx_destroy.restype = None; L.filo_ctx_destroy.argtypes = [vp]
+    L.filo_last_error.restype = i32; L.filo_last_error.argtypes = [vp, C.c_char_p, i32]
+    L.filo_load_series.restype = i32
+    L.filo_load_series.argtypes = [vp, i64, vp, vp, i32, i32, vp, i32, i32, C.POINTER(vp)]
+    L.filo_synth_table.restype = i32; L.filo_synth_table.argtypes = [vp, C.POINTER(SynthSpec), C.POINTER(vp)]
+    L.filo_table_set_groups.restype = i32; L.filo_table_set_groups.argtypes = [vp, vp, vp, i32]
+    L.filo_table_get_info.restype = i32; L.filo_table_get_info.argtypes = [vp, C.POINTER(TableInfo)]
+    L.filo_table_read_record.restype = i64; L.filo_table_read_record.argtypes = [vp, vp, i64, vp, i64]
+    L.filo_table_free.restype = None; L.filo_table_free.argtypes = [vp, vp]
+    L.filo_num_windows.restype = i32; L.filo_num_windows.argtypes = [i64, i64, i64]
+    L.filo_query.restype = i32
+    L.filo_query.argtypes = [vp, vp, i32, i64, i64, i64, i64, i32, i32, i32, vp, vp, C.POINTER(Stats)]
+    L.filo_query_device.restype = i32
+    L.filo_query_device.argtypes = [vp, vp, i32, i64, i64, i64, i64, i32, i32, i32, vp, vp, vp, C.POINTER(Stats)]
+    L.filo_present_partials.restype = i32; L.filo_present_partials.argtypes = [vp, i32, i64, vp, vp, vp, vp]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def num_windows(start, step, end):
+    return lib().filo_num_windows(start, step, end)
+
+
+def sin_table(rows):
+    return np.sin(np.arange(1, rows + 1, dtype=np.float64))
+
+
+class Table:
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+
+    def info(self):
+        ti = TableInfo()
+        self.ctx._check(lib().filo_table_get_info(self.h, C.byref(ti)))
+        return ti
+
+    def set_groups(self, group_ids, n_groups):
+        g = np.ascontiguousarray(group_ids, np.int32) if group_ids is not None else None
+        self.ctx._check(lib().filo_table_set_groups(self.ctx.h, self.h, _p(g), n_groups))
+
+    def read_record(self, series):
+        buf = np.zeros(1 << 16, np.uint8)
+        n = lib().filo_table_read_record(self.ctx.h, self.h, series, _p(buf), buf.size)
+        if n < 0 and -n > buf.size:
+            buf = np.zeros(-n, np.uint8)
+            n = lib().filo_table_read_record(self.ctx.h, self.h, series, _p(buf), buf.size)
+        if n < 0:
+            self.ctx._check(int(n))
+        return buf[:n].copy()
+
+    def free(self):
+        if self.h:
+            lib().filo_table_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    def __init__(self, device=0, inclusive_range=True, group_by_cardinality_limit=0, min_step_ms=0, max_data_per_shard_query=0):
+        cfg = Cfg(int(inclusive_range), group_by_cardinality_limit, min_step_ms, max_data_per_shard_query)
+        h = C.c_void_p()
+        rc = lib().filo_ctx_create(device, C.byref(cfg), C.byref(h))
+        if rc != 0:
+            buf = C.create_string_buffer(512)
+            lib().filo_last_error(None, buf, 512)
+            raise FiloError(rc, buf.value.decode())
+        self.h = h
+        self.last_stats = None
+
+    def close(self):
+        if self.h:
+            lib().filo_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            buf = C.create_string_buffer(1024)
+            lib().filo_last_error(self.h, buf, 1024)
+            raise FiloError(rc, buf.value.decode())
+
+    def load_series(self, n_chunks, info_addrs, ts_col=0, val_col=1, group_ids=None, n_groups=0, schema_flags=0):
+        nch = np.ascontiguousarray(n_chunks, np.int32)
+        addrs = np.ascontiguousarray(info_addrs, np.uint64)
+        g = np.ascontiguousarray(group_ids, np.int32) if group_ids is not None else None
+        h = C.c_void_p()
+        self._check(lib().filo_load_series(self.h, nch.size, _p(nch), _p(addrs), ts_col, val_col, _p(g), n_groups, schema_flags, C.byref(h)))
+        return Table(self, h)
+
+    def synth_table(self, n_series, rows_per_series, rows_per_chunk=400, t0_ms=1_700_000_000_000, interval_ms=15000,
+                    ts_jitter_ms=0, value_kind=0, value_enc=0, reset_period=0, nan_per_million=0, n_groups=0,
+                    schema_flags=0, seed=42, series_id_base=0):
+        st = sin_table(rows_per_series)
+        spec = SynthSpec(n_series, rows_per_series, rows_per_chunk, t0_ms, interval_ms, ts_jitter_ms, value_kind, value_enc,
+                         reset_period, nan_per_million, n_groups, schema_flags, seed, series_id_base, st.ctypes.data)
+        h = C.c_void_p()
+        self._check(lib().filo_synth_table(self.h, C.byref(spec), C.byref(h)))
+        return Table(self, h)
+
+    def out_shapes(self, table, start, step, end, aggr, k):
+        ti = table.info()
+        T = num_windows(start, step if step > 0 else 1, end)
+        if aggr == AGG_NONE:
+            return (ti.n_series, T), None
+        if aggr in (AGG_TOPK, AGG_BOTTOMK):
+            return (ti.n_groups, T, k), (ti.n_groups, T, k)
+        return (ti.n_groups, T), (ti.n_groups, T)
+
+    def query(self, table, fn, start, step, end, window, aggr=AGG_NONE, k=0, flags=0):
+        """PeriodicSamplesMapper(+AggregateMapReduce) -> host numpy arrays (values[, aux])."""
+        vs, as_ = self.out_shapes(table, start, step, end, aggr, k)
+        out = np.zeros(vs, np.float64)
+        aux = np.zeros(as_, np.int64) if as_ is not None else None
+        st = Stats()
+        self._check(lib().filo_query(self.h, table.h, fn, start, step, end, window, aggr, k, flags, _p(out), _p(aux), C.byref(st)))
+        self.last_stats = st.as_dict()
+        if aggr in (AGG_AVG, AGG_TOPK, AGG_BOTTOMK) or (flags & Q_PARTIAL and aggr != AGG_NONE):
+            return out, aux
+        return out
+
+    def query_device(self, table, fn, start, step, end, window, d_out, d_aux=0, aggr=AGG_NONE, k=0, flags=0, stream=0, want_stats=True):
+        st = Stats()
+        self._check(lib().filo_query_device(self.h, table.h, fn, start, step, end, window, aggr, k, flags,
+                                            C.c_void_p(d_out), C.c_void_p(d_aux) if d_aux else None,
+                                            C.c_void_p(stream) if stream else None, C.byref(st) if want_stats else None))
+        if want_stats:
+            self.last_stats = st.as_dict()
+        return self.last_stats
+
+    def present_partials(self, aggr, n, d_values, d_counts, d_out, stream=0):
+        self._check(lib().filo_present_partials(self.h, aggr, n, C.c_void_p(d_values), C.c_void_p(d_counts), C.c_void_p(d_out),
+                                                C.c_void_p(stream) if stream else None))

@@ -1,0 +1,524 @@
+// C-ABI implementation (include/filo_b200.h): context, chunk-arena loader, query orchestration.
+// Host side only orchestrates: every query result is produced by the sm_100a kernels in scan_kernels.cu.
+#include "../../include/filo_b200.h"
+#include "kernels.h"
+#include "host_util.h"
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace filo;
+
+struct filo_ctx {
+  int device = 0;
+  filo_cfg cfg{};
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  size_t max_smem_optin = 0;
+  std::mutex err_mu;
+  std::string err;
+};
+
+struct filo_table {
+  int64_t n_series = 0, n_chunks = 0, n_samples = 0, arena_bytes = 0, algorithmic_bytes = 0;
+  int32_t max_rows = 0, max_chunks = 0, schema_flags = 0;
+  uint8_t* d_arena = nullptr;
+  int64_t* d_rec_off = nullptr;     // [n_series + 1]
+  // grouping
+  int32_t n_groups = 1;
+  bool grouped = false;             // false: single group, order == identity
+  int32_t* d_order = nullptr;       // [n_series] series ordinals sorted by group (stable)
+  int64_t* d_group_start = nullptr; // [n_groups + 1]
+  int64_t* d_gis = nullptr;         // [n_groups + 1] first item of each group
+  int64_t* d_item_begin = nullptr;  // [n_items + 1]
+  int64_t n_items = 0;
+  int seg = 1;
+};
+
+static thread_local std::string tl_err;
+
+static int32_t fail(filo_ctx* ctx, int32_t code, const std::string& msg) {
+  tl_err = msg;
+  if (ctx) { std::lock_guard<std::mutex> g(ctx->err_mu); ctx->err = msg; }
+  return code;
+}
+#define CUDA_TRY(ctx, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) \
+  return fail(ctx, _e == cudaErrorMemoryAllocation ? FILO_ERR_OOM : FILO_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
+
+extern "C" {
+
+int32_t filo_last_error(filo_ctx* ctx, char* buf, int32_t len) {
+  std::string m;
+  if (ctx) { std::lock_guard<std::mutex> g(ctx->err_mu); m = ctx->err; } else m = tl_err;
+  if (buf && len > 0) { int n = std::min<int>(len - 1, (int)m.size()); std::memcpy(buf, m.data(), n); buf[n] = 0; }
+  return (int32_t)m.size();
+}
+
+int32_t filo_ctx_create(int32_t device, const filo_cfg* cfg, filo_ctx** out) {
+  if (!out) return fail(nullptr, FILO_ERR_INVALID_ARG, "out is null");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, FILO_ERR_CUDA, std::string("no CUDA device (no CPU fallback exists): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, FILO_ERR_INVALID_ARG, "bad device ordinal");
+  CUDA_TRY(nullptr, cudaSetDevice(device));
+  auto* c = new filo_ctx();
+  c->device = device;
+  if (cfg) c->cfg = *cfg; else { c->cfg.inclusive_range = 1; c->cfg.group_by_cardinality_limit = 0; c->cfg.min_step_ms = 0; c->cfg.max_data_per_shard_query = 0; }
+  cudaDeviceProp p; CUDA_TRY(nullptr, cudaGetDeviceProperties(&p, device));
+  c->sm_count = p.multiProcessorCount;
+  c->max_smem_optin = p.sharedMemPerBlockOptin;
+  CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  return FILO_OK;
+}
+
+void filo_ctx_destroy(filo_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+void filo_table_free(filo_ctx* ctx, filo_table* t) {
+  if (!t) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  cudaFree(t->d_arena); cudaFree(t->d_rec_off); cudaFree(t->d_order); cudaFree(t->d_group_start);
+  cudaFree(t->d_gis); cudaFree(t->d_item_begin);
+  delete t;
+}
+
+int32_t filo_table_get_info(const filo_table* t, filo_table_info* o) {
+  if (!t || !o) return FILO_ERR_INVALID_ARG;
+  o->n_series = t->n_series; o->n_chunks = t->n_chunks; o->n_samples = t->n_samples; o->arena_bytes = t->arena_bytes;
+  o->algorithmic_bytes = t->algorithmic_bytes; o->max_rows_per_series = t->max_rows; o->max_chunks_per_series = t->max_chunks;
+  o->n_groups = t->n_groups; o->schema_flags = t->schema_flags;
+  return FILO_OK;
+}
+
+int32_t filo_num_windows(int64_t start, int64_t step, int64_t end) {
+  if (step <= 0) step = 1;
+  if (end < start) return 1;
+  return (int32_t)((end - start) / step) + 1;
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// grouping: stable sort of series by group id on the device, group bounds, work items of <= seg series of one group
+// ------------------------------------------------------------------------------------------------------------------
+static int32_t build_groups(filo_ctx* ctx, filo_table* t, const int32_t* d_group_ids /* device, may be null */, int32_t n_groups) {
+  cudaStream_t s = ctx->stream;
+  cudaFree(t->d_order); cudaFree(t->d_group_start); cudaFree(t->d_gis); cudaFree(t->d_item_begin);
+  t->d_order = nullptr; t->d_group_start = t->d_gis = t->d_item_begin = nullptr;
+  const int64_t S = t->n_series;
+  if (n_groups <= 0) n_groups = 1;
+  t->n_groups = n_groups;
+  t->grouped = d_group_ids != nullptr;
+  // seg: enough items to fill the machine a few times over, capped so partial rows stay small
+  int64_t target_items = (int64_t)ctx->sm_count * 64 * 4;
+  int64_t seg = S / std::max<int64_t>(target_items, 1);
+  t->seg = (int)std::min<int64_t>(std::max<int64_t>(seg, 1), 256);
+  CUDA_TRY(ctx, cudaMalloc(&t->d_group_start, (size_t)(n_groups + 1) * 8));
+  CUDA_TRY(ctx, cudaMalloc(&t->d_gis, (size_t)(n_groups + 1) * 8));
+  if (t->grouped && S > 0) {
+    int32_t *keys_out = nullptr, *vals_in = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&t->d_order, (size_t)S * 4));
+    CUDA_TRY(ctx, cudaMalloc(&keys_out, (size_t)S * 4));
+    CUDA_TRY(ctx, cudaMalloc(&vals_in, (size_t)S * 4));
+    CUDA_TRY(ctx, launch_iota(vals_in, S, s));
+    size_t tmp_bytes = 0;
+    int end_bit = 1; while ((1ll << end_bit) < n_groups && end_bit < 31) ++end_bit;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_group_ids, keys_out, vals_in, t->d_order, (int)S, 0, end_bit, s);
+    void* tmp = nullptr; CUDA_TRY(ctx, cudaMalloc(&tmp, tmp_bytes + 16));
+    CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d_group_ids, keys_out, vals_in, t->d_order, (int)S, 0, end_bit, s));
+    CUDA_TRY(ctx, launch_group_bounds(keys_out, S, n_groups, t->d_group_start, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    cudaFree(tmp); cudaFree(keys_out); cudaFree(vals_in);
+  } else {
+    std::vector<int64_t> gs(n_groups + 1, S); gs[0] = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(t->d_group_start, gs.data(), gs.size() * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  }
+  // items
+  int64_t* d_cnt = nullptr; CUDA_TRY(ctx, cudaMalloc(&d_cnt, (size_t)(n_groups + 1) * 8));
+  CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)(n_groups + 1) * 8, s));
+  CUDA_TRY(ctx, launch_group_item_count(t->d_group_start, n_groups, t->seg, d_cnt, s));
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cnt, t->d_gis, n_groups + 1, s);
+  void* tmp = nullptr; CUDA_TRY(ctx, cudaMalloc(&tmp, tmp_bytes + 16));
+  CUDA_TRY(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_cnt, t->d_gis, n_groups + 1, s));
+  int64_t n_items = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&n_items, t->d_gis + n_groups, 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  t->n_items = n_items;
+  CUDA_TRY(ctx, cudaMalloc(&t->d_item_begin, (size_t)(n_items + 1) * 8));
+  CUDA_TRY(ctx, launch_fill_items(t->d_group_start, t->d_gis, n_groups, t->seg, n_items, S, t->d_item_begin, s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  cudaFree(tmp); cudaFree(d_cnt);
+  return FILO_OK;
+}
+
+// shared by the loader and the synthetic generator
+int32_t filo_internal_finish_table(filo_ctx* ctx, filo_table* t, const int32_t* d_group_ids, int32_t n_groups) {
+  return build_groups(ctx, t, d_group_ids, n_groups);
+}
+filo_table* filo_internal_new_table() { return new filo_table(); }
+void filo_internal_set_arena(filo_table* t, uint8_t* d_arena, int64_t* d_rec_off, int64_t n_series, int64_t n_chunks, int64_t n_samples,
+                             int64_t arena_bytes, int64_t algorithmic_bytes, int32_t max_rows, int32_t max_chunks, int32_t schema_flags) {
+  t->d_arena = d_arena; t->d_rec_off = d_rec_off; t->n_series = n_series; t->n_chunks = n_chunks; t->n_samples = n_samples;
+  t->arena_bytes = arena_bytes; t->algorithmic_bytes = algorithmic_bytes; t->max_rows = max_rows; t->max_chunks = max_chunks;
+  t->schema_flags = schema_flags;
+}
+cudaStream_t filo_internal_stream(filo_ctx* ctx) { return ctx->stream; }
+int filo_internal_device(filo_ctx* ctx) { return ctx->device; }
+int32_t filo_internal_fail(filo_ctx* ctx, int32_t code, const char* msg) { return fail(ctx, code, msg); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// loader: walk ChunkSetInfo blocks -> records -> device arena
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct VecInfo { const uint8_t* p; int32_t total; int32_t len; bool drop_patch; bool drop; };
+
+inline int32_t rd32(const uint8_t* p) { int32_t v; std::memcpy(&v, p, 4); return v; }
+inline int64_t rd64(const uint8_t* p) { int64_t v; std::memcpy(&v, p, 8); return v; }
+
+// IntBinaryVector.simple validity (MatchError otherwise), IntBinaryVector.scala:120-137
+inline bool inner_ok(const uint8_t* in, int32_t& len) {
+  int nbits = in[6] & 0x7f; bool sgn = in[6] & 0x80; int bs = in[7] & 0x3f;
+  bool ok = sgn ? (nbits == 32 || nbits == 16 || nbits == 8) : (nbits == 32 || nbits == 16 || nbits == 8 || nbits == 4 || nbits == 2);
+  if (!ok) return false;
+  len = ((rd32(in) - 4) * 8 + (bs != 0 ? bs - 8 : 0)) / nbits;
+  return true;
+}
+
+// returns 0 ok, else FILO_ERR_*
+int classify_ts(const uint8_t* v, VecInfo& o) {
+  int wire = (uint16_t)(v[4] | (v[5] << 8));
+  if (wire == WIRE_MASKED) { v = v + rd32(v + 8); wire = (uint16_t)(v[4] | (v[5] << 8)); if (wire == WIRE_MASKED) return FILO_ERR_CORRUPT_VECTOR; }
+  o.p = v; o.total = rd32(v) + 4; o.drop_patch = false; o.drop = false;
+  if (wire == WIRE_DDV_CONST) { if (o.total != 24) return FILO_ERR_CORRUPT_VECTOR; o.len = rd32(v + 8); }
+  else if (wire == WIRE_RAW64) o.len = (rd32(v) - 4) / 8;
+  else if (wire == WIRE_DDV) { if (o.total < 28 || !inner_ok(v + 20, o.len)) return FILO_ERR_CORRUPT_VECTOR; }
+  else return FILO_ERR_CORRUPT_VECTOR;
+  return (o.total >= 8 && o.len >= 0) ? 0 : FILO_ERR_CORRUPT_VECTOR;
+}
+int classify_val(const uint8_t* v, VecInfo& o) {
+  int wire = (uint16_t)(v[4] | (v[5] << 8));
+  const bool outer_drop = (v[7] & 0x80) != 0;
+  bool masked = false;
+  if (wire == WIRE_MASKED) { masked = true; v = v + rd32(v + 8); wire = (uint16_t)(v[4] | (v[5] << 8)); if (wire == WIRE_MASKED) return FILO_ERR_CORRUPT_VECTOR; }
+  o.p = v; o.total = rd32(v) + 4; o.drop_patch = masked; o.drop = outer_drop;
+  if (wire == WIRE_RAW64) o.len = (rd32(v) - 4) / 8;
+  else if (wire == WIRE_DDV_CONST) { if (o.total != 24) return FILO_ERR_CORRUPT_VECTOR; o.len = rd32(v + 8); }
+  else if (wire == WIRE_DDV) { if (o.total < 28 || !inner_ok(v + 20, o.len)) return FILO_ERR_CORRUPT_VECTOR; }
+  else if (wire == WIRE_XOR) {
+    o.len = rd32(v + XOR_OFF_N);
+    int ng = (uint16_t)(v[12] | (v[13] << 8)), po = (uint16_t)(v[14] | (v[15] << 8));
+    if (o.len <= 0 || ng != (o.len - 1 + 7) / 8 || po < 16 + 2 * ng || (po & 7) || po + 8 > o.total) return FILO_ERR_CORRUPT_VECTOR;
+  } else return FILO_ERR_CORRUPT_VECTOR;
+  return (o.total >= 8 && o.len >= 0) ? 0 : FILO_ERR_CORRUPT_VECTOR;
+}
+
+struct SeriesPlan { uint32_t rec_bytes; uint32_t n_chunks; uint32_t n_rows; uint32_t flags; };
+
+} // namespace
+
+extern "C" int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32_t* n_chunks, const uint64_t* addrs,
+                                    int32_t ts_col, int32_t val_col, const int32_t* group_ids, int32_t n_groups,
+                                    int32_t schema_flags, filo_table** out) {
+  if (!ctx || !out || n_series < 0 || (n_series > 0 && (!n_chunks || !addrs)) || ts_col < 0 || val_col < 0)
+    return fail(ctx, FILO_ERR_INVALID_ARG, "filo_load_series: bad arguments");
+  if (group_ids && n_groups <= 0) return fail(ctx, FILO_ERR_INVALID_ARG, "group_ids given but n_groups <= 0");
+  if (group_ids && ctx->cfg.group_by_cardinality_limit > 0 && n_groups > ctx->cfg.group_by_cardinality_limit)
+    return fail(ctx, FILO_ERR_QUERY_LIMIT, "Query exceeded group-by cardinality limit");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int nthreads = host_threads();
+  std::vector<int64_t> chunk_base((size_t)n_series + 1, 0);
+  for (int64_t i = 0; i < n_series; ++i) {
+    if (n_chunks[i] < 0) return fail(ctx, FILO_ERR_INVALID_ARG, "negative n_chunks");
+    chunk_base[i + 1] = chunk_base[i] + n_chunks[i];
+  }
+  // ---- pass 1: validate + size
+  std::vector<SeriesPlan> plan((size_t)n_series);
+  std::atomic<int> err_code{0}; std::atomic<int64_t> err_series{-1};
+  std::vector<int64_t> t_chunks(nthreads, 0), t_samples(nthreads, 0), t_alg(nthreads, 0);
+  std::vector<int32_t> t_maxrows(nthreads, 0), t_maxch(nthreads, 0);
+  parallel_for(n_series, nthreads, [&](int tid, int64_t b, int64_t e) {
+    for (int64_t i = b; i < e && !err_code.load(std::memory_order_relaxed); ++i) {
+      uint32_t bytes = sizeof(RecordHeader), rows = 0, nch = 0, flags = REC_ALL_TS_CONST;
+      int64_t prev_start = INT64_MIN, prev_end = INT64_MIN;
+      for (int32_t j = 0; j < n_chunks[i]; ++j) {
+        const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)addrs[chunk_base[i] + j]);
+        const int32_t numRows = rd32(info + 8);
+        if (numRows <= 0) continue;                                   // skipped by WindowedChunkIterator (ChunkSetInfo.scala:493)
+        const int64_t startT = (int64_t)(((1ull << 63) ^ (uint64_t)rd64(info)) >> 22), endT = rd64(info + 20);
+        VecInfo tv, vv;
+        int rc = classify_ts(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * ts_col)), tv);
+        if (!rc) rc = classify_val(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * val_col)), vv);
+        if (!rc && (numRows > tv.len || numRows > vv.len)) rc = FILO_ERR_CORRUPT_VECTOR;
+        if (!rc && (startT < prev_start || endT < prev_end)) rc = FILO_ERR_UNSUPPORTED;
+        if (rc) { int z = 0; if (err_code.compare_exchange_strong(z, rc)) err_series = i; return; }
+        prev_start = startT; prev_end = endT;
+        bytes += sizeof(ChunkEntry) + align_up((uint32_t)tv.total, 8) + align_up((uint32_t)vv.total, 8);
+        rows += (uint32_t)vv.len; ++nch;
+        const int twire = (uint16_t)(tv.p[4] | (tv.p[5] << 8)), vwire = (uint16_t)(vv.p[4] | (vv.p[5] << 8));
+        if (twire != WIRE_DDV_CONST) flags &= ~REC_ALL_TS_CONST;
+        if (vv.drop) flags |= REC_ANY_DROP;
+        if (vwire != WIRE_RAW64) flags |= REC_ANY_DECODE;
+        t_samples[tid] += numRows; t_alg[tid] += 28 + 16 + tv.total + vv.total;
+      }
+      plan[i] = SeriesPlan{align_up(bytes, 16), nch, rows, flags};
+      t_chunks[tid] += nch; t_maxrows[tid] = std::max<int32_t>(t_maxrows[tid], (int32_t)rows); t_maxch[tid] = std::max<int32_t>(t_maxch[tid], (int32_t)nch);
+    }
+  });
+  if (err_code) {
+    const char* what = err_code == FILO_ERR_UNSUPPORTED ? "chunks of a series are not in increasing time order (unsupported on the device path)"
+                                                       : "CorruptVector: unknown or inconsistent BinaryVector wire format";
+    return fail(ctx, err_code, std::string(what) + " at series " + std::to_string(err_series.load()));
+  }
+  std::vector<int64_t> rec_off((size_t)n_series + 1, 0);
+  for (int64_t i = 0; i < n_series; ++i) rec_off[i + 1] = rec_off[i] + plan[i].rec_bytes;
+  const int64_t arena_bytes = rec_off[n_series];
+  if (ctx->cfg.max_data_per_shard_query > 0) {
+    int64_t alg = 0; for (auto a : t_alg) alg += a;
+    if (alg > ctx->cfg.max_data_per_shard_query) return fail(ctx, FILO_ERR_QUERY_LIMIT, "raw data bytes scanned exceeds max-data-per-shard-query");
+  }
+  // ---- pass 2: fill pinned slabs, copy
+  auto* t = new filo_table();
+  uint8_t* d_arena = nullptr; int64_t* d_rec_off = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&d_arena, (size_t)arena_bytes + 64));
+  CUDA_TRY(ctx, cudaMalloc(&d_rec_off, (size_t)(n_series + 1) * 8));
+  CUDA_TRY(ctx, cudaMemsetAsync(d_arena + arena_bytes, 0, 64, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_rec_off, rec_off.data(), (size_t)(n_series + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t SLAB = std::min<size_t>((size_t)64 << 20, std::max<size_t>((size_t)arena_bytes, 1 << 16));
+  uint8_t* slab[2] = {nullptr, nullptr}; cudaEvent_t ev[2];
+  for (int b = 0; b < 2; ++b) { CUDA_TRY(ctx, cudaHostAlloc(&slab[b], SLAB + (1 << 20), cudaHostAllocDefault)); CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming)); }
+  int64_t s0 = 0; int which = 0;
+  while (s0 < n_series) {
+    int64_t s1 = s0; const int64_t base = rec_off[s0];
+    while (s1 < n_series && (size_t)(rec_off[s1 + 1] - base) <= SLAB) ++s1;
+    if (s1 == s0) {   // a single record larger than the slab: grow this slab
+      cudaFreeHost(slab[which]); size_t need = (size_t)plan[s0].rec_bytes;
+      CUDA_TRY(ctx, cudaEventSynchronize(ev[which]));
+      CUDA_TRY(ctx, cudaHostAlloc(&slab[which], need + (1 << 20), cudaHostAllocDefault)); s1 = s0 + 1;
+    }
+    CUDA_TRY(ctx, cudaEventSynchronize(ev[which]));
+    uint8_t* dst0 = slab[which];
+    parallel_for(s1 - s0, nthreads, [&](int, int64_t b, int64_t e) {
+      for (int64_t ii = b; ii < e; ++ii) {
+        const int64_t i = s0 + ii;
+        uint8_t* rec = dst0 + (rec_off[i] - base);
+        std::memset(rec, 0, plan[i].rec_bytes);
+        RecordHeader h{plan[i].rec_bytes, plan[i].n_chunks, plan[i].n_rows, plan[i].flags};
+        std::memcpy(rec, &h, sizeof h);
+        uint32_t off = sizeof(RecordHeader) + plan[i].n_chunks * (uint32_t)sizeof(ChunkEntry);
+        uint32_t c = 0, row_base = 0;
+        for (int32_t j = 0; j < n_chunks[i]; ++j) {
+          const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)addrs[chunk_base[i] + j]);
+          const int32_t numRows = rd32(info + 8);
+          if (numRows <= 0) continue;
+          VecInfo tv, vv;
+          classify_ts(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * ts_col)), tv);
+          classify_val(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * val_col)), vv);
+          ChunkEntry ce;
+          ce.start_time = (int64_t)(((1ull << 63) ^ (uint64_t)rd64(info)) >> 22); ce.end_time = rd64(info + 20);
+          ce.num_rows = numRows; ce.ts_off = off; std::memcpy(rec + off, tv.p, tv.total); off += align_up((uint32_t)tv.total, 8);
+          ce.val_off = off; std::memcpy(rec + off, vv.p, vv.total);
+          if (vv.drop_patch) { if (vv.drop) rec[off + 7] |= 0x80; else rec[off + 7] &= 0x7f; }
+          off += align_up((uint32_t)vv.total, 8);
+          ce.row_base = row_base; row_base += (uint32_t)vv.len;
+          std::memcpy(rec + sizeof(RecordHeader) + c * sizeof(ChunkEntry), &ce, sizeof ce); ++c;
+        }
+      }
+    });
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_arena + base, dst0, (size_t)(rec_off[s1] - base), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ev[which], ctx->stream));
+    which ^= 1; s0 = s1;
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int b = 0; b < 2; ++b) { cudaFreeHost(slab[b]); cudaEventDestroy(ev[b]); }
+  int64_t nch = 0, ns = 0, alg = 0; int32_t mr = 0, mc = 0;
+  for (int i = 0; i < nthreads; ++i) { nch += t_chunks[i]; ns += t_samples[i]; alg += t_alg[i]; mr = std::max(mr, t_maxrows[i]); mc = std::max(mc, t_maxch[i]); }
+  filo_internal_set_arena(t, d_arena, d_rec_off, n_series, nch, ns, arena_bytes + (n_series + 1) * 8, alg, mr, mc, schema_flags);
+  // groups
+  int32_t* d_gid = nullptr;
+  if (group_ids && n_series > 0) {
+    for (int64_t i = 0; i < n_series; ++i) if (group_ids[i] < 0 || group_ids[i] >= n_groups) { filo_table_free(ctx, t); return fail(ctx, FILO_ERR_INVALID_ARG, "group id out of range"); }
+    CUDA_TRY(ctx, cudaMalloc(&d_gid, (size_t)n_series * 4));
+    CUDA_TRY(ctx, cudaMemcpy(d_gid, group_ids, (size_t)n_series * 4, cudaMemcpyHostToDevice));
+  }
+  int32_t rc = build_groups(ctx, t, d_gid, group_ids ? n_groups : 1);
+  cudaFree(d_gid);
+  if (rc) { filo_table_free(ctx, t); return rc; }
+  *out = t;
+  return FILO_OK;
+}
+
+extern "C" int32_t filo_table_set_groups(filo_ctx* ctx, filo_table* t, const int32_t* group_ids, int32_t n_groups) {
+  if (!ctx || !t) return fail(ctx, FILO_ERR_INVALID_ARG, "null");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (group_ids && ctx->cfg.group_by_cardinality_limit > 0 && n_groups > ctx->cfg.group_by_cardinality_limit)
+    return fail(ctx, FILO_ERR_QUERY_LIMIT, "Query exceeded group-by cardinality limit");
+  int32_t* d_gid = nullptr;
+  if (group_ids && t->n_series > 0) {
+    for (int64_t i = 0; i < t->n_series; ++i) if (group_ids[i] < 0 || group_ids[i] >= n_groups) return fail(ctx, FILO_ERR_INVALID_ARG, "group id out of range");
+    CUDA_TRY(ctx, cudaMalloc(&d_gid, (size_t)t->n_series * 4));
+    CUDA_TRY(ctx, cudaMemcpy(d_gid, group_ids, (size_t)t->n_series * 4, cudaMemcpyHostToDevice));
+  }
+  int32_t rc = build_groups(ctx, t, d_gid, group_ids ? n_groups : 1);
+  cudaFree(d_gid);
+  return rc;
+}
+
+extern "C" int64_t filo_table_read_record(filo_ctx* ctx, const filo_table* t, int64_t series, uint8_t* out, int64_t cap) {
+  if (!ctx || !t || series < 0 || series >= t->n_series) return fail(ctx, FILO_ERR_INVALID_ARG, "bad series");
+  cudaSetDevice(ctx->device);
+  int64_t off[2];
+  if (cudaMemcpy(off, t->d_rec_off + series, 16, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(ctx, FILO_ERR_CUDA, "read rec_off");
+  int64_t n = off[1] - off[0];
+  if (n > cap) return -n;
+  if (cudaMemcpy(out, t->d_arena + off[0], (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(ctx, FILO_ERR_CUDA, "read record");
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// query
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+struct Temp {   // stream-ordered temporaries, freed on scope exit
+  cudaStream_t s; std::vector<void*> ptrs;
+  explicit Temp(cudaStream_t st) : s(st) {}
+  ~Temp() { for (void* p : ptrs) cudaFreeAsync(p, s); }
+  cudaError_t alloc(void** p, size_t bytes) { cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, s); if (e == cudaSuccess) ptrs.push_back(*p); return e; }
+};
+}
+
+extern "C" int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t fn, int64_t start, int64_t step, int64_t end, int64_t window,
+                                     int32_t agg, int32_t k, int32_t flags, void* d_out_values, void* d_out_aux, void* cuda_stream,
+                                     filo_stats* stats) {
+  if (!ctx || !t || !d_out_values) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_query: null argument");
+  if (fn < FILO_FN_LAST || fn > FILO_FN_TIMESTAMP) return fail(ctx, FILO_ERR_INVALID_ARG, "unknown range function");
+  if (agg < FILO_AGG_NONE || agg > FILO_AGG_BOTTOMK) return fail(ctx, FILO_ERR_INVALID_ARG, "unknown aggregation operator");
+  // PeriodicSamplesMapper.scala:45-49, 67-68
+  if (start > end) return fail(ctx, FILO_ERR_INVALID_ARG, "start should be <= end");
+  if (!(start == end || step > 0)) return fail(ctx, FILO_ERR_INVALID_ARG, "step should be > 0 for range query");
+  if (start < end && step < ctx->cfg.min_step_ms) return fail(ctx, FILO_ERR_BAD_QUERY, "step should be at least min-step");
+  const int64_t adjustedStep = step > 0 ? step : step + 1;
+  const bool isLast = (fn == FILO_FN_LAST || fn == FILO_FN_TIMESTAMP);
+  if (window <= 0) { if (isLast) window = 5 * 60 * 1000 + 1; else return fail(ctx, FILO_ERR_INVALID_ARG, "Need positive window lengths to apply range function"); }
+  if ((agg == FILO_AGG_TOPK || agg == FILO_AGG_BOTTOMK) && (k <= 0 || k > FILO_MAX_TOPK)) return fail(ctx, FILO_ERR_INVALID_ARG, "topk/bottomk k must be in [1, 32]");
+  if ((agg == FILO_AGG_TOPK || agg == FILO_AGG_BOTTOMK || agg == FILO_AGG_AVG) && !d_out_aux && !(agg == FILO_AGG_AVG && !(flags & FILO_Q_PARTIAL)))
+    return fail(ctx, FILO_ERR_INVALID_ARG, "out_aux required");
+  if ((flags & FILO_Q_PARTIAL) && agg != FILO_AGG_NONE && agg != FILO_AGG_TOPK && agg != FILO_AGG_BOTTOMK && !d_out_aux)
+    return fail(ctx, FILO_ERR_INVALID_ARG, "partial aggregates need out_aux (counts)");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  QueryParams q{};
+  q.start = start; q.step = adjustedStep; q.end = end; q.window = window; q.T = filo_num_windows(start, adjustedStep, end);
+  q.fn = fn; q.cumulative = (t->schema_flags & FILO_SCHEMA_CUMULATIVE) ? 1 : 0; q.inclusive = ctx->cfg.inclusive_range ? 1 : 0;
+  const bool need_corr = (fn == FILO_FN_RATE || fn == FILO_FN_INCREASE) && q.cumulative;
+  const bool fused = (agg != FILO_AGG_NONE && agg != FILO_AGG_TOPK && agg != FILO_AGG_BOTTOMK);
+
+  Temp tmp(s);
+  int* d_err = nullptr; unsigned long long* d_counters = nullptr;
+  CUDA_TRY(ctx, tmp.alloc((void**)&d_err, 16)); CUDA_TRY(ctx, tmp.alloc((void**)&d_counters, 16));
+  CUDA_TRY(ctx, cudaMemsetAsync(d_err, 0, 16, s)); CUDA_TRY(ctx, cudaMemsetAsync(d_counters, 0, 16, s));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (stats) { CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1)); }
+
+  // per-warp scratch: chunk descriptors + decoded rows
+  uint32_t scratch = align_up((uint32_t)t->max_chunks * 112u, 16) + (uint32_t)t->max_rows * 8u * (need_corr ? 3u : 2u);
+  scratch = align_up(scratch + 16, 16);
+  const uint32_t acc_bytes = fused ? align_up((uint32_t)q.T * 12u, 16) : 0;
+  const size_t cta_smem = (size_t)(scratch + acc_bytes) * SCAN_WARPS;
+  const size_t smem_cap = std::min<size_t>(ctx->max_smem_optin, 200 * 1024);
+  const int use_smem = cta_smem <= smem_cap;
+  int ctas_per_sm = 16;    // 64 warps / SCAN_WARPS
+  if (use_smem) ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(220 * 1024) / std::max<size_t>(cta_smem + 1024, 1)));
+  const int64_t work = fused ? t->n_items : t->n_series;
+  int grid = (int)std::min<int64_t>((work + SCAN_WARPS - 1) / SCAN_WARPS, (int64_t)ctx->sm_count * ctas_per_sm);
+  if (grid < 1) grid = 1;
+  uint8_t* gscratch = nullptr;
+  if (!use_smem) CUDA_TRY(ctx, tmp.alloc((void**)&gscratch, (size_t)grid * SCAN_WARPS * (scratch + acc_bytes)));
+  ScanLaunch L{t->d_arena, t->d_rec_off, t->n_series, q, gscratch, scratch, use_smem, d_counters, d_err, grid, s};
+  int64_t launches = 0;
+  if (stats) CUDA_TRY(ctx, cudaEventRecord(e0, s));
+  if (agg == FILO_AGG_NONE) {
+    CUDA_TRY(ctx, launch_scan_series(L, (double*)d_out_values)); launches = 1;
+  } else if (!fused) {
+    double* per = nullptr;
+    CUDA_TRY(ctx, tmp.alloc((void**)&per, (size_t)t->n_series * q.T * 8));
+    CUDA_TRY(ctx, launch_scan_series(L, per));
+    CUDA_TRY(ctx, launch_topk(per, t->grouped ? t->d_order : nullptr, t->d_group_start, t->n_groups, q.T, k, agg == FILO_AGG_BOTTOMK,
+                              (double*)d_out_values, (int64_t*)d_out_aux, s));
+    launches = 2;
+  } else {
+    double* pval = nullptr; uint32_t* pcnt = nullptr;
+    CUDA_TRY(ctx, tmp.alloc((void**)&pval, (size_t)t->n_items * q.T * 8));
+    CUDA_TRY(ctx, tmp.alloc((void**)&pcnt, (size_t)t->n_items * q.T * 4));
+    CUDA_TRY(ctx, launch_scan_agg(L, t->grouped ? t->d_order : nullptr, t->d_item_begin, t->n_items, agg, pval, pcnt, acc_bytes));
+    CUDA_TRY(ctx, launch_merge_partials(pval, pcnt, t->d_gis, t->n_groups, q.T, agg, (flags & FILO_Q_PARTIAL) ? 1 : 0,
+                                        (double*)d_out_values, (int64_t*)d_out_aux, s));
+    launches = 2;
+  }
+  if (stats) {
+    CUDA_TRY(ctx, cudaEventRecord(e1, s));
+    int herr[4]; unsigned long long hc[2];
+    CUDA_TRY(ctx, cudaMemcpyAsync(herr, d_err, 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(hc, d_counters, 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    stats->kernel_ns = (int64_t)((double)ms * 1e6); stats->samples_scanned = (int64_t)hc[0]; stats->bytes_scanned = (int64_t)hc[1];
+    stats->kernel_launches = launches; stats->h2d_bytes = 0; stats->d2h_bytes = 0;
+    if (herr[0]) {
+      const char* what = herr[0] == 4 ? "series needs more decode scratch than the table statistics promised" : "CorruptVector on device";
+      return fail(ctx, FILO_ERR_CORRUPT_VECTOR, std::string(what) + " (code " + std::to_string(herr[0]) + ") at series " +
+                  std::to_string((int64_t)herr[1] | ((int64_t)herr[2] << 31)));
+    }
+  }
+  return FILO_OK;
+}
+
+extern "C" int32_t filo_query(filo_ctx* ctx, const filo_table* t, int32_t fn, int64_t start, int64_t step, int64_t end, int64_t window,
+                              int32_t agg, int32_t k, int32_t flags, double* out_values, int64_t* out_aux, filo_stats* stats) {
+  if (!ctx || !t || !out_values) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_query: null argument");
+  if (start > end) return fail(ctx, FILO_ERR_INVALID_ARG, "start should be <= end");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int64_t adjustedStep = step > 0 ? step : step + 1;
+  const int T = filo_num_windows(start, adjustedStep, end);
+  size_t nvals, naux = 0;
+  if (agg == FILO_AGG_NONE) nvals = (size_t)t->n_series * T;
+  else if (agg == FILO_AGG_TOPK || agg == FILO_AGG_BOTTOMK) { if (k <= 0 || k > FILO_MAX_TOPK) return fail(ctx, FILO_ERR_INVALID_ARG, "topk/bottomk k must be in [1, 32]"); nvals = naux = (size_t)t->n_groups * T * k; }
+  else { nvals = (size_t)t->n_groups * T; naux = nvals; }
+  cudaStream_t s = ctx->stream;
+  double* d_vals = nullptr; int64_t* d_aux = nullptr;
+  CUDA_TRY(ctx, cudaMallocAsync((void**)&d_vals, std::max<size_t>(nvals, 1) * 8, s));
+  if (naux) CUDA_TRY(ctx, cudaMallocAsync((void**)&d_aux, naux * 8, s));
+  filo_stats st{};
+  int32_t rc = filo_query_device(ctx, t, fn, start, step, end, window, agg, k, flags, d_vals, d_aux, s, &st);
+  if (rc == FILO_OK) {
+    cudaError_t e = cudaMemcpyAsync(out_values, d_vals, nvals * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && naux && out_aux) e = cudaMemcpyAsync(out_aux, d_aux, naux * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = fail(ctx, FILO_ERR_CUDA, std::string("result copy: ") + cudaGetErrorString(e));
+    st.d2h_bytes = (int64_t)(nvals * 8 + ((naux && out_aux) ? naux * 8 : 0));
+  }
+  cudaFreeAsync(d_vals, s); if (d_aux) cudaFreeAsync(d_aux, s);
+  if (stats) *stats = st;
+  return rc;
+}
+
+extern "C" int32_t filo_present_partials(filo_ctx* ctx, int32_t agg, int64_t n, void* d_values, void* d_counts, void* d_out, void* cuda_stream) {
+  if (!ctx || !d_values || !d_counts || !d_out || n < 0) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_present_partials: bad argument");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  if (n > 0) CUDA_TRY(ctx, launch_present(agg, n, (const double*)d_values, (const int64_t*)d_counts, (double*)d_out, s));
+  return FILO_OK;
+}

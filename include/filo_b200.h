@@ -1,0 +1,185 @@
+/*
+ * filo_b200.h — C-ABI of the B200-native chunk-scan + range-vector aggregation engine for FiloDB.
+ *
+ * This is the drop-in boundary: a JVM (FiloDB) process binds these symbols through the JNI shim
+ * (filodb_b200/csrc/jni_shim.cpp) exactly the way the reference binds its existing
+ * native seam on this path:
+ *     core/src/main/scala/filodb.memory/format/vectors/SimdNativeMethods.scala:68-86   (@native simdSumDouble/...)
+ *     core/src/rust/filodb_core/src/simd_vectors.rs:163-200                            (Java_..._simdSumDouble)
+ * Conventions mirrored from that seam (core/src/rust/filodb_core/src/exec.rs:15-61, errors.rs:36-47, lib.rs:5-17):
+ *   - primitives and raw addresses only (jlong addresses of off-heap BinaryVectors / ChunkSetInfos);
+ *   - no exception/abort ever crosses the boundary: every entry returns an int32 status (0 = OK, <0 = error) and
+ *     the message is fetched with filo_last_error(); the JNI shim turns non-zero into java.lang.RuntimeException;
+ *   - the callee COPIES chunk bytes during filo_load_series and never retains host pointers: the caller holds the
+ *     partition ChunkMap shared locks + shard eviction lock only for the duration of that call
+ *     (core/src/main/scala/filodb.memory/data/ChunkMap.scala:17-41, EvictionLock.scala:24-32).
+ *
+ * What the entry points replace (reference file:line):
+ *   filo_load_series  <- RawDataRangeVector.chunkInfos / WindowedChunkIterator chunk resolution
+ *                        core/src/main/scala/filodb.core/query/RangeVector.scala:365-399
+ *                        core/src/main/scala/filodb.core/store/ChunkSetInfo.scala:445-529 (ChunkSetInfo layout :133-154)
+ *   filo_query        <- PeriodicSamplesMapper.apply -> ChunkedWindowIteratorD.doNext -> ChunkedRangeFunction.addChunks/apply
+ *                        query/src/main/scala/filodb/query/exec/PeriodicSamplesMapper.scala:61-190, 256-347
+ *                        query/src/main/scala/filodb/query/exec/rangefn/RangeFunction.scala:84-242, 595-724
+ *                        query/src/main/scala/filodb/query/exec/rangefn/RateFunctions.scala:72-111, 230-322, 424-445
+ *                        query/src/main/scala/filodb/query/exec/rangefn/AggrOverTimeFunctions.scala:40-116, 553-572, 924-1015
+ *                        + AggregateMapReduce.apply / RangeVectorAggregator.mapReduce / RowAggregators
+ *                        query/src/main/scala/filodb/query/exec/AggrOverRangeVectors.scala:119-182, 214-378
+ *                        query/src/main/scala/filodb/query/exec/aggregator/{Sum,Min,Max,Count,Avg,TopBottomK}RowAggregator.scala
+ *   filo_synth_table  <- (bench/test only) TestTimeseriesProducer + the appenders' optimize()
+ *                        gateway/src/main/scala/filodb/timeseries/TestTimeseriesProducer.scala:147,196-198
+ *
+ * Output timestamps are implicit: window i ends at start_ms + i*step_ms (RvRange, PeriodicSamplesMapper.scala:48).
+ * There is NO CPU fallback: every query runs the sm_100a kernels; a missing/failed device is an error.
+ */
+#ifndef FILO_B200_H
+#define FILO_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct filo_ctx filo_ctx;
+typedef struct filo_table filo_table;
+
+/* status codes */
+enum {
+  FILO_OK = 0,
+  FILO_ERR_INVALID_ARG = -1,
+  FILO_ERR_CUDA = -2,
+  FILO_ERR_CORRUPT_VECTOR = -3,     /* CorruptVectorException, ChunkSetInfo.scala:424-429 */
+  FILO_ERR_UNSUPPORTED = -4,        /* encoding/ordering the device path does not handle; caller keeps the JVM path */
+  FILO_ERR_QUERY_LIMIT = -5,        /* QueryLimitException: scanned-bytes / group-by cardinality limits */
+  FILO_ERR_BAD_QUERY = -6,          /* BadQueryException: step below min-step */
+  FILO_ERR_OOM = -7
+};
+
+/* InternalRangeFunction subset on this path (query/.../exec/InternalRangeFunction.scala:11-70) */
+enum {
+  FILO_FN_LAST = 0,                 /* None / Last                 -> LastSampleChunkedFunctionD */
+  FILO_FN_RATE = 1,                 /* Rate      (CumlDeltaToggler: counter -> ChunkedRateFunction, else RateOverDelta) */
+  FILO_FN_INCREASE = 2,             /* Increase  (counter -> ChunkedIncreaseFunction, else SumOverTime) */
+  FILO_FN_DELTA = 3,                /* ChunkedDeltaFunction */
+  FILO_FN_SUM_OVER_TIME = 4,
+  FILO_FN_AVG_OVER_TIME = 5,
+  FILO_FN_COUNT_OVER_TIME = 6,
+  FILO_FN_MIN_OVER_TIME = 7,
+  FILO_FN_MAX_OVER_TIME = 8,
+  FILO_FN_TIMESTAMP = 9
+};
+
+/* AggregationOperator subset (query/src/main/scala/filodb/query/PlanEnums.scala:99-114) */
+enum {
+  FILO_AGG_NONE = 0, FILO_AGG_SUM = 1, FILO_AGG_AVG = 2, FILO_AGG_MIN = 3, FILO_AGG_MAX = 4,
+  FILO_AGG_COUNT = 5, FILO_AGG_TOPK = 6, FILO_AGG_BOTTOMK = 7
+};
+
+/* schema_flags of filo_load_series */
+enum {
+  FILO_SCHEMA_CUMULATIVE = 1        /* schema.hasCumulativeTemporalityColumn (detectDrops column), Schemas.scala:190-193 */
+};
+
+/* query flags */
+enum {
+  FILO_Q_PARTIAL = 1                /* aggregates are returned in mergeable form for the cross-GPU reduce (see filo_query_device) */
+};
+
+typedef struct {
+  int32_t inclusive_range;            /* filodb.query.inclusive-range (filodb-defaults.conf:590), default 1 */
+  int32_t group_by_cardinality_limit; /* enforcedLimits.groupByCardinality, 0 = unlimited (AggrOverRangeVectors.scala:237-246) */
+  int64_t min_step_ms;                /* filodb.query.min-step (filodb-defaults.conf:626), 0 = not enforced */
+  int64_t max_data_per_shard_query;   /* bytes, 0 = unlimited (ChunkSetInfo.scala:361-368) */
+} filo_cfg;
+
+typedef struct {
+  int64_t bytes_scanned;              /* Σ totalBytes(ts)+totalBytes(value) of chunks scanned (dataBytesScannedCtr) */
+  int64_t samples_scanned;            /* Σ numRows of chunks scanned (samplesScannedCtr, ChunkSetInfo.scala:360) */
+  int64_t kernel_ns;                  /* device time of the kernels of this call (CUDA events) */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  int64_t kernel_launches;
+} filo_stats;
+
+typedef struct {
+  int64_t n_series;
+  int64_t n_chunks;
+  int64_t n_samples;                  /* Σ numRows */
+  int64_t arena_bytes;                /* device bytes of the chunk arena (records + index) */
+  int64_t algorithmic_bytes;          /* Σ chunks (28 + 8*ncols + totalBytes(ts) + totalBytes(value)), SURVEY §8(d) */
+  int32_t max_rows_per_series;
+  int32_t max_chunks_per_series;
+  int32_t n_groups;
+  int32_t schema_flags;
+} filo_table_info;
+
+/* Synthetic table spec (bench + tests): the reference's own generator shapes, encoded on the GPU.
+ * value_kind: 0 gauge  15 + sin(n+1) + N(0,1)            (TestTimeseriesProducer.scala:147)
+ *             1 counter v += max(0, 15 + sin + N(0,1))    (TestTimeseriesProducer.scala:196-198), resets ~1/reset_period rows
+ *             2 integral counter (values rounded -> DeltaDeltaVector-as-long encoding, DoubleVector.scala:86-96)
+ * value_enc:  0 raw f64 (DoubleVector.optimize for non-integral data), 1 XOR-NibblePack container, 2 DoubleVector.optimize (DDV if integral)
+ * ts_jitter_ms: 0 -> regular scrapes (const DDV, 24 bytes); >250 -> DeltaDeltaVector with residuals */
+typedef struct {
+  int64_t n_series;
+  int32_t rows_per_series;
+  int32_t rows_per_chunk;             /* max-chunks-size (400) */
+  int64_t t0_ms;
+  int32_t interval_ms;
+  int32_t ts_jitter_ms;
+  int32_t value_kind;
+  int32_t value_enc;
+  int32_t reset_period;               /* counters: expected rows between resets (0 = never) */
+  int32_t nan_per_million;            /* stale markers: probability (ppm) that a chunk's last row is NaN */
+  int32_t n_groups;                   /* group id = hash(series) % n_groups (0 -> no grouping) */
+  int32_t schema_flags;
+  uint64_t seed;
+  int64_t series_id_base;             /* global id of series 0 of this table (multi-GPU shards generate disjoint ids) */
+  const double* sin_table;            /* host pointer, rows_per_series doubles: sin(n+1) as computed by the caller */
+} filo_synth_spec;
+
+int32_t filo_ctx_create(int32_t device_ordinal, const filo_cfg* cfg /* NULL = defaults */, filo_ctx** out);
+void    filo_ctx_destroy(filo_ctx* ctx);
+/* Copies the last error message of this ctx (thread-local when ctx is NULL) into buf; returns its length. */
+int32_t filo_last_error(filo_ctx* ctx, char* buf, int32_t len);
+
+/* Ingest a set of time series into a device chunk arena.
+ *  n_chunks[i]        chunks of series i, in increasing chunkID order (what partition.infos yields)
+ *  chunk_info_addrs   Σ n_chunks native addresses of ChunkSetInfo blocks (ChunkSetInfo.scala:133-154); vector pointers
+ *                     inside them are dereferenced for columns ts_col / val_col
+ *  group_ids          per-series group ordinal in [0, n_groups) for a later across-series aggregate, or NULL */
+int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32_t* n_chunks, const uint64_t* chunk_info_addrs,
+                         int32_t ts_col, int32_t val_col, const int32_t* group_ids, int32_t n_groups,
+                         int32_t schema_flags, filo_table** out);
+int32_t filo_synth_table(filo_ctx* ctx, const filo_synth_spec* spec, filo_table** out);
+int32_t filo_table_set_groups(filo_ctx* ctx, filo_table* t, const int32_t* group_ids, int32_t n_groups);
+int32_t filo_table_get_info(const filo_table* t, filo_table_info* out);
+/* Copies the device arena record of one series back to the host (tests: byte parity of the GPU encoder). */
+int64_t filo_table_read_record(filo_ctx* ctx, const filo_table* t, int64_t series, uint8_t* out, int64_t cap);
+void    filo_table_free(filo_ctx* ctx, filo_table* t);
+
+/* Number of output windows: first window always, then while window_end + step <= end (ChunkSetInfo.scala:462). */
+int32_t filo_num_windows(int64_t start_ms, int64_t step_ms, int64_t end_ms);
+
+/* PeriodicSamplesMapper (+ AggregateMapReduce when aggr_op != NONE) over a loaded table; results to HOST buffers.
+ *  out_values: aggr NONE -> [n_series * T]; SUM/AVG/MIN/MAX/COUNT -> [n_groups * T]; TOPK/BOTTOMK -> [n_groups * T * k]
+ *  out_aux:    AVG -> counts [n_groups*T]; TOPK/BOTTOMK -> series ordinals [n_groups*T*k] (-1 = empty); else may be NULL */
+int32_t filo_query(filo_ctx* ctx, const filo_table* t, int32_t range_fn,
+                   int64_t start_ms, int64_t step_ms, int64_t end_ms, int64_t window_ms,
+                   int32_t aggr_op, int32_t k, int32_t flags,
+                   double* out_values, int64_t* out_aux, filo_stats* stats);
+/* Same, results left in DEVICE buffers (d_out_values / d_out_aux are device pointers), enqueued on cuda_stream
+ * (a cudaStream_t, may be NULL = ctx stream); does not synchronize unless stats != NULL.
+ * With FILO_Q_PARTIAL: SUM/AVG/COUNT -> values = Σ of non-NaN inputs (0 when none), aux = contributing count;
+ * MIN/MAX -> values = min/max with +Inf/-Inf identity, aux = count.  Merge across GPUs with ncclSum / ncclMin /
+ * ncclMax on values and ncclSum on aux, then call filo_present_partials. */
+int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t range_fn,
+                          int64_t start_ms, int64_t step_ms, int64_t end_ms, int64_t window_ms,
+                          int32_t aggr_op, int32_t k, int32_t flags,
+                          void* d_out_values, void* d_out_aux, void* cuda_stream, filo_stats* stats);
+/* RowAggregator "present" after a cross-GPU merge: n = n_groups*T cells; writes NaN where count == 0, Σ/n for AVG. */
+int32_t filo_present_partials(filo_ctx* ctx, int32_t aggr_op, int64_t n, void* d_values, void* d_counts,
+                              void* d_out_values, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FILO_B200_H */

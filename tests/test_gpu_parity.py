@@ -1,0 +1,347 @@
+"""GPU parity: the CUDA path (through the C-ABI) vs the CPU oracle on the same chunk bytes.
+
+Per-series results (PeriodicSamplesMapper) must be BIT-EXACT: the kernels follow the reference's operation order and are
+compiled without FMA contraction.  Across-series aggregates: min/max/count bit-exact; sum/avg within 1e-9 relative (the
+reference folds in arrival order, the device folds per work item then per group — SURVEY.md §7 "FP parity")."""
+import math
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+NaN = float("nan")
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import filodb_b200.capi as capi
+    ctx = capi.Context(0)
+    yield capi, ctx
+    ctx.close()
+
+
+def same_bits(a, b):
+    a = np.ascontiguousarray(a, np.float64); b = np.ascontiguousarray(b, np.float64)
+    an, bn = np.isnan(a), np.isnan(b)
+    return a.shape == b.shape and (an == bn).all() and (a[~an].view(np.uint64) == b[~bn].view(np.uint64)).all()
+
+
+def assert_same(a, b, what=""):
+    if not same_bits(a, b):
+        a = np.asarray(a); b = np.asarray(b)
+        bad = np.argwhere(~((a == b) | (np.isnan(a) & np.isnan(b))))
+        i = tuple(bad[0])
+        raise AssertionError("%s: %d mismatches, first at %s: gpu=%r oracle=%r" % (what, len(bad), i, a[i], b[i]))
+
+
+ALL_FNS = ["FN_LAST", "FN_RATE", "FN_INCREASE", "FN_DELTA", "FN_SUM_OVER_TIME", "FN_AVG_OVER_TIME", "FN_COUNT_OVER_TIME",
+           "FN_MIN_OVER_TIME", "FN_MAX_OVER_TIME", "FN_TIMESTAMP"]
+
+
+def build_store(o, rng, n_series, kind, val_mode, jitter, detect_drops, nan_frac=0.0, rows=480, chunks=(400, 80), t0=1_700_000_000_000, interval=15000):
+    st = o.Store()
+    for s in range(n_series):
+        ts = t0 + np.arange(rows, dtype=np.int64) * interval
+        if jitter:
+            ts = ts + rng.integers(-jitter, jitter + 1, rows)
+        if kind == "gauge":
+            v = 15 + np.sin(np.arange(1, rows + 1)) + rng.normal(0, 1, rows)
+        elif kind == "counter":
+            v = np.cumsum(np.maximum(0, 15 + np.sin(np.arange(1, rows + 1)) + rng.normal(0, 1, rows)))
+            for r in np.nonzero(rng.random(rows) < 0.01)[0]:
+                if r > 0: v[r:] = v[r:] - v[r] + rng.random() * 5
+        elif kind == "intcounter":
+            v = np.cumsum(rng.integers(0, 40, rows)).astype(float)
+            for r in np.nonzero(rng.random(rows) < 0.01)[0]:
+                if r > 0: v[r:] = v[r:] - v[r] + float(rng.integers(0, 5))
+        elif kind == "linear":
+            v = np.arange(1, rows + 1, dtype=float) * (s + 1)
+        else:
+            raise ValueError(kind)
+        if nan_frac:
+            v = v.copy(); v[rng.random(rows) < nan_frac] = NaN
+        st.add_series_rows(ts, v, list(chunks), val_mode=val_mode, detect_drops=detect_drops)
+    return st
+
+
+CASES = [
+    # kind, val_mode, jitter, cumulative/detectDrops, nan_frac
+    ("gauge", 2, 0, False, 0.0),
+    ("gauge", 1, 0, False, 0.02),
+    ("gauge", 0, 3000, False, 0.02),
+    ("counter", 2, 0, True, 0.01),
+    ("counter", 1, 2000, True, 0.01),
+    ("intcounter", 0, 0, True, 0.0),
+    ("intcounter", 0, 100, True, 0.0),
+    ("linear", 0, 0, False, 0.0),
+    ("gauge", 1, 0, True, 0.05),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[("%s-v%d-j%d-%s-nan%g" % c) for c in CASES])
+def test_per_series_bit_exact(gpu, oracle, case):
+    capi, ctx = gpu; o = oracle
+    kind, val_mode, jitter, cumulative, nan_frac = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    st = build_store(o, rng, 40, kind, val_mode, jitter, cumulative, nan_frac)
+    nch, addrs = st.all_info_addrs()
+    tab = ctx.load_series(nch, addrs, schema_flags=capi.SCHEMA_CUMULATIVE if cumulative else 0)
+    ti = tab.info()
+    assert ti.n_series == 40 and ti.n_samples == 40 * 480
+    assert ti.algorithmic_bytes == st.algorithmic_bytes()
+    t0 = 1_700_000_000_000
+    queries = [(t0 + 300000, 15000, t0 + 479 * 15000, 300000),      # BASELINE shape: [5m] step 15s
+               (t0 + 60000, 15000, t0 + 479 * 15000 + 90000, 60000),  # [1m], runs past the data
+               (t0 - 100000, 47000, t0 + 480 * 15000, 333333),        # unaligned step/window
+               (t0 + 5999000, 1, t0 + 5999000, 300000)]               # instant query
+    for (start, step, end, window) in queries:
+        for name in ALL_FNS:
+            fn = getattr(capi, name)
+            got = ctx.query(tab, fn, start, step, end, window)
+            exp = st.query(getattr(o, name), start, step, end, window, cumulative=cumulative)
+            assert_same(got, exp, "%s %s q=%s" % (case, name, (start, step, end, window)))
+            assert ctx.last_stats["samples_scanned"] == st.last_stats["samples_scanned"]
+            assert ctx.last_stats["bytes_scanned"] == st.last_stats["bytes_scanned"]
+    tab.free()
+
+
+def test_golden_known_answers_on_gpu(gpu, oracle):
+    """The reference's own known-answer tests, through the CUDA path (WindowIteratorSpec.scala:219-284, RateFunctionsSpec.scala:58-158)."""
+    capi, ctx = gpu; o = oracle
+    from tests.test_oracle_golden import PROM_SAMPLES, PROM_EXPECTED, OT_SAMPLES, COUNTER_SAMPLES, _store_one
+    st = _store_one(o, PROM_SAMPLES)
+    tab = ctx.load_series(*st.all_info_addrs(), schema_flags=capi.SCHEMA_CUMULATIVE)
+    start, step, end, window = 1548191496000, 15000, 1548191796000, 300000
+    out = ctx.query(tab, capi.FN_RATE, start, step, end, window)[0]
+    for k, v in enumerate(out):
+        if start + k * step in PROM_EXPECTED:
+            assert v == pytest.approx(PROM_EXPECTED[start + k * step], abs=1e-10)
+    samples = [(1614821996000, NaN), (1614821996100, 489.0), (1614821997000, NaN), (1614822566000, 19.0),
+               (1614822596000, 26.0), (1614822626000, 26.0), (1614822656000, 26.0), (1614822686000, 26.0),
+               (1614822716000, 26.0), (1614822717000, NaN), (1614822866000, 5.0)]
+    st = _store_one(o, samples)
+    tab = ctx.load_series(*st.all_info_addrs(), schema_flags=capi.SCHEMA_CUMULATIVE)
+    assert ctx.query(tab, capi.FN_RATE, 1614822880000, 15000, 1614822880000, 900000)[0, 0] == 0.5870753512132821
+    st = _store_one(o, OT_SAMPLES, detect_drops=False)
+    tab = ctx.load_series(*st.all_info_addrs())
+    out = ctx.query(tab, capi.FN_SUM_OVER_TIME, 50000, 100000, 1100000, 100000)[0]
+    assert [(50000 + 100000 * k, v) for k, v in enumerate(out) if not math.isnan(v)] == \
+        [(150000, 1.0), (250000, 5.0), (350000, 12.0), (450000, 13.0), (750000, 17.0)]
+    # drops in the middle of chunks, 1 and 2 chunks (RateFunctionsSpec.scala:117-158)
+    reset1 = [(8072000, 4419.0), (8082100, 4511.0), (8092196, 4614.0), (8102215, 4724.0), (8112223, 4909.0),
+              (8122388, 948.0), (8132570, 1000.0), (8142822, 1095.0), (8152858, 1102.0), (8162999, 1201.0)]
+    reset2 = [(8173000, 1325.0), (8183000, 1511.0), (8193000, 214.0), (8203000, 324.0), (8213000, 409.0)]
+    expected = (409.0 + 4909.0 + 1511.0 - 4419.0) / (8213000 - 8072000) * 1000
+    for rows in ([10, 5], [15]):
+        st = _store_one(o, reset1 + reset2, chunk_rows=rows)
+        tab = ctx.load_series(*st.all_info_addrs(), schema_flags=capi.SCHEMA_CUMULATIVE)
+        assert ctx.query(tab, capi.FN_RATE, 8213070, 10000, 8213070, 8213070 - 8071950)[0, 0] == pytest.approx(expected, abs=1e-7)
+
+
+def test_edge_cases(gpu, oracle):
+    capi, ctx = gpu; o = oracle
+    rng = np.random.default_rng(77)
+    st = o.Store()
+    t0 = 1_700_000_000_000
+    # ragged: 1-row chunks, single-NaN chunk, 2-row chunk (raw long timestamps), many small chunks, a gap between chunks
+    st.add_series_rows([t0], [5.0], [1], val_mode=2, detect_drops=True)
+    st.add_series_rows([t0, t0 + 15000, t0 + 30000], [1.0, 2.0, NaN], [2, 1], val_mode=2, detect_drops=True)
+    ts = t0 + np.arange(100) * 15000
+    st.add_series_rows(ts, rng.random(100), [7] * 14 + [2], val_mode=1)
+    ts2 = np.concatenate([t0 + np.arange(50) * 15000, t0 + 3_000_000 + np.arange(50) * 15000])
+    st.add_series_rows(ts2, np.cumsum(rng.random(100)), [50, 50], val_mode=2, detect_drops=True)
+    st.add_series_rows(ts, np.full(100, NaN), [60, 40], val_mode=2)          # all NaN
+    st.add_series_rows(ts, np.zeros(100), [60, 40], val_mode=0)              # constant 0 -> const DDV values
+    st.add_series_rows(ts, -np.arange(100.0), [60, 40], val_mode=0, detect_drops=True)   # decreasing integral counter
+    st.add_series_rows(ts, np.where(np.arange(100) % 2 == 0, -0.0, 0.0), [100], val_mode=2)
+    for cumulative in (False, True):
+        tab = ctx.load_series(*st.all_info_addrs(), schema_flags=capi.SCHEMA_CUMULATIVE if cumulative else 0)
+        for (start, step, end, window) in [(t0, 15000, t0 + 100 * 15000, 60000), (t0 - 10**6, 7000, t0 + 4 * 10**6, 123456),
+                                           (t0 + 10**7, 15000, t0 + 10**7 + 60000, 30000)]:
+            for name in ALL_FNS:
+                got = ctx.query(tab, getattr(capi, name), start, step, end, window)
+                exp = st.query(getattr(o, name), start, step, end, window, cumulative=cumulative)
+                assert_same(got, exp, "%s cumulative=%s q=%s" % (name, cumulative, (start, step, end, window)))
+        tab.free()
+    # empty table
+    tab = ctx.load_series(np.zeros(0, np.int32), np.zeros(0, np.uint64))
+    assert ctx.query(tab, capi.FN_SUM_OVER_TIME, t0, 15000, t0 + 60000, 30000).shape == (0, 5)
+    # non-inclusive range config (filodb.query.inclusive-range = false)
+    ctx2 = capi.Context(0, inclusive_range=False)
+    tab = ctx2.load_series(*st.all_info_addrs())
+    for name in ("FN_SUM_OVER_TIME", "FN_RATE", "FN_LAST"):
+        got = ctx2.query(tab, getattr(capi, name), t0, 15000, t0 + 100 * 15000, 60000)
+        exp = st.query(getattr(o, name), t0, 15000, t0 + 100 * 15000, 60000, inclusive=False)
+        assert_same(got, exp, name + " non-inclusive")
+    ctx2.close()
+
+
+def test_many_chunks_and_long_series(gpu, oracle):
+    """Series far larger than the shared-memory scratch (global-scratch path) and > 8 chunks (binary chunk search)."""
+    capi, ctx = gpu; o = oracle
+    rng = np.random.default_rng(5)
+    rows = 6000
+    t0 = 1_700_000_000_000
+    st = o.Store()
+    for s in range(6):
+        ts = t0 + np.arange(rows, dtype=np.int64) * 10000 + (rng.integers(-2000, 2001, rows) if s % 2 else 0)
+        v = np.cumsum(rng.random(rows) * 10)
+        st.add_series_rows(ts, v, [400] * 15, val_mode=s % 3, detect_drops=True)
+    tab = ctx.load_series(*st.all_info_addrs(), schema_flags=capi.SCHEMA_CUMULATIVE)
+    for (start, step, end, window) in [(t0 + 600000, 60000, t0 + rows * 10000, 600000), (t0, 3600000, t0 + rows * 10000, 7200000)]:
+        for name in ("FN_RATE", "FN_SUM_OVER_TIME", "FN_MAX_OVER_TIME", "FN_LAST", "FN_COUNT_OVER_TIME"):
+            got = ctx.query(tab, getattr(capi, name), start, step, end, window)
+            exp = st.query(getattr(o, name), start, step, end, window, cumulative=True)
+            assert_same(got, exp, name)
+
+
+def test_aggregates(gpu, oracle):
+    capi, ctx = gpu; o = oracle
+    rng = np.random.default_rng(123)
+    S, G = 300, 7
+    st = build_store(o, rng, S, "counter", 1, 0, True, 0.01)
+    groups = rng.integers(0, G, S).astype(np.int32)
+    groups[groups == 3] = 2      # leave group 3 empty
+    nch, addrs = st.all_info_addrs()
+    tab = ctx.load_series(nch, addrs, group_ids=groups, n_groups=G, schema_flags=capi.SCHEMA_CUMULATIVE)
+    t0 = 1_700_000_000_000
+    start, step, end, window = t0 + 60000, 15000, t0 + 479 * 15000, 60000
+    for fn_name in ("FN_INCREASE", "FN_RATE", "FN_COUNT_OVER_TIME"):
+        fn = getattr(capi, fn_name); ofn = getattr(o, fn_name)
+        for aggr_name in ("AGG_SUM", "AGG_MIN", "AGG_MAX", "AGG_COUNT", "AGG_AVG"):
+            aggr = getattr(capi, aggr_name)
+            got = ctx.query(tab, fn, start, step, end, window, aggr=aggr)
+            exp = st.query(ofn, start, step, end, window, cumulative=True, aggr=getattr(o, aggr_name), group_ids=groups, n_groups=G)
+            if aggr_name == "AGG_AVG":
+                (gv, gc), (ev, ec) = got, exp
+                assert (gc == ec).all()
+                assert np.isnan(gv[3]).all()
+                np.testing.assert_allclose(gv, ev, rtol=1e-9, atol=0, equal_nan=True)
+            elif aggr_name == "AGG_SUM":
+                np.testing.assert_allclose(got, exp, rtol=1e-9, atol=0, equal_nan=True)
+            else:
+                assert_same(got, exp, fn_name + " " + aggr_name)
+    # no grouping: one group
+    tab.set_groups(None, 1)
+    got = ctx.query(tab, capi.FN_RATE, start, step, end, window, aggr=capi.AGG_SUM)
+    exp = st.query(o.FN_RATE, start, step, end, window, cumulative=True, aggr=o.AGG_SUM, n_groups=1)
+    np.testing.assert_allclose(got, exp, rtol=1e-9, equal_nan=True)
+    # partial (mergeable) form + present
+    tab.set_groups(groups, G)
+    pv, pc = ctx.query(tab, capi.FN_RATE, start, step, end, window, aggr=capi.AGG_AVG, flags=capi.Q_PARTIAL)
+    ev, ec = st.query(o.FN_RATE, start, step, end, window, cumulative=True, aggr=o.AGG_AVG, group_ids=groups, n_groups=G)
+    assert (pc == ec).all()
+    with np.errstate(invalid="ignore", divide="ignore"):
+        np.testing.assert_allclose(np.where(pc > 0, pv / pc, np.nan), ev, rtol=1e-9, equal_nan=True)
+    # topk / bottomk
+    for aggr_name, rev in (("AGG_TOPK", True), ("AGG_BOTTOMK", False)):
+        gv, gi = ctx.query(tab, capi.FN_RATE, start, step, end, window, aggr=getattr(capi, aggr_name), k=3)
+        ev, ei = st.query(o.FN_RATE, start, step, end, window, cumulative=True, aggr=getattr(o, aggr_name), k=3, group_ids=groups, n_groups=G)
+        assert_same(gv, ev, aggr_name + " values")
+        per = st.query(o.FN_RATE, start, step, end, window, cumulative=True)
+        ok = gi >= 0
+        assert (ok == (ei >= 0)).all()
+        gs, ts_ = np.nonzero(ok.any(axis=2))
+        for g, t in zip(gs, ts_):
+            for j in range(3):
+                if gi[g, t, j] >= 0:
+                    assert groups[gi[g, t, j]] == g and same_bits(per[gi[g, t, j], t], gv[g, t, j])
+    tab.free()
+
+
+def test_error_paths(gpu, oracle):
+    capi, ctx = gpu; o = oracle
+    t0 = 1_700_000_000_000
+    st = o.Store()
+    ts = t0 + np.arange(10) * 15000
+    st.add_series_rows(ts, np.arange(10.0) + 0.5, [10], val_mode=2)
+    # corrupt wire format -> CorruptVectorException equivalent (ChunkSetInfo.scala:424-429)
+    bad = st.vector_bytes(0, 0, 1).copy(); bad[4] = 0x07
+    s2 = o.Store(); s2.add_series(); s2.add_chunk_raw(0, int(ts[0]), int(ts[-1]), 10, st.vector_bytes(0, 0, 0), bad)
+    with pytest.raises(capi.FiloError) as e:
+        ctx.load_series(*s2.all_info_addrs())
+    assert e.value.code == capi.ERR_CORRUPT_VECTOR
+    # numRows larger than the vectors
+    s3 = o.Store(); s3.add_series(); s3.add_chunk_raw(0, int(ts[0]), int(ts[-1]), 11, st.vector_bytes(0, 0, 0), st.vector_bytes(0, 0, 1))
+    with pytest.raises(capi.FiloError) as e:
+        ctx.load_series(*s3.all_info_addrs())
+    assert e.value.code == capi.ERR_CORRUPT_VECTOR
+    # chunks out of time order -> unsupported (caller keeps the JVM path)
+    s4 = o.Store(); s4.add_series()
+    s4.add_chunk(0, ts + 10**6, np.arange(10.0)); s4.add_chunk(0, ts, np.arange(10.0))
+    with pytest.raises(capi.FiloError) as e:
+        ctx.load_series(*s4.all_info_addrs())
+    assert e.value.code == capi.ERR_UNSUPPORTED
+    tab = ctx.load_series(*st.all_info_addrs())
+    for args, code in (((capi.FN_SUM_OVER_TIME, t0 + 100, 15000, t0, 1000), capi.ERR_INVALID_ARG),       # start > end
+                       ((capi.FN_SUM_OVER_TIME, t0, 0, t0 + 1000, 1000), capi.ERR_INVALID_ARG),            # step 0 on a range
+                       ((capi.FN_SUM_OVER_TIME, t0, 15000, t0 + 1000, 0), capi.ERR_INVALID_ARG),           # window 0
+                       ((99, t0, 15000, t0 + 1000, 1000), capi.ERR_INVALID_ARG)):
+        with pytest.raises(capi.FiloError) as e:
+            ctx.query(tab, *args)
+        assert e.value.code == code
+    ctx3 = capi.Context(0, min_step_ms=5000, group_by_cardinality_limit=2, max_data_per_shard_query=10)
+    with pytest.raises(capi.FiloError) as e:
+        ctx3.load_series(*st.all_info_addrs())
+    assert e.value.code == capi.ERR_QUERY_LIMIT
+    ctx3.close()
+    ctx4 = capi.Context(0, min_step_ms=5000, group_by_cardinality_limit=2)
+    tab4 = ctx4.load_series(*st.all_info_addrs())
+    with pytest.raises(capi.FiloError) as e:
+        ctx4.query(tab4, capi.FN_SUM_OVER_TIME, t0, 1000, t0 + 60000, 30000)
+    assert e.value.code == capi.ERR_BAD_QUERY
+    with pytest.raises(capi.FiloError) as e:
+        tab4.set_groups(np.zeros(1, np.int32), 3)
+    assert e.value.code == capi.ERR_QUERY_LIMIT
+    ctx4.close()
+
+
+SYNTH_CASES = [
+    dict(value_kind=0, value_enc=0, ts_jitter_ms=0),
+    dict(value_kind=0, value_enc=1, ts_jitter_ms=0, nan_per_million=200000),
+    dict(value_kind=1, value_enc=1, ts_jitter_ms=2000, reset_period=100, schema_flags=1, nan_per_million=100000),
+    dict(value_kind=2, value_enc=2, ts_jitter_ms=100, reset_period=150, schema_flags=1),
+    dict(value_kind=1, value_enc=0, ts_jitter_ms=0, reset_period=50, schema_flags=1),
+    dict(value_kind=2, value_enc=2, ts_jitter_ms=0, schema_flags=1, nan_per_million=300000),
+]
+
+
+@pytest.mark.parametrize("case", SYNTH_CASES, ids=[str(i) for i in range(len(SYNTH_CASES))])
+def test_gpu_encoder_matches_reference_appenders(gpu, oracle, case):
+    """The GPU generator/encoder writes exactly the bytes FiloDB's appenders' optimize() would (oracle restatement)."""
+    capi, ctx = gpu; o = oracle
+    from tests import synth_ref as sr
+    rows, rpc, S, seed, base = 173, 64, 24, 99, 1000
+    t0, interval = 1_700_000_000_000, 15000
+    tab = ctx.synth_table(S, rows, rows_per_chunk=rpc, t0_ms=t0, interval_ms=interval, seed=seed, series_id_base=base, n_groups=5, **case)
+    st_tab = capi.sin_table(rows)
+    cumulative = bool(case.get("schema_flags", 0) & 1)
+    val_mode = {0: o.VAL_RAW, 1: o.VAL_XOR, 2: o.VAL_OPTIMIZE}[case["value_enc"]]
+    st = o.Store()
+    for s in range(S):
+        ts, vals = sr.gen_series(seed, base + s, rows, rpc, t0, interval, case.get("ts_jitter_ms", 0), case["value_kind"],
+                                 case.get("reset_period", 0), case.get("nan_per_million", 0), st_tab)
+        st.add_series_rows(ts, vals, sr.chunk_rows(rows, rpc), val_mode=val_mode, detect_drops=cumulative)
+    alg = 0
+    for s in range(S):
+        rec = tab.read_record(s)
+        hdr = np.frombuffer(rec[:16].tobytes(), np.uint32)
+        assert hdr[0] == rec.size and hdr[1] == len(sr.chunk_rows(rows, rpc)) and hdr[2] == rows
+        for c in range(int(hdr[1])):
+            e = rec[16 + 32 * c: 48 + 32 * c].tobytes()
+            start_t, end_t = np.frombuffer(e[:16], np.int64)
+            nrows, ts_off, val_off, row_base = np.frombuffer(e[16:], np.uint32)
+            tsb, vb = st.vector_bytes(s, c, 0), st.vector_bytes(s, c, 1)
+            assert rec[ts_off:ts_off + tsb.size].tobytes() == tsb.tobytes(), "ts vector bytes series %d chunk %d" % (s, c)
+            assert rec[val_off:val_off + vb.size].tobytes() == vb.tobytes(), "value vector bytes series %d chunk %d" % (s, c)
+            alg += 28 + 16 + tsb.size + vb.size
+    assert tab.info().algorithmic_bytes == alg == st.algorithmic_bytes()
+    # and queries over the synthetic table agree with the oracle over the re-built chunks
+    start, step, end, window = t0 + 60000, 15000, t0 + rows * interval, 120000
+    for name in ("FN_RATE", "FN_SUM_OVER_TIME", "FN_LAST"):
+        got = ctx.query(tab, getattr(capi, name), start, step, end, window)
+        exp = st.query(getattr(o, name), start, step, end, window, cumulative=cumulative)
+        assert_same(got, exp, name)
+    groups = np.array([sr.group_id(seed, base + s, 5) for s in range(S)], np.int32)
+    got = ctx.query(tab, capi.FN_SUM_OVER_TIME, start, step, end, window, aggr=capi.AGG_MAX)
+    exp = st.query(o.FN_SUM_OVER_TIME, start, step, end, window, cumulative=cumulative, aggr=o.AGG_MAX, group_ids=groups, n_groups=5)
+    assert_same(got, exp, "group max over synthetic table")
