@@ -69,6 +69,7 @@ def _sig(L):
         ("fo_store_add_chunk", i32, [vp, i64, vp, vp, i32, i32, i32, i32]),
         ("fo_store_add_chunk_raw", i32, [vp, i64, i64, i64, i32, vp, i32, vp, i32]),
         ("fo_store_add_series_rows", i32, [vp, vp, vp, i64, vp, i32, i32, i32, i32]),
+        ("fo_store_add_from_arena", i64, [vp, vp, vp, i64]),
         ("fo_store_num_chunks", i32, [vp, i64]), ("fo_store_info_addrs", None, [vp, i64, vp]),
         ("fo_store_vector_bytes", i64, [vp, i64, i32, i32, vp, i64]),
         ("fo_store_algorithmic_bytes", i64, [vp]),
@@ -266,6 +267,11 @@ class Store:
         if lib().fo_store_add_series_rows(self.h, _p(ts), _p(vals), ts.size, _p(cr), cr.size, val_mode, int(detect_drops), ts_mode) != 0:
             raise RuntimeError(last_error())
         return self.num_series - 1
+
+    def add_from_arena(self, arena, rec_off, n_series):
+        """arena: uint8 numpy array (kept alive by the store), rec_off: int64 offsets relative to arena[0]."""
+        self._arena = arena; self._rec_off = np.ascontiguousarray(rec_off, np.int64)
+        return lib().fo_store_add_from_arena(self.h, _p(arena), _p(self._rec_off), n_series)
 
     def num_chunks(self, series): return lib().fo_store_num_chunks(self.h, series)
 

@@ -21,14 +21,15 @@ struct Store {
 };
 thread_local std::string g_err;
 
-void finishChunk(Chunk& c, int64_t startTime, int64_t endTime, int32_t numRows, int64_t ingestionTimeMs) {
+void finishChunk(Chunk& c, int64_t startTime, int64_t endTime, int32_t numRows, int64_t ingestionTimeMs,
+                 const uint8_t* tsExt = nullptr, const uint8_t* valExt = nullptr) {
   c.info.assign(csi::OffsetVectors + 16, 0);
   setLong(c.info.data() + csi::OffsetChunkID, csi::chunkID(startTime, ingestionTimeMs / 1000));
   setInt(c.info.data() + csi::OffsetNumRows, numRows);
   setLong(c.info.data() + csi::OffsetIngestionTime, ingestionTimeMs);
   setLong(c.info.data() + csi::OffsetEndTime, endTime);
-  setLong(c.info.data() + csi::OffsetVectors, (int64_t)(uintptr_t)c.ts.data());
-  setLong(c.info.data() + csi::OffsetVectors + 8, (int64_t)(uintptr_t)c.val.data());
+  setLong(c.info.data() + csi::OffsetVectors, (int64_t)(uintptr_t)(tsExt ? tsExt : c.ts.data()));
+  setLong(c.info.data() + csi::OffsetVectors + 8, (int64_t)(uintptr_t)(valExt ? valExt : c.val.data()));
 }
 }
 
@@ -170,6 +171,25 @@ int32_t fo_store_add_series_rows(void* sp, const int64_t* ts, const double* vals
   }
   return 0;
 }
+// Builds series over a HOST copy of the product's device chunk arena (filodb_b200/csrc/filo_record.h layout: 16-byte record
+// header {rec_bytes, n_chunks, n_rows, flags}, then 32-byte entries {start, end, numRows, tsOff, valOff, rowBase}).  Zero-copy:
+// the ChunkSetInfo blocks point into `arena`, which must outlive the store.  Used by bench.py's cpu_baseline leg.
+int64_t fo_store_add_from_arena(void* sp, const uint8_t* arena, const int64_t* rec_off, int64_t n_series) {
+  Store* s = (Store*)sp;
+  for (int64_t i = 0; i < n_series; ++i) {
+    const uint8_t* rec = arena + rec_off[i];
+    int32_t nch = getInt(rec + 4);
+    int64_t si = fo_store_add_series(sp);
+    for (int32_t c = 0; c < nch; ++c) {
+      const uint8_t* e = rec + 16 + 32 * (int64_t)c;
+      auto ch = std::make_unique<Chunk>();
+      finishChunk(*ch, getLong(e), getLong(e + 8), getInt(e + 16), getLong(e + 8) + 1000,
+                  rec + (uint32_t)getInt(e + 20), rec + (uint32_t)getInt(e + 24));
+      s->series[si]->chunks.push_back(std::move(ch));
+    }
+  }
+  return (int64_t)s->series.size();
+}
 int32_t fo_store_num_chunks(void* sp, int64_t series) { return (int32_t)((Store*)sp)->series[series]->chunks.size(); }
 // ChunkSetInfo addresses of a series (what RawDataRangeVector.chunkInfos yields), for the product's filo_load_series.
 void fo_store_info_addrs(void* sp, int64_t series, uint64_t* out) {
@@ -185,7 +205,8 @@ int64_t fo_store_vector_bytes(void* sp, int64_t series, int32_t chunk, int32_t c
 // Algorithmic bytes per SURVEY §8(d): Σ chunks (28 + 8*ncols + totalBytes(ts) + totalBytes(val))
 int64_t fo_store_algorithmic_bytes(void* sp) {
   Store* s = (Store*)sp; int64_t b = 0;
-  for (auto& se : s->series) for (auto& c : se->chunks) b += 28 + 16 + (int64_t)c->ts.size() + (int64_t)c->val.size();
+  for (auto& se : s->series) for (auto& c : se->chunks)
+    b += 28 + 16 + (int64_t)totalBytes(csi::vectorPtr(c->info.data(), 0)) + (int64_t)totalBytes(csi::vectorPtr(c->info.data(), 1));
   return b;
 }
 
