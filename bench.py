@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native FiloDB chunk-scan + range-vector-aggregation path.
+
+Workload (BASELINE.json configs[1], "C2"): per GPU 10M series x 2h@15s (480 rows, chunks 400+80), const-DDV timestamps,
+XOR-NibblePack ("Gorilla-compressed") gauge values 15+sin(n+1)+N(0,1) with 0.1% NaN stale markers at chunk ends,
+query rate()[5m] step 15s over the 2 h (T = 481 windows), gauge schema => RateOverDeltaChunkedFunctionD
+(sum_over_time / window * 1000), no across-series aggregate: output is [series x T] f64.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # product arm, one JSON line on rank 0
+  python bench.py --impl reference ...                           # reference CPU path (oracle port) on host cores
+
+A step = one pass of the hot path over the whole resident table (1 kernel launch).  `value` = samples scanned per second
+(Σ numRows of the chunks scanned, the quantity FiloDB counts in samplesScannedCtr) with inputs resident in HBM;
+`e2e` = the same through the C-ABI with HOST buffers: filo_load_series (gather + H2D) + filo_query (+ D2H) every step.
+Multi-GPU: series are sharded by id across ranks (FiloDB shard -> GPU), no data-path collective for this query
+(`--workload c5` runs sum(rate) by(cluster) with one NCCL all-reduce of the [G x T] partials).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T0_MS = 1_700_000_000_000
+INTERVAL = 15000
+ROWS = 480
+ROWS_PER_CHUNK = 400
+WINDOW = 300000
+STEP = 15000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="filo", choices=["filo", "reference"])
+    ap.add_argument("--series", type=int, default=10_000_000, help="series per GPU")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c2-raw", "c2-counter", "c3", "c5"])
+    ap.add_argument("--e2e-series", type=int, default=-1, help="series in the end-to-end leg (-1 = all)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-series", type=int, default=2_000_000, help="bounded sample for the CPU baseline legs")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+WORKLOADS = {
+    # name: (synth kwargs, fn, aggr, n_groups, description)
+    "c2": (dict(value_kind=0, value_enc=1, nan_per_million=1000), "FN_RATE", "AGG_NONE", 0,
+           "C2: {S} series x 2h@15s (480 rows, chunks 400+80), const-DDV ts, XOR-NibblePack gauge, rate()[5m] step 15s, T=481, no aggregate"),
+    "c2-raw": (dict(value_kind=0, value_enc=0, nan_per_million=1000), "FN_RATE", "AGG_NONE", 0,
+               "C2 variant: raw f64 gauge values (the reference's native DoubleVector encoding)"),
+    "c2-counter": (dict(value_kind=1, value_enc=1, nan_per_million=1000, reset_period=1000, schema_flags=1), "FN_RATE", "AGG_NONE", 0,
+                   "C2 variant: prom-counter schema (extrapolated Prometheus rate with counter correction)"),
+    "c3": (dict(value_kind=1, value_enc=1, reset_period=1000, schema_flags=1, ts_jitter_ms=2000), "FN_INCREASE", "AGG_SUM", 1000,
+           "C3: counters, DDV ts + XOR values, increase()[1m] then sum by(job), 1000 jobs"),
+    "c5": (dict(value_kind=1, value_enc=1, reset_period=1000, schema_flags=1), "FN_RATE", "AGG_SUM", 100,
+           "C5: counters, sum(rate()[5m]) by(cluster), 100 clusters, NCCL all-reduce of the [G x T] partials"),
+}
+
+
+def query_range(workload):
+    window = 60000 if workload == "c3" else WINDOW
+    return T0_MS, STEP, T0_MS + 7200000, window
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def host_chunk_infos(arena, rec_off, n_series):
+    """Host mirror of a shard's chunk metadata over a host copy of the arena: builds ChunkSetInfo blocks
+    (core/src/main/scala/filodb.core/store/ChunkSetInfo.scala:133-154) whose vector pointers point into `arena`.
+    Returns (n_chunks int32[S], info_addrs uint64[Σ], keepalive)."""
+    base = arena.ctypes.data
+    nch = arena[(rec_off[:n_series, None] + np.arange(4, 8)[None, :])].copy().view(np.uint32).reshape(-1).astype(np.int32)
+    total = int(nch.sum())
+    infos = np.zeros((total, 44), np.uint8)
+    cb = np.concatenate([[0], np.cumsum(nch)]).astype(np.int64)
+    maxc = int(nch.max()) if n_series else 0
+    for c in range(maxc):
+        sel = np.nonzero(nch > c)[0]
+        eoff = rec_off[sel] + 16 + 32 * c
+        ent = arena[(eoff[:, None] + np.arange(32)[None, :])].copy()
+        start = ent[:, 0:8].copy().view(np.int64).reshape(-1)
+        end = ent[:, 8:16].copy().view(np.int64).reshape(-1)
+        nrows = ent[:, 16:20].copy().view(np.int32).reshape(-1)
+        tso = ent[:, 20:24].copy().view(np.uint32).reshape(-1).astype(np.uint64)
+        vlo = ent[:, 24:28].copy().view(np.uint32).reshape(-1).astype(np.uint64)
+        row = cb[sel] + c
+        ing = end + 1000
+        chunk_id = ((np.uint64(1) << np.uint64(63)) ^ (start.astype(np.uint64) << np.uint64(22))) | ((ing // 1000) % (48 * 24 * 3600)).astype(np.uint64)
+        infos[row, 0:8] = chunk_id.view(np.uint8).reshape(-1, 8)
+        infos[row, 8:12] = nrows.view(np.uint8).reshape(-1, 4)
+        infos[row, 12:20] = ing.view(np.uint8).reshape(-1, 8)
+        infos[row, 20:28] = end.view(np.uint8).reshape(-1, 8)
+        recb = np.uint64(base) + rec_off[sel].astype(np.uint64)
+        infos[row, 28:36] = (recb + tso).view(np.uint8).reshape(-1, 8)
+        infos[row, 36:44] = (recb + vlo).view(np.uint8).reshape(-1, 8)
+    addrs = np.uint64(infos.ctypes.data) + np.arange(total, dtype=np.uint64) * np.uint64(44)
+    return nch, addrs, infos
+
+
+def _splitmix64_np(x):
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        z = x
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def synth_group_ids(seed, base, n, n_groups):
+    """group id of series base..base+n of a synthetic table (same hash as filodb_b200/csrc/synth_kernels.cu)."""
+    with np.errstate(over="ignore"):
+        gid = np.arange(base, base + n, dtype=np.uint64)
+        h = _splitmix64_np(np.uint64(seed) ^ np.uint64(0xA5A5A5A5) ^ (gid * np.uint64(0x9E3779B97F4A7C15)))
+    return (h % np.uint64(n_groups)).astype(np.int32)
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own CPU path for this query — the C++ restatement under oracle/ (the JVM cannot run
+    in this image) — on all host threads, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle import oracle as o
+    synth, fn_name, aggr_name, n_groups, desc = WORKLOADS[args.workload]
+    S = min(args.series, args.cpu_series)
+    cores = os.cpu_count() or 1
+    st = o.Store()
+    st.add_synth(S, ROWS, ROWS_PER_CHUNK, T0_MS, INTERVAL, seed=42, threads=cores, **synth)   # same rows/bytes as the GPU generator
+    start, step, end, window = query_range(args.workload)
+    cumulative = bool(synth.get("schema_flags", 0) & 1)
+    groups = o.synth_group_ids(42, 0, S, n_groups) if n_groups else None
+
+    def one():
+        st.query(getattr(o, fn_name), start, step, end, window, cumulative=cumulative, aggr=getattr(o, aggr_name),
+                 group_ids=groups, n_groups=max(n_groups, 1), threads=cores)
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = (time.perf_counter() - t0) / args.steps
+    samples = S * ROWS
+    val = samples / dt
+    line = {"impl": "reference", "metric": "samples/s scanned+aggregated (rate over 10M series)", "value": val, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc.format(S=args.series), "sample": "%d of %d series per step" % (S, args.series)},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": "%d series (%.1f%% of the workload) per step, all %d host threads, oracle C++ restatement of ChunkedWindowIteratorD" % (S, 100.0 * S / args.series, cores)},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    import filodb_b200.capi as capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    synth, fn_name, aggr_name, n_groups, desc = WORKLOADS[args.workload]
+    fn, aggr = getattr(capi, fn_name), getattr(capi, aggr_name)
+    S = args.series
+    ctx = capi.Context(local_rank)
+    t_gen = time.perf_counter()
+    tab = ctx.synth_table(S, ROWS, ROWS_PER_CHUNK, T0_MS, INTERVAL, n_groups=n_groups, seed=42, series_id_base=rank * S, **synth)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    ti = tab.info()
+    start, step, end, window = query_range(args.workload)
+    T = capi.num_windows(start, step, end)
+    stream = torch.cuda.current_stream().cuda_stream
+    if aggr == capi.AGG_NONE:
+        out = torch.empty(S * T, dtype=torch.float64, device="cuda"); aux = None
+        out_bytes = S * T * 8
+        flags = 0
+    else:
+        out = torch.empty(n_groups * T, dtype=torch.float64, device="cuda")
+        aux = torch.empty(n_groups * T, dtype=torch.int64, device="cuda")
+        final = torch.empty(n_groups * T, dtype=torch.float64, device="cuda")
+        out_bytes = n_groups * T * 8
+        flags = capi.Q_PARTIAL if world > 1 else 0
+
+    def step_fn():
+        ctx.query_device(tab, fn, start, step, end, window, out.data_ptr(), aux.data_ptr() if aux is not None else 0,
+                         aggr=aggr, flags=flags, stream=stream, want_stats=False)
+        if aggr != capi.AGG_NONE and world > 1:      # the one cross-shard exchange of the plan (ReduceAggregateExec)
+            dist.all_reduce(out, op=dist.ReduceOp.SUM); dist.all_reduce(aux, op=dist.ReduceOp.SUM)
+            ctx.present_partials(aggr, n_groups * T, out.data_ptr(), aux.data_ptr(), final.data_ptr(), stream=stream)
+
+    # kernel-only duration of the dominant kernel (for the roofline) via the library's own CUDA events
+    st = ctx.query_device(tab, fn, start, step, end, window, out.data_ptr(), aux.data_ptr() if aux is not None else 0,
+                          aggr=aggr, flags=flags, stream=stream, want_stats=True)
+    assert st["samples_scanned"] == ti.n_samples, (st, ti.n_samples)
+    for _ in range(args.warmup):
+        step_fn()
+    torch.cuda.synchronize()
+    kern_ns = []
+    for _ in range(3):
+        kern_ns.append(ctx.query_device(tab, fn, start, step, end, window, out.data_ptr(), aux.data_ptr() if aux is not None else 0,
+                                        aggr=aggr, flags=flags, stream=stream, want_stats=True)["kernel_ns"])
+    sampler = ClockSampler(local_rank)
+    if dist: dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist: dist.barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    if dist:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    samples_step = ti.n_samples * world
+    value = samples_step / (ms / 1e3)
+    peak, peak_src = measured_peak()
+    alg_bytes = ti.algorithmic_bytes + (S * 4 if aggr != capi.AGG_NONE else 0) + out_bytes
+    kern_ms = float(np.median(kern_ns)) / 1e6
+    achieved = alg_bytes / (kern_ms / 1e3) / 1e9
+    launches_per_step = 1 if aggr == capi.AGG_NONE else 2
+
+    line = {"metric": "samples/s scanned+aggregated (rate over 10M series); % HBM roofline", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc.format(S=S) + " (per GPU; series sharded by id across GPUs)", "series_per_gpu": S, "rows": ROWS, "windows": T,
+                       "window_ms": window, "step_ms": step, "l2": "inputs (%.1f GB arena) far larger than the 126 MB L2; no flush needed" % (ti.arena_bytes / 1e9),
+                       "table_gen_s": round(t_gen, 2), "arena_bytes": ti.arena_bytes},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "scan_series_kernel" if aggr == capi.AGG_NONE else "scan_agg_kernel",
+                         "kernel_ms": kern_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src}}
+
+    # ---- end-to-end through the C-ABI with host buffers (load + query + result read-back every step)
+    del out
+    torch.cuda.empty_cache()
+    if not args.no_e2e:
+        Se = S if args.e2e_series < 0 else min(S, args.e2e_series)
+        os.environ.setdefault("FILO_HOST_THREADS", str(min(64, os.cpu_count() or 8)))
+        arena, rec_off = tab.read_arena(0, Se)
+        nch, addrs, keep = host_chunk_infos(arena, rec_off, Se)
+        n_out = Se * T if aggr == capi.AGG_NONE else n_groups * T
+        hout = torch.empty(n_out, dtype=torch.float64).pin_memory()
+        hout_np = hout.numpy()
+        gids = None
+        if n_groups:
+            gids = synth_group_ids(42, rank * S, Se, n_groups)
+        import ctypes as C
+        L = capi.lib()
+
+        def e2e_step():
+            h = C.c_void_p()
+            ctx._check(L.filo_load_series(ctx.h, Se, nch.ctypes.data_as(C.c_void_p), addrs.ctypes.data_as(C.c_void_p), 0, 1,
+                                          gids.ctypes.data_as(C.c_void_p) if gids is not None else None, n_groups, synth.get("schema_flags", 0), C.byref(h)))
+            st_ = capi.Stats()
+            ctx._check(L.filo_query(ctx.h, h, fn, start, step, end, window, aggr, 0, 0, hout_np.ctypes.data_as(C.c_void_p), None, C.byref(st_)))
+            L.filo_table_free(ctx.h, h)
+        e2e_step()
+        if dist: dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        if dist:
+            t = torch.tensor([dt], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+        line["e2e"] = {"value": Se * ROWS * world / dt, "unit": "samples/s", "h2d_bytes_per_step": int(arena.size), "d2h_bytes_per_step": int(n_out * 8),
+                       "s_per_step": dt, "steps": args.e2e_steps, "series_per_gpu": Se,
+                       "what": "filo_load_series (walk ChunkSetInfo blocks in host memory, gather into pinned slabs, H2D) + filo_query (kernel + D2H into a pinned host buffer) + filo_table_free, per step"}
+        del arena, keep, hout
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample, all host threads
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as o
+        Sc = min(S, args.cpu_series)
+        arena, rec_off = tab.read_arena(0, Sc)
+        ost = o.Store(); ost.add_from_arena(arena, rec_off, Sc)
+        cores = os.cpu_count() or 1
+        cumulative = bool(synth.get("schema_flags", 0) & 1)
+        gids = None
+        if n_groups:
+            gids = synth_group_ids(42, 0, Sc, n_groups)
+        t0 = time.perf_counter()
+        ost.query(getattr(o, fn_name), start, step, end, window, cumulative=cumulative, aggr=getattr(o, aggr_name), group_ids=gids,
+                  n_groups=max(n_groups, 1), threads=cores)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": Sc * ROWS / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+                                "sample": "%d of %d series (%.1f s wall on %d threads); C++ restatement of ChunkedWindowIteratorD + range functions, not a JVM number" % (Sc, S, dt, cores)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    tab.free(); ctx.close()
+    if dist: dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

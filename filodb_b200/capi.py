@@ -14,7 +14,7 @@ Q_PARTIAL = 1
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CORRUPT_VECTOR, ERR_UNSUPPORTED, ERR_QUERY_LIMIT, ERR_BAD_QUERY, ERR_OOM = 0, -1, -2, -3, -4, -5, -6, -7
 
 EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_last_error", "filo_load_series", "filo_synth_table",
-           "filo_table_set_groups", "filo_table_get_info", "filo_table_read_record", "filo_table_free",
+           "filo_table_set_groups", "filo_table_get_info", "filo_table_read_record", "filo_table_read_arena", "filo_table_free",
            "filo_num_windows", "filo_query", "filo_query_device", "filo_present_partials"]
 
 
@@ -77,6 +77,7 @@ def _sig(L):
     L.filo_table_set_groups.restype = i32; L.filo_table_set_groups.argtypes = [vp, vp, vp, i32]
     L.filo_table_get_info.restype = i32; L.filo_table_get_info.argtypes = [vp, C.POINTER(TableInfo)]
     L.filo_table_read_record.restype = i64; L.filo_table_read_record.argtypes = [vp, vp, i64, vp, i64]
+    L.filo_table_read_arena.restype = i64; L.filo_table_read_arena.argtypes = [vp, vp, i64, i64, vp, i64, vp]
     L.filo_table_free.restype = None; L.filo_table_free.argtypes = [vp, vp]
     L.filo_num_windows.restype = i32; L.filo_num_windows.argtypes = [i64, i64, i64]
     L.filo_query.restype = i32
@@ -120,6 +121,20 @@ class Table:
         if n < 0:
             self.ctx._check(int(n))
         return buf[:n].copy()
+
+    def read_arena(self, first, n, out=None):
+        """Host copy of the records of series [first, first+n): (bytes uint8[], rec_off int64[n+1] relative to bytes[0])."""
+        off = np.zeros(n + 1, np.int64)
+        need = lib().filo_table_read_arena(self.ctx.h, self.h, first, n, None, 0, _p(off))
+        if need > 0 or need < -(1 << 62):
+            self.ctx._check(int(need))
+        nbytes = -need
+        buf = out if out is not None else np.empty(max(nbytes, 1), np.uint8)
+        assert buf.size >= nbytes
+        got = lib().filo_table_read_arena(self.ctx.h, self.h, first, n, _p(buf), buf.size, _p(off))
+        if got < 0:
+            self.ctx._check(int(got))
+        return buf[:got], off
 
     def free(self):
         if self.h:

@@ -388,6 +388,20 @@ extern "C" int64_t filo_table_read_record(filo_ctx* ctx, const filo_table* t, in
   return n;
 }
 
+extern "C" int64_t filo_table_read_arena(filo_ctx* ctx, const filo_table* t, int64_t first, int64_t n, uint8_t* out, int64_t cap,
+                                         int64_t* rec_off_out) {
+  if (!ctx || !t || first < 0 || n < 0 || first + n > t->n_series || !rec_off_out) return fail(ctx, FILO_ERR_INVALID_ARG, "bad range");
+  cudaSetDevice(ctx->device);
+  if (cudaMemcpy(rec_off_out, t->d_rec_off + first, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail(ctx, FILO_ERR_CUDA, "read rec_off");
+  const int64_t base = rec_off_out[0], bytes = rec_off_out[n] - base;
+  for (int64_t i = 0; i <= n; ++i) rec_off_out[i] -= base;
+  if (bytes > cap || !out) return -bytes;
+  if (bytes > 0 && cudaMemcpy(out, t->d_arena + base, (size_t)bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail(ctx, FILO_ERR_CUDA, "read arena");
+  return bytes;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // query
 // ------------------------------------------------------------------------------------------------------------------

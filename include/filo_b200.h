@@ -154,6 +154,11 @@ int32_t filo_table_set_groups(filo_ctx* ctx, filo_table* t, const int32_t* group
 int32_t filo_table_get_info(const filo_table* t, filo_table_info* out);
 /* Copies the device arena record of one series back to the host (tests: byte parity of the GPU encoder). */
 int64_t filo_table_read_record(filo_ctx* ctx, const filo_table* t, int64_t series, uint8_t* out, int64_t cap);
+/* Copies the arena records of series [first, first+n) to the host: `out` receives the record bytes back to back,
+ * rec_off_out receives n+1 byte offsets relative to out.  Returns the byte count, or -(bytes needed) when cap is too small.
+ * (bench/test: host-side mirror of the chunk memory a FiloDB shard would hold off-heap.) */
+int64_t filo_table_read_arena(filo_ctx* ctx, const filo_table* t, int64_t first, int64_t n, uint8_t* out, int64_t cap,
+                              int64_t* rec_off_out);
 void    filo_table_free(filo_ctx* ctx, filo_table* t);
 
 /* Number of output windows: first window always, then while window_end + step <= end (ChunkSetInfo.scala:462). */

@@ -70,6 +70,8 @@ def _sig(L):
         ("fo_store_add_chunk_raw", i32, [vp, i64, i64, i64, i32, vp, i32, vp, i32]),
         ("fo_store_add_series_rows", i32, [vp, vp, vp, i64, vp, i32, i32, i32, i32]),
         ("fo_store_add_from_arena", i64, [vp, vp, vp, i64]),
+        ("fo_store_add_synth", i64, [vp, i64, i32, i32, i64, i32, i32, i32, i32, i32, i32, i32, C.c_uint64, i64, vp, i32]),
+        ("fo_synth_group_ids", i32, [C.c_uint64, i64, i64, i32, vp]),
         ("fo_store_num_chunks", i32, [vp, i64]), ("fo_store_info_addrs", None, [vp, i64, vp]),
         ("fo_store_vector_bytes", i64, [vp, i64, i32, i32, vp, i64]),
         ("fo_store_algorithmic_bytes", i64, [vp]),
@@ -273,6 +275,15 @@ class Store:
         self._arena = arena; self._rec_off = np.ascontiguousarray(rec_off, np.int64)
         return lib().fo_store_add_from_arena(self.h, _p(arena), _p(self._rec_off), n_series)
 
+    def add_synth(self, n_series, rows, rows_per_chunk=400, t0_ms=1_700_000_000_000, interval_ms=15000, ts_jitter_ms=0,
+                  value_kind=0, value_enc=0, reset_period=0, nan_per_million=0, schema_flags=0, seed=42, series_id_base=0,
+                  threads=1, **_ignored):
+        """Same deterministic generator as the product's GPU generator (filo_synth_table), restated on the CPU."""
+        st = np.sin(np.arange(1, rows + 1, dtype=np.float64))
+        return lib().fo_store_add_synth(self.h, n_series, rows, rows_per_chunk, t0_ms, interval_ms, ts_jitter_ms, value_kind,
+                                        value_enc, reset_period, nan_per_million, int(bool(schema_flags & 1)), seed,
+                                        series_id_base, _p(st), threads)
+
     def num_chunks(self, series): return lib().fo_store_num_chunks(self.h, series)
 
     def info_addrs(self, series):
@@ -322,4 +333,10 @@ def sliding(ts, vals, fn, start, step, end, window, cumulative=False):
     ts = np.ascontiguousarray(ts, np.int64); vals = np.ascontiguousarray(vals, np.float64)
     out = np.zeros(num_windows(start, step, end), np.float64)
     lib().fo_sliding(_p(ts), _p(vals), ts.size, fn, int(cumulative), start, step, end, window, _p(out))
+    return out
+
+
+def synth_group_ids(seed, series_id_base, n, n_groups):
+    out = np.zeros(n, np.int32)
+    lib().fo_synth_group_ids(seed, series_id_base, n, n_groups, _p(out))
     return out

@@ -190,6 +190,66 @@ int64_t fo_store_add_from_arena(void* sp, const uint8_t* arena, const int64_t* r
   }
   return (int64_t)s->series.size();
 }
+// Deterministic synthetic series (same hash-based row generator as filodb_b200/csrc/synth_kernels.cu, restated here so the
+// reference arm of bench.py needs nothing from the product), encoded with the appenders' optimize() restatement above.
+static inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull; uint64_t z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31);
+}
+int64_t fo_store_add_synth(void* sp, int64_t n_series, int32_t rows, int32_t rpc, int64_t t0, int32_t interval, int32_t jitter,
+                           int32_t value_kind, int32_t value_enc, int32_t reset_period, int32_t nan_ppm, int32_t cumulative,
+                           uint64_t seed, int64_t gid_base, const double* sin_table, int32_t nthreads) {
+  Store* s = (Store*)sp;
+  const int64_t first = (int64_t)s->series.size();
+  for (int64_t i = 0; i < n_series; ++i) s->series.emplace_back(new StoreSeries());
+  const double noise_scale = 1.0 / 37837.22772881784;
+  std::atomic<int64_t> next{0};
+  auto worker = [&]() {
+    std::vector<int64_t> ts(rows); std::vector<double> vals(rows);
+    for (;;) {
+      int64_t i = next.fetch_add(1); if (i >= n_series) break;
+      const uint64_t gid = (uint64_t)(gid_base + i);
+      const uint64_t key = splitmix64(seed ^ (gid * 0xD1342543DE82EF95ull));
+      auto rh = [&](int row, int salt) { return splitmix64(key + ((uint64_t)(uint32_t)row << 3) + (uint64_t)salt); };
+      double v = 0.0;
+      for (int r = 0; r < rows; ++r) {
+        int64_t t = t0 + (int64_t)r * interval;
+        if (jitter > 0) t += (int64_t)(rh(r, 3) % (uint64_t)(2 * jitter + 1)) - jitter;
+        ts[r] = t;
+        const bool lastInChunk = ((r % rpc) == rpc - 1) || r == rows - 1;
+        if (lastInChunk && nan_ppm > 0 && (int)(rh(r, 1) % 1000000ull) < nan_ppm) { vals[r] = NaN; continue; }
+        const uint64_t h = rh(r, 0);
+        const int x = (int)(h & 0xffff) + (int)((h >> 16) & 0xffff) + (int)((h >> 32) & 0xffff) + (int)(h >> 48);
+        const double noise = (double)(x - 131070) * noise_scale;
+        const double sm = (15.0 + sin_table[r]) + noise;
+        if (value_kind == 0) { vals[r] = sm; continue; }
+        double inc = sm > 0.0 ? sm : 0.0;
+        if (value_kind == 2) inc = std::rint(inc);
+        if (reset_period > 0 && r > 0 && (rh(r, 2) % (uint64_t)reset_period) == 0) v = inc; else v = v + inc;
+        vals[r] = v;
+      }
+      auto& ser = *s->series[first + i];
+      for (int r0 = 0; r0 < rows; r0 += rpc) {
+        const int n = std::min(rpc, rows - r0);
+        auto c = std::make_unique<Chunk>();
+        c->ts = enc::timestamps(ts.data() + r0, n);
+        if (value_enc == 1) c->val = enc::doublesXor(vals.data() + r0, n, cumulative != 0);
+        else if (value_enc == 0) { c->val = enc::rawDoubles(vals.data() + r0, n); if (cumulative && enc::counterDropFlag(vals.data() + r0, n)) pv_markDrop(c->val.data()); }
+        else c->val = enc::doubles(vals.data() + r0, n, cumulative != 0);
+        finishChunk(*c, ts[r0], ts[r0 + n - 1], n, ts[r0 + n - 1] + 1000);
+        ser.chunks.push_back(std::move(c));
+      }
+    }
+  };
+  if (nthreads <= 1) worker();
+  else { std::vector<std::thread> th; for (int i = 0; i < nthreads; ++i) th.emplace_back(worker); for (auto& t : th) t.join(); }
+  return (int64_t)s->series.size();
+}
+int32_t fo_synth_group_ids(uint64_t seed, int64_t gid_base, int64_t n, int32_t n_groups, int32_t* out) {
+  for (int64_t i = 0; i < n; ++i)
+    out[i] = n_groups > 0 ? (int32_t)(splitmix64(seed ^ 0xA5A5A5A5ull ^ ((uint64_t)(gid_base + i) * 0x9E3779B97F4A7C15ull)) % (uint64_t)n_groups) : 0;
+  return 0;
+}
 int32_t fo_store_num_chunks(void* sp, int64_t series) { return (int32_t)((Store*)sp)->series[series]->chunks.size(); }
 // ChunkSetInfo addresses of a series (what RawDataRangeVector.chunkInfos yields), for the product's filo_load_series.
 void fo_store_info_addrs(void* sp, int64_t series, uint64_t* out) {
