@@ -6,6 +6,7 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -27,6 +28,9 @@ struct filo_ctx {
 struct filo_table {
   int64_t n_series = 0, n_chunks = 0, n_samples = 0, arena_bytes = 0, algorithmic_bytes = 0;
   int32_t max_rows = 0, max_chunks = 0, schema_flags = 0;
+  uint32_t max_rec_bytes = 0;       // largest record (staging buffer size of the v2 kernels)
+  bool any_nonconst_ts = true;      // some timestamp vector is not a const DDV (needs decoded ts slots)
+  bool any_drop = true;             // some value vector carries the counter drop flag (needs corrected slots)
   uint8_t* d_arena = nullptr;
   int64_t* d_rec_off = nullptr;     // [n_series + 1]
   // grouping
@@ -174,6 +178,9 @@ void filo_internal_set_arena(filo_table* t, uint8_t* d_arena, int64_t* d_rec_off
   t->d_arena = d_arena; t->d_rec_off = d_rec_off; t->n_series = n_series; t->n_chunks = n_chunks; t->n_samples = n_samples;
   t->arena_bytes = arena_bytes; t->algorithmic_bytes = algorithmic_bytes; t->max_rows = max_rows; t->max_chunks = max_chunks;
   t->schema_flags = schema_flags;
+}
+void filo_internal_set_layout(filo_table* t, uint32_t max_rec_bytes, bool any_nonconst_ts, bool any_drop) {
+  t->max_rec_bytes = max_rec_bytes; t->any_nonconst_ts = any_nonconst_ts; t->any_drop = any_drop;
 }
 cudaStream_t filo_internal_stream(filo_ctx* ctx) { return ctx->stream; }
 int filo_internal_device(filo_ctx* ctx) { return ctx->device; }
@@ -347,6 +354,11 @@ extern "C" int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32
   int64_t nch = 0, ns = 0, alg = 0; int32_t mr = 0, mc = 0;
   for (int i = 0; i < nthreads; ++i) { nch += t_chunks[i]; ns += t_samples[i]; alg += t_alg[i]; mr = std::max(mr, t_maxrows[i]); mc = std::max(mc, t_maxch[i]); }
   filo_internal_set_arena(t, d_arena, d_rec_off, n_series, nch, ns, arena_bytes + (n_series + 1) * 8, alg, mr, mc, schema_flags);
+  {
+    uint32_t max_rec = 0, f_or = 0, f_and = ~0u;
+    for (int64_t i = 0; i < n_series; ++i) { max_rec = std::max(max_rec, plan[i].rec_bytes); f_or |= plan[i].flags; f_and &= plan[i].flags; }
+    filo_internal_set_layout(t, max_rec, n_series > 0 && !(f_and & REC_ALL_TS_CONST), (f_or & REC_ANY_DROP) != 0);
+  }
   // groups
   int32_t* d_gid = nullptr;
   if (group_ids && n_series > 0) {
@@ -447,29 +459,49 @@ extern "C" int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (stats) { CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1)); }
 
-  // per-warp scratch: chunk descriptors + decoded rows
-  uint32_t scratch = align_up((uint32_t)t->max_chunks * 112u, 16) + (uint32_t)t->max_rows * 8u * (need_corr ? 3u : 2u);
-  scratch = align_up(scratch + 16, 16);
+  // ---- kernel selection.  v2 (TMA-staged, blocked reductions) needs its whole per-warp working set in shared memory;
+  //      v1 (generic, global-memory record reads, optional global scratch) takes everything else.  FILO_KERNEL=v1 forces v1.
   const uint32_t acc_bytes = fused ? align_up((uint32_t)q.T * 12u, 16) : 0;
-  const size_t cta_smem = (size_t)(scratch + acc_bytes) * SCAN_WARPS;
-  const size_t smem_cap = std::min<size_t>(ctx->max_smem_optin, 200 * 1024);
-  const int use_smem = cta_smem <= smem_cap;
-  int ctas_per_sm = 16;    // 64 warps / SCAN_WARPS
-  if (use_smem) ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(220 * 1024) / std::max<size_t>(cta_smem + 1024, 1)));
+  const bool delta_fn = (fn == FILO_FN_DELTA);
+  const bool need_corr2 = need_corr && t->any_drop;
+  uint32_t scratch2 = align_up((uint32_t)t->max_chunks * (uint32_t)CHUNK_DESC_BYTES, 16) +
+                      ((uint32_t)t->max_rows + (uint32_t)t->max_chunks * 8u) * 8u * (1u + (t->any_nonconst_ts ? 1u : 0u) + (need_corr2 ? 1u : 0u));
+  scratch2 = align_up(scratch2 + 16, 16);
+  (void)delta_fn;
+  const uint32_t rec_cap = align_up(t->max_rec_bytes + 16, 128);
+  const size_t per_warp2 = v2_smem_per_warp(rec_cap, scratch2, acc_bytes);
+  const char* force = std::getenv("FILO_KERNEL");
+  const bool want_v1 = force && std::string(force) == "v1";
+  const bool use_v2 = !want_v1 && t->max_rec_bytes > 0 && per_warp2 * FAST_WARPS + 1024 <= std::min<size_t>(ctx->max_smem_optin, 227 * 1024);
   const int64_t work = fused ? t->n_items : t->n_series;
-  int grid = (int)std::min<int64_t>((work + SCAN_WARPS - 1) / SCAN_WARPS, (int64_t)ctx->sm_count * ctas_per_sm);
-  if (grid < 1) grid = 1;
-  uint8_t* gscratch = nullptr;
-  if (!use_smem) CUDA_TRY(ctx, tmp.alloc((void**)&gscratch, (size_t)grid * SCAN_WARPS * (scratch + acc_bytes)));
-  ScanLaunch L{t->d_arena, t->d_rec_off, t->n_series, q, gscratch, scratch, use_smem, d_counters, d_err, grid, s};
   int64_t launches = 0;
+  uint8_t* gscratch = nullptr;
+  ScanLaunch L{t->d_arena, t->d_rec_off, t->n_series, q, nullptr, 0, 0, d_counters, d_err, 1, s};
+  uint32_t rec_cap_used = 0;
+  if (use_v2) {
+    const size_t cta_smem = per_warp2 * FAST_WARPS + 1024;
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(64 / FAST_WARPS, (size_t)(228 * 1024) / cta_smem));
+    L.grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + FAST_WARPS - 1) / FAST_WARPS, (int64_t)ctx->sm_count * ctas_per_sm));
+    L.scratch_bytes = scratch2; L.use_smem = 1; rec_cap_used = rec_cap;
+  } else {
+    uint32_t scratch = align_up((uint32_t)t->max_chunks * (uint32_t)CHUNK_DESC_BYTES, 16) + (uint32_t)t->max_rows * 8u * (need_corr ? 3u : 2u);
+    scratch = align_up(scratch + 16, 16);
+    const size_t cta_smem = (size_t)(scratch + acc_bytes) * SCAN_WARPS;
+    const int use_smem = cta_smem <= std::min<size_t>(ctx->max_smem_optin, 200 * 1024);
+    int ctas_per_sm = 16;
+    if (use_smem) ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(220 * 1024) / std::max<size_t>(cta_smem + 1024, 1)));
+    L.grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + SCAN_WARPS - 1) / SCAN_WARPS, (int64_t)ctx->sm_count * ctas_per_sm));
+    if (!use_smem) CUDA_TRY(ctx, tmp.alloc((void**)&gscratch, (size_t)L.grid * SCAN_WARPS * (scratch + acc_bytes)));
+    L.gscratch = gscratch; L.scratch_bytes = scratch; L.use_smem = use_smem;
+  }
   if (stats) CUDA_TRY(ctx, cudaEventRecord(e0, s));
   if (agg == FILO_AGG_NONE) {
-    CUDA_TRY(ctx, launch_scan_series(L, (double*)d_out_values)); launches = 1;
+    CUDA_TRY(ctx, use_v2 ? launch_scan_series_v2(L, (double*)d_out_values, rec_cap_used) : launch_scan_series(L, (double*)d_out_values));
+    launches = 1;
   } else if (!fused) {
     double* per = nullptr;
     CUDA_TRY(ctx, tmp.alloc((void**)&per, (size_t)t->n_series * q.T * 8));
-    CUDA_TRY(ctx, launch_scan_series(L, per));
+    CUDA_TRY(ctx, use_v2 ? launch_scan_series_v2(L, per, rec_cap_used) : launch_scan_series(L, per));
     CUDA_TRY(ctx, launch_topk(per, t->grouped ? t->d_order : nullptr, t->d_group_start, t->n_groups, q.T, k, agg == FILO_AGG_BOTTOMK,
                               (double*)d_out_values, (int64_t*)d_out_aux, s));
     launches = 2;
@@ -477,7 +509,9 @@ extern "C" int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t
     double* pval = nullptr; uint32_t* pcnt = nullptr;
     CUDA_TRY(ctx, tmp.alloc((void**)&pval, (size_t)t->n_items * q.T * 8));
     CUDA_TRY(ctx, tmp.alloc((void**)&pcnt, (size_t)t->n_items * q.T * 4));
-    CUDA_TRY(ctx, launch_scan_agg(L, t->grouped ? t->d_order : nullptr, t->d_item_begin, t->n_items, agg, pval, pcnt, acc_bytes));
+    const int32_t* order = t->grouped ? t->d_order : nullptr;
+    CUDA_TRY(ctx, use_v2 ? launch_scan_agg_v2(L, order, t->d_item_begin, t->n_items, agg, pval, pcnt, acc_bytes, rec_cap_used)
+                         : launch_scan_agg(L, order, t->d_item_begin, t->n_items, agg, pval, pcnt, acc_bytes));
     CUDA_TRY(ctx, launch_merge_partials(pval, pcnt, t->d_gis, t->n_groups, q.T, agg, (flags & FILO_Q_PARTIAL) ? 1 : 0,
                                         (double*)d_out_values, (int64_t*)d_out_aux, s));
     launches = 2;

@@ -6,7 +6,9 @@
 
 namespace filo {
 
-constexpr int SCAN_WARPS = 4;          // warps (= series in flight) per CTA
+constexpr int SCAN_WARPS = 4;          // warps (= series in flight) per CTA, v1 kernels
+constexpr int FAST_WARPS = 4;          // v2 kernels
+constexpr int CHUNK_DESC_BYTES = 144;  // sizeof(ChunkDesc), scan_device.cuh
 constexpr int FILO_MAX_TOPK = 32;
 enum { AGG_NONE = 0, AGG_SUM = 1, AGG_AVG = 2, AGG_MIN = 3, AGG_MAX = 4, AGG_COUNT = 5, AGG_TOPK = 6, AGG_BOTTOMK = 7 };
 
@@ -27,6 +29,10 @@ struct ScanLaunch {
 cudaError_t launch_scan_series(const ScanLaunch& L, double* out);
 cudaError_t launch_scan_agg(const ScanLaunch& L, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg_op,
                             double* pval, uint32_t* pcnt, uint32_t acc_bytes);
+cudaError_t launch_scan_series_v2(const ScanLaunch& L, double* out, uint32_t rec_cap);
+cudaError_t launch_scan_agg_v2(const ScanLaunch& L, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg_op,
+                               double* pval, uint32_t* pcnt, uint32_t acc_bytes, uint32_t rec_cap);
+size_t v2_smem_per_warp(uint32_t rec_cap, uint32_t scratch_bytes, uint32_t acc_bytes);
 cudaError_t launch_merge_partials(const double* pval, const uint32_t* pcnt, const int64_t* gis, int n_groups, int T, int agg_op,
                                   int partial_out, double* out_val, int64_t* out_cnt, cudaStream_t s);
 cudaError_t launch_present(int agg_op, int64_t n, const double* vals, const int64_t* cnts, double* out, cudaStream_t s);

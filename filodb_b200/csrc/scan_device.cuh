@@ -30,11 +30,18 @@ struct __align__(16) ChunkDesc {
   int64_t ts_init, val_init;
   int32_t ts_slope, val_slope;
   int32_t num_rows, ts_len, val_len;
-  uint8_t val_is_long, dropped, pad0, pad1;
+  uint8_t val_is_long, dropped, pshift, fast32;   // pshift: log2 of the transposition period of val_slots (0 = linear)
   double upd_last, upd_corr;    // dropped chunk: last non-NaN value (or 0) and the chunk's total correction
   double first_val, last_val;   // apply(0), apply(len-1)
+  int32_t pitch;                // transposed value layout: slot(r) = (r & (P-1)) * pitch + (r >> pshift), P = 1 << pshift
+  int32_t kA, kB;               // windows [kA, kB] whose only contributing rows are an unclamped row range of this chunk
+  int32_t sA;                   // first row of window kA (rows advance by one per window in that interval)
+  int32_t Wr;                   // last row - first row of every window in [kA, kB]
+  int32_t has_nan;              // some value of the chunk is NaN (double slots only)
+  int32_t pad_[2];
 };
-static_assert(sizeof(ChunkDesc) == 112, "ChunkDesc size");
+static_assert(sizeof(ChunkDesc) == 144, "ChunkDesc size");
+__device__ __forceinline__ int tidx(const ChunkDesc& c, int r) { return (r & ((1 << c.pshift) - 1)) * c.pitch + (r >> c.pshift); }
 
 // ------------------------------------------------------------------------------------------------ loads
 __device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
@@ -66,7 +73,8 @@ __device__ __forceinline__ int int_length(const uint8_t* in) {               // 
 // ------------------------------------------------------------------------------------------------ XOR decode
 // Warp-cooperative decode of a FiloXorDoubleVector into out[0..n).  Lane g handles NibblePack group g (8 values):
 // field extraction is independent per group thanks to the group-offset table; the XOR chain is a warp prefix-XOR.
-__device__ __forceinline__ void xor_decode_warp(const uint8_t* v, double* out, int lane) {
+__device__ __forceinline__ void xor_decode_warp(const uint8_t* v, double* out, int lane, int pshift = 0, int pitch = 0) {
+  const int Pm = (1 << pshift) - 1;
   const int n = (int)ld32(v + XOR_OFF_N);
   const uint32_t w12 = ld32(v + XOR_OFF_NGROUPS);
   const int ng = w12 & 0xffff, payloadOff = w12 >> 16;
@@ -121,7 +129,7 @@ __device__ __forceinline__ void xor_decode_warp(const uint8_t* v, double* out, i
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         int idx = 1 + g * 8 + i;
-        if (idx < n) reinterpret_cast<uint64_t*>(out)[idx] = basev ^ d[i];
+        if (idx < n) reinterpret_cast<uint64_t*>(out)[(idx & Pm) * pitch + (idx >> pshift)] = basev ^ d[i];
       }
     }
     carry ^= __shfl_sync(0xffffffffu, incl, 31);
@@ -132,14 +140,17 @@ __device__ __forceinline__ void xor_decode_warp(const uint8_t* v, double* out, i
 struct ScratchCursor { uint8_t* p; };
 
 __device__ __forceinline__ double slot_value(const ChunkDesc& c, int r) {
-  if (c.val_is_long) return (double)reinterpret_cast<const int64_t*>(c.val_slots)[r];   // DoubleLongWrapDataReader.apply
-  return reinterpret_cast<const double*>(c.val_slots)[r];
+  if (c.val_is_long) return (double)reinterpret_cast<const int64_t*>(c.val_slots)[tidx(c, r)];   // DoubleLongWrapDataReader.apply
+  return reinterpret_cast<const double*>(c.val_slots)[tidx(c, r)];
 }
 
 // Resolves chunk `e` of the record into `d`; decodes into scratch as needed.  Returns an error code (0 = ok).
 // All lanes call it with identical arguments; stores to *d are done by lane 0 and published with __syncwarp.
 __device__ __forceinline__ int resolve_chunk(const uint8_t* rec, const ChunkEntry* e, ChunkDesc* d, ScratchCursor& sc,
-                                             bool need_corrected, int lane) {
+                                             bool need_corrected, int lane, int pshift = 0, bool copy_all = false) {
+  const int Pm = (1 << pshift) - 1;
+  int pitch = 0;
+#define TIDX(r) (((r) & Pm) * pitch + ((r) >> pshift))
   const uint8_t* tv = rec + e->ts_off;
   const uint8_t* vv = rec + e->val_off;
   const uint32_t tw = ld32(tv + 4), vw = ld32(vv + 4);
@@ -151,6 +162,11 @@ __device__ __forceinline__ int resolve_chunk(const uint8_t* rec, const ChunkEntr
     ts_len = (int32_t)ld32(tv + 8); ts_init = (int64_t)ld64_a4(tv + 12); ts_slope = (int32_t)ld32(tv + 20);
   } else if (twire == WIRE_RAW64) {
     ts_len = ((int32_t)ld32(tv) - 4) / 8; ts_slots = reinterpret_cast<const int64_t*>(tv + 8);
+    if (copy_all) {                                      // the staged record buffer is recycled right after resolve
+      int64_t* slots = reinterpret_cast<int64_t*>(sc.p);
+      for (int r = lane; r < ts_len; r += 32) slots[r] = ts_slots[r];
+      ts_slots = slots; sc.p += (size_t)ts_len * 8;
+    }
   } else if (twire == WIRE_DDV) {                        // DeltaDeltaVector.scala:138-156
     const uint8_t* in = tv + 20;
     const uint32_t iw = ld32(in + 4);
@@ -165,12 +181,21 @@ __device__ __forceinline__ int resolve_chunk(const uint8_t* rec, const ChunkEntr
   const void* val_slots = nullptr; int64_t val_init = 0; int32_t val_slope = 0; int32_t val_len = 0; bool is_long = false;
   const bool dropped = (vw >> 31) & 1;                   // PrimitiveVectorReader.dropped, BinaryVector.scala:530-531
   if (vwire == WIRE_RAW64) {
-    val_len = ((int32_t)ld32(vv) - 4) / 8; val_slots = vv + 8;
+    val_len = ((int32_t)ld32(vv) - 4) / 8;
+    if (pshift == 0 && !copy_all) val_slots = vv + 8;    // addressable in place
+    else {                                               // blocked window sums want the transposed layout: copy
+      pitch = (val_len + Pm) >> pshift;
+      uint64_t* slots = reinterpret_cast<uint64_t*>(sc.p);
+      const uint64_t* src = reinterpret_cast<const uint64_t*>(vv + 8);
+      for (int r = lane; r < val_len; r += 32) slots[TIDX(r)] = src[r];
+      val_slots = slots; sc.p += ((size_t)pitch << pshift) * 8;
+    }
   } else if (vwire == WIRE_DDV_CONST) {
     is_long = true; val_len = (int32_t)ld32(vv + 8); val_init = (int64_t)ld64_a4(vv + 12); val_slope = (int32_t)ld32(vv + 20);
+    pitch = (val_len + Pm) >> pshift;
     int64_t* slots = reinterpret_cast<int64_t*>(sc.p);
-    for (int r = lane; r < val_len; r += 32) slots[r] = val_init + (int64_t)(int32_t)((uint32_t)val_slope * (uint32_t)r);
-    val_slots = slots; sc.p += (size_t)val_len * 8;
+    for (int r = lane; r < val_len; r += 32) slots[TIDX(r)] = val_init + (int64_t)(int32_t)((uint32_t)val_slope * (uint32_t)r);
+    val_slots = slots; sc.p += ((size_t)pitch << pshift) * 8;
   } else if (vwire == WIRE_DDV) {
     is_long = true;
     const uint8_t* in = vv + 20;
@@ -178,15 +203,18 @@ __device__ __forceinline__ int resolve_chunk(const uint8_t* rec, const ChunkEntr
     const int nbits = (iw >> 16) & 0x7f; const bool sgn = (iw >> 23) & 1;
     val_len = int_length(in);
     val_init = (int64_t)ld64(vv + 8); val_slope = (int32_t)ld32(vv + 16);
+    pitch = (val_len + Pm) >> pshift;
     int64_t* slots = reinterpret_cast<int64_t*>(sc.p);
-    for (int r = lane; r < val_len; r += 32) slots[r] = val_init + (int64_t)val_slope * r + (int64_t)int_apply(in, nbits, sgn, r);
-    val_slots = slots; sc.p += (size_t)val_len * 8;
+    for (int r = lane; r < val_len; r += 32) slots[TIDX(r)] = val_init + (int64_t)val_slope * r + (int64_t)int_apply(in, nbits, sgn, r);
+    val_slots = slots; sc.p += ((size_t)pitch << pshift) * 8;
   } else if (vwire == WIRE_XOR) {
     val_len = (int32_t)ld32(vv + XOR_OFF_N);
+    pitch = (val_len + Pm) >> pshift;
     double* slots = reinterpret_cast<double*>(sc.p);
-    xor_decode_warp(vv, slots, lane);
-    val_slots = slots; sc.p += (size_t)val_len * 8;
+    xor_decode_warp(vv, slots, lane, pshift, pitch);
+    val_slots = slots; sc.p += ((size_t)pitch << pshift) * 8;
   } else err = err ? err : FILO_DEV_ERR_VAL_WIRE;
+#undef TIDX
   __syncwarp();
   if (err) return err;
   if (val_len <= 0 || ts_len <= 0) return FILO_DEV_ERR_EMPTY;
@@ -195,11 +223,20 @@ __device__ __forceinline__ int resolve_chunk(const uint8_t* rec, const ChunkEntr
     d->ts_slots = ts_slots; d->val_slots = val_slots; d->corr_slots = nullptr;
     d->ts_init = ts_init; d->val_init = val_init; d->ts_slope = ts_slope; d->val_slope = val_slope;
     d->num_rows = e->num_rows; d->ts_len = ts_len; d->val_len = val_len;
-    d->val_is_long = is_long; d->dropped = dropped; d->pad0 = d->pad1 = 0;
+    d->val_is_long = is_long; d->dropped = dropped; d->pshift = (uint8_t)((val_slots == (const void*)(vv + 8)) ? 0 : pshift);
+    d->pitch = pitch; d->kA = 0; d->kB = -1; d->sA = 0; d->Wr = 0;
+    // row search may use 32-bit arithmetic when no Int wrap can occur in slope * n (DeltaDeltaVector.scala:241-253)
+    d->fast32 = (ts_slots == nullptr && ts_slope > 0 && (int64_t)ts_slope * ((int64_t)ts_len + 1) < 0x7fffffffLL) ? 1 : 0;
     d->upd_last = 0; d->upd_corr = 0;
   }
   __syncwarp();
   if (lane == 0) { d->first_val = slot_value(*d, 0); d->last_val = slot_value(*d, val_len - 1); }
+  if (pshift != 0) {                                     // blocked reductions want to know whether NaN bookkeeping is needed
+    bool any = false;
+    if (!is_long) for (int r = lane; r < val_len; r += 32) any |= is_nan(slot_value(*d, r));
+    const unsigned m = __ballot_sync(0xffffffffu, any);
+    if (lane == 0) d->has_nan = m != 0;
+  } else if (lane == 0) d->has_nan = 1;
   // ---- CorrectingDoubleVectorReader.corrected / updateCorrection (DoubleVector.scala:325-342, 375-391)
   if (dropped && need_corrected) {
     double* cs = reinterpret_cast<double*>(sc.p);
@@ -236,16 +273,21 @@ __device__ __forceinline__ int resolve_chunk(const uint8_t* rec, const ChunkEntr
 // first row with ts >= t (== len if none): binarySearch(...) & 0x7fffffff;  *exact = bit 31 clear
 __device__ __forceinline__ int ts_search(const ChunkDesc& c, int64_t item, bool& exact) {
   if (c.ts_slots == nullptr) {                            // DeltaDeltaConstDataReader.binarySearch, DeltaDeltaVector.scala:245-253
-    const int64_t slope = (int64_t)c.ts_slope;
     const int32_t len = c.ts_len;
+    if (c.fast32) {
+      // slope > 0 and slope*(len+1) < 2^31: same quotient as the reference's truncating Long division, in 32-bit arithmetic
+      const int64_t diff = item - c.ts_init;
+      if (diff <= 0) { exact = (diff == 0); return 0; }
+      const uint32_t slope = (uint32_t)c.ts_slope;
+      if (diff > (int64_t)(len - 1) * (int64_t)slope) { exact = false; return len; }
+      const uint32_t g = ((uint32_t)diff + slope - 1) / slope;
+      exact = (g * slope == (uint32_t)diff);
+      return (int)g;
+    }
+    const int64_t slope = (int64_t)c.ts_slope;
     int32_t guess;
     if (slope == 0) guess = (item <= c.ts_init) ? 0 : len;
-    else {
-      const int64_t num = item - c.ts_init + (slope - 1);
-      // 32-bit fast path when the operands are small (the common case); identical truncating quotient
-      if (num >= 0 && num <= 0x7fffffffLL && slope > 0) guess = (int32_t)((uint32_t)num / (uint32_t)slope);
-      else guess = (int32_t)(num / slope);
-    }
+    else guess = (int32_t)((item - c.ts_init + (slope - 1)) / slope);
     if (guess < 0) { exact = false; return 0; }
     if (guess >= len) { exact = false; return len; }
     const int64_t at = c.ts_init + (int64_t)(int32_t)((uint32_t)c.ts_slope * (uint32_t)guess);
@@ -279,14 +321,14 @@ __device__ __forceinline__ double chunk_sum(const ChunkDesc& c, int s, int e, in
   if (c.val_is_long) {
     const int64_t* lv = reinterpret_cast<const int64_t*>(c.val_slots);
     int64_t resid = 0;
-    for (int r = s; r <= e; ++r) resid += lv[r] - (c.val_init + (int64_t)c.val_slope * r);
+    for (int r = s; r <= e; ++r) resid += lv[tidx(c, r)] - (c.val_init + (int64_t)c.val_slope * r);
     cnt = e - s + 1;
     return slope_sum(c.val_init, c.val_slope, s, e) + (double)resid;
   }
   const double* dv = reinterpret_cast<const double*>(c.val_slots);
   double sum = 0.0; int n = 0;
   // NaN-seeded sum that skips NaN == (0.0 + v1 + v2 ...) over non-NaN values, NaN if there are none
-  for (int r = s; r <= e; ++r) { double v = dv[r]; if (v == v) { sum += v; ++n; } }
+  for (int r = s; r <= e; ++r) { double v = dv[tidx(c, r)]; if (v == v) { sum += v; ++n; } }
   cnt = n;
   return n ? sum : __longlong_as_double(0x7ff8000000000000LL);
 }

@@ -8,6 +8,7 @@
 #define FILO_DEV_ERR_SCRATCH 4
 #include "scan_device.cuh"
 #include "kernels.h"
+#include "scan_fast.cuh"
 
 namespace filo {
 
@@ -59,7 +60,7 @@ scan_series_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
                    QueryParams q, double* __restrict__ out,
                    uint8_t* gscratch, uint32_t scratch_bytes, int use_smem,
                    unsigned long long* d_counters, int* d_err) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t gw = (int64_t)blockIdx.x * SCAN_WARPS + warp, nw = (int64_t)gridDim.x * SCAN_WARPS;
   uint8_t* scratch = use_smem ? smem + (size_t)warp * scratch_bytes : gscratch + (size_t)gw * scratch_bytes;
@@ -92,7 +93,7 @@ scan_agg_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ r
                 QueryParams q, int agg_op, double* __restrict__ pval, uint32_t* __restrict__ pcnt,
                 uint8_t* gscratch, uint32_t scratch_bytes, uint32_t acc_bytes, int use_smem,
                 unsigned long long* d_counters, int* d_err) {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t gw = (int64_t)blockIdx.x * SCAN_WARPS + warp, nw = (int64_t)gridDim.x * SCAN_WARPS;
   const uint32_t per_warp = scratch_bytes + acc_bytes;
@@ -249,8 +250,150 @@ __global__ void fill_items_kernel(const int64_t* __restrict__ group_start, const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// v2 kernels (scan_fast.cuh): TMA-staged records + blocked window reductions.  Per-warp shared memory:
+//   [mbarrier 16 B][record staging buffer rec_cap][result transpose stage][accumulators (agg only)][decode scratch]
+// One staging buffer per warp: the record is dead as soon as its chunks are resolved into scratch, so the bulk copy of the
+// NEXT series is issued right after resolve and overlaps the whole window phase of the current one.
+// ---------------------------------------------------------------------------------------------------------------
+struct WarpStage {
+  uint64_t* bar; uint8_t* buf; uint32_t cap; uint32_t parity; bool staged;
+  const uint8_t* arena; const int64_t* rec_off;
+  __device__ __forceinline__ void issue(int64_t series, int lane) {        // all lanes call; lane 0 issues
+    const int64_t o = rec_off[series];
+    const uint32_t bytes = (uint32_t)(rec_off[series + 1] - o);
+    staged = cap != 0 && bytes <= cap;
+    if (staged && lane == 0) { mbar_expect_tx(bar, bytes); tma_load_1d(buf, arena + o, bytes, bar); }
+  }
+  __device__ __forceinline__ const uint8_t* acquire(int64_t series) {       // record of `series`, previously issued
+    if (!staged) return arena + rec_off[series];
+    mbar_wait(bar, parity); parity ^= 1;
+    return buf;
+  }
+};
+
+__global__ void __launch_bounds__(FAST_WARPS * 32)
+scan_series_kernel_v2(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, int64_t n_series,
+                      QueryParams q, double* __restrict__ out, uint32_t rec_cap, uint32_t scratch_bytes,
+                      unsigned long long* d_counters, int* d_err) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t gw = (int64_t)blockIdx.x * FAST_WARPS + warp, nw = (int64_t)gridDim.x * FAST_WARPS;
+  const uint32_t per_warp = 16 + rec_cap + STAGE_BYTES + scratch_bytes;
+  uint8_t* base = smem + (size_t)warp * per_warp;
+  WarpStage st{reinterpret_cast<uint64_t*>(base), base + 16, rec_cap, 0, false, arena, rec_off};
+  double* stage = reinterpret_cast<double*>(base + 16 + rec_cap);
+  uint8_t* scratch = base + 16 + rec_cap + STAGE_BYTES;
+  if (lane == 0) { mbar_init(st.bar, 1); mbar_fence_init(); }
+  __syncwarp();
+  int64_t rows = 0, bytes = 0;
+  int64_t i = gw;
+  if (i < n_series) st.issue(i, lane);
+  for (; i < n_series; i += nw) {
+    const uint8_t* rec = st.acquire(i);
+    double* o = out + (size_t)i * q.T;
+    int err;
+    const int64_t inext = i + nw;
+    process_series(rec, q, scratch, scratch_bytes, stage, lane, err, rows, bytes,
+                   [&](int k, double v, bool valid) { if (valid) o[k] = v; },
+                   [&]() { if (inext < n_series) st.issue(inext, lane); });
+    if (err) {
+      if (lane == 0) report_error(d_err, err, i);
+      __syncwarp();
+      if (inext < n_series) st.issue(inext, lane);      // process_series returned before its release hook ran
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && (rows | bytes)) { atomicAdd(&d_counters[0], (unsigned long long)rows); atomicAdd(&d_counters[1], (unsigned long long)bytes); }
+}
+
+__global__ void __launch_bounds__(FAST_WARPS * 32)
+scan_agg_kernel_v2(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, const int32_t* __restrict__ order,
+                   const int64_t* __restrict__ item_begin, int64_t n_items,
+                   QueryParams q, int agg_op, double* __restrict__ pval, uint32_t* __restrict__ pcnt,
+                   uint32_t rec_cap, uint32_t scratch_bytes, uint32_t acc_bytes,
+                   unsigned long long* d_counters, int* d_err) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t gw = (int64_t)blockIdx.x * FAST_WARPS + warp, nw = (int64_t)gridDim.x * FAST_WARPS;
+  const uint32_t per_warp = 16 + rec_cap + STAGE_BYTES + acc_bytes + scratch_bytes;
+  uint8_t* base = smem + (size_t)warp * per_warp;
+  WarpStage st{reinterpret_cast<uint64_t*>(base), base + 16, rec_cap, 0, false, arena, rec_off};
+  double* stage = reinterpret_cast<double*>(base + 16 + rec_cap);
+  double* acc = reinterpret_cast<double*>(base + 16 + rec_cap + STAGE_BYTES);
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(base + 16 + rec_cap + STAGE_BYTES + (size_t)q.T * 8);
+  uint8_t* scratch = base + 16 + rec_cap + STAGE_BYTES + acc_bytes;
+  if (lane == 0) { mbar_init(st.bar, 1); mbar_fence_init(); }
+  __syncwarp();
+  const double ident = agg_op == AGG_MIN ? __longlong_as_double(0x7ff0000000000000LL)
+                     : agg_op == AGG_MAX ? __longlong_as_double(0xfff0000000000000LL) : 0.0;
+  int64_t rows = 0, bytes = 0;
+  // flattened (item, position) walk so that the next series to prefetch is always known
+  int64_t it = gw;
+  int64_t pos = 0, pend = 0;
+  auto advance_item = [&]() { while (it < n_items) { pos = item_begin[it]; pend = item_begin[it + 1]; if (pos < pend) return true; it += nw; } return false; };
+  bool have = advance_item();
+  if (have) st.issue(order ? order[pos] : pos, lane);
+  while (have) {
+    for (int k = lane; k < q.T; k += 32) { acc[k] = ident; cnt[k] = 0; }
+    __syncwarp();
+    const int64_t my_item = it;
+    while (true) {
+      const int64_t i = order ? order[pos] : pos;
+      // next series in walk order
+      int64_t npos = pos + 1, nit = it, npend = pend; bool nhave = true;
+      if (npos >= pend) { nit = it + nw; nhave = false; while (nit < n_items) { npos = item_begin[nit]; npend = item_begin[nit + 1]; if (npos < npend) { nhave = true; break; } nit += nw; } }
+      const int64_t inext = nhave ? (order ? order[npos] : npos) : -1;
+      const uint8_t* rec = st.acquire(i);
+      int err;
+      process_series(rec, q, scratch, scratch_bytes, stage, lane, err, rows, bytes,
+                     [&](int k, double v, bool valid) {
+                       if (valid && v == v) {              // RowAggregators skip NaN (SumRowAggregator.scala:22-29 ...)
+                         double a = acc[k];
+                         if (agg_op == AGG_MIN) a = v < a ? v : a;
+                         else if (agg_op == AGG_MAX) a = v > a ? v : a;
+                         else if (agg_op != AGG_COUNT) a += v;
+                         acc[k] = a; cnt[k] += 1;
+                       }
+                     },
+                     [&]() { if (inext >= 0) st.issue(inext, lane); });
+      if (err) {
+        if (lane == 0) report_error(d_err, err, i);
+        __syncwarp();
+        if (inext >= 0) st.issue(inext, lane);
+      }
+      __syncwarp();
+      const bool same_item = nhave && nit == it;
+      pos = npos; pend = npend; it = nit; have = nhave;
+      if (!same_item) break;
+    }
+    double* pv = pval + (size_t)my_item * q.T; uint32_t* pc = pcnt + (size_t)my_item * q.T;
+    for (int k = lane; k < q.T; k += 32) { pv[k] = acc[k]; pc[k] = cnt[k]; }
+    __syncwarp();
+  }
+  if (lane == 0 && (rows | bytes)) { atomicAdd(&d_counters[0], (unsigned long long)rows); atomicAdd(&d_counters[1], (unsigned long long)bytes); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host-callable launchers
 // ---------------------------------------------------------------------------------------------------------------
+cudaError_t launch_scan_series_v2(const ScanLaunch& L, double* out, uint32_t rec_cap) {
+  const size_t smem = (size_t)(16 + rec_cap + STAGE_BYTES + L.scratch_bytes) * FAST_WARPS;
+  cudaError_t e = cudaFuncSetAttribute(scan_series_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  scan_series_kernel_v2<<<L.grid, FAST_WARPS * 32, smem, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, rec_cap, L.scratch_bytes,
+                                                                      L.d_counters, L.d_err);
+  return cudaGetLastError();
+}
+cudaError_t launch_scan_agg_v2(const ScanLaunch& L, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg_op,
+                               double* pval, uint32_t* pcnt, uint32_t acc_bytes, uint32_t rec_cap) {
+  const size_t smem = (size_t)(16 + rec_cap + STAGE_BYTES + acc_bytes + L.scratch_bytes) * FAST_WARPS;
+  cudaError_t e = cudaFuncSetAttribute(scan_agg_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  scan_agg_kernel_v2<<<L.grid, FAST_WARPS * 32, smem, L.stream>>>(L.arena, L.rec_off, order, item_begin, n_items, L.q, agg_op, pval, pcnt,
+                                                                   rec_cap, L.scratch_bytes, acc_bytes, L.d_counters, L.d_err);
+  return cudaGetLastError();
+}
+size_t v2_smem_per_warp(uint32_t rec_cap, uint32_t scratch_bytes, uint32_t acc_bytes) { return 16 + (size_t)rec_cap + STAGE_BYTES + acc_bytes + scratch_bytes; }
 cudaError_t launch_scan_series(const ScanLaunch& L, double* out) {
   size_t smem = L.use_smem ? (size_t)L.scratch_bytes * SCAN_WARPS : 0;
   if (smem > 48 * 1024) {

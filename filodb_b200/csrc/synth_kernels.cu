@@ -20,6 +20,7 @@ filo_table* filo_internal_new_table();
 void filo_internal_set_arena(filo_table* t, uint8_t* d_arena, int64_t* d_rec_off, int64_t n_series, int64_t n_chunks, int64_t n_samples,
                              int64_t arena_bytes, int64_t algorithmic_bytes, int32_t max_rows, int32_t max_chunks, int32_t schema_flags);
 int32_t filo_internal_finish_table(filo_ctx* ctx, filo_table* t, const int32_t* d_group_ids, int32_t n_groups);
+void filo_internal_set_layout(filo_table* t, uint32_t max_rec_bytes, bool any_nonconst_ts, bool any_drop);
 cudaStream_t filo_internal_stream(filo_ctx* ctx);
 int filo_internal_device(filo_ctx* ctx);
 int32_t filo_internal_fail(filo_ctx* ctx, int32_t code, const char* msg);
@@ -354,11 +355,22 @@ extern "C" int32_t filo_synth_table(filo_ctx* ctx, const filo_synth_spec* sp, fi
   unsigned long long alg = 0;
   S_TRY(cudaMemcpyAsync(&alg, d_alg, 8, cudaMemcpyDeviceToHost, s));
   S_TRY(cudaStreamSynchronize(s));
+  uint32_t max_rec = 0;
+  if (S > 0) {
+    uint32_t* d_max = nullptr; S_TRY(cudaMalloc(&d_max, 4));
+    size_t tb = 0; cub::DeviceReduce::Max(nullptr, tb, d_bytes, d_max, (int)S, s);
+    void* t2 = nullptr; S_TRY(cudaMalloc(&t2, tb + 16));
+    S_TRY(cub::DeviceReduce::Max(t2, tb, d_bytes, d_max, (int)S, s));
+    S_TRY(cudaMemcpyAsync(&max_rec, d_max, 4, cudaMemcpyDeviceToHost, s));
+    S_TRY(cudaStreamSynchronize(s));
+    cudaFree(t2); cudaFree(d_max);
+  }
   cudaFree(tmp); cudaFree(d_bytes); cudaFree(d_wide); cudaFree(d_sin); cudaFree(d_alg);
   const int nch = (sp->rows_per_series + sp->rows_per_chunk - 1) / sp->rows_per_chunk;
   filo_table* t = filo_internal_new_table();
   filo_internal_set_arena(t, d_arena, d_off, S, S * nch, S * (int64_t)sp->rows_per_series, arena_bytes + (S + 1) * 8, (int64_t)alg,
                           sp->rows_per_series, nch, sp->schema_flags);
+  filo_internal_set_layout(t, max_rec, sp->ts_jitter_ms > 250, (sp->schema_flags & FILO_SCHEMA_CUMULATIVE) != 0);
   int32_t rc = filo_internal_finish_table(ctx, t, d_gid, sp->n_groups > 0 ? sp->n_groups : 1);
   cudaFree(d_gid);
   if (rc) { filo_table_free(ctx, t); return rc; }

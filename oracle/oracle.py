@@ -309,11 +309,16 @@ class Store:
     def algorithmic_bytes(self): return lib().fo_store_algorithmic_bytes(self.h)
 
     def query(self, fn, start, step, end, window, cumulative=False, inclusive=True, aggr=AGG_NONE, k=0,
-              group_ids=None, n_groups=1, threads=1, series_begin=0, series_end=-1):
+              group_ids=None, n_groups=1, threads=1, series_begin=0, series_end=-1, reuse_out=False):
         S = (self.num_series if series_end < 0 else series_end) - series_begin
         T = num_windows(start, step, end)
         if aggr == AGG_NONE:
-            out = np.zeros((S, T), np.float64); aux = None
+            if reuse_out and getattr(self, "_out", None) is not None and self._out.shape == (S, T):
+                out = self._out        # timing loops: do not pay page faults of a fresh [S x T] buffer every call
+            else:
+                out = np.zeros((S, T), np.float64)
+                if reuse_out: self._out = out
+            aux = None
         elif aggr in (AGG_TOPK, AGG_BOTTOMK):
             out = np.zeros((n_groups, T, k), np.float64); aux = np.zeros((n_groups, T, k), np.int64)
         else:

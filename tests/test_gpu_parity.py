@@ -11,12 +11,16 @@ pytestmark = pytest.mark.gpu
 NaN = float("nan")
 
 
-@pytest.fixture(scope="module")
-def gpu():
+@pytest.fixture(scope="module", params=["v2", "v1"])
+def gpu(request):
+    """Every test runs against both kernel generations: v2 (TMA-staged, blocked reductions; the default) and v1 (generic)."""
+    import os
     import filodb_b200.capi as capi
+    os.environ["FILO_KERNEL"] = request.param
     ctx = capi.Context(0)
     yield capi, ctx
     ctx.close()
+    os.environ.pop("FILO_KERNEL", None)
 
 
 def same_bits(a, b):
