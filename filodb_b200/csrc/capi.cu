@@ -461,12 +461,12 @@ extern "C" int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t
 
   // ---- kernel selection.  v2 (TMA-staged, blocked reductions) needs its whole per-warp working set in shared memory;
   //      v1 (generic, global-memory record reads, optional global scratch) takes everything else.  FILO_KERNEL=v1 forces v1.
-  const uint32_t acc_bytes = fused ? align_up((uint32_t)q.T * 12u, 16) : 0;
+  const uint32_t acc_bytes = fused ? align_up((uint32_t)q.T * 12u, 128) : 0;
   const bool delta_fn = (fn == FILO_FN_DELTA);
   const bool need_corr2 = need_corr && t->any_drop;
   uint32_t scratch2 = align_up((uint32_t)t->max_chunks * (uint32_t)CHUNK_DESC_BYTES, 16) +
                       ((uint32_t)t->max_rows + (uint32_t)t->max_chunks * 8u) * 8u * (1u + (t->any_nonconst_ts ? 1u : 0u) + (need_corr2 ? 1u : 0u));
-  scratch2 = align_up(scratch2 + 16, 16);
+  scratch2 = align_up(scratch2 + 16, 128);
   (void)delta_fn;
   const uint32_t rec_cap = align_up(t->max_rec_bytes + 16, 128);
   const size_t per_warp2 = v2_smem_per_warp(rec_cap, scratch2, acc_bytes);

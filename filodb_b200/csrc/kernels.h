@@ -8,6 +8,7 @@ namespace filo {
 
 constexpr int SCAN_WARPS = 4;          // warps (= series in flight) per CTA, v1 kernels
 constexpr int FAST_WARPS = 4;          // v2 kernels
+constexpr int FAST_MIN_CTAS = 4;       // register budget of the v2 kernels: 4 CTAs x 128 threads per SM (<= 128 regs/thread)
 constexpr int CHUNK_DESC_BYTES = 144;  // sizeof(ChunkDesc), scan_device.cuh
 constexpr int FILO_MAX_TOPK = 32;
 enum { AGG_NONE = 0, AGG_SUM = 1, AGG_AVG = 2, AGG_MIN = 3, AGG_MAX = 4, AGG_COUNT = 5, AGG_TOPK = 6, AGG_BOTTOMK = 7 };

@@ -30,18 +30,15 @@ struct __align__(16) ChunkDesc {
   int64_t ts_init, val_init;
   int32_t ts_slope, val_slope;
   int32_t num_rows, ts_len, val_len;
-  uint8_t val_is_long, dropped, pshift, fast32;   // pshift: log2 of the transposition period of val_slots (0 = linear)
+  uint8_t val_is_long, dropped, has_nan, fast32;  // has_nan: some double slot is NaN (always 1 when unknown)
   double upd_last, upd_corr;    // dropped chunk: last non-NaN value (or 0) and the chunk's total correction
   double first_val, last_val;   // apply(0), apply(len-1)
-  int32_t pitch;                // transposed value layout: slot(r) = (r & (P-1)) * pitch + (r >> pshift), P = 1 << pshift
   int32_t kA, kB;               // windows [kA, kB] whose only contributing rows are an unclamped row range of this chunk
   int32_t sA;                   // first row of window kA (rows advance by one per window in that interval)
   int32_t Wr;                   // last row - first row of every window in [kA, kB]
-  int32_t has_nan;              // some value of the chunk is NaN (double slots only)
-  int32_t pad_[2];
+  int32_t pad_[4];
 };
 static_assert(sizeof(ChunkDesc) == 144, "ChunkDesc size");
-__device__ __forceinline__ int tidx(const ChunkDesc& c, int r) { return (r & ((1 << c.pshift) - 1)) * c.pitch + (r >> c.pshift); }
 
 // ------------------------------------------------------------------------------------------------ loads
 __device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }
@@ -73,15 +70,15 @@ __device__ __forceinline__ int int_length(const uint8_t* in) {               // 
 // ------------------------------------------------------------------------------------------------ XOR decode
 // Warp-cooperative decode of a FiloXorDoubleVector into out[0..n).  Lane g handles NibblePack group g (8 values):
 // field extraction is independent per group thanks to the group-offset table; the XOR chain is a warp prefix-XOR.
-__device__ __forceinline__ void xor_decode_warp(const uint8_t* v, double* out, int lane, int pshift = 0, int pitch = 0) {
-  const int Pm = (1 << pshift) - 1;
+__device__ __forceinline__ bool xor_decode_warp(const uint8_t* v, double* out, int lane) {
+  bool any_nan = false;
   const int n = (int)ld32(v + XOR_OFF_N);
   const uint32_t w12 = ld32(v + XOR_OFF_NGROUPS);
   const int ng = w12 & 0xffff, payloadOff = w12 >> 16;
   const uint8_t* payload = v + payloadOff;
-  if (n <= 0) return;
+  if (n <= 0) return false;
   uint64_t carry = ld64(payload);
-  if (lane == 0) reinterpret_cast<uint64_t*>(out)[0] = carry;
+  if (lane == 0) { reinterpret_cast<uint64_t*>(out)[0] = carry; any_nan = (carry & 0x7fffffffffffffffull) > 0x7ff0000000000000ull; }
   const uint8_t* groups = payload + 8;
   const uint16_t* tab = reinterpret_cast<const uint16_t*>(v + XOR_OFF_GROUPTAB);
   for (int g0 = 0; g0 < ng; g0 += 32) {
@@ -129,28 +126,31 @@ __device__ __forceinline__ void xor_decode_warp(const uint8_t* v, double* out, i
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         int idx = 1 + g * 8 + i;
-        if (idx < n) reinterpret_cast<uint64_t*>(out)[(idx & Pm) * pitch + (idx >> pshift)] = basev ^ d[i];
+        if (idx < n) {
+          const uint64_t bits = basev ^ d[i];
+          reinterpret_cast<uint64_t*>(out)[idx] = bits;
+          any_nan |= (bits & 0x7fffffffffffffffull) > 0x7ff0000000000000ull;
+        }
       }
     }
     carry ^= __shfl_sync(0xffffffffu, incl, 31);
   }
+  return any_nan;
 }
 
 // ------------------------------------------------------------------------------------------------ chunk resolve
 struct ScratchCursor { uint8_t* p; };
 
 __device__ __forceinline__ double slot_value(const ChunkDesc& c, int r) {
-  if (c.val_is_long) return (double)reinterpret_cast<const int64_t*>(c.val_slots)[tidx(c, r)];   // DoubleLongWrapDataReader.apply
-  return reinterpret_cast<const double*>(c.val_slots)[tidx(c, r)];
+  if (c.val_is_long) return (double)reinterpret_cast<const int64_t*>(c.val_slots)[r];   // DoubleLongWrapDataReader.apply
+  return reinterpret_cast<const double*>(c.val_slots)[r];
 }
 
 // Resolves chunk `e` of the record into `d`; decodes into scratch as needed.  Returns an error code (0 = ok).
 // All lanes call it with identical arguments; stores to *d are done by lane 0 and published with __syncwarp.
 __device__ __forceinline__ int resolve_chunk(const uint8_t* rec, const ChunkEntry* e, ChunkDesc* d, ScratchCursor& sc,
-                                             bool need_corrected, int lane, int pshift = 0, bool copy_all = false) {
-  const int Pm = (1 << pshift) - 1;
-  int pitch = 0;
-#define TIDX(r) (((r) & Pm) * pitch + ((r) >> pshift))
+                                             bool need_corrected, int lane, bool copy_all = false) {
+  bool lane_nan = false; bool nan_known = false;
   const uint8_t* tv = rec + e->ts_off;
   const uint8_t* vv = rec + e->val_off;
   const uint32_t tw = ld32(tv + 4), vw = ld32(vv + 4);
@@ -182,20 +182,19 @@ __device__ __forceinline__ int resolve_chunk(const uint8_t* rec, const ChunkEntr
   const bool dropped = (vw >> 31) & 1;                   // PrimitiveVectorReader.dropped, BinaryVector.scala:530-531
   if (vwire == WIRE_RAW64) {
     val_len = ((int32_t)ld32(vv) - 4) / 8;
-    if (pshift == 0 && !copy_all) val_slots = vv + 8;    // addressable in place
-    else {                                               // blocked window sums want the transposed layout: copy
-      pitch = (val_len + Pm) >> pshift;
+    if (!copy_all) val_slots = vv + 8;                   // addressable in place
+    else {                                               // the staged record buffer is recycled right after resolve
       uint64_t* slots = reinterpret_cast<uint64_t*>(sc.p);
       const uint64_t* src = reinterpret_cast<const uint64_t*>(vv + 8);
-      for (int r = lane; r < val_len; r += 32) slots[TIDX(r)] = src[r];
-      val_slots = slots; sc.p += ((size_t)pitch << pshift) * 8;
+      for (int r = lane; r < val_len; r += 32) { const uint64_t b = src[r]; slots[r] = b; lane_nan |= (b & 0x7fffffffffffffffull) > 0x7ff0000000000000ull; }
+      nan_known = true;
+      val_slots = slots; sc.p += (size_t)val_len * 8;
     }
   } else if (vwire == WIRE_DDV_CONST) {
     is_long = true; val_len = (int32_t)ld32(vv + 8); val_init = (int64_t)ld64_a4(vv + 12); val_slope = (int32_t)ld32(vv + 20);
-    pitch = (val_len + Pm) >> pshift;
     int64_t* slots = reinterpret_cast<int64_t*>(sc.p);
-    for (int r = lane; r < val_len; r += 32) slots[TIDX(r)] = val_init + (int64_t)(int32_t)((uint32_t)val_slope * (uint32_t)r);
-    val_slots = slots; sc.p += ((size_t)pitch << pshift) * 8;
+    for (int r = lane; r < val_len; r += 32) slots[r] = val_init + (int64_t)(int32_t)((uint32_t)val_slope * (uint32_t)r);
+    val_slots = slots; sc.p += (size_t)val_len * 8; nan_known = true;
   } else if (vwire == WIRE_DDV) {
     is_long = true;
     const uint8_t* in = vv + 20;
@@ -203,18 +202,16 @@ __device__ __forceinline__ int resolve_chunk(const uint8_t* rec, const ChunkEntr
     const int nbits = (iw >> 16) & 0x7f; const bool sgn = (iw >> 23) & 1;
     val_len = int_length(in);
     val_init = (int64_t)ld64(vv + 8); val_slope = (int32_t)ld32(vv + 16);
-    pitch = (val_len + Pm) >> pshift;
     int64_t* slots = reinterpret_cast<int64_t*>(sc.p);
-    for (int r = lane; r < val_len; r += 32) slots[TIDX(r)] = val_init + (int64_t)val_slope * r + (int64_t)int_apply(in, nbits, sgn, r);
-    val_slots = slots; sc.p += ((size_t)pitch << pshift) * 8;
+    for (int r = lane; r < val_len; r += 32) slots[r] = val_init + (int64_t)val_slope * r + (int64_t)int_apply(in, nbits, sgn, r);
+    val_slots = slots; sc.p += (size_t)val_len * 8; nan_known = true;
   } else if (vwire == WIRE_XOR) {
     val_len = (int32_t)ld32(vv + XOR_OFF_N);
-    pitch = (val_len + Pm) >> pshift;
     double* slots = reinterpret_cast<double*>(sc.p);
-    xor_decode_warp(vv, slots, lane, pshift, pitch);
-    val_slots = slots; sc.p += ((size_t)pitch << pshift) * 8;
+    lane_nan = xor_decode_warp(vv, slots, lane); nan_known = true;
+    val_slots = slots; sc.p += (size_t)val_len * 8;
   } else err = err ? err : FILO_DEV_ERR_VAL_WIRE;
-#undef TIDX
+  const unsigned nan_ballot = __ballot_sync(0xffffffffu, lane_nan);
   __syncwarp();
   if (err) return err;
   if (val_len <= 0 || ts_len <= 0) return FILO_DEV_ERR_EMPTY;
@@ -223,20 +220,14 @@ __device__ __forceinline__ int resolve_chunk(const uint8_t* rec, const ChunkEntr
     d->ts_slots = ts_slots; d->val_slots = val_slots; d->corr_slots = nullptr;
     d->ts_init = ts_init; d->val_init = val_init; d->ts_slope = ts_slope; d->val_slope = val_slope;
     d->num_rows = e->num_rows; d->ts_len = ts_len; d->val_len = val_len;
-    d->val_is_long = is_long; d->dropped = dropped; d->pshift = (uint8_t)((val_slots == (const void*)(vv + 8)) ? 0 : pshift);
-    d->pitch = pitch; d->kA = 0; d->kB = -1; d->sA = 0; d->Wr = 0;
+    d->val_is_long = is_long; d->dropped = dropped; d->has_nan = (uint8_t)((!nan_known || nan_ballot != 0) ? 1 : 0);
+    d->kA = 0; d->kB = -1; d->sA = 0; d->Wr = 0;
     // row search may use 32-bit arithmetic when no Int wrap can occur in slope * n (DeltaDeltaVector.scala:241-253)
     d->fast32 = (ts_slots == nullptr && ts_slope > 0 && (int64_t)ts_slope * ((int64_t)ts_len + 1) < 0x7fffffffLL) ? 1 : 0;
     d->upd_last = 0; d->upd_corr = 0;
   }
   __syncwarp();
   if (lane == 0) { d->first_val = slot_value(*d, 0); d->last_val = slot_value(*d, val_len - 1); }
-  if (pshift != 0) {                                     // blocked reductions want to know whether NaN bookkeeping is needed
-    bool any = false;
-    if (!is_long) for (int r = lane; r < val_len; r += 32) any |= is_nan(slot_value(*d, r));
-    const unsigned m = __ballot_sync(0xffffffffu, any);
-    if (lane == 0) d->has_nan = m != 0;
-  } else if (lane == 0) d->has_nan = 1;
   // ---- CorrectingDoubleVectorReader.corrected / updateCorrection (DoubleVector.scala:325-342, 375-391)
   if (dropped && need_corrected) {
     double* cs = reinterpret_cast<double*>(sc.p);
@@ -321,14 +312,14 @@ __device__ __forceinline__ double chunk_sum(const ChunkDesc& c, int s, int e, in
   if (c.val_is_long) {
     const int64_t* lv = reinterpret_cast<const int64_t*>(c.val_slots);
     int64_t resid = 0;
-    for (int r = s; r <= e; ++r) resid += lv[tidx(c, r)] - (c.val_init + (int64_t)c.val_slope * r);
+    for (int r = s; r <= e; ++r) resid += lv[r] - (c.val_init + (int64_t)c.val_slope * r);
     cnt = e - s + 1;
     return slope_sum(c.val_init, c.val_slope, s, e) + (double)resid;
   }
   const double* dv = reinterpret_cast<const double*>(c.val_slots);
   double sum = 0.0; int n = 0;
   // NaN-seeded sum that skips NaN == (0.0 + v1 + v2 ...) over non-NaN values, NaN if there are none
-  for (int r = s; r <= e; ++r) { double v = dv[tidx(c, r)]; if (v == v) { sum += v; ++n; } }
+  for (int r = s; r <= e; ++r) { double v = dv[r]; if (v == v) { sum += v; ++n; } }
   cnt = n;
   return n ? sum : __longlong_as_double(0x7ff8000000000000LL);
 }

@@ -271,18 +271,19 @@ struct WarpStage {
   }
 };
 
-__global__ void __launch_bounds__(FAST_WARPS * 32)
+template <int CLS>
+__global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_CTAS)
 scan_series_kernel_v2(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, int64_t n_series,
                       QueryParams q, double* __restrict__ out, uint32_t rec_cap, uint32_t scratch_bytes,
                       unsigned long long* d_counters, int* d_err) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t gw = (int64_t)blockIdx.x * FAST_WARPS + warp, nw = (int64_t)gridDim.x * FAST_WARPS;
-  const uint32_t per_warp = 16 + rec_cap + STAGE_BYTES + scratch_bytes;
+  const uint32_t per_warp = WARP_HDR_BYTES + rec_cap + STAGE_BYTES + scratch_bytes;
   uint8_t* base = smem + (size_t)warp * per_warp;
-  WarpStage st{reinterpret_cast<uint64_t*>(base), base + 16, rec_cap, 0, false, arena, rec_off};
-  double* stage = reinterpret_cast<double*>(base + 16 + rec_cap);
-  uint8_t* scratch = base + 16 + rec_cap + STAGE_BYTES;
+  WarpStage st{reinterpret_cast<uint64_t*>(base), base + WARP_HDR_BYTES, rec_cap, 0, false, arena, rec_off};
+  double* stage = reinterpret_cast<double*>(base + WARP_HDR_BYTES + rec_cap);
+  uint8_t* scratch = base + WARP_HDR_BYTES + rec_cap + STAGE_BYTES;
   if (lane == 0) { mbar_init(st.bar, 1); mbar_fence_init(); }
   __syncwarp();
   int64_t rows = 0, bytes = 0;
@@ -293,7 +294,7 @@ scan_series_kernel_v2(const uint8_t* __restrict__ arena, const int64_t* __restri
     double* o = out + (size_t)i * q.T;
     int err;
     const int64_t inext = i + nw;
-    process_series(rec, q, scratch, scratch_bytes, stage, lane, err, rows, bytes,
+    process_series<CLS>(rec, q, scratch, scratch_bytes, stage, lane, err, rows, bytes,
                    [&](int k, double v, bool valid) { if (valid) o[k] = v; },
                    [&]() { if (inext < n_series) st.issue(inext, lane); });
     if (err) {
@@ -306,7 +307,8 @@ scan_series_kernel_v2(const uint8_t* __restrict__ arena, const int64_t* __restri
   if (lane == 0 && (rows | bytes)) { atomicAdd(&d_counters[0], (unsigned long long)rows); atomicAdd(&d_counters[1], (unsigned long long)bytes); }
 }
 
-__global__ void __launch_bounds__(FAST_WARPS * 32)
+template <int CLS>
+__global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_CTAS)
 scan_agg_kernel_v2(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, const int32_t* __restrict__ order,
                    const int64_t* __restrict__ item_begin, int64_t n_items,
                    QueryParams q, int agg_op, double* __restrict__ pval, uint32_t* __restrict__ pcnt,
@@ -315,13 +317,13 @@ scan_agg_kernel_v2(const uint8_t* __restrict__ arena, const int64_t* __restrict_
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t gw = (int64_t)blockIdx.x * FAST_WARPS + warp, nw = (int64_t)gridDim.x * FAST_WARPS;
-  const uint32_t per_warp = 16 + rec_cap + STAGE_BYTES + acc_bytes + scratch_bytes;
+  const uint32_t per_warp = WARP_HDR_BYTES + rec_cap + STAGE_BYTES + acc_bytes + scratch_bytes;
   uint8_t* base = smem + (size_t)warp * per_warp;
-  WarpStage st{reinterpret_cast<uint64_t*>(base), base + 16, rec_cap, 0, false, arena, rec_off};
-  double* stage = reinterpret_cast<double*>(base + 16 + rec_cap);
-  double* acc = reinterpret_cast<double*>(base + 16 + rec_cap + STAGE_BYTES);
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(base + 16 + rec_cap + STAGE_BYTES + (size_t)q.T * 8);
-  uint8_t* scratch = base + 16 + rec_cap + STAGE_BYTES + acc_bytes;
+  WarpStage st{reinterpret_cast<uint64_t*>(base), base + WARP_HDR_BYTES, rec_cap, 0, false, arena, rec_off};
+  double* stage = reinterpret_cast<double*>(base + WARP_HDR_BYTES + rec_cap);
+  double* acc = reinterpret_cast<double*>(base + WARP_HDR_BYTES + rec_cap + STAGE_BYTES);
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(base + WARP_HDR_BYTES + rec_cap + STAGE_BYTES + (size_t)q.T * 8);
+  uint8_t* scratch = base + WARP_HDR_BYTES + rec_cap + STAGE_BYTES + acc_bytes;
   if (lane == 0) { mbar_init(st.bar, 1); mbar_fence_init(); }
   __syncwarp();
   const double ident = agg_op == AGG_MIN ? __longlong_as_double(0x7ff0000000000000LL)
@@ -345,7 +347,7 @@ scan_agg_kernel_v2(const uint8_t* __restrict__ arena, const int64_t* __restrict_
       const int64_t inext = nhave ? (order ? order[npos] : npos) : -1;
       const uint8_t* rec = st.acquire(i);
       int err;
-      process_series(rec, q, scratch, scratch_bytes, stage, lane, err, rows, bytes,
+      process_series<CLS>(rec, q, scratch, scratch_bytes, stage, lane, err, rows, bytes,
                      [&](int k, double v, bool valid) {
                        if (valid && v == v) {              // RowAggregators skip NaN (SumRowAggregator.scala:22-29 ...)
                          double a = acc[k];
@@ -376,24 +378,43 @@ scan_agg_kernel_v2(const uint8_t* __restrict__ arena, const int64_t* __restrict_
 // ---------------------------------------------------------------------------------------------------------------
 // host-callable launchers
 // ---------------------------------------------------------------------------------------------------------------
-cudaError_t launch_scan_series_v2(const ScanLaunch& L, double* out, uint32_t rec_cap) {
-  const size_t smem = (size_t)(16 + rec_cap + STAGE_BYTES + L.scratch_bytes) * FAST_WARPS;
-  cudaError_t e = cudaFuncSetAttribute(scan_series_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int CLS>
+static cudaError_t launch_series_v2_cls(const ScanLaunch& L, double* out, uint32_t rec_cap, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(scan_series_kernel_v2<CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  scan_series_kernel_v2<<<L.grid, FAST_WARPS * 32, smem, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, rec_cap, L.scratch_bytes,
-                                                                      L.d_counters, L.d_err);
+  scan_series_kernel_v2<CLS><<<L.grid, FAST_WARPS * 32, smem, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, rec_cap, L.scratch_bytes,
+                                                                           L.d_counters, L.d_err);
+  return cudaGetLastError();
+}
+cudaError_t launch_scan_series_v2(const ScanLaunch& L, double* out, uint32_t rec_cap) {
+  const size_t smem = (size_t)(WARP_HDR_BYTES + rec_cap + STAGE_BYTES + L.scratch_bytes) * FAST_WARPS;
+  switch (fn_class_of(L.q.fn, L.q.cumulative)) {
+    case CLASS_SUM: return launch_series_v2_cls<CLASS_SUM>(L, out, rec_cap, smem);
+    case CLASS_MINMAX: return launch_series_v2_cls<CLASS_MINMAX>(L, out, rec_cap, smem);
+    case CLASS_COUNTER: return launch_series_v2_cls<CLASS_COUNTER>(L, out, rec_cap, smem);
+    default: return launch_series_v2_cls<CLASS_POINT>(L, out, rec_cap, smem);
+  }
+}
+template <int CLS>
+static cudaError_t launch_agg_v2_cls(const ScanLaunch& L, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg_op,
+                                     double* pval, uint32_t* pcnt, uint32_t acc_bytes, uint32_t rec_cap, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(scan_agg_kernel_v2<CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  scan_agg_kernel_v2<CLS><<<L.grid, FAST_WARPS * 32, smem, L.stream>>>(L.arena, L.rec_off, order, item_begin, n_items, L.q, agg_op, pval, pcnt,
+                                                                        rec_cap, L.scratch_bytes, acc_bytes, L.d_counters, L.d_err);
   return cudaGetLastError();
 }
 cudaError_t launch_scan_agg_v2(const ScanLaunch& L, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg_op,
                                double* pval, uint32_t* pcnt, uint32_t acc_bytes, uint32_t rec_cap) {
-  const size_t smem = (size_t)(16 + rec_cap + STAGE_BYTES + acc_bytes + L.scratch_bytes) * FAST_WARPS;
-  cudaError_t e = cudaFuncSetAttribute(scan_agg_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  scan_agg_kernel_v2<<<L.grid, FAST_WARPS * 32, smem, L.stream>>>(L.arena, L.rec_off, order, item_begin, n_items, L.q, agg_op, pval, pcnt,
-                                                                   rec_cap, L.scratch_bytes, acc_bytes, L.d_counters, L.d_err);
-  return cudaGetLastError();
+  const size_t smem = (size_t)(WARP_HDR_BYTES + rec_cap + STAGE_BYTES + acc_bytes + L.scratch_bytes) * FAST_WARPS;
+  switch (fn_class_of(L.q.fn, L.q.cumulative)) {
+    case CLASS_SUM: return launch_agg_v2_cls<CLASS_SUM>(L, order, item_begin, n_items, agg_op, pval, pcnt, acc_bytes, rec_cap, smem);
+    case CLASS_MINMAX: return launch_agg_v2_cls<CLASS_MINMAX>(L, order, item_begin, n_items, agg_op, pval, pcnt, acc_bytes, rec_cap, smem);
+    case CLASS_COUNTER: return launch_agg_v2_cls<CLASS_COUNTER>(L, order, item_begin, n_items, agg_op, pval, pcnt, acc_bytes, rec_cap, smem);
+    default: return launch_agg_v2_cls<CLASS_POINT>(L, order, item_begin, n_items, agg_op, pval, pcnt, acc_bytes, rec_cap, smem);
+  }
 }
-size_t v2_smem_per_warp(uint32_t rec_cap, uint32_t scratch_bytes, uint32_t acc_bytes) { return 16 + (size_t)rec_cap + STAGE_BYTES + acc_bytes + scratch_bytes; }
+size_t v2_smem_per_warp(uint32_t rec_cap, uint32_t scratch_bytes, uint32_t acc_bytes) { return WARP_HDR_BYTES + (size_t)rec_cap + STAGE_BYTES + acc_bytes + scratch_bytes; }
 cudaError_t launch_scan_series(const ScanLaunch& L, double* out) {
   size_t smem = L.use_smem ? (size_t)L.scratch_bytes * SCAN_WARPS : 0;
   if (smem > 48 * 1024) {
