@@ -3,6 +3,7 @@
 #include "../../include/filo_b200.h"
 #include "kernels.h"
 #include "host_util.h"
+#include "scan_tile_layout.h"
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <atomic>
@@ -494,17 +495,43 @@ extern "C" int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t
     if (!use_smem) CUDA_TRY(ctx, tmp.alloc((void**)&gscratch, (size_t)L.grid * SCAN_WARPS * (scratch + acc_bytes)));
     L.gscratch = gscratch; L.scratch_bytes = scratch; L.use_smem = use_smem;
   }
+  // v3 tile kernel (scan_tile.cuh): SUM-class functions over regular series; irregular series are appended to a list that the
+  // v2 kernel processes right after, into the same output buffer.  FILO_KERNEL=v2 disables the tile kernel.
+  const bool want_v2 = force && std::string(force) == "v2";
+  const int fn_cls = fn_class_of(fn, q.cumulative);
+  const TileSmem TL = tile_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)q.T);
+  const bool use_tile = use_v2 && !want_v2 && fn_cls == CLASS_SUM && t->n_series > 0 &&
+                        (size_t)TL.total + 1024 <= std::min<size_t>(ctx->max_smem_optin, 227 * 1024);
+  auto run_per_series = [&](double* outp) -> int32_t {
+    if (use_tile) {
+      int64_t* d_list = nullptr; unsigned long long* d_cnt = nullptr;
+      CUDA_TRY(ctx, tmp.alloc((void**)&d_list, (size_t)t->n_series * 8));
+      CUDA_TRY(ctx, tmp.alloc((void**)&d_cnt, 16));
+      CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, 16, s));
+      ScanLaunch LT = L;
+      const int ctas_per_sm = ((size_t)TL.total + 1024) * 2 <= (size_t)228 * 1024 ? 2 : 1;
+      const int64_t n_tiles = (t->n_series + TILE_NS - 1) / TILE_NS;
+      LT.grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * ctas_per_sm));
+      CUDA_TRY(ctx, launch_scan_tile_sum(LT, outp, TL, d_list, d_cnt));
+      ScanLaunch LF = L; LF.list = d_list; LF.list_count = d_cnt;
+      CUDA_TRY(ctx, launch_scan_series_v2(LF, outp, rec_cap_used));
+      launches += 2;
+    } else {
+      CUDA_TRY(ctx, use_v2 ? launch_scan_series_v2(L, outp, rec_cap_used) : launch_scan_series(L, outp));
+      launches += 1;
+    }
+    return FILO_OK;
+  };
   if (stats) CUDA_TRY(ctx, cudaEventRecord(e0, s));
   if (agg == FILO_AGG_NONE) {
-    CUDA_TRY(ctx, use_v2 ? launch_scan_series_v2(L, (double*)d_out_values, rec_cap_used) : launch_scan_series(L, (double*)d_out_values));
-    launches = 1;
+    { int32_t rc = run_per_series((double*)d_out_values); if (rc) return rc; }
   } else if (!fused) {
     double* per = nullptr;
     CUDA_TRY(ctx, tmp.alloc((void**)&per, (size_t)t->n_series * q.T * 8));
-    CUDA_TRY(ctx, use_v2 ? launch_scan_series_v2(L, per, rec_cap_used) : launch_scan_series(L, per));
+    { int32_t rc = run_per_series(per); if (rc) return rc; }
     CUDA_TRY(ctx, launch_topk(per, t->grouped ? t->d_order : nullptr, t->d_group_start, t->n_groups, q.T, k, agg == FILO_AGG_BOTTOMK,
                               (double*)d_out_values, (int64_t*)d_out_aux, s));
-    launches = 2;
+    launches += 1;
   } else {
     double* pval = nullptr; uint32_t* pcnt = nullptr;
     CUDA_TRY(ctx, tmp.alloc((void**)&pval, (size_t)t->n_items * q.T * 8));

@@ -20,7 +20,6 @@
 
 namespace filo {
 
-enum { FN_LAST = 0, FN_RATE, FN_INCREASE, FN_DELTA, FN_SUM, FN_AVG, FN_COUNT, FN_MIN, FN_MAX, FN_TIMESTAMP };
 
 struct __align__(16) ChunkDesc {
   int64_t start_time, end_time;
@@ -36,7 +35,9 @@ struct __align__(16) ChunkDesc {
   int32_t kA, kB;               // windows [kA, kB] whose only contributing rows are an unclamped row range of this chunk
   int32_t sA;                   // first row of window kA (rows advance by one per window in that interval)
   int32_t Wr;                   // last row - first row of every window in [kA, kB]
-  int32_t pad_[4];
+  int32_t blk0, blk_n;          // blocked-reduction work list: first block index / number of blocks of this chunk
+  int32_t nrows_eff;            // min(num_rows, ts_len, val_len)
+  int32_t pad_;
 };
 static_assert(sizeof(ChunkDesc) == 144, "ChunkDesc size");
 
@@ -129,7 +130,7 @@ __device__ __forceinline__ bool xor_decode_warp(const uint8_t* v, double* out, i
         if (idx < n) {
           const uint64_t bits = basev ^ d[i];
           reinterpret_cast<uint64_t*>(out)[idx] = bits;
-          any_nan |= (bits & 0x7fffffffffffffffull) > 0x7ff0000000000000ull;
+          any_nan |= ((uint32_t)(bits >> 32) & 0x7ff00000u) == 0x7ff00000u;    // NaN or Inf: conservative, 2 instructions
         }
       }
     }
@@ -221,7 +222,7 @@ __device__ __forceinline__ int resolve_chunk(const uint8_t* rec, const ChunkEntr
     d->ts_init = ts_init; d->val_init = val_init; d->ts_slope = ts_slope; d->val_slope = val_slope;
     d->num_rows = e->num_rows; d->ts_len = ts_len; d->val_len = val_len;
     d->val_is_long = is_long; d->dropped = dropped; d->has_nan = (uint8_t)((!nan_known || nan_ballot != 0) ? 1 : 0);
-    d->kA = 0; d->kB = -1; d->sA = 0; d->Wr = 0;
+    d->kA = 0; d->kB = -1; d->sA = 0; d->Wr = 0; d->blk0 = 0; d->blk_n = 0; d->nrows_eff = 0;
     // row search may use 32-bit arithmetic when no Int wrap can occur in slope * n (DeltaDeltaVector.scala:241-253)
     d->fast32 = (ts_slots == nullptr && ts_slope > 0 && (int64_t)ts_slope * ((int64_t)ts_len + 1) < 0x7fffffffLL) ? 1 : 0;
     d->upd_last = 0; d->upd_corr = 0;

@@ -5,14 +5,15 @@
 //      previous series was being reduced (one staging buffer + one mbarrier per warp);
 //   2. chunks are resolved/decoded into per-warp scratch (scan_device.cuh); afterwards the staging buffer is dead and the
 //      bulk copy of the NEXT series is issued;
-//   3. "interior" windows — windows whose only contributing rows are an unclamped row range [s, s+Wr] of ONE chunk with
-//      const-DDV timestamps whose slope equals the query step (the vast majority in practice) — are reduced BLK_R at a time
-//      per lane: the lane walks rows s0 .. s0+Wr+R-1 once and feeds each row to the accumulators of the windows containing
-//      it.  Every accumulator still sees its rows in row order starting from 0.0, i.e. exactly the reference's sequential sum
-//      (DoubleVector.scala:243-253), but a row is loaded once per R windows.  R = 15 (odd): lane base rows are 15 apart, so the
-//      64-bit shared-memory reads of a warp are bank-conflict-free in the plain linear layout;
-//   4. the remaining windows (series start/end, chunk boundaries, irregular timestamps) are enumerated densely and take the
-//      general path (eval_window), which restates the reference state machine literally.
+//   3. "single-chunk" windows — windows whose contributing rows all belong to ONE chunk with const-DDV timestamps whose slope
+//      equals the query step (the vast majority in practice; the row range may be clamped by the chunk's first/last row) —
+//      are reduced BLK_R at a time per lane: the lane walks rows s0 .. s0+Wr+R-1 once and feeds each row to the accumulators
+//      of the windows containing it.  Every accumulator still sees its rows in row order starting from 0.0, i.e. exactly the
+//      reference's sequential sum (DoubleVector.scala:243-253), but a row is loaded once per R windows.  Rows outside the
+//      chunk are fed as +0.0, which is an exact no-op for an accumulator that started at +0.0.  R = 15 (odd): lane base rows
+//      are 15 apart, so the 64-bit shared-memory reads of a warp are bank-conflict-free in the plain linear layout;
+//   4. the remaining windows (rows from two chunks, irregular timestamps) are enumerated densely and take the general path
+//      (eval_window), which restates the reference state machine literally.
 // Results leave through a Sink called by all lanes (lane-consecutive windows on the bulk path: coalesced stores).
 #pragma once
 #include "scan_device.cuh"
@@ -21,7 +22,8 @@ namespace filo {
 
 constexpr int BLK_R = 15;                // windows per lane in the blocked reduction (odd => conflict-free linear layout)
 constexpr int STAGE_PITCH = 33;          // doubles; stage[j * 33 + lane]
-constexpr int STAGE_BYTES = (BLK_R * STAGE_PITCH * 8 + 127) / 128 * 128;
+constexpr int STAGE_VALS_BYTES = BLK_R * STAGE_PITCH * 8;             // 3960
+constexpr int STAGE_BYTES = (STAGE_VALS_BYTES + 256 + 127) / 128 * 128;   // + per-block {k0, nwin} for the transposed read-out
 constexpr int WARP_HDR_BYTES = 128;      // mbarrier slot; keeps every per-warp region 128-byte aligned (TMA destination needs 16)
 
 // ------------------------------------------------------------------------------------------------ TMA / mbarrier
@@ -49,88 +51,95 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ------------------------------------------------------------------------------------------------ integer helpers
-__device__ __forceinline__ int64_t floor_div(int64_t a, int64_t b) {        // b > 0
-  if (a >= 0 && a <= 0xffffffffLL && b <= 0xffffffffLL) return (int64_t)((uint32_t)a / (uint32_t)b);
-  if (a < 0 && -a <= 0x7fffffffLL && b <= 0x7fffffffLL) { const uint32_t na = (uint32_t)(-a), ub = (uint32_t)b; return -(int64_t)((na + ub - 1) / ub); }
-  int64_t q = a / b; if ((a % b) != 0 && a < 0) --q; return q;
-}
-__device__ __forceinline__ int64_t ceil_div(int64_t a, int64_t b) {         // b > 0
-  if (a > 0 && a <= 0x7fffffffLL && b <= 0x7fffffffLL) return (int64_t)(((uint32_t)a + (uint32_t)b - 1) / (uint32_t)b);
-  return -floor_div(-a, b);
-}
+// Division by the (kernel-invariant) query step: double reciprocal + one correction, exact for |a| < 2^31, d < 2^31.
+struct StepDiv {
+  int64_t d; double inv;
+  __device__ __forceinline__ void init(int64_t dd) { d = dd; inv = 1.0 / (double)dd; }
+  __device__ __forceinline__ uint32_t udiv(uint32_t n) const {
+    uint32_t q = __double2uint_rz(__dmul_rn((double)n, inv));
+    const int32_t r = (int32_t)(n - q * (uint32_t)d);
+    if (r < 0) --q; else if ((uint32_t)r >= (uint32_t)d) ++q;
+    return q;
+  }
+  __device__ __forceinline__ int64_t floor_div(int64_t a) const {
+    if (d < 0x7fffffffLL) {
+      if (a >= 0 && a < 0x7fffffffLL) return (int64_t)udiv((uint32_t)a);
+      if (a < 0 && a > -0x3fffffffLL) return -(int64_t)udiv((uint32_t)(-a) + (uint32_t)d - 1);
+    }
+    int64_t q = a / d; if ((a % d) != 0 && a < 0) --q; return q;
+  }
+  __device__ __forceinline__ int64_t ceil_div(int64_t a) const { return -floor_div(-a); }
+};
 
 // x / y for a loop-invariant y, with rcp = RN(1/y) precomputed: q0 = RN(x*rcp); r = x - q0*y (exact, FMA); q = RN(q0 + r*rcp).
 // This is the final correction step of the IEEE division sequence (Markstein) and returns the correctly rounded quotient
 // whenever q0 is a normal number well inside the exponent range; anything else takes the real division.
 __device__ __forceinline__ double div_invariant(double x, double y, double rcp) {
   const double q0 = __dmul_rn(x, rcp);
-  const double aq = fabs(q0);
-  if (aq > 1e-290 && aq < 1e290) { const double r = __fma_rn(-q0, y, x); return __fma_rn(r, rcp, q0); }
+  const uint32_t ex = ((uint32_t)__double2hiint(q0) >> 20) & 0x7ff;     // biased exponent
+  if (ex > 64u && ex < 1983u) { const double r = __fma_rn(-q0, y, x); return __fma_rn(r, rcp, q0); }
   return x / y;
 }
 
-enum { CLASS_SUM = 0, CLASS_MINMAX = 1, CLASS_POINT = 2, CLASS_COUNTER = 3 };
-__host__ __device__ __forceinline__ int fn_class_of(int fn, int cumulative) {
-  switch (fn) {
-    case FN_SUM: case FN_AVG: case FN_COUNT: return CLASS_SUM;
-    case FN_RATE: case FN_INCREASE: return cumulative ? CLASS_COUNTER : CLASS_SUM;
-    case FN_DELTA: return CLASS_COUNTER;
-    case FN_MIN: case FN_MAX: return CLASS_MINMAX;
-    default: return CLASS_POINT;
-  }
-}
-
-// Interior window interval of chunk c.  Only for const-DDV timestamps with 0 < slope == step.  D[0..n) resolved chunks.
-// Window k is interior to chunk c iff (all affine in k, SURVEY.md Appendix B / DESIGN.md §3.3):
-//   wStart_k >= ts[0]                      rows unclamped from below
+// Single-chunk window interval [kA, kB] of chunk c (const-DDV timestamps with 0 < slope == step).  Window k belongs to it
+// iff, all affine in k (SURVEY.md Appendix B / DESIGN.md §3.3):
+//   wEnd_k   >= ts[0]                        the (unclamped) row range reaches into the chunk from below
+//   wStart_k <= ts[nrows-1]                  ... and from above
 //   wStart_k >  max(endTime_{c-1}, last ts of c-1)   previous chunk neither in the window's chunk set nor contributing rows
-//   wEnd_k   <  ts[0] + nrows*slope        rows unclamped from above
-//   wEnd_k   <  first ts of chunk c+1      next chunk contributes no row (it may be in the chunk set; it is a no-op there)
-//   wStart_k <= endTime_c                  chunk c still in the chunk set (ChunkSetInfo.scala:481-483)
-// Lanes 0..2 (then 0..1) each do one division; results are broadcast.
-__device__ __forceinline__ void interior_interval(ChunkDesc* D, int n, int c, const QueryParams& q, int lane) {
+//   wEnd_k   <  first ts of chunk c+1        next chunk contributes no row (it may be in the chunk set; it is a no-op there)
+//   wStart_k <= endTime_c                    chunk c still in the chunk set (ChunkSetInfo.scala:481-483)
+// sA = unclamped first row of window kA (may be negative), Wr = last - first row of every window.
+// Lanes 0..4 (then 0..1) each do one division; results are broadcast.
+__device__ __forceinline__ void chunk_interval(ChunkDesc* D, int n, int c, const QueryParams& q, const StepDiv& sd, int lane) {
   ChunkDesc& d = D[c];
   int64_t winDur = q.inclusive ? q.window : q.window - 1; if (winDur < 0) winDur = 0;
-  const int64_t S0 = q.start - winDur, E0 = q.start, step = q.step;
+  const int64_t S0 = q.start - winDur, E0 = q.start;
   const int64_t slope = d.ts_slope, init = d.ts_init;
   int nrows = d.num_rows < d.ts_len ? d.num_rows : d.ts_len; if (d.val_len < nrows) nrows = d.val_len;
-  int64_t L = init;
-  if (c > 0) {
-    const ChunkDesc& p = D[c - 1];
-    int64_t pm = p.end_time; const int64_t plast = ts_apply(p, p.ts_len - 1); if (plast > pm) pm = plast;
-    if (pm + 1 > L) L = pm + 1;
-  }
-  int64_t U = init + (int64_t)nrows * slope - 1;
-  if (c + 1 < n) { const int64_t nfirst = D[c + 1].ts_init; if (nfirst - 1 < U) U = nfirst - 1; }
   int64_t v = 0;
-  if (lane == 0) v = ceil_div(L - S0, step);
-  else if (lane == 1) v = floor_div(U - E0, step);
-  else if (lane == 2) v = floor_div(d.end_time - S0, step);
-  int64_t kA = __shfl_sync(0xffffffffu, v, 0), kB = __shfl_sync(0xffffffffu, v, 1);
-  const int64_t kB2 = __shfl_sync(0xffffffffu, v, 2);
-  if (kB2 < kB) kB = kB2;
+  if (lane == 0) v = sd.ceil_div(init - E0);                                           // wEnd_k >= ts[0]
+  else if (lane == 1) {                                                                 // wStart_k > prevMax
+    v = 0;
+    if (c > 0) {
+      const ChunkDesc& p = D[c - 1];
+      int64_t pm = p.end_time; const int64_t plast = ts_apply(p, p.ts_len - 1); if (plast > pm) pm = plast;
+      v = sd.ceil_div(pm + 1 - S0);
+    }
+  }
+  else if (lane == 2) v = sd.floor_div(init + (int64_t)(nrows - 1) * slope - S0);       // wStart_k <= ts[nrows-1]
+  else if (lane == 3) v = (c + 1 < n) ? sd.floor_div(D[c + 1].ts_init - 1 - E0) : (int64_t)q.T;   // wEnd_k < next first ts
+  else if (lane == 4) v = sd.floor_div(d.end_time - S0);                                // wStart_k <= endTime_c
+  int64_t kA = __shfl_sync(0xffffffffu, v, 0);
+  { const int64_t t = __shfl_sync(0xffffffffu, v, 1); if (t > kA) kA = t; }
+  int64_t kB = __shfl_sync(0xffffffffu, v, 2);
+  { const int64_t t = __shfl_sync(0xffffffffu, v, 3); if (t < kB) kB = t; }
+  { const int64_t t = __shfl_sync(0xffffffffu, v, 4); if (t < kB) kB = t; }
   if (kA < 0) kA = 0;
   if (kB > q.T - 1) kB = q.T - 1;
   int64_t w = 0;
   if (kA <= kB) {
-    if (lane == 0) w = ceil_div(S0 + kA * step - init, slope);          // first row of window kA
-    else if (lane == 1) w = floor_div(E0 + kA * step - init, slope);    // last row of window kA
+    if (lane == 0) w = sd.ceil_div(S0 + kA * q.step - init);          // unclamped first row of window kA (slope == step)
+    else if (lane == 1) w = sd.floor_div(E0 + kA * q.step - init);    // unclamped last row of window kA
   }
   const int64_t sA = __shfl_sync(0xffffffffu, w, 0), eA = __shfl_sync(0xffffffffu, w, 1);
   if (lane == 0) {
     if (kA <= kB && eA >= sA) { d.kA = (int32_t)kA; d.kB = (int32_t)kB; d.sA = (int32_t)sA; d.Wr = (int32_t)(eA - sA); }
     else { d.kA = 0; d.kB = -1; d.sA = 0; d.Wr = 0; }
+    d.nrows_eff = nrows;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ blocked reductions
-// `base` points at the lane's first row; rows beyond `nvalid-1` (tail block only) are clamped and feed discarded windows.
-// Accumulator j (window k0 + j) takes rows i in [j, j + Wr], in row order.  Requires Wr >= BLK_R - 1.
+// Lane's block: windows j = 0..R-1, window j takes rows r0 + i for i in [j, j + Wr], in row order.  Rows outside [0, nrows)
+// are fed as +0.0 (exact no-op).  Requires Wr >= BLK_R - 1.  With CHECK_NAN, NaN rows are skipped and counted out.
 template <bool CHECK_NAN>
-__device__ __forceinline__ void blocked_sum(const double* __restrict__ base, int nvalid, int Wr, double acc[BLK_R], int cnt[BLK_R]) {
+__device__ __forceinline__ void blocked_sum(const double* __restrict__ slots, int r0, int nrows, int Wr, double acc[BLK_R], int cnt[BLK_R]) {
   auto load = [&](int i, int& ok) -> double {
-    double v = base[i < nvalid ? i : nvalid - 1];
-    if (CHECK_NAN) { ok = (v == v) ? 1 : 0; if (!ok) v = 0.0; } else ok = 1;   // NaN rows are skipped (DoubleVector.scala:243-253)
+    const int r = r0 + i;
+    ok = ((unsigned)r < (unsigned)nrows) ? 1 : 0;
+    double v = 0.0;
+    if (ok) v = slots[r];
+    if (CHECK_NAN) { if (v != v) { v = 0.0; ok = 0; } }     // DoubleVector.scala:243-253
     return v;
   };
 #pragma unroll
@@ -154,26 +163,29 @@ __device__ __forceinline__ void blocked_sum(const double* __restrict__ base, int
   }
   if (!CHECK_NAN) {
 #pragma unroll
-    for (int j = 0; j < BLK_R; ++j) cnt[j] = Wr + 1;
+    for (int j = 0; j < BLK_R; ++j) {                      // rows of window j inside the chunk
+      int lo = r0 + j; if (lo < 0) lo = 0;
+      int hi = r0 + j + Wr; if (hi > nrows - 1) hi = nrows - 1;
+      cnt[j] = hi >= lo ? hi - lo + 1 : 0;
+    }
   }
 }
 
 template <bool IS_MIN>
-__device__ __forceinline__ void blocked_minmax(const ChunkDesc& c, int r0, int Wr, double acc[BLK_R]) {
-  const int rmax = c.val_len - 1;
+__device__ __forceinline__ void blocked_minmax(const ChunkDesc& c, int r0, int nrows, int Wr, double acc[BLK_R]) {
   const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll
   for (int j = 0; j < BLK_R; ++j) acc[j] = NaNv;
   for (int i = 0; i <= Wr + BLK_R - 1; ++i) {
-    int r = r0 + i; if (r > rmax) r = rmax;
-    const double v = slot_value(c, r);
+    const int r = r0 + i;
+    const double v = ((unsigned)r < (unsigned)nrows) ? slot_value(c, r) : NaNv;     // NaN is ignored by min/maxIgnoreNaN
 #pragma unroll
     for (int j = 0; j < BLK_R; ++j)
       if (i >= j && i <= j + Wr) acc[j] = IS_MIN ? min_ignore_nan(acc[j], v) : max_ignore_nan(acc[j], v);
   }
 }
 
-// finalize one interior window of a SUM-class function from (chunk sum over non-NaN rows, non-NaN count)
+// finalize one single-chunk window of a SUM-class function from (chunk sum over non-NaN rows, non-NaN count)
 struct SumFinish {
   int fn; double div, rcp;
   __device__ __forceinline__ void init(const QueryParams& q) {
@@ -186,13 +198,10 @@ struct SumFinish {
     const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
     // exactly one contributing chunk: sum = isNaN(cs) ? NaN : 0 + cs, count = nn   (AggrOverTimeFunctions.scala:568-570)
     const double sum = nn ? cs : NaNv;
-    switch (fn) {
-      case FN_SUM: case FN_INCREASE: return sum;
-      case FN_RATE: return __dmul_rn(div_invariant(sum, div, rcp), 1000.0);
-      case FN_AVG: return nn > 0 ? sum / (double)nn : sum;            // AggrOverTimeFunctions.scala:1000
-      case FN_COUNT: return (double)nn;
-    }
-    return NaNv;
+    if (fn == FN_RATE) return __dmul_rn(div_invariant(sum, div, rcp), 1000.0);
+    if (fn == FN_SUM || fn == FN_INCREASE) return sum;
+    if (fn == FN_AVG) return nn > 0 ? sum / (double)nn : sum;            // AggrOverTimeFunctions.scala:1000
+    return (double)nn;                                                   // FN_COUNT
   }
 };
 
@@ -240,7 +249,10 @@ __device__ __forceinline__ void process_series(const uint8_t* rec, const QueryPa
         bytes_scanned += (int64_t)ld32(rec + E[cLo + c].ts_off) + 4 + (int64_t)ld32(rec + E[cLo + c].val_off) + 4;
       }
     }
-    if (regular) for (int c = 0; c < n; ++c) interior_interval(D, n, c, q, lane);
+    if (regular) {
+      StepDiv sd; sd.init(q.step);
+      for (int c = 0; c < n; ++c) chunk_interval(D, n, c, q, sd, lane);
+    }
   }
   __syncwarp();
   release();          // every byte of the record that is still needed now lives in scratch: the staging buffer may be refilled
@@ -256,78 +268,126 @@ __device__ __forceinline__ void process_series(const uint8_t* rec, const QueryPa
     return;
   }
 
-  // ---- phase 1: interior windows, chunk by chunk
+  // ---- phase 1: single-chunk windows
   SumFinish fin; fin.init(q);
-  for (int c = 0; c < n; ++c) {
-    const ChunkDesc& d = D[c];
-    const int kA = d.kA, kB = d.kB;
-    if (kA > kB) continue;
-    const int Wr = d.Wr;
-    const int nwin = kB - kA + 1;
-    if (CLS == CLASS_COUNTER) {
-      // single chunk, no correction carried in (RangeFunction.scala:138-163 with correctionMeta == NoCorrection)
-      int64_t winDur = q.inclusive ? q.window : q.window - 1; if (winDur < 0) winDur = 0;
-      for (int w0 = 0; w0 < nwin; w0 += 32) {
-        const int w = w0 + lane;
-        double res = __longlong_as_double(0x7ff8000000000000LL);
-        if (w < nwin) {
-          const int k = kA + w, s = d.sA + w, e = s + Wr;
-          const bool skip = (q.fn != FN_DELTA) && s == 0 && e == 0 && is_nan(slot_value(d, 0));
-          if (!skip && e > s) {
-            const int64_t tS = d.ts_init + (int64_t)d.ts_slope * s, tE = d.ts_init + (int64_t)d.ts_slope * e;
-            double loV, hiV;
-            if (q.fn == FN_DELTA || !d.dropped) { loV = slot_value(d, s); hiV = slot_value(d, e); }
-            else { loV = d.corr_slots[s]; hiV = d.corr_slots[e]; }
-            const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - winDur;
-            const int64_t cws = q.inclusive ? wStart : wStart - 1;
-            res = extrapolated_rate(cws, wEnd, e - s + 1, tS, loV, tE, hiV, q.fn != FN_DELTA, q.fn == FN_RATE);
-          }
-        }
-        sink(kA + w, res, w < nwin);
-      }
-      continue;
+  if (CLS == CLASS_SUM) {
+    // (a) all chunks whose windows can be blocked (double slots, Wr >= R-1, same Wr) share ONE block list, so that the lanes of
+    //     a warp stay busy even when a chunk has few windows
+    int uniWr = -1, total_blocks = 0; bool any_nan = false;
+    for (int c = 0; c < n; ++c) {
+      const ChunkDesc& d = D[c];
+      const bool elig = d.kA <= d.kB && !d.val_is_long && d.Wr >= BLK_R - 1 && (uniWr < 0 || d.Wr == uniWr);
+      if (elig) { uniWr = d.Wr; any_nan |= d.has_nan != 0; }
+      if (lane == 0) { D[c].blk0 = total_blocks; D[c].blk_n = elig ? (d.kB - d.kA + BLK_R) / BLK_R : 0; }
+      if (elig) total_blocks += (d.kB - d.kA + BLK_R) / BLK_R;
     }
-    if (CLS == CLASS_SUM && (d.val_is_long || Wr < BLK_R - 1)) {
-      // DoubleLongWrapDataReader.sum is a closed form + exact Long residual sum (DeltaDeltaVector.scala:190-194), and short
-      // windows do not amortise a block: one window per lane, rows s..s+Wr known without any search
-      for (int w0 = 0; w0 < nwin; w0 += 32) {
-        const int w = w0 + lane;
-        double res = 0.0;
-        if (w < nwin) { int cnt; const double cs = chunk_sum(d, d.sA + w, d.sA + w + Wr, cnt); res = fin(cs, cnt); }
-        sink(kA + w, res, w < nwin);
-      }
-      continue;
-    }
-    // blocked reductions: lane handles BLK_R consecutive windows
-    const int nblk = (nwin + BLK_R - 1) / BLK_R;
-    for (int b0 = 0; b0 < nblk; b0 += 32) {
-      const int b = b0 + lane;
+    __syncwarp();
+    int* stage_k0 = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(stage) + STAGE_VALS_BYTES);
+    int* stage_nw = stage_k0 + 32;
+    for (int B0 = 0; B0 < total_blocks; B0 += 32) {
+      const int B = B0 + lane;
       double acc[BLK_R]; int cnt[BLK_R];
-      if (b < nblk) {
+      int k0 = 0, nw = 0;
+      if (B < total_blocks) {
+        int c = 0;
+        if (n <= 4) { while (c + 1 < n && B >= D[c].blk0 + D[c].blk_n) ++c; }
+        else { int lo = 0, hi = n - 1; while (lo < hi) { const int m = (lo + hi + 1) >> 1; if (D[m].blk0 <= B) lo = m; else hi = m - 1; } c = lo;
+               while (c > 0 && D[c].blk_n == 0) --c; }
+        const ChunkDesc& d = D[c];
+        const int b = B - d.blk0;
         const int r0 = d.sA + b * BLK_R;
-        if (CLS == CLASS_SUM) {
-          const double* base = reinterpret_cast<const double*>(d.val_slots) + r0;
-          if (d.has_nan) blocked_sum<true>(base, d.val_len - r0, Wr, acc, cnt); else blocked_sum<false>(base, d.val_len - r0, Wr, acc, cnt);
+        const double* slots = reinterpret_cast<const double*>(d.val_slots);
+        if (any_nan) blocked_sum<true>(slots, r0, d.nrows_eff, uniWr, acc, cnt); else blocked_sum<false>(slots, r0, d.nrows_eff, uniWr, acc, cnt);
 #pragma unroll
-          for (int j = 0; j < BLK_R; ++j) acc[j] = fin(acc[j], cnt[j]);
-        } else if (q.fn == FN_MIN) blocked_minmax<true>(d, r0, Wr, acc);
-        else blocked_minmax<false>(d, r0, Wr, acc);
+        for (int j = 0; j < BLK_R; ++j) acc[j] = fin(acc[j], cnt[j]);
+        k0 = d.kA + b * BLK_R; nw = d.kB - k0 + 1; if (nw > BLK_R) nw = BLK_R;
       }
       // transpose through shared memory so that results leave lane-consecutive
 #pragma unroll
       for (int j = 0; j < BLK_R; ++j) stage[j * STAGE_PITCH + lane] = acc[j];
+      stage_k0[lane] = k0; stage_nw[lane] = nw;
       __syncwarp();
 #pragma unroll
       for (int m = 0; m < BLK_R; ++m) {
-        const int off = m * 32 + lane;                      // window offset within this group of 32*R
+        const int off = m * 32 + lane;
         const int bl = off / BLK_R, j = off - bl * BLK_R;
-        const int w = b0 * BLK_R + off;
-        sink(kA + w, stage[j * STAGE_PITCH + bl], w < nwin);
+        sink(stage_k0[bl] + j, stage[j * STAGE_PITCH + bl], j < stage_nw[bl]);
       }
       __syncwarp();
     }
+    // (b) the rest (DDV-as-long values: closed form + exact Long residual sum, DeltaDeltaVector.scala:190-194; short windows;
+    //     a chunk whose Wr differs): one window per lane, the clamped row range is known without any search
+    for (int c = 0; c < n; ++c) {
+      const ChunkDesc& d = D[c];
+      if (d.kA > d.kB || d.blk_n != 0) continue;
+      const int nwin = d.kB - d.kA + 1;
+      for (int w0 = 0; w0 < nwin; w0 += 32) {
+        const int w = w0 + lane;
+        double res = 0.0;
+        if (w < nwin) {
+          int s = d.sA + w, e = s + d.Wr; if (s < 0) s = 0; if (e > d.nrows_eff - 1) e = d.nrows_eff - 1;
+          int cnt = 0; double cs = 0.0;
+          if (s <= e) cs = chunk_sum(d, s, e, cnt);
+          res = fin(cs, cnt);
+        }
+        sink(d.kA + w, res, w < nwin);
+      }
+    }
+  } else {
+    for (int c = 0; c < n; ++c) {
+      const ChunkDesc& d = D[c];
+      const int kA = d.kA, kB = d.kB;
+      if (kA > kB) continue;
+      const int Wr = d.Wr;
+      const int nwin = kB - kA + 1;
+      if (CLS == CLASS_COUNTER) {
+        // single chunk, no correction carried in (RangeFunction.scala:138-163 with correctionMeta == NoCorrection)
+        int64_t winDur = q.inclusive ? q.window : q.window - 1; if (winDur < 0) winDur = 0;
+        for (int w0 = 0; w0 < nwin; w0 += 32) {
+          const int w = w0 + lane;
+          double res = __longlong_as_double(0x7ff8000000000000LL);
+          if (w < nwin) {
+            const int k = kA + w;
+            int s = d.sA + w, e = s + Wr; if (s < 0) s = 0; if (e > d.nrows_eff - 1) e = d.nrows_eff - 1;
+            const bool skip = (q.fn != FN_DELTA) && s == 0 && e == 0 && is_nan(slot_value(d, 0));
+            if (!skip && e > s) {
+              const int64_t tS = d.ts_init + (int64_t)d.ts_slope * s, tE = d.ts_init + (int64_t)d.ts_slope * e;
+              double loV, hiV;
+              if (q.fn == FN_DELTA || !d.dropped) { loV = slot_value(d, s); hiV = slot_value(d, e); }
+              else { loV = d.corr_slots[s]; hiV = d.corr_slots[e]; }
+              const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - winDur;
+              const int64_t cws = q.inclusive ? wStart : wStart - 1;
+              res = extrapolated_rate(cws, wEnd, e - s + 1, tS, loV, tE, hiV, q.fn != FN_DELTA, q.fn == FN_RATE);
+            }
+          }
+          sink(kA + w, res, w < nwin);
+        }
+        continue;
+      }
+      // CLASS_MINMAX: blocked, lane handles BLK_R consecutive windows
+      const int nblk = (nwin + BLK_R - 1) / BLK_R;
+      for (int b0 = 0; b0 < nblk; b0 += 32) {
+        const int b = b0 + lane;
+        double acc[BLK_R];
+        if (b < nblk) {
+          const int r0 = d.sA + b * BLK_R;
+          if (q.fn == FN_MIN) blocked_minmax<true>(d, r0, d.nrows_eff, Wr, acc); else blocked_minmax<false>(d, r0, d.nrows_eff, Wr, acc);
+        }
+#pragma unroll
+        for (int j = 0; j < BLK_R; ++j) stage[j * STAGE_PITCH + lane] = acc[j];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < BLK_R; ++m) {
+          const int off = m * 32 + lane;
+          const int bl = off / BLK_R, j = off - bl * BLK_R;
+          const int w = b0 * BLK_R + off;
+          sink(kA + w, stage[j * STAGE_PITCH + bl], w < nwin);
+        }
+        __syncwarp();
+      }
+    }
   }
-  // ---- phase 2: the windows outside every interior interval, enumerated densely, through the literal state machine
+  // ---- phase 2: the windows outside every single-chunk interval, enumerated densely, through the literal state machine
   int total = 0;
   { int prev = -1; for (int c = 0; c < n; ++c) { if (D[c].kA <= D[c].kB) { total += D[c].kA - prev - 1; prev = D[c].kB; } } total += q.T - prev - 1; }
   for (int u0 = 0; u0 < total; u0 += 32) {

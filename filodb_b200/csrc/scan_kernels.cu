@@ -9,6 +9,7 @@
 #include "scan_device.cuh"
 #include "kernels.h"
 #include "scan_fast.cuh"
+#include "scan_tile.cuh"
 
 namespace filo {
 
@@ -275,7 +276,9 @@ template <int CLS>
 __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_CTAS)
 scan_series_kernel_v2(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, int64_t n_series,
                       QueryParams q, double* __restrict__ out, uint32_t rec_cap, uint32_t scratch_bytes,
-                      unsigned long long* d_counters, int* d_err) {
+                      unsigned long long* d_counters, int* d_err,
+                      const int64_t* __restrict__ list, const unsigned long long* __restrict__ list_count) {
+  if (list) n_series = (int64_t)*list_count;             // fallback pass of the tile kernel: only the listed series
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t gw = (int64_t)blockIdx.x * FAST_WARPS + warp, nw = (int64_t)gridDim.x * FAST_WARPS;
@@ -287,20 +290,23 @@ scan_series_kernel_v2(const uint8_t* __restrict__ arena, const int64_t* __restri
   if (lane == 0) { mbar_init(st.bar, 1); mbar_fence_init(); }
   __syncwarp();
   int64_t rows = 0, bytes = 0;
-  int64_t i = gw;
-  if (i < n_series) st.issue(i, lane);
-  for (; i < n_series; i += nw) {
+  int64_t ii = gw;
+  if (ii < n_series) st.issue(list ? list[ii] : ii, lane);
+  for (; ii < n_series; ii += nw) {
+    const int64_t i = list ? list[ii] : ii;
     const uint8_t* rec = st.acquire(i);
     double* o = out + (size_t)i * q.T;
     int err;
-    const int64_t inext = i + nw;
+    const int64_t inext_i = ii + nw;
+    const bool has_next = inext_i < n_series;
+    const int64_t inext = has_next ? (list ? list[inext_i] : inext_i) : 0;
     process_series<CLS>(rec, q, scratch, scratch_bytes, stage, lane, err, rows, bytes,
                    [&](int k, double v, bool valid) { if (valid) o[k] = v; },
-                   [&]() { if (inext < n_series) st.issue(inext, lane); });
+                   [&]() { if (has_next) st.issue(inext, lane); });
     if (err) {
       if (lane == 0) report_error(d_err, err, i);
       __syncwarp();
-      if (inext < n_series) st.issue(inext, lane);      // process_series returned before its release hook ran
+      if (has_next) st.issue(inext, lane);      // process_series returned before its release hook ran
     }
     __syncwarp();
   }
@@ -383,7 +389,7 @@ static cudaError_t launch_series_v2_cls(const ScanLaunch& L, double* out, uint32
   cudaError_t e = cudaFuncSetAttribute(scan_series_kernel_v2<CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   scan_series_kernel_v2<CLS><<<L.grid, FAST_WARPS * 32, smem, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, rec_cap, L.scratch_bytes,
-                                                                           L.d_counters, L.d_err);
+                                                                           L.d_counters, L.d_err, L.list, L.list_count);
   return cudaGetLastError();
 }
 cudaError_t launch_scan_series_v2(const ScanLaunch& L, double* out, uint32_t rec_cap) {
@@ -413,6 +419,13 @@ cudaError_t launch_scan_agg_v2(const ScanLaunch& L, const int32_t* order, const 
     case CLASS_COUNTER: return launch_agg_v2_cls<CLASS_COUNTER>(L, order, item_begin, n_items, agg_op, pval, pcnt, acc_bytes, rec_cap, smem);
     default: return launch_agg_v2_cls<CLASS_POINT>(L, order, item_begin, n_items, agg_op, pval, pcnt, acc_bytes, rec_cap, smem);
   }
+}
+cudaError_t launch_scan_tile_sum(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count) {
+  cudaError_t e = cudaFuncSetAttribute(scan_tile_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total);
+  if (e != cudaSuccess) return e;
+  scan_tile_sum_kernel<<<L.grid, TILE_THREADS, T.total, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, T, fallback_list, fallback_count,
+                                                                     L.d_counters, L.d_err);
+  return cudaGetLastError();
 }
 size_t v2_smem_per_warp(uint32_t rec_cap, uint32_t scratch_bytes, uint32_t acc_bytes) { return WARP_HDR_BYTES + (size_t)rec_cap + STAGE_BYTES + acc_bytes + scratch_bytes; }
 cudaError_t launch_scan_series(const ScanLaunch& L, double* out) {

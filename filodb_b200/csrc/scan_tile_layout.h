@@ -1,0 +1,46 @@
+// Shared-memory layout of the v3 tile kernel (scan_tile.cuh); plain structs, usable from host code.
+#pragma once
+#include <stdint.h>
+#include "filo_record.h"
+#include "scan_params.h"
+namespace filo {
+constexpr int TILE_NS = 8;               // series per tile (even: keeps the bulk store 16-byte aligned for odd T)
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_MAXC = 4;             // chunks in range per series on the fast path
+constexpr int TILE_MAXG = 64;            // NibblePack groups per series on the fast path (64 * 8 = 512 rows)
+
+struct TileChunk {
+  int64_t init, end_time;
+  int32_t nrows, row_base;
+  int32_t kA, kB, sA, Wr;
+  uint32_t val_off; int32_t wire;
+  int32_t ngroups, grp_base;
+  int32_t blk0, blk_n;
+  int32_t has_nan, tlen;      // tlen: timestamp vector length
+  int32_t vlen, pad;          // vlen: value vector length
+};
+struct TileSeries {
+  int32_t n, regular, rec_off, nblocks, nrest, ngroups, nrows, pad;
+  TileChunk c[TILE_MAXC];
+};
+
+struct TileSmem {                         // byte offsets inside dynamic shared memory (all multiples of 128)
+  uint32_t rec, vals, out, desc, gtot, total;
+  uint32_t rec_cap, vals_pitch /*doubles per series*/, out_pitch /*doubles per series = T*/;
+};
+FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t T) {
+  TileSmem L;
+  L.rec_cap = align_up(TILE_NS * max_rec_bytes + 128, 128);
+  L.vals_pitch = (max_rows + 2 + 1) | 1;                       // odd pitch (doubles)
+  L.out_pitch = T;
+  uint32_t o = 128;                                            // mbarrier slot
+  L.rec = o; o += L.rec_cap;
+  L.vals = o; o += align_up(TILE_NS * L.vals_pitch * 8, 128);
+  L.out = o; o += align_up(TILE_NS * T * 8, 128);
+  L.desc = o; o += align_up(TILE_NS * (uint32_t)sizeof(TileSeries), 128);
+  L.gtot = o; o += TILE_NS * TILE_MAXG * 8;
+  L.total = o;
+  return L;
+}
+
+} // namespace filo

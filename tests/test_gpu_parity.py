@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 NaN = float("nan")
 
 
-@pytest.fixture(scope="module", params=["v2", "v1"])
+@pytest.fixture(scope="module", params=["v3", "v2", "v1"])
 def gpu(request):
     """Every test runs against both kernel generations: v2 (TMA-staged, blocked reductions; the default) and v1 (generic)."""
     import os
