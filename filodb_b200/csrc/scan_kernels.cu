@@ -420,12 +420,21 @@ cudaError_t launch_scan_agg_v2(const ScanLaunch& L, const int32_t* order, const 
     default: return launch_agg_v2_cls<CLASS_POINT>(L, order, item_begin, n_items, agg_op, pval, pcnt, acc_bytes, rec_cap, smem);
   }
 }
-cudaError_t launch_scan_tile_sum(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count) {
-  cudaError_t e = cudaFuncSetAttribute(scan_tile_sum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total);
+template <int FN>
+static cudaError_t launch_tile_fn(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count) {
+  cudaError_t e = cudaFuncSetAttribute(scan_tile_sum_kernel<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total);
   if (e != cudaSuccess) return e;
-  scan_tile_sum_kernel<<<L.grid, TILE_THREADS, T.total, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, T, fallback_list, fallback_count,
-                                                                     L.d_counters, L.d_err);
+  scan_tile_sum_kernel<FN><<<L.grid, TILE_THREADS, T.total, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, T, fallback_list, fallback_count,
+                                                                         L.d_counters, L.d_err);
   return cudaGetLastError();
+}
+cudaError_t launch_scan_tile_sum(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count) {
+  switch (L.q.fn) {
+    case FN_RATE: return launch_tile_fn<FN_RATE>(L, out, T, fallback_list, fallback_count);
+    case FN_AVG: return launch_tile_fn<FN_AVG>(L, out, T, fallback_list, fallback_count);
+    case FN_COUNT: return launch_tile_fn<FN_COUNT>(L, out, T, fallback_list, fallback_count);
+    default: return launch_tile_fn<FN_SUM>(L, out, T, fallback_list, fallback_count);      // FN_SUM, FN_INCREASE on a delta schema
+  }
 }
 size_t v2_smem_per_warp(uint32_t rec_cap, uint32_t scratch_bytes, uint32_t acc_bytes) { return WARP_HDR_BYTES + (size_t)rec_cap + STAGE_BYTES + acc_bytes + scratch_bytes; }
 cudaError_t launch_scan_series(const ScanLaunch& L, double* out) {

@@ -5,12 +5,12 @@
 // cp.async.bulk store.  Between the two, all 256 threads work on uniform work items:
 //   setup    warp w resolves series w: chunk range, regularity, single-chunk window intervals (scan_fast.cuh definitions)
 //   decode   item = (series, NibblePack group): field extraction + local XOR prefix; a per-series segmented prefix over the
-//            group totals; an apply pass.  Raw f64 vectors are copied.  NaN/Inf presence is recorded per chunk.
+//            group totals; an apply pass over the same items.  Raw f64 vectors are copied.  NaN/Inf presence is recorded.
 //   windows  item = (series, block of BLK_R single-chunk windows): register-blocked sequential sums (exact reference order);
 //            item = (series, other window): literal per-chunk fold for windows that take rows from two chunks.
 // A series is "regular" when every chunk in range has const-DDV timestamps with slope == step and XOR/raw double values,
 // with at most TILE_MAXC chunks and TILE_MAXG NibblePack groups; anything else is appended to a fallback list that the
-// generic v2/v1 kernel processes afterwards (same output buffer), so the result is always complete and identical.
+// generic v2 kernel processes afterwards (same output buffer), so the result is always complete and identical.
 #pragma once
 #include "scan_fast.cuh"
 #include "scan_tile_layout.h"
@@ -24,10 +24,22 @@ __device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint3
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// compile-time specialised finish of one single-chunk window (SumFinish of scan_fast.cuh with FN known)
+template <int FN>
+__device__ __forceinline__ double tile_finish(double cs, int nn, double div, double rcp) {
+  const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
+  if (FN == FN_COUNT) return (double)nn;
+  const double sum = nn ? cs : NaNv;
+  if (FN == FN_RATE) return __dmul_rn(div_invariant(sum, div, rcp), 1000.0);
+  if (FN == FN_AVG) return nn > 0 ? sum / (double)nn : sum;            // AggrOverTimeFunctions.scala:1000
+  return sum;                                                          // FN_SUM, FN_INCREASE (delta schema)
+}
+
 // literal per-chunk fold for one window of a regular series (TimeRangeFunction family on const-DDV timestamps):
-// chunk-set membership ChunkSetInfo.scala:481-510, row range RangeFunction.scala:185-190, fold AggrOverTimeFunctions.scala:560-571
-__device__ __forceinline__ double tile_eval_window(const TileSeries& S, const double* vals, const QueryParams& q, const StepDiv& sd,
-                                                   const SumFinish& fin, int k) {
+// chunk-set membership ChunkSetInfo.scala:481-510, row range RangeFunction.scala:185-190, fold AggrOverTimeFunctions.scala:560-571.
+// Rows advance one per window, so the unclamped row range of window k is [s0 + k, e0 + k] (no search, no division).
+template <int FN>
+__device__ __forceinline__ double tile_eval_window(const TileSeries& S, const double* vals, const QueryParams& q, double div, int k) {
   const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
   int64_t winDur = q.inclusive ? q.window : q.window - 1; if (winDur < 0) winDur = 0;
   const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - winDur;
@@ -36,28 +48,27 @@ __device__ __forceinline__ double tile_eval_window(const TileSeries& S, const do
     const TileChunk& ch = S.c[c];
     if (ch.end_time < wStart) continue;
     if (c > 0 && !(S.c[c - 1].end_time < wEnd)) continue;
-    int64_t su = sd.ceil_div(wStart - ch.init); if (su < 0) su = 0;
-    int64_t eu = sd.floor_div(wEnd - ch.init); if (eu > ch.nrows - 1) eu = ch.nrows - 1;
+    int su = ch.s0 + k; if (su < 0) su = 0;
+    int eu = ch.e0 + k; if (eu > ch.nrows - 1) eu = ch.nrows - 1;
     if (su > eu) continue;
     const double* v = vals + ch.row_base;
     double cs = 0.0; int nn = 0;
-    for (int r = (int)su; r <= (int)eu; ++r) { const double x = v[r]; if (x == x) { cs += x; ++nn; } }
+    for (int r = su; r <= eu; ++r) { const double x = v[r]; if (x == x) { cs += x; ++nn; } }
     anyrows = true;
     const double csn = nn ? cs : NaNv;
     if (nn && sum != sum) sum = 0.0;
     sum += csn; cnt += nn;
   }
-  switch (q.fn) {
-    case FN_SUM: case FN_INCREASE: return sum;
-    case FN_RATE: return sum / fin.div * 1000.0;
-    case FN_AVG: return cnt > 0 ? sum / (double)cnt : (sum != sum ? sum : 0.0);
-    default: return anyrows ? (double)cnt : NaNv;          // FN_COUNT
-  }
+  if (FN == FN_RATE) return sum / div * 1000.0;
+  if (FN == FN_AVG) return cnt > 0 ? sum / (double)cnt : (sum != sum ? sum : 0.0);
+  if (FN == FN_COUNT) return anyrows ? (double)cnt : NaNv;
+  return sum;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Tile kernel, SUM class (sum/avg/count_over_time, rate/increase on delta schemas), no across-series aggregate.
 // ---------------------------------------------------------------------------------------------------------------------
+template <int FN>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
 scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, int64_t n_series,
                      QueryParams q, double* __restrict__ out, TileSmem L,
@@ -71,11 +82,14 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
   double* otile = reinterpret_cast<double*>(smem + L.out);
   TileSeries* SD = reinterpret_cast<TileSeries*>(smem + L.desc);
   uint64_t* gtot = reinterpret_cast<uint64_t*>(smem + L.gtot);
+  TileMeta* M = reinterpret_cast<TileMeta*>(smem + L.meta);
   const int64_t n_tiles = (n_series + TILE_NS - 1) / TILE_NS;
   if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   __syncthreads();
   StepDiv sd; sd.init(q.step);
-  SumFinish fin; fin.init(q);
+  int64_t winDur = q.inclusive ? q.window : q.window - 1; if (winDur < 0) winDur = 0;
+  const double fdiv = (double)(q.inclusive ? winDur : winDur + 1), frcp = 1.0 / fdiv;     // RateFunctions.scala:436-442
+  const int64_t S0 = q.start - winDur, E0 = q.start;
   uint32_t parity = 0;
   int64_t rows_scanned = 0, bytes_scanned = 0;
   const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
@@ -112,7 +126,7 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
         if (t1 > t2) cHi = cLo;
         const int n = cHi - cLo;
         bool regular = staged && n <= TILE_MAXC && (n == 0 || (h->flags & REC_ALL_TS_CONST));
-        int ngroups = 0, nrows_tot = 0;
+        int ngroups = 0, nrows_tot = 0; bool any_raw = false;
         if (regular) {
           for (int c = 0; c < n; ++c) {
             const ChunkEntry& e = E[cLo + c];
@@ -121,7 +135,7 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
             const int tlen = (int)ld32(tv + 8); const int64_t init = (int64_t)ld64_a4(tv + 12); const int slope = (int)ld32(tv + 20);
             int vlen, ng = 0;
             if (vwire == WIRE_XOR) { vlen = (int)ld32(vv + XOR_OFF_N); ng = (int)(ld32(vv + XOR_OFF_NGROUPS) & 0xffff); }
-            else if (vwire == WIRE_RAW64) vlen = ((int)ld32(vv) - 4) / 8;
+            else if (vwire == WIRE_RAW64) { vlen = ((int)ld32(vv) - 4) / 8; any_raw = true; }
             else { regular = false; break; }
             if ((int64_t)slope != q.step || tlen <= 0 || vlen <= 0) { regular = false; break; }
             int nrows = e.num_rows < tlen ? e.num_rows : tlen; if (vlen < nrows) nrows = vlen;
@@ -142,8 +156,6 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
         __syncwarp();
         if (regular) {
           // single-chunk window intervals (same definition as scan_fast.cuh chunk_interval)
-          int64_t winDur = q.inclusive ? q.window : q.window - 1; if (winDur < 0) winDur = 0;
-          const int64_t S0 = q.start - winDur, E0 = q.start;
           int nblocks = 0, covered = 0;
           const int64_t lastEnd = q.start + (int64_t)(q.T - 1) * q.step;
           for (int c = 0; c < n; ++c) {
@@ -156,16 +168,17 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
             else if (lane == 2) v = sd.floor_div(ch.init + (int64_t)(ch.nrows - 1) * q.step - S0);
             else if (lane == 3) v = (c + 1 < n) ? sd.floor_div(S.c[c + 1].init - 1 - E0) : (int64_t)q.T;
             else if (lane == 4) v = sd.floor_div(ch.end_time - S0);
+            else if (lane == 5) v = sd.ceil_div(S0 - ch.init);            // s0: unclamped first row of window 0
+            else if (lane == 6) v = sd.floor_div(E0 - ch.init);           // e0: unclamped last row of window 0
             int64_t kA = __shfl_sync(0xffffffffu, v, 0);
             { const int64_t x = __shfl_sync(0xffffffffu, v, 1); if (x > kA) kA = x; }
             int64_t kB = __shfl_sync(0xffffffffu, v, 2);
             { const int64_t x = __shfl_sync(0xffffffffu, v, 3); if (x < kB) kB = x; }
             { const int64_t x = __shfl_sync(0xffffffffu, v, 4); if (x < kB) kB = x; }
+            const int64_t s0 = __shfl_sync(0xffffffffu, v, 5), e0 = __shfl_sync(0xffffffffu, v, 6);
             if (kA < 0) kA = 0;
             if (kB > q.T - 1) kB = q.T - 1;
-            int64_t w = 0;
-            if (kA <= kB) { if (lane == 0) w = sd.ceil_div(S0 + kA * q.step - ch.init); else if (lane == 1) w = sd.floor_div(E0 + kA * q.step - ch.init); }
-            const int64_t sA = __shfl_sync(0xffffffffu, w, 0), eA = __shfl_sync(0xffffffffu, w, 1);
+            const int64_t sA = s0 + kA, eA = e0 + kA;
             const bool ok = kA <= kB && eA >= sA;
             const int Wr = ok ? (int)(eA - sA) : 0;
             const int nwin = ok ? (int)(kB - kA + 1) : 0;
@@ -174,6 +187,7 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
             const int nb = blocked ? (nwin + BLK_R - 1) / BLK_R : 0;
             if (lane == 0) {
               ch.kA = blocked ? (int)kA : 0; ch.kB = blocked ? (int)kB : -1; ch.sA = (int)sA; ch.Wr = Wr; ch.blk0 = nblocks; ch.blk_n = nb;
+              ch.s0 = (int)s0; ch.e0 = (int)e0;
             }
             nblocks += nb; if (blocked) covered += nwin;
             // a chunk that the window iterator never pulls (it starts after the last window end) is not counted as scanned
@@ -182,25 +196,36 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
               rows_scanned -= e.num_rows; bytes_scanned -= (int64_t)ld32(rec + e.ts_off) + 4 + (int64_t)ld32(rec + e.val_off) + 4;
             }
           }
-          if (lane == 0) { S.n = n; S.regular = 1; S.rec_off = (int)roff; S.nblocks = nblocks; S.nrest = q.T - covered; S.ngroups = ngroups; S.nrows = nrows_tot; }
+          if (lane == 0) { S.n = n; S.regular = 1; S.rec_off = (int)roff; S.nblocks = nblocks; S.nrest = q.T - covered; S.ngroups = ngroups; S.nrows = nrows_tot; S.pad = any_raw; }
         } else if (lane == 0) {
-          S.n = 0; S.regular = 0; S.nblocks = 0; S.nrest = 0; S.ngroups = 0; S.nrows = 0;
+          S.n = 0; S.regular = 0; S.nblocks = 0; S.nrest = 0; S.ngroups = 0; S.nrows = 0; S.pad = 0;
           const unsigned long long slot = atomicAdd(fallback_count, 1ull);
           fallback_list[slot] = i0 + warp;
         }
       }
     }
     __syncthreads();
+    if (tid == 0) {                              // tile work-list prefixes (read after the next barriers)
+      int p = 0, r = 0, raw = 0, allreg = 1;
+      for (int s = 0; s < TILE_NS; ++s) {
+        M->pref[s] = p; M->rpref[s] = r;
+        if (SD[s].regular == 1) { p += SD[s].nblocks; r += SD[s].nrest; raw |= SD[s].pad; }
+        if (s < ns && SD[s].regular != 1) allreg = 0;
+      }
+      M->pref[TILE_NS] = p; M->rpref[TILE_NS] = r; M->any_nan = 0; M->any_raw = raw; M->all_regular = allreg;
+    }
     // ------------------------------------------------------------------ decode pass 1: fields + local prefix, group totals
+    // item = (group slot, series) with the series index fastest: neighbouring lanes write to different series' rows, which
+    // spreads the 8-value stores over the shared-memory banks
+#pragma unroll 2
     for (int it = tid; it < TILE_NS * TILE_MAXG; it += TILE_THREADS) {
-      const int s = it / TILE_MAXG, slot = it - s * TILE_MAXG;
+      const int s = it & (TILE_NS - 1), slot = it >> 3;
       const TileSeries& S = SD[s];
       if (S.regular != 1 || slot >= S.ngroups) continue;
       int c = 0; while (c + 1 < S.n && slot >= S.c[c + 1].grp_base) ++c;
       const TileChunk& ch = S.c[c];
       const int g = slot - ch.grp_base;
       const uint8_t* v = recbuf + ch.val_off;
-      const int nvals = (int)ld32(v + XOR_OFF_N);
       const uint32_t w12 = ld32(v + XOR_OFF_NGROUPS);
       const uint8_t* groups = v + (w12 >> 16) + 8;
       const uint16_t* tab = reinterpret_cast<const uint16_t*>(v + XOR_OFF_GROUPTAB);
@@ -231,27 +256,28 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
       }
       uint64_t x = 0;
       uint64_t* dst = reinterpret_cast<uint64_t*>(vals + (size_t)s * L.vals_pitch + ch.row_base) + 1 + g * 8;
-      const int nleft = nvals - 1 - g * 8;
+      const int nleft = ch.vlen - 1 - g * 8;
 #pragma unroll
       for (int i = 0; i < 8; ++i) { x ^= d[i]; if (i < nleft) dst[i] = x; }
       gtot[s * TILE_MAXG + slot] = x;
     }
+    __syncthreads();
     // raw f64 vectors: plain copy (+ NaN/Inf presence)
-    for (int s = 0; s < TILE_NS; ++s) {
-      const TileSeries& S = SD[s];
-      if (S.regular != 1) continue;
-      for (int c = 0; c < S.n; ++c) {
-        const TileChunk& ch = S.c[c];
-        if (ch.wire != WIRE_RAW64) continue;
-        const uint64_t* src = reinterpret_cast<const uint64_t*>(recbuf + ch.val_off + 8);
-        uint64_t* dst = reinterpret_cast<uint64_t*>(vals + (size_t)s * L.vals_pitch + ch.row_base);
-        bool nan = false;
-        const int len = ((int)ld32(recbuf + ch.val_off) - 4) / 8;
-        for (int r = tid; r < len; r += TILE_THREADS) { const uint64_t b = src[r]; dst[r] = b; nan |= ((uint32_t)(b >> 32) & 0x7ff00000u) == 0x7ff00000u; }
-        if (nan) SD[s].c[c].has_nan = 1;
+    if (M->any_raw) {
+      for (int s = 0; s < TILE_NS; ++s) {
+        const TileSeries& S = SD[s];
+        if (S.regular != 1) continue;
+        for (int c = 0; c < S.n; ++c) {
+          const TileChunk& ch = S.c[c];
+          if (ch.wire != WIRE_RAW64) continue;
+          const uint64_t* src = reinterpret_cast<const uint64_t*>(recbuf + ch.val_off + 8);
+          uint64_t* dst = reinterpret_cast<uint64_t*>(vals + (size_t)s * L.vals_pitch + ch.row_base);
+          bool nan = false;
+          for (int r = tid; r < ch.vlen; r += TILE_THREADS) { const uint64_t b = src[r]; dst[r] = b; nan |= ((uint32_t)(b >> 32) & 0x7ff00000u) == 0x7ff00000u; }
+          if (nan) M->any_nan = 1;
+        }
       }
     }
-    __syncthreads();
     // ------------------------------------------------------------------ decode pass 2: per-series segmented prefix of group totals
     if (warp < TILE_NS && SD[warp].regular == 1) {
       const TileSeries& S = SD[warp];
@@ -260,14 +286,17 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
         if (ch.wire != WIRE_XOR) continue;
         const uint8_t* v = recbuf + ch.val_off;
         uint64_t carry = ld64(v + (ld32(v + XOR_OFF_NGROUPS) >> 16));        // first value of the chunk
-        if (lane == 0) reinterpret_cast<uint64_t*>(vals + (size_t)warp * L.vals_pitch + ch.row_base)[0] = carry;
+        if (lane == 0) {
+          reinterpret_cast<uint64_t*>(vals + (size_t)warp * L.vals_pitch + ch.row_base)[0] = carry;
+          if (((uint32_t)(carry >> 32) & 0x7ff00000u) == 0x7ff00000u) M->any_nan = 1;
+        }
         for (int g0 = 0; g0 < ch.ngroups; g0 += 32) {
           const int g = g0 + lane;
           const uint64_t x = g < ch.ngroups ? gtot[warp * TILE_MAXG + ch.grp_base + g] : 0;
           uint64_t incl = x;
 #pragma unroll
           for (int off = 1; off < 32; off <<= 1) { const uint64_t y = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl ^= y; }
-          if (g < ch.ngroups) gtot[warp * TILE_MAXG + ch.grp_base + g] = carry ^ incl ^ x;   // exclusive prefix (value before the group)
+          if (g < ch.ngroups) gtot[warp * TILE_MAXG + ch.grp_base + g] = carry ^ incl ^ x;   // value before the group
           carry ^= __shfl_sync(0xffffffffu, incl, 31);
         }
       }
@@ -277,40 +306,38 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
     const int64_t tnext = t + gridDim.x;
     bool staged_next = false;
     if (tnext < n_tiles) staged_next = issue_tile(tnext);
-    // ------------------------------------------------------------------ decode pass 3: apply the prefix, record NaN/Inf presence
-    for (int s = 0; s < TILE_NS; ++s) {
+    // ------------------------------------------------------------------ decode pass 3: apply the prefix (same items as pass 1)
+#pragma unroll 2
+    for (int it = tid; it < TILE_NS * TILE_MAXG; it += TILE_THREADS) {
+      const int s = it & (TILE_NS - 1), slot = it >> 3;
       const TileSeries& S = SD[s];
-      if (S.regular != 1) continue;
-      for (int c = 0; c < S.n; ++c) {
-        const TileChunk& ch = S.c[c];
-        if (ch.wire != WIRE_XOR) continue;
-        uint64_t* row = reinterpret_cast<uint64_t*>(vals + (size_t)s * L.vals_pitch + ch.row_base);
-        const int len = ch.vlen;
-        bool nan = false;
-        for (int r = tid; r < len; r += TILE_THREADS) {
-          uint64_t b = row[r];
-          if (r > 0) { b ^= gtot[s * TILE_MAXG + ch.grp_base + ((r - 1) >> 3)]; row[r] = b; }
-          nan |= (r < ch.nrows) && ((uint32_t)(b >> 32) & 0x7ff00000u) == 0x7ff00000u;
-        }
-        if (nan) SD[s].c[c].has_nan = 1;
+      if (S.regular != 1 || slot >= S.ngroups) continue;
+      int c = 0; while (c + 1 < S.n && slot >= S.c[c + 1].grp_base) ++c;
+      const TileChunk& ch = S.c[c];
+      const int g = slot - ch.grp_base;
+      const uint64_t pre = gtot[s * TILE_MAXG + slot];
+      uint64_t* dst = reinterpret_cast<uint64_t*>(vals + (size_t)s * L.vals_pitch + ch.row_base) + 1 + g * 8;
+      const int nleft = ch.vlen - 1 - g * 8;
+      uint32_t hi_or = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (i < nleft) {
+        const uint64_t b = dst[i] ^ pre; dst[i] = b;
+        hi_or |= (((uint32_t)(b >> 32) & 0x7ff00000u) == 0x7ff00000u) ? 1u : 0u;      // NaN or Inf: conservative
       }
+      if (hi_or) M->any_nan = 1;
     }
     if (tid == 0) tma_store_wait_read();       // the previous tile's bulk store must have finished reading `otile`
     __syncthreads();
     // ------------------------------------------------------------------ windows: blocked single-chunk windows
     {
-      int pref[TILE_NS + 1]; pref[0] = 0; bool any_nan = false;
-#pragma unroll
-      for (int s = 0; s < TILE_NS; ++s) {
-        pref[s + 1] = pref[s] + (SD[s].regular == 1 ? SD[s].nblocks : 0);
-        if (SD[s].regular == 1) for (int c = 0; c < SD[s].n; ++c) any_nan |= SD[s].c[c].has_nan != 0;
-      }
-      for (int it = tid; it < pref[TILE_NS]; it += TILE_THREADS) {
+      const bool any_nan = M->any_nan != 0;
+      const int nitems = M->pref[TILE_NS];
+      for (int it = tid; it < nitems; it += TILE_THREADS) {
         int s = 0;
 #pragma unroll
-        for (int j = 1; j < TILE_NS; ++j) if (it >= pref[j]) s = j;
+        for (int j = 1; j < TILE_NS; ++j) if (it >= M->pref[j]) s = j;
         const TileSeries& S = SD[s];
-        const int B = it - pref[s];
+        const int B = it - M->pref[s];
         int c = 0; while (c + 1 < S.n && B >= S.c[c].blk0 + S.c[c].blk_n) ++c;
         const TileChunk& ch = S.c[c];
         const int b = B - ch.blk0;
@@ -322,38 +349,33 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
         int nw = ch.kB - k0 + 1; if (nw > BLK_R) nw = BLK_R;
         double* o = otile + (size_t)s * L.out_pitch + k0;
 #pragma unroll
-        for (int j = 0; j < BLK_R; ++j) if (j < nw) o[j] = fin(acc[j], cnt[j]);
+        for (int j = 0; j < BLK_R; ++j) if (j < nw) o[j] = tile_finish<FN>(acc[j], cnt[j], fdiv, frcp);
       }
       // ---------------------------------------------------------------- windows: everything else (chunk junctions, short windows)
-      int rpref[TILE_NS + 1]; rpref[0] = 0;
-#pragma unroll
-      for (int s = 0; s < TILE_NS; ++s) rpref[s + 1] = rpref[s] + (SD[s].regular == 1 ? SD[s].nrest : 0);
-      for (int it = tid; it < rpref[TILE_NS]; it += TILE_THREADS) {
+      const int nrest = M->rpref[TILE_NS];
+      for (int it = tid; it < nrest; it += TILE_THREADS) {
         int s = 0;
 #pragma unroll
-        for (int j = 1; j < TILE_NS; ++j) if (it >= rpref[j]) s = j;
+        for (int j = 1; j < TILE_NS; ++j) if (it >= M->rpref[j]) s = j;
         const TileSeries& S = SD[s];
-        int u = it - rpref[s];
-        int k, prev = -1; bool found = false;          // u-th window not covered by a blocked interval
+        int u = it - M->rpref[s];
+        int prev = -1; bool found = false;          // u-th window not covered by a blocked interval
         for (int c = 0; c < S.n && !found; ++c) {
           if (S.c[c].kA > S.c[c].kB) continue;
           const int gap = S.c[c].kA - prev - 1;
           if (u < gap) found = true; else { u -= gap; prev = S.c[c].kB; }
         }
-        k = prev + 1 + u;
-        otile[(size_t)s * L.out_pitch + k] = tile_eval_window(S, vals + (size_t)s * L.vals_pitch, q, sd, fin, k);
+        const int k = prev + 1 + u;
+        otile[(size_t)s * L.out_pitch + k] = tile_eval_window<FN>(S, vals + (size_t)s * L.vals_pitch, q, fdiv, k);
       }
     }
     fence_async_smem();        // make this thread's writes to the output tile visible to the async proxy (bulk store below)
     __syncthreads();
     // ------------------------------------------------------------------ results: one bulk store for the tile (regular rows only)
     {
-      bool all_regular = true;
-#pragma unroll
-      for (int s = 0; s < TILE_NS; ++s) if (s < ns && SD[s].regular != 1) all_regular = false;
       double* gout = out + (size_t)i0 * q.T;
       const uint32_t bytes = (uint32_t)ns * (uint32_t)q.T * 8u;
-      if (all_regular && out_aligned && (bytes & 15) == 0 && (((size_t)i0 * q.T * 8) & 15) == 0) {
+      if (M->all_regular && out_aligned && (bytes & 15) == 0 && (((size_t)i0 * q.T * 8) & 15) == 0) {
         if (tid == 0) tma_store_1d(gout, otile, bytes);
       } else {
         for (int s = 0; s < ns; ++s) {

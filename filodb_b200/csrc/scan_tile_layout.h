@@ -18,14 +18,21 @@ struct TileChunk {
   int32_t blk0, blk_n;
   int32_t has_nan, tlen;      // tlen: timestamp vector length
   int32_t vlen, pad;          // vlen: value vector length
+  int32_t s0, e0;             // unclamped first / last row of window k = 0 (rows advance by one per window)
 };
 struct TileSeries {
   int32_t n, regular, rec_off, nblocks, nrest, ngroups, nrows, pad;
   TileChunk c[TILE_MAXC];
 };
 
+struct TileMeta {                         // per-tile work-list prefixes and flags
+  int32_t pref[TILE_NS + 1];              // blocked work items per series (prefix)
+  int32_t rpref[TILE_NS + 1];             // other windows per series (prefix)
+  int32_t any_nan, any_raw, all_regular, pad;
+};
+
 struct TileSmem {                         // byte offsets inside dynamic shared memory (all multiples of 128)
-  uint32_t rec, vals, out, desc, gtot, total;
+  uint32_t rec, vals, out, desc, gtot, meta, total;
   uint32_t rec_cap, vals_pitch /*doubles per series*/, out_pitch /*doubles per series = T*/;
 };
 FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t T) {
@@ -39,6 +46,7 @@ FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, u
   L.out = o; o += align_up(TILE_NS * T * 8, 128);
   L.desc = o; o += align_up(TILE_NS * (uint32_t)sizeof(TileSeries), 128);
   L.gtot = o; o += TILE_NS * TILE_MAXG * 8;
+  L.meta = o; o += 128;
   L.total = o;
   return L;
 }
