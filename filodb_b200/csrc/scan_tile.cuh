@@ -3,9 +3,11 @@
 // A CTA processes tiles of TILE_NS consecutive series.  Records of consecutive series are adjacent in the arena, so a tile's
 // chunk pages arrive with ONE cp.async.bulk (TMA) into shared memory, and the tile's [TILE_NS x T] results leave with ONE
 // cp.async.bulk store.  Between the two, all 256 threads work on uniform work items:
-//   setup    warp w resolves series w: chunk range, regularity, single-chunk window intervals (scan_fast.cuh definitions)
-//   decode   item = (series, NibblePack group): field extraction + local XOR prefix; a per-series segmented prefix over the
-//            group totals; an apply pass over the same items.  Raw f64 vectors are copied.  NaN/Inf presence is recorded.
+//   setup    warp w resolves series w, lane = (chunk, quantity): chunk range, regularity, single-chunk window intervals
+//            (same definition as scan_fast.cuh chunk_interval, three divisions per chunk)
+//   decode   item = (series, NibblePack group), two items per thread held in registers: branch-free field extraction +
+//            local XOR prefix, group totals combined inside the warp, warp totals exchanged through shared memory, then the
+//            finished values are stored once.  Raw f64 vectors are copied.  NaN/Inf presence is recorded.
 //   windows  item = (series, block of BLK_R single-chunk windows): register-blocked sequential sums (exact reference order);
 //            item = (series, other window): literal per-chunk fold for windows that take rows from two chunks.
 // A series is "regular" when every chunk in range has const-DDV timestamps with slope == step and XOR/raw double values,
@@ -38,22 +40,21 @@ __device__ __forceinline__ double tile_finish(double cs, int nn, double div, dou
 // literal per-chunk fold for one window of a regular series (TimeRangeFunction family on const-DDV timestamps):
 // chunk-set membership ChunkSetInfo.scala:481-510, row range RangeFunction.scala:185-190, fold AggrOverTimeFunctions.scala:560-571.
 // Rows advance one per window, so the unclamped row range of window k is [s0 + k, e0 + k] (no search, no division).
-template <int FN>
-__device__ __forceinline__ double tile_eval_window(const TileSeries& S, const double* vals, const QueryParams& q, double div, int k) {
+template <int FN, bool CHECK_NAN>
+__device__ __forceinline__ double tile_eval_window(const TileSeries& S, const double* vals, int64_t wStart, int64_t wEnd, double div, int k) {
   const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
-  int64_t winDur = q.inclusive ? q.window : q.window - 1; if (winDur < 0) winDur = 0;
-  const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - winDur;
   double sum = NaNv; int cnt = 0; bool anyrows = false;
   for (int c = 0; c < S.n; ++c) {
     const TileChunk& ch = S.c[c];
-    if (ch.end_time < wStart) continue;
-    if (c > 0 && !(S.c[c - 1].end_time < wEnd)) continue;
+    bool member = !(ch.end_time < wStart);
+    if (c > 0 && !(S.c[c - 1].end_time < wEnd)) member = false;
     int su = ch.s0 + k; if (su < 0) su = 0;
     int eu = ch.e0 + k; if (eu > ch.nrows - 1) eu = ch.nrows - 1;
-    if (su > eu) continue;
+    if (!member || su > eu) continue;
     const double* v = vals + ch.row_base;
     double cs = 0.0; int nn = 0;
-    for (int r = su; r <= eu; ++r) { const double x = v[r]; if (x == x) { cs += x; ++nn; } }
+    if (CHECK_NAN) { for (int r = su; r <= eu; ++r) { const double x = v[r]; if (x == x) { cs += x; ++nn; } } }
+    else { for (int r = su; r <= eu; ++r) cs += v[r]; nn = eu - su + 1; }
     anyrows = true;
     const double csn = nn ? cs : NaNv;
     if (nn && sum != sum) sum = 0.0;
@@ -65,6 +66,9 @@ __device__ __forceinline__ double tile_eval_window(const TileSeries& S, const do
   return sum;
 }
 
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) { return (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)v, src); }
+__device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d) { return (uint64_t)__shfl_up_sync(0xffffffffu, (unsigned long long)v, d); }
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Tile kernel, SUM class (sum/avg/count_over_time, rate/increase on delta schemas), no across-series aggregate.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -74,6 +78,7 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
                      QueryParams q, double* __restrict__ out, TileSmem L,
                      int64_t* __restrict__ fallback_list, unsigned long long* __restrict__ fallback_count,
                      unsigned long long* d_counters, int* d_err) {
+  static_assert(TILE_NS == 8 && TILE_THREADS == 256 && TILE_MAXC == 4 && TILE_MAXG == 64, "item mappings below assume this shape");
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -81,7 +86,8 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
   double* vals = reinterpret_cast<double*>(smem + L.vals);
   double* otile = reinterpret_cast<double*>(smem + L.out);
   TileSeries* SD = reinterpret_cast<TileSeries*>(smem + L.desc);
-  uint64_t* gtot = reinterpret_cast<uint64_t*>(smem + L.gtot);
+  uint64_t* gexcl = reinterpret_cast<uint64_t*>(smem + L.gtot);        // [series][slot]: XOR of the warp's earlier group totals
+  uint64_t* gwtot = gexcl + TILE_NS * TILE_MAXG;                       // [series][warp]: XOR of the warp's 8 group totals
   TileMeta* M = reinterpret_cast<TileMeta*>(smem + L.meta);
   const int64_t n_tiles = (n_series + TILE_NS - 1) / TILE_NS;
   if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
@@ -110,158 +116,208 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
     const int ns = (int)((i0 + TILE_NS < n_series ? i0 + TILE_NS : n_series) - i0);
     const int64_t tile_base = rec_off[i0];
     if (staged) { mbar_wait(bar, parity); parity ^= 1; }
-    // ------------------------------------------------------------------ setup: warp w <-> series w
-    if (warp < TILE_NS) {
+    // ------------------------------------------------------------------ setup: warp w <-> series w, lane = chunk * 8 + quantity
+    {
       TileSeries& S = SD[warp];
-      if (warp >= ns) { if (lane == 0) { S.n = 0; S.regular = 2; S.nblocks = 0; S.nrest = 0; S.ngroups = 0; S.nrows = 0; } }
-      else {
-        const uint32_t roff = (uint32_t)(rec_off[i0 + warp] - tile_base);
-        const uint8_t* rec = staged ? recbuf + roff : arena + tile_base + roff;
+      const int c = lane >> 3, j = lane & 7;
+      bool regular = false; int n = 0, cLo = 0; uint32_t roff = 0;
+      const uint8_t* rec = recbuf;
+      if (warp < ns && staged) {
+        roff = (uint32_t)(rec_off[i0 + warp] - tile_base);
+        rec = recbuf + roff;
         const RecordHeader* h = reinterpret_cast<const RecordHeader*>(rec);
         const ChunkEntry* E = reinterpret_cast<const ChunkEntry*>(rec + sizeof(RecordHeader));
         const int nch = (int)h->n_chunks;
         const int64_t t1 = q.start - q.window, t2 = q.end;
-        int cLo = 0; while (cLo < nch && E[cLo].end_time < t1) ++cLo;
+        while (cLo < nch && E[cLo].end_time < t1) ++cLo;
         int cHi = cLo; while (cHi < nch && E[cHi].start_time <= t2) ++cHi;
         if (t1 > t2) cHi = cLo;
-        const int n = cHi - cLo;
-        bool regular = staged && n <= TILE_MAXC && (n == 0 || (h->flags & REC_ALL_TS_CONST));
-        int ngroups = 0, nrows_tot = 0; bool any_raw = false;
-        if (regular) {
-          for (int c = 0; c < n; ++c) {
-            const ChunkEntry& e = E[cLo + c];
-            const uint8_t* tv = rec + e.ts_off; const uint8_t* vv = rec + e.val_off;
-            const int vwire = ld32(vv + 4) & 0xffff;
-            const int tlen = (int)ld32(tv + 8); const int64_t init = (int64_t)ld64_a4(tv + 12); const int slope = (int)ld32(tv + 20);
-            int vlen, ng = 0;
-            if (vwire == WIRE_XOR) { vlen = (int)ld32(vv + XOR_OFF_N); ng = (int)(ld32(vv + XOR_OFF_NGROUPS) & 0xffff); }
-            else if (vwire == WIRE_RAW64) { vlen = ((int)ld32(vv) - 4) / 8; any_raw = true; }
-            else { regular = false; break; }
-            if ((int64_t)slope != q.step || tlen <= 0 || vlen <= 0) { regular = false; break; }
-            int nrows = e.num_rows < tlen ? e.num_rows : tlen; if (vlen < nrows) nrows = vlen;
-            if (lane == 0) {
-              TileChunk& ch = S.c[c];
-              ch.init = init; ch.end_time = e.end_time; ch.nrows = nrows; ch.row_base = nrows_tot;
-              ch.val_off = roff + e.val_off; ch.wire = vwire; ch.ngroups = ng; ch.grp_base = ngroups; ch.has_nan = 0;
-              ch.tlen = tlen; ch.vlen = vlen;
-            }
-            ngroups += ng; nrows_tot += vlen;
-            if (lane == 0) {      // CountingChunkInfoIterator, ChunkSetInfo.scala:336-380 (every chunk in range is pulled when regular)
-              rows_scanned += e.num_rows;
-              bytes_scanned += (int64_t)ld32(tv) + 4 + (int64_t)ld32(vv) + 4;
-            }
-          }
-          if (ngroups > TILE_MAXG || nrows_tot + 2 > (int)L.vals_pitch) regular = false;
+        n = cHi - cLo;
+        regular = n <= TILE_MAXC && (n == 0 || (h->flags & REC_ALL_TS_CONST));
+      }
+      const ChunkEntry* E = reinterpret_cast<const ChunkEntry*>(rec + sizeof(RecordHeader)) + cLo;
+      const bool have = regular && c < n;
+      int64_t init = 0, end_time = 0; int tlen = 0, vlen = 0, ng = 0, vwire = 0, nrows = 0, num_rows = 0, vbytes = 0; uint32_t voff = 0, w12 = 0;
+      bool okc = true;
+      if (have) {
+        const ChunkEntry& e = E[c];
+        const uint8_t* tv = rec + e.ts_off; const uint8_t* vv = rec + e.val_off;
+        vwire = ld32(vv + 4) & 0xffff;
+        tlen = (int)ld32(tv + 8); init = (int64_t)ld64_a4(tv + 12); const int slope = (int)ld32(tv + 20);
+        end_time = e.end_time; num_rows = e.num_rows; voff = roff + e.val_off;
+        vbytes = (int)ld32(tv) + 4 + (int)ld32(vv) + 4;
+        if (vwire == WIRE_XOR) { vlen = (int)ld32(vv + XOR_OFF_N); w12 = ld32(vv + XOR_OFF_NGROUPS); ng = (int)(w12 & 0xffff); }
+        else if (vwire == WIRE_RAW64) vlen = ((int)ld32(vv) - 4) / 8;
+        else okc = false;
+        if ((int64_t)slope != q.step || tlen <= 0 || vlen <= 0) okc = false;
+        nrows = num_rows < tlen ? num_rows : tlen; if (vlen < nrows) nrows = vlen;
+        if (!okc) { ng = 0; vlen = 0; }
+      }
+      regular = regular && __all_sync(0xffffffffu, okc);
+      // exclusive prefixes over the series' chunks (lanes 0, 8, 16, 24 hold chunk 0..3)
+      auto xpre = [&](int v, int& total) -> int {
+        const int a0 = __shfl_sync(0xffffffffu, v, 0), a1 = __shfl_sync(0xffffffffu, v, 8), a2 = __shfl_sync(0xffffffffu, v, 16), a3 = __shfl_sync(0xffffffffu, v, 24);
+        total = a0 + a1 + a2 + a3;
+        return (c > 0 ? a0 : 0) + (c > 1 ? a1 : 0) + (c > 2 ? a2 : 0);
+      };
+      int ngroups = 0, nrows_tot = 0;
+      const int grp_base = xpre(ng, ngroups), row_base = xpre(vlen, nrows_tot);
+      if (ngroups > TILE_MAXG || nrows_tot + 2 > (int)L.vals_pitch) regular = false;
+      if (warp < ns && regular) {
+        // three divisions per chunk (lane quantity j): s0, e0 = unclamped first / last row of window 0; v4 = last window whose
+        // start is <= endTime.  The other bounds of scan_fast.cuh chunk_interval follow from these and the neighbours':
+        //   ceil((init - E0)/step) = -e0           floor((lastTs - S0)/step) = nrows - 1 - s0
+        //   ceil((max(prevEnd, prevLastTs) + 1 - S0)/step) = max(prev.v4 + 1, prev.tlen - prev.s0)
+        //   floor((next.init - 1 - E0)/step) = -(next.e0 + 1)
+        int64_t v = 0;
+        if (have) {
+          if (j == 0) v = sd.ceil_div(S0 - init);
+          else if (j == 1) v = sd.floor_div(E0 - init);
+          else if (j == 2) v = sd.floor_div(end_time - S0);
         }
-        __syncwarp();
-        if (regular) {
-          // single-chunk window intervals (same definition as scan_fast.cuh chunk_interval)
-          int nblocks = 0, covered = 0;
+        const int lb = lane & 24;
+        const int64_t s0 = __shfl_sync(0xffffffffu, v, lb), e0 = __shfl_sync(0xffffffffu, v, lb + 1), v4 = __shfl_sync(0xffffffffu, v, lb + 2);
+        const int64_t s0p = __shfl_up_sync(0xffffffffu, s0, 8), v4p = __shfl_up_sync(0xffffffffu, v4, 8), e0n = __shfl_down_sync(0xffffffffu, e0, 8);
+        const int tlenp = __shfl_up_sync(0xffffffffu, tlen, 8);
+        const int64_t endp = __shfl_up_sync(0xffffffffu, end_time, 8);
+        int64_t kA = -e0;
+        if (c > 0) { int64_t x = v4p + 1; const int64_t y = (int64_t)tlenp - s0p; if (y > x) x = y; if (x > kA) kA = x; }
+        int64_t kB = (int64_t)(nrows - 1) - s0;
+        { const int64_t x = (c + 1 < n) ? -(e0n + 1) : (int64_t)q.T; if (x < kB) kB = x; }
+        if (v4 < kB) kB = v4;
+        if (kA < 0) kA = 0;
+        if (kB > q.T - 1) kB = q.T - 1;
+        const int64_t sA = s0 + kA, eA = e0 + kA;
+        const bool ok = have && kA <= kB && eA >= sA;
+        const int Wr = ok ? (int)(eA - sA) : 0;
+        const int nwin = ok ? (int)(kB - kA + 1) : 0;
+        // blocked only when the windows are long enough to amortise a block; short windows go through the per-window path
+        const bool blocked = ok && Wr >= BLK_R - 1;
+        const int nb = blocked ? (nwin + BLK_R - 1) / BLK_R : 0;
+        int nblocks = 0, covered = 0;
+        const int blk0 = xpre(nb, nblocks); (void)xpre(blocked ? nwin : 0, covered);
+        if (have && j == 0) {
+          TileChunk& ch = S.c[c];
+          ch.init = init; ch.end_time = end_time; ch.nrows = nrows; ch.row_base = row_base;
+          ch.val_off = voff; ch.wire = vwire; ch.ngroups = ng; ch.grp_base = grp_base; ch.tlen = tlen; ch.vlen = vlen;
+          ch.kA = blocked ? (int)kA : 0; ch.kB = blocked ? (int)kB : -1; ch.sA = (int)sA; ch.Wr = Wr; ch.blk0 = blk0; ch.blk_n = nb;
+          ch.s0 = (int)s0; ch.e0 = (int)e0;
+          if (vwire == WIRE_XOR) {
+            const uint32_t po = w12 >> 16;
+            ch.first = ld64(recbuf + voff + po); ch.grp_off = voff + po + 8; ch.tab_off = voff + XOR_OFF_GROUPTAB;
+          } else { ch.first = 0; ch.grp_off = 0; ch.tab_off = 0; }
+          // CountingChunkInfoIterator, ChunkSetInfo.scala:336-380: every chunk in range is pulled, except one that starts after
+          // the last window end (the window iterator never reaches it)
           const int64_t lastEnd = q.start + (int64_t)(q.T - 1) * q.step;
-          for (int c = 0; c < n; ++c) {
-            TileChunk& ch = S.c[c];
-            int64_t v = 0;
-            if (lane == 0) v = sd.ceil_div(ch.init - E0);
-            else if (lane == 1) {
-              if (c > 0) { const TileChunk& p = S.c[c - 1]; int64_t pm = p.end_time; const int64_t pl = p.init + (int64_t)(p.tlen - 1) * q.step; if (pl > pm) pm = pl; v = sd.ceil_div(pm + 1 - S0); }
-            }
-            else if (lane == 2) v = sd.floor_div(ch.init + (int64_t)(ch.nrows - 1) * q.step - S0);
-            else if (lane == 3) v = (c + 1 < n) ? sd.floor_div(S.c[c + 1].init - 1 - E0) : (int64_t)q.T;
-            else if (lane == 4) v = sd.floor_div(ch.end_time - S0);
-            else if (lane == 5) v = sd.ceil_div(S0 - ch.init);            // s0: unclamped first row of window 0
-            else if (lane == 6) v = sd.floor_div(E0 - ch.init);           // e0: unclamped last row of window 0
-            int64_t kA = __shfl_sync(0xffffffffu, v, 0);
-            { const int64_t x = __shfl_sync(0xffffffffu, v, 1); if (x > kA) kA = x; }
-            int64_t kB = __shfl_sync(0xffffffffu, v, 2);
-            { const int64_t x = __shfl_sync(0xffffffffu, v, 3); if (x < kB) kB = x; }
-            { const int64_t x = __shfl_sync(0xffffffffu, v, 4); if (x < kB) kB = x; }
-            const int64_t s0 = __shfl_sync(0xffffffffu, v, 5), e0 = __shfl_sync(0xffffffffu, v, 6);
-            if (kA < 0) kA = 0;
-            if (kB > q.T - 1) kB = q.T - 1;
-            const int64_t sA = s0 + kA, eA = e0 + kA;
-            const bool ok = kA <= kB && eA >= sA;
-            const int Wr = ok ? (int)(eA - sA) : 0;
-            const int nwin = ok ? (int)(kB - kA + 1) : 0;
-            // blocked only when the windows are long enough to amortise a block; short windows go through the per-window path
-            const bool blocked = ok && Wr >= BLK_R - 1;
-            const int nb = blocked ? (nwin + BLK_R - 1) / BLK_R : 0;
-            if (lane == 0) {
-              ch.kA = blocked ? (int)kA : 0; ch.kB = blocked ? (int)kB : -1; ch.sA = (int)sA; ch.Wr = Wr; ch.blk0 = nblocks; ch.blk_n = nb;
-              ch.s0 = (int)s0; ch.e0 = (int)e0;
-            }
-            nblocks += nb; if (blocked) covered += nwin;
-            // a chunk that the window iterator never pulls (it starts after the last window end) is not counted as scanned
-            if (lane == 0 && c > 0 && !(S.c[c - 1].end_time < lastEnd)) {
-              const ChunkEntry& e = E[cLo + c];
-              rows_scanned -= e.num_rows; bytes_scanned -= (int64_t)ld32(rec + e.ts_off) + 4 + (int64_t)ld32(rec + e.val_off) + 4;
-            }
-          }
-          if (lane == 0) { S.n = n; S.regular = 1; S.rec_off = (int)roff; S.nblocks = nblocks; S.nrest = q.T - covered; S.ngroups = ngroups; S.nrows = nrows_tot; S.pad = any_raw; }
-        } else if (lane == 0) {
-          S.n = 0; S.regular = 0; S.nblocks = 0; S.nrest = 0; S.ngroups = 0; S.nrows = 0; S.pad = 0;
+          if (!(c > 0 && !(endp < lastEnd))) { rows_scanned += num_rows; bytes_scanned += vbytes; }
+        }
+        if (j == 1) S.gb[c] = have ? grp_base : 0x7fffffff;
+        if (lane == 0) {
+          S.n = n; S.regular = 1; S.rec_off = (int)roff; S.nblocks = nblocks; S.nrest = q.T - covered; S.ngroups = ngroups; S.nrows = nrows_tot;
+        }
+        const unsigned rawm = __ballot_sync(0xffffffffu, have && vwire == WIRE_RAW64);
+        if (lane == 0) S.any_raw = rawm != 0;
+      } else if (lane == 0) {
+        S.n = 0; S.regular = warp < ns ? 0 : 2; S.nblocks = 0; S.nrest = 0; S.ngroups = 0; S.nrows = 0; S.any_raw = 0;
+        if (warp < ns) {
           const unsigned long long slot = atomicAdd(fallback_count, 1ull);
           fallback_list[slot] = i0 + warp;
         }
       }
     }
     __syncthreads();
-    if (tid == 0) {                              // tile work-list prefixes (read after the next barriers)
-      int p = 0, r = 0, raw = 0, allreg = 1;
-      for (int s = 0; s < TILE_NS; ++s) {
-        M->pref[s] = p; M->rpref[s] = r;
-        if (SD[s].regular == 1) { p += SD[s].nblocks; r += SD[s].nrest; raw |= SD[s].pad; }
-        if (s < ns && SD[s].regular != 1) allreg = 0;
-      }
-      M->pref[TILE_NS] = p; M->rpref[TILE_NS] = r; M->any_nan = 0; M->any_raw = raw; M->all_regular = allreg;
-    }
-    // ------------------------------------------------------------------ decode pass 1: fields + local prefix, group totals
-    // item = (group slot, series) with the series index fastest: neighbouring lanes write to different series' rows, which
-    // spreads the 8-value stores over the shared-memory banks
-#pragma unroll 2
-    for (int it = tid; it < TILE_NS * TILE_MAXG; it += TILE_THREADS) {
-      const int s = it & (TILE_NS - 1), slot = it >> 3;
-      const TileSeries& S = SD[s];
-      if (S.regular != 1 || slot >= S.ngroups) continue;
-      int c = 0; while (c + 1 < S.n && slot >= S.c[c + 1].grp_base) ++c;
-      const TileChunk& ch = S.c[c];
-      const int g = slot - ch.grp_base;
-      const uint8_t* v = recbuf + ch.val_off;
-      const uint32_t w12 = ld32(v + XOR_OFF_NGROUPS);
-      const uint8_t* groups = v + (w12 >> 16) + 8;
-      const uint16_t* tab = reinterpret_cast<const uint16_t*>(v + XOR_OFF_GROUPTAB);
-      const uint8_t* gp = groups + tab[g];
-      uint64_t d[8];
+    if (warp == 0) {                             // tile work-list prefixes and flags (read after the next barrier)
+      const int s = lane & 7;
+      const bool reg = SD[s].regular == 1;
+      int p = reg ? SD[s].nblocks : 0, r = reg ? SD[s].nrest : 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = 0;
-      const uint32_t mask = gp[0];
-      if (mask != 0) {
+      for (int o = 1; o < 8; o <<= 1) {
+        const int pp = __shfl_up_sync(0xffffffffu, p, o), rr = __shfl_up_sync(0xffffffffu, r, o);
+        if (s >= o) { p += pp; r += rr; }
+      }
+      const unsigned rawm = __ballot_sync(0xffffffffu, reg && SD[s].any_raw), irr = __ballot_sync(0xffffffffu, s < ns && !reg);
+      if (lane < 8) { M->pref[lane + 1] = p; M->rpref[lane + 1] = r; }
+      if (lane == 0) { M->pref[0] = 0; M->rpref[0] = 0; M->any_nan = 0; M->any_raw = rawm != 0; M->all_regular = irr == 0; }
+    }
+    // ------------------------------------------------------------------ decode: two (series, group slot) items per thread
+    // Lane -> series lane & 7 (neighbouring lanes store to different series' rows: with the odd row pitch the 8-byte stores
+    // of a warp spread over all banks); warp w owns the slots 8w .. 8w+7 of every series: item jj -> slot 8w + 4jj + (lane >> 3).
+    {
+      const int ds = lane & 7;
+      const TileSeries& S = SD[ds];
+      const bool sreg = S.regular == 1;
+      uint64_t d[2][8]; uint64_t excl[2]; int cc[2]; bool act[2];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int slot = warp * 8 + jj * 4 + (lane >> 3);
+        const bool active = sreg && slot < S.ngroups;
+        const int c = (slot >= S.gb[1] ? 1 : 0) + (slot >= S.gb[2] ? 1 : 0) + (slot >= S.gb[3] ? 1 : 0);
+        const TileChunk& ch = S.c[c];
+        cc[jj] = c; act[jj] = active;
+        const uint8_t* gp = recbuf;
+        if (active) gp = recbuf + ch.grp_off + reinterpret_cast<const uint16_t*>(recbuf + ch.tab_off)[slot - ch.grp_base];
+        const uint32_t mask = active ? gp[0] : 0u;
         const uint32_t hdr = gp[1];
-        const int numBits = ((hdr >> 4) + 1) * 4;
-        const int tz = (hdr & 0x0f) * 4;
-        const uint64_t fmask = numBits >= 64 ? ~0ull : ((1ull << numBits) - 1);
+        const uint32_t numBits = ((hdr >> 4) + 1) * 4;
+        const uint32_t tz = (hdr & 0x0f) * 4;
+        const uint64_t fmask = ~0ull >> (64 - numBits);
         const uintptr_t a0 = reinterpret_cast<uintptr_t>(gp + 2);
-        uint32_t bit = (uint32_t)(a0 & 7) * 8;
-        const uint8_t* base = reinterpret_cast<const uint8_t*>(a0 & ~(uintptr_t)7);
+        uint32_t bit = (uint32_t)(a0 & 3) * 8;
+        const uint32_t* base = reinterpret_cast<const uint32_t*>(a0 & ~(uintptr_t)3);
+        uint64_t x = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if (mask & (1u << i)) {
-            const uint8_t* wp = base + ((bit >> 6) << 3);
-            const int off = (int)(bit & 63);
-            uint64_t val = ld64(wp) >> off;
-            if (off + numBits > 64) val |= ld64(wp + 8) << (64 - off);
-            d[i] = (val & fmask) << tz;
-            bit += numBits;
-          }
+          const bool on = (mask >> i) & 1u;
+          const uint32_t* wp = base + (bit >> 5);
+          const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+          const uint32_t lo = __funnelshift_r(w0, w1, bit), hi = __funnelshift_r(w1, w2, bit);
+          const uint64_t val = ((((uint64_t)hi << 32) | lo) & fmask) << tz;
+          x ^= on ? val : 0ull;
+          bit += on ? numBits : 0u;
+          d[jj][i] = x;
         }
       }
-      uint64_t x = 0;
-      uint64_t* dst = reinterpret_cast<uint64_t*>(vals + (size_t)s * L.vals_pitch + ch.row_base) + 1 + g * 8;
-      const int nleft = ch.vlen - 1 - g * 8;
+      // XOR of the group totals of earlier slots of the same series inside this warp (lanes ds, ds+8, ds+16, ds+24; item 0 first)
+      uint64_t i0x = d[0][7], i1x = d[1][7];
+      { const uint64_t y0 = shfl_up_u64(i0x, 8), y1 = shfl_up_u64(i1x, 8); if (lane >= 8) { i0x ^= y0; i1x ^= y1; } }
+      { const uint64_t y0 = shfl_up_u64(i0x, 16), y1 = shfl_up_u64(i1x, 16); if (lane >= 16) { i0x ^= y0; i1x ^= y1; } }
+      const uint64_t tot0 = shfl_u64(i0x, 24 + ds), tot1 = shfl_u64(i1x, 24 + ds);
+      excl[0] = i0x ^ d[0][7]; excl[1] = i1x ^ d[1][7] ^ tot0;
+      gexcl[ds * TILE_MAXG + warp * 8 + (lane >> 3)] = excl[0];
+      gexcl[ds * TILE_MAXG + warp * 8 + 4 + (lane >> 3)] = excl[1];
+      if (lane >= 24) gwtot[ds * 8 + warp] = tot0 ^ tot1;
+      __syncthreads();
+      // value before group g of chunk c = first_c ^ (prefix at the slot) ^ (prefix at the chunk's first slot); the prefix at a
+      // slot = XOR of the earlier warps' totals ^ the in-warp part
+      uint32_t nz = 0x7ff00000u;
+      {
+        const TileChunk& c0 = S.c[cc[0]]; const TileChunk& c1 = S.c[cc[1]];
+        const int gb0 = act[0] ? c0.grp_base : 0, gb1 = act[1] ? c1.grp_base : 0;
+        uint64_t pre0 = c0.first ^ excl[0] ^ gexcl[ds * TILE_MAXG + gb0];
+        uint64_t pre1 = c1.first ^ excl[1] ^ gexcl[ds * TILE_MAXG + gb1];
+        const int wl0 = gb0 >> 3, wl1 = gb1 >> 3;
+        for (int w = 0; w < warp; ++w) {
+          const uint64_t tw = gwtot[ds * 8 + w];
+          if (w >= wl0) pre0 ^= tw;
+          if (w >= wl1) pre1 ^= tw;
+        }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { x ^= d[i]; if (i < nleft) dst[i] = x; }
-      gtot[s * TILE_MAXG + slot] = x;
+        for (int jj = 0; jj < 2; ++jj) {
+          const TileChunk& ch = jj ? c1 : c0;
+          const uint64_t pre = jj ? pre1 : pre0;
+          const int g = warp * 8 + jj * 4 + (lane >> 3) - ch.grp_base;
+          uint64_t* dst = reinterpret_cast<uint64_t*>(vals + (size_t)ds * L.vals_pitch + ch.row_base) + 1 + g * 8;
+          const int nleft = act[jj] ? ch.vlen - 1 - g * 8 : 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint64_t b = d[jj][i] ^ pre;
+            if (i < nleft) { dst[i] = b; const uint32_t e = ~(uint32_t)(b >> 32) & 0x7ff00000u; nz = e < nz ? e : nz; }
+          }
+          if (act[jj] && g == 0) { dst[-1] = ch.first; const uint32_t e = ~(uint32_t)(ch.first >> 32) & 0x7ff00000u; nz = e < nz ? e : nz; }
+        }
+      }
+      if (nz == 0) M->any_nan = 1;               // an exponent of all ones: NaN or Inf (conservative)
     }
-    __syncthreads();
     // raw f64 vectors: plain copy (+ NaN/Inf presence)
     if (M->any_raw) {
       for (int s = 0; s < TILE_NS; ++s) {
@@ -278,56 +334,12 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
         }
       }
     }
-    // ------------------------------------------------------------------ decode pass 2: per-series segmented prefix of group totals
-    if (warp < TILE_NS && SD[warp].regular == 1) {
-      const TileSeries& S = SD[warp];
-      for (int c = 0; c < S.n; ++c) {
-        const TileChunk& ch = S.c[c];
-        if (ch.wire != WIRE_XOR) continue;
-        const uint8_t* v = recbuf + ch.val_off;
-        uint64_t carry = ld64(v + (ld32(v + XOR_OFF_NGROUPS) >> 16));        // first value of the chunk
-        if (lane == 0) {
-          reinterpret_cast<uint64_t*>(vals + (size_t)warp * L.vals_pitch + ch.row_base)[0] = carry;
-          if (((uint32_t)(carry >> 32) & 0x7ff00000u) == 0x7ff00000u) M->any_nan = 1;
-        }
-        for (int g0 = 0; g0 < ch.ngroups; g0 += 32) {
-          const int g = g0 + lane;
-          const uint64_t x = g < ch.ngroups ? gtot[warp * TILE_MAXG + ch.grp_base + g] : 0;
-          uint64_t incl = x;
-#pragma unroll
-          for (int off = 1; off < 32; off <<= 1) { const uint64_t y = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl ^= y; }
-          if (g < ch.ngroups) gtot[warp * TILE_MAXG + ch.grp_base + g] = carry ^ incl ^ x;   // value before the group
-          carry ^= __shfl_sync(0xffffffffu, incl, 31);
-        }
-      }
-    }
+    if (tid == 0) tma_store_wait_read();       // the previous tile's bulk store must have finished reading `otile`
     __syncthreads();
     // the record bytes are dead now: prefetch the next tile into the staging buffer while this one is reduced
     const int64_t tnext = t + gridDim.x;
     bool staged_next = false;
     if (tnext < n_tiles) staged_next = issue_tile(tnext);
-    // ------------------------------------------------------------------ decode pass 3: apply the prefix (same items as pass 1)
-#pragma unroll 2
-    for (int it = tid; it < TILE_NS * TILE_MAXG; it += TILE_THREADS) {
-      const int s = it & (TILE_NS - 1), slot = it >> 3;
-      const TileSeries& S = SD[s];
-      if (S.regular != 1 || slot >= S.ngroups) continue;
-      int c = 0; while (c + 1 < S.n && slot >= S.c[c + 1].grp_base) ++c;
-      const TileChunk& ch = S.c[c];
-      const int g = slot - ch.grp_base;
-      const uint64_t pre = gtot[s * TILE_MAXG + slot];
-      uint64_t* dst = reinterpret_cast<uint64_t*>(vals + (size_t)s * L.vals_pitch + ch.row_base) + 1 + g * 8;
-      const int nleft = ch.vlen - 1 - g * 8;
-      uint32_t hi_or = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) if (i < nleft) {
-        const uint64_t b = dst[i] ^ pre; dst[i] = b;
-        hi_or |= (((uint32_t)(b >> 32) & 0x7ff00000u) == 0x7ff00000u) ? 1u : 0u;      // NaN or Inf: conservative
-      }
-      if (hi_or) M->any_nan = 1;
-    }
-    if (tid == 0) tma_store_wait_read();       // the previous tile's bulk store must have finished reading `otile`
-    __syncthreads();
     // ------------------------------------------------------------------ windows: blocked single-chunk windows
     {
       const bool any_nan = M->any_nan != 0;
@@ -366,7 +378,10 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
           if (u < gap) found = true; else { u -= gap; prev = S.c[c].kB; }
         }
         const int k = prev + 1 + u;
-        otile[(size_t)s * L.out_pitch + k] = tile_eval_window<FN>(S, vals + (size_t)s * L.vals_pitch, q, fdiv, k);
+        const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - winDur;
+        const double* sv = vals + (size_t)s * L.vals_pitch;
+        otile[(size_t)s * L.out_pitch + k] = any_nan ? tile_eval_window<FN, true>(S, sv, wStart, wEnd, fdiv, k)
+                                                     : tile_eval_window<FN, false>(S, sv, wStart, wEnd, fdiv, k);
       }
     }
     fence_async_smem();        // make this thread's writes to the output tile visible to the async proxy (bulk store below)
@@ -388,7 +403,7 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
     staged = staged_next;
   }
   if (tid == 0) tma_store_wait_read();
-  if (lane == 0 && (rows_scanned | bytes_scanned)) {
+  if (rows_scanned | bytes_scanned) {
     atomicAdd(&d_counters[0], (unsigned long long)rows_scanned); atomicAdd(&d_counters[1], (unsigned long long)bytes_scanned);
   }
 }

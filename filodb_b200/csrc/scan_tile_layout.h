@@ -11,17 +11,19 @@ constexpr int TILE_MAXG = 64;            // NibblePack groups per series on the 
 
 struct TileChunk {
   int64_t init, end_time;
+  uint64_t first;             // XOR vectors: bits of the chunk's first value
   int32_t nrows, row_base;
   int32_t kA, kB, sA, Wr;
   uint32_t val_off; int32_t wire;
+  uint32_t grp_off, tab_off;  // XOR vectors: byte offsets (in the staged tile) of the first group / of the u16 group table
   int32_t ngroups, grp_base;
   int32_t blk0, blk_n;
-  int32_t has_nan, tlen;      // tlen: timestamp vector length
-  int32_t vlen, pad;          // vlen: value vector length
+  int32_t tlen, vlen;         // timestamp / value vector lengths
   int32_t s0, e0;             // unclamped first / last row of window k = 0 (rows advance by one per window)
 };
 struct TileSeries {
-  int32_t n, regular, rec_off, nblocks, nrest, ngroups, nrows, pad;
+  int32_t n, regular, rec_off, nblocks, nrest, ngroups, nrows, any_raw;
+  int32_t gb[TILE_MAXC];      // grp_base of chunk c (INT_MAX for c >= n): chunk of a group slot = #{c >= 1 : gb[c] <= slot}
   TileChunk c[TILE_MAXC];
 };
 
@@ -45,7 +47,7 @@ FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, u
   L.vals = o; o += align_up(TILE_NS * L.vals_pitch * 8, 128);
   L.out = o; o += align_up(TILE_NS * T * 8, 128);
   L.desc = o; o += align_up(TILE_NS * (uint32_t)sizeof(TileSeries), 128);
-  L.gtot = o; o += TILE_NS * TILE_MAXG * 8;
+  L.gtot = o; o += TILE_NS * TILE_MAXG * 8 + TILE_NS * (TILE_THREADS / 32) * 8;   // per-slot in-warp prefixes + per-warp totals
   L.meta = o; o += 128;
   L.total = o;
   return L;
