@@ -224,6 +224,7 @@ def main():
         return
     import torch
     import filodb_b200.capi as capi
+    from filodb_b200 import shard
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -263,7 +264,7 @@ def main():
         ctx.query_device(tab, fn, start, step, end, window, out.data_ptr(), aux.data_ptr() if aux is not None else 0,
                          aggr=aggr, flags=flags, stream=stream, want_stats=False)
         if aggr != capi.AGG_NONE and world > 1:      # the one cross-shard exchange of the plan (ReduceAggregateExec)
-            dist.all_reduce(out, op=dist.ReduceOp.SUM); dist.all_reduce(aux, op=dist.ReduceOp.SUM)
+            shard.merge_partials(out, aux, aggr, dist)
             ctx.present_partials(aggr, n_groups * T, out.data_ptr(), aux.data_ptr(), final.data_ptr(), stream=stream)
 
     # kernel-only duration of the dominant kernel (for the roofline) via the library's own CUDA events

@@ -7,6 +7,7 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -499,7 +500,15 @@ extern "C" int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t
   // v2 kernel processes right after, into the same output buffer.  FILO_KERNEL=v2 disables the tile kernel.
   const bool want_v2 = force && std::string(force) == "v2";
   const int fn_cls = fn_class_of(fn, q.cumulative);
-  const TileSmem TL = tile_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)q.T);
+  // zero rows around a chunk let clamped windows run without bounds checks: a window spans at most window/step + 1 rows
+  // at either end; when that does not leave room for two CTAs per SM the tile kernel falls back to checked loads
+  TileSmem TL;
+  {
+    const uint64_t wrows = (uint64_t)(q.window / q.step) + 1;
+    const uint32_t full_pad = (uint32_t)std::min<uint64_t>(2 * wrows, 1u << 20) + 16;
+    TL = tile_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)q.T, full_pad);
+    if (((size_t)TL.total + 1024) * 2 > (size_t)228 * 1024) TL = tile_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)q.T, 16);
+  }
   const bool use_tile = use_v2 && !want_v2 && fn_cls == CLASS_SUM && t->n_series > 0 &&
                         (size_t)TL.total + 1024 <= std::min<size_t>(ctx->max_smem_optin, 227 * 1024);
   auto run_per_series = [&](double* outp) -> int32_t {
@@ -512,9 +521,13 @@ extern "C" int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t
       const int ctas_per_sm = ((size_t)TL.total + 1024) * 2 <= (size_t)228 * 1024 ? 2 : 1;
       const int64_t n_tiles = (t->n_series + TILE_NS - 1) / TILE_NS;
       LT.grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * ctas_per_sm));
+      static const bool dbg = std::getenv("FILO_DEBUG_SYNC") != nullptr;
+      if (dbg) { fprintf(stderr, "[filo] tile kernel fn=%d T=%d grid=%d smem=%u pitch=%u\n", fn, q.T, LT.grid, TL.total, TL.vals_pitch); fflush(stderr); }
       CUDA_TRY(ctx, launch_scan_tile_sum(LT, outp, TL, d_list, d_cnt));
+      if (dbg) { CUDA_TRY(ctx, cudaStreamSynchronize(s)); fprintf(stderr, "[filo] tile kernel done\n"); fflush(stderr); }
       ScanLaunch LF = L; LF.list = d_list; LF.list_count = d_cnt;
       CUDA_TRY(ctx, launch_scan_series_v2(LF, outp, rec_cap_used));
+      if (dbg) { CUDA_TRY(ctx, cudaStreamSynchronize(s)); fprintf(stderr, "[filo] fallback kernel done\n"); fflush(stderr); }
       launches += 2;
     } else {
       CUDA_TRY(ctx, use_v2 ? launch_scan_series_v2(L, outp, rec_cap_used) : launch_scan_series(L, outp));

@@ -132,10 +132,14 @@ __device__ __forceinline__ void chunk_interval(ChunkDesc* D, int n, int c, const
 // ------------------------------------------------------------------------------------------------ blocked reductions
 // Lane's block: windows j = 0..R-1, window j takes rows r0 + i for i in [j, j + Wr], in row order.  Rows outside [0, nrows)
 // are fed as +0.0 (exact no-op).  Requires Wr >= BLK_R - 1.  With CHECK_NAN, NaN rows are skipped and counted out.
-template <bool CHECK_NAN>
+// CHECK_BOUNDS = false: the caller guarantees that every row a valid window reads outside [0, nrows) holds +0.0 and that
+// rows up to BLK_R - 1 past the last valid window are readable.  NEED_CNT = false: cnt[] is not produced.
+template <bool CHECK_NAN, bool CHECK_BOUNDS = true, bool NEED_CNT = true>
 __device__ __forceinline__ void blocked_sum(const double* __restrict__ slots, int r0, int nrows, int Wr, double acc[BLK_R], int cnt[BLK_R]) {
+  static_assert(!CHECK_NAN || (CHECK_BOUNDS && NEED_CNT), "NaN-aware sums count rows and must not see padding");
   auto load = [&](int i, int& ok) -> double {
     const int r = r0 + i;
+    if (!CHECK_BOUNDS) { ok = 1; return slots[r]; }
     ok = ((unsigned)r < (unsigned)nrows) ? 1 : 0;
     double v = 0.0;
     if (ok) v = slots[r];
@@ -164,9 +168,11 @@ __device__ __forceinline__ void blocked_sum(const double* __restrict__ slots, in
   if (!CHECK_NAN) {
 #pragma unroll
     for (int j = 0; j < BLK_R; ++j) {                      // rows of window j inside the chunk
-      int lo = r0 + j; if (lo < 0) lo = 0;
-      int hi = r0 + j + Wr; if (hi > nrows - 1) hi = nrows - 1;
-      cnt[j] = hi >= lo ? hi - lo + 1 : 0;
+      if (NEED_CNT) {
+        int lo = r0 + j; if (lo < 0) lo = 0;
+        int hi = r0 + j + Wr; if (hi > nrows - 1) hi = nrows - 1;
+        cnt[j] = hi >= lo ? hi - lo + 1 : 0;
+      } else cnt[j] = 1;                                   // a blocked window always has a row inside its chunk
     }
   }
 }

@@ -424,7 +424,7 @@ template <int FN>
 static cudaError_t launch_tile_fn(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count) {
   cudaError_t e = cudaFuncSetAttribute(scan_tile_sum_kernel<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total);
   if (e != cudaSuccess) return e;
-  scan_tile_sum_kernel<FN><<<L.grid, TILE_THREADS, T.total, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, T, fallback_list, fallback_count,
+  scan_tile_sum_kernel<FN><<<L.grid, TILE_LAUNCH_THREADS, T.total, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, T, fallback_list, fallback_count,
                                                                          L.d_counters, L.d_err);
   return cudaGetLastError();
 }

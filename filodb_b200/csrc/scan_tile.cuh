@@ -73,7 +73,7 @@ __device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d) { return (uin
 // Tile kernel, SUM class (sum/avg/count_over_time, rate/increase on delta schemas), no across-series aggregate.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int FN>
-__global__ void __launch_bounds__(TILE_THREADS, 2)
+__global__ void __launch_bounds__(TILE_LAUNCH_THREADS, 2)
 scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, int64_t n_series,
                      QueryParams q, double* __restrict__ out, TileSmem L,
                      int64_t* __restrict__ fallback_list, unsigned long long* __restrict__ fallback_count,
@@ -81,49 +81,50 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
   static_assert(TILE_NS == 8 && TILE_THREADS == 256 && TILE_MAXC == 4 && TILE_MAXG == 64, "item mappings below assume this shape");
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool producer = warp == TILE_THREADS / 32;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   uint8_t* recbuf = smem + L.rec;
   double* vals = reinterpret_cast<double*>(smem + L.vals);
   double* otile = reinterpret_cast<double*>(smem + L.out);
-  TileSeries* SD = reinterpret_cast<TileSeries*>(smem + L.desc);
   uint64_t* gexcl = reinterpret_cast<uint64_t*>(smem + L.gtot);        // [series][slot]: XOR of the warp's earlier group totals
   uint64_t* gwtot = gexcl + TILE_NS * TILE_MAXG;                       // [series][warp]: XOR of the warp's 8 group totals
-  TileMeta* M = reinterpret_cast<TileMeta*>(smem + L.meta);
   const int64_t n_tiles = (n_series + TILE_NS - 1) / TILE_NS;
   if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   __syncthreads();
-  StepDiv sd; sd.init(q.step);
   int64_t winDur = q.inclusive ? q.window : q.window - 1; if (winDur < 0) winDur = 0;
   const double fdiv = (double)(q.inclusive ? winDur : winDur + 1), frcp = 1.0 / fdiv;     // RateFunctions.scala:436-442
   const int64_t S0 = q.start - winDur, E0 = q.start;
-  uint32_t parity = 0;
-  int64_t rows_scanned = 0, bytes_scanned = 0;
-  const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  auto bar_consumers = [] { asm volatile("bar.sync 1, %0;" ::"n"(TILE_THREADS) : "memory"); };
+  // Every tile passes two CTA-wide barriers: A = "descriptors of the tile are ready" (producer -> consumers),
+  // B = "the tile's record bytes are dead" (consumers -> producer: the staging buffer may be refilled).  The producer warp
+  // loads and resolves tile t+1 while the consumers reduce the windows of tile t.
 
-  auto issue_tile = [&](int64_t t) -> bool {          // returns whether the tile is staged through TMA
-    const int64_t i0 = t * TILE_NS, i1 = (i0 + TILE_NS < n_series) ? i0 + TILE_NS : n_series;
-    const int64_t o = rec_off[i0];
-    const uint32_t bytes = (uint32_t)(rec_off[i1] - o);
-    if (bytes > L.rec_cap - 64) return false;
-    if (tid == 0) { mbar_expect_tx(bar, bytes); tma_load_1d(recbuf, arena + o, bytes, bar); }
-    return true;
-  };
-  int64_t t = blockIdx.x;
-  bool staged = (t < n_tiles) ? issue_tile(t) : false;
-
-  for (; t < n_tiles; t += gridDim.x) {
-    const int64_t i0 = t * TILE_NS;
-    const int ns = (int)((i0 + TILE_NS < n_series ? i0 + TILE_NS : n_series) - i0);
-    const int64_t tile_base = rec_off[i0];
-    if (staged) { mbar_wait(bar, parity); parity ^= 1; }
-    // ------------------------------------------------------------------ setup: warp w <-> series w, lane = chunk * 8 + quantity
-    {
-      TileSeries& S = SD[warp];
-      const int c = lane >> 3, j = lane & 7;
+  if (producer) {
+    // ================================================================== producer warp: tile load + per-series setup
+    StepDiv sd; sd.init(q.step);
+    uint32_t parity = 0;
+    int64_t rows_scanned = 0, bytes_scanned = 0;
+    int b = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, b ^= 1) {
+      TileSeries* SDn = reinterpret_cast<TileSeries*>(smem + L.desc + b * L.desc_stride);
+      TileMeta* Mn = reinterpret_cast<TileMeta*>(smem + L.meta + b * 128);
+      const int64_t i0 = t * TILE_NS, i1 = (i0 + TILE_NS < n_series) ? i0 + TILE_NS : n_series;
+      const int ns = (int)(i1 - i0);
+      const int64_t tile_base = rec_off[i0];
+      const uint32_t tile_bytes = (uint32_t)(rec_off[i1] - tile_base);
+      const bool staged = tile_bytes <= L.rec_cap - 64;
+      if (staged) {
+        if (lane == 0) { mbar_expect_tx(bar, tile_bytes); tma_load_1d(recbuf, arena + tile_base, tile_bytes, bar); }
+        mbar_wait(bar, parity); parity ^= 1;
+      }
+      // ---------------------------------------------------------------- setup: lane = series * 4 + chunk
+      const int s = lane >> 2, c = lane & 3, lb = lane & 28;
+      TileSeries& S = SDn[s];
+      const bool present = s < ns;
       bool regular = false; int n = 0, cLo = 0; uint32_t roff = 0;
       const uint8_t* rec = recbuf;
-      if (warp < ns && staged) {
-        roff = (uint32_t)(rec_off[i0 + warp] - tile_base);
+      if (present && staged) {
+        roff = (uint32_t)(rec_off[i0 + s] - tile_base);
         rec = recbuf + roff;
         const RecordHeader* h = reinterpret_cast<const RecordHeader*>(rec);
         const ChunkEntry* E = reinterpret_cast<const ChunkEntry*>(rec + sizeof(RecordHeader));
@@ -136,7 +137,7 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
         regular = n <= TILE_MAXC && (n == 0 || (h->flags & REC_ALL_TS_CONST));
       }
       const ChunkEntry* E = reinterpret_cast<const ChunkEntry*>(rec + sizeof(RecordHeader)) + cLo;
-      const bool have = regular && c < n;
+      bool have = regular && c < n;
       int64_t init = 0, end_time = 0; int tlen = 0, vlen = 0, ng = 0, vwire = 0, nrows = 0, num_rows = 0, vbytes = 0; uint32_t voff = 0, w12 = 0;
       bool okc = true;
       if (have) {
@@ -151,100 +152,135 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
         else okc = false;
         if ((int64_t)slope != q.step || tlen <= 0 || vlen <= 0) okc = false;
         nrows = num_rows < tlen ? num_rows : tlen; if (vlen < nrows) nrows = vlen;
-        if (!okc) { ng = 0; vlen = 0; }
       }
-      regular = regular && __all_sync(0xffffffffu, okc);
-      // exclusive prefixes over the series' chunks (lanes 0, 8, 16, 24 hold chunk 0..3)
+      const unsigned okm = __ballot_sync(0xffffffffu, okc);     // (not inside the &&: every lane must take part)
+      regular = regular && ((okm >> lb) & 0xfu) == 0xfu;
+      have = have && regular;
+      if (!have) { ng = 0; nrows = 0; }
+      // exclusive prefix / total over the series' chunks (lanes lb .. lb+3)
       auto xpre = [&](int v, int& total) -> int {
-        const int a0 = __shfl_sync(0xffffffffu, v, 0), a1 = __shfl_sync(0xffffffffu, v, 8), a2 = __shfl_sync(0xffffffffu, v, 16), a3 = __shfl_sync(0xffffffffu, v, 24);
+        const int a0 = __shfl_sync(0xffffffffu, v, lb), a1 = __shfl_sync(0xffffffffu, v, lb + 1), a2 = __shfl_sync(0xffffffffu, v, lb + 2), a3 = __shfl_sync(0xffffffffu, v, lb + 3);
         total = a0 + a1 + a2 + a3;
         return (c > 0 ? a0 : 0) + (c > 1 ? a1 : 0) + (c > 2 ? a2 : 0);
       };
-      int ngroups = 0, nrows_tot = 0;
-      const int grp_base = xpre(ng, ngroups), row_base = xpre(vlen, nrows_tot);
-      if (ngroups > TILE_MAXG || nrows_tot + 2 > (int)L.vals_pitch) regular = false;
-      if (warp < ns && regular) {
-        // three divisions per chunk (lane quantity j): s0, e0 = unclamped first / last row of window 0; v4 = last window whose
-        // start is <= endTime.  The other bounds of scan_fast.cuh chunk_interval follow from these and the neighbours':
-        //   ceil((init - E0)/step) = -e0           floor((lastTs - S0)/step) = nrows - 1 - s0
-        //   ceil((max(prevEnd, prevLastTs) + 1 - S0)/step) = max(prev.v4 + 1, prev.tlen - prev.s0)
-        //   floor((next.init - 1 - E0)/step) = -(next.e0 + 1)
-        int64_t v = 0;
-        if (have) {
-          if (j == 0) v = sd.ceil_div(S0 - init);
-          else if (j == 1) v = sd.floor_div(E0 - init);
-          else if (j == 2) v = sd.floor_div(end_time - S0);
-        }
-        const int lb = lane & 24;
-        const int64_t s0 = __shfl_sync(0xffffffffu, v, lb), e0 = __shfl_sync(0xffffffffu, v, lb + 1), v4 = __shfl_sync(0xffffffffu, v, lb + 2);
-        const int64_t s0p = __shfl_up_sync(0xffffffffu, s0, 8), v4p = __shfl_up_sync(0xffffffffu, v4, 8), e0n = __shfl_down_sync(0xffffffffu, e0, 8);
-        const int tlenp = __shfl_up_sync(0xffffffffu, tlen, 8);
-        const int64_t endp = __shfl_up_sync(0xffffffffu, end_time, 8);
-        int64_t kA = -e0;
-        if (c > 0) { int64_t x = v4p + 1; const int64_t y = (int64_t)tlenp - s0p; if (y > x) x = y; if (x > kA) kA = x; }
-        int64_t kB = (int64_t)(nrows - 1) - s0;
-        { const int64_t x = (c + 1 < n) ? -(e0n + 1) : (int64_t)q.T; if (x < kB) kB = x; }
-        if (v4 < kB) kB = v4;
-        if (kA < 0) kA = 0;
-        if (kB > q.T - 1) kB = q.T - 1;
-        const int64_t sA = s0 + kA, eA = e0 + kA;
-        const bool ok = have && kA <= kB && eA >= sA;
-        const int Wr = ok ? (int)(eA - sA) : 0;
-        const int nwin = ok ? (int)(kB - kA + 1) : 0;
-        // blocked only when the windows are long enough to amortise a block; short windows go through the per-window path
-        const bool blocked = ok && Wr >= BLK_R - 1;
-        const int nb = blocked ? (nwin + BLK_R - 1) / BLK_R : 0;
-        int nblocks = 0, covered = 0;
-        const int blk0 = xpre(nb, nblocks); (void)xpre(blocked ? nwin : 0, covered);
-        if (have && j == 0) {
-          TileChunk& ch = S.c[c];
-          ch.init = init; ch.end_time = end_time; ch.nrows = nrows; ch.row_base = row_base;
-          ch.val_off = voff; ch.wire = vwire; ch.ngroups = ng; ch.grp_base = grp_base; ch.tlen = tlen; ch.vlen = vlen;
-          ch.kA = blocked ? (int)kA : 0; ch.kB = blocked ? (int)kB : -1; ch.sA = (int)sA; ch.Wr = Wr; ch.blk0 = blk0; ch.blk_n = nb;
-          ch.s0 = (int)s0; ch.e0 = (int)e0;
-          if (vwire == WIRE_XOR) {
-            const uint32_t po = w12 >> 16;
-            ch.first = ld64(recbuf + voff + po); ch.grp_off = voff + po + 8; ch.tab_off = voff + XOR_OFF_GROUPTAB;
-          } else { ch.first = 0; ch.grp_off = 0; ch.tab_off = 0; }
-          // CountingChunkInfoIterator, ChunkSetInfo.scala:336-380: every chunk in range is pulled, except one that starts after
-          // the last window end (the window iterator never reaches it)
-          const int64_t lastEnd = q.start + (int64_t)(q.T - 1) * q.step;
-          if (!(c > 0 && !(endp < lastEnd))) { rows_scanned += num_rows; bytes_scanned += vbytes; }
-        }
-        if (j == 1) S.gb[c] = have ? grp_base : 0x7fffffff;
-        if (lane == 0) {
+      int ngroups = 0;
+      const int grp_base = xpre(ng, ngroups);
+      // three divisions per chunk: s0, e0 = unclamped first / last row of window 0; v4 = last window whose start is <= endTime.
+      // The other bounds of scan_fast.cuh chunk_interval follow from these and the neighbours':
+      //   ceil((init - E0)/step) = -e0           floor((lastTs - S0)/step) = nrows - 1 - s0
+      //   ceil((max(prevEnd, prevLastTs) + 1 - S0)/step) = max(prev.v4 + 1, prev.tlen - prev.s0)
+      //   floor((next.init - 1 - E0)/step) = -(next.e0 + 1)
+      int64_t s0 = 0, e0 = 0, v4 = 0;
+      if (have) { s0 = sd.ceil_div(S0 - init); e0 = sd.floor_div(E0 - init); v4 = sd.floor_div(end_time - S0); }
+      const int64_t s0p = __shfl_up_sync(0xffffffffu, s0, 1), v4p = __shfl_up_sync(0xffffffffu, v4, 1), e0n = __shfl_down_sync(0xffffffffu, e0, 1);
+      const int tlenp = __shfl_up_sync(0xffffffffu, tlen, 1);
+      const int64_t endp = __shfl_up_sync(0xffffffffu, end_time, 1);
+      int64_t kA = -e0;
+      if (c > 0) { int64_t x = v4p + 1; const int64_t y = (int64_t)tlenp - s0p; if (y > x) x = y; if (x > kA) kA = x; }
+      int64_t kB = (int64_t)(nrows - 1) - s0;
+      { const int64_t x = (c + 1 < n) ? -(e0n + 1) : (int64_t)q.T; if (x < kB) kB = x; }
+      if (v4 < kB) kB = v4;
+      if (kA < 0) kA = 0;
+      if (kB > q.T - 1) kB = q.T - 1;
+      const int64_t sA = s0 + kA, eA = e0 + kA;
+      const bool ok = have && kA <= kB && eA >= sA;
+      const int Wr = ok ? (int)(eA - sA) : 0;
+      const int nwin = ok ? (int)(kB - kA + 1) : 0;
+      // blocked only when the windows are long enough to amortise a block; short windows go through the per-window path
+      const bool blocked = ok && Wr >= BLK_R - 1;
+      const int nb = blocked ? (nwin + BLK_R - 1) / BLK_R : 0;
+      // zero rows around the chunk so that blocked sums read clamped-away rows as +0.0 without a bounds check
+      int lowz = 0, highz = 0;
+      if (blocked) {
+        if (sA < 0) lowz = (int)-sA;
+        const int64_t over = sA + (nwin - 1) + Wr - (nrows - 1); if (over > 0) highz = (int)over;
+      }
+      int need = 0;
+      (void)xpre(lowz + nrows + highz, need);
+      const bool padded = need + BLK_R <= (int)L.vals_pitch;
+      if (!padded) { lowz = 0; highz = 0; }
+      int nrows_tot = 0;
+      const int row_base = xpre(lowz + nrows + highz, nrows_tot) + lowz;
+      if (ngroups > TILE_MAXG || nrows_tot + 2 > (int)L.vals_pitch) { regular = false; have = false; }
+      int nblocks = 0, covered = 0;
+      const int blk0 = xpre(have ? nb : 0, nblocks); (void)xpre(have && blocked ? nwin : 0, covered);
+      if (have) {
+        TileChunk& ch = S.c[c];
+        ch.init = init; ch.end_time = end_time; ch.nrows = nrows; ch.row_base = row_base;
+        ch.val_off = voff; ch.wire = vwire; ch.ngroups = ng; ch.grp_base = grp_base; ch.tlen = tlen; ch.vlen = vlen;
+        ch.kA = blocked ? (int)kA : 0; ch.kB = blocked ? (int)kB : -1; ch.sA = (int)sA; ch.Wr = Wr; ch.blk0 = blk0; ch.blk_n = nb;
+        ch.s0 = (int)s0; ch.e0 = (int)e0;
+        if (vwire == WIRE_XOR) {
+          const uint32_t po = w12 >> 16;
+          ch.first = ld64(recbuf + voff + po); ch.grp_off = voff + po + 8; ch.tab_off = voff + XOR_OFF_GROUPTAB;
+        } else { ch.first = 0; ch.grp_off = 0; ch.tab_off = 0; }
+        ch.lowz = lowz; ch.highz = highz;          // zeroed by the consumers before they decode the tile
+        // CountingChunkInfoIterator, ChunkSetInfo.scala:336-380: every chunk in range is pulled, except one that starts after
+        // the last window end (the window iterator never reaches it)
+        const int64_t lastEnd = q.start + (int64_t)(q.T - 1) * q.step;
+        if (!(c > 0 && !(endp < lastEnd))) { rows_scanned += num_rows; bytes_scanned += vbytes; }
+      }
+      S.gb[c] = have ? grp_base : 0x7fffffff;
+      const unsigned rawm = __ballot_sync(0xffffffffu, have && vwire == WIRE_RAW64);
+      const unsigned irrm = __ballot_sync(0xffffffffu, present && !regular);
+      const unsigned unpm = __ballot_sync(0xffffffffu, have && !padded);
+      if (c == 0) {
+        if (regular) {
           S.n = n; S.regular = 1; S.rec_off = (int)roff; S.nblocks = nblocks; S.nrest = q.T - covered; S.ngroups = ngroups; S.nrows = nrows_tot;
-        }
-        const unsigned rawm = __ballot_sync(0xffffffffu, have && vwire == WIRE_RAW64);
-        if (lane == 0) S.any_raw = rawm != 0;
-      } else if (lane == 0) {
-        S.n = 0; S.regular = warp < ns ? 0 : 2; S.nblocks = 0; S.nrest = 0; S.ngroups = 0; S.nrows = 0; S.any_raw = 0;
-        if (warp < ns) {
-          const unsigned long long slot = atomicAdd(fallback_count, 1ull);
-          fallback_list[slot] = i0 + warp;
+          S.any_raw = ((rawm >> lb) & 0xfu) != 0;
+        } else {
+          S.n = 0; S.regular = present ? 0 : 2; S.nblocks = 0; S.nrest = 0; S.ngroups = 0; S.nrows = 0; S.any_raw = 0;
+          if (present) {
+            const unsigned long long slot = atomicAdd(fallback_count, 1ull);
+            fallback_list[slot] = i0 + s;
+          }
         }
       }
-    }
-    __syncthreads();
-    if (warp == 0) {                             // tile work-list prefixes and flags (read after the next barrier)
-      const int s = lane & 7;
-      const bool reg = SD[s].regular == 1;
-      int p = reg ? SD[s].nblocks : 0, r = reg ? SD[s].nrest : 0;
+      // tile work-list prefixes over the series (values sit in the c == 0 lanes)
+      int p = (c == 0 && regular) ? nblocks : 0, r = (c == 0 && regular) ? q.T - covered : 0;
 #pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
+      for (int o = 1; o < 32; o <<= 1) {
         const int pp = __shfl_up_sync(0xffffffffu, p, o), rr = __shfl_up_sync(0xffffffffu, r, o);
-        if (s >= o) { p += pp; r += rr; }
+        if (lane >= o) { p += pp; r += rr; }
       }
-      const unsigned rawm = __ballot_sync(0xffffffffu, reg && SD[s].any_raw), irr = __ballot_sync(0xffffffffu, s < ns && !reg);
-      if (lane < 8) { M->pref[lane + 1] = p; M->rpref[lane + 1] = r; }
-      if (lane == 0) { M->pref[0] = 0; M->rpref[0] = 0; M->any_nan = 0; M->any_raw = rawm != 0; M->all_regular = irr == 0; }
+      if (c == 0) { Mn->pref[s + 1] = p; Mn->rpref[s + 1] = r; }
+      if (lane == 0) { Mn->pref[0] = 0; Mn->rpref[0] = 0; Mn->any_nan = 0; Mn->any_raw = rawm != 0; Mn->all_regular = irrm == 0; Mn->all_padded = unpm == 0; Mn->staged = staged; Mn->ns = ns; Mn->i0 = i0; }
+      __syncthreads();          // A(t)
+      __syncthreads();          // B(t)
+    }
+    if (rows_scanned | bytes_scanned) {
+      atomicAdd(&d_counters[0], (unsigned long long)rows_scanned); atomicAdd(&d_counters[1], (unsigned long long)bytes_scanned);
+    }
+    return;
+  }
+
+  // ==================================================================== consumer warps
+  const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  uint32_t parity = 0;
+  int b = 0;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, b ^= 1) {
+    const TileSeries* SDc = reinterpret_cast<const TileSeries*>(smem + L.desc + b * L.desc_stride);
+    TileMeta* Mc = reinterpret_cast<TileMeta*>(smem + L.meta + b * 128);
+    __syncthreads();            // A(t)
+    if (Mc->staged) { mbar_wait(bar, parity); parity ^= 1; }    // already complete (the producer saw it); orders the TMA writes
+    const int64_t i0 = Mc->i0; const int ns = Mc->ns;
+    // zero rows around the chunks (warp 0, lane = series * 4 + chunk); read by the blocked sums after the next barriers
+    if (warp == 0) {
+      const TileSeries& S = SDc[lane >> 2];
+      const int c = lane & 3;
+      if (S.regular == 1 && c < S.n) {
+        const TileChunk& ch = S.c[c];
+        double* zr = vals + (size_t)(lane >> 2) * L.vals_pitch + ch.row_base;
+        for (int i = 1; i <= ch.lowz; ++i) zr[-i] = 0.0;
+        for (int i = 0; i < ch.highz; ++i) zr[ch.nrows + i] = 0.0;
+      }
     }
     // ------------------------------------------------------------------ decode: two (series, group slot) items per thread
     // Lane -> series lane & 7 (neighbouring lanes store to different series' rows: with the odd row pitch the 8-byte stores
     // of a warp spread over all banks); warp w owns the slots 8w .. 8w+7 of every series: item jj -> slot 8w + 4jj + (lane >> 3).
     {
       const int ds = lane & 7;
-      const TileSeries& S = SD[ds];
+      const TileSeries& S = SDc[ds];
       const bool sreg = S.regular == 1;
       uint64_t d[2][8]; uint64_t excl[2]; int cc[2]; bool act[2];
 #pragma unroll
@@ -286,7 +322,7 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
       gexcl[ds * TILE_MAXG + warp * 8 + (lane >> 3)] = excl[0];
       gexcl[ds * TILE_MAXG + warp * 8 + 4 + (lane >> 3)] = excl[1];
       if (lane >= 24) gwtot[ds * 8 + warp] = tot0 ^ tot1;
-      __syncthreads();
+      bar_consumers();
       // value before group g of chunk c = first_c ^ (prefix at the slot) ^ (prefix at the chunk's first slot); the prefix at a
       // slot = XOR of the earlier warps' totals ^ the in-warp part
       uint32_t nz = 0x7ff00000u;
@@ -307,7 +343,7 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
           const uint64_t pre = jj ? pre1 : pre0;
           const int g = warp * 8 + jj * 4 + (lane >> 3) - ch.grp_base;
           uint64_t* dst = reinterpret_cast<uint64_t*>(vals + (size_t)ds * L.vals_pitch + ch.row_base) + 1 + g * 8;
-          const int nleft = act[jj] ? ch.vlen - 1 - g * 8 : 0;
+          const int nleft = act[jj] ? ch.nrows - 1 - g * 8 : 0;     // rows past nrows are never read as data
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const uint64_t b = d[jj][i] ^ pre;
@@ -316,12 +352,12 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
           if (act[jj] && g == 0) { dst[-1] = ch.first; const uint32_t e = ~(uint32_t)(ch.first >> 32) & 0x7ff00000u; nz = e < nz ? e : nz; }
         }
       }
-      if (nz == 0) M->any_nan = 1;               // an exponent of all ones: NaN or Inf (conservative)
+      if (nz == 0) Mc->any_nan = 1;               // an exponent of all ones: NaN or Inf (conservative)
     }
     // raw f64 vectors: plain copy (+ NaN/Inf presence)
-    if (M->any_raw) {
+    if (Mc->any_raw) {
       for (int s = 0; s < TILE_NS; ++s) {
-        const TileSeries& S = SD[s];
+        const TileSeries& S = SDc[s];
         if (S.regular != 1) continue;
         for (int c = 0; c < S.n; ++c) {
           const TileChunk& ch = S.c[c];
@@ -329,34 +365,35 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
           const uint64_t* src = reinterpret_cast<const uint64_t*>(recbuf + ch.val_off + 8);
           uint64_t* dst = reinterpret_cast<uint64_t*>(vals + (size_t)s * L.vals_pitch + ch.row_base);
           bool nan = false;
-          for (int r = tid; r < ch.vlen; r += TILE_THREADS) { const uint64_t b = src[r]; dst[r] = b; nan |= ((uint32_t)(b >> 32) & 0x7ff00000u) == 0x7ff00000u; }
-          if (nan) M->any_nan = 1;
+          for (int r = tid; r < ch.nrows; r += TILE_THREADS) { const uint64_t b = src[r]; dst[r] = b; nan |= ((uint32_t)(b >> 32) & 0x7ff00000u) == 0x7ff00000u; }
+          if (nan) Mc->any_nan = 1;
         }
       }
     }
     if (tid == 0) tma_store_wait_read();       // the previous tile's bulk store must have finished reading `otile`
-    __syncthreads();
-    // the record bytes are dead now: prefetch the next tile into the staging buffer while this one is reduced
-    const int64_t tnext = t + gridDim.x;
-    bool staged_next = false;
-    if (tnext < n_tiles) staged_next = issue_tile(tnext);
+    __syncthreads();            // B(t): the record bytes are dead, the producer refills the staging buffer
     // ------------------------------------------------------------------ windows: blocked single-chunk windows
+    bool all_reg;
     {
-      const bool any_nan = M->any_nan != 0;
-      const int nitems = M->pref[TILE_NS];
+      const bool any_nan = Mc->any_nan != 0, padded = Mc->all_padded != 0;
+      all_reg = Mc->all_regular != 0;              // read here: warp 0 rewrites the tile flags during the next tile's setup
+      const int nitems = Mc->pref[TILE_NS];
       for (int it = tid; it < nitems; it += TILE_THREADS) {
         int s = 0;
 #pragma unroll
-        for (int j = 1; j < TILE_NS; ++j) if (it >= M->pref[j]) s = j;
-        const TileSeries& S = SD[s];
-        const int B = it - M->pref[s];
+        for (int j = 1; j < TILE_NS; ++j) if (it >= Mc->pref[j]) s = j;
+        const TileSeries& S = SDc[s];
+        const int B = it - Mc->pref[s];
         int c = 0; while (c + 1 < S.n && B >= S.c[c].blk0 + S.c[c].blk_n) ++c;
         const TileChunk& ch = S.c[c];
         const int b = B - ch.blk0;
         const int r0 = ch.sA + b * BLK_R;
         const double* slots = vals + (size_t)s * L.vals_pitch + ch.row_base;
         double acc[BLK_R]; int cnt[BLK_R];
-        if (any_nan) blocked_sum<true>(slots, r0, ch.nrows, ch.Wr, acc, cnt); else blocked_sum<false>(slots, r0, ch.nrows, ch.Wr, acc, cnt);
+        constexpr bool NEED_CNT = FN == FN_AVG || FN == FN_COUNT;
+        if (any_nan) blocked_sum<true, true, true>(slots, r0, ch.nrows, ch.Wr, acc, cnt);
+        else if (padded) blocked_sum<false, false, NEED_CNT>(slots, r0, ch.nrows, ch.Wr, acc, cnt);
+        else blocked_sum<false, true, NEED_CNT>(slots, r0, ch.nrows, ch.Wr, acc, cnt);
         const int k0 = ch.kA + b * BLK_R;
         int nw = ch.kB - k0 + 1; if (nw > BLK_R) nw = BLK_R;
         double* o = otile + (size_t)s * L.out_pitch + k0;
@@ -364,13 +401,13 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
         for (int j = 0; j < BLK_R; ++j) if (j < nw) o[j] = tile_finish<FN>(acc[j], cnt[j], fdiv, frcp);
       }
       // ---------------------------------------------------------------- windows: everything else (chunk junctions, short windows)
-      const int nrest = M->rpref[TILE_NS];
+      const int nrest = Mc->rpref[TILE_NS];
       for (int it = tid; it < nrest; it += TILE_THREADS) {
         int s = 0;
 #pragma unroll
-        for (int j = 1; j < TILE_NS; ++j) if (it >= M->rpref[j]) s = j;
-        const TileSeries& S = SD[s];
-        int u = it - M->rpref[s];
+        for (int j = 1; j < TILE_NS; ++j) if (it >= Mc->rpref[j]) s = j;
+        const TileSeries& S = SDc[s];
+        int u = it - Mc->rpref[s];
         int prev = -1; bool found = false;          // u-th window not covered by a blocked interval
         for (int c = 0; c < S.n && !found; ++c) {
           if (S.c[c].kA > S.c[c].kB) continue;
@@ -385,27 +422,23 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
       }
     }
     fence_async_smem();        // make this thread's writes to the output tile visible to the async proxy (bulk store below)
-    __syncthreads();
+    bar_consumers();
     // ------------------------------------------------------------------ results: one bulk store for the tile (regular rows only)
     {
       double* gout = out + (size_t)i0 * q.T;
       const uint32_t bytes = (uint32_t)ns * (uint32_t)q.T * 8u;
-      if (M->all_regular && out_aligned && (bytes & 15) == 0 && (((size_t)i0 * q.T * 8) & 15) == 0) {
+      if (all_reg && out_aligned && (bytes & 15) == 0 && (((size_t)i0 * q.T * 8) & 15) == 0) {
         if (tid == 0) tma_store_1d(gout, otile, bytes);
       } else {
         for (int s = 0; s < ns; ++s) {
-          if (SD[s].regular != 1) continue;
+          if (SDc[s].regular != 1) continue;
           for (int k = tid; k < q.T; k += TILE_THREADS) gout[(size_t)s * q.T + k] = otile[(size_t)s * L.out_pitch + k];
         }
-        __syncthreads();
+        bar_consumers();
       }
     }
-    staged = staged_next;
   }
   if (tid == 0) tma_store_wait_read();
-  if (rows_scanned | bytes_scanned) {
-    atomicAdd(&d_counters[0], (unsigned long long)rows_scanned); atomicAdd(&d_counters[1], (unsigned long long)bytes_scanned);
-  }
 }
 
 } // namespace filo

@@ -5,7 +5,8 @@
 #include "scan_params.h"
 namespace filo {
 constexpr int TILE_NS = 8;               // series per tile (even: keeps the bulk store 16-byte aligned for odd T)
-constexpr int TILE_THREADS = 256;
+constexpr int TILE_THREADS = 256;        // consumer threads (decode + windows)
+constexpr int TILE_LAUNCH_THREADS = TILE_THREADS + 32;   // + one producer warp (tile load, per-series setup of the next tile)
 constexpr int TILE_MAXC = 4;             // chunks in range per series on the fast path
 constexpr int TILE_MAXG = 64;            // NibblePack groups per series on the fast path (64 * 8 = 512 rows)
 
@@ -20,6 +21,7 @@ struct TileChunk {
   int32_t blk0, blk_n;
   int32_t tlen, vlen;         // timestamp / value vector lengths
   int32_t s0, e0;             // unclamped first / last row of window k = 0 (rows advance by one per window)
+  int32_t lowz, highz;        // zero rows before / after the chunk's rows (clamped windows read them as +0.0)
 };
 struct TileSeries {
   int32_t n, regular, rec_off, nblocks, nrest, ngroups, nrows, any_raw;
@@ -30,25 +32,27 @@ struct TileSeries {
 struct TileMeta {                         // per-tile work-list prefixes and flags
   int32_t pref[TILE_NS + 1];              // blocked work items per series (prefix)
   int32_t rpref[TILE_NS + 1];             // other windows per series (prefix)
-  int32_t any_nan, any_raw, all_regular, pad;
+  int32_t any_nan, any_raw, all_regular, all_padded;
+  int32_t staged, ns; int64_t i0;
 };
 
 struct TileSmem {                         // byte offsets inside dynamic shared memory (all multiples of 128)
   uint32_t rec, vals, out, desc, gtot, meta, total;
-  uint32_t rec_cap, vals_pitch /*doubles per series*/, out_pitch /*doubles per series = T*/;
+  uint32_t rec_cap, vals_pitch /*doubles per series*/, out_pitch /*doubles per series = T*/, desc_stride /*bytes between the two descriptor buffers*/;
 };
-FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t T) {
+FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t T, uint32_t pad_rows) {
   TileSmem L;
   L.rec_cap = align_up(TILE_NS * max_rec_bytes + 128, 128);
-  L.vals_pitch = (max_rows + 2 + 1) | 1;                       // odd pitch (doubles)
+  L.desc_stride = align_up(TILE_NS * (uint32_t)sizeof(TileSeries), 128);
+  L.vals_pitch = (max_rows + pad_rows + 2 + 1) | 1;            // odd pitch (doubles); pad_rows: zero rows for clamped windows
   L.out_pitch = T;
   uint32_t o = 128;                                            // mbarrier slot
   L.rec = o; o += L.rec_cap;
   L.vals = o; o += align_up(TILE_NS * L.vals_pitch * 8, 128);
   L.out = o; o += align_up(TILE_NS * T * 8, 128);
-  L.desc = o; o += align_up(TILE_NS * (uint32_t)sizeof(TileSeries), 128);
+  L.desc = o; o += 2 * align_up(TILE_NS * (uint32_t)sizeof(TileSeries), 128);      // double-buffered: setup of tile t+1 overlaps tile t
   L.gtot = o; o += TILE_NS * TILE_MAXG * 8 + TILE_NS * (TILE_THREADS / 32) * 8;   // per-slot in-warp prefixes + per-warp totals
-  L.meta = o; o += 128;
+  L.meta = o; o += 2 * 128;
   L.total = o;
   return L;
 }
