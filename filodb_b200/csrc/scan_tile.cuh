@@ -307,10 +307,10 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
           const uint32_t* wp = base + (bit >> 5);
           const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
           const uint32_t lo = __funnelshift_r(w0, w1, bit), hi = __funnelshift_r(w1, w2, bit);
-          const uint64_t val = ((((uint64_t)hi << 32) | lo) & fmask) << tz;
-          x ^= on ? val : 0ull;
+          const uint64_t fm = on ? fmask : 0ull;
+          x ^= (((uint64_t)hi << 32) | lo) & fm;       // running XOR of the unshifted fields ((a ^ b) << tz == (a << tz) ^ (b << tz))
           bit += on ? numBits : 0u;
-          d[jj][i] = x;
+          d[jj][i] = x << tz;
         }
       }
       // XOR of the group totals of earlier slots of the same series inside this warp (lanes ds, ds+8, ds+16, ds+24; item 0 first)
@@ -397,8 +397,33 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
         const int k0 = ch.kA + b * BLK_R;
         int nw = ch.kB - k0 + 1; if (nw > BLK_R) nw = BLK_R;
         double* o = otile + (size_t)s * L.out_pitch + k0;
+        if (FN == FN_RATE) {
+          // sum / window * 1000 for 15 windows: one range test for the whole block (div_invariant's exactness condition),
+          // then the two-FMA correction without per-window branches; any unusual quotient (0, NaN, Inf, tiny, huge) sends
+          // the block through the per-window version
+          double q0[BLK_R]; uint32_t worst = 0;
 #pragma unroll
-        for (int j = 0; j < BLK_R; ++j) if (j < nw) o[j] = tile_finish<FN>(acc[j], cnt[j], fdiv, frcp);
+          for (int j = 0; j < BLK_R; ++j) {
+            acc[j] = cnt[j] ? acc[j] : __longlong_as_double(0x7ff8000000000000LL);
+            q0[j] = __dmul_rn(acc[j], frcp);
+            const uint32_t e = ((uint32_t)__double2hiint(q0[j]) & 0x7ff00000u) - (65u << 20);
+            worst = e > worst ? e : worst;
+          }
+          if (worst < (1918u << 20)) {
+#pragma unroll
+            for (int j = 0; j < BLK_R; ++j) {
+              const double r = __fma_rn(-q0[j], fdiv, acc[j]);
+              const double v = __dmul_rn(__fma_rn(r, frcp, q0[j]), 1000.0);
+              if (j < nw) o[j] = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLK_R; ++j) if (j < nw) o[j] = __dmul_rn(div_invariant(acc[j], fdiv, frcp), 1000.0);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < BLK_R; ++j) if (j < nw) o[j] = tile_finish<FN>(acc[j], cnt[j], fdiv, frcp);
+        }
       }
       // ---------------------------------------------------------------- windows: everything else (chunk junctions, short windows)
       const int nrest = Mc->rpref[TILE_NS];
