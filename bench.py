@@ -179,6 +179,19 @@ def synth_group_ids(seed, base, n, n_groups):
     return (h % np.uint64(n_groups)).astype(np.int32)
 
 
+def measured_traffic(workload, S):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu capture of this same
+    command (profiles/traffic.json: bytes per launch at the recorded series count); None when not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            rec = json.load(f).get(workload)
+        if rec and int(rec["series"]) == int(S):
+            return float(rec["dram_bytes_per_launch"])
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def run_reference(args, rank, world):
     """Reference arm: the reference's own CPU path for this query — the C++ restatement under oracle/ (the JVM cannot run
     in this image) — on all host threads, on a bounded sample of the same workload."""
@@ -299,7 +312,8 @@ def main():
     alg_bytes = ti.algorithmic_bytes + (S * 4 if aggr != capi.AGG_NONE else 0) + out_bytes
     kern_ms = float(np.median(kern_ns)) / 1e6
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9
-    launches_per_step = 1 if aggr == capi.AGG_NONE else 2
+    launches_per_step = int(st["kernel_launches"])
+    traffic = measured_traffic(args.workload, S)
 
     line = {"metric": "samples/s scanned+aggregated (rate over 10M series); % HBM roofline", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -310,7 +324,7 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "scan_series_kernel" if aggr == capi.AGG_NONE else "scan_agg_kernel",
+                         "traffic": traffic, "kernel": "scan_tile_kernel (CTA-tile scan; + v2 fallback pass" + ("" if aggr == capi.AGG_NONE else " + merge_partials") + ")",
                          "kernel_ms": kern_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src}}
 
     # ---- end-to-end through the C-ABI with host buffers (load + query + result read-back every step)

@@ -504,12 +504,13 @@ extern "C" int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t
   // at either end; when that does not leave room for two CTAs per SM the tile kernel falls back to checked loads
   TileSmem TL;
   {
+    const bool ctr = fn_cls == CLASS_COUNTER;
     const uint64_t wrows = (uint64_t)(q.window / q.step) + 1;
-    const uint32_t full_pad = (uint32_t)std::min<uint64_t>(2 * wrows, 1u << 20) + 16;
-    TL = tile_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)q.T, full_pad);
-    if (((size_t)TL.total + 1024) * 2 > (size_t)228 * 1024) TL = tile_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)q.T, 16);
+    const uint32_t full_pad = ctr ? 0u : (uint32_t)std::min<uint64_t>(2 * wrows, 1u << 20) + 16;
+    TL = tile_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)q.T, full_pad, ctr);
+    if (((size_t)TL.total + 1024) * 2 > (size_t)228 * 1024) TL = tile_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)q.T, ctr ? 0u : 16u, ctr);
   }
-  const bool use_tile = use_v2 && !want_v2 && fn_cls == CLASS_SUM && t->n_series > 0 &&
+  const bool use_tile = use_v2 && !want_v2 && (fn_cls == CLASS_SUM || fn_cls == CLASS_COUNTER) && t->n_series > 0 &&
                         (size_t)TL.total + 1024 <= std::min<size_t>(ctx->max_smem_optin, 227 * 1024);
   auto run_per_series = [&](double* outp) -> int32_t {
     if (use_tile) {
@@ -523,7 +524,7 @@ extern "C" int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t
       LT.grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * ctas_per_sm));
       static const bool dbg = std::getenv("FILO_DEBUG_SYNC") != nullptr;
       if (dbg) { fprintf(stderr, "[filo] tile kernel fn=%d T=%d grid=%d smem=%u pitch=%u\n", fn, q.T, LT.grid, TL.total, TL.vals_pitch); fflush(stderr); }
-      CUDA_TRY(ctx, launch_scan_tile_sum(LT, outp, TL, d_list, d_cnt));
+      CUDA_TRY(ctx, launch_scan_tile(LT, outp, TL, d_list, d_cnt));
       if (dbg) { CUDA_TRY(ctx, cudaStreamSynchronize(s)); fprintf(stderr, "[filo] tile kernel done\n"); fflush(stderr); }
       ScanLaunch LF = L; LF.list = d_list; LF.list_count = d_cnt;
       CUDA_TRY(ctx, launch_scan_series_v2(LF, outp, rec_cap_used));
@@ -550,11 +551,26 @@ extern "C" int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t
     CUDA_TRY(ctx, tmp.alloc((void**)&pval, (size_t)t->n_items * q.T * 8));
     CUDA_TRY(ctx, tmp.alloc((void**)&pcnt, (size_t)t->n_items * q.T * 4));
     const int32_t* order = t->grouped ? t->d_order : nullptr;
-    CUDA_TRY(ctx, use_v2 ? launch_scan_agg_v2(L, order, t->d_item_begin, t->n_items, agg, pval, pcnt, acc_bytes, rec_cap_used)
-                         : launch_scan_agg(L, order, t->d_item_begin, t->n_items, agg, pval, pcnt, acc_bytes));
+    if (use_tile && q.T <= TILE_AGG_ACC * TILE_THREADS) {
+      // tile kernel folds every item into one partial row; items with a series it declines go through the v2 kernel
+      int64_t* d_list = nullptr; unsigned long long* d_cnt = nullptr;
+      CUDA_TRY(ctx, tmp.alloc((void**)&d_list, (size_t)t->n_items * 8));
+      CUDA_TRY(ctx, tmp.alloc((void**)&d_cnt, 16));
+      CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, 16, s));
+      ScanLaunch LT = L;
+      const int ctas_per_sm = ((size_t)TL.total + 1024) * 2 <= (size_t)228 * 1024 ? 2 : 1;
+      LT.grid = (int)std::max<int64_t>(1, std::min<int64_t>(t->n_items, (int64_t)ctx->sm_count * ctas_per_sm));
+      CUDA_TRY(ctx, launch_scan_tile_agg(LT, TL, order, t->d_item_begin, t->n_items, agg, pval, pcnt, d_list, d_cnt));
+      ScanLaunch LF = L; LF.list = d_list; LF.list_count = d_cnt;
+      CUDA_TRY(ctx, launch_scan_agg_v2(LF, order, t->d_item_begin, t->n_items, agg, pval, pcnt, acc_bytes, rec_cap_used));
+      launches += 1;
+    } else {
+      CUDA_TRY(ctx, use_v2 ? launch_scan_agg_v2(L, order, t->d_item_begin, t->n_items, agg, pval, pcnt, acc_bytes, rec_cap_used)
+                           : launch_scan_agg(L, order, t->d_item_begin, t->n_items, agg, pval, pcnt, acc_bytes));
+    }
     CUDA_TRY(ctx, launch_merge_partials(pval, pcnt, t->d_gis, t->n_groups, q.T, agg, (flags & FILO_Q_PARTIAL) ? 1 : 0,
                                         (double*)d_out_values, (int64_t*)d_out_aux, s));
-    launches = 2;
+    launches += 2;
   }
   if (stats) {
     CUDA_TRY(ctx, cudaEventRecord(e1, s));

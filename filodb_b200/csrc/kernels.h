@@ -36,7 +36,9 @@ cudaError_t launch_scan_series_v2(const ScanLaunch& L, double* out, uint32_t rec
 cudaError_t launch_scan_agg_v2(const ScanLaunch& L, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg_op,
                                double* pval, uint32_t* pcnt, uint32_t acc_bytes, uint32_t rec_cap);
 size_t v2_smem_per_warp(uint32_t rec_cap, uint32_t scratch_bytes, uint32_t acc_bytes);
-cudaError_t launch_scan_tile_sum(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count);
+cudaError_t launch_scan_tile(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count);
+cudaError_t launch_scan_tile_agg(const ScanLaunch& L, const TileSmem& T, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg_op,
+                                 double* pval, uint32_t* pcnt, int64_t* fallback_list, unsigned long long* fallback_count);
 cudaError_t launch_merge_partials(const double* pval, const uint32_t* pcnt, const int64_t* gis, int n_groups, int T, int agg_op,
                                   int partial_out, double* out_val, int64_t* out_cnt, cudaStream_t s);
 cudaError_t launch_present(int agg_op, int64_t n, const double* vals, const int64_t* cnts, double* out, cudaStream_t s);

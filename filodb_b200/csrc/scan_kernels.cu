@@ -319,7 +319,9 @@ scan_agg_kernel_v2(const uint8_t* __restrict__ arena, const int64_t* __restrict_
                    const int64_t* __restrict__ item_begin, int64_t n_items,
                    QueryParams q, int agg_op, double* __restrict__ pval, uint32_t* __restrict__ pcnt,
                    uint32_t rec_cap, uint32_t scratch_bytes, uint32_t acc_bytes,
-                   unsigned long long* d_counters, int* d_err) {
+                   unsigned long long* d_counters, int* d_err,
+                   const int64_t* __restrict__ list, const unsigned long long* __restrict__ list_count) {
+  if (list) n_items = (int64_t)*list_count;              // fallback pass of the tile kernel: only the listed items
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t gw = (int64_t)blockIdx.x * FAST_WARPS + warp, nw = (int64_t)gridDim.x * FAST_WARPS;
@@ -338,18 +340,19 @@ scan_agg_kernel_v2(const uint8_t* __restrict__ arena, const int64_t* __restrict_
   // flattened (item, position) walk so that the next series to prefetch is always known
   int64_t it = gw;
   int64_t pos = 0, pend = 0;
-  auto advance_item = [&]() { while (it < n_items) { pos = item_begin[it]; pend = item_begin[it + 1]; if (pos < pend) return true; it += nw; } return false; };
+  auto real_item = [&](int64_t x) -> int64_t { return list ? list[x] : x; };
+  auto advance_item = [&]() { while (it < n_items) { const int64_t ri = real_item(it); pos = item_begin[ri]; pend = item_begin[ri + 1]; if (pos < pend) return true; it += nw; } return false; };
   bool have = advance_item();
   if (have) st.issue(order ? order[pos] : pos, lane);
   while (have) {
     for (int k = lane; k < q.T; k += 32) { acc[k] = ident; cnt[k] = 0; }
     __syncwarp();
-    const int64_t my_item = it;
+    const int64_t my_item = real_item(it);
     while (true) {
       const int64_t i = order ? order[pos] : pos;
       // next series in walk order
       int64_t npos = pos + 1, nit = it, npend = pend; bool nhave = true;
-      if (npos >= pend) { nit = it + nw; nhave = false; while (nit < n_items) { npos = item_begin[nit]; npend = item_begin[nit + 1]; if (npos < npend) { nhave = true; break; } nit += nw; } }
+      if (npos >= pend) { nit = it + nw; nhave = false; while (nit < n_items) { const int64_t ri = real_item(nit); npos = item_begin[ri]; npend = item_begin[ri + 1]; if (npos < npend) { nhave = true; break; } nit += nw; } }
       const int64_t inext = nhave ? (order ? order[npos] : npos) : -1;
       const uint8_t* rec = st.acquire(i);
       int err;
@@ -407,7 +410,7 @@ static cudaError_t launch_agg_v2_cls(const ScanLaunch& L, const int32_t* order, 
   cudaError_t e = cudaFuncSetAttribute(scan_agg_kernel_v2<CLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   scan_agg_kernel_v2<CLS><<<L.grid, FAST_WARPS * 32, smem, L.stream>>>(L.arena, L.rec_off, order, item_begin, n_items, L.q, agg_op, pval, pcnt,
-                                                                        rec_cap, L.scratch_bytes, acc_bytes, L.d_counters, L.d_err);
+                                                                        rec_cap, L.scratch_bytes, acc_bytes, L.d_counters, L.d_err, L.list, L.list_count);
   return cudaGetLastError();
 }
 cudaError_t launch_scan_agg_v2(const ScanLaunch& L, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg_op,
@@ -420,21 +423,41 @@ cudaError_t launch_scan_agg_v2(const ScanLaunch& L, const int32_t* order, const 
     default: return launch_agg_v2_cls<CLASS_POINT>(L, order, item_begin, n_items, agg_op, pval, pcnt, acc_bytes, rec_cap, smem);
   }
 }
-template <int FN>
-static cudaError_t launch_tile_fn(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count) {
-  cudaError_t e = cudaFuncSetAttribute(scan_tile_sum_kernel<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total);
+struct TileAggArgs { const int32_t* order; const int64_t* item_begin; int64_t n_items; int agg_op; double* pval; uint32_t* pcnt; };
+template <int CLS, int FN, bool AGG>
+static cudaError_t launch_tile_fn(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count,
+                                  const TileAggArgs& A) {
+  cudaError_t e = cudaFuncSetAttribute(scan_tile_kernel<CLS, FN, AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total);
   if (e != cudaSuccess) return e;
-  scan_tile_sum_kernel<FN><<<L.grid, TILE_LAUNCH_THREADS, T.total, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, T, fallback_list, fallback_count,
-                                                                         L.d_counters, L.d_err);
+  scan_tile_kernel<CLS, FN, AGG><<<L.grid, TILE_LAUNCH_THREADS, T.total, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, T, fallback_list, fallback_count,
+      L.d_counters, L.d_err, A.order, A.item_begin, A.n_items, A.agg_op, A.pval, A.pcnt);
   return cudaGetLastError();
 }
-cudaError_t launch_scan_tile_sum(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count) {
-  switch (L.q.fn) {
-    case FN_RATE: return launch_tile_fn<FN_RATE>(L, out, T, fallback_list, fallback_count);
-    case FN_AVG: return launch_tile_fn<FN_AVG>(L, out, T, fallback_list, fallback_count);
-    case FN_COUNT: return launch_tile_fn<FN_COUNT>(L, out, T, fallback_list, fallback_count);
-    default: return launch_tile_fn<FN_SUM>(L, out, T, fallback_list, fallback_count);      // FN_SUM, FN_INCREASE on a delta schema
+template <bool AGG>
+static cudaError_t launch_tile_any(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count,
+                                   const TileAggArgs& A) {
+  if (fn_class_of(L.q.fn, L.q.cumulative) == CLASS_COUNTER) {
+    switch (L.q.fn) {
+      case FN_RATE: return launch_tile_fn<CLASS_COUNTER, FN_RATE, AGG>(L, out, T, fallback_list, fallback_count, A);
+      case FN_INCREASE: return launch_tile_fn<CLASS_COUNTER, FN_INCREASE, AGG>(L, out, T, fallback_list, fallback_count, A);
+      default: return launch_tile_fn<CLASS_COUNTER, FN_DELTA, AGG>(L, out, T, fallback_list, fallback_count, A);
+    }
   }
+  switch (L.q.fn) {
+    case FN_RATE: return launch_tile_fn<CLASS_SUM, FN_RATE, AGG>(L, out, T, fallback_list, fallback_count, A);
+    case FN_AVG: return launch_tile_fn<CLASS_SUM, FN_AVG, AGG>(L, out, T, fallback_list, fallback_count, A);
+    case FN_COUNT: return launch_tile_fn<CLASS_SUM, FN_COUNT, AGG>(L, out, T, fallback_list, fallback_count, A);
+    default: return launch_tile_fn<CLASS_SUM, FN_SUM, AGG>(L, out, T, fallback_list, fallback_count, A);      // FN_SUM, FN_INCREASE on a delta schema
+  }
+}
+cudaError_t launch_scan_tile(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count) {
+  return launch_tile_any<false>(L, out, T, fallback_list, fallback_count, TileAggArgs{nullptr, nullptr, 0, 0, nullptr, nullptr});
+}
+// fused across-series aggregate: one partial row per item (same contract as launch_scan_agg_v2); items with an irregular series
+// are appended to fallback_list
+cudaError_t launch_scan_tile_agg(const ScanLaunch& L, const TileSmem& T, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg_op,
+                                 double* pval, uint32_t* pcnt, int64_t* fallback_list, unsigned long long* fallback_count) {
+  return launch_tile_any<true>(L, nullptr, T, fallback_list, fallback_count, TileAggArgs{order, item_begin, n_items, agg_op, pval, pcnt});
 }
 size_t v2_smem_per_warp(uint32_t rec_cap, uint32_t scratch_bytes, uint32_t acc_bytes) { return WARP_HDR_BYTES + (size_t)rec_cap + STAGE_BYTES + acc_bytes + scratch_bytes; }
 cudaError_t launch_scan_series(const ScanLaunch& L, double* out) {

@@ -66,18 +66,59 @@ __device__ __forceinline__ double tile_eval_window(const TileSeries& S, const do
   return sum;
 }
 
+// literal per-chunk fold of the counter functions for one window of a regular series: CounterChunkedRangeFunction.addChunks
+// (RangeFunction.scala:131-172), ChunkedRateFunctionBase (RateFunctions.scala:230-285), correction carry
+// (DoubleVector.scala:177-207, 375-391).  Rows of dropped chunks already hold the corrected values (see the kernel).
+template <int FN>
+__device__ __forceinline__ double tile_eval_counter(const TileSeries& S, const TileCtr* K, const double* vals, const QueryParams& q,
+                                                    int64_t wStart, int64_t wEnd, int k) {
+  const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
+  int32_t numSamples = 0; int64_t loT = INT64_MAX, hiT = 0; double loV = NaNv, hiV = NaNv;
+  bool some = false; double corrLast = 0.0, corr = 0.0;                // correctionMeta
+  for (int c = 0; c < S.n; ++c) {
+    const TileChunk& ch = S.c[c];
+    if (ch.end_time < wStart) continue;                                // ChunkSetInfo.scala:481-510
+    if (c > 0 && !(S.c[c - 1].end_time < wEnd)) continue;
+    int su = ch.s0 + k; if (su < 0) su = 0;
+    int eu = ch.e0 + k; if (eu > ch.nrows - 1) eu = ch.nrows - 1;
+    const double* v = vals + ch.row_base;
+    const double first = __longlong_as_double((long long)ch.first);
+    if (FN != FN_DELTA && some) { if (first != first || first < corrLast) corr = corr + corrLast; }
+    if (su <= eu) {
+      const int64_t tS = ch.init + (int64_t)su * q.step, tE = ch.init + (int64_t)eu * q.step;
+      const bool skip = FN != FN_DELTA && su == 0 && eu == 0 && first != first;      // RateFunctions.scala:255-256
+      if (!skip && (tS < loT || tE > hiT)) {
+        numSamples += eu - su + 1;
+        if (tS < loT) { loT = tS; loV = (FN != FN_DELTA && some) ? v[su] + corr : v[su]; }
+        if (tE > hiT) { hiT = tE; hiV = (FN != FN_DELTA && some) ? v[eu] + corr : v[eu]; }
+      }
+    }
+    if (FN != FN_DELTA) {
+      if (K[c].dropped) { corrLast = K[c].upd_last; corr = (some ? corr : 0.0) + K[c].upd_corr; }
+      else { corrLast = v[ch.vlen - 1]; corr = some ? corr : 0.0; }
+    }
+    some = true;
+  }
+  const int64_t cws = q.inclusive ? wStart : wStart - 1;               // RateFunctions.scala:270-285
+  if (hiT > loT) return extrapolated_rate(cws, wEnd, numSamples, loT, loV, hiT, hiV, FN != FN_DELTA, FN == FN_RATE);
+  return NaNv;
+}
+
 __device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) { return (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)v, src); }
 __device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d) { return (uint64_t)__shfl_up_sync(0xffffffffu, (unsigned long long)v, d); }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Tile kernel, SUM class (sum/avg/count_over_time, rate/increase on delta schemas), no across-series aggregate.
+// Tile kernel, no across-series aggregate.  CLS = CLASS_SUM: sum/avg/count_over_time, rate/increase on delta schemas;
+// CLS = CLASS_COUNTER: rate/increase on cumulative schemas (counter correction) and delta.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int FN>
+template <int CLS, int FN, bool AGG>
 __global__ void __launch_bounds__(TILE_LAUNCH_THREADS, 2)
-scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, int64_t n_series,
+scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, int64_t n_series,
                      QueryParams q, double* __restrict__ out, TileSmem L,
                      int64_t* __restrict__ fallback_list, unsigned long long* __restrict__ fallback_count,
-                     unsigned long long* d_counters, int* d_err) {
+                     unsigned long long* d_counters, int* d_err,
+                     const int32_t* __restrict__ order, const int64_t* __restrict__ item_begin, int64_t n_items, int agg_op,
+                     double* __restrict__ pval, uint32_t* __restrict__ pcnt) {
   static_assert(TILE_NS == 8 && TILE_THREADS == 256 && TILE_MAXC == 4 && TILE_MAXG == 64, "item mappings below assume this shape");
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -88,7 +129,18 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
   double* otile = reinterpret_cast<double*>(smem + L.out);
   uint64_t* gexcl = reinterpret_cast<uint64_t*>(smem + L.gtot);        // [series][slot]: XOR of the warp's earlier group totals
   uint64_t* gwtot = gexcl + TILE_NS * TILE_MAXG;                       // [series][warp]: XOR of the warp's 8 group totals
-  const int64_t n_tiles = (n_series + TILE_NS - 1) / TILE_NS;
+  // Tile walk.  Work items are strided over the CTAs; an item is a run of consecutive positions processed in tiles of
+  // TILE_NS.  Per-series mode: item = one tile of consecutive series.  AGG mode: item = <= seg series of ONE group in
+  // group-sorted order (positions index `order`), folded into one partial row per item (pval/pcnt, see scan_agg_kernel).
+  const int64_t n_work = AGG ? n_items : (n_series + TILE_NS - 1) / TILE_NS;
+  struct Walk { int64_t it, pb, pe; };
+  auto item_range = [&](Walk& w) {
+    if (AGG) { w.pb = item_begin[w.it]; w.pe = item_begin[w.it + 1]; }
+    else { w.pb = w.it * TILE_NS; w.pe = w.pb + TILE_NS < n_series ? w.pb + TILE_NS : n_series; }
+  };
+  auto walk_seek = [&](Walk& w) -> bool { while (w.it < n_work) { item_range(w); if (w.pb < w.pe) return true; w.it += gridDim.x; } return false; };
+  auto walk_start = [&](Walk& w) -> bool { w.it = blockIdx.x; return walk_seek(w); };
+  auto walk_next = [&](Walk& w) -> bool { w.pb += TILE_NS; if (w.pb < w.pe) return true; w.it += gridDim.x; return walk_seek(w); };
   if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   __syncthreads();
   int64_t winDur = q.inclusive ? q.window : q.window - 1; if (winDur < 0) winDur = 0;
@@ -105,26 +157,37 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
     uint32_t parity = 0;
     int64_t rows_scanned = 0, bytes_scanned = 0;
     int b = 0;
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, b ^= 1) {
+    Walk w;
+    for (bool more = walk_start(w); more; more = walk_next(w), b ^= 1) {
       TileSeries* SDn = reinterpret_cast<TileSeries*>(smem + L.desc + b * L.desc_stride);
       TileMeta* Mn = reinterpret_cast<TileMeta*>(smem + L.meta + b * 128);
-      const int64_t i0 = t * TILE_NS, i1 = (i0 + TILE_NS < n_series) ? i0 + TILE_NS : n_series;
-      const int ns = (int)(i1 - i0);
-      const int64_t tile_base = rec_off[i0];
-      const uint32_t tile_bytes = (uint32_t)(rec_off[i1] - tile_base);
+      TileCtr* CTn = reinterpret_cast<TileCtr*>(smem + L.ctr) + b * (TILE_NS * TILE_MAXC);
+      const int64_t i0 = w.pb;
+      const int ns = (int)(w.pe - w.pb < TILE_NS ? w.pe - w.pb : TILE_NS);
+      // lanes 0..ns-1: series id, record offset and size; records land back to back in the staging buffer
+      int64_t sid_l = -1, src_l = 0; uint32_t sz_l = 0;
+      if (lane < ns) { sid_l = (AGG && order) ? (int64_t)order[i0 + lane] : i0 + lane; src_l = rec_off[sid_l]; sz_l = (uint32_t)(rec_off[sid_l + 1] - src_l); }
+      uint32_t incl = sz_l;
+#pragma unroll
+      for (int o = 1; o < TILE_NS; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+      const uint32_t tile_bytes = __shfl_sync(0xffffffffu, incl, TILE_NS - 1), roff_l = incl - sz_l;
       const bool staged = tile_bytes <= L.rec_cap - 64;
       if (staged) {
-        if (lane == 0) { mbar_expect_tx(bar, tile_bytes); tma_load_1d(recbuf, arena + tile_base, tile_bytes, bar); }
+        if (lane == 0) mbar_expect_tx(bar, tile_bytes);
+        __syncwarp();
+        if (AGG) { if (lane < ns) tma_load_1d(recbuf + roff_l, arena + src_l, sz_l, bar); }      // gathered through `order`
+        else if (lane == 0) tma_load_1d(recbuf, arena + src_l, tile_bytes, bar);                   // adjacent records: one copy
         mbar_wait(bar, parity); parity ^= 1;
       }
       // ---------------------------------------------------------------- setup: lane = series * 4 + chunk
       const int s = lane >> 2, c = lane & 3, lb = lane & 28;
       TileSeries& S = SDn[s];
       const bool present = s < ns;
-      bool regular = false; int n = 0, cLo = 0; uint32_t roff = 0;
+      bool regular = false; int n = 0, cLo = 0;
+      const uint32_t roff = __shfl_sync(0xffffffffu, roff_l, s);
+      const int64_t sid = __shfl_sync(0xffffffffu, sid_l, s);
       const uint8_t* rec = recbuf;
       if (present && staged) {
-        roff = (uint32_t)(rec_off[i0 + s] - tile_base);
         rec = recbuf + roff;
         const RecordHeader* h = reinterpret_cast<const RecordHeader*>(rec);
         const ChunkEntry* E = reinterpret_cast<const ChunkEntry*>(rec + sizeof(RecordHeader));
@@ -138,12 +201,13 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
       }
       const ChunkEntry* E = reinterpret_cast<const ChunkEntry*>(rec + sizeof(RecordHeader)) + cLo;
       bool have = regular && c < n;
-      int64_t init = 0, end_time = 0; int tlen = 0, vlen = 0, ng = 0, vwire = 0, nrows = 0, num_rows = 0, vbytes = 0; uint32_t voff = 0, w12 = 0;
+      int64_t init = 0, end_time = 0; int tlen = 0, vlen = 0, ng = 0, vwire = 0, nrows = 0, num_rows = 0, vbytes = 0, dropped = 0; uint32_t voff = 0, w12 = 0;
       bool okc = true;
       if (have) {
         const ChunkEntry& e = E[c];
         const uint8_t* tv = rec + e.ts_off; const uint8_t* vv = rec + e.val_off;
-        vwire = ld32(vv + 4) & 0xffff;
+        const uint32_t vw4 = ld32(vv + 4);
+        vwire = vw4 & 0xffff; dropped = (vw4 >> 31) & 1;       // PrimitiveVectorReader.dropped, BinaryVector.scala:530-531
         tlen = (int)ld32(tv + 8); init = (int64_t)ld64_a4(tv + 12); const int slope = (int)ld32(tv + 20);
         end_time = e.end_time; num_rows = e.num_rows; voff = roff + e.val_off;
         vbytes = (int)ld32(tv) + 4 + (int)ld32(vv) + 4;
@@ -152,6 +216,7 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
         else okc = false;
         if ((int64_t)slope != q.step || tlen <= 0 || vlen <= 0) okc = false;
         nrows = num_rows < tlen ? num_rows : tlen; if (vlen < nrows) nrows = vlen;
+        if (CLS == CLASS_COUNTER && vlen != nrows) okc = false;     // updateCorrection reads the vector's last element
       }
       const unsigned okm = __ballot_sync(0xffffffffu, okc);     // (not inside the &&: every lane must take part)
       regular = regular && ((okm >> lb) & 0xfu) == 0xfu;
@@ -182,16 +247,21 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
       if (v4 < kB) kB = v4;
       if (kA < 0) kA = 0;
       if (kB > q.T - 1) kB = q.T - 1;
+      if (CLS == CLASS_COUNTER) {          // only windows whose row range is not clamped by the chunk's ends
+        if (-s0 > kA) kA = -s0;
+        const int64_t x = (int64_t)(nrows - 1) - e0; if (x < kB) kB = x;
+      }
       const int64_t sA = s0 + kA, eA = e0 + kA;
       const bool ok = have && kA <= kB && eA >= sA;
       const int Wr = ok ? (int)(eA - sA) : 0;
       const int nwin = ok ? (int)(kB - kA + 1) : 0;
       // blocked only when the windows are long enough to amortise a block; short windows go through the per-window path
-      const bool blocked = ok && Wr >= BLK_R - 1;
-      const int nb = blocked ? (nwin + BLK_R - 1) / BLK_R : 0;
+      // COUNTER: work item = one window of the interval (needs two samples: Wr >= 1)
+      const bool blocked = ok && Wr >= (CLS == CLASS_COUNTER ? 1 : BLK_R - 1);
+      const int nb = !blocked ? 0 : (CLS == CLASS_COUNTER ? nwin : (nwin + BLK_R - 1) / BLK_R);
       // zero rows around the chunk so that blocked sums read clamped-away rows as +0.0 without a bounds check
       int lowz = 0, highz = 0;
-      if (blocked) {
+      if (blocked && CLS == CLASS_SUM) {
         if (sA < 0) lowz = (int)-sA;
         const int64_t over = sA + (nwin - 1) + Wr - (nrows - 1); if (over > 0) highz = (int)over;
       }
@@ -213,7 +283,22 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
         if (vwire == WIRE_XOR) {
           const uint32_t po = w12 >> 16;
           ch.first = ld64(recbuf + voff + po); ch.grp_off = voff + po + 8; ch.tab_off = voff + XOR_OFF_GROUPTAB;
-        } else { ch.first = 0; ch.grp_off = 0; ch.tab_off = 0; }
+        } else { ch.first = ld64(recbuf + voff + 8); ch.grp_off = 0; ch.tab_off = 0; }
+        if (CLS == CLASS_COUNTER) {
+          // RateFunctions.extrapolatedRate (RateFunctions.scala:72-111) for the chunk's unclamped single-chunk windows: the
+          // sample times move with the window, so durationToStart/End, sampledInterval, numSamples are window-invariant
+          TileCtr& kc = CTn[s * TILE_MAXC + c];
+          kc.dropped = dropped; kc.upd_last = 0.0; kc.upd_corr = 0.0;
+          if (blocked) {
+            const double dTS = (double)(init + s0 * q.step - S0 + (q.inclusive ? 0 : 1)) / 1000.0, dTE = (double)(E0 - (init + e0 * q.step)) / 1000.0;
+            const double sI = (double)((e0 - s0) * q.step) / 1000.0;
+            const double avg = sI / ((double)(Wr + 1) - 1.0), thr = avg * 1.1, half = avg / 2.0;
+            const double endpart = dTE < thr ? dTE : half;
+            const double eTI = (sI + (dTS < thr ? dTS : half)) + endpart;
+            kc.dTS = dTS; kc.thr = thr; kc.half = half; kc.endpart = endpart; kc.sI = sI; kc.ratio0 = eTI / sI;
+            kc.skipC = 2.0 * dTS / sI;      // v1 > delta * skipC  =>  durationToZero >= durationToStart (no zero-point clamp)
+          }
+        }
         ch.lowz = lowz; ch.highz = highz;          // zeroed by the consumers before they decode the tile
         // CountingChunkInfoIterator, ChunkSetInfo.scala:336-380: every chunk in range is pulled, except one that starts after
         // the last window end (the window iterator never reaches it)
@@ -223,16 +308,18 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
       S.gb[c] = have ? grp_base : 0x7fffffff;
       const unsigned rawm = __ballot_sync(0xffffffffu, have && vwire == WIRE_RAW64);
       const unsigned irrm = __ballot_sync(0xffffffffu, present && !regular);
+      if (AGG && irrm != 0) regular = false;      // an item is folded as a whole: one irregular series sends the item to the fallback
       const unsigned unpm = __ballot_sync(0xffffffffu, have && !padded);
+      const unsigned drpm = __ballot_sync(0xffffffffu, have && dropped);
       if (c == 0) {
         if (regular) {
           S.n = n; S.regular = 1; S.rec_off = (int)roff; S.nblocks = nblocks; S.nrest = q.T - covered; S.ngroups = ngroups; S.nrows = nrows_tot;
           S.any_raw = ((rawm >> lb) & 0xfu) != 0;
         } else {
           S.n = 0; S.regular = present ? 0 : 2; S.nblocks = 0; S.nrest = 0; S.ngroups = 0; S.nrows = 0; S.any_raw = 0;
-          if (present) {
+          if (present && !AGG) {
             const unsigned long long slot = atomicAdd(fallback_count, 1ull);
-            fallback_list[slot] = i0 + s;
+            fallback_list[slot] = sid;
           }
         }
       }
@@ -244,7 +331,7 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
         if (lane >= o) { p += pp; r += rr; }
       }
       if (c == 0) { Mn->pref[s + 1] = p; Mn->rpref[s + 1] = r; }
-      if (lane == 0) { Mn->pref[0] = 0; Mn->rpref[0] = 0; Mn->any_nan = 0; Mn->any_raw = rawm != 0; Mn->all_regular = irrm == 0; Mn->all_padded = unpm == 0; Mn->staged = staged; Mn->ns = ns; Mn->i0 = i0; }
+      if (lane == 0) { Mn->pref[0] = 0; Mn->rpref[0] = 0; Mn->any_nan = 0; Mn->any_raw = rawm != 0; Mn->all_regular = irrm == 0; Mn->all_padded = unpm == 0; Mn->any_drop = drpm != 0; Mn->staged = staged; Mn->ns = ns; Mn->i0 = i0; }
       __syncthreads();          // A(t)
       __syncthreads();          // B(t)
     }
@@ -258,9 +345,16 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
   const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   uint32_t parity = 0;
   int b = 0;
-  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, b ^= 1) {
+  double aacc[TILE_AGG_ACC]; uint32_t acnt[TILE_AGG_ACC]; bool item_bad = false;      // AGG: this thread's windows tid + j * TILE_THREADS
+  const double agg_ident = agg_op == AGG_MIN ? __longlong_as_double(0x7ff0000000000000LL)
+                         : agg_op == AGG_MAX ? __longlong_as_double(0xfff0000000000000LL) : 0.0;
+#pragma unroll
+  for (int j = 0; j < TILE_AGG_ACC; ++j) { aacc[j] = agg_ident; acnt[j] = 0; }
+  Walk w;
+  for (bool more = walk_start(w); more; more = walk_next(w), b ^= 1) {
     const TileSeries* SDc = reinterpret_cast<const TileSeries*>(smem + L.desc + b * L.desc_stride);
     TileMeta* Mc = reinterpret_cast<TileMeta*>(smem + L.meta + b * 128);
+    TileCtr* CTc = reinterpret_cast<TileCtr*>(smem + L.ctr) + b * (TILE_NS * TILE_MAXC);
     __syncthreads();            // A(t)
     if (Mc->staged) { mbar_wait(bar, parity); parity ^= 1; }    // already complete (the producer saw it); orders the TMA writes
     const int64_t i0 = Mc->i0; const int ns = Mc->ns;
@@ -370,6 +464,43 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
         }
       }
     }
+    // ------------------------------------------------------------------ counter correction of dropped chunks (warp w <-> series w)
+    // CorrectingDoubleVectorReader.corrected / updateCorrection (DoubleVector.scala:325-342, 375-391): rows become
+    // (NaN -> 0) + running correction, in place; drops are folded serially so the additions keep the reference's order
+    if (CLS == CLASS_COUNTER && FN != FN_DELTA && Mc->any_drop) {
+      bar_consumers();
+      const TileSeries& S = SDc[warp];
+      if (S.regular == 1) {
+        for (int c = 0; c < S.n; ++c) {
+          TileCtr& kc = CTc[warp * TILE_MAXC + c];
+          if (!kc.dropped) continue;
+          const TileChunk& ch = S.c[c];
+          double* cv = vals + (size_t)warp * L.vals_pitch + ch.row_base;
+          double acc = 0.0, lastNonNaN = 0.0; bool haveLast = false;
+          double carry = -1.7976931348623157e308;                 // Double.MinValue
+          for (int r0 = 0; r0 < ch.vlen; r0 += 32) {
+            const int r = r0 + lane; const bool inb = r < ch.vlen;
+            const double raw = inb ? cv[r] : 0.0;
+            const bool nan_v = inb ? raw != raw : true;
+            const double v = nan_v ? 0.0 : raw;
+            double prev = __shfl_up_sync(0xffffffffu, v, 1); if (lane == 0) prev = carry;
+            const bool isdrop = inb && v < prev;
+            unsigned m = __ballot_sync(0xffffffffu, isdrop);
+            double mine = acc;
+            while (m) {
+              const int bb = __ffs(m) - 1; m &= m - 1;
+              acc += __shfl_sync(0xffffffffu, prev, bb);
+              if (lane >= bb) mine = acc;
+            }
+            if (inb) cv[r] = v + mine;
+            const unsigned nn = __ballot_sync(0xffffffffu, inb && !nan_v);
+            if (nn) { lastNonNaN = __shfl_sync(0xffffffffu, v, 31 - __clz(nn)); haveLast = true; }
+            carry = __shfl_sync(0xffffffffu, v, 31);
+          }
+          if (lane == 0) { kc.upd_last = haveLast ? lastNonNaN : 0.0; kc.upd_corr = acc; }
+        }
+      }
+    }
     if (tid == 0) tma_store_wait_read();       // the previous tile's bulk store must have finished reading `otile`
     __syncthreads();            // B(t): the record bytes are dead, the producer refills the staging buffer
     // ------------------------------------------------------------------ windows: blocked single-chunk windows
@@ -386,6 +517,24 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
         const int B = it - Mc->pref[s];
         int c = 0; while (c + 1 < S.n && B >= S.c[c].blk0 + S.c[c].blk_n) ++c;
         const TileChunk& ch = S.c[c];
+        if (CLS == CLASS_COUNTER) {
+          // one unclamped single-chunk window: lowest/highest sample = first/last row of the window (RateFunctions.scala:257-267)
+          const int kk = ch.kA + (B - ch.blk0);
+          const double* cv = vals + (size_t)s * L.vals_pitch + ch.row_base;
+          const double v1 = cv[ch.s0 + kk], v2 = cv[ch.e0 + kk];
+          const TileCtr& kc = CTc[s * TILE_MAXC + c];
+          const double delta = v2 - v1;
+          double ratio = kc.ratio0;
+          if (FN != FN_DELTA && delta > 0 && v1 >= 0 && !(v1 > delta * kc.skipC)) {      // zero-point clamp may apply (:84-90)
+            const double dz = kc.sI * (v1 / delta);
+            const double dts = dz < kc.dTS ? dz : kc.dTS;
+            const double eTI = (kc.sI + (dts < kc.thr ? dts : kc.half)) + kc.endpart;
+            ratio = eTI / kc.sI;
+          }
+          const double scaled = delta * ratio;
+          otile[(size_t)s * L.out_pitch + kk] = FN == FN_RATE ? __dmul_rn(div_invariant(scaled, fdiv, frcp), 1000.0) : scaled;
+          continue;
+        }
         const int b = B - ch.blk0;
         const int r0 = ch.sA + b * BLK_R;
         const double* slots = vals + (size_t)s * L.vals_pitch + ch.row_base;
@@ -442,14 +591,52 @@ scan_tile_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restric
         const int k = prev + 1 + u;
         const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - winDur;
         const double* sv = vals + (size_t)s * L.vals_pitch;
-        otile[(size_t)s * L.out_pitch + k] = any_nan ? tile_eval_window<FN, true>(S, sv, wStart, wEnd, fdiv, k)
-                                                     : tile_eval_window<FN, false>(S, sv, wStart, wEnd, fdiv, k);
+        if (CLS == CLASS_COUNTER) otile[(size_t)s * L.out_pitch + k] = tile_eval_counter<FN>(S, CTc + s * TILE_MAXC, sv, q, wStart, wEnd, k);
+        else otile[(size_t)s * L.out_pitch + k] = any_nan ? tile_eval_window<FN, true>(S, sv, wStart, wEnd, fdiv, k)
+                                                          : tile_eval_window<FN, false>(S, sv, wStart, wEnd, fdiv, k);
       }
     }
     fence_async_smem();        // make this thread's writes to the output tile visible to the async proxy (bulk store below)
     bar_consumers();
-    // ------------------------------------------------------------------ results: one bulk store for the tile (regular rows only)
-    {
+    // ------------------------------------------------------------------ results
+    if (AGG) {
+      // fold the tile's rows into this thread's accumulators (RowAggregators skip NaN: SumRowAggregator.scala:22-29 ...);
+      // the item's partial row leaves after its last tile
+      item_bad |= !all_reg;
+      if (all_reg) {
+#pragma unroll
+        for (int j = 0; j < TILE_AGG_ACC; ++j) {
+          const int k = tid + j * TILE_THREADS;
+          if (k < q.T) {
+            double a = aacc[j]; uint32_t n = acnt[j];
+            for (int s = 0; s < ns; ++s) {
+              const double v = otile[(size_t)s * L.out_pitch + k];
+              if (v == v) {
+                if (agg_op == AGG_MIN) a = v < a ? v : a; else if (agg_op == AGG_MAX) a = v > a ? v : a; else if (agg_op != AGG_COUNT) a += v;
+                ++n;
+              }
+            }
+            aacc[j] = a; acnt[j] = n;
+          }
+        }
+      }
+      if (w.pb + TILE_NS >= w.pe) {               // last tile of the item
+        if (!item_bad) {
+#pragma unroll
+          for (int j = 0; j < TILE_AGG_ACC; ++j) {
+            const int k = tid + j * TILE_THREADS;
+            if (k < q.T) { pval[(size_t)w.it * q.T + k] = aacc[j]; pcnt[(size_t)w.it * q.T + k] = acnt[j]; }
+          }
+        } else if (tid == 0) {
+          const unsigned long long slot = atomicAdd(fallback_count, 1ull);
+          fallback_list[slot] = w.it;
+        }
+#pragma unroll
+        for (int j = 0; j < TILE_AGG_ACC; ++j) { aacc[j] = agg_ident; acnt[j] = 0; }
+        item_bad = false;
+      }
+    } else {
+      // one bulk store for the tile (regular rows only)
       double* gout = out + (size_t)i0 * q.T;
       const uint32_t bytes = (uint32_t)ns * (uint32_t)q.T * 8u;
       if (all_reg && out_aligned && (bytes & 15) == 0 && (((size_t)i0 * q.T * 8) & 15) == 0) {

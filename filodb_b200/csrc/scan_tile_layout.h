@@ -8,6 +8,7 @@ constexpr int TILE_NS = 8;               // series per tile (even: keeps the bul
 constexpr int TILE_THREADS = 256;        // consumer threads (decode + windows)
 constexpr int TILE_LAUNCH_THREADS = TILE_THREADS + 32;   // + one producer warp (tile load, per-series setup of the next tile)
 constexpr int TILE_MAXC = 4;             // chunks in range per series on the fast path
+constexpr int TILE_AGG_ACC = 2;           // fused aggregate: per-thread accumulators -> T <= TILE_AGG_ACC * TILE_THREADS windows
 constexpr int TILE_MAXG = 64;            // NibblePack groups per series on the fast path (64 * 8 = 512 rows)
 
 struct TileChunk {
@@ -29,18 +30,27 @@ struct TileSeries {
   TileChunk c[TILE_MAXC];
 };
 
+// COUNTER class only: per-chunk constants of the extrapolation for windows whose rows lie inside the chunk and are not clamped
+// (RateFunctions.scala:72-111 with every window-invariant subexpression evaluated once), and the chunk's correction summary
+struct TileCtr {
+  double dTS, thr, half, endpart, sI, ratio0, skipC;   // see scan_tile.cuh (producer) for the definitions
+  double upd_last, upd_corr;                           // dropped chunk: last non-NaN value (or 0), total correction (consumers)
+  int32_t dropped, pad;
+};
+
 struct TileMeta {                         // per-tile work-list prefixes and flags
   int32_t pref[TILE_NS + 1];              // blocked work items per series (prefix)
   int32_t rpref[TILE_NS + 1];             // other windows per series (prefix)
   int32_t any_nan, any_raw, all_regular, all_padded;
   int32_t staged, ns; int64_t i0;
+  int32_t any_drop, pad;
 };
 
 struct TileSmem {                         // byte offsets inside dynamic shared memory (all multiples of 128)
-  uint32_t rec, vals, out, desc, gtot, meta, total;
+  uint32_t rec, vals, out, desc, gtot, meta, ctr, total;
   uint32_t rec_cap, vals_pitch /*doubles per series*/, out_pitch /*doubles per series = T*/, desc_stride /*bytes between the two descriptor buffers*/;
 };
-FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t T, uint32_t pad_rows) {
+FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t T, uint32_t pad_rows, bool counter_class = false) {
   TileSmem L;
   L.rec_cap = align_up(TILE_NS * max_rec_bytes + 128, 128);
   L.desc_stride = align_up(TILE_NS * (uint32_t)sizeof(TileSeries), 128);
@@ -53,6 +63,7 @@ FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, u
   L.desc = o; o += 2 * align_up(TILE_NS * (uint32_t)sizeof(TileSeries), 128);      // double-buffered: setup of tile t+1 overlaps tile t
   L.gtot = o; o += TILE_NS * TILE_MAXG * 8 + TILE_NS * (TILE_THREADS / 32) * 8;   // per-slot in-warp prefixes + per-warp totals
   L.meta = o; o += 2 * 128;
+  L.ctr = o; if (counter_class) o += 2 * align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileCtr), 128);
   L.total = o;
   return L;
 }
