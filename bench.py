@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="filo", choices=["filo", "reference"])
     ap.add_argument("--series", type=int, default=10_000_000, help="series per GPU")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c2-raw", "c2-counter", "c3", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c2-raw", "c2-counter", "c3", "c3-const", "c5"])
     ap.add_argument("--e2e-series", type=int, default=-1, help="series in the end-to-end leg (-1 = all)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-series", type=int, default=2_000_000, help="bounded sample for the CPU baseline legs")
@@ -62,13 +62,15 @@ WORKLOADS = {
                    "C2 variant: prom-counter schema (extrapolated Prometheus rate with counter correction)"),
     "c3": (dict(value_kind=1, value_enc=1, reset_period=1000, schema_flags=1, ts_jitter_ms=2000), "FN_INCREASE", "AGG_SUM", 1000,
            "C3: counters, DDV ts + XOR values, increase()[1m] then sum by(job), 1000 jobs"),
+    "c3-const": (dict(value_kind=1, value_enc=1, reset_period=1000, schema_flags=1), "FN_INCREASE", "AGG_SUM", 1000,
+                 "C3 variant: regular scrapes (const-DDV ts, what the reference's +-250 ms rule produces for <=100 ms jitter), XOR counters, increase()[1m] then sum by(job), 1000 jobs"),
     "c5": (dict(value_kind=1, value_enc=1, reset_period=1000, schema_flags=1), "FN_RATE", "AGG_SUM", 100,
            "C5: counters, sum(rate()[5m]) by(cluster), 100 clusters, NCCL all-reduce of the [G x T] partials"),
 }
 
 
 def query_range(workload):
-    window = 60000 if workload == "c3" else WINDOW
+    window = 60000 if workload.startswith("c3") else WINDOW
     return T0_MS, STEP, T0_MS + 7200000, window
 
 
@@ -345,10 +347,14 @@ def main():
         L = capi.lib()
 
         def e2e_step():
+            st_ = capi.Stats()
+            if aggr == capi.AGG_NONE:      # per-series result: one pipelined call (gather / H2D / kernels / D2H of consecutive batches overlap)
+                ctx._check(L.filo_scan_series(ctx.h, Se, nch.ctypes.data_as(C.c_void_p), addrs.ctypes.data_as(C.c_void_p), 0, 1, synth.get("schema_flags", 0),
+                                              fn, start, step, end, window, hout_np.ctypes.data_as(C.c_void_p), C.byref(st_)))
+                return
             h = C.c_void_p()
             ctx._check(L.filo_load_series(ctx.h, Se, nch.ctypes.data_as(C.c_void_p), addrs.ctypes.data_as(C.c_void_p), 0, 1,
                                           gids.ctypes.data_as(C.c_void_p) if gids is not None else None, n_groups, synth.get("schema_flags", 0), C.byref(h)))
-            st_ = capi.Stats()
             ctx._check(L.filo_query(ctx.h, h, fn, start, step, end, window, aggr, 0, 0, hout_np.ctypes.data_as(C.c_void_p), None, C.byref(st_)))
             L.filo_table_free(ctx.h, h)
         e2e_step()
@@ -361,7 +367,9 @@ def main():
             t = torch.tensor([dt], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
         line["e2e"] = {"value": Se * ROWS * world / dt, "unit": "samples/s", "h2d_bytes_per_step": int(arena.size), "d2h_bytes_per_step": int(n_out * 8),
                        "s_per_step": dt, "steps": args.e2e_steps, "series_per_gpu": Se,
-                       "what": "filo_load_series (walk ChunkSetInfo blocks in host memory, gather into pinned slabs, H2D) + filo_query (kernel + D2H into a pinned host buffer) + filo_table_free, per step"}
+                       "what": ("filo_scan_series: walk ChunkSetInfo blocks in host memory, gather into pinned slabs, H2D, kernels, D2H into a pinned host buffer, pipelined in batches"
+                                if aggr == capi.AGG_NONE else
+                                "filo_load_series (walk ChunkSetInfo blocks in host memory, gather into pinned slabs, H2D) + filo_query (kernels + D2H) + filo_table_free, per step")}
         del arena, keep, hout
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample, all host threads
     if rank == 0 and world == 1 and not args.no_cpu:

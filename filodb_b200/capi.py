@@ -15,7 +15,7 @@ OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CORRUPT_VECTOR, ERR_UNSUPPORTED, ERR_QUERY_LI
 
 EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_last_error", "filo_load_series", "filo_synth_table",
            "filo_table_set_groups", "filo_table_get_info", "filo_table_read_record", "filo_table_read_arena", "filo_table_free",
-           "filo_num_windows", "filo_query", "filo_query_device", "filo_present_partials"]
+           "filo_num_windows", "filo_query", "filo_query_device", "filo_scan_series", "filo_present_partials"]
 
 
 class Cfg(C.Structure):
@@ -84,6 +84,8 @@ def _sig(L):
     L.filo_query.argtypes = [vp, vp, i32, i64, i64, i64, i64, i32, i32, i32, vp, vp, C.POINTER(Stats)]
     L.filo_query_device.restype = i32
     L.filo_query_device.argtypes = [vp, vp, i32, i64, i64, i64, i64, i32, i32, i32, vp, vp, vp, C.POINTER(Stats)]
+    L.filo_scan_series.restype = i32
+    L.filo_scan_series.argtypes = [vp, i64, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, vp, C.POINTER(Stats)]
     L.filo_present_partials.restype = i32; L.filo_present_partials.argtypes = [vp, i32, i64, vp, vp, vp, vp]
 
 
@@ -214,6 +216,21 @@ class Context:
         self.last_stats = st.as_dict()
         if aggr in (AGG_AVG, AGG_TOPK, AGG_BOTTOMK) or (flags & Q_PARTIAL and aggr != AGG_NONE):
             return out, aux
+        return out
+
+    def scan_series(self, n_chunks, info_addrs, fn, start, step, end, window, ts_col=0, val_col=1, schema_flags=0, out=None):
+        """filo_scan_series: ingest + query + read-back of host-resident chunks in one pipelined call -> [n_series, T].
+        `out` may be a preallocated (ideally pinned) float64 array of n_series * T elements."""
+        nch = np.ascontiguousarray(n_chunks, np.int32)
+        addrs = np.ascontiguousarray(info_addrs, np.uint64)
+        T = num_windows(start, step, end)
+        if out is None:
+            out = np.zeros((nch.size, T), np.float64)
+        assert out.size == nch.size * T and out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
+        st = Stats()
+        self._check(lib().filo_scan_series(self.h, nch.size, _p(nch), _p(addrs), ts_col, val_col, schema_flags, fn, start, step, end, window,
+                                           out.ctypes.data, C.byref(st)))
+        self.last_stats = st.as_dict()
         return out
 
     def query_device(self, table, fn, start, step, end, window, d_out, d_aux=0, aggr=AGG_NONE, k=0, flags=0, stream=0, want_stats=True):

@@ -25,6 +25,18 @@ struct filo_ctx {
   size_t max_smem_optin = 0;
   std::mutex err_mu;
   std::string err;
+  // filo_scan_series pipeline slots (pinned staging + device buffers), kept across calls
+  struct ScanSlot {
+    uint8_t* h_in = nullptr; size_t h_in_cap = 0;        // pinned: records of the batch
+    int64_t* h_off = nullptr; size_t h_off_cap = 0;      // pinned: record offsets relative to the batch
+    uint8_t* d_in = nullptr; size_t d_in_cap = 0;
+    int64_t* d_off = nullptr; size_t d_off_cap = 0;
+    double* d_out = nullptr; size_t d_out_cap = 0;
+    void* h_sink = nullptr;                              // pinned AsyncSink
+    cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
+  };
+  std::mutex scan_mu;
+  ScanSlot scan[3];
 };
 
 struct filo_table {
@@ -88,6 +100,12 @@ void filo_ctx_destroy(filo_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  for (auto& sl : ctx->scan) {
+    if (sl.stream) cudaStreamSynchronize(sl.stream);
+    cudaFreeHost(sl.h_in); cudaFreeHost(sl.h_off); cudaFreeHost(sl.h_sink); cudaFree(sl.d_in); cudaFree(sl.d_off); cudaFree(sl.d_out);
+    if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+  }
   delete ctx;
 }
 
@@ -237,6 +255,85 @@ int classify_val(const uint8_t* v, VecInfo& o) {
 
 struct SeriesPlan { uint32_t rec_bytes; uint32_t n_chunks; uint32_t n_rows; uint32_t flags; };
 
+struct LoadIn { int64_t n_series; const int32_t* n_chunks; const uint64_t* addrs; const int64_t* chunk_base; int32_t ts_col, val_col; };
+struct PlanTotals { int64_t chunks = 0, samples = 0, alg = 0; int32_t maxrows = 0, maxch = 0; uint32_t max_rec = 0, f_or = 0, f_and = ~0u; };
+
+// pass 1 of the loader for one series: validate the vectors, size the record.  Returns 0 or FILO_ERR_*.
+inline int plan_series(const LoadIn& in, int64_t i, SeriesPlan& out, PlanTotals& tot) {
+  uint32_t bytes = sizeof(RecordHeader), rows = 0, nch = 0, flags = REC_ALL_TS_CONST;
+  int64_t prev_start = INT64_MIN, prev_end = INT64_MIN;
+  for (int32_t j = 0; j < in.n_chunks[i]; ++j) {
+    const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)in.addrs[in.chunk_base[i] + j]);
+    const int32_t numRows = rd32(info + 8);
+    if (numRows <= 0) continue;                                   // skipped by WindowedChunkIterator (ChunkSetInfo.scala:493)
+    const int64_t startT = (int64_t)(((1ull << 63) ^ (uint64_t)rd64(info)) >> 22), endT = rd64(info + 20);
+    VecInfo tv, vv;
+    int rc = classify_ts(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * in.ts_col)), tv);
+    if (!rc) rc = classify_val(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * in.val_col)), vv);
+    if (!rc && (numRows > tv.len || numRows > vv.len)) rc = FILO_ERR_CORRUPT_VECTOR;
+    if (!rc && (startT < prev_start || endT < prev_end)) rc = FILO_ERR_UNSUPPORTED;
+    if (rc) return rc;
+    prev_start = startT; prev_end = endT;
+    bytes += sizeof(ChunkEntry) + align_up((uint32_t)tv.total, 8) + align_up((uint32_t)vv.total, 8);
+    rows += (uint32_t)vv.len; ++nch;
+    const int twire = (uint16_t)(tv.p[4] | (tv.p[5] << 8)), vwire = (uint16_t)(vv.p[4] | (vv.p[5] << 8));
+    if (twire != WIRE_DDV_CONST) flags &= ~REC_ALL_TS_CONST;
+    if (vv.drop) flags |= REC_ANY_DROP;
+    if (vwire != WIRE_RAW64) flags |= REC_ANY_DECODE;
+    tot.samples += numRows; tot.alg += 28 + 16 + tv.total + vv.total;
+  }
+  out = SeriesPlan{align_up(bytes, 16), nch, rows, flags};
+  tot.chunks += nch; tot.maxrows = std::max<int32_t>(tot.maxrows, (int32_t)rows); tot.maxch = std::max<int32_t>(tot.maxch, (int32_t)nch);
+  tot.max_rec = std::max(tot.max_rec, out.rec_bytes); tot.f_or |= flags; tot.f_and &= flags;
+  return 0;
+}
+inline void merge_totals(PlanTotals& a, const PlanTotals& b) {
+  a.chunks += b.chunks; a.samples += b.samples; a.alg += b.alg; a.maxrows = std::max(a.maxrows, b.maxrows); a.maxch = std::max(a.maxch, b.maxch);
+  a.max_rec = std::max(a.max_rec, b.max_rec); a.f_or |= b.f_or; a.f_and &= b.f_and;
+}
+// pass 2 of the loader for one series: header, chunk entries, vectors copied verbatim
+inline void fill_record(const LoadIn& in, int64_t i, const SeriesPlan& p, uint8_t* rec) {
+  std::memset(rec, 0, sizeof(RecordHeader) + p.n_chunks * sizeof(ChunkEntry));
+  RecordHeader h{p.rec_bytes, p.n_chunks, p.n_rows, p.flags};
+  std::memcpy(rec, &h, sizeof h);
+  uint32_t off = sizeof(RecordHeader) + p.n_chunks * (uint32_t)sizeof(ChunkEntry);
+  uint32_t c = 0, row_base = 0;
+  for (int32_t j = 0; j < in.n_chunks[i]; ++j) {
+    const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)in.addrs[in.chunk_base[i] + j]);
+    const int32_t numRows = rd32(info + 8);
+    if (numRows <= 0) continue;
+    VecInfo tv, vv;
+    classify_ts(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * in.ts_col)), tv);
+    classify_val(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * in.val_col)), vv);
+    ChunkEntry ce;
+    ce.start_time = (int64_t)(((1ull << 63) ^ (uint64_t)rd64(info)) >> 22); ce.end_time = rd64(info + 20);
+    ce.num_rows = numRows; ce.ts_off = off; std::memcpy(rec + off, tv.p, tv.total);
+    { const uint32_t pad = align_up((uint32_t)tv.total, 8) - (uint32_t)tv.total; if (pad) std::memset(rec + off + tv.total, 0, pad); off += (uint32_t)tv.total + pad; }
+    ce.val_off = off; std::memcpy(rec + off, vv.p, vv.total);
+    if (vv.drop_patch) { if (vv.drop) rec[off + 7] |= 0x80; else rec[off + 7] &= 0x7f; }
+    { const uint32_t pad = align_up((uint32_t)vv.total, 8) - (uint32_t)vv.total; if (pad) std::memset(rec + off + vv.total, 0, pad); off += (uint32_t)vv.total + pad; }
+    ce.row_base = row_base; row_base += (uint32_t)vv.len;
+    std::memcpy(rec + sizeof(RecordHeader) + c * sizeof(ChunkEntry), &ce, sizeof ce); ++c;
+  }
+  if (off < p.rec_bytes) std::memset(rec + off, 0, p.rec_bytes - off);
+}
+// pass 1 over all series (pool); fills plan[] and the totals, returns 0 or the first error with its series
+inline int plan_all(const LoadIn& in, std::vector<SeriesPlan>& plan, PlanTotals& tot, int64_t& err_series_out) {
+  HostPool& pool = host_pool();
+  std::vector<PlanTotals> part((size_t)pool.size());
+  std::atomic<int> err_code{0}; std::atomic<int64_t> err_series{-1};
+  pool.run(in.n_series, [&](int w, int64_t b, int64_t e) {
+    for (int64_t i = b; i < e && !err_code.load(std::memory_order_relaxed); ++i) {
+      const int rc = plan_series(in, i, plan[(size_t)i], part[(size_t)w]);
+      if (rc) { int z = 0; if (err_code.compare_exchange_strong(z, rc)) err_series = i; return; }
+    }
+  });
+  for (auto& p : part) merge_totals(tot, p);
+  err_series_out = err_series.load();
+  return err_code.load();
+}
+
+
 } // namespace
 
 extern "C" int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32_t* n_chunks, const uint64_t* addrs,
@@ -248,7 +345,6 @@ extern "C" int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32
   if (group_ids && ctx->cfg.group_by_cardinality_limit > 0 && n_groups > ctx->cfg.group_by_cardinality_limit)
     return fail(ctx, FILO_ERR_QUERY_LIMIT, "Query exceeded group-by cardinality limit");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  const int nthreads = host_threads();
   std::vector<int64_t> chunk_base((size_t)n_series + 1, 0);
   for (int64_t i = 0; i < n_series; ++i) {
     if (n_chunks[i] < 0) return fail(ctx, FILO_ERR_INVALID_ARG, "negative n_chunks");
@@ -256,49 +352,18 @@ extern "C" int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32
   }
   // ---- pass 1: validate + size
   std::vector<SeriesPlan> plan((size_t)n_series);
-  std::atomic<int> err_code{0}; std::atomic<int64_t> err_series{-1};
-  std::vector<int64_t> t_chunks(nthreads, 0), t_samples(nthreads, 0), t_alg(nthreads, 0);
-  std::vector<int32_t> t_maxrows(nthreads, 0), t_maxch(nthreads, 0);
-  parallel_for(n_series, nthreads, [&](int tid, int64_t b, int64_t e) {
-    for (int64_t i = b; i < e && !err_code.load(std::memory_order_relaxed); ++i) {
-      uint32_t bytes = sizeof(RecordHeader), rows = 0, nch = 0, flags = REC_ALL_TS_CONST;
-      int64_t prev_start = INT64_MIN, prev_end = INT64_MIN;
-      for (int32_t j = 0; j < n_chunks[i]; ++j) {
-        const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)addrs[chunk_base[i] + j]);
-        const int32_t numRows = rd32(info + 8);
-        if (numRows <= 0) continue;                                   // skipped by WindowedChunkIterator (ChunkSetInfo.scala:493)
-        const int64_t startT = (int64_t)(((1ull << 63) ^ (uint64_t)rd64(info)) >> 22), endT = rd64(info + 20);
-        VecInfo tv, vv;
-        int rc = classify_ts(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * ts_col)), tv);
-        if (!rc) rc = classify_val(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * val_col)), vv);
-        if (!rc && (numRows > tv.len || numRows > vv.len)) rc = FILO_ERR_CORRUPT_VECTOR;
-        if (!rc && (startT < prev_start || endT < prev_end)) rc = FILO_ERR_UNSUPPORTED;
-        if (rc) { int z = 0; if (err_code.compare_exchange_strong(z, rc)) err_series = i; return; }
-        prev_start = startT; prev_end = endT;
-        bytes += sizeof(ChunkEntry) + align_up((uint32_t)tv.total, 8) + align_up((uint32_t)vv.total, 8);
-        rows += (uint32_t)vv.len; ++nch;
-        const int twire = (uint16_t)(tv.p[4] | (tv.p[5] << 8)), vwire = (uint16_t)(vv.p[4] | (vv.p[5] << 8));
-        if (twire != WIRE_DDV_CONST) flags &= ~REC_ALL_TS_CONST;
-        if (vv.drop) flags |= REC_ANY_DROP;
-        if (vwire != WIRE_RAW64) flags |= REC_ANY_DECODE;
-        t_samples[tid] += numRows; t_alg[tid] += 28 + 16 + tv.total + vv.total;
-      }
-      plan[i] = SeriesPlan{align_up(bytes, 16), nch, rows, flags};
-      t_chunks[tid] += nch; t_maxrows[tid] = std::max<int32_t>(t_maxrows[tid], (int32_t)rows); t_maxch[tid] = std::max<int32_t>(t_maxch[tid], (int32_t)nch);
-    }
-  });
-  if (err_code) {
+  const LoadIn in{n_series, n_chunks, addrs, chunk_base.data(), ts_col, val_col};
+  PlanTotals tot; int64_t err_series = -1;
+  if (const int err_code = plan_all(in, plan, tot, err_series)) {
     const char* what = err_code == FILO_ERR_UNSUPPORTED ? "chunks of a series are not in increasing time order (unsupported on the device path)"
                                                        : "CorruptVector: unknown or inconsistent BinaryVector wire format";
-    return fail(ctx, err_code, std::string(what) + " at series " + std::to_string(err_series.load()));
+    return fail(ctx, err_code, std::string(what) + " at series " + std::to_string(err_series));
   }
   std::vector<int64_t> rec_off((size_t)n_series + 1, 0);
   for (int64_t i = 0; i < n_series; ++i) rec_off[i + 1] = rec_off[i] + plan[i].rec_bytes;
   const int64_t arena_bytes = rec_off[n_series];
-  if (ctx->cfg.max_data_per_shard_query > 0) {
-    int64_t alg = 0; for (auto a : t_alg) alg += a;
-    if (alg > ctx->cfg.max_data_per_shard_query) return fail(ctx, FILO_ERR_QUERY_LIMIT, "raw data bytes scanned exceeds max-data-per-shard-query");
-  }
+  if (ctx->cfg.max_data_per_shard_query > 0 && tot.alg > ctx->cfg.max_data_per_shard_query)
+    return fail(ctx, FILO_ERR_QUERY_LIMIT, "raw data bytes scanned exceeds max-data-per-shard-query");
   // ---- pass 2: fill pinned slabs, copy
   auto* t = new filo_table();
   uint8_t* d_arena = nullptr; int64_t* d_rec_off = nullptr;
@@ -306,7 +371,7 @@ extern "C" int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32
   CUDA_TRY(ctx, cudaMalloc(&d_rec_off, (size_t)(n_series + 1) * 8));
   CUDA_TRY(ctx, cudaMemsetAsync(d_arena + arena_bytes, 0, 64, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_rec_off, rec_off.data(), (size_t)(n_series + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-  const size_t SLAB = std::min<size_t>((size_t)64 << 20, std::max<size_t>((size_t)arena_bytes, 1 << 16));
+  const size_t SLAB = std::min<size_t>((size_t)256 << 20, std::max<size_t>((size_t)arena_bytes, 1 << 16));
   uint8_t* slab[2] = {nullptr, nullptr}; cudaEvent_t ev[2];
   for (int b = 0; b < 2; ++b) { CUDA_TRY(ctx, cudaHostAlloc(&slab[b], SLAB + (1 << 20), cudaHostAllocDefault)); CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming)); }
   int64_t s0 = 0; int which = 0;
@@ -320,32 +385,8 @@ extern "C" int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32
     }
     CUDA_TRY(ctx, cudaEventSynchronize(ev[which]));
     uint8_t* dst0 = slab[which];
-    parallel_for(s1 - s0, nthreads, [&](int, int64_t b, int64_t e) {
-      for (int64_t ii = b; ii < e; ++ii) {
-        const int64_t i = s0 + ii;
-        uint8_t* rec = dst0 + (rec_off[i] - base);
-        std::memset(rec, 0, plan[i].rec_bytes);
-        RecordHeader h{plan[i].rec_bytes, plan[i].n_chunks, plan[i].n_rows, plan[i].flags};
-        std::memcpy(rec, &h, sizeof h);
-        uint32_t off = sizeof(RecordHeader) + plan[i].n_chunks * (uint32_t)sizeof(ChunkEntry);
-        uint32_t c = 0, row_base = 0;
-        for (int32_t j = 0; j < n_chunks[i]; ++j) {
-          const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)addrs[chunk_base[i] + j]);
-          const int32_t numRows = rd32(info + 8);
-          if (numRows <= 0) continue;
-          VecInfo tv, vv;
-          classify_ts(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * ts_col)), tv);
-          classify_val(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * val_col)), vv);
-          ChunkEntry ce;
-          ce.start_time = (int64_t)(((1ull << 63) ^ (uint64_t)rd64(info)) >> 22); ce.end_time = rd64(info + 20);
-          ce.num_rows = numRows; ce.ts_off = off; std::memcpy(rec + off, tv.p, tv.total); off += align_up((uint32_t)tv.total, 8);
-          ce.val_off = off; std::memcpy(rec + off, vv.p, vv.total);
-          if (vv.drop_patch) { if (vv.drop) rec[off + 7] |= 0x80; else rec[off + 7] &= 0x7f; }
-          off += align_up((uint32_t)vv.total, 8);
-          ce.row_base = row_base; row_base += (uint32_t)vv.len;
-          std::memcpy(rec + sizeof(RecordHeader) + c * sizeof(ChunkEntry), &ce, sizeof ce); ++c;
-        }
-      }
+    host_pool().run(s1 - s0, [&](int, int64_t b, int64_t e) {
+      for (int64_t ii = b; ii < e; ++ii) { const int64_t i = s0 + ii; fill_record(in, i, plan[(size_t)i], dst0 + (rec_off[i] - base)); }
     });
     CUDA_TRY(ctx, cudaMemcpyAsync(d_arena + base, dst0, (size_t)(rec_off[s1] - base), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaEventRecord(ev[which], ctx->stream));
@@ -353,14 +394,8 @@ extern "C" int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32
   }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   for (int b = 0; b < 2; ++b) { cudaFreeHost(slab[b]); cudaEventDestroy(ev[b]); }
-  int64_t nch = 0, ns = 0, alg = 0; int32_t mr = 0, mc = 0;
-  for (int i = 0; i < nthreads; ++i) { nch += t_chunks[i]; ns += t_samples[i]; alg += t_alg[i]; mr = std::max(mr, t_maxrows[i]); mc = std::max(mc, t_maxch[i]); }
-  filo_internal_set_arena(t, d_arena, d_rec_off, n_series, nch, ns, arena_bytes + (n_series + 1) * 8, alg, mr, mc, schema_flags);
-  {
-    uint32_t max_rec = 0, f_or = 0, f_and = ~0u;
-    for (int64_t i = 0; i < n_series; ++i) { max_rec = std::max(max_rec, plan[i].rec_bytes); f_or |= plan[i].flags; f_and &= plan[i].flags; }
-    filo_internal_set_layout(t, max_rec, n_series > 0 && !(f_and & REC_ALL_TS_CONST), (f_or & REC_ANY_DROP) != 0);
-  }
+  filo_internal_set_arena(t, d_arena, d_rec_off, n_series, tot.chunks, tot.samples, arena_bytes + (n_series + 1) * 8, tot.alg, tot.maxrows, tot.maxch, schema_flags);
+  filo_internal_set_layout(t, tot.max_rec, n_series > 0 && !(tot.f_and & REC_ALL_TS_CONST), (tot.f_or & REC_ANY_DROP) != 0);
   // groups
   int32_t* d_gid = nullptr;
   if (group_ids && n_series > 0) {
@@ -428,9 +463,26 @@ struct Temp {   // stream-ordered temporaries, freed on scope exit
 };
 }
 
+namespace {
+// device error word + scan counters of one asynchronous query, copied to pinned host memory on the query's stream
+struct AsyncSink { int herr[4]; unsigned long long hc[2]; int64_t launches; };
+}
+static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn, int64_t start, int64_t step, int64_t end, int64_t window,
+                                 int32_t agg, int32_t k, int32_t flags, void* d_out_values, void* d_out_aux, void* cuda_stream,
+                                 filo_stats* stats, AsyncSink* sink);
 extern "C" int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t fn, int64_t start, int64_t step, int64_t end, int64_t window,
                                      int32_t agg, int32_t k, int32_t flags, void* d_out_values, void* d_out_aux, void* cuda_stream,
                                      filo_stats* stats) {
+  return query_device_impl(ctx, t, fn, start, step, end, window, agg, k, flags, d_out_values, d_out_aux, cuda_stream, stats, nullptr);
+}
+static int32_t report_device_error(filo_ctx* ctx, const int herr[4], int64_t series_base) {
+  const char* what = herr[0] == 4 ? "series needs more decode scratch than the table statistics promised" : "CorruptVector on device";
+  return fail(ctx, FILO_ERR_CORRUPT_VECTOR, std::string(what) + " (code " + std::to_string(herr[0]) + ") at series " +
+              std::to_string(series_base + ((int64_t)herr[1] | ((int64_t)herr[2] << 31))));
+}
+static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn, int64_t start, int64_t step, int64_t end, int64_t window,
+                                 int32_t agg, int32_t k, int32_t flags, void* d_out_values, void* d_out_aux, void* cuda_stream,
+                                 filo_stats* stats, AsyncSink* sink) {
   if (!ctx || !t || !d_out_values) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_query: null argument");
   if (fn < FILO_FN_LAST || fn > FILO_FN_TIMESTAMP) return fail(ctx, FILO_ERR_INVALID_ARG, "unknown range function");
   if (agg < FILO_AGG_NONE || agg > FILO_AGG_BOTTOMK) return fail(ctx, FILO_ERR_INVALID_ARG, "unknown aggregation operator");
@@ -581,11 +633,12 @@ extern "C" int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
     stats->kernel_ns = (int64_t)((double)ms * 1e6); stats->samples_scanned = (int64_t)hc[0]; stats->bytes_scanned = (int64_t)hc[1];
     stats->kernel_launches = launches; stats->h2d_bytes = 0; stats->d2h_bytes = 0;
-    if (herr[0]) {
-      const char* what = herr[0] == 4 ? "series needs more decode scratch than the table statistics promised" : "CorruptVector on device";
-      return fail(ctx, FILO_ERR_CORRUPT_VECTOR, std::string(what) + " (code " + std::to_string(herr[0]) + ") at series " +
-                  std::to_string((int64_t)herr[1] | ((int64_t)herr[2] << 31)));
-    }
+    if (herr[0]) return report_device_error(ctx, herr, 0);
+  }
+  if (sink) {           // asynchronous caller: the words land in pinned memory when the stream reaches this point
+    sink->launches = launches;
+    CUDA_TRY(ctx, cudaMemcpyAsync(sink->herr, d_err, 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(sink->hc, d_counters, 16, cudaMemcpyDeviceToHost, s));
   }
   return FILO_OK;
 }
@@ -617,6 +670,124 @@ extern "C" int32_t filo_query(filo_ctx* ctx, const filo_table* t, int32_t fn, in
   cudaFreeAsync(d_vals, s); if (d_aux) cudaFreeAsync(d_aux, s);
   if (stats) *stats = st;
   return rc;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// filo_scan_series: ingest + query + result read-back of host-resident chunks in one pipelined call
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+template <class T> int32_t grow_pinned(filo_ctx* ctx, T*& p, size_t& cap, size_t need) {
+  if (need <= cap) return FILO_OK;
+  cudaFreeHost(p); p = nullptr; cap = 0;
+  CUDA_TRY(ctx, cudaHostAlloc((void**)&p, need, cudaHostAllocDefault));
+  cap = need; return FILO_OK;
+}
+template <class T> int32_t grow_device(filo_ctx* ctx, T*& p, size_t& cap, size_t need) {
+  if (need <= cap) return FILO_OK;
+  cudaFree(p); p = nullptr; cap = 0;
+  CUDA_TRY(ctx, cudaMalloc((void**)&p, need));
+  cap = need; return FILO_OK;
+}
+}
+
+extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32_t* n_chunks, const uint64_t* addrs,
+                                    int32_t ts_col, int32_t val_col, int32_t schema_flags,
+                                    int32_t fn, int64_t start, int64_t step, int64_t end, int64_t window,
+                                    double* out_values, filo_stats* stats) {
+  if (!ctx || n_series < 0 || (n_series > 0 && (!n_chunks || !addrs || !out_values)) || ts_col < 0 || val_col < 0)
+    return fail(ctx, FILO_ERR_INVALID_ARG, "filo_scan_series: bad arguments");
+  if (start > end) return fail(ctx, FILO_ERR_INVALID_ARG, "start should be <= end");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  std::lock_guard<std::mutex> one(ctx->scan_mu);          // the slots are shared: one streaming scan per context at a time
+  const int64_t adjustedStep = step > 0 ? step : step + 1;
+  const int T = filo_num_windows(start, adjustedStep, end);
+  std::vector<int64_t> chunk_base((size_t)n_series + 1, 0);
+  for (int64_t i = 0; i < n_series; ++i) {
+    if (n_chunks[i] < 0) return fail(ctx, FILO_ERR_INVALID_ARG, "negative n_chunks");
+    chunk_base[i + 1] = chunk_base[i] + n_chunks[i];
+  }
+  // ---- pass 1: validate + size (same rules as filo_load_series)
+  std::vector<SeriesPlan> plan((size_t)n_series);
+  const LoadIn in{n_series, n_chunks, addrs, chunk_base.data(), ts_col, val_col};
+  PlanTotals tot; int64_t err_series = -1;
+  if (const int err_code = plan_all(in, plan, tot, err_series)) {
+    const char* what = err_code == FILO_ERR_UNSUPPORTED ? "chunks of a series are not in increasing time order (unsupported on the device path)"
+                                                       : "CorruptVector: unknown or inconsistent BinaryVector wire format";
+    return fail(ctx, err_code, std::string(what) + " at series " + std::to_string(err_series));
+  }
+  if (ctx->cfg.max_data_per_shard_query > 0 && tot.alg > ctx->cfg.max_data_per_shard_query)
+    return fail(ctx, FILO_ERR_QUERY_LIMIT, "raw data bytes scanned exceeds max-data-per-shard-query");
+  // ---- batches: consecutive series, <= SLAB bytes of records and a bounded result block
+  const size_t SLAB = (size_t)192 << 20;
+  const int64_t max_rows_out = std::max<int64_t>(1, (int64_t)(((size_t)256 << 20) / ((size_t)std::max(T, 1) * 8)));
+  struct Batch { int64_t s0, s1; size_t bytes; };
+  std::vector<Batch> batches;
+  size_t max_bytes = 0; int64_t max_n = 0;
+  for (int64_t s0 = 0; s0 < n_series;) {
+    int64_t s1 = s0; size_t bytes = 0;
+    while (s1 < n_series && s1 - s0 < max_rows_out && (s1 == s0 || bytes + plan[(size_t)s1].rec_bytes <= SLAB)) { bytes += plan[(size_t)s1].rec_bytes; ++s1; }
+    batches.push_back(Batch{s0, s1, bytes});
+    max_bytes = std::max(max_bytes, bytes); max_n = std::max(max_n, s1 - s0);
+    s0 = s1;
+  }
+  const int NSLOT = 3;
+  for (int i = 0; i < NSLOT; ++i) {
+    filo_ctx::ScanSlot& sl = ctx->scan[i];
+    if (!sl.stream) { CUDA_TRY(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)); CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)); }
+    if (!sl.h_sink) CUDA_TRY(ctx, cudaHostAlloc(&sl.h_sink, sizeof(AsyncSink), cudaHostAllocDefault));
+    if (int32_t rc = grow_pinned(ctx, sl.h_in, sl.h_in_cap, max_bytes + 64)) return rc;
+    if (int32_t rc = grow_pinned(ctx, sl.h_off, sl.h_off_cap, (size_t)(max_n + 1) * 8)) return rc;
+    if (int32_t rc = grow_device(ctx, sl.d_in, sl.d_in_cap, max_bytes + 64)) return rc;
+    if (int32_t rc = grow_device(ctx, sl.d_off, sl.d_off_cap, (size_t)(max_n + 1) * 8)) return rc;
+    if (int32_t rc = grow_device(ctx, sl.d_out, sl.d_out_cap, (size_t)max_n * (size_t)std::max(T, 1) * 8)) return rc;
+  }
+  // ---- pipeline: gather batch b (host pool) while the GPU copies/scans batch b-1 and returns batch b-2
+  filo_stats acc{};
+  struct InFlight { int64_t s0 = -1; } fl[3];
+  int32_t rc = FILO_OK;
+  auto retire = [&](int i) -> int32_t {             // the slot's previous batch has completed: collect its counters / errors
+    filo_ctx::ScanSlot& sl = ctx->scan[i];
+    if (fl[i].s0 < 0) return FILO_OK;
+    CUDA_TRY(ctx, cudaEventSynchronize(sl.done));
+    const AsyncSink* k = reinterpret_cast<const AsyncSink*>(sl.h_sink);
+    acc.samples_scanned += (int64_t)k->hc[0]; acc.bytes_scanned += (int64_t)k->hc[1]; acc.kernel_launches += k->launches;
+    const int64_t base = fl[i].s0; fl[i].s0 = -1;
+    if (k->herr[0]) return report_device_error(ctx, k->herr, base);
+    return FILO_OK;
+  };
+  for (size_t bi = 0; bi < batches.size() && rc == FILO_OK; ++bi) {
+    const Batch& B = batches[bi];
+    const int si = (int)(bi % NSLOT);
+    filo_ctx::ScanSlot& sl = ctx->scan[si];
+    if ((rc = retire(si)) != FILO_OK) break;
+    const int64_t nb = B.s1 - B.s0;
+    sl.h_off[0] = 0;
+    for (int64_t j = 0; j < nb; ++j) sl.h_off[j + 1] = sl.h_off[j] + plan[(size_t)(B.s0 + j)].rec_bytes;
+    host_pool().run(nb, [&](int, int64_t b, int64_t e) {
+      for (int64_t j = b; j < e; ++j) fill_record(in, B.s0 + j, plan[(size_t)(B.s0 + j)], sl.h_in + sl.h_off[j]);
+    });
+    std::memset(sl.h_in + B.bytes, 0, 64);
+    cudaError_t ce = cudaMemcpyAsync(sl.d_in, sl.h_in, B.bytes + 64, cudaMemcpyHostToDevice, sl.stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(sl.d_off, sl.h_off, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, sl.stream);
+    if (ce != cudaSuccess) { rc = fail(ctx, FILO_ERR_CUDA, std::string("scan H2D: ") + cudaGetErrorString(ce)); break; }
+    filo_table view;                                    // a table over the slot's buffers (not owned)
+    view.n_series = nb; view.d_arena = sl.d_in; view.d_rec_off = sl.d_off; view.max_rows = tot.maxrows; view.max_chunks = tot.maxch;
+    view.max_rec_bytes = tot.max_rec; view.any_nonconst_ts = !(tot.f_and & REC_ALL_TS_CONST); view.any_drop = (tot.f_or & REC_ANY_DROP) != 0;
+    view.schema_flags = schema_flags; view.n_groups = 1; view.grouped = false;
+    rc = query_device_impl(ctx, &view, fn, start, step, end, window, FILO_AGG_NONE, 0, 0, sl.d_out, nullptr, sl.stream, nullptr,
+                           reinterpret_cast<AsyncSink*>(sl.h_sink));
+    if (rc != FILO_OK) break;
+    ce = cudaMemcpyAsync(out_values + (size_t)B.s0 * T, sl.d_out, (size_t)nb * T * 8, cudaMemcpyDeviceToHost, sl.stream);
+    if (ce == cudaSuccess) ce = cudaEventRecord(sl.done, sl.stream);
+    if (ce != cudaSuccess) { rc = fail(ctx, FILO_ERR_CUDA, std::string("scan D2H: ") + cudaGetErrorString(ce)); break; }
+    fl[si].s0 = B.s0;
+    acc.h2d_bytes += (int64_t)B.bytes + (nb + 1) * 8; acc.d2h_bytes += nb * (int64_t)T * 8;
+  }
+  for (int i = 0; i < NSLOT; ++i) { const int32_t r2 = retire(i); if (rc == FILO_OK) rc = r2; }
+  if (rc != FILO_OK) { for (int i = 0; i < NSLOT; ++i) if (ctx->scan[i].stream) cudaStreamSynchronize(ctx->scan[i].stream); return rc; }
+  if (stats) *stats = acc;
+  return FILO_OK;
 }
 
 extern "C" int32_t filo_present_partials(filo_ctx* ctx, int32_t agg, int64_t n, void* d_values, void* d_counts, void* d_out, void* cuda_stream) {

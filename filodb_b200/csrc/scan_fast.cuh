@@ -35,6 +35,9 @@ __device__ __forceinline__ void mbar_fence_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -73,11 +76,12 @@ struct StepDiv {
 
 // x / y for a loop-invariant y, with rcp = RN(1/y) precomputed: q0 = RN(x*rcp); r = x - q0*y (exact, FMA); q = RN(q0 + r*rcp).
 // This is the final correction step of the IEEE division sequence (Markstein) and returns the correctly rounded quotient
-// whenever q0 is a normal number well inside the exponent range; anything else takes the real division.
+// whenever q0 is a normal number well inside the exponent range; anything else takes the real division.  y > 0 is assumed.
 __device__ __forceinline__ double div_invariant(double x, double y, double rcp) {
   const double q0 = __dmul_rn(x, rcp);
   const uint32_t ex = ((uint32_t)__double2hiint(q0) >> 20) & 0x7ff;     // biased exponent
   if (ex > 64u && ex < 1983u) { const double r = __fma_rn(-q0, y, x); return __fma_rn(r, rcp, q0); }
+  if (x == 0.0) return q0;                 // +-0 / y (y > 0, finite): the product already has the quotient's sign
   return x / y;
 }
 

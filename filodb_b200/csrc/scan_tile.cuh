@@ -66,12 +66,60 @@ __device__ __forceinline__ double tile_eval_window(const TileSeries& S, const do
   return sum;
 }
 
+__device__ __forceinline__ double nan0(double x) { return x != x ? 0.0 : x; }
+// correction accumulated up to and including row r: the drops' amounts added in row order (same additions as the
+// reference's running `_correction += last`)
+__device__ __forceinline__ double drops_cum(const TileDrops& D, int r) {
+  const int n = D.n < TILE_MAXDROP ? D.n : TILE_MAXDROP;
+  if (n == 0) return 0.0;
+  if (n == 1) return D.pos[0] <= r ? D.amt[0] : 0.0;
+  double cum = 0.0; int last = -1;
+  for (int t = 0; t < n; ++t) {                 // selection in position order (the list is appended in decode order)
+    int best = 0x7fffffff, bj = 0;
+    for (int j = 0; j < n; ++j) if (D.pos[j] > last && D.pos[j] < best) { best = D.pos[j]; bj = j; }
+    last = best;
+    if (best <= r) cum += D.amt[bj];
+  }
+  return cum;
+}
+// value of row r as the counter functions see it: CorrectingDoubleVectorReader.corrected for a drop-flagged chunk, raw otherwise
+__device__ __forceinline__ double ctr_value(const double* v, int r, const TileDrops& D, bool dropped) {
+  const double x = v[r];
+  if (!dropped) return x;
+  return nan0(x) + drops_cum(D, r);
+}
+
+// RateFunctions.extrapolatedRate (RateFunctions.scala:72-111), same operations in the same order; the divisions by the constants
+// 1000 and (windowEnd - windowStart) use the exact invariant-divisor sequence, and the zero-point quotient is only formed
+// when durationToZero can be below durationToStart: v1 * sI > 2 * dTS * delta  =>  sI * (v1 / delta) >= dTS
+template <bool IS_COUNTER, bool IS_RATE>
+__device__ __forceinline__ double extrapolated_rate_tile(int64_t windowStart, int64_t windowEnd, int32_t numSamples, int64_t t1, double v1,
+                                                         int64_t t2, double v2, double fdiv, double frcp) {
+  double durationToStart = div_invariant((double)(t1 - windowStart), 1000.0, 0.001);
+  const double durationToEnd = div_invariant((double)(windowEnd - t2), 1000.0, 0.001);
+  const double sampledInterval = div_invariant((double)(t2 - t1), 1000.0, 0.001);
+  const double averageDurationBetweenSamples = sampledInterval / ((double)numSamples - 1.0);
+  const double delta = v2 - v1;
+  if (IS_COUNTER && delta > 0 && v1 >= 0) {
+    if (!(v1 * sampledInterval > 2.0 * durationToStart * delta)) {
+      const double durationToZero = sampledInterval * (v1 / delta);
+      if (durationToZero < durationToStart) durationToStart = durationToZero;
+    }
+  }
+  const double extrapolationThreshold = averageDurationBetweenSamples * 1.1;
+  double extrapolateToInterval = sampledInterval;
+  extrapolateToInterval += (durationToStart < extrapolationThreshold) ? durationToStart : averageDurationBetweenSamples / 2.0;
+  extrapolateToInterval += (durationToEnd < extrapolationThreshold) ? durationToEnd : averageDurationBetweenSamples / 2.0;
+  const double scaledDelta = delta * (extrapolateToInterval / sampledInterval);
+  return IS_RATE ? __dmul_rn(div_invariant(scaledDelta, fdiv, frcp), 1000.0) : scaledDelta;
+}
+
 // literal per-chunk fold of the counter functions for one window of a regular series: CounterChunkedRangeFunction.addChunks
 // (RangeFunction.scala:131-172), ChunkedRateFunctionBase (RateFunctions.scala:230-285), correction carry
-// (DoubleVector.scala:177-207, 375-391).  Rows of dropped chunks already hold the corrected values (see the kernel).
+// (DoubleVector.scala:177-207, 375-391).
 template <int FN>
-__device__ __forceinline__ double tile_eval_counter(const TileSeries& S, const TileCtr* K, const double* vals, const QueryParams& q,
-                                                    int64_t wStart, int64_t wEnd, int k) {
+__device__ __forceinline__ double tile_eval_counter(const TileSeries& S, const TileCtr* K, const TileDrops* DR, const double* vals, const QueryParams& q,
+                                                    int64_t wStart, int64_t wEnd, int k, double fdiv, double frcp) {
   const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
   int32_t numSamples = 0; int64_t loT = INT64_MAX, hiT = 0; double loV = NaNv, hiV = NaNv;
   bool some = false; double corrLast = 0.0, corr = 0.0;                // correctionMeta
@@ -89,18 +137,23 @@ __device__ __forceinline__ double tile_eval_counter(const TileSeries& S, const T
       const bool skip = FN != FN_DELTA && su == 0 && eu == 0 && first != first;      // RateFunctions.scala:255-256
       if (!skip && (tS < loT || tE > hiT)) {
         numSamples += eu - su + 1;
-        if (tS < loT) { loT = tS; loV = (FN != FN_DELTA && some) ? v[su] + corr : v[su]; }
-        if (tE > hiT) { hiT = tE; hiV = (FN != FN_DELTA && some) ? v[eu] + corr : v[eu]; }
+        const bool drp = FN != FN_DELTA && K[c].dropped;
+        if (tS < loT) { loT = tS; const double b = ctr_value(v, su, DR[c], drp); loV = (FN != FN_DELTA && some) ? b + corr : b; }
+        if (tE > hiT) { hiT = tE; const double b = ctr_value(v, eu, DR[c], drp); hiV = (FN != FN_DELTA && some) ? b + corr : b; }
       }
     }
     if (FN != FN_DELTA) {
-      if (K[c].dropped) { corrLast = K[c].upd_last; corr = (some ? corr : 0.0) + K[c].upd_corr; }
+      if (K[c].dropped) {                                                // CorrectingDoubleVectorReader.updateCorrection, :375-391
+        int idx = ch.vlen - 1; double lastValue = 0.0;
+        do { lastValue = v[idx]; idx -= 1; } while (lastValue != lastValue && idx >= 0);
+        corrLast = nan0(lastValue); corr = (some ? corr : 0.0) + drops_cum(DR[c], ch.vlen - 1);
+      }
       else { corrLast = v[ch.vlen - 1]; corr = some ? corr : 0.0; }
     }
     some = true;
   }
   const int64_t cws = q.inclusive ? wStart : wStart - 1;               // RateFunctions.scala:270-285
-  if (hiT > loT) return extrapolated_rate(cws, wEnd, numSamples, loT, loV, hiT, hiV, FN != FN_DELTA, FN == FN_RATE);
+  if (hiT > loT) return extrapolated_rate_tile<FN != FN_DELTA, FN == FN_RATE>(cws, wEnd, numSamples, loT, loV, hiT, hiV, fdiv, frcp);
   return NaNv;
 }
 
@@ -141,21 +194,21 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
   auto walk_seek = [&](Walk& w) -> bool { while (w.it < n_work) { item_range(w); if (w.pb < w.pe) return true; w.it += gridDim.x; } return false; };
   auto walk_start = [&](Walk& w) -> bool { w.it = blockIdx.x; return walk_seek(w); };
   auto walk_next = [&](Walk& w) -> bool { w.pb += TILE_NS; if (w.pb < w.pe) return true; w.it += gridDim.x; return walk_seek(w); };
-  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  uint64_t* ready = bar + 1;            // ready[b]: descriptors of the tile in buffer b are complete (producer -> consumers)
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(ready, 1); mbar_init(ready + 1, 1); mbar_fence_init(); }
   __syncthreads();
   int64_t winDur = q.inclusive ? q.window : q.window - 1; if (winDur < 0) winDur = 0;
   const double fdiv = (double)(q.inclusive ? winDur : winDur + 1), frcp = 1.0 / fdiv;     // RateFunctions.scala:436-442
   const int64_t S0 = q.start - winDur, E0 = q.start;
   auto bar_consumers = [] { asm volatile("bar.sync 1, %0;" ::"n"(TILE_THREADS) : "memory"); };
-  // Every tile passes two CTA-wide barriers: A = "descriptors of the tile are ready" (producer -> consumers),
-  // B = "the tile's record bytes are dead" (consumers -> producer: the staging buffer may be refilled).  The producer warp
+  // Per tile: A = "descriptors of the tile are ready" (producer -> consumers, an mbarrier), B = "the tile's record bytes are
+  // dead" (a CTA-wide barrier: consumers -> producer, the staging buffer may be refilled; decode -> windows among consumers).  The producer warp
   // loads and resolves tile t+1 while the consumers reduce the windows of tile t.
 
   if (producer) {
     // ================================================================== producer warp: tile load + per-series setup
     StepDiv sd; sd.init(q.step);
     uint32_t parity = 0;
-    int64_t rows_scanned = 0, bytes_scanned = 0;
     int b = 0;
     Walk w;
     for (bool more = walk_start(w); more; more = walk_next(w), b ^= 1) {
@@ -274,6 +327,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
       if (ngroups > TILE_MAXG || nrows_tot + 2 > (int)L.vals_pitch) { regular = false; have = false; }
       int nblocks = 0, covered = 0;
       const int blk0 = xpre(have ? nb : 0, nblocks); (void)xpre(have && blocked ? nwin : 0, covered);
+      int cnt_rows = 0, cnt_bytes = 0;            // this chunk's contribution to the scan counters
       if (have) {
         TileChunk& ch = S.c[c];
         ch.init = init; ch.end_time = end_time; ch.nrows = nrows; ch.row_base = row_base;
@@ -288,7 +342,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
           // RateFunctions.extrapolatedRate (RateFunctions.scala:72-111) for the chunk's unclamped single-chunk windows: the
           // sample times move with the window, so durationToStart/End, sampledInterval, numSamples are window-invariant
           TileCtr& kc = CTn[s * TILE_MAXC + c];
-          kc.dropped = dropped; kc.upd_last = 0.0; kc.upd_corr = 0.0;
+          kc.dropped = dropped;
           if (blocked) {
             const double dTS = (double)(init + s0 * q.step - S0 + (q.inclusive ? 0 : 1)) / 1000.0, dTE = (double)(E0 - (init + e0 * q.step)) / 1000.0;
             const double sI = (double)((e0 - s0) * q.step) / 1000.0;
@@ -303,8 +357,9 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         // CountingChunkInfoIterator, ChunkSetInfo.scala:336-380: every chunk in range is pulled, except one that starts after
         // the last window end (the window iterator never reaches it)
         const int64_t lastEnd = q.start + (int64_t)(q.T - 1) * q.step;
-        if (!(c > 0 && !(endp < lastEnd))) { rows_scanned += num_rows; bytes_scanned += vbytes; }
+        if (!(c > 0 && !(endp < lastEnd))) { cnt_rows = num_rows; cnt_bytes = vbytes; }
       }
+      { int tr = 0, tb = 0; (void)xpre(cnt_rows, tr); (void)xpre(cnt_bytes, tb); if (c == 0) { S.cnt_rows = tr; S.cnt_bytes = tb; } }
       S.gb[c] = have ? grp_base : 0x7fffffff;
       const unsigned rawm = __ballot_sync(0xffffffffu, have && vwire == WIRE_RAW64);
       const unsigned irrm = __ballot_sync(0xffffffffu, present && !regular);
@@ -313,7 +368,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
       const unsigned drpm = __ballot_sync(0xffffffffu, have && dropped);
       if (c == 0) {
         if (regular) {
-          S.n = n; S.regular = 1; S.rec_off = (int)roff; S.nblocks = nblocks; S.nrest = q.T - covered; S.ngroups = ngroups; S.nrows = nrows_tot;
+          S.sid = sid; S.n = n; S.regular = 1; S.rec_off = (int)roff; S.nblocks = nblocks; S.nrest = q.T - covered; S.ngroups = ngroups; S.nrows = nrows_tot;
           S.any_raw = ((rawm >> lb) & 0xfu) != 0;
         } else {
           S.n = 0; S.regular = present ? 0 : 2; S.nblocks = 0; S.nrest = 0; S.ngroups = 0; S.nrows = 0; S.any_raw = 0;
@@ -332,11 +387,9 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
       }
       if (c == 0) { Mn->pref[s + 1] = p; Mn->rpref[s + 1] = r; }
       if (lane == 0) { Mn->pref[0] = 0; Mn->rpref[0] = 0; Mn->any_nan = 0; Mn->any_raw = rawm != 0; Mn->all_regular = irrm == 0; Mn->all_padded = unpm == 0; Mn->any_drop = drpm != 0; Mn->staged = staged; Mn->ns = ns; Mn->i0 = i0; }
-      __syncthreads();          // A(t)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ready + b);      // A(t): release the descriptors
       __syncthreads();          // B(t)
-    }
-    if (rows_scanned | bytes_scanned) {
-      atomicAdd(&d_counters[0], (unsigned long long)rows_scanned); atomicAdd(&d_counters[1], (unsigned long long)bytes_scanned);
     }
     return;
   }
@@ -350,18 +403,23 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
                          : agg_op == AGG_MAX ? __longlong_as_double(0xfff0000000000000LL) : 0.0;
 #pragma unroll
   for (int j = 0; j < TILE_AGG_ACC; ++j) { aacc[j] = agg_ident; acnt[j] = 0; }
+  int64_t rows_scanned = 0, bytes_scanned = 0, pend_rows = 0, pend_bytes = 0;
+  uint32_t tj = 0;                      // tiles done by this CTA: buffer tj & 1, phase (tj >> 1) & 1 of its ready barrier
   Walk w;
   for (bool more = walk_start(w); more; more = walk_next(w), b ^= 1) {
     const TileSeries* SDc = reinterpret_cast<const TileSeries*>(smem + L.desc + b * L.desc_stride);
     TileMeta* Mc = reinterpret_cast<TileMeta*>(smem + L.meta + b * 128);
     TileCtr* CTc = reinterpret_cast<TileCtr*>(smem + L.ctr) + b * (TILE_NS * TILE_MAXC);
-    __syncthreads();            // A(t)
+    TileDrops* DRc = reinterpret_cast<TileDrops*>(smem + L.drops);
+    mbar_wait(ready + b, (tj >> 1) & 1); ++tj;   // A(t): descriptors ready (no consumer-wide barrier: the windows-end barrier of the
+                                                 // previous tile already separates the tiles)
     if (Mc->staged) { mbar_wait(bar, parity); parity ^= 1; }    // already complete (the producer saw it); orders the TMA writes
     const int64_t i0 = Mc->i0; const int ns = Mc->ns;
     // zero rows around the chunks (warp 0, lane = series * 4 + chunk); read by the blocked sums after the next barriers
     if (warp == 0) {
       const TileSeries& S = SDc[lane >> 2];
       const int c = lane & 3;
+      if (CLS == CLASS_COUNTER) DRc[lane].n = 0;
       if (S.regular == 1 && c < S.n) {
         const TileChunk& ch = S.c[c];
         double* zr = vals + (size_t)(lane >> 2) * L.vals_pitch + ch.row_base;
@@ -420,6 +478,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
       // value before group g of chunk c = first_c ^ (prefix at the slot) ^ (prefix at the chunk's first slot); the prefix at a
       // slot = XOR of the earlier warps' totals ^ the in-warp part
       uint32_t nz = 0x7ff00000u;
+      const bool any_drop = CLS == CLASS_COUNTER && Mc->any_drop != 0;
       {
         const TileChunk& c0 = S.c[cc[0]]; const TileChunk& c1 = S.c[cc[1]];
         const int gb0 = act[0] ? c0.grp_base : 0, gb1 = act[1] ? c1.grp_base : 0;
@@ -443,6 +502,20 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
             const uint64_t b = d[jj][i] ^ pre;
             if (i < nleft) { dst[i] = b; const uint32_t e = ~(uint32_t)(b >> 32) & 0x7ff00000u; nz = e < nz ? e : nz; }
           }
+          if (CLS == CLASS_COUNTER && FN != FN_DELTA && any_drop) {
+            // counter drops inside a drop-flagged chunk (DoubleVector.scala:330-340): row r drops when (NaN -> 0) of it is below
+            // (NaN -> 0) of row r - 1; the value before the group is the XOR prefix itself
+            if (act[jj] && CTc[ds * TILE_MAXC + cc[jj]].dropped) {
+              TileDrops& D = DRc[ds * TILE_MAXC + cc[jj]];
+              double prevv = nan0(__longlong_as_double((long long)pre));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const double cur = nan0(__longlong_as_double((long long)(d[jj][i] ^ pre)));
+                if (i < nleft && cur < prevv) { const int at = atomicAdd(&D.n, 1); if (at < TILE_MAXDROP) { D.pos[at] = 1 + g * 8 + i; D.amt[at] = prevv; } }
+                prevv = cur;
+              }
+            }
+          }
           if (act[jj] && g == 0) { dst[-1] = ch.first; const uint32_t e = ~(uint32_t)(ch.first >> 32) & 0x7ff00000u; nz = e < nz ? e : nz; }
         }
       }
@@ -459,56 +532,63 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
           const uint64_t* src = reinterpret_cast<const uint64_t*>(recbuf + ch.val_off + 8);
           uint64_t* dst = reinterpret_cast<uint64_t*>(vals + (size_t)s * L.vals_pitch + ch.row_base);
           bool nan = false;
-          for (int r = tid; r < ch.nrows; r += TILE_THREADS) { const uint64_t b = src[r]; dst[r] = b; nan |= ((uint32_t)(b >> 32) & 0x7ff00000u) == 0x7ff00000u; }
-          if (nan) Mc->any_nan = 1;
-        }
-      }
-    }
-    // ------------------------------------------------------------------ counter correction of dropped chunks (warp w <-> series w)
-    // CorrectingDoubleVectorReader.corrected / updateCorrection (DoubleVector.scala:325-342, 375-391): rows become
-    // (NaN -> 0) + running correction, in place; drops are folded serially so the additions keep the reference's order
-    if (CLS == CLASS_COUNTER && FN != FN_DELTA && Mc->any_drop) {
-      bar_consumers();
-      const TileSeries& S = SDc[warp];
-      if (S.regular == 1) {
-        for (int c = 0; c < S.n; ++c) {
-          TileCtr& kc = CTc[warp * TILE_MAXC + c];
-          if (!kc.dropped) continue;
-          const TileChunk& ch = S.c[c];
-          double* cv = vals + (size_t)warp * L.vals_pitch + ch.row_base;
-          double acc = 0.0, lastNonNaN = 0.0; bool haveLast = false;
-          double carry = -1.7976931348623157e308;                 // Double.MinValue
-          for (int r0 = 0; r0 < ch.vlen; r0 += 32) {
-            const int r = r0 + lane; const bool inb = r < ch.vlen;
-            const double raw = inb ? cv[r] : 0.0;
-            const bool nan_v = inb ? raw != raw : true;
-            const double v = nan_v ? 0.0 : raw;
-            double prev = __shfl_up_sync(0xffffffffu, v, 1); if (lane == 0) prev = carry;
-            const bool isdrop = inb && v < prev;
-            unsigned m = __ballot_sync(0xffffffffu, isdrop);
-            double mine = acc;
-            while (m) {
-              const int bb = __ffs(m) - 1; m &= m - 1;
-              acc += __shfl_sync(0xffffffffu, prev, bb);
-              if (lane >= bb) mine = acc;
+          const bool drp = CLS == CLASS_COUNTER && FN != FN_DELTA && CTc[s * TILE_MAXC + c].dropped;
+          for (int r = tid; r < ch.nrows; r += TILE_THREADS) {
+            const uint64_t b = src[r]; dst[r] = b; nan |= ((uint32_t)(b >> 32) & 0x7ff00000u) == 0x7ff00000u;
+            if (drp && r > 0) {
+              const double cur = nan0(__longlong_as_double((long long)b)), prevv = nan0(__longlong_as_double((long long)src[r - 1]));
+              if (cur < prevv) { TileDrops& D = DRc[s * TILE_MAXC + c]; const int at = atomicAdd(&D.n, 1); if (at < TILE_MAXDROP) { D.pos[at] = r; D.amt[at] = prevv; } }
             }
-            if (inb) cv[r] = v + mine;
-            const unsigned nn = __ballot_sync(0xffffffffu, inb && !nan_v);
-            if (nn) { lastNonNaN = __shfl_sync(0xffffffffu, v, 31 - __clz(nn)); haveLast = true; }
-            carry = __shfl_sync(0xffffffffu, v, 31);
           }
-          if (lane == 0) { kc.upd_last = haveLast ? lastNonNaN : 0.0; kc.upd_corr = acc; }
+          if (nan) Mc->any_nan = 1;
         }
       }
     }
     if (tid == 0) tma_store_wait_read();       // the previous tile's bulk store must have finished reading `otile`
     __syncthreads();            // B(t): the record bytes are dead, the producer refills the staging buffer
     // ------------------------------------------------------------------ windows: blocked single-chunk windows
-    bool all_reg;
     {
       const bool any_nan = Mc->any_nan != 0, padded = Mc->all_padded != 0;
-      all_reg = Mc->all_regular != 0;              // read here: warp 0 rewrites the tile flags during the next tile's setup
-      const int nitems = Mc->pref[TILE_NS];
+      if (CLS == CLASS_COUNTER) {
+        // warp w <-> series w: the unclamped single-chunk windows of each chunk, lanes over windows.  Lowest / highest sample
+        // = first / last row of the window (RateFunctions.scala:257-267); the extrapolation constants come from the producer
+        TileSeries& S = const_cast<TileSeries&>(SDc[warp]);
+        if (S.regular == 1) {
+          bool overflow = false;
+          for (int c = 0; c < S.n; ++c) overflow |= FN != FN_DELTA && CTc[warp * TILE_MAXC + c].dropped && DRc[warp * TILE_MAXC + c].n > TILE_MAXDROP;
+          if (overflow) {                         // more drops in one chunk than the list holds: the generic kernel takes the series
+            __syncwarp();
+            if (lane == 0) {
+              S.regular = 0; Mc->all_regular = 0;
+              if (!AGG) { const unsigned long long slot = atomicAdd(fallback_count, 1ull); fallback_list[slot] = S.sid; }
+            }
+          } else {
+            for (int c = 0; c < S.n; ++c) {
+              const TileChunk& ch = S.c[c];
+              if (ch.kA > ch.kB) continue;
+              const TileCtr kc = CTc[warp * TILE_MAXC + c];
+              const TileDrops& D = DRc[warp * TILE_MAXC + c];
+              const bool drp = FN != FN_DELTA && kc.dropped;
+              const double* cv = vals + (size_t)warp * L.vals_pitch + ch.row_base;
+              double* o = otile + (size_t)warp * L.out_pitch;
+              for (int kk = ch.kA + lane; kk <= ch.kB; kk += 32) {
+                const double v1 = ctr_value(cv, ch.s0 + kk, D, drp), v2 = ctr_value(cv, ch.e0 + kk, D, drp);
+                const double delta = v2 - v1;
+                double ratio = kc.ratio0;
+                if (FN != FN_DELTA && delta > 0 && v1 >= 0 && !(v1 > delta * kc.skipC)) {      // zero-point clamp may apply (:84-90)
+                  const double dz = kc.sI * (v1 / delta);
+                  const double dts = dz < kc.dTS ? dz : kc.dTS;
+                  const double eTI = (kc.sI + (dts < kc.thr ? dts : kc.half)) + kc.endpart;
+                  ratio = eTI / kc.sI;
+                }
+                const double scaled = delta * ratio;
+                o[kk] = FN == FN_RATE ? __dmul_rn(div_invariant(scaled, fdiv, frcp), 1000.0) : scaled;
+              }
+            }
+          }
+        }
+      }
+      const int nitems = CLS == CLASS_COUNTER ? 0 : Mc->pref[TILE_NS];
       for (int it = tid; it < nitems; it += TILE_THREADS) {
         int s = 0;
 #pragma unroll
@@ -517,24 +597,6 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         const int B = it - Mc->pref[s];
         int c = 0; while (c + 1 < S.n && B >= S.c[c].blk0 + S.c[c].blk_n) ++c;
         const TileChunk& ch = S.c[c];
-        if (CLS == CLASS_COUNTER) {
-          // one unclamped single-chunk window: lowest/highest sample = first/last row of the window (RateFunctions.scala:257-267)
-          const int kk = ch.kA + (B - ch.blk0);
-          const double* cv = vals + (size_t)s * L.vals_pitch + ch.row_base;
-          const double v1 = cv[ch.s0 + kk], v2 = cv[ch.e0 + kk];
-          const TileCtr& kc = CTc[s * TILE_MAXC + c];
-          const double delta = v2 - v1;
-          double ratio = kc.ratio0;
-          if (FN != FN_DELTA && delta > 0 && v1 >= 0 && !(v1 > delta * kc.skipC)) {      // zero-point clamp may apply (:84-90)
-            const double dz = kc.sI * (v1 / delta);
-            const double dts = dz < kc.dTS ? dz : kc.dTS;
-            const double eTI = (kc.sI + (dts < kc.thr ? dts : kc.half)) + kc.endpart;
-            ratio = eTI / kc.sI;
-          }
-          const double scaled = delta * ratio;
-          otile[(size_t)s * L.out_pitch + kk] = FN == FN_RATE ? __dmul_rn(div_invariant(scaled, fdiv, frcp), 1000.0) : scaled;
-          continue;
-        }
         const int b = B - ch.blk0;
         const int r0 = ch.sA + b * BLK_R;
         const double* slots = vals + (size_t)s * L.vals_pitch + ch.row_base;
@@ -591,13 +653,19 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         const int k = prev + 1 + u;
         const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - winDur;
         const double* sv = vals + (size_t)s * L.vals_pitch;
-        if (CLS == CLASS_COUNTER) otile[(size_t)s * L.out_pitch + k] = tile_eval_counter<FN>(S, CTc + s * TILE_MAXC, sv, q, wStart, wEnd, k);
+        if (CLS == CLASS_COUNTER) otile[(size_t)s * L.out_pitch + k] = tile_eval_counter<FN>(S, CTc + s * TILE_MAXC, DRc + s * TILE_MAXC, sv, q, wStart, wEnd, k, fdiv, frcp);
         else otile[(size_t)s * L.out_pitch + k] = any_nan ? tile_eval_window<FN, true>(S, sv, wStart, wEnd, fdiv, k)
                                                           : tile_eval_window<FN, false>(S, sv, wStart, wEnd, fdiv, k);
       }
     }
     fence_async_smem();        // make this thread's writes to the output tile visible to the async proxy (bulk store below)
     bar_consumers();
+    // tile flags of this tile stay valid until the producer's setup two tiles ahead, which waits for the next B barrier;
+    // a counter series whose drop list overflowed was declared irregular during the windows
+    const bool all_reg = Mc->all_regular != 0;
+    // scan counters (CountingChunkInfoIterator): series this kernel answers; series / items handed to the fallback are counted there
+    if (tid < ns && SDc[tid].regular == 1) { pend_rows += SDc[tid].cnt_rows; pend_bytes += SDc[tid].cnt_bytes; }
+    if (!AGG) { rows_scanned += pend_rows; bytes_scanned += pend_bytes; pend_rows = 0; pend_bytes = 0; }
     // ------------------------------------------------------------------ results
     if (AGG) {
       // fold the tile's rows into this thread's accumulators (RowAggregators skip NaN: SumRowAggregator.scala:22-29 ...);
@@ -627,10 +695,12 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
             const int k = tid + j * TILE_THREADS;
             if (k < q.T) { pval[(size_t)w.it * q.T + k] = aacc[j]; pcnt[(size_t)w.it * q.T + k] = acnt[j]; }
           }
+          rows_scanned += pend_rows; bytes_scanned += pend_bytes;
         } else if (tid == 0) {
           const unsigned long long slot = atomicAdd(fallback_count, 1ull);
           fallback_list[slot] = w.it;
         }
+        pend_rows = 0; pend_bytes = 0;
 #pragma unroll
         for (int j = 0; j < TILE_AGG_ACC; ++j) { aacc[j] = agg_ident; acnt[j] = 0; }
         item_bad = false;
@@ -651,6 +721,9 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
     }
   }
   if (tid == 0) tma_store_wait_read();
+  if (rows_scanned | bytes_scanned) {
+    atomicAdd(&d_counters[0], (unsigned long long)rows_scanned); atomicAdd(&d_counters[1], (unsigned long long)bytes_scanned);
+  }
 }
 
 } // namespace filo

@@ -26,16 +26,24 @@ struct TileChunk {
 };
 struct TileSeries {
   int32_t n, regular, rec_off, nblocks, nrest, ngroups, nrows, any_raw;
+  int64_t sid;                // series ordinal in the table
+  int32_t cnt_rows, cnt_bytes; // rows / vector bytes of the chunks the window iterator pulls (scan counters)
   int32_t gb[TILE_MAXC];      // grp_base of chunk c (INT_MAX for c >= n): chunk of a group slot = #{c >= 1 : gb[c] <= slot}
   TileChunk c[TILE_MAXC];
 };
 
-// COUNTER class only: per-chunk constants of the extrapolation for windows whose rows lie inside the chunk and are not clamped
-// (RateFunctions.scala:72-111 with every window-invariant subexpression evaluated once), and the chunk's correction summary
+// COUNTER class only.  TileCtr (producer, double-buffered): per-chunk constants of the extrapolation for windows whose rows lie
+// inside the chunk and are not clamped (RateFunctions.scala:72-111 with every window-invariant subexpression evaluated once).
 struct TileCtr {
   double dTS, thr, half, endpart, sI, ratio0, skipC;   // see scan_tile.cuh (producer) for the definitions
-  double upd_last, upd_corr;                           // dropped chunk: last non-NaN value (or 0), total correction (consumers)
   int32_t dropped, pad;
+};
+// TileDrops (consumers, per tile): counter drops of a drop-flagged chunk, found while its rows are decoded
+// (CorrectingDoubleVectorReader.corrected, DoubleVector.scala:325-342): row position and the amount added to the correction
+constexpr int TILE_MAXDROP = 4;
+struct TileDrops {
+  int32_t n, pos[TILE_MAXDROP], pad[3];
+  double amt[TILE_MAXDROP];
 };
 
 struct TileMeta {                         // per-tile work-list prefixes and flags
@@ -47,7 +55,7 @@ struct TileMeta {                         // per-tile work-list prefixes and fla
 };
 
 struct TileSmem {                         // byte offsets inside dynamic shared memory (all multiples of 128)
-  uint32_t rec, vals, out, desc, gtot, meta, ctr, total;
+  uint32_t rec, vals, out, desc, gtot, meta, ctr, drops, total;
   uint32_t rec_cap, vals_pitch /*doubles per series*/, out_pitch /*doubles per series = T*/, desc_stride /*bytes between the two descriptor buffers*/;
 };
 FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t T, uint32_t pad_rows, bool counter_class = false) {
@@ -63,7 +71,8 @@ FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, u
   L.desc = o; o += 2 * align_up(TILE_NS * (uint32_t)sizeof(TileSeries), 128);      // double-buffered: setup of tile t+1 overlaps tile t
   L.gtot = o; o += TILE_NS * TILE_MAXG * 8 + TILE_NS * (TILE_THREADS / 32) * 8;   // per-slot in-warp prefixes + per-warp totals
   L.meta = o; o += 2 * 128;
-  L.ctr = o; if (counter_class) o += 2 * align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileCtr), 128);
+  L.ctr = o; L.drops = o;
+  if (counter_class) { o += 2 * align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileCtr), 128); L.drops = o; o += align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileDrops), 128); }
   L.total = o;
   return L;
 }

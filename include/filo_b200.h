@@ -180,6 +180,16 @@ int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t range_fn,
                           int64_t start_ms, int64_t step_ms, int64_t end_ms, int64_t window_ms,
                           int32_t aggr_op, int32_t k, int32_t flags,
                           void* d_out_values, void* d_out_aux, void* cuda_stream, filo_stats* stats);
+/* PeriodicSamplesMapper over host-resident chunks in ONE pipelined call: filo_load_series + filo_query (aggr NONE) +
+ * result read-back, processed in batches so that the host gather of batch b, the H2D copy and the kernels of batch b-1
+ * and the D2H of batch b-2 overlap (pinned staging kept in the context).  Same argument meaning, validation and errors as
+ * filo_load_series / filo_query; out_values: host [n_series * T] (pinned memory lets the D2H copies overlap).
+ * Replaces the per-partition ChunkedWindowIterator loop of PeriodicSamplesMapper.apply (PeriodicSamplesMapper.scala:78-146)
+ * for a whole shard's RawDataRangeVectors.  stats->kernel_ns is not filled (batches overlap). */
+int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32_t* n_chunks, const uint64_t* chunk_info_addrs,
+                         int32_t ts_col, int32_t val_col, int32_t schema_flags,
+                         int32_t range_fn, int64_t start_ms, int64_t step_ms, int64_t end_ms, int64_t window_ms,
+                         double* out_values, filo_stats* stats);
 /* RowAggregator "present" after a cross-GPU merge: n = n_groups*T cells; writes NaN where count == 0, Σ/n for AVG. */
 int32_t filo_present_partials(filo_ctx* ctx, int32_t aggr_op, int64_t n, void* d_values, void* d_counts,
                               void* d_out_values, void* cuda_stream);

@@ -349,3 +349,28 @@ def test_gpu_encoder_matches_reference_appenders(gpu, oracle, case):
     got = ctx.query(tab, capi.FN_SUM_OVER_TIME, start, step, end, window, aggr=capi.AGG_MAX)
     exp = st.query(o.FN_SUM_OVER_TIME, start, step, end, window, cumulative=cumulative, aggr=o.AGG_MAX, group_ids=groups, n_groups=5)
     assert_same(got, exp, "group max over synthetic table")
+
+
+def test_scan_series_pipelined_matches_oracle(gpu, oracle):
+    """filo_scan_series (ingest + query + read-back in one pipelined call) returns what load + query returns, bit for bit,
+    with the same scan counters; errors surface the same way."""
+    capi, ctx = gpu; o = oracle
+    rng = np.random.default_rng(5)
+    t0 = 1_700_000_000_000
+    for kind, cumulative, nan_frac in (("gauge", False, 0.02), ("counter", True, 0.01)):
+        st = build_store(o, rng, 300, kind, 2, 0, cumulative, nan_frac)
+        nch, addrs = st.all_info_addrs()
+        flags = capi.SCHEMA_CUMULATIVE if cumulative else 0
+        for (start, step, end, window) in [(t0, 15000, t0 + 7200000, 300000), (t0 + 60000, 47000, t0 + 480 * 15000, 333333)]:
+            for name in ("FN_RATE", "FN_SUM_OVER_TIME", "FN_MAX_OVER_TIME", "FN_LAST"):
+                got = ctx.scan_series(nch, addrs, getattr(capi, name), start, step, end, window, schema_flags=flags)
+                stats = dict(ctx.last_stats)
+                exp = st.query(getattr(o, name), start, step, end, window, cumulative=cumulative)
+                assert_same(got, exp, "scan_series %s %s" % (kind, name))
+                assert stats["samples_scanned"] == st.last_stats["samples_scanned"]
+                assert stats["bytes_scanned"] == st.last_stats["bytes_scanned"]
+                assert stats["d2h_bytes"] == got.size * 8
+    with pytest.raises(capi.FiloError):
+        ctx.scan_series(nch, addrs, capi.FN_RATE, t0 + 10, 15000, t0, 300000)          # start > end
+    empty = ctx.scan_series(np.zeros(0, np.int32), np.zeros(0, np.uint64), capi.FN_RATE, t0, 15000, t0 + 60000, 300000)
+    assert empty.shape == (0, 5)
