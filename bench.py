@@ -220,10 +220,12 @@ def run_reference(args, rank, world):
     dt = (time.perf_counter() - t0) / args.steps
     samples = S * ROWS
     val = samples / dt
-    line = {"impl": "reference", "metric": "samples/s scanned+aggregated (rate over 10M series)", "value": val, "unit": "samples/s",
+    line = {"impl": "reference", "metric": "samples/s scanned+aggregated (rate over 10M series); % HBM roofline", "value": val, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc.format(S=args.series), "sample": "%d of %d series per step" % (S, args.series)},
+            "config": {"workload": desc.format(S=args.series) + " (per GPU; series sharded by id across GPUs)", "series_per_gpu": args.series, "rows": ROWS,
+                       "windows": int(o.num_windows(start, step, end)), "window_ms": window, "step_ms": step,
+                       "sample": "%d of %d series per step" % (S, args.series)},
             "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": "%d series (%.1f%% of the workload) per step, all %d host threads, oracle C++ restatement of ChunkedWindowIteratorD" % (S, 100.0 * S / args.series, cores)},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -334,7 +336,7 @@ def main():
     torch.cuda.empty_cache()
     if not args.no_e2e:
         Se = S if args.e2e_series < 0 else min(S, args.e2e_series)
-        os.environ.setdefault("FILO_HOST_THREADS", str(min(64, os.cpu_count() or 8)))
+        os.environ.setdefault("FILO_HOST_THREADS", str(max(4, min(64, (os.cpu_count() or 8) // world))))   # host gather threads per rank
         arena, rec_off = tab.read_arena(0, Se)
         nch, addrs, keep = host_chunk_infos(arena, rec_off, Se)
         n_out = Se * T if aggr == capi.AGG_NONE else n_groups * T

@@ -53,6 +53,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
+// same, for waits that may last microseconds: the suspend-time hint lets the hardware park the thread instead of spinning
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+  } while (!ok);
+}
+
 // ------------------------------------------------------------------------------------------------ integer helpers
 // Division by the (kernel-invariant) query step: double reciprocal + one correction, exact for |a| < 2^31, d < 2^31.
 struct StepDiv {

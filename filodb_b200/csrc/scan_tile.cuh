@@ -67,19 +67,14 @@ __device__ __forceinline__ double tile_eval_window(const TileSeries& S, const do
 }
 
 __device__ __forceinline__ double nan0(double x) { return x != x ? 0.0 : x; }
-// correction accumulated up to and including row r: the drops' amounts added in row order (same additions as the
-// reference's running `_correction += last`)
+// correction accumulated up to and including row r.  The list has been sorted by position and its amounts replaced by their
+// running sums in position order (tile kernel, start of the window phase) -- the same additions as the reference's running
+// `_correction += last` -- so the answer is the entry of the last drop at or before r.
 __device__ __forceinline__ double drops_cum(const TileDrops& D, int r) {
   const int n = D.n < TILE_MAXDROP ? D.n : TILE_MAXDROP;
-  if (n == 0) return 0.0;
-  if (n == 1) return D.pos[0] <= r ? D.amt[0] : 0.0;
-  double cum = 0.0; int last = -1;
-  for (int t = 0; t < n; ++t) {                 // selection in position order (the list is appended in decode order)
-    int best = 0x7fffffff, bj = 0;
-    for (int j = 0; j < n; ++j) if (D.pos[j] > last && D.pos[j] < best) { best = D.pos[j]; bj = j; }
-    last = best;
-    if (best <= r) cum += D.amt[bj];
-  }
+  double cum = 0.0;
+#pragma unroll
+  for (int j = 0; j < TILE_MAXDROP; ++j) if (j < n && D.pos[j] <= r) cum = D.amt[j];
   return cum;
 }
 // value of row r as the counter functions see it: CorrectingDoubleVectorReader.corrected for a drop-flagged chunk, raw otherwise
@@ -94,11 +89,20 @@ __device__ __forceinline__ double ctr_value(const double* v, int r, const TileDr
 // when durationToZero can be below durationToStart: v1 * sI > 2 * dTS * delta  =>  sI * (v1 / delta) >= dTS
 template <bool IS_COUNTER, bool IS_RATE>
 __device__ __forceinline__ double extrapolated_rate_tile(int64_t windowStart, int64_t windowEnd, int32_t numSamples, int64_t t1, double v1,
-                                                         int64_t t2, double v2, double fdiv, double frcp) {
+                                                         int64_t t2, double v2, double fdiv, double frcp, int64_t step, const TileCtrTab* tab) {
   double durationToStart = div_invariant((double)(t1 - windowStart), 1000.0, 0.001);
   const double durationToEnd = div_invariant((double)(windowEnd - t2), 1000.0, 0.001);
-  const double sampledInterval = div_invariant((double)(t2 - t1), 1000.0, 0.001);
-  const double averageDurationBetweenSamples = sampledInterval / ((double)numSamples - 1.0);
+  const int64_t si_ms = t2 - t1;
+  const int m = numSamples - 1;
+  double sampledInterval, extrapolationThreshold, half, rcpSI;
+  if (m <= TILE_CTR_TABMAX && si_ms == (int64_t)m * step) {      // samples m steps apart: the terms depend on m only (see the table)
+    const TileCtrTab e = tab[m];
+    sampledInterval = e.sI; extrapolationThreshold = e.thr; half = e.half; rcpSI = e.rcpSI;
+  } else {
+    sampledInterval = div_invariant((double)si_ms, 1000.0, 0.001);
+    const double averageDurationBetweenSamples = sampledInterval / ((double)numSamples - 1.0);
+    extrapolationThreshold = averageDurationBetweenSamples * 1.1; half = averageDurationBetweenSamples / 2.0; rcpSI = 0.0;
+  }
   const double delta = v2 - v1;
   if (IS_COUNTER && delta > 0 && v1 >= 0) {
     if (!(v1 * sampledInterval > 2.0 * durationToStart * delta)) {
@@ -106,11 +110,11 @@ __device__ __forceinline__ double extrapolated_rate_tile(int64_t windowStart, in
       if (durationToZero < durationToStart) durationToStart = durationToZero;
     }
   }
-  const double extrapolationThreshold = averageDurationBetweenSamples * 1.1;
   double extrapolateToInterval = sampledInterval;
-  extrapolateToInterval += (durationToStart < extrapolationThreshold) ? durationToStart : averageDurationBetweenSamples / 2.0;
-  extrapolateToInterval += (durationToEnd < extrapolationThreshold) ? durationToEnd : averageDurationBetweenSamples / 2.0;
-  const double scaledDelta = delta * (extrapolateToInterval / sampledInterval);
+  extrapolateToInterval += (durationToStart < extrapolationThreshold) ? durationToStart : half;
+  extrapolateToInterval += (durationToEnd < extrapolationThreshold) ? durationToEnd : half;
+  const double ratio = rcpSI != 0.0 ? div_invariant(extrapolateToInterval, sampledInterval, rcpSI) : extrapolateToInterval / sampledInterval;
+  const double scaledDelta = delta * ratio;
   return IS_RATE ? __dmul_rn(div_invariant(scaledDelta, fdiv, frcp), 1000.0) : scaledDelta;
 }
 
@@ -119,7 +123,7 @@ __device__ __forceinline__ double extrapolated_rate_tile(int64_t windowStart, in
 // (DoubleVector.scala:177-207, 375-391).
 template <int FN>
 __device__ __forceinline__ double tile_eval_counter(const TileSeries& S, const TileCtr* K, const TileDrops* DR, const double* vals, const QueryParams& q,
-                                                    int64_t wStart, int64_t wEnd, int k, double fdiv, double frcp) {
+                                                    int64_t wStart, int64_t wEnd, int k, double fdiv, double frcp, const TileCtrTab* tab) {
   const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
   int32_t numSamples = 0; int64_t loT = INT64_MAX, hiT = 0; double loV = NaNv, hiV = NaNv;
   bool some = false; double corrLast = 0.0, corr = 0.0;                // correctionMeta
@@ -153,7 +157,7 @@ __device__ __forceinline__ double tile_eval_counter(const TileSeries& S, const T
     some = true;
   }
   const int64_t cws = q.inclusive ? wStart : wStart - 1;               // RateFunctions.scala:270-285
-  if (hiT > loT) return extrapolated_rate_tile<FN != FN_DELTA, FN == FN_RATE>(cws, wEnd, numSamples, loT, loV, hiT, hiV, fdiv, frcp);
+  if (hiT > loT) return extrapolated_rate_tile<FN != FN_DELTA, FN == FN_RATE>(cws, wEnd, numSamples, loT, loV, hiT, hiV, fdiv, frcp, q.step, tab);
   return NaNv;
 }
 
@@ -300,7 +304,8 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
       if (v4 < kB) kB = v4;
       if (kA < 0) kA = 0;
       if (kB > q.T - 1) kB = q.T - 1;
-      if (CLS == CLASS_COUNTER) {          // only windows whose row range is not clamped by the chunk's ends
+      const int64_t kA2 = kA, kB2 = kB;    // every single-chunk window of the chunk
+      if (CLS == CLASS_COUNTER) {          // [kA, kB]: only windows whose row range is not clamped by the chunk's ends
         if (-s0 > kA) kA = -s0;
         const int64_t x = (int64_t)(nrows - 1) - e0; if (x < kB) kB = x;
       }
@@ -332,6 +337,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         TileChunk& ch = S.c[c];
         ch.init = init; ch.end_time = end_time; ch.nrows = nrows; ch.row_base = row_base;
         ch.val_off = voff; ch.wire = vwire; ch.ngroups = ng; ch.grp_base = grp_base; ch.tlen = tlen; ch.vlen = vlen;
+        ch.kA2 = (have && kA2 <= kB2) ? (int)kA2 : 0; ch.kB2 = (have && kA2 <= kB2) ? (int)kB2 : -1;
         ch.kA = blocked ? (int)kA : 0; ch.kB = blocked ? (int)kB : -1; ch.sA = (int)sA; ch.Wr = Wr; ch.blk0 = blk0; ch.blk_n = nb;
         ch.s0 = (int)s0; ch.e0 = (int)e0;
         if (vwire == WIRE_XOR) {
@@ -396,6 +402,18 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
 
   // ==================================================================== consumer warps
   const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const TileCtrTab* CTAB = reinterpret_cast<const TileCtrTab*>(smem + L.tab);
+  if (CLS == CLASS_COUNTER) {
+    // extrapolation terms of RateFunctions.scala:74-77,92 for samples m steps apart: sampledInterval = (m * step) / 1000,
+    // averageDurationBetweenSamples = sampledInterval / (numSamples - 1) with numSamples - 1 = m
+    if (tid <= TILE_CTR_TABMAX) {
+      TileCtrTab& e = reinterpret_cast<TileCtrTab*>(smem + L.tab)[tid];
+      const double sI = (double)((int64_t)tid * q.step) / 1000.0;
+      const double avg = sI / ((double)(tid + 1) - 1.0);
+      e.sI = sI; e.thr = avg * 1.1; e.half = avg / 2.0; e.rcpSI = tid > 0 ? 1.0 / sI : 0.0;
+    }
+    bar_consumers();
+  }
   uint32_t parity = 0;
   int b = 0;
   double aacc[TILE_AGG_ACC]; uint32_t acnt[TILE_AGG_ACC]; bool item_bad = false;      // AGG: this thread's windows tid + j * TILE_THREADS
@@ -411,7 +429,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
     TileMeta* Mc = reinterpret_cast<TileMeta*>(smem + L.meta + b * 128);
     TileCtr* CTc = reinterpret_cast<TileCtr*>(smem + L.ctr) + b * (TILE_NS * TILE_MAXC);
     TileDrops* DRc = reinterpret_cast<TileDrops*>(smem + L.drops);
-    mbar_wait(ready + b, (tj >> 1) & 1); ++tj;   // A(t): descriptors ready (no consumer-wide barrier: the windows-end barrier of the
+    mbar_wait_parked(ready + b, (tj >> 1) & 1); ++tj;   // A(t): descriptors ready (no consumer-wide barrier: the windows-end barrier of the
                                                  // previous tile already separates the tiles)
     if (Mc->staged) { mbar_wait(bar, parity); parity ^= 1; }    // already complete (the producer saw it); orders the TMA writes
     const int64_t i0 = Mc->i0; const int ns = Mc->ns;
@@ -508,11 +526,20 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
             if (act[jj] && CTc[ds * TILE_MAXC + cc[jj]].dropped) {
               TileDrops& D = DRc[ds * TILE_MAXC + cc[jj]];
               double prevv = nan0(__longlong_as_double((long long)pre));
+              uint32_t dm = 0;                 // bit i: row i of the group drops
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const double cur = nan0(__longlong_as_double((long long)(d[jj][i] ^ pre)));
-                if (i < nleft && cur < prevv) { const int at = atomicAdd(&D.n, 1); if (at < TILE_MAXDROP) { D.pos[at] = 1 + g * 8 + i; D.amt[at] = prevv; } }
+                dm |= (i < nleft && cur < prevv) ? (1u << i) : 0u;
                 prevv = cur;
+              }
+              while (dm) {                     // rare: record position and amount (the value before the drop)
+                const int i = __ffs(dm) - 1; dm &= dm - 1;
+                uint64_t prevbits = pre;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (j == i - 1) prevbits = d[jj][j] ^ pre;
+                const int at = atomicAdd(&D.n, 1);
+                if (at < TILE_MAXDROP) { D.pos[at] = 1 + g * 8 + i; D.amt[at] = nan0(__longlong_as_double((long long)prevbits)); }
               }
             }
           }
@@ -556,6 +583,19 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         if (S.regular == 1) {
           bool overflow = false;
           for (int c = 0; c < S.n; ++c) overflow |= FN != FN_DELTA && CTc[warp * TILE_MAXC + c].dropped && DRc[warp * TILE_MAXC + c].n > TILE_MAXDROP;
+          if (!overflow && FN != FN_DELTA && lane < S.n && CTc[warp * TILE_MAXC + lane].dropped) {
+            // lane c: sort chunk c's drops by row and turn the amounts into running sums (reference order of additions)
+            TileDrops& D = DRc[warp * TILE_MAXC + lane];
+            const int n = D.n;
+            for (int i = 1; i < n; ++i) {
+              const int p = D.pos[i]; const double a = D.amt[i]; int j = i - 1;
+              while (j >= 0 && D.pos[j] > p) { D.pos[j + 1] = D.pos[j]; D.amt[j + 1] = D.amt[j]; --j; }
+              D.pos[j + 1] = p; D.amt[j + 1] = a;
+            }
+            double run = 0.0;
+            for (int i = 0; i < n; ++i) { run += D.amt[i]; D.amt[i] = run; }
+          }
+          __syncwarp();
           if (overflow) {                         // more drops in one chunk than the list holds: the generic kernel takes the series
             __syncwarp();
             if (lane == 0) {
@@ -565,14 +605,24 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
           } else {
             for (int c = 0; c < S.n; ++c) {
               const TileChunk& ch = S.c[c];
-              if (ch.kA > ch.kB) continue;
+              if (ch.kA2 > ch.kB2) continue;
+              const bool hasfast = ch.kA <= ch.kB;
               const TileCtr kc = CTc[warp * TILE_MAXC + c];
               const TileDrops& D = DRc[warp * TILE_MAXC + c];
               const bool drp = FN != FN_DELTA && kc.dropped;
               const double* cv = vals + (size_t)warp * L.vals_pitch + ch.row_base;
               double* o = otile + (size_t)warp * L.out_pitch;
-              for (int kk = ch.kA + lane; kk <= ch.kB; kk += 32) {
-                const double v1 = ctr_value(cv, ch.s0 + kk, D, drp), v2 = ctr_value(cv, ch.e0 + kk, D, drp);
+              // drops of this chunk (warp-uniform): none / one (position and amount in registers) / several (list walk)
+              const int dn = drp ? D.n : 0;
+              const int dpos0 = dn >= 1 ? D.pos[0] : 0x7fffffff;
+              const double damt0 = dn >= 1 ? D.amt[0] : 0.0;
+              for (int kk = ch.kA + lane; hasfast && kk <= ch.kB; kk += 32) {
+                const int r1 = ch.s0 + kk, r2 = ch.e0 + kk;
+                double v1 = cv[r1], v2 = cv[r2];
+                if (drp) {
+                  if (dn <= 1) { v1 = nan0(v1) + (r1 >= dpos0 ? damt0 : 0.0); v2 = nan0(v2) + (r2 >= dpos0 ? damt0 : 0.0); }
+                  else { v1 = nan0(v1) + drops_cum(D, r1); v2 = nan0(v2) + drops_cum(D, r2); }     // sorted running sums
+                }
                 const double delta = v2 - v1;
                 double ratio = kc.ratio0;
                 if (FN != FN_DELTA && delta > 0 && v1 >= 0 && !(v1 > delta * kc.skipC)) {      // zero-point clamp may apply (:84-90)
@@ -583,6 +633,38 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
                 }
                 const double scaled = delta * ratio;
                 o[kk] = FN == FN_RATE ? __dmul_rn(div_invariant(scaled, fdiv, frcp), 1000.0) : scaled;
+              }
+              // the chunk's clamped single-chunk windows (window start before its first row or end after its last): the
+              // sample distance varies with the window, the table supplies the terms that depend on it
+              const int nlo = hasfast ? ch.kA - ch.kA2 : ch.kB2 - ch.kA2 + 1, nhi = hasfast ? ch.kB2 - ch.kB : 0;
+              for (int u = lane; u < nlo + nhi; u += 32) {
+                const int kk = u < nlo ? ch.kA2 + u : ch.kB + 1 + (u - nlo);
+                int r1 = ch.s0 + kk; if (r1 < 0) r1 = 0;
+                int r2 = ch.e0 + kk; if (r2 > ch.nrows - 1) r2 = ch.nrows - 1;
+                double res = __longlong_as_double(0x7ff8000000000000LL);
+                if (r2 > r1) {                                   // highestTime > lowestTime (RateFunctions.scala:271,284)
+                  double v1 = cv[r1], v2 = cv[r2];
+                  if (drp) { v1 = nan0(v1) + drops_cum(D, r1); v2 = nan0(v2) + drops_cum(D, r2); }
+                  const int64_t wEnd = q.start + (int64_t)kk * q.step, cws = wEnd - winDur - (q.inclusive ? 0 : 1);
+                  res = extrapolated_rate_tile<FN != FN_DELTA, FN == FN_RATE>(cws, wEnd, r2 - r1 + 1, ch.init + (int64_t)r1 * q.step, v1,
+                                                                              ch.init + (int64_t)r2 * q.step, v2, fdiv, frcp, q.step, CTAB);
+                }
+                o[kk] = res;
+              }
+            }
+            // windows outside every chunk's single-chunk interval (chunk junctions, no data): literal fold, lanes over the gaps
+            {
+              const double* sv = vals + (size_t)warp * L.vals_pitch;
+              double* o = otile + (size_t)warp * L.out_pitch;
+              int prev = -1;
+              for (int c = 0; c <= S.n; ++c) {
+                int gend = q.T;
+                if (c < S.n) { if (S.c[c].kA2 > S.c[c].kB2) continue; gend = S.c[c].kA2; }
+                for (int k = prev + 1 + lane; k < gend; k += 32) {
+                  const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - winDur;
+                  o[k] = tile_eval_counter<FN>(S, CTc + warp * TILE_MAXC, DRc + warp * TILE_MAXC, sv, q, wStart, wEnd, k, fdiv, frcp, CTAB);
+                }
+                if (c < S.n) prev = S.c[c].kB2;
               }
             }
           }
@@ -637,7 +719,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         }
       }
       // ---------------------------------------------------------------- windows: everything else (chunk junctions, short windows)
-      const int nrest = Mc->rpref[TILE_NS];
+      const int nrest = CLS == CLASS_COUNTER ? 0 : Mc->rpref[TILE_NS];
       for (int it = tid; it < nrest; it += TILE_THREADS) {
         int s = 0;
 #pragma unroll
@@ -653,7 +735,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         const int k = prev + 1 + u;
         const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - winDur;
         const double* sv = vals + (size_t)s * L.vals_pitch;
-        if (CLS == CLASS_COUNTER) otile[(size_t)s * L.out_pitch + k] = tile_eval_counter<FN>(S, CTc + s * TILE_MAXC, DRc + s * TILE_MAXC, sv, q, wStart, wEnd, k, fdiv, frcp);
+        if (CLS == CLASS_COUNTER) otile[(size_t)s * L.out_pitch + k] = tile_eval_counter<FN>(S, CTc + s * TILE_MAXC, DRc + s * TILE_MAXC, sv, q, wStart, wEnd, k, fdiv, frcp, CTAB);
         else otile[(size_t)s * L.out_pitch + k] = any_nan ? tile_eval_window<FN, true>(S, sv, wStart, wEnd, fdiv, k)
                                                           : tile_eval_window<FN, false>(S, sv, wStart, wEnd, fdiv, k);
       }

@@ -23,6 +23,7 @@ struct TileChunk {
   int32_t tlen, vlen;         // timestamp / value vector lengths
   int32_t s0, e0;             // unclamped first / last row of window k = 0 (rows advance by one per window)
   int32_t lowz, highz;        // zero rows before / after the chunk's rows (clamped windows read them as +0.0)
+  int32_t kA2, kB2;           // COUNTER: all single-chunk windows of the chunk, clamped ones included ([kA, kB] = unclamped)
 };
 struct TileSeries {
   int32_t n, regular, rec_off, nblocks, nrest, ngroups, nrows, any_raw;
@@ -41,6 +42,9 @@ struct TileCtr {
 // TileDrops (consumers, per tile): counter drops of a drop-flagged chunk, found while its rows are decoded
 // (CorrectingDoubleVectorReader.corrected, DoubleVector.scala:325-342): row position and the amount added to the correction
 constexpr int TILE_MAXDROP = 4;
+// per-query table of the extrapolation terms that depend only on (numSamples - 1) = m when the samples are m steps apart
+constexpr int TILE_CTR_TABMAX = 64;
+struct TileCtrTab { double sI, thr, half, rcpSI; };      // sampledInterval, 1.1 * average interval, average / 2, RN(1 / sI)
 struct TileDrops {
   int32_t n, pos[TILE_MAXDROP], pad[3];
   double amt[TILE_MAXDROP];
@@ -55,7 +59,7 @@ struct TileMeta {                         // per-tile work-list prefixes and fla
 };
 
 struct TileSmem {                         // byte offsets inside dynamic shared memory (all multiples of 128)
-  uint32_t rec, vals, out, desc, gtot, meta, ctr, drops, total;
+  uint32_t rec, vals, out, desc, gtot, meta, ctr, drops, tab, total;
   uint32_t rec_cap, vals_pitch /*doubles per series*/, out_pitch /*doubles per series = T*/, desc_stride /*bytes between the two descriptor buffers*/;
 };
 FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t T, uint32_t pad_rows, bool counter_class = false) {
@@ -71,8 +75,9 @@ FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, u
   L.desc = o; o += 2 * align_up(TILE_NS * (uint32_t)sizeof(TileSeries), 128);      // double-buffered: setup of tile t+1 overlaps tile t
   L.gtot = o; o += TILE_NS * TILE_MAXG * 8 + TILE_NS * (TILE_THREADS / 32) * 8;   // per-slot in-warp prefixes + per-warp totals
   L.meta = o; o += 2 * 128;
-  L.ctr = o; L.drops = o;
-  if (counter_class) { o += 2 * align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileCtr), 128); L.drops = o; o += align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileDrops), 128); }
+  L.ctr = o; L.drops = o; L.tab = o;
+  if (counter_class) { o += 2 * align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileCtr), 128); L.drops = o; o += align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileDrops), 128);
+                       L.tab = o; o += align_up((TILE_CTR_TABMAX + 1) * (uint32_t)sizeof(TileCtrTab), 128); }
   L.total = o;
   return L;
 }
