@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: gpuretry.sh <timeout> '<command>'   -- retries while gpurun answers "no slot free" (exit 3)
 for i in 1 2 3 4 5 6 7 8 9 10; do
-  /usr/local/graft/bin/gpurun --timeout "$1" -- "$2"
+  /usr/local/graft/bin/gpurun ${GPURUN_EXTRA} --timeout "$1" -- "$2"
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
   sleep 90
