@@ -15,7 +15,7 @@ OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CORRUPT_VECTOR, ERR_UNSUPPORTED, ERR_QUERY_LI
 
 EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_last_error", "filo_load_series", "filo_synth_table",
            "filo_table_set_groups", "filo_table_get_info", "filo_table_read_record", "filo_table_read_arena", "filo_table_free",
-           "filo_num_windows", "filo_query", "filo_query_device", "filo_scan_series", "filo_present_partials"]
+           "filo_num_windows", "filo_query", "filo_query_device", "filo_scan_series", "filo_host_register", "filo_host_unregister", "filo_present_partials"]
 
 
 class Cfg(C.Structure):
@@ -86,6 +86,8 @@ def _sig(L):
     L.filo_query_device.argtypes = [vp, vp, i32, i64, i64, i64, i64, i32, i32, i32, vp, vp, vp, C.POINTER(Stats)]
     L.filo_scan_series.restype = i32
     L.filo_scan_series.argtypes = [vp, i64, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, vp, C.POINTER(Stats)]
+    L.filo_host_register.restype = i32; L.filo_host_register.argtypes = [vp, vp, i64]
+    L.filo_host_unregister.restype = i32; L.filo_host_unregister.argtypes = [vp, vp]
     L.filo_present_partials.restype = i32; L.filo_present_partials.argtypes = [vp, i32, i64, vp, vp, vp, vp]
 
 
@@ -217,6 +219,13 @@ class Context:
         if aggr in (AGG_AVG, AGG_TOPK, AGG_BOTTOMK) or (flags & Q_PARTIAL and aggr != AGG_NONE):
             return out, aux
         return out
+
+    def host_register(self, arr):
+        """filo_host_register over a numpy array's buffer (chunk vectors inside it are then gathered by the GPU directly)."""
+        self._check(lib().filo_host_register(self.h, arr.ctypes.data, arr.nbytes))
+
+    def host_unregister(self, arr):
+        self._check(lib().filo_host_unregister(self.h, arr.ctypes.data))
 
     def scan_series(self, n_chunks, info_addrs, fn, start, step, end, window, ts_col=0, val_col=1, schema_flags=0, out=None):
         """filo_scan_series: ingest + query + read-back of host-resident chunks in one pipelined call -> [n_series, T].

@@ -7,6 +7,7 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -33,10 +34,17 @@ struct filo_ctx {
     int64_t* d_off = nullptr; size_t d_off_cap = 0;
     double* d_out = nullptr; size_t d_out_cap = 0;
     void* h_sink = nullptr;                              // pinned AsyncSink
+    void* h_gch = nullptr; size_t h_gch_cap = 0;         // pinned: gather list of the batch (zero-copy path)
+    void* d_gch = nullptr; size_t d_gch_cap = 0;
+    void* h_gs = nullptr; size_t h_gs_cap = 0;           // pinned: per-series gather headers
+    void* d_gs = nullptr; size_t d_gs_cap = 0;
     cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
   };
   std::mutex scan_mu;
   ScanSlot scan[3];
+  // host memory registered for device access (filo_host_register): chunk vectors inside these ranges are gathered by the GPU
+  struct HostRange { uintptr_t base; size_t bytes; };
+  std::vector<HostRange> ranges;
 };
 
 struct filo_table {
@@ -100,9 +108,11 @@ void filo_ctx_destroy(filo_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  for (auto& r : ctx->ranges) cudaHostUnregister((void*)r.base);
   for (auto& sl : ctx->scan) {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
     cudaFreeHost(sl.h_in); cudaFreeHost(sl.h_off); cudaFreeHost(sl.h_sink); cudaFree(sl.d_in); cudaFree(sl.d_off); cudaFree(sl.d_out);
+    cudaFreeHost(sl.h_gch); cudaFreeHost(sl.h_gs); cudaFree(sl.d_gch); cudaFree(sl.d_gs);
     if (sl.done) cudaEventDestroy(sl.done);
     if (sl.stream) cudaStreamDestroy(sl.stream);
   }
@@ -673,6 +683,80 @@ extern "C" int32_t filo_query(filo_ctx* ctx, const filo_table* t, int32_t fn, in
 }
 
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// zero-copy gather: the GPU reads chunk vectors straight out of registered (pinned, mapped) host memory
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+struct GatherChunk {            // one chunk with rows, in series order
+  uint64_t ts_src, val_src;     // host addresses (UVA) of the vectors to copy
+  int64_t start_time, end_time;
+  int32_t num_rows, ts_bytes, val_bytes, val_len;
+  int32_t drop_patch, pad;      // 0: keep, 1: set, 2: clear the counter drop bit (masked wrappers carry it on the outer vector)
+};
+struct GatherSeries { uint32_t rec_bytes, n_chunks, n_rows, flags; int64_t first_chunk; };
+
+__device__ __forceinline__ void copy_bytes_warp(uint8_t* dst, const uint8_t* src, int n, int lane) {
+  // dst is 8-byte aligned; src usually is at least 4-byte aligned (BinaryVectors are allocated word aligned)
+  if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+    const int nw = n >> 2;
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src); uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
+    for (int i = lane; i < nw; i += 32) d4[i] = s4[i];
+    for (int i = (nw << 2) + lane; i < n; i += 32) dst[i] = src[i];
+  } else {
+    for (int i = lane; i < n; i += 32) dst[i] = src[i];
+  }
+}
+// warp per series: record header, chunk entries, vectors verbatim (same bytes fill_record writes on the host)
+__global__ void __launch_bounds__(256) gather_records_kernel(const GatherSeries* __restrict__ gs, const GatherChunk* __restrict__ gc,
+                                                             const int64_t* __restrict__ rec_off, int64_t n, uint8_t* __restrict__ arena) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = w; i < n; i += nw) {
+    const GatherSeries S = gs[i];
+    uint8_t* rec = arena + rec_off[i];
+    if (lane == 0) { RecordHeader h{S.rec_bytes, S.n_chunks, S.n_rows, S.flags}; *reinterpret_cast<RecordHeader*>(rec) = h; }
+    uint32_t off = sizeof(RecordHeader) + S.n_chunks * (uint32_t)sizeof(ChunkEntry), row_base = 0;
+    for (uint32_t c = 0; c < S.n_chunks; ++c) {
+      const GatherChunk G = gc[S.first_chunk + c];
+      const uint32_t ts_off = off, ts_pad = align_up((uint32_t)G.ts_bytes, 8), val_off = off + ts_pad, val_pad = align_up((uint32_t)G.val_bytes, 8);
+      if (lane == 0) {
+        ChunkEntry ce; ce.start_time = G.start_time; ce.end_time = G.end_time; ce.num_rows = G.num_rows; ce.ts_off = ts_off; ce.val_off = val_off; ce.row_base = row_base;
+        reinterpret_cast<ChunkEntry*>(rec + sizeof(RecordHeader))[c] = ce;
+      }
+      copy_bytes_warp(rec + ts_off, reinterpret_cast<const uint8_t*>(G.ts_src), G.ts_bytes, lane);
+      copy_bytes_warp(rec + val_off, reinterpret_cast<const uint8_t*>(G.val_src), G.val_bytes, lane);
+      if (lane < (int)(ts_pad - G.ts_bytes)) rec[ts_off + G.ts_bytes + lane] = 0;
+      if (lane < (int)(val_pad - G.val_bytes)) rec[val_off + G.val_bytes + lane] = 0;
+      __syncwarp();
+      if (lane == 0 && G.drop_patch) { if (G.drop_patch == 1) rec[val_off + 7] |= 0x80; else rec[val_off + 7] &= 0x7f; }
+      off = val_off + val_pad; row_base += (uint32_t)G.val_len;
+    }
+    for (uint32_t k = off + lane; k < S.rec_bytes; k += 32) rec[k] = 0;
+  }
+}
+}
+
+extern "C" int32_t filo_host_register(filo_ctx* ctx, const void* base, int64_t bytes) {
+  if (!ctx || !base || bytes <= 0) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_host_register: bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaHostRegister(const_cast<void*>(base), (size_t)bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+  std::lock_guard<std::mutex> g(ctx->scan_mu);
+  ctx->ranges.push_back({(uintptr_t)base, (size_t)bytes});
+  return FILO_OK;
+}
+extern "C" int32_t filo_host_unregister(filo_ctx* ctx, const void* base) {
+  if (!ctx || !base) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_host_unregister: bad arguments");
+  std::lock_guard<std::mutex> g(ctx->scan_mu);
+  for (size_t i = 0; i < ctx->ranges.size(); ++i) if (ctx->ranges[i].base == (uintptr_t)base) {
+    for (auto& sl : ctx->scan) if (sl.stream) cudaStreamSynchronize(sl.stream);
+    CUDA_TRY(ctx, cudaHostUnregister(const_cast<void*>(base)));
+    ctx->ranges.erase(ctx->ranges.begin() + (long)i);
+    return FILO_OK;
+  }
+  return fail(ctx, FILO_ERR_INVALID_ARG, "filo_host_unregister: range not registered");
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // filo_scan_series: ingest + query + result read-back of host-resident chunks in one pipelined call
 // ------------------------------------------------------------------------------------------------------------------
@@ -707,6 +791,11 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
     if (n_chunks[i] < 0) return fail(ctx, FILO_ERR_INVALID_ARG, "negative n_chunks");
     chunk_base[i + 1] = chunk_base[i] + n_chunks[i];
   }
+  static const bool timing = std::getenv("FILO_DEBUG_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
+  const auto t_begin = now();
+  double t_fill = 0, t_retire = 0, t_enq = 0;
   // ---- pass 1: validate + size (same rules as filo_load_series)
   std::vector<SeriesPlan> plan((size_t)n_series);
   const LoadIn in{n_series, n_chunks, addrs, chunk_base.data(), ts_col, val_col};
@@ -718,25 +807,51 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
   }
   if (ctx->cfg.max_data_per_shard_query > 0 && tot.alg > ctx->cfg.max_data_per_shard_query)
     return fail(ctx, FILO_ERR_QUERY_LIMIT, "raw data bytes scanned exceeds max-data-per-shard-query");
+  const double t_plan = ms_since(t_begin);
   // ---- batches: consecutive series, <= SLAB bytes of records and a bounded result block
   const size_t SLAB = (size_t)192 << 20;
   const int64_t max_rows_out = std::max<int64_t>(1, (int64_t)(((size_t)256 << 20) / ((size_t)std::max(T, 1) * 8)));
-  struct Batch { int64_t s0, s1; size_t bytes; };
+  struct Batch { int64_t s0, s1; size_t bytes; int64_t chunks; };
   std::vector<Batch> batches;
-  size_t max_bytes = 0; int64_t max_n = 0;
+  size_t max_bytes = 0; int64_t max_n = 0, max_chunks = 0;
   for (int64_t s0 = 0; s0 < n_series;) {
-    int64_t s1 = s0; size_t bytes = 0;
-    while (s1 < n_series && s1 - s0 < max_rows_out && (s1 == s0 || bytes + plan[(size_t)s1].rec_bytes <= SLAB)) { bytes += plan[(size_t)s1].rec_bytes; ++s1; }
-    batches.push_back(Batch{s0, s1, bytes});
-    max_bytes = std::max(max_bytes, bytes); max_n = std::max(max_n, s1 - s0);
+    int64_t s1 = s0; size_t bytes = 0; int64_t chunks = 0;
+    while (s1 < n_series && s1 - s0 < max_rows_out && (s1 == s0 || bytes + plan[(size_t)s1].rec_bytes <= SLAB)) { bytes += plan[(size_t)s1].rec_bytes; chunks += plan[(size_t)s1].n_chunks; ++s1; }
+    batches.push_back(Batch{s0, s1, bytes, chunks});
+    max_bytes = std::max(max_bytes, bytes); max_n = std::max(max_n, s1 - s0); max_chunks = std::max(max_chunks, chunks);
     s0 = s1;
+  }
+  // zero-copy gather when every vector of the call lies in memory registered with filo_host_register (checked per series below)
+  std::vector<filo_ctx::HostRange> ranges = ctx->ranges;
+  auto in_ranges = [&](const uint8_t* p, size_t n) { for (auto& r : ranges) if ((uintptr_t)p >= r.base && (uintptr_t)p + n <= r.base + r.bytes) return true; return false; };
+  bool use_gather = !ranges.empty();
+  if (use_gather) {
+    std::atomic<bool> all_in{true};
+    host_pool().run(n_series, [&](int, int64_t b, int64_t e) {
+      for (int64_t i = b; i < e && all_in.load(std::memory_order_relaxed); ++i)
+        for (int32_t j = 0; j < n_chunks[i]; ++j) {
+          const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)addrs[chunk_base[(size_t)i] + j]);
+          if (rd32(info + 8) <= 0) continue;
+          VecInfo tv, vv;
+          classify_ts(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * ts_col)), tv);
+          classify_val(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * val_col)), vv);
+          if (!in_ranges(tv.p, (size_t)tv.total) || !in_ranges(vv.p, (size_t)vv.total)) { all_in = false; break; }
+        }
+    });
+    use_gather = all_in.load();
   }
   const int NSLOT = 3;
   for (int i = 0; i < NSLOT; ++i) {
     filo_ctx::ScanSlot& sl = ctx->scan[i];
     if (!sl.stream) { CUDA_TRY(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)); CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)); }
     if (!sl.h_sink) CUDA_TRY(ctx, cudaHostAlloc(&sl.h_sink, sizeof(AsyncSink), cudaHostAllocDefault));
-    if (int32_t rc = grow_pinned(ctx, sl.h_in, sl.h_in_cap, max_bytes + 64)) return rc;
+    if (!use_gather) { if (int32_t rc = grow_pinned(ctx, sl.h_in, sl.h_in_cap, max_bytes + 64)) return rc; }
+    else {
+      if (int32_t rc = grow_pinned(ctx, sl.h_gch, sl.h_gch_cap, (size_t)(max_chunks + 1) * sizeof(GatherChunk))) return rc;
+      if (int32_t rc = grow_device(ctx, sl.d_gch, sl.d_gch_cap, (size_t)(max_chunks + 1) * sizeof(GatherChunk))) return rc;
+      if (int32_t rc = grow_pinned(ctx, sl.h_gs, sl.h_gs_cap, (size_t)(max_n + 1) * sizeof(GatherSeries))) return rc;
+      if (int32_t rc = grow_device(ctx, sl.d_gs, sl.d_gs_cap, (size_t)(max_n + 1) * sizeof(GatherSeries))) return rc;
+    }
     if (int32_t rc = grow_pinned(ctx, sl.h_off, sl.h_off_cap, (size_t)(max_n + 1) * 8)) return rc;
     if (int32_t rc = grow_device(ctx, sl.d_in, sl.d_in_cap, max_bytes + 64)) return rc;
     if (int32_t rc = grow_device(ctx, sl.d_off, sl.d_off_cap, (size_t)(max_n + 1) * 8)) return rc;
@@ -760,16 +875,58 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
     const Batch& B = batches[bi];
     const int si = (int)(bi % NSLOT);
     filo_ctx::ScanSlot& sl = ctx->scan[si];
-    if ((rc = retire(si)) != FILO_OK) break;
+    { const auto t0 = now(); rc = retire(si); t_retire += ms_since(t0); }
+    if (rc != FILO_OK) break;
     const int64_t nb = B.s1 - B.s0;
+    const auto t_f0 = now();
     sl.h_off[0] = 0;
     for (int64_t j = 0; j < nb; ++j) sl.h_off[j + 1] = sl.h_off[j] + plan[(size_t)(B.s0 + j)].rec_bytes;
-    host_pool().run(nb, [&](int, int64_t b, int64_t e) {
-      for (int64_t j = b; j < e; ++j) fill_record(in, B.s0 + j, plan[(size_t)(B.s0 + j)], sl.h_in + sl.h_off[j]);
-    });
-    std::memset(sl.h_in + B.bytes, 0, 64);
-    cudaError_t ce = cudaMemcpyAsync(sl.d_in, sl.h_in, B.bytes + 64, cudaMemcpyHostToDevice, sl.stream);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(sl.d_off, sl.h_off, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, sl.stream);
+    cudaError_t ce = cudaSuccess;
+    if (use_gather) {
+      // gather list: per series header + per chunk source addresses; the GPU copies the vectors out of the registered memory
+      GatherSeries* gs = reinterpret_cast<GatherSeries*>(sl.h_gs); GatherChunk* gc = reinterpret_cast<GatherChunk*>(sl.h_gch);
+      int64_t cb = 0;
+      for (int64_t j = 0; j < nb; ++j) { const SeriesPlan& p = plan[(size_t)(B.s0 + j)]; gs[j] = GatherSeries{p.rec_bytes, p.n_chunks, p.n_rows, p.flags, cb}; cb += p.n_chunks; }
+      host_pool().run(nb, [&](int, int64_t b, int64_t e) {
+        for (int64_t j = b; j < e; ++j) {
+          const int64_t i = B.s0 + j; GatherChunk* o = gc + gs[j].first_chunk;
+          for (int32_t jj = 0; jj < n_chunks[i]; ++jj) {
+            const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)addrs[chunk_base[(size_t)i] + jj]);
+            const int32_t numRows = rd32(info + 8);
+            if (numRows <= 0) continue;
+            VecInfo tv, vv;
+            classify_ts(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * ts_col)), tv);
+            classify_val(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * val_col)), vv);
+            GatherChunk g;
+            g.ts_src = (uint64_t)(uintptr_t)tv.p; g.val_src = (uint64_t)(uintptr_t)vv.p;
+            g.start_time = (int64_t)(((1ull << 63) ^ (uint64_t)rd64(info)) >> 22); g.end_time = rd64(info + 20);
+            g.num_rows = numRows; g.ts_bytes = tv.total; g.val_bytes = vv.total; g.val_len = vv.len;
+            g.drop_patch = vv.drop_patch ? (vv.drop ? 1 : 2) : 0; g.pad = 0;
+            *o++ = g;
+          }
+        }
+      });
+      t_fill += ms_since(t_f0);
+      ce = cudaMemcpyAsync(sl.d_gs, sl.h_gs, (size_t)nb * sizeof(GatherSeries), cudaMemcpyHostToDevice, sl.stream);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(sl.d_gch, sl.h_gch, (size_t)B.chunks * sizeof(GatherChunk), cudaMemcpyHostToDevice, sl.stream);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(sl.d_off, sl.h_off, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, sl.stream);
+      if (ce == cudaSuccess) {
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nb + 7) / 8, (int64_t)ctx->sm_count * 8));
+        gather_records_kernel<<<grid, 256, 0, sl.stream>>>(reinterpret_cast<const GatherSeries*>(sl.d_gs), reinterpret_cast<const GatherChunk*>(sl.d_gch),
+                                                           sl.d_off, nb, sl.d_in);
+        ce = cudaGetLastError();
+      }
+      if (ce == cudaSuccess) ce = cudaMemsetAsync(sl.d_in + B.bytes, 0, 64, sl.stream);
+    } else {
+      host_pool().run(nb, [&](int, int64_t b, int64_t e) {
+        for (int64_t j = b; j < e; ++j) fill_record(in, B.s0 + j, plan[(size_t)(B.s0 + j)], sl.h_in + sl.h_off[j]);
+      });
+      std::memset(sl.h_in + B.bytes, 0, 64);
+      t_fill += ms_since(t_f0);
+      ce = cudaMemcpyAsync(sl.d_in, sl.h_in, B.bytes + 64, cudaMemcpyHostToDevice, sl.stream);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(sl.d_off, sl.h_off, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, sl.stream);
+    }
+    const auto t_e0 = now();
     if (ce != cudaSuccess) { rc = fail(ctx, FILO_ERR_CUDA, std::string("scan H2D: ") + cudaGetErrorString(ce)); break; }
     filo_table view;                                    // a table over the slot's buffers (not owned)
     view.n_series = nb; view.d_arena = sl.d_in; view.d_rec_off = sl.d_off; view.max_rows = tot.maxrows; view.max_chunks = tot.maxch;
@@ -782,10 +939,13 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
     if (ce == cudaSuccess) ce = cudaEventRecord(sl.done, sl.stream);
     if (ce != cudaSuccess) { rc = fail(ctx, FILO_ERR_CUDA, std::string("scan D2H: ") + cudaGetErrorString(ce)); break; }
     fl[si].s0 = B.s0;
-    acc.h2d_bytes += (int64_t)B.bytes + (nb + 1) * 8; acc.d2h_bytes += nb * (int64_t)T * 8;
+    t_enq += ms_since(t_e0);
+    acc.h2d_bytes += (int64_t)B.bytes + (nb + 1) * 8 + (use_gather ? (int64_t)(nb * sizeof(GatherSeries) + B.chunks * sizeof(GatherChunk)) : 0); acc.d2h_bytes += nb * (int64_t)T * 8;
   }
   for (int i = 0; i < NSLOT; ++i) { const int32_t r2 = retire(i); if (rc == FILO_OK) rc = r2; }
   if (rc != FILO_OK) { for (int i = 0; i < NSLOT; ++i) if (ctx->scan[i].stream) cudaStreamSynchronize(ctx->scan[i].stream); return rc; }
+  if (timing) fprintf(stderr, "[filo] scan_series: %lld series, %zu batches, total %.1f ms: plan %.1f, fill %.1f, enqueue %.1f, slot waits %.1f\n",
+                      (long long)n_series, batches.size(), ms_since(t_begin), t_plan, t_fill, t_enq, t_retire);
   if (stats) *stats = acc;
   return FILO_OK;
 }

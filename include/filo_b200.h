@@ -180,6 +180,13 @@ int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t range_fn,
                           int64_t start_ms, int64_t step_ms, int64_t end_ms, int64_t window_ms,
                           int32_t aggr_op, int32_t k, int32_t flags,
                           void* d_out_values, void* d_out_aux, void* cuda_stream, filo_stats* stats);
+/* Registers a region of host memory that holds chunk vectors (FiloDB's off-heap block memory, BlockManager pages) for direct
+ * device access: pinned + mapped once, like the reference maps its blocks once at start-up.  filo_scan_series then lets the
+ * GPU gather the vectors of a call straight out of the region (no staging copy on the host) whenever every vector of the
+ * call lies inside registered regions; otherwise it stages through pinned slabs as before.  Unregister before freeing. */
+int32_t filo_host_register(filo_ctx* ctx, const void* base, int64_t bytes);
+int32_t filo_host_unregister(filo_ctx* ctx, const void* base);
+
 /* PeriodicSamplesMapper over host-resident chunks in ONE pipelined call: filo_load_series + filo_query (aggr NONE) +
  * result read-back, processed in batches so that the host gather of batch b, the H2D copy and the kernels of batch b-1
  * and the D2H of batch b-2 overlap (pinned staging kept in the context).  Same argument meaning, validation and errors as

@@ -374,3 +374,33 @@ def test_scan_series_pipelined_matches_oracle(gpu, oracle):
         ctx.scan_series(nch, addrs, capi.FN_RATE, t0 + 10, 15000, t0, 300000)          # start > end
     empty = ctx.scan_series(np.zeros(0, np.int32), np.zeros(0, np.uint64), capi.FN_RATE, t0, 15000, t0 + 60000, 300000)
     assert empty.shape == (0, 5)
+
+
+def test_scan_series_zero_copy_gather(gpu, oracle):
+    """With the chunk memory registered (filo_host_register) the GPU gathers the vectors itself: same bits, same counters, and
+    the arena it builds is byte-identical to the staged one (filo_load_series)."""
+    capi, ctx = gpu; o = oracle
+    t0 = 1_700_000_000_000
+    S = 700
+    tab = ctx.synth_table(S, 480, 400, t0, 15000, value_kind=1, value_enc=1, reset_period=200, nan_per_million=20000, schema_flags=1, seed=7)
+    arena, rec_off = tab.read_arena(0, S)
+    import bench
+    nch, addrs, keep = bench.host_chunk_infos(arena, rec_off, S)
+    start, step, end, window = t0, 15000, t0 + 7200000, 300000
+    staged = ctx.scan_series(nch, addrs, capi.FN_RATE, start, step, end, window, schema_flags=capi.SCHEMA_CUMULATIVE)
+    st_staged = dict(ctx.last_stats)
+    ctx.host_register(arena)
+    try:
+        for name in ("FN_RATE", "FN_SUM_OVER_TIME", "FN_LAST"):
+            got = ctx.scan_series(nch, addrs, getattr(capi, name), start, step, end, window, schema_flags=capi.SCHEMA_CUMULATIVE)
+            st = dict(ctx.last_stats)
+            exp = ctx.query(tab, getattr(capi, name), start, step, end, window)
+            assert_same(got, exp, "zero-copy scan %s" % name)
+            assert st["samples_scanned"] == ctx.last_stats["samples_scanned"] and st["bytes_scanned"] == ctx.last_stats["bytes_scanned"]
+        got = ctx.scan_series(nch, addrs, capi.FN_RATE, start, step, end, window, schema_flags=capi.SCHEMA_CUMULATIVE)
+        assert_same(got, staged, "zero-copy vs staged")
+        assert ctx.last_stats["samples_scanned"] == st_staged["samples_scanned"]
+        assert ctx.last_stats["h2d_bytes"] < st_staged["h2d_bytes"]          # only the gather lists cross by explicit copy
+    finally:
+        ctx.host_unregister(arena)
+    tab.free()
