@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="filo", choices=["filo", "reference"])
     ap.add_argument("--series", type=int, default=10_000_000, help="series per GPU")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c2-raw", "c2-counter", "c3", "c3-const", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c2-raw", "c2-counter", "c3", "c3-const", "c4", "c5"])
     ap.add_argument("--e2e-series", type=int, default=-1, help="series in the end-to-end leg (-1 = all)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-series", type=int, default=2_000_000, help="bounded sample for the CPU baseline legs")
@@ -201,6 +201,34 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import oracle as o
+    if args.workload == "c4" and rank == 0:
+        from oracle import hist as H, oracle as o
+        nb, K = 20, min(args.cpu_series, 1024)
+        b = H.Buckets.custom([2.0 * 3 ** i for i in range(nb - 1)] + [float("inf")])
+        rng = np.random.default_rng(42)
+        st = H.HistStore(b)
+        ts = T0_MS + np.arange(ROWS, dtype=np.int64) * INTERVAL
+        for s_ in range(K):
+            obs = np.zeros((ROWS, nb), np.int64)
+            obs[np.arange(ROWS), (np.arange(ROWS) + s_) % nb] = 1 + rng.integers(0, 3, ROWS)
+            st.add_series(ts, np.cumsum(np.cumsum(obs, axis=1), axis=0), [ROWS_PER_CHUNK, ROWS - ROWS_PER_CHUNK])
+        start, step, end, window = T0_MS, STEP, T0_MS + 7200000, WINDOW
+        def one_h():
+            st.query(o.FN_RATE, start, step, end, window, aggr=True, group_ids=np.zeros(K, np.int32), n_groups=1, q=0.99)
+        for _ in range(args.warmup): one_h()
+        t0 = time.perf_counter()
+        for _ in range(args.steps): one_h()
+        dt = (time.perf_counter() - t0) / args.steps
+        val = K * ROWS / dt
+        print(json.dumps({"impl": "reference", "metric": "samples/s scanned+aggregated (rate over 10M series); % HBM roofline", "value": val, "unit": "samples/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "i64 bucket counts -> f64 rates", "data": "synthetic",
+                          "config": {"workload": "C4: histogram_quantile(0.99, sum(rate(h[5m]))) over SectDelta histogram series, 20 custom buckets", "sample": "%d series per step" % K},
+                          "cpu_baseline": {"value": val, "unit": "samples/s", "cores": 1, "kind": "port", "sample": "%d series per step, 1 thread, oracle restatement of ChunkedWindowIteratorH + HistRateFunction" % K},
+                          "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    if args.workload == "c4":
+        return
     synth, fn_name, aggr_name, n_groups, desc = WORKLOADS[args.workload]
     S = min(args.series, args.cpu_series)
     cores = os.cpu_count() or 1
@@ -233,12 +261,115 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+
+def run_c4(args, rank, world, local_rank):
+    """C4: histogram_quantile(0.99, sum(rate(h[5m]))) over SectDelta histogram series (20 custom buckets 2*3^i, +Inf:
+    gateway/.../TestTimeseriesProducer.scala:229-235).  The chunks are produced by the oracle's restatement of the reference
+    appenders for a few thousand distinct series and replicated to the requested series count (the GPU generator does not write
+    histogram vectors yet); the query path is filo_load_series + filo_query_hist."""
+    import torch
+    import filodb_b200.capi as capi
+    from oracle import hist as H, oracle as o
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    S = min(args.series, 1_000_000)
+    K = min(S, 2048)
+    nb = 20
+    b = H.Buckets.custom([2.0 * 3 ** i for i in range(nb - 1)] + [float("inf")])
+    rng = np.random.default_rng(42 + rank)
+    st = H.HistStore(b)
+    ts = T0_MS + np.arange(ROWS, dtype=np.int64) * INTERVAL
+    for s in range(K):
+        obs = np.zeros((ROWS, nb), np.int64)
+        obs[np.arange(ROWS), (np.arange(ROWS) + s) % nb] = 1 + rng.integers(0, 3, ROWS)      # bucket n % B incremented each row (:244-248)
+        rows = np.cumsum(np.cumsum(obs, axis=1), axis=0)
+        if s % 97 == 0: rows[300:] = np.cumsum(np.cumsum(obs[300:], axis=1), axis=0)          # a counter reset
+        st.add_series(ts, rows, [ROWS_PER_CHUNK, ROWS - ROWS_PER_CHUNK])
+    nch_k, addrs_k = st.all_info_addrs()
+    reps = (S + K - 1) // K
+    nch = np.tile(nch_k, reps)[:S].copy()
+    addrs = np.tile(addrs_k.reshape(K, -1), (reps, 1))[:S].reshape(-1).copy()
+    ctx = capi.Context(local_rank)
+    t_gen = time.perf_counter()
+    tab = ctx.load_series(nch, addrs, schema_flags=capi.SCHEMA_CUMULATIVE)
+    t_gen = time.perf_counter() - t_gen
+    ti = tab.info()
+    start, step, end, window = T0_MS, STEP, T0_MS + 7200000, WINDOW
+    T = capi.num_windows(start, step, end)
+
+    def one():
+        ctx.query_hist(tab, capi.FN_RATE, start, step, end, window, aggr=capi.AGG_SUM, quantile=0.99, want_values=False)
+        return ctx.last_stats
+    st0 = one()
+    assert st0["samples_scanned"] == ti.n_samples, (st0, ti.n_samples)
+    for _ in range(args.warmup): one()
+    sampler = ClockSampler(local_rank)
+    if dist: dist.barrier()
+    torch.cuda.synchronize(); sampler.start()
+    kns = [one()["kernel_ns"] for _ in range(args.steps)]          # device time of the step's kernels (CUDA events on the launching stream)
+    torch.cuda.synchronize()
+    if dist: dist.barrier()
+    clocks = sampler.stop()
+    ms = float(np.sum(kns)) / 1e6 / args.steps
+    if dist:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    peak, peak_src = measured_peak()
+    alg_bytes = ti.algorithmic_bytes + T * 8
+    kern_ms = float(np.median(kns)) / 1e6
+    line = {"metric": "samples/s scanned+aggregated (rate over 10M series); % HBM roofline", "value": ti.n_samples * world / (ms / 1e3), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "i64 bucket counts -> f64 rates", "data": "synthetic",
+            "config": {"workload": "C4: %d histogram series x 2h@15s (480 rows, chunks 400+80), SectDelta vectors, 20 custom buckets, "
+                                   "histogram_quantile(0.99, sum(rate(h[5m]))) step 15s, T=%d (per GPU; %d distinct series replicated; shards are independent, no cross-GPU merge)" % (S, T, K),
+                       "series_per_gpu": S, "rows": ROWS, "windows": T, "buckets": nb, "window_ms": window, "step_ms": step,
+                       "l2": "inputs (%.1f GB arena) larger than the 126 MB L2" % (ti.arena_bytes / 1e9), "table_load_s": round(t_gen, 2)},
+            "gpu_launches": int(st0["kernel_launches"]) * args.steps, "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / (kern_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg_bytes / (kern_ms / 1e3) / 1e9 / peak,
+                         "traffic": None, "kernel": "hist_scan_kernel (+ hist_merge_kernel)", "kernel_ms": kern_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src}}
+    # end to end: load (host gather + H2D) + query + quantile read-back per step, bounded number of series
+    if not args.no_e2e:
+        Se = min(S, 200_000 if args.e2e_series < 0 else args.e2e_series)
+        nche, addrse = nch[:Se], addrs[:int(nch[:Se].sum())]
+        def e2e_step():
+            tb = ctx.load_series(nche, addrse, schema_flags=capi.SCHEMA_CUMULATIVE)
+            ctx.query_hist(tb, capi.FN_RATE, start, step, end, window, aggr=capi.AGG_SUM, quantile=0.99, want_values=False)
+            tb.free()
+        e2e_step()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps): e2e_step()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        line["e2e"] = {"value": Se * ROWS * world / dt, "unit": "samples/s", "h2d_bytes_per_step": int(ti.arena_bytes * Se / S), "d2h_bytes_per_step": T * 8,
+                       "s_per_step": dt, "series_per_gpu": Se, "what": "filo_load_series + filo_query_hist + filo_table_free per step"}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        Sc = min(K, 1024)
+        sub = H.HistStore(b)
+        # the oracle store of the first Sc distinct series is `st` itself when Sc == K; query it single-threaded
+        t0 = time.perf_counter()
+        st.query(o.FN_RATE, start, step, end, window, aggr=True, group_ids=np.zeros(K, np.int32), n_groups=1, q=0.99)
+        dtc = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": K * ROWS / dtc, "unit": "samples/s", "cores": 1, "kind": "port",
+                                "sample": "%d of %d series (%.1f s on 1 thread); C++ restatement of ChunkedWindowIteratorH + HistRateFunction + HistSum + quantile" % (K, S, dtc)}
+        del sub
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    tab.free()
+    if dist: dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "c4":
+        run_c4(args, rank, world, local_rank)
         return
     import torch
     import filodb_b200.capi as capi

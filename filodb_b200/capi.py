@@ -15,7 +15,7 @@ OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CORRUPT_VECTOR, ERR_UNSUPPORTED, ERR_QUERY_LI
 
 EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_last_error", "filo_load_series", "filo_synth_table",
            "filo_table_set_groups", "filo_table_get_info", "filo_table_read_record", "filo_table_read_arena", "filo_table_free",
-           "filo_num_windows", "filo_query", "filo_query_device", "filo_scan_series", "filo_host_register", "filo_host_unregister", "filo_present_partials"]
+           "filo_num_windows", "filo_query", "filo_query_device", "filo_scan_series", "filo_query_hist", "filo_host_register", "filo_host_unregister", "filo_present_partials"]
 
 
 class Cfg(C.Structure):
@@ -34,7 +34,7 @@ class Stats(C.Structure):
 class TableInfo(C.Structure):
     _fields_ = [("n_series", C.c_int64), ("n_chunks", C.c_int64), ("n_samples", C.c_int64), ("arena_bytes", C.c_int64),
                 ("algorithmic_bytes", C.c_int64), ("max_rows_per_series", C.c_int32), ("max_chunks_per_series", C.c_int32),
-                ("n_groups", C.c_int32), ("schema_flags", C.c_int32)]
+                ("n_groups", C.c_int32), ("schema_flags", C.c_int32), ("hist_buckets", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SynthSpec(C.Structure):
@@ -86,6 +86,8 @@ def _sig(L):
     L.filo_query_device.argtypes = [vp, vp, i32, i64, i64, i64, i64, i32, i32, i32, vp, vp, vp, C.POINTER(Stats)]
     L.filo_scan_series.restype = i32
     L.filo_scan_series.argtypes = [vp, i64, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, vp, C.POINTER(Stats)]
+    L.filo_query_hist.restype = i32
+    L.filo_query_hist.argtypes = [vp, vp, i32, i64, i64, i64, i64, i32, C.c_double, vp, vp, C.POINTER(Stats)]
     L.filo_host_register.restype = i32; L.filo_host_register.argtypes = [vp, vp, i64]
     L.filo_host_unregister.restype = i32; L.filo_host_unregister.argtypes = [vp, vp]
     L.filo_present_partials.restype = i32; L.filo_present_partials.argtypes = [vp, i32, i64, vp, vp, vp, vp]
@@ -219,6 +221,19 @@ class Context:
         if aggr in (AGG_AVG, AGG_TOPK, AGG_BOTTOMK) or (flags & Q_PARTIAL and aggr != AGG_NONE):
             return out, aux
         return out
+
+    def query_hist(self, table, fn, start, step, end, window, aggr=AGG_NONE, quantile=None, want_values=True):
+        """filo_query_hist -> values [rows, T, buckets] (NaN buckets = empty histogram)[, quantile [rows, T]]; rows = series or groups."""
+        ti = table.info(); T = num_windows(start, step, end)
+        rows = ti.n_series if aggr == AGG_NONE else ti.n_groups
+        vals = np.zeros((rows, T, ti.hist_buckets), np.float64) if want_values else None
+        qs = np.zeros((rows, T), np.float64) if quantile is not None else None
+        st = Stats()
+        self._check(lib().filo_query_hist(self.h, table.h, fn, start, step, end, window, aggr, float("nan") if quantile is None else float(quantile),
+                                          _p(vals), _p(qs), C.byref(st)))
+        self.last_stats = st.as_dict()
+        if quantile is None: return vals
+        return (vals, qs) if want_values else qs
 
     def host_register(self, arr):
         """filo_host_register over a numpy array's buffer (chunk vectors inside it are then gathered by the GPU directly)."""

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -64,6 +65,9 @@ struct filo_table {
   int64_t* d_item_begin = nullptr;  // [n_items + 1]
   int64_t n_items = 0;
   int seg = 1;
+  // histogram tables (value column = HistogramVector): one bucket scheme for the whole table
+  bool hist = false; int hist_nb = 0;
+  std::vector<double> hist_tops; double* d_hist_tops = nullptr;
 };
 
 static thread_local std::string tl_err;
@@ -123,7 +127,7 @@ void filo_table_free(filo_ctx* ctx, filo_table* t) {
   if (!t) return;
   if (ctx) cudaSetDevice(ctx->device);
   cudaFree(t->d_arena); cudaFree(t->d_rec_off); cudaFree(t->d_order); cudaFree(t->d_group_start);
-  cudaFree(t->d_gis); cudaFree(t->d_item_begin);
+  cudaFree(t->d_gis); cudaFree(t->d_item_begin); cudaFree(t->d_hist_tops);
   delete t;
 }
 
@@ -131,7 +135,7 @@ int32_t filo_table_get_info(const filo_table* t, filo_table_info* o) {
   if (!t || !o) return FILO_ERR_INVALID_ARG;
   o->n_series = t->n_series; o->n_chunks = t->n_chunks; o->n_samples = t->n_samples; o->arena_bytes = t->arena_bytes;
   o->algorithmic_bytes = t->algorithmic_bytes; o->max_rows_per_series = t->max_rows; o->max_chunks_per_series = t->max_chunks;
-  o->n_groups = t->n_groups; o->schema_flags = t->schema_flags;
+  o->n_groups = t->n_groups; o->schema_flags = t->schema_flags; o->hist_buckets = t->hist ? t->hist_nb : 0; o->reserved = 0;
   return FILO_OK;
 }
 
@@ -221,7 +225,7 @@ int32_t filo_internal_fail(filo_ctx* ctx, int32_t code, const char* msg) { retur
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
 
-struct VecInfo { const uint8_t* p; int32_t total; int32_t len; bool drop_patch; bool drop; };
+struct VecInfo { const uint8_t* p; int32_t total; int32_t len; bool drop_patch; bool drop; bool hist = false; };
 
 inline int32_t rd32(const uint8_t* p) { int32_t v; std::memcpy(&v, p, 4); return v; }
 inline int64_t rd64(const uint8_t* p) { int64_t v; std::memcpy(&v, p, 8); return v; }
@@ -259,6 +263,11 @@ int classify_val(const uint8_t* v, VecInfo& o) {
     o.len = rd32(v + XOR_OFF_N);
     int ng = (uint16_t)(v[12] | (v[13] << 8)), po = (uint16_t)(v[14] | (v[15] << 8));
     if (o.len <= 0 || ng != (o.len - 1 + 7) / 8 || po < 16 + 2 * ng || (po & 7) || po + 8 > o.total) return FILO_ERR_CORRUPT_VECTOR;
+  } else if (wire == WIRE_H_SECTDELTA || wire == WIRE_H_SIMPLE) {          // HistogramVector header, HistogramVector.scala:239-244
+    if (masked || o.total < 13) return FILO_ERR_CORRUPT_VECTOR;
+    o.len = (uint16_t)(v[6] | (v[7] << 8)); o.drop = false; o.hist = true;
+    const int fmt = v[8], defBytes = (uint16_t)(v[9] | (v[10] << 8));
+    if (o.len > 0 && (!(fmt == 3 || fmt == 4 || fmt == 5) || 11 + defBytes > o.total)) return fmt == 9 || fmt == 0x10 ? FILO_ERR_UNSUPPORTED : FILO_ERR_CORRUPT_VECTOR;
   } else return FILO_ERR_CORRUPT_VECTOR;
   return (o.total >= 8 && o.len >= 0) ? 0 : FILO_ERR_CORRUPT_VECTOR;
 }
@@ -266,7 +275,13 @@ int classify_val(const uint8_t* v, VecInfo& o) {
 struct SeriesPlan { uint32_t rec_bytes; uint32_t n_chunks; uint32_t n_rows; uint32_t flags; };
 
 struct LoadIn { int64_t n_series; const int32_t* n_chunks; const uint64_t* addrs; const int64_t* chunk_base; int32_t ts_col, val_col; };
-struct PlanTotals { int64_t chunks = 0, samples = 0, alg = 0; int32_t maxrows = 0, maxch = 0; uint32_t max_rec = 0, f_or = 0, f_and = ~0u; };
+struct PlanTotals { int64_t chunks = 0, samples = 0, alg = 0; int32_t maxrows = 0, maxch = 0; uint32_t max_rec = 0, f_or = 0, f_and = ~0u;
+                    const uint8_t* hist_def = nullptr; bool any_scalar = false, hist_mismatch = false; };
+// same bucket scheme: format code, definition length and bytes of two HistogramVector headers (HistogramVector.matchBucketDef, :262-268)
+inline bool same_hist_def(const uint8_t* a, const uint8_t* b) {
+  const int da = (uint16_t)(a[9] | (a[10] << 8)), db = (uint16_t)(b[9] | (b[10] << 8));
+  return a[8] == b[8] && da == db && std::memcmp(a + 11, b + 11, (size_t)da) == 0;
+}
 
 // pass 1 of the loader for one series: validate the vectors, size the record.  Returns 0 or FILO_ERR_*.
 inline int plan_series(const LoadIn& in, int64_t i, SeriesPlan& out, PlanTotals& tot) {
@@ -290,6 +305,8 @@ inline int plan_series(const LoadIn& in, int64_t i, SeriesPlan& out, PlanTotals&
     if (twire != WIRE_DDV_CONST) flags &= ~REC_ALL_TS_CONST;
     if (vv.drop) flags |= REC_ANY_DROP;
     if (vwire != WIRE_RAW64) flags |= REC_ANY_DECODE;
+    if (vv.hist) { flags |= REC_HIST; if (!tot.hist_def) tot.hist_def = vv.p; else if (vv.len > 0 && !same_hist_def(tot.hist_def, vv.p)) tot.hist_mismatch = true; }
+    else tot.any_scalar = true;
     tot.samples += numRows; tot.alg += 28 + 16 + tv.total + vv.total;
   }
   out = SeriesPlan{align_up(bytes, 16), nch, rows, flags};
@@ -300,6 +317,31 @@ inline int plan_series(const LoadIn& in, int64_t i, SeriesPlan& out, PlanTotals&
 inline void merge_totals(PlanTotals& a, const PlanTotals& b) {
   a.chunks += b.chunks; a.samples += b.samples; a.alg += b.alg; a.maxrows = std::max(a.maxrows, b.maxrows); a.maxch = std::max(a.maxch, b.maxch);
   a.max_rec = std::max(a.max_rec, b.max_rec); a.f_or |= b.f_or; a.f_and &= b.f_and;
+  if (!a.hist_def) a.hist_def = b.hist_def; else if (b.hist_def && !same_hist_def(a.hist_def, b.hist_def)) a.hist_mismatch = true;
+  a.any_scalar |= b.any_scalar; a.hist_mismatch |= b.hist_mismatch;
+}
+// host NibblePack.unpackDoubleXOR (NibblePack.scala:374-447) for the custom bucket tops of a table (a few dozen values)
+inline bool host_unpack_double_xor(const uint8_t* buf, int cap, double* out, int n) {
+  auto rdl = [&](int idx) { uint64_t w = 0; for (int i = 0; i < 8 && idx + i < cap; ++i) w |= (uint64_t)buf[idx + i] << (8 * i); return w; };
+  if (cap < 8 || n <= 0) return false;
+  uint64_t last = rdl(0); std::memcpy(&out[0], &last, 8);
+  int pos = 8, o = 1;
+  while (o < n && pos < cap) {
+    const uint32_t mask = buf[pos]; uint64_t d[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int used = 1;
+    if (mask) {
+      const int hdr = buf[pos + 1], numBits = ((hdr >> 4) + 1) * 4, tz = (hdr & 15) * 4;
+      used = 2 + (numBits * __builtin_popcount(mask) + 7) / 8;
+      int bit = 0;
+      for (int i = 0; i < 8; ++i) if (mask & (1u << i)) {
+        uint64_t v = 0;
+        for (int k = 0; k < numBits; ++k) { const int bb = bit + k; const int by = pos + 2 + (bb >> 3); if (by < cap && ((buf[by] >> (bb & 7)) & 1)) v |= 1ull << k; }
+        d[i] = v << tz; bit += numBits;
+      }
+    }
+    for (int i = 0; i < 8 && o < n; ++i, ++o) { last ^= d[i]; std::memcpy(&out[o], &last, 8); }
+    pos += used;
+  }
+  return o == n;
 }
 // pass 2 of the loader for one series: header, chunk entries, vectors copied verbatim
 inline void fill_record(const LoadIn& in, int64_t i, const SeriesPlan& p, uint8_t* rec) {
@@ -374,6 +416,8 @@ extern "C" int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32
   const int64_t arena_bytes = rec_off[n_series];
   if (ctx->cfg.max_data_per_shard_query > 0 && tot.alg > ctx->cfg.max_data_per_shard_query)
     return fail(ctx, FILO_ERR_QUERY_LIMIT, "raw data bytes scanned exceeds max-data-per-shard-query");
+  if (tot.hist_def && tot.any_scalar) return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram and scalar value vectors in one table");
+  if (tot.hist_mismatch) return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram bucket schemes differ inside the table (unsupported on the device path)");
   // ---- pass 2: fill pinned slabs, copy
   auto* t = new filo_table();
   uint8_t* d_arena = nullptr; int64_t* d_rec_off = nullptr;
@@ -406,6 +450,22 @@ extern "C" int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32
   for (int b = 0; b < 2; ++b) { cudaFreeHost(slab[b]); cudaEventDestroy(ev[b]); }
   filo_internal_set_arena(t, d_arena, d_rec_off, n_series, tot.chunks, tot.samples, arena_bytes + (n_series + 1) * 8, tot.alg, tot.maxrows, tot.maxch, schema_flags);
   filo_internal_set_layout(t, tot.max_rec, n_series > 0 && !(tot.f_and & REC_ALL_TS_CONST), (tot.f_or & REC_ANY_DROP) != 0);
+  if (tot.hist_def) {                                  // histogram table: one bucket scheme, tops kept for histogram_quantile
+    const uint8_t* hd = tot.hist_def;
+    const int fmt = hd[8], nb = (uint16_t)(hd[11] | (hd[12] << 8));
+    t->hist = true; t->hist_nb = nb; t->hist_tops.assign((size_t)nb, 0.0);
+    bool ok = nb > 0 && nb <= 64;
+    if (ok && (fmt == 3 || fmt == 4)) {                // GeometricBuckets.bucketTop, Histogram.scala:606
+      double first, mult; std::memcpy(&first, hd + 13, 8); std::memcpy(&mult, hd + 21, 8);
+      for (int i = 0; i < nb; ++i) t->hist_tops[(size_t)i] = first * std::pow(mult, (double)i) + (fmt == 4 ? -1.0 : 0.0);
+    } else if (ok && fmt == 5) {                        // CustomBuckets: u16 n + NibblePack.packDoubles(les), Histogram.scala:878-884
+      const int defBytes = (uint16_t)(hd[9] | (hd[10] << 8));
+      ok = host_unpack_double_xor(hd + 13, defBytes - 2, t->hist_tops.data(), nb);
+    } else ok = false;
+    if (!ok) { filo_table_free(ctx, t); return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram bucket scheme not supported on the device path (1..64 geometric or custom buckets)"); }
+    CUDA_TRY(ctx, cudaMalloc(&t->d_hist_tops, (size_t)nb * 8));
+    CUDA_TRY(ctx, cudaMemcpy(t->d_hist_tops, t->hist_tops.data(), (size_t)nb * 8, cudaMemcpyHostToDevice));
+  }
   // groups
   int32_t* d_gid = nullptr;
   if (group_ids && n_series > 0) {
@@ -495,6 +555,7 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
                                  filo_stats* stats, AsyncSink* sink) {
   if (!ctx || !t || !d_out_values) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_query: null argument");
   if (fn < FILO_FN_LAST || fn > FILO_FN_TIMESTAMP) return fail(ctx, FILO_ERR_INVALID_ARG, "unknown range function");
+  if (t->hist) return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram table: use filo_query_hist");
   if (agg < FILO_AGG_NONE || agg > FILO_AGG_BOTTOMK) return fail(ctx, FILO_ERR_INVALID_ARG, "unknown aggregation operator");
   // PeriodicSamplesMapper.scala:45-49, 67-68
   if (start > end) return fail(ctx, FILO_ERR_INVALID_ARG, "start should be <= end");
@@ -697,8 +758,9 @@ struct GatherChunk {            // one chunk with rows, in series order
 struct GatherSeries { uint32_t rec_bytes, n_chunks, n_rows, flags; int64_t first_chunk; };
 
 __device__ __forceinline__ void copy_bytes_warp(uint8_t* dst, const uint8_t* src, int n, int lane) {
-  // dst is 8-byte aligned; src usually is at least 4-byte aligned (BinaryVectors are allocated word aligned)
-  if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+  // dst is 8-byte aligned; BinaryVectors are allocated word aligned (32-bit loads measured faster than 64-bit ones over PCIe)
+  const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+  if ((a & 3) == 0) {
     const int nw = n >> 2;
     const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src); uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
     for (int i = lane; i < nw; i += 32) d4[i] = s4[i];
@@ -807,6 +869,7 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
   }
   if (ctx->cfg.max_data_per_shard_query > 0 && tot.alg > ctx->cfg.max_data_per_shard_query)
     return fail(ctx, FILO_ERR_QUERY_LIMIT, "raw data bytes scanned exceeds max-data-per-shard-query");
+  if (tot.hist_def) return fail(ctx, FILO_ERR_UNSUPPORTED, "filo_scan_series: histogram columns go through filo_load_series + filo_query_hist");
   const double t_plan = ms_since(t_begin);
   // ---- batches: consecutive series, <= SLAB bytes of records and a bounded result block
   const size_t SLAB = (size_t)192 << 20;
@@ -947,6 +1010,75 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
   if (timing) fprintf(stderr, "[filo] scan_series: %lld series, %zu batches, total %.1f ms: plan %.1f, fill %.1f, enqueue %.1f, slot waits %.1f\n",
                       (long long)n_series, batches.size(), ms_since(t_begin), t_plan, t_fill, t_enq, t_retire);
   if (stats) *stats = acc;
+  return FILO_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// filo_query_hist: PeriodicSamplesMapper over a histogram column (+ HistSumRowAggregator, + histogram_quantile)
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int32_t filo_query_hist(filo_ctx* ctx, const filo_table* t, int32_t fn, int64_t start, int64_t step, int64_t end, int64_t window,
+                                   int32_t agg, double quantile, double* out_values, double* out_quantile, filo_stats* stats) {
+  if (!ctx || !t || (!out_values && !out_quantile)) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_query_hist: null argument");
+  if (!t->hist) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_query_hist: not a histogram table");
+  if (agg != FILO_AGG_NONE && agg != FILO_AGG_SUM) return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram aggregates: sum only");
+  if (!(fn == FILO_FN_RATE || fn == FILO_FN_INCREASE) || !(t->schema_flags & FILO_SCHEMA_CUMULATIVE))
+    return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram range functions on the device path: rate / increase over cumulative (SectDelta) histograms");
+  if (agg == FILO_AGG_NONE && out_quantile) return fail(ctx, FILO_ERR_INVALID_ARG, "histogram_quantile is applied to the aggregated histogram (aggr SUM)");
+  // PeriodicSamplesMapper.scala:45-49, 67-68
+  if (start > end) return fail(ctx, FILO_ERR_INVALID_ARG, "start should be <= end");
+  if (!(start == end || step > 0)) return fail(ctx, FILO_ERR_INVALID_ARG, "step should be > 0 for range query");
+  if (start < end && step < ctx->cfg.min_step_ms) return fail(ctx, FILO_ERR_BAD_QUERY, "step should be at least min-step");
+  if (window <= 0) return fail(ctx, FILO_ERR_INVALID_ARG, "Need positive window lengths to apply range function");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const int64_t adjustedStep = step > 0 ? step : step + 1;
+  QueryParams q{};
+  q.start = start; q.step = adjustedStep; q.end = end; q.window = window; q.T = filo_num_windows(start, adjustedStep, end);
+  q.fn = fn; q.cumulative = 1; q.inclusive = ctx->cfg.inclusive_range ? 1 : 0;
+  const int nb = t->hist_nb, T = q.T;
+  const bool fused = agg == FILO_AGG_SUM;
+  const size_t smem = hist_smem_bytes(t->max_rows, nb, T, fused);
+  if (smem + 2048 > std::min<size_t>(ctx->max_smem_optin, 227 * 1024))
+    return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram query does not fit the device working set (rows x buckets or windows x buckets too large)");
+  Temp tmp(s);
+  int* d_err = nullptr; unsigned long long* d_counters = nullptr;
+  CUDA_TRY(ctx, tmp.alloc((void**)&d_err, 16)); CUDA_TRY(ctx, tmp.alloc((void**)&d_counters, 16));
+  CUDA_TRY(ctx, cudaMemsetAsync(d_err, 0, 16, s)); CUDA_TRY(ctx, cudaMemsetAsync(d_counters, 0, 16, s));
+  cudaEvent_t e0, e1; CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1));
+  const int64_t work = fused ? t->n_items : t->n_series;
+  ScanLaunch L{t->d_arena, t->d_rec_off, t->n_series, q, nullptr, 0, 0, d_counters, d_err, 1, s};
+  const int ctas_per_sm = (int)std::max<size_t>(1, (size_t)(228 * 1024) / (smem + 2048));
+  L.grid = (int)std::max<int64_t>(1, std::min<int64_t>(work, (int64_t)ctx->sm_count * ctas_per_sm));
+  const int64_t rows = fused ? t->n_groups : t->n_series;
+  double *d_out = nullptr, *d_q = nullptr, *pval = nullptr; uint8_t* pany = nullptr;
+  if (out_values) CUDA_TRY(ctx, tmp.alloc((void**)&d_out, (size_t)rows * T * nb * 8));
+  if (out_quantile) CUDA_TRY(ctx, tmp.alloc((void**)&d_q, (size_t)rows * T * 8));
+  CUDA_TRY(ctx, cudaEventRecord(e0, s));
+  if (fused) {
+    CUDA_TRY(ctx, tmp.alloc((void**)&pval, (size_t)t->n_items * T * nb * 8));
+    CUDA_TRY(ctx, tmp.alloc((void**)&pany, (size_t)t->n_items * T + 16));
+    CUDA_TRY(ctx, launch_hist_scan(L, nb, t->max_rows, t->grouped ? t->d_order : nullptr, t->d_item_begin, t->n_items, 1, nullptr, pval, pany));
+    CUDA_TRY(ctx, launch_hist_merge(pval, pany, t->d_gis, t->n_groups, T, nb, t->d_hist_tops, out_quantile ? quantile : std::nan(""), d_out, d_q, s));
+  } else {
+    CUDA_TRY(ctx, launch_hist_scan(L, nb, t->max_rows, nullptr, nullptr, 0, 0, d_out, nullptr, nullptr));
+  }
+  CUDA_TRY(ctx, cudaEventRecord(e1, s));
+  int herr[4]; unsigned long long hc[2];
+  CUDA_TRY(ctx, cudaMemcpyAsync(herr, d_err, 16, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaMemcpyAsync(hc, d_counters, 16, cudaMemcpyDeviceToHost, s));
+  if (out_values) CUDA_TRY(ctx, cudaMemcpyAsync(out_values, d_out, (size_t)rows * T * nb * 8, cudaMemcpyDeviceToHost, s));
+  if (out_quantile) CUDA_TRY(ctx, cudaMemcpyAsync(out_quantile, d_q, (size_t)rows * T * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (stats) {
+    stats->kernel_ns = (int64_t)((double)ms * 1e6); stats->samples_scanned = (int64_t)hc[0]; stats->bytes_scanned = (int64_t)hc[1];
+    stats->kernel_launches = fused ? 2 : 1; stats->h2d_bytes = 0;
+    stats->d2h_bytes = (int64_t)((out_values ? (size_t)rows * T * nb * 8 : 0) + (out_quantile ? (size_t)rows * T * 8 : 0));
+  }
+  if (herr[0] == 5) return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram series with more chunks / sections / rows in range than the device path holds, at series " +
+                                std::to_string((int64_t)herr[1] | ((int64_t)herr[2] << 31)));
+  if (herr[0]) return report_device_error(ctx, herr, 0);
   return FILO_OK;
 }
 

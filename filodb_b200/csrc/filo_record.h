@@ -22,6 +22,7 @@ enum : uint32_t {
   REC_ALL_TS_CONST = 1u,      // every chunk's timestamp vector is a const DDV (closed-form row search)
   REC_ANY_DROP     = 2u,      // some value vector has the counter drop flag
   REC_ANY_DECODE   = 4u,      // some value vector needs decoding (XOR container / DDV-long)
+  REC_HIST         = 8u,      // the value column holds histogram vectors (HistogramVector.scala)
 };
 
 struct ChunkEntry {
@@ -40,7 +41,9 @@ constexpr int WIRE_DDV        = (0x08 << 8) | 0x08;   // DELTA2 / INT_NOMASK
 constexpr int WIRE_DDV_CONST  = (0x06 << 8) | 0x08;   // DELTA2 / REPEATED
 constexpr int WIRE_MASKED     = (0x00 << 8) | 0x06;   // BINSIMPLE / PRIMITIVE
 constexpr int WIRE_RAW64      = (0x05 << 8) | 0x06;   // BINSIMPLE / PRIMITIVE_NOMASK
-constexpr int WIRE_XOR        = (0x21 << 8) | 0x06;   // BINSIMPLE / XOR_NIBBLE (this repo's container)
+constexpr int WIRE_XOR        = (0x21 << 8) | 0x06;
+constexpr int WIRE_H_SIMPLE   = (0x10 << 8) | 0x09;   // HISTOGRAM / H_SIMPLE   (WireFormat.scala:17,35)
+constexpr int WIRE_H_SECTDELTA = (0x12 << 8) | 0x09;  // HISTOGRAM / H_SECTDELTA (WireFormat.scala:37)   // BINSIMPLE / XOR_NIBBLE (this repo's container)
 
 // XOR container header (oracle/filo_format.hpp documents the same layout):
 //  +0 i32 numBytes  +4 u16 wire  +6 u16 flags(bit15 drop)  +8 i32 n  +12 u16 numGroups  +14 u16 payloadOff

@@ -13,6 +13,11 @@
 //   NibblePack      NibblePack.scala:395-447 (unpack8), 374-384 (unpackDoubleXOR)
 // Compiled with -fmad=false: the JVM never contracts a*b+c, and parity is bit-exact per series.
 #pragma once
+#ifndef FILO_DEV_ERR_TS_WIRE
+#define FILO_DEV_ERR_TS_WIRE 1
+#define FILO_DEV_ERR_VAL_WIRE 2
+#define FILO_DEV_ERR_EMPTY 3
+#endif
 #include <stdint.h>
 #include <cuda_runtime.h>
 #include "filo_record.h"

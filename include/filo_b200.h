@@ -110,6 +110,8 @@ typedef struct {
   int32_t max_chunks_per_series;
   int32_t n_groups;
   int32_t schema_flags;
+  int32_t hist_buckets;               /* > 0: histogram table with this many buckets */
+  int32_t reserved;
 } filo_table_info;
 
 /* Synthetic table spec (bench + tests): the reference's own generator shapes, encoded on the GPU.
@@ -180,6 +182,20 @@ int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t range_fn,
                           int64_t start_ms, int64_t step_ms, int64_t end_ms, int64_t window_ms,
                           int32_t aggr_op, int32_t k, int32_t flags,
                           void* d_out_values, void* d_out_aux, void* cuda_stream, filo_stats* stats);
+/* Histogram value columns (HistogramVector.scala: H_SIMPLE / H_SECTDELTA vectors).  filo_load_series accepts them as the value
+ * column when every series of the table uses ONE bucket scheme (1..64 geometric or custom buckets; otel exponential buckets are
+ * declined with FILO_ERR_UNSUPPORTED); filo_table_info.schema_flags keeps the caller's flags.  filo_query_hist runs
+ *   HistRateFunction / HistIncreaseFunction (RateFunctions.scala:330-418) over cumulative SectDelta histograms with counter
+ *   correction (SectDeltaHistogramReader, HistogramVector.scala:628-738), optionally HistSumRowAggregator
+ *   (aggregator/HistSumRowAggregator.scala) over the table's groups and HistogramQuantileImpl (InstantFunction.scala:362-368).
+ *  aggr NONE: out_values [n_series * T * buckets] (an empty histogram = NaN buckets), out_quantile must be NULL
+ *  aggr SUM : out_values [n_groups * T * buckets] or NULL, out_quantile [n_groups * T] or NULL (quantile in [0,1])
+ * Partial sums of a group are folded in a fixed order and made monotonic once at the end (the reference re-runs
+ * makeMonotonic after every add): identical for monotonic inputs, within 1e-9 relative otherwise. */
+int32_t filo_query_hist(filo_ctx* ctx, const filo_table* t, int32_t range_fn,
+                        int64_t start_ms, int64_t step_ms, int64_t end_ms, int64_t window_ms,
+                        int32_t aggr_op, double quantile, double* out_values, double* out_quantile, filo_stats* stats);
+
 /* Registers a region of host memory that holds chunk vectors (FiloDB's off-heap block memory, BlockManager pages) for direct
  * device access: pinned + mapped once, like the reference maps its blocks once at start-up.  filo_scan_series then lets the
  * GPU gather the vectors of a call straight out of the region (no staging copy on the host) whenever every vector of the
