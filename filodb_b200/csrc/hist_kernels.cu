@@ -153,9 +153,9 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
           const uint8_t* s = hv + 11 + defBytes; int start = 0;
           while (s + 4 <= endp && start < numHist) {
             const int sbytes = (int)(s[0] | (s[1] << 8)), sn = s[2], stype = s[3];
-            if (s + 4 + sbytes > endp || sn == 0) break;
+            if (s + 4 + sbytes > endp || sn == 0 || start >= e.num_rows) break;
             if (nsect >= HIST_MAXSECT) { err = 5; break; }
-            SE[nsect] = HistSect{c, rows + start, sn, stype, (uint32_t)((s + 4) - rec)};
+            SE[nsect] = HistSect{c, rows + start, sn < e.num_rows - start ? sn : e.num_rows - start, stype, (uint32_t)((s + 4) - rec)};   // rows past numRows are not read
             if (stype == 1 && start > 0) d.has_drop = 1;
             ++nsect; ++d.nsect; start += sn; s += 4 + sbytes;
           }
