@@ -467,7 +467,9 @@ def main():
     del out
     torch.cuda.empty_cache()
     if not args.no_e2e:
-        Se = S if args.e2e_series < 0 else min(S, args.e2e_series)
+        # default: all series on one GPU; with several ranks on one host each rank takes a 1/world share (the host gather, the pinned
+        # result buffers and PCIe are shared by the ranks of a box)
+        Se = (S if world == 1 else max(1_000_000, S // world)) if args.e2e_series < 0 else min(S, args.e2e_series)
         os.environ.setdefault("FILO_HOST_THREADS", str(max(4, min(64, (os.cpu_count() or 8) // world))))   # host gather threads per rank
         arena, rec_off = tab.read_arena(0, Se)
         nch, addrs, keep = host_chunk_infos(arena, rec_off, Se)

@@ -1022,8 +1022,8 @@ extern "C" int32_t filo_query_hist(filo_ctx* ctx, const filo_table* t, int32_t f
   if (!ctx || !t || (!out_values && !out_quantile)) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_query_hist: null argument");
   if (!t->hist) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_query_hist: not a histogram table");
   if (agg != FILO_AGG_NONE && agg != FILO_AGG_SUM) return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram aggregates: sum only");
-  if (!(fn == FILO_FN_RATE || fn == FILO_FN_INCREASE) || !(t->schema_flags & FILO_SCHEMA_CUMULATIVE))
-    return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram range functions on the device path: rate / increase over cumulative (SectDelta) histograms");
+  if (!(fn == FILO_FN_RATE || fn == FILO_FN_INCREASE || fn == FILO_FN_SUM_OVER_TIME))
+    return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram range functions on the device path: rate, increase, sum_over_time");
   if (agg == FILO_AGG_NONE && out_quantile) return fail(ctx, FILO_ERR_INVALID_ARG, "histogram_quantile is applied to the aggregated histogram (aggr SUM)");
   // PeriodicSamplesMapper.scala:45-49, 67-68
   if (start > end) return fail(ctx, FILO_ERR_INVALID_ARG, "start should be <= end");
@@ -1035,7 +1035,7 @@ extern "C" int32_t filo_query_hist(filo_ctx* ctx, const filo_table* t, int32_t f
   const int64_t adjustedStep = step > 0 ? step : step + 1;
   QueryParams q{};
   q.start = start; q.step = adjustedStep; q.end = end; q.window = window; q.T = filo_num_windows(start, adjustedStep, end);
-  q.fn = fn; q.cumulative = 1; q.inclusive = ctx->cfg.inclusive_range ? 1 : 0;
+  q.fn = fn; q.cumulative = (t->schema_flags & FILO_SCHEMA_CUMULATIVE) ? 1 : 0; q.inclusive = ctx->cfg.inclusive_range ? 1 : 0;
   const int nb = t->hist_nb, T = q.T;
   const bool fused = agg == FILO_AGG_SUM;
   const size_t smem = hist_smem_bytes(t->max_rows, nb, T, fused);

@@ -22,7 +22,7 @@ constexpr int HIST_MAXSECT = 96;      // sections per series
 
 struct HistWin { int32_t lo_row, hi_row, a, lo_c, hi_c, num_samples; int64_t lo_t, hi_t; };
 struct HistSect { int32_t chunk, start_row /*global row of the section's first histogram*/, n, type; uint32_t first_rec /*byte offset in record*/; };
-struct HistChunkD { int32_t row_base, nrows, nsect, has_drop; int64_t end_time; };
+struct HistChunkD { int32_t row_base, nrows, nsect, has_drop; int64_t end_time; int32_t sect, pad; };
 
 // NibblePack.unpack8 (NibblePack.scala:395-447) over bytes in global memory; returns bytes consumed
 __device__ __forceinline__ uint64_t rd_long(const uint8_t* p, int cap, int index) {
@@ -119,6 +119,9 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
   int64_t winDur = q.inclusive ? q.window : q.window - 1; if (winDur < 0) winDur = 0;
   const int64_t n_work = agg ? n_items : n_series;
   int64_t rows_scanned = 0, bytes_scanned = 0;
+  // sum mode: sum_over_time, and rate / increase on a delta-temporality schema (SumOverTimeChunkedFunctionH,
+  // AggrOverTimeFunctions.scala:587-606; RateOverDeltaChunkedFunctionH, RateFunctions.scala:470-494)
+  const bool sum_mode = q.fn == FN_SUM || !q.cumulative;
 
   for (int64_t it = blockIdx.x; it < n_work; it += gridDim.x) {
     const int64_t pb = agg ? item_begin[it] : it, pe = agg ? item_begin[it + 1] : it + 1;
@@ -147,8 +150,9 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
           const int numHist = (int)(ld32(hv + 4) >> 16) & 0xffff;             // u16 at +6
           const int defBytes = (int)(hv[9] | (hv[10] << 8));
           const int vnb = (int)(hv[11] | (hv[12] << 8));
-          if (wire != WIRE_H_SECTDELTA || vnb != nb || numHist < e.num_rows) { err = 1; break; }
-          HistChunkD d; d.row_base = rows; d.nrows = e.num_rows; d.nsect = 0; d.has_drop = 0; d.end_time = e.end_time;
+          // counter functions need the SectDelta reader (a RowHistogramReader is not a CounterVectorReader, RangeFunction.scala:142)
+          if (!(wire == WIRE_H_SECTDELTA || (wire == WIRE_H_SIMPLE && sum_mode)) || vnb != nb || numHist < e.num_rows) { err = 1; break; }
+          HistChunkD d; d.sect = wire == WIRE_H_SECTDELTA; d.pad = 0; d.row_base = rows; d.nrows = e.num_rows; d.nsect = 0; d.has_drop = 0; d.end_time = e.end_time;
           const uint8_t* endp = hv + (int32_t)ld32(hv) + 4;
           const uint8_t* s = hv + 11 + defBytes; int start = 0;
           while (s + 4 <= endp && start < numHist) {
@@ -187,10 +191,52 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         if (r == S.start_row || r >= S.start_row + S.n) continue;
         const uint8_t* p = rec + S.first_rec;
         for (int k = r - S.start_row; k > 0; --k) p += (int)(p[0] | (p[1] << 8)) + 2;      // SectionReader.skipAhead
-        decode_record(p, nb, cv + (size_t)S.start_row * nb, cv + (size_t)r * nb, bad);
+        decode_record(p, nb, CH[S.chunk].sect ? cv + (size_t)S.start_row * nb : nullptr, cv + (size_t)r * nb, bad);
       }
       if (bad) { if (atomicCAS(&d_err[0], 0, 1) == 0) { d_err[1] = (int)(sid & 0x7fffffff); d_err[2] = (int)(sid >> 31); } }
       __syncthreads();
+      if (sum_mode) {
+        // per-bucket running sums over the rows of each chunk (int64, exact): the reference adds the rows as doubles
+        // (RowHistogramReader.sum, HistogramVector.scala:613-621), which is the same number while the sums stay below 2^53
+        for (int cb = tid; cb < n * nb; cb += HIST_THREADS) {
+          const int c = cb / nb, b = cb - c * nb;
+          const HistChunkD d = CH[c];
+          int64_t run = 0;
+          for (int r = d.row_base; r < d.row_base + d.nrows; ++r) { run += cv[(size_t)r * nb + b]; cv[(size_t)r * nb + b] = run; }
+          if (run >= (1ll << 53) || run < 0) { if (atomicCAS(&d_err[0], 0, 5) == 0) { d_err[1] = (int)(sid & 0x7fffffff); d_err[2] = (int)(sid >> 31); } }
+        }
+        __syncthreads();
+        // thread per window: chunks folded in order, h = sum.copy for the first, h.add(sum) (+ makeMonotonic) afterwards
+        for (int k = tid; k < q.T; k += HIST_THREADS) {
+          const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - winDur;
+          double hv[64]; bool has = false;
+          for (int c = 0; c < n; ++c) {
+            const HistChunkD d = CH[c];
+            if (d.end_time < wStart) continue;
+            if (c > 0 && !(CH[c - 1].end_time < wEnd)) continue;
+            const int64_t* t = tss + d.row_base;
+            int lo = 0, hi = d.nrows;
+            while (lo < hi) { const int m = (lo + hi) >> 1; if (t[m] < wStart) lo = m + 1; else hi = m; }
+            const int s0 = lo;
+            lo = 0; hi = d.nrows;
+            while (lo < hi) { const int m = (lo + hi) >> 1; if (t[m] <= wEnd) lo = m + 1; else hi = m; }
+            const int e0 = lo - 1;
+            if (s0 > e0) continue;
+            const int64_t* ce = cv + (size_t)(d.row_base + e0) * nb; const int64_t* cs = s0 > 0 ? cv + (size_t)(d.row_base + s0 - 1) * nb : nullptr;
+            if (!has) { for (int b = 0; b < nb; ++b) hv[b] = (double)(ce[b] - (cs ? cs[b] : 0)); has = true; }
+            else {
+              for (int b = 0; b < nb; ++b) hv[b] += (double)(ce[b] - (cs ? cs[b] : 0));
+              double mx = 0.0;                                                  // makeMonotonic, Histogram.scala:440-449
+              for (int b = 0; b < nb; ++b) { if (hv[b] < mx || hv[b] != hv[b]) hv[b] = mx; else if (hv[b] > mx) mx = hv[b]; }
+            }
+          }
+          if (has && q.fn == FN_RATE) for (int b = 0; b < nb; ++b) hv[b] = hv[b] / (double)(wEnd - wStart) * 1000.0;   // RateFunctions.scala:481 (raw windowStart)
+          if (!agg) { double* o = out + ((size_t)sid * q.T + k) * nb; for (int b = 0; b < nb; ++b) o[b] = has ? hv[b] : NaNv; }
+          else if (has) { for (int b = 0; b < nb; ++b) acc[(size_t)k * nb + b] += hv[b]; any[k] = 1; }
+        }
+        __syncthreads();
+        continue;
+      }
       // ---- corrections.  Inside a chunk (lazy val corrections, :690-707; correctedValue :730-746): every Drop section starting
       //      at row ci > 0 adds the RAW histogram of row ci-1 to all rows >= ci.  Thread per (chunk, bucket), sequential over rows.
       for (int cb = tid; cb < n * nb; cb += HIST_THREADS) {

@@ -190,8 +190,10 @@ int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t range_fn,
  *   (aggregator/HistSumRowAggregator.scala) over the table's groups and HistogramQuantileImpl (InstantFunction.scala:362-368).
  *  aggr NONE: out_values [n_series * T * buckets] (an empty histogram = NaN buckets), out_quantile must be NULL
  *  aggr SUM : out_values [n_groups * T * buckets] or NULL, out_quantile [n_groups * T] or NULL (quantile in [0,1])
- * Partial sums of a group are folded in a fixed order and made monotonic once at the end (the reference re-runs
- * makeMonotonic after every add): identical for monotonic inputs, within 1e-9 relative otherwise. */
+ * Partial sums of a group are folded in a fixed order and made monotonic once at the end.  The reference re-runs
+ * makeMonotonic after every add, which makes its own result depend on the arrival order of the series whenever a member
+ * histogram is not monotonic over its buckets (extrapolation around a counter reset): such cells agree only approximately;
+ * all other cells agree to 1e-9 relative (tests/test_gpu_parity.py::test_hist_rate_sum_quantile). */
 int32_t filo_query_hist(filo_ctx* ctx, const filo_table* t, int32_t range_fn,
                         int64_t start_ms, int64_t step_ms, int64_t end_ms, int64_t window_ms,
                         int32_t aggr_op, double quantile, double* out_values, double* out_quantile, filo_stats* stats);
