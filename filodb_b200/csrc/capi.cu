@@ -1038,7 +1038,7 @@ extern "C" int32_t filo_query_hist(filo_ctx* ctx, const filo_table* t, int32_t f
   q.fn = fn; q.cumulative = (t->schema_flags & FILO_SCHEMA_CUMULATIVE) ? 1 : 0; q.inclusive = ctx->cfg.inclusive_range ? 1 : 0;
   const int nb = t->hist_nb, T = q.T;
   const bool fused = agg == FILO_AGG_SUM;
-  const size_t smem = hist_smem_bytes(t->max_rows, nb, T, fused);
+  const size_t smem = hist_smem_bytes(t->max_rows, nb, T, fused, t->max_rec_bytes);
   if (smem + 2048 > std::min<size_t>(ctx->max_smem_optin, 227 * 1024))
     return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram query does not fit the device working set (rows x buckets or windows x buckets too large)");
   Temp tmp(s);
@@ -1058,10 +1058,10 @@ extern "C" int32_t filo_query_hist(filo_ctx* ctx, const filo_table* t, int32_t f
   if (fused) {
     CUDA_TRY(ctx, tmp.alloc((void**)&pval, (size_t)t->n_items * T * nb * 8));
     CUDA_TRY(ctx, tmp.alloc((void**)&pany, (size_t)t->n_items * T + 16));
-    CUDA_TRY(ctx, launch_hist_scan(L, nb, t->max_rows, t->grouped ? t->d_order : nullptr, t->d_item_begin, t->n_items, 1, nullptr, pval, pany));
+    CUDA_TRY(ctx, launch_hist_scan(L, nb, t->max_rows, t->max_rec_bytes, t->grouped ? t->d_order : nullptr, t->d_item_begin, t->n_items, 1, nullptr, pval, pany));
     CUDA_TRY(ctx, launch_hist_merge(pval, pany, t->d_gis, t->n_groups, T, nb, t->d_hist_tops, out_quantile ? quantile : std::nan(""), d_out, d_q, s));
   } else {
-    CUDA_TRY(ctx, launch_hist_scan(L, nb, t->max_rows, nullptr, nullptr, 0, 0, d_out, nullptr, nullptr));
+    CUDA_TRY(ctx, launch_hist_scan(L, nb, t->max_rows, t->max_rec_bytes, nullptr, nullptr, 0, 0, d_out, nullptr, nullptr));
   }
   CUDA_TRY(ctx, cudaEventRecord(e1, s));
   int herr[4]; unsigned long long hc[2];

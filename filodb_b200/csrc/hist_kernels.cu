@@ -13,14 +13,16 @@
 // highest sample; then one thread per (window, bucket) evaluates extrapolatedRate.
 #include "kernels.h"
 #include "scan_device.cuh"
+#include "scan_fast.cuh"
 
 namespace filo {
 
-constexpr int HIST_THREADS = 256;
+constexpr int HIST_THREADS = 1024;
 constexpr int HIST_MAXC = 8;          // chunks in range per series
 constexpr int HIST_MAXSECT = 96;      // sections per series
 
-struct HistWin { int32_t lo_row, hi_row, a, lo_c, hi_c, num_samples; int64_t lo_t, hi_t; };
+struct HistWin { int32_t lo_row, hi_row, a, lo_c, hi_c, num_samples; int64_t lo_t, hi_t;
+                 double dTS, thr, half, endpart, sI, ratio0, skipC; };     // window-invariant terms of extrapolatedRate (all buckets share the sample times)
 struct HistSect { int32_t chunk, start_row /*global row of the section's first histogram*/, n, type; uint32_t first_rec /*byte offset in record*/; };
 struct HistChunkD { int32_t row_base, nrows, nsect, has_drop; int64_t end_time; int32_t sect, pad; };
 
@@ -76,8 +78,8 @@ __device__ __forceinline__ int64_t ts_of(const uint8_t* tv, int twire, int r) {
   return (int64_t)ld64(tv + 8) + (int64_t)(int32_t)ld32(tv + 16) * r + (int64_t)int_apply(in, (iw >> 16) & 0x7f, (iw >> 23) & 1, r);
 }
 
-struct HistLayout { uint32_t cv, ts, pt, pd, tot, lastraw, win, acc, any, sect, total; };
-__host__ __device__ inline HistLayout hist_layout(int max_rows, int nb, int T, bool agg) {
+struct HistLayout { uint32_t cv, ts, pt, pd, tot, lastraw, win, acc, any, sect, rec, total; };
+__host__ __device__ inline HistLayout hist_layout(int max_rows, int nb, int T, bool agg, uint32_t max_rec) {
   HistLayout L; uint32_t o = 0;
   L.cv = o; o += (uint32_t)max_rows * nb * 8;
   L.ts = o; o += (uint32_t)max_rows * 8;
@@ -89,18 +91,20 @@ __host__ __device__ inline HistLayout hist_layout(int max_rows, int nb, int T, b
   L.acc = o; if (agg) o += (uint32_t)T * nb * 8;
   L.any = o; if (agg) o += ((uint32_t)T + 7) & ~7u;
   L.sect = o; o += HIST_MAXSECT * (uint32_t)sizeof(HistSect);
+  o = (o + 15) & ~15u;
+  L.rec = o; o += (max_rec + 15) & ~15u;               // the series' record, staged so that parsing and decoding read shared memory
   L.total = (o + 127) & ~127u;
   return L;
 }
 
 // err codes written to d_err[0]: 1 corrupt vector, 5 unsupported shape (too many chunks / sections / rows)
 __global__ void __launch_bounds__(HIST_THREADS)
-hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, int64_t n_series, QueryParams q, int nb, int max_rows,
+hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, int64_t n_series, QueryParams q, int nb, int max_rows, uint32_t max_rec,
                  const int32_t* __restrict__ order, const int64_t* __restrict__ item_begin, int64_t n_items, int agg,
                  double* __restrict__ out /* !agg: [S][T][nb] */, double* __restrict__ pval /* agg: [items][T][nb] */, uint8_t* __restrict__ pany,
                  unsigned long long* d_counters, int* d_err) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const HistLayout L = hist_layout(max_rows, nb, q.T, agg != 0);
+  const HistLayout L = hist_layout(max_rows, nb, q.T, agg != 0, max_rec);
   int64_t* cv = reinterpret_cast<int64_t*>(smem + L.cv);
   int64_t* tss = reinterpret_cast<int64_t*>(smem + L.ts);
   int64_t* PT = reinterpret_cast<int64_t*>(smem + L.pt);
@@ -122,6 +126,7 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
   // sum mode: sum_over_time, and rate / increase on a delta-temporality schema (SumOverTimeChunkedFunctionH,
   // AggrOverTimeFunctions.scala:587-606; RateOverDeltaChunkedFunctionH, RateFunctions.scala:470-494)
   const bool sum_mode = q.fn == FN_SUM || !q.cumulative;
+  const double fdiv = (double)(q.inclusive ? winDur : winDur + 1), frcp = 1.0 / fdiv;       // windowEnd - curWindowStart
 
   for (int64_t it = blockIdx.x; it < n_work; it += gridDim.x) {
     const int64_t pb = agg ? item_begin[it] : it, pe = agg ? item_begin[it + 1] : it + 1;
@@ -129,7 +134,14 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
     __syncthreads();
     for (int64_t pos = pb; pos < pe; ++pos) {
       const int64_t sid = (agg && order) ? (int64_t)order[pos] : pos;
-      const uint8_t* rec = arena + rec_off[sid];
+      const uint8_t* grec = arena + rec_off[sid];
+      {                                                    // stage the record (16-byte aligned, rec_bytes multiple of 16)
+        const uint32_t rb = reinterpret_cast<const RecordHeader*>(grec)->rec_bytes;
+        const uint4* src = reinterpret_cast<const uint4*>(grec); uint4* dst = reinterpret_cast<uint4*>(smem + L.rec);
+        for (uint32_t i = tid; i < (rb >> 4); i += HIST_THREADS) dst[i] = src[i];
+      }
+      __syncthreads();
+      const uint8_t* rec = smem + L.rec;
       const RecordHeader* h = reinterpret_cast<const RecordHeader*>(rec);
       const ChunkEntry* E = reinterpret_cast<const ChunkEntry*>(rec + sizeof(RecordHeader));
       // ---- chunk range + section tables (thread 0; a few dozen sections per series)
@@ -303,6 +315,14 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
             }
           }
         }
+        if (w.hi_t > w.lo_t) {                       // RateFunctions.scala:72-111 with the per-window terms evaluated once
+          const int64_t cws = q.inclusive ? wStart : wStart - 1;
+          const double dTS = (double)(w.lo_t - cws) / 1000.0, dTE = (double)(wEnd - w.hi_t) / 1000.0, sI = (double)(w.hi_t - w.lo_t) / 1000.0;
+          const double avg = sI / ((double)w.num_samples - 1.0), thr = avg * 1.1, half = avg / 2.0;
+          const double endpart = dTE < thr ? dTE : half;
+          const double eTI = (sI + (dTS < thr ? dTS : half)) + endpart;
+          w.dTS = dTS; w.thr = thr; w.half = half; w.endpart = endpart; w.sI = sI; w.ratio0 = eTI / sI; w.skipC = 2.0 * dTS / sI;
+        }
         W[k] = w;
       }
       __syncthreads();
@@ -312,11 +332,18 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         const HistWin w = W[k];
         double r = NaNv; bool has = false;
         if (w.hi_t > w.lo_t) {
-          const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - winDur, cws = q.inclusive ? wStart : wStart - 1;
           const int64_t clo = (PT[(size_t)w.lo_c * nb + b] - PT[(size_t)w.a * nb + b]) + (PD[(size_t)w.lo_c * nb + b] - PD[(size_t)w.a * nb + b]);
           const int64_t chi = (PT[(size_t)w.hi_c * nb + b] - PT[(size_t)w.a * nb + b]) + (PD[(size_t)w.hi_c * nb + b] - PD[(size_t)w.a * nb + b]);
           const double lo = (double)(cv[(size_t)w.lo_row * nb + b] + clo), hi = (double)(cv[(size_t)w.hi_row * nb + b] + chi);
-          r = extrapolated_rate(cws, wEnd, w.num_samples, w.lo_t, lo, w.hi_t, hi, true, q.fn == FN_RATE);
+          const double delta = hi - lo;
+          double ratio = w.ratio0;
+          if (delta > 0 && lo >= 0 && !(lo > delta * w.skipC)) {                  // the zero-point clamp may apply (:84-90)
+            const double dz = w.sI * (lo / delta);
+            const double dts = dz < w.dTS ? dz : w.dTS;
+            ratio = ((w.sI + (dts < w.thr ? dts : w.half)) + w.endpart) / w.sI;
+          }
+          const double scaled = delta * ratio;
+          r = q.fn == FN_RATE ? __dmul_rn(div_invariant(scaled, fdiv, frcp), 1000.0) : scaled;
           has = true;
         }
         if (!agg) out[((size_t)sid * q.T + k) * nb + b] = r;                  // an empty histogram is returned as NaN buckets
@@ -383,13 +410,13 @@ __global__ void hist_merge_kernel(const double* __restrict__ pval, const uint8_t
   if (out_q) out_q[i] = qv;
 }
 
-size_t hist_smem_bytes(int max_rows, int nb, int T, bool agg) { return hist_layout(max_rows, nb, T, agg).total; }
-cudaError_t launch_hist_scan(const ScanLaunch& L, int nb, int max_rows, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg,
+size_t hist_smem_bytes(int max_rows, int nb, int T, bool agg, uint32_t max_rec) { return hist_layout(max_rows, nb, T, agg, max_rec).total; }
+cudaError_t launch_hist_scan(const ScanLaunch& L, int nb, int max_rows, uint32_t max_rec, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg,
                              double* out, double* pval, uint8_t* pany) {
-  const size_t smem = hist_layout(max_rows, nb, L.q.T, agg != 0).total;
+  const size_t smem = hist_layout(max_rows, nb, L.q.T, agg != 0, max_rec).total;
   cudaError_t e = cudaFuncSetAttribute(hist_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  hist_scan_kernel<<<L.grid, HIST_THREADS, smem, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, nb, max_rows, order, item_begin, n_items, agg,
+  hist_scan_kernel<<<L.grid, HIST_THREADS, smem, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, nb, max_rows, max_rec, order, item_begin, n_items, agg,
                                                              out, pval, pany, L.d_counters, L.d_err);
   return cudaGetLastError();
 }

@@ -17,6 +17,7 @@
 #define FILO_DEV_ERR_TS_WIRE 1
 #define FILO_DEV_ERR_VAL_WIRE 2
 #define FILO_DEV_ERR_EMPTY 3
+#define FILO_DEV_ERR_SCRATCH 4
 #endif
 #include <stdint.h>
 #include <cuda_runtime.h>
