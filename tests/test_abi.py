@@ -1,0 +1,60 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads and exports every entry point include/filo_b200.h declares,
+the product refuses to run without a CUDA device (no CPU fallback), and nothing under filodb_b200/ touches the oracle."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "filo_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"^\s*(?:int32_t|int64_t|void|const char\*)\s+(filo_[a-z0-9_]+)\s*\(", src, flags=re.M)))
+
+
+def test_header_declares_the_documented_entry_points():
+    names = _declared_functions()
+    for must in ("filo_ctx_create", "filo_load_series", "filo_query", "filo_query_device", "filo_scan_series", "filo_query_hist",
+                 "filo_present_partials", "filo_host_register", "filo_table_free", "filo_last_error"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from filodb_b200 import build, capi
+    path = build.build(force=False)                      # nvcc cross-compiles sm_100a without a GPU
+    lib = C.CDLL(path)
+    missing = [n for n in _declared_functions() if not hasattr(lib, n)]
+    assert not missing, "declared in include/filo_b200.h but not exported: %s" % missing
+    assert sorted(capi.EXPORTS) == sorted(_declared_functions())      # the ctypes mirror covers the whole header
+
+
+def test_num_windows_matches_periodic_samples_mapper():
+    """Host-only entry point: windows of [start, end] by step (PeriodicSamplesMapper / RvRange semantics)."""
+    from filodb_b200 import capi
+    assert capi.num_windows(0, 15000, 7200000) == 481
+    assert capi.num_windows(100, 47000, 100 + 47000 * 3 + 46999) == 4
+    assert capi.num_windows(5, 1, 5) == 1
+    assert capi.num_windows(5, 0, 5) == 1                 # instant query: step 0 is adjusted to 1
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from filodb_b200 import capi
+    with pytest.raises(capi.FiloError):
+        capi.Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "filodb_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|#include\s+\"[./]*oracle/|libfilo_oracle", txt, flags=re.M):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, "product files reference the oracle: %s" % bad
