@@ -58,3 +58,23 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|#include\s+\"[./]*oracle/|libfilo_oracle", txt, flags=re.M):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, "product files reference the oracle: %s" % bad
+
+
+def test_cpp_operator_mirror_compiles_and_keeps_reference_requirements(tmp_path):
+    """include/filo_b200.hpp (PeriodicSamplesMapper / AggregateMapReduce / FusedGpuExec over the C-ABI) builds as C++17, its
+    constructors reject what the Scala `require`s reject (PeriodicSamplesMapper.scala:45-49), and without a CUDA device the
+    executor throws instead of falling back."""
+    import subprocess
+    from filodb_b200 import build
+    lib = build.build(force=False)
+    exe = str(tmp_path / "mirror")
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "operator_mirror_requires.cpp"), "-o", exe,
+                    "-L", os.path.dirname(lib), "-lfilo_b200", "-Wl,-rpath," + os.path.dirname(lib)], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "start 100 should be <= end 50" in out
+    assert "step should be > 0" in out
+    assert "Need positive window lengths" in out
+    import torch
+    if not torch.cuda.is_available():
+        assert "QueryError -2" in out and "ok=4" in out
