@@ -555,3 +555,24 @@ def test_aggregators_vs_transpose_and_fold(oracle):
             assert got == sorted(got, reverse=not rev)
             for v, i in zip(vals[0, t], ids[0, t]):
                 if i >= 0: assert per[i, t] == v
+
+
+def test_aggregators_literal_known_answers(oracle):
+    # AggrOverRangeVectorsSpec.scala:421-470 ("should return NaN when all values are NaN for a timestamp"): literal expectations
+    o = oracle
+    ts = np.array([1000, 2000], np.int64)
+    st = o.Store()
+    for v in (5.6, 4.4, 5.4):
+        st.add_series_rows(ts, np.array([NaN, v]), [2], val_mode=0)
+    g = np.zeros(3, np.int32)
+    q = lambda aggr, **kw: st.query(o.FN_LAST, 1000, 1000, 2000, 500, aggr=aggr, group_ids=g, n_groups=1, **kw)
+    s = q(o.AGG_SUM);   assert math.isnan(s[0, 0]) and s[0, 1] == 15.4
+    m = q(o.AGG_MIN);   assert math.isnan(m[0, 0]) and m[0, 1] == 4.4
+    x = q(o.AGG_MAX);   assert math.isnan(x[0, 0]) and x[0, 1] == 5.6
+    c = q(o.AGG_COUNT); assert math.isnan(c[0, 0]) and c[0, 1] == 3.0
+    a, n = q(o.AGG_AVG); assert math.isnan(a[0, 0]) and abs(a[0, 1] - 5.133333333333333) < 1e-9 and n[0, 1] == 3   # the spec compares with |d| < error
+    assert a[0, 1] == ((5.6 * 1 + 4.4 * 1) / 2 * 2 + 5.4 * 1) / 3                     # AvgRowAggregator.scala:38-46 running mean, exact
+    vals, ids = q(o.AGG_BOTTOMK, k=2)
+    assert all(i < 0 for i in ids[0, 0]) and sorted(v for v, i in zip(vals[0, 1], ids[0, 1]) if i >= 0) == [4.4, 5.4]
+    vals, ids = q(o.AGG_TOPK, k=2)
+    assert all(i < 0 for i in ids[0, 0]) and sorted(v for v, i in zip(vals[0, 1], ids[0, 1]) if i >= 0) == [5.4, 5.6]
