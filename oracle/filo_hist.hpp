@@ -2,7 +2,8 @@
 // Histogram buckets + BinaryHistogram blobs, section-based HistogramVectors (simple and SectDelta), their readers with
 // counter correction, the histogram range functions, HistSum row aggregation and histogram_quantile.
 // Every function cites the reference file:line it restates (paths under core/src/main/scala/filodb.memory/format/ and
-// query/src/main/scala/filodb/query/exec/).  Otel exponential buckets are not restated (rejected as unsupported).
+// query/src/main/scala/filodb/query/exec/).  Otel exponential buckets (Base2ExpHistogramBuckets, ExpHistogramVector.scala) are restated
+// for the value/bucket arithmetic, the row vector and sum(); the XOR (double-valued) blob formats are not.
 #pragma once
 #include "filo_format.hpp"
 #include "filo_query.hpp"
@@ -14,30 +15,85 @@ namespace hist {
 // BinaryHistogram format codes, vectors/HistogramVector.scala:136-143
 enum : uint8_t { FMT_NULL = 0x00, FMT_GEO_DELTA = 0x03, FMT_GEO1_DELTA = 0x04, FMT_CUSTOM_DELTA = 0x05, FMT_OTEL_DELTA = 0x09,
                  FMT_GEO_XOR = 0x08, FMT_CUSTOM_XOR = 0x0a, FMT_OTEL_XOR = 0x10 };
-constexpr int WIRE_H_SIMPLE = (0x10 << 8) | 0x09, WIRE_H_SECTDELTA = (0x12 << 8) | 0x09;     // WireFormat.scala:17,35-37
+constexpr int WIRE_H_SIMPLE = (0x10 << 8) | 0x09, WIRE_H_SECTDELTA = (0x12 << 8) | 0x09, WIRE_H_EXP_SIMPLE = (0x13 << 8) | 0x09;     // WireFormat.scala:17,35-38
 constexpr int OffsetNumHistograms = 6, OffsetFormatCode = 8, OffsetBucketDefSize = 9, OffsetBucketDef = 11;   // HistogramVector.scala:239-244
 
 // ---------------------------------------------------------------------------------------------------------------------
 // HistogramBuckets: GeometricBuckets (Histogram.scala:601-626), CustomBuckets (:874-899)
 // ---------------------------------------------------------------------------------------------------------------------
 struct Buckets {
-  enum Kind { EMPTY = 0, GEOMETRIC = 1, CUSTOM = 2 } kind = EMPTY;
+  enum Kind { EMPTY = 0, GEOMETRIC = 1, CUSTOM = 2, EXP = 3 } kind = EMPTY;
   double first = 0, mult = 0; bool minusOne = false; int n = 0;
   std::vector<double> les;
+  int scale = 0, startIdx = 0;            // EXP: Base2ExpHistogramBuckets(scale, startIndexPositiveBuckets, numPositiveBuckets = n - 1)
+  static constexpr int maxPositiveBuckets = 180, maxAbsScale = 20;          // Histogram.scala:639,645
+  // Base2ExpHistogramBuckets.base / logBase, Histogram.scala:647-658 (tables of Math.pow(2, Math.pow(2, -scale)) and its Math.log)
+  static double expBase(int sc) {
+    if (sc < -maxAbsScale || sc > maxAbsScale) throw std::invalid_argument("requirement failed: Invalid scale");
+    return std::pow(2.0, std::pow(2.0, (double)-sc));
+  }
+  static double expLogBase(int sc) { return std::log(expBase(sc)); }
   int numBuckets() const { return n; }
+  int numPositive() const { return n - 1; }
   double bucketTop(int no) const {
     if (kind == CUSTOM) return les[(size_t)no];
+    if (kind == EXP) {                                                       // Histogram.scala:716-727
+      if (no == 0) return 0.0;
+      const int index = startIdx + no - 1;
+      return std::exp((double)(index + 1) * expLogBase(scale));
+    }
     return (first * std::pow(mult, (double)no)) + (minusOne ? -1.0 : 0.0);     // Histogram.scala:606
+  }
+  double startBucketTop() const { return bucketTop(1); }                     // :695-696
+  double endBucketTop() const { return bucketTop(n - 1); }
+  int bucketIndexToArrayIndex(int index) const { return index - startIdx + 1; }   // :803
+  bool canAccommodate(const Buckets& o) const { return endBucketTop() >= o.endBucketTop() && startBucketTop() <= o.startBucketTop(); }   // :767-770
+  // Base2ExpHistogramBuckets.add, :772-795: the scheme that covers both ranges, scale reduced until it fits maxPosBuckets
+  Buckets expAdd(const Buckets& o, int maxPosBuckets = maxPositiveBuckets) const {
+    if (canAccommodate(o)) return *this;
+    const double minTop = std::min(startBucketTop(), o.startBucketTop()), maxTop = std::max(endBucketTop(), o.endBucketTop());
+    int newScale = std::min(scale, o.scale);
+    double newBase = std::max(expBase(scale), expBase(o.scale));
+    auto toInt = [](double d) { return std::isnan(d) ? 0 : d >= 2147483647.0 ? INT32_MAX : d <= -2147483648.0 ? INT32_MIN : (int)d; };   // Double.toInt
+    int idxEnd = toInt(std::ceil(std::log(maxTop) / std::log(newBase))) - 1;
+    int idxStart = toInt(std::floor(std::log(minTop) / std::log(newBase))) - 1;
+    while (idxEnd - idxStart + 1 > maxPosBuckets) {
+      newScale -= 1;
+      newBase = expBase(newScale);
+      idxEnd = toInt(std::ceil(std::log(maxTop) / std::log(newBase))) - 1;
+      idxStart = toInt(std::floor(std::log(minTop) / std::log(newBase))) - 1;
+    }
+    return exponential(newScale, idxStart, idxEnd - idxStart + 1);
+  }
+  // addValues, :810-866: fold a histogram of a finer (or equal) scheme into values laid out for this scheme
+  template <class H> void expAddValues(std::vector<double>& ourValues, const Buckets& otherBuckets, const H& other) const {
+    if ((int)ourValues.size() != n || other.numBuckets() != otherBuckets.n || !canAccommodate(otherBuckets)) throw std::invalid_argument("requirement failed");
+    const int scaleIncrease = otherBuckets.scale - scale;
+    const int fac = (int)std::pow(2.0, (double)scaleIncrease);
+    ourValues[0] += other.bucketValue(0);
+    for (int ourBucketIndex = startIdx; ourBucketIndex < startIdx + numPositive(); ++ourBucketIndex) {
+      const int ourPlus1 = ourBucketIndex + 1;
+      const int otherPlus1 = (int)((int64_t)ourPlus1 * fac);               // Int multiply (wraps like the JVM's)
+      const int ourArrayIndex = bucketIndexToArrayIndex(ourPlus1 - 1);
+      const int otherArrayIndex = otherBuckets.bucketIndexToArrayIndex(otherPlus1 - 1);
+      if (otherArrayIndex > 0 && otherArrayIndex < otherBuckets.n) ourValues[(size_t)ourArrayIndex] += other.bucketValue(otherArrayIndex);
+      else if (otherArrayIndex >= otherBuckets.n) {
+        if (ourArrayIndex == 0) throw std::invalid_argument("requirement failed: double counting zero bucket");
+        ourValues[(size_t)ourArrayIndex] += other.bucketValue(otherBuckets.n - 1);
+      }
+    }
   }
   bool operator==(const Buckets& o) const {
     if (kind != o.kind) return false;
     if (kind == GEOMETRIC) return first == o.first && mult == o.mult && n == o.n && minusOne == o.minusOne;
     if (kind == CUSTOM) return les == o.les;
+    if (kind == EXP) return scale == o.scale && startIdx == o.startIdx && n == o.n;
     return true;
   }
   bool operator!=(const Buckets& o) const { return !(*this == o); }
   // similarForMath, Histogram.scala:620-625, 893-898: equal, or one geometric and one custom with the same tops
   bool similarForMath(const Buckets& o) const {
+    if (kind == EXP || o.kind == EXP) return kind == o.kind && *this == o;   // Histogram.scala:758-765
     if (kind != o.kind && kind != EMPTY && o.kind != EMPTY) {
       if (n != o.n) return false;
       for (int i = 0; i < n; ++i) if (bucketTop(i) != o.bucketTop(i)) return false;
@@ -45,7 +101,7 @@ struct Buckets {
     }
     return *this == o;
   }
-  uint8_t deltaFormat() const { return kind == GEOMETRIC ? (minusOne ? FMT_GEO1_DELTA : FMT_GEO_DELTA) : kind == CUSTOM ? FMT_CUSTOM_DELTA : FMT_NULL; }
+  uint8_t deltaFormat() const { return kind == GEOMETRIC ? (minusOne ? FMT_GEO1_DELTA : FMT_GEO_DELTA) : kind == CUSTOM ? FMT_CUSTOM_DELTA : kind == EXP ? FMT_OTEL_DELTA : FMT_NULL; }   // HistogramVector.scala:192-198
   // serialize at pos; returns the position after the definition.  Geometric: Histogram.scala:609-617; Custom: :878-884
   int serialize(std::vector<uint8_t>& buf, int pos) const {
     if (kind == GEOMETRIC) {
@@ -62,6 +118,17 @@ struct Buckets {
       setShort(&buf[(size_t)pos], (int16_t)(finalPos - pos - 2));
       return finalPos;
     }
+    if (kind == EXP) {                                                       // Histogram.scala:729-752
+      if ((int)buf.size() < pos + 18) buf.resize((size_t)pos + 18);
+      setShort(&buf[(size_t)pos], (int16_t)(2 + 2 + 4 + 2 + 4 + 2));
+      setShort(&buf[(size_t)pos + 2], (int16_t)n);
+      setShort(&buf[(size_t)pos + 4], (int16_t)scale);
+      setInt(&buf[(size_t)pos + 6], startIdx);
+      setShort(&buf[(size_t)pos + 10], (int16_t)numPositive());
+      setInt(&buf[(size_t)pos + 12], 0);                                     // startIndexNegativeBuckets
+      setShort(&buf[(size_t)pos + 16], 0);                                   // numNegativeBuckets
+      return pos + 18;
+    }
     throw std::invalid_argument("serialize: empty buckets");
   }
   // HistogramBuckets.apply(acc, bucketsDef, formatCode), Histogram.scala:541-547: `def` points at the u16 length prefix
@@ -75,12 +142,17 @@ struct Buckets {
       b.les.assign((size_t)b.n, 0.0);
       const int cap = (getShort(def) & 0xffff) - 2;
       if (b.n > 0 && nibble::unpackDoubleXOR(def + 4, cap, b.les.data(), b.n) != nibble::Ok) throw CorruptVector("custom buckets: input too short");
-    } else if (formatCode == FMT_OTEL_DELTA || formatCode == FMT_OTEL_XOR) {
-      throw std::invalid_argument("otel exponential buckets are not restated");
+    } else if (formatCode == FMT_OTEL_DELTA || formatCode == FMT_OTEL_XOR) {                      // :557-565
+      b = exponential(getShort(def + 4), getInt(def + 6), getShort(def + 10));
     }
     return b;
   }
   static Buckets geometric(double first, double mult, int n, bool minusOne = false) { Buckets b; b.kind = GEOMETRIC; b.first = first; b.mult = mult; b.n = n; b.minusOne = minusOne; return b; }
+  static Buckets exponential(int scale, int startIdx, int numPos) {           // constructor requirements, Histogram.scala:688-692
+    if (!(numPos <= maxPositiveBuckets && numPos >= 0)) throw std::invalid_argument("requirement failed: Invalid buckets: numPositiveBuckets");
+    if (scale < -maxAbsScale || scale > maxAbsScale) throw std::invalid_argument("requirement failed: Invalid scale");
+    Buckets b; b.kind = EXP; b.scale = scale; b.startIdx = startIdx; b.n = numPos + 1; return b;
+  }
   static Buckets custom(const double* les, int n) { Buckets b; b.kind = CUSTOM; b.n = n; b.les.assign(les, les + n); return b; }
 };
 
@@ -107,12 +179,33 @@ struct MutHist {
   double bucketValue(int no) const { return values[(size_t)no]; }
   static MutHist emptyNaN(const Buckets& b) { MutHist h; h.buckets = b; h.values.assign((size_t)b.n, NaN); return h; }   // MutableHistogram.empty, :454-455
   static MutHist from(const LongHist& l) { MutHist h; h.buckets = l.buckets; h.values.resize(l.values.size()); for (size_t i = 0; i < l.values.size(); ++i) h.values[i] = (double)l.values[i]; return h; }
-  // addNoCorrection, :347-421 (same-scheme branch and the mismatch branch; otel branch not restated)
+  // addNoCorrection, :367-421 (same-scheme branch, the exponential-scheme branch and the mismatch branch)
   template <class H> bool addNoCorrection(const H& o) {
     if (buckets.similarForMath(o.buckets)) {
       if (numBuckets() > 0 && std::isnan(values[0])) std::fill(values.begin(), values.end(), 0.0);
       for (int b = 0; b < numBuckets(); ++b) values[(size_t)b] += o.bucketValue(b);
       return true;
+    }
+    if (buckets.kind == Buckets::EXP && o.buckets.kind == Buckets::EXP) {    // :376-404
+      if (std::isnan(values[0])) std::fill(values.begin(), values.end(), 0.0);
+      if (buckets.canAccommodate(o.buckets)) {
+        buckets.expAddValues(values, o.buckets, o);
+      } else if (buckets.numPositive() == 0) {                               // we are zero-only: take the other scheme
+        const double zero = values[0];
+        buckets = o.buckets;
+        values.resize((size_t)o.numBuckets());
+        for (int b = 0; b < o.numBuckets(); ++b) values[(size_t)b] = o.bucketValue(b);
+        values[0] += zero;
+      } else if (o.buckets.numPositive() == 0) {
+        values[0] += o.bucketValue(0);
+      } else {
+        const Buckets nb = buckets.expAdd(o.buckets);
+        std::vector<double> nv((size_t)nb.n, 0.0);
+        nb.expAddValues(nv, buckets, *this);
+        nb.expAddValues(nv, o.buckets, o);
+        buckets = nb; values = std::move(nv);
+      }
+      return false;
     }
     for (int b = 0; b < numBuckets(); ++b) values[(size_t)b] = NaN;
     return false;
@@ -127,7 +220,7 @@ struct MutHist {
   }
   double topBucketValue() const { return numBuckets() <= 0 ? NaN : bucketValue(numBuckets() - 1); }  // Histogram.scala:50-51
   int firstBucketGTE(double rank) const { int b = 0; while (bucketValue(b) < rank) ++b; return b; } // :44-48
-  // Histogram.quantile, :65-108 (non-exponential buckets; min = 0, max = +Inf, evenDistribution = false)
+  // Histogram.quantile, :65-108 (min = 0, max = +Inf, evenDistribution = false)
   double quantile(double q) const {
     if (q < 0) return -std::numeric_limits<double>::infinity();
     if (q > 1) return std::numeric_limits<double>::infinity();
@@ -144,7 +237,10 @@ struct MutHist {
     const double count = bucket == 0 ? bucketValue(bucket) : bucketValue(bucket) - bucketValue(bucket - 1);
     rank -= (bucket == 0 ? 0.0 : bucketValue(bucket - 1));
     const double fraction = rank / count;
-    return bucketStart + (bucketEnd - bucketStart) * fraction;
+    if (buckets.kind != Buckets::EXP || bucketStart == 0) return bucketStart + (bucketEnd - bucketStart) * fraction;
+    auto log2j = [](double v) { return std::log(v) / std::log(2.0); };       // :111
+    const double logEnd = log2j(bucketEnd), logStart = log2j(bucketStart);
+    return std::pow(2.0, logStart + (logEnd - logStart) * fraction);
   }
 };
 // `topBucketValue <= 0` with NaN: Scala `NaN <= 0` is false, so a NaN top goes on to firstBucketGTE (NaN comparisons false
@@ -202,16 +298,17 @@ inline LongHist toHistogram(Ptr b) {
 enum AddResponse { Ack = 0, InvalidHistogram = 1, BucketSchemaMismatch = 2, VectorTooSmall = 3 };
 
 struct HistAppender {
-  bool sect; int maxBytes; std::vector<uint8_t> v;
+  bool sect; bool exp = false; int maxBytes; std::vector<uint8_t> v;
   int curSection = -1, bytesLeft = 0;                     // SectionWriter state (offsets into v)
   // DeltaSectDiffPackSink state, NibblePack.scala:296-345
   bool sinkInit = false; std::vector<int64_t> originalDeltas, lastHistDeltas;
-  HistAppender(bool sectDelta, int maxBytes_) : sect(sectDelta), maxBytes(maxBytes_), v((size_t)maxBytes_, 0) {
-    setShort(&v[4], (int16_t)(sect ? WIRE_H_SECTDELTA : WIRE_H_SIMPLE));
+  // expVector: AppendableExpHistogramVector (ExpHistogramVector.scala:37-121): every record is a whole BinaryHistogram blob
+  HistAppender(bool sectDelta, int maxBytes_, bool expVector = false) : sect(sectDelta && !expVector), exp(expVector), maxBytes(maxBytes_), v((size_t)maxBytes_, 0) {
+    setShort(&v[4], (int16_t)(exp ? WIRE_H_EXP_SIMPLE : sect ? WIRE_H_SECTDELTA : WIRE_H_SIMPLE));
     setShort(&v[OffsetNumHistograms], 0);
     setInt(&v[0], OffsetBucketDef + 2);                  // reset(): setNumBytes(OffsetNumBuckets + 2), :426-429
   }
-  int maxElementsPerSection() const { return sect ? 16 : 64; }
+  int maxElementsPerSection() const { return sect ? 16 : 64; }             // :340, :497; ExpHistogramVector.scala:51
   int length() const { return getShort(&v[OffsetNumHistograms]) & 0xffff; }
   int secNumBytes(int s) const { return getShort(&v[(size_t)s]) & 0xffff; }
   int secNumElems(int s) const { return v[(size_t)s + 2]; }
@@ -245,6 +342,12 @@ struct HistAppender {
     if (bin::bucketDefNumBytes(buf) > bin::totalLength(buf)) return InvalidHistogram;
     const int numItems = length();
     const int defBytes = bin::bucketDefNumBytes(buf);
+    if (exp) {                                                              // ExpHistogramVector.scala:73-97
+      if (numItems == 0) { const int firstSect = OffsetNumHistograms + 2; secInit(firstSect, 0); curSection = firstSect; bytesLeft = (maxBytes - firstSect) - 4; }
+      const AddResponse r = appendBlob(buf, bin::totalLength(buf));
+      if (r == Ack) { setInt(&v[0], maxBytes - bytesLeft - 4); setShort(&v[OffsetNumHistograms], (int16_t)(numItems + 1)); }
+      return r;
+    }
     if (numItems == 0) {
       std::memcpy(&v[OffsetBucketDef], buf + 5, (size_t)defBytes);
       setShort(&v[OffsetBucketDefSize], (int16_t)defBytes);
@@ -293,18 +396,19 @@ struct HistAppender {
 struct HistCorrection { bool some = false; LongHist lastValue, correction; };    // NoCorrection == !some; HistogramCorrection :618
 
 struct HistReader {
-  Ptr vec = nullptr; bool sect = false; int len = 0, nb = 0; Buckets buckets;
+  Ptr vec = nullptr; bool sect = false, exp = false; int len = 0, nb = 0; Buckets buckets;
   bool corrInit = false; std::vector<std::pair<int, LongHist>> corrections;
   explicit HistReader(Ptr v) : vec(v) {
     const int w = vectorType(v);
-    if (w == WIRE_H_SECTDELTA) sect = true; else if (w != WIRE_H_SIMPLE) throw CorruptVector("not a histogram vector");
+    if (w == WIRE_H_SECTDELTA) sect = true; else if (w == WIRE_H_EXP_SIMPLE) exp = true; else if (w != WIRE_H_SIMPLE) throw CorruptVector("not a histogram vector");
     len = getShort(v + OffsetNumHistograms) & 0xffff;
+    if (exp) { buckets = Buckets::exponential(20, 0, 0); nb = 1; return; }   // RowExpHistogramReader.buckets = emptyExpBuckets, ExpHistogramVector.scala:134
     nb = len > 0 ? getShort(v + OffsetBucketDef) & 0xffff : 0;
     buckets = len > 0 ? Buckets::parse(v + OffsetBucketDefSize, (uint8_t)v[OffsetFormatCode]) : Buckets();
   }
   int length() const { return len; }
   Ptr endAddr() const { return vec + getInt(vec) + 4; }
-  Ptr firstSection() const { return vec + OffsetBucketDef + (getShort(vec + OffsetBucketDefSize) & 0xffff); }
+  Ptr firstSection() const { return exp ? vec + OffsetNumHistograms + 2 : vec + OffsetBucketDef + (getShort(vec + OffsetBucketDefSize) & 0xffff); }
   // SectionReader.locate, Section.scala:176-203: section holding elemNo, its starting element, pointer to the record
   void locate(int elemNo, Ptr& sectOut, int& sectStart, Ptr& rec) const {
     if (elemNo < 0 || elemNo >= len) throw std::out_of_range("is out of vector bounds");
@@ -321,6 +425,7 @@ struct HistReader {
   LongHist apply(int index) const {                                          // :601-609 / :646-666
     if (len <= 0) throw std::invalid_argument("EmptyHistogramException");
     Ptr s, rec; int start; locate(index, s, start, rec);
+    if (exp) return bin::toHistogram(rec + 2);                               // ExpHistogramVector.scala:172-189: the record is a blob with its own scheme
     LongHist h; h.buckets = buckets;
     unpackRecord(rec, h.values);
     if (sect && index != start) {

@@ -6,7 +6,8 @@ import numpy as np
 
 from .oracle import lib as _lib
 
-GEOMETRIC, CUSTOM = 1, 2
+GEOMETRIC, CUSTOM, EXP = 1, 2, 3
+FMT_OTEL_DELTA = 9
 ACK, INVALID_HISTOGRAM, BUCKET_SCHEMA_MISMATCH, VECTOR_TOO_SMALL = 0, 1, 2, 3
 FMT_GEO_DELTA, FMT_GEO1_DELTA, FMT_CUSTOM_DELTA = 3, 4, 5
 _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
@@ -38,6 +39,11 @@ def lib():
         L.fo_hist_vec_detect_drop.argtypes = [_vp, _i32, _vp, _vp]
         L.fo_hist_vec_update_correction.argtypes = [_vp, _i32, _vp, _vp, _vp]
         L.fo_hist_vec_corrected.argtypes = [_vp, _i32, _i32, _vp, _vp]
+        L.fo_hist_vec_apply_exp.argtypes = [_vp, _i32, _vp, _vp, _i32]
+        L.fo_hist_vec_sum_exp.argtypes = [_vp, _i32, _i32, _vp, _vp, _i32]
+        L.fo_hist_exp_add_scheme.argtypes = [_vp, _vp, _i32, _vp]
+        L.fo_hist_exp_add_values.argtypes = [_vp, _vp, _vp, _vp]
+        L.fo_hist_exp_add_no_correction.argtypes = [_vp, _vp, _vp, _vp, _vp, _i32]
         L.fo_hstore_new.restype = _vp
         L.fo_hstore_free.restype = None; L.fo_hstore_free.argtypes = [_vp]
         L.fo_hstore_add_series.restype = _i64; L.fo_hstore_add_series.argtypes = [_vp]
@@ -68,6 +74,39 @@ class Buckets:
     @staticmethod
     def geometric(first, mult, n, minus_one=False):
         return Buckets(GEOMETRIC, n, first, mult, minus_one)
+
+    @staticmethod
+    def exponential(scale, start_index, num_positive):
+        """Base2ExpHistogramBuckets(scale, startIndexPositiveBuckets, numPositiveBuckets) (Histogram.scala:684-866)."""
+        return Buckets(EXP, num_positive + 1, float(scale), float(start_index))
+
+    @property
+    def scheme(self):
+        return np.array([int(self.first), int(self.mult), self.n], np.int32)
+
+    def can_accommodate(self, other):
+        out = np.zeros(3, np.int32); a, b = self.scheme, other.scheme
+        r = lib().fo_hist_exp_add_scheme(_p(a), _p(b), 180, _p(out))
+        if r < 0: raise RuntimeError(_err())
+        return bool(r & 1)
+
+    def add(self, other, max_pos=180):
+        out = np.zeros(3, np.int32); a, b = self.scheme, other.scheme
+        if lib().fo_hist_exp_add_scheme(_p(a), _p(b), max_pos, _p(out)) < 0: raise RuntimeError(_err())
+        return Buckets.exponential(int(out[0]), int(out[1]), int(out[2]) - 1)
+
+    def add_values(self, our_values, other, other_values):
+        v = np.array(our_values, np.float64); o = np.ascontiguousarray(other_values, np.float64); a, b = self.scheme, other.scheme
+        if lib().fo_hist_exp_add_values(_p(a), _p(v), _p(b), _p(o)) != 0: raise RuntimeError(_err())
+        return v
+
+    def add_no_correction(self, values, other, other_values):
+        """MutableHistogram(self, values).addNoCorrection(MutableHistogram(other, other_values)) -> (buckets, values)."""
+        sch = self.scheme.copy(); a = np.ascontiguousarray(values, np.float64); o = np.ascontiguousarray(other_values, np.float64)
+        out = np.zeros(512, np.float64); b = other.scheme
+        n = lib().fo_hist_exp_add_no_correction(_p(sch), _p(a), _p(b), _p(o), _p(out), out.size)
+        if n < 0: raise RuntimeError(_err())
+        return Buckets.exponential(int(sch[0]), int(sch[1]), int(sch[2]) - 1), out[:n].copy()
 
     @staticmethod
     def custom(les):
@@ -124,7 +163,8 @@ def make_monotonic(values):
 
 
 class Appender:
-    """AppendableHistogramVector / AppendableSectDeltaHistVector (HistogramVector.scala:326-436, 489-545)."""
+    """AppendableHistogramVector / AppendableSectDeltaHistVector (HistogramVector.scala:326-436, 489-545);
+    sect=2: AppendableExpHistogramVector (ExpHistogramVector.scala:37-121)."""
 
     def __init__(self, sect, max_bytes):
         self.h = lib().fo_hist_appender_new(int(sect), max_bytes)
@@ -168,6 +208,19 @@ class Reader:
         n = lib().fo_hist_vec_section_types(_p(self.vec), _p(out), out.size)
         if n < 0: raise RuntimeError(_err())
         return out[:n].tolist()
+
+    def apply_exp(self, i):
+        """RowExpHistogramReader.apply -> ((scale, start, numPositive), values) (ExpHistogramVector.scala:172-189)."""
+        sch = np.zeros(3, np.int32); out = np.zeros(256, np.int64)
+        n = lib().fo_hist_vec_apply_exp(_p(self.vec), i, _p(sch), _p(out), out.size)
+        if n < 0: raise RuntimeError(_err())
+        return (int(sch[0]), int(sch[1]), int(sch[2]) - 1), out[:n].copy()
+
+    def sum_exp(self, start, end):
+        sch = np.zeros(3, np.int32); out = np.zeros(256, np.float64)
+        n = lib().fo_hist_vec_sum_exp(_p(self.vec), start, end, _p(sch), _p(out), out.size)
+        if n < 0: raise RuntimeError(_err())
+        return (int(sch[0]), int(sch[1]), int(sch[2]) - 1), out[:n].copy()
 
     def sum(self, start, end):
         out = np.zeros(self.num_buckets, np.float64)

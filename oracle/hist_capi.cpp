@@ -11,6 +11,7 @@ thread_local std::string h_err;
 Buckets mkBuckets(int kind, double first, double mult, int minusOne, const double* les, int n) {
   if (kind == 1) return Buckets::geometric(first, mult, n, minusOne != 0);
   if (kind == 2) return Buckets::custom(les, n);
+  if (kind == 3) return Buckets::exponential((int)first, (int)mult, n - 1);      // (scale, startIndexPositiveBuckets, numPositiveBuckets)
   return Buckets();
 }
 struct HChunk { std::vector<uint8_t> ts, hv, info; };
@@ -59,7 +60,7 @@ double fo_hist_quantile(int kind, double first, double mult, int minusOne, const
 void fo_hist_make_monotonic(double* values, int n) { MutHist h; h.buckets.n = n; h.values.assign(values, values + n); h.makeMonotonic(); std::memcpy(values, h.values.data(), (size_t)n * 8); }
 
 // ---- appender
-void* fo_hist_appender_new(int32_t sect, int32_t maxBytes) { return new HistAppender(sect != 0, maxBytes); }
+void* fo_hist_appender_new(int32_t sect, int32_t maxBytes) { return new HistAppender(sect == 1, maxBytes, sect == 2 /* exp vector */); }
 void fo_hist_appender_free(void* a) { delete (HistAppender*)a; }
 int32_t fo_hist_appender_add(void* a, const uint8_t* blob, int32_t len) {
   try { return ((HistAppender*)a)->addData(blob, len); } catch (std::exception& e) { h_err = e.what(); return -2; }
@@ -84,6 +85,54 @@ int32_t fo_hist_vec_section_types(const uint8_t* vec, int32_t* out, int32_t cap)
 int32_t fo_hist_vec_sum(const uint8_t* vec, int32_t start, int32_t end, double* out) {
   try { HistReader r(vec); MutHist s = r.sum(start, end); std::memcpy(out, s.values.data(), s.values.size() * 8); return 0; } catch (std::exception& e) { h_err = e.what(); return -2; }
 }
+// ---- exponential schemes: scheme out = (scale, startIndexPositiveBuckets, numBuckets)
+int32_t fo_hist_vec_apply_exp(const uint8_t* vec, int32_t i, int32_t* scheme, int64_t* out, int32_t cap) {
+  try {
+    HistReader r(vec); LongHist h = r.apply(i);
+    if (h.numBuckets() > cap) return -1;
+    scheme[0] = h.buckets.scale; scheme[1] = h.buckets.startIdx; scheme[2] = h.buckets.n;
+    std::memcpy(out, h.values.data(), h.values.size() * 8); return h.numBuckets();
+  } catch (std::exception& e) { h_err = e.what(); return -2; }
+}
+int32_t fo_hist_vec_sum_exp(const uint8_t* vec, int32_t start, int32_t end, int32_t* scheme, double* out, int32_t cap) {
+  try {
+    HistReader r(vec); MutHist s = r.sum(start, end);
+    if (s.numBuckets() > cap) return -1;
+    scheme[0] = s.buckets.scale; scheme[1] = s.buckets.startIdx; scheme[2] = s.buckets.n;
+    std::memcpy(out, s.values.data(), s.values.size() * 8); return s.numBuckets();
+  } catch (std::exception& e) { h_err = e.what(); return -2; }
+}
+// Base2ExpHistogramBuckets.add + canAccommodate; a/b/out = (scale, start, numBuckets)
+int32_t fo_hist_exp_add_scheme(const int32_t* a, const int32_t* b, int32_t maxPos, int32_t* out) {
+  try {
+    Buckets x = Buckets::exponential(a[0], a[1], a[2] - 1), y = Buckets::exponential(b[0], b[1], b[2] - 1);
+    Buckets r = x.expAdd(y, maxPos);
+    out[0] = r.scale; out[1] = r.startIdx; out[2] = r.n;
+    return (x.canAccommodate(y) ? 1 : 0) | (y.canAccommodate(x) ? 2 : 0);
+  } catch (std::exception& e) { h_err = e.what(); return -2; }
+}
+// addValues: fold `other` (scheme b) into values laid out for scheme a
+int32_t fo_hist_exp_add_values(const int32_t* a, double* ourValues, const int32_t* b, const double* otherValues) {
+  try {
+    Buckets x = Buckets::exponential(a[0], a[1], a[2] - 1);
+    MutHist o; o.buckets = Buckets::exponential(b[0], b[1], b[2] - 1); o.values.assign(otherValues, otherValues + b[2]);
+    std::vector<double> v(ourValues, ourValues + a[2]);
+    x.expAddValues(v, o.buckets, o);
+    std::memcpy(ourValues, v.data(), v.size() * 8); return 0;
+  } catch (std::exception& e) { h_err = e.what(); return -2; }
+}
+// MutableHistogram.addNoCorrection for two exponential histograms; result scheme/values in a / out (cap values)
+int32_t fo_hist_exp_add_no_correction(int32_t* a, const double* aValues, const int32_t* b, const double* bValues, double* out, int32_t cap) {
+  try {
+    MutHist x; x.buckets = Buckets::exponential(a[0], a[1], a[2] - 1); x.values.assign(aValues, aValues + a[2]);
+    MutHist y; y.buckets = Buckets::exponential(b[0], b[1], b[2] - 1); y.values.assign(bValues, bValues + b[2]);
+    x.addNoCorrection(y);
+    if (x.numBuckets() > cap) return -1;
+    a[0] = x.buckets.scale; a[1] = x.buckets.startIdx; a[2] = x.buckets.n;
+    std::memcpy(out, x.values.data(), x.values.size() * 8); return x.numBuckets();
+  } catch (std::exception& e) { h_err = e.what(); return -2; }
+}
+
 // correction API: meta = (has, lastValue[nb], correction[nb]); outputs written in place
 int32_t fo_hist_vec_detect_drop(const uint8_t* vec, int32_t has, const int64_t* last, int64_t* corr_inout) {
   try {

@@ -228,3 +228,147 @@ def test_hist_sum_aggregate_and_quantile():
             assert acc.tolist() == agg[g, k].tolist()
             assert qs[g, k] == b.quantile(agg[g, k], 0.99)
     assert np.isfinite(qs).all()
+
+
+# ------------------------------------------------------------------ otel exponential buckets (Base2ExpHistogramBuckets)
+def test_exp_buckets_serialize_tops_and_index_mapping():
+    """HistogramTest.scala:76-84 (18-byte definition incl. start indexes beyond i16), :497-520 (tops), :545-551."""
+    for b in (H.Buckets.exponential(3, -5, 16), H.Buckets.exponential(3, -9037032, 150)):
+        d = b.serialize()
+        assert len(d) == 18
+        assert H.parse_buckets(d, H.FMT_OTEL_DELTA).tolist() == b.tops().tolist()
+    b1 = H.Buckets.exponential(3, -5, 11)                                         # 0.707 .. 1.68
+    t = b1.tops()
+    assert len(t) == 12 and t[0] == 0.0
+    assert t[1] == pytest.approx(0.7071067811865475, abs=1e-4) and t[-1] == pytest.approx(1.6817928305074294, abs=1e-4)
+    assert t[-5 - -5 + 1 + 4] == 1.0                                              # bucketTop(bucketIndexToArrayIndex(-1)) shouldEqual 1.0
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        scale, start, n = int(rng.integers(-20, 21)), int(rng.integers(-100000, 100001)), int(rng.integers(1, 181))
+        with np.errstate(over="ignore", under="ignore"):
+            base = np.float64(2.0) ** (np.float64(2.0) ** -scale)
+            if not (base ** (start + 1) < 1e10 and base ** (start + n) < 1e10): continue
+        tops = H.Buckets.exponential(scale, start, n).tops()
+        for i in range(1, n + 1):
+            assert tops[i] == pytest.approx(base ** (start + i), abs=1e-6)
+
+
+def test_exp_quantile_known_answers():
+    """HistogramTest.scala:120-131."""
+    b = H.Buckets.exponential(3, -5, 11)
+    v = np.arange(1, 13, dtype=np.float64)
+    assert b.quantile(v, 0.5) == pytest.approx(1.0, abs=1e-5)
+    assert b.quantile(v, 0.75) == pytest.approx(1.2968395546510099, abs=1e-5)
+    assert b.quantile(v, 0.25) == pytest.approx(0.7711054127039704, abs=1e-5)
+    assert b.quantile(v, 0.99) == pytest.approx(1.6643974694230492, abs=1e-5)
+    assert b.quantile(v, 0.01) == 0.0                                             # zero bucket
+    assert b.quantile(v, 0.085) == pytest.approx(0.014142135623730961, abs=1e-5)
+
+
+def test_exp_scheme_add_and_add_values():
+    """HistogramTest.scala:553-606, :623-642."""
+    E = H.Buckets.exponential
+    b1, b2, b3 = E(3, -5, 11), E(2, -2, 6), E(2, -4, 8)
+    assert b2.tops()[-1] == pytest.approx(1.9999999999999998, abs=1e-4)
+    assert not b1.can_accommodate(b2) and not b2.can_accommodate(b1)
+    assert b3.can_accommodate(b1) and b3.can_accommodate(b2)
+    badd = b1.add(b2)
+    assert badd.n == 9 and int(badd.first) == 2
+    assert badd.tops()[1] == pytest.approx(0.5946035575013606, abs=1e-4) and badd.tops()[-1] == pytest.approx(1.9999999999999998, abs=1e-4)
+    assert badd.can_accommodate(b1) and badd.can_accommodate(b2)
+    v = badd.add_values(np.zeros(9), b1, np.arange(12.0))
+    assert v.tolist() == [0.0, 0.0, 1.0, 3.0, 5.0, 7.0, 9.0, 11.0, 11.0]
+    v = badd.add_values(v, b2, np.arange(7.0))
+    assert v.tolist() == [0.0, 0.0, 1.0, 4.0, 7.0, 10.0, 13.0, 16.0, 17.0]
+    b4, b5 = E(5, 15, 36), E(3, 10, 6)
+    assert b4.n == 37 and b4.tops()[1] == pytest.approx(1.414213562373094, abs=1e-4) and b4.tops()[-1] == pytest.approx(3.0183288551868377, abs=1e-4)
+    assert b5.n == 7 and b5.tops()[1] == pytest.approx(2.59367910930202, abs=1e-4) and b5.tops()[-1] == pytest.approx(4.000000000000002, abs=1e-4)
+    badd2 = badd.add(b4).add(b5)
+    v2 = badd2.add_values(np.zeros(badd2.n), badd, v)
+    assert v2.tolist() == [0.0, 0.0, 1.0, 4.0, 7.0, 10.0, 13.0, 16.0, 17.0, 17.0, 17.0, 17.0, 17.0, 17.0]
+    v2 = badd2.add_values(v2, b4, np.arange(37.0))
+    assert v2.tolist() == [0.0, 0.0, 1.0, 4.0, 7.0, 10.0, 14.0, 25.0, 34.0, 42.0, 50.0, 53.0, 53.0, 53.0]
+    v2 = badd2.add_values(v2, b5, [0.0, 10.0, 11, 12, 13, 14, 15])
+    assert v2.tolist() == [0.0, 0.0, 1.0, 4.0, 7.0, 10.0, 14.0, 25.0, 34.0, 42.0, 61.0, 66.0, 68.0, 68.0]
+    # non-overlapping ranges of one scale; scale reduction under a bucket budget
+    nb = E(3, -5, 11).add(E(3, 15, 11))
+    assert nb.n == 32 and int(nb.mult) == -5
+    a1 = E(6, -50, 21).add(E(6, 100, 26), max_pos=128)
+    assert a1.scheme.tolist() == [5, -26, 91]
+    assert a1.can_accommodate(E(6, -50, 21)) and a1.can_accommodate(E(6, 100, 26))
+    a2 = E(6, -50, 21).add(E(6, 100, 26), max_pos=64)
+    assert a2.scheme.tolist() == [4, -14, 47]
+
+
+def test_exp_add_zero_only_histograms():
+    """HistogramTest.scala:608-621."""
+    b1, b2 = H.Buckets.exponential(20, 10, 0), H.Buckets.exponential(3, 10, 6)
+    m2 = [1.0, 10.0, 11, 12, 13, 14, 15]
+    rb, rv = b1.add_no_correction([1.0], b2, m2)
+    assert rb.scheme.tolist() == b2.scheme.tolist() and rv.tolist() == [2.0, 10.0, 11, 12, 13, 14, 15]
+    rb, rv = b2.add_no_correction(m2, b1, [1.0])
+    assert rb.scheme.tolist() == b2.scheme.tolist() and rv.tolist() == [2.0, 10.0, 11, 12, 13, 14, 15]
+
+
+OTEL_EXP = [((3, -3, 1), [0, 3]), ((20, -3, 9), [0, 4, 5, 6, 7, 8, 9, 10, 11, 12]), ((20, -888388, 1), [0, 5])]   # ExpHistogramVectorTest.scala:35-39
+EXP_VECTOR_HEX = ("5C00000009130300540003001800160009100002000300FDFFFFFF01000000000000000200031E00"
+                  "1C000910000A001400FDFFFFFF0900000000000000FE00141111010300111800160009100002001400BC71F2FF0100000000000000020005")
+
+
+def _exp_vector(max_bytes=1024, hists=OTEL_EXP):
+    app = H.Appender(2, max_bytes)
+    for sch, vals in hists:
+        assert app.add(H.Buckets.exponential(*sch).write_delta(vals)) == H.ACK
+    return app
+
+
+def test_exp_vector_bytes_match_the_documented_example():
+    """ExpHistogramVector.scala:19-35 gives the bytes of the vector holding the three histograms of ExpHistogramVectorTest.scala:35-39."""
+    app = _exp_vector()
+    assert app.length == 3
+    assert app.bytes().tobytes().hex().upper() == EXP_VECTOR_HEX
+    rd = H.Reader(app.bytes())
+    assert rd.length == 3
+    for i, (sch, vals) in enumerate(OTEL_EXP):
+        got_s, got_v = rd.apply_exp(i)
+        assert got_s == sch and got_v.tolist() == vals
+
+
+def test_exp_vector_sum_and_capacity():
+    """ExpHistogramVectorTest.scala:201-212 (sum over rows of different schemes), :96-116 (159 histograms of 127 buckets fit a 15 kB
+    vector), :131-145 (575 one-observation histograms fit, the 576th does not), :117-129 (180 positive buckets)."""
+    rd = H.Reader(_exp_vector().bytes())
+    sch, vals = rd.sum_exp(0, 2)
+    assert sch == (3, -8, 9)
+    assert vals.tolist() == [0.0, 0.0, 5.0, 5.0, 5.0, 5.0, 8.0, 8.0, 14.0, 20.0]
+    counts = np.array([0] * 55 + [1] * 7 + [2, 2, 3, 3, 3, 3, 4, 5, 5, 5, 6, 6, 8, 8, 9, 9, 11, 12, 14, 15, 17, 19, 20, 22, 23, 26, 28, 31, 34, 37,
+                                            41, 45, 48, 53, 58, 64, 70, 76, 84, 90, 99, 108, 118, 129, 140, 152, 167, 182, 199, 217, 237, 258,
+                                            282, 308, 336, 367, 400, 435, 474, 517, 565, 617, 672, 732, 749], np.int64)
+    assert counts.size == 127
+    scheme = H.Buckets.exponential(3, -78, 126)
+    app = H.Appender(2, 15000)
+    for _ in range(159):
+        assert app.add(scheme.write_delta(counts)) == H.ACK
+        counts = counts + 10
+    assert H.Reader(app.bytes()).length == 159
+    one = H.Buckets.exponential(20, 9037032, 1).write_delta([0, 1])
+    app = H.Appender(2, 15000)
+    for i in range(576):
+        assert app.add(one) == (H.ACK if i < 575 else H.VECTOR_TOO_SMALL)
+    assert H.Reader(app.bytes()).length == 575
+    big = H.Buckets.exponential(5, -1, 180)
+    c = np.zeros(181, np.int64); c[-1] = 2
+    app = H.Appender(2, 15000)
+    assert app.add(big.write_delta(c)) == H.ACK
+    s, v = H.Reader(app.bytes()).apply_exp(0)
+    assert s == (5, -1, 180) and v.tolist() == c.tolist()
+
+
+def test_exp_vector_rejects_invalid_blobs_and_empty_reads():
+    """ExpHistogramVectorTest.scala:12-21, :214-229."""
+    app = H.Appender(2, 1024)
+    assert app.add(np.frombuffer(b"monkeying" + bytes(32), np.uint8)) == H.INVALID_HISTOGRAM
+    assert app.add(np.array([1, 0, 0, 0, 0, 0, 0, 0], np.uint8)) == H.INVALID_HISTOGRAM      # null histogram
+    assert app.length == 0
+    with pytest.raises(RuntimeError):
+        H.Reader(app.bytes()).apply_exp(0)
