@@ -310,6 +310,23 @@ def test_exp_add_zero_only_histograms():
     assert rb.scheme.tolist() == b2.scheme.tolist() and rv.tolist() == [2.0, 10.0, 11, 12, 13, 14, 15]
 
 
+# cumulative counts of the "real data" histogram of HistogramTest.scala:135-166 / ExpHistogramVectorTest.scala:64-95, scheme (3, -78, 126)
+REAL_COUNTS = np.array([0] * 55 + [1] * 7 + [2, 2, 3, 3, 3, 3, 4, 5, 5, 5, 6, 6, 8, 8, 9, 9, 11, 12, 14, 15, 17, 19, 20, 22, 23, 26, 28, 31, 34, 37,
+                                             41, 45, 48, 53, 58, 64, 70, 76, 84, 90, 99, 108, 118, 129, 140, 152, 167, 182, 199, 217, 237, 258,
+                                             282, 308, 336, 367, 400, 435, 474, 517, 565, 617, 672, 732, 749], np.int64)
+
+
+def test_exp_quantile_real_data():
+    """HistogramTest.scala:133-176 (quantiles with the default min / max)."""
+    b = H.Buckets.exponential(3, -78, 126)
+    t = b.tops()
+    assert t[1] == pytest.approx(0.0012664448775888738, rel=1e-12) and t[-1] == pytest.approx(64.00000000000009, rel=1e-12)
+    v = REAL_COUNTS.astype(np.float64)
+    assert b.quantile(v, 0.5) == pytest.approx(29.927691427444305, abs=1e-5)
+    assert b.quantile(v, 0.99) == pytest.approx(61.602904581469566, abs=1e-5)
+    assert b.quantile(v, 0.01) == pytest.approx(0.6916552392692796, abs=1e-5)
+
+
 OTEL_EXP = [((3, -3, 1), [0, 3]), ((20, -3, 9), [0, 4, 5, 6, 7, 8, 9, 10, 11, 12]), ((20, -888388, 1), [0, 5])]   # ExpHistogramVectorTest.scala:35-39
 EXP_VECTOR_HEX = ("5C00000009130300540003001800160009100002000300FDFFFFFF01000000000000000200031E00"
                   "1C000910000A001400FDFFFFFF0900000000000000FE00141111010300111800160009100002001400BC71F2FF0100000000000000020005")
@@ -341,9 +358,7 @@ def test_exp_vector_sum_and_capacity():
     sch, vals = rd.sum_exp(0, 2)
     assert sch == (3, -8, 9)
     assert vals.tolist() == [0.0, 0.0, 5.0, 5.0, 5.0, 5.0, 8.0, 8.0, 14.0, 20.0]
-    counts = np.array([0] * 55 + [1] * 7 + [2, 2, 3, 3, 3, 3, 4, 5, 5, 5, 6, 6, 8, 8, 9, 9, 11, 12, 14, 15, 17, 19, 20, 22, 23, 26, 28, 31, 34, 37,
-                                            41, 45, 48, 53, 58, 64, 70, 76, 84, 90, 99, 108, 118, 129, 140, 152, 167, 182, 199, 217, 237, 258,
-                                            282, 308, 336, 367, 400, 435, 474, 517, 565, 617, 672, 732, 749], np.int64)
+    counts = REAL_COUNTS.copy()
     assert counts.size == 127
     scheme = H.Buckets.exponential(3, -78, 126)
     app = H.Appender(2, 15000)
