@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfilo_b200.so")
 OBJ = os.path.join(HERE, "csrc", "_obj")
-SOURCES = ["scan_kernels.cu", "hist_kernels.cu", "synth_kernels.cu", "capi.cu"]
+SOURCES = ["scan_kernels.cu", "hist_kernels.cu", "hist_kernels2.cu", "synth_kernels.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-DFILO_BUILDING"] + os.environ.get("FILO_NVCC_EXTRA", "").split()
 

@@ -147,6 +147,9 @@ int32_t filo_num_windows(int64_t start, int64_t step, int64_t end) {
 
 } // extern "C"
 
+// FILO_HIST_V2=1 selects the second histogram scan kernel (hist_kernels2.cu) for the shapes it serves
+static bool hist_v2_enabled() { const char* e = getenv("FILO_HIST_V2"); return e && e[0] == '1'; }
+
 // ------------------------------------------------------------------------------------------------------------------
 // grouping: stable sort of series by group id on the device, group bounds, work items of <= seg series of one group
 // ------------------------------------------------------------------------------------------------------------------
@@ -160,8 +163,12 @@ static int32_t build_groups(filo_ctx* ctx, filo_table* t, const int32_t* d_group
   t->grouped = d_group_ids != nullptr;
   // seg: enough items to fill the machine a few times over, capped so partial rows stay small
   int64_t target_items = (int64_t)ctx->sm_count * 64 * 4;
+  int64_t seg_cap = 256;
+  // histogram tables under the second scan kernel: an item's partial is T * buckets doubles (tens of KB) and one CTA folds an
+  // item, so a few items per CTA
+  if (t->hist && hist_v2_enabled()) { target_items = (int64_t)ctx->sm_count * 2 * 6; seg_cap = 4096; }
   int64_t seg = S / std::max<int64_t>(target_items, 1);
-  t->seg = (int)std::min<int64_t>(std::max<int64_t>(seg, 1), 256);
+  t->seg = (int)std::min<int64_t>(std::max<int64_t>(seg, 1), seg_cap);
   CUDA_TRY(ctx, cudaMalloc(&t->d_group_start, (size_t)(n_groups + 1) * 8));
   CUDA_TRY(ctx, cudaMalloc(&t->d_gis, (size_t)(n_groups + 1) * 8));
   if (t->grouped && S > 0) {
@@ -1055,7 +1062,18 @@ extern "C" int32_t filo_query_hist(filo_ctx* ctx, const filo_table* t, int32_t f
   if (out_values) CUDA_TRY(ctx, tmp.alloc((void**)&d_out, (size_t)rows * T * nb * 8));
   if (out_quantile) CUDA_TRY(ctx, tmp.alloc((void**)&d_q, (size_t)rows * T * 8));
   CUDA_TRY(ctx, cudaEventRecord(e0, s));
-  if (fused) {
+  // second kernel: fused sum of rate / increase over cumulative histograms, when its working set leaves room for two CTAs per SM
+  const size_t smem2 = hist2_smem_bytes(t->max_rows, nb, t->max_rec_bytes);
+  const bool v2 = fused && hist_v2_enabled() && q.cumulative && (fn == FILO_FN_RATE || fn == FILO_FN_INCREASE) && T <= 32 * 512 && nb <= 64 &&
+                  smem2 + 1024 <= std::min<size_t>(ctx->max_smem_optin, 227 * 1024);
+  if (v2) {
+    const int cps = (int)std::max<size_t>(1, std::min<size_t>(2, (size_t)(228 * 1024) / (smem2 + 1024)));
+    L.grid = (int)std::max<int64_t>(1, std::min<int64_t>(t->n_items, (int64_t)ctx->sm_count * cps));
+    CUDA_TRY(ctx, tmp.alloc((void**)&pval, (size_t)t->n_items * T * nb * 8));
+    CUDA_TRY(ctx, tmp.alloc((void**)&pany, (size_t)t->n_items * T + 16));
+    CUDA_TRY(ctx, launch_hist_scan2(L, nb, t->max_rows, t->max_rec_bytes, t->grouped ? t->d_order : nullptr, t->d_item_begin, t->n_items, pval, pany));
+    CUDA_TRY(ctx, launch_hist_merge2(pval, pany, t->d_gis, t->n_groups, T, nb, t->d_hist_tops, out_quantile ? quantile : std::nan(""), d_out, d_q, s));
+  } else if (fused) {
     CUDA_TRY(ctx, tmp.alloc((void**)&pval, (size_t)t->n_items * T * nb * 8));
     CUDA_TRY(ctx, tmp.alloc((void**)&pany, (size_t)t->n_items * T + 16));
     CUDA_TRY(ctx, launch_hist_scan(L, nb, t->max_rows, t->max_rec_bytes, t->grouped ? t->d_order : nullptr, t->d_item_begin, t->n_items, 1, nullptr, pval, pany));

@@ -1,0 +1,127 @@
+// Histogram column scan, second version (fused sum of hist rate / increase over cumulative SectDelta histograms): the kernel that
+// strings the phases of hist_phases.h together.  Selected by filo_query_hist when FILO_HIST_V2=1 (see capi.cu); the first
+// version (hist_kernels.cu) serves every other shape.
+#include "kernels.h"
+#include "hist_phases.h"
+
+namespace filo {
+
+__device__ __forceinline__ void h2_report(int* d_err, int code, int64_t sid) {
+  if (atomicCAS(&d_err[0], 0, code) == 0) { d_err[1] = (int)(sid & 0x7fffffff); d_err[2] = (int)(sid >> 31); }
+}
+
+// One CTA folds work items (runs of series of one group, positions index `order`) into the item's partial row
+// pval[it][bucket][window] (bucket-major) and pany[it][window].
+__global__ void __launch_bounds__(H2_THREADS, 2)
+hist_scan2_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, QueryParams q, int nb, int max_rows, uint32_t max_rec,
+                  const int32_t* __restrict__ order, const int64_t* __restrict__ item_begin, int64_t n_items,
+                  double* __restrict__ pval, uint8_t* __restrict__ pany, unsigned long long* d_counters, int* d_err) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  H2Ctx X; h2_ctx_init(X, smem, h2_layout(max_rows, nb, max_rec), q, nb);
+  const int tid = threadIdx.x;
+  int64_t rows_scanned = 0, bytes_scanned = 0;
+  for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int64_t pb = item_begin[it], pe = item_begin[it + 1];
+    double* pv = pval + (size_t)it * q.T * nb; uint8_t* pa = pany + (size_t)it * q.T;
+    for (int i = tid; i < q.T * nb; i += H2_THREADS) pv[i] = 0.0;
+    uint32_t anyb = 0;                                   // bit j: window tid + j * H2_THREADS has a histogram
+    __syncthreads();                                     // the zero fill is visible to the owners of the windows
+    for (int64_t pos = pb; pos < pe; ++pos) {
+      const int64_t sid = order ? (int64_t)order[pos] : pos;
+      {                                                  // stage the record (16-byte aligned, rec_bytes a multiple of 16)
+        const uint8_t* grec = arena + rec_off[sid];
+        const uint32_t rb = reinterpret_cast<const RecordHeader*>(grec)->rec_bytes;
+        const uint4* src = reinterpret_cast<const uint4*>(grec); uint4* dst = reinterpret_cast<uint4*>(smem + X.L.rec);
+        for (uint32_t i = tid; i < (rb >> 4); i += H2_THREADS) dst[i] = src[i];
+      }
+      __syncthreads();
+      h2_tables(tid, X, max_rows);
+      __syncthreads();
+      if (tid == 0) {
+        const H2Ctl* C = X.ctl();
+        rows_scanned += C->rows_scanned; bytes_scanned += C->bytes_scanned;
+        if (C->err) h2_report(d_err, C->err, sid);
+      }
+      h2_decode_rows(tid, H2_THREADS, X);
+      __syncthreads();
+      if (tid == 0 && X.ctl()->bad) h2_report(d_err, 1, sid);
+      h2_add_base(tid, H2_THREADS, X);
+      __syncthreads();
+      h2_chunk_corrections(tid, H2_THREADS, X);
+      __syncthreads();
+      h2_chunk_less(tid, X);
+      __syncthreads();
+      h2_carried(tid, H2_THREADS, X);
+      __syncthreads();
+      int j = 0;
+      for (int k = tid; k < q.T; k += H2_THREADS, ++j) if (h2_window(k, X, pv)) anyb |= 1u << j;
+      __syncthreads();                                   // the series' rows and record are dead
+    }
+    { int j = 0; for (int k = tid; k < q.T; k += H2_THREADS, ++j) pa[k] = (uint8_t)((anyb >> j) & 1u); }
+  }
+  if (tid == 0 && (rows_scanned | bytes_scanned)) { atomicAdd(&d_counters[0], (unsigned long long)rows_scanned); atomicAdd(&d_counters[1], (unsigned long long)bytes_scanned); }
+}
+
+// Fold the partial rows of each group in item order (deterministic), then MutableHistogram.makeMonotonic (Histogram.scala:440-449)
+// and Histogram.quantile (:65-108, non-exponential buckets).  Thread per (group, window); partial rows are bucket-major.
+__global__ void hist_merge2_kernel(const double* __restrict__ pval, const uint8_t* __restrict__ pany, const int64_t* __restrict__ gis,
+                                   int n_groups, int T, int nb, const double* __restrict__ tops, double qtl,
+                                   double* __restrict__ out_values /* [G][T][nb] or null */, double* __restrict__ out_q /* [G][T] or null */) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_groups * T) return;
+  const int g = (int)(i / T), k = (int)(i - (int64_t)g * T);
+  const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
+  double v[64]; bool any = false;
+  for (int b = 0; b < nb; ++b) v[b] = 0.0;
+  for (int64_t it = gis[g]; it < gis[g + 1]; ++it) {
+    if (!pany[(size_t)it * T + k]) continue;
+    any = true;
+    const double* pv = pval + (size_t)it * T * nb + k;
+    for (int b = 0; b < nb; ++b) v[b] += pv[(size_t)b * T];
+  }
+  double qv = NaNv;
+  if (any) {
+    double mx = 0.0;                                                         // makeMonotonic
+    for (int b = 0; b < nb; ++b) { if (v[b] < mx || v[b] != v[b]) v[b] = mx; else if (v[b] > mx) mx = v[b]; }
+    if (qtl == qtl) {                                                        // Histogram.quantile
+      const double top = v[nb - 1];
+      if (qtl < 0) qv = __longlong_as_double(0xfff0000000000000LL);
+      else if (qtl > 1) qv = __longlong_as_double(0x7ff0000000000000LL);
+      else if (nb < 2 || !(top > 0)) qv = NaNv;
+      else {
+        double rank = qtl * top;
+        int bucket = 0; while (v[bucket] < rank) ++bucket;
+        const double bucketStart = bucket == 0 ? 0.0 : tops[bucket - 1];
+        const double bucketEnd = tops[bucket];
+        if (bucket == nb - 1 && isinf(bucketEnd) && bucketEnd > 0) qv = tops[nb - 2];
+        else if (bucket == 0 && tops[0] <= 0) qv = tops[0];
+        else {
+          const double count = bucket == 0 ? v[bucket] : v[bucket] - v[bucket - 1];
+          rank -= (bucket == 0 ? 0.0 : v[bucket - 1]);
+          qv = bucketStart + (bucketEnd - bucketStart) * (rank / count);
+        }
+      }
+    }
+  }
+  if (out_values) for (int b = 0; b < nb; ++b) out_values[(size_t)i * nb + b] = any ? v[b] : NaNv;
+  if (out_q) out_q[i] = qv;
+}
+
+size_t hist2_smem_bytes(int max_rows, int nb, uint32_t max_rec) { return h2_layout(max_rows, nb, max_rec).total; }
+cudaError_t launch_hist_scan2(const ScanLaunch& L, int nb, int max_rows, uint32_t max_rec, const int32_t* order, const int64_t* item_begin, int64_t n_items,
+                              double* pval, uint8_t* pany) {
+  const size_t smem = h2_layout(max_rows, nb, max_rec).total;
+  cudaError_t e = cudaFuncSetAttribute(hist_scan2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  hist_scan2_kernel<<<L.grid, H2_THREADS, smem, L.stream>>>(L.arena, L.rec_off, L.q, nb, max_rows, max_rec, order, item_begin, n_items, pval, pany, L.d_counters, L.d_err);
+  return cudaGetLastError();
+}
+cudaError_t launch_hist_merge2(const double* pval, const uint8_t* pany, const int64_t* gis, int n_groups, int T, int nb, const double* tops, double q,
+                               double* out_values, double* out_q, cudaStream_t s) {
+  const int64_t n = (int64_t)n_groups * T;
+  if (n <= 0) return cudaSuccess;
+  hist_merge2_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pval, pany, gis, n_groups, T, nb, tops, q, out_values, out_q);
+  return cudaGetLastError();
+}
+
+} // namespace filo

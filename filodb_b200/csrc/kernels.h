@@ -49,6 +49,12 @@ cudaError_t launch_hist_scan(const ScanLaunch& L, int nb, int max_rows, uint32_t
                              double* out, double* pval, uint8_t* pany);
 cudaError_t launch_hist_merge(const double* pval, const uint8_t* pany, const int64_t* gis, int n_groups, int T, int nb, const double* tops, double q,
                               double* out_values, double* out_q, cudaStream_t s);
+// second version of the histogram scan (hist_kernels2.cu): fused sum of rate / increase over cumulative SectDelta histograms
+size_t hist2_smem_bytes(int max_rows, int nb, uint32_t max_rec);
+cudaError_t launch_hist_scan2(const ScanLaunch& L, int nb, int max_rows, uint32_t max_rec, const int32_t* order, const int64_t* item_begin, int64_t n_items,
+                              double* pval, uint8_t* pany);
+cudaError_t launch_hist_merge2(const double* pval, const uint8_t* pany, const int64_t* gis, int n_groups, int T, int nb, const double* tops, double q,
+                               double* out_values, double* out_q, cudaStream_t s);
 cudaError_t launch_iota(int32_t* a, int64_t n, cudaStream_t s);
 cudaError_t launch_group_bounds(const int32_t* sorted_keys, int64_t n, int n_groups, int64_t* group_start, cudaStream_t s);
 cudaError_t launch_group_item_count(const int64_t* group_start, int n_groups, int seg, int64_t* cnt, cudaStream_t s);
