@@ -147,8 +147,8 @@ int32_t filo_num_windows(int64_t start, int64_t step, int64_t end) {
 
 } // extern "C"
 
-// FILO_HIST_V2=1 selects the second histogram scan kernel (hist_kernels2.cu) for the shapes it serves
-static bool hist_v2_enabled() { const char* e = getenv("FILO_HIST_V2"); return e && e[0] == '1'; }
+// The second histogram scan kernel (hist_kernels2.cu) serves the shapes it covers unless FILO_HIST_V2=0 (A/B runs against the first)
+static bool hist_v2_enabled() { const char* e = getenv("FILO_HIST_V2"); return !(e && e[0] == '0'); }
 
 // ------------------------------------------------------------------------------------------------------------------
 // grouping: stable sort of series by group id on the device, group bounds, work items of <= seg series of one group

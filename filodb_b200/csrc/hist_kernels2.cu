@@ -1,6 +1,6 @@
 // Histogram column scan, second version (fused sum of hist rate / increase over cumulative SectDelta histograms): the kernel that
-// strings the phases of hist_phases.h together.  Selected by filo_query_hist when FILO_HIST_V2=1 (see capi.cu); the first
-// version (hist_kernels.cu) serves every other shape.
+// strings the phases of hist_phases.h together.  filo_query_hist selects it for the shapes it serves (capi.cu; FILO_HIST_V2=0 turns it
+// off for A/B runs); the first version (hist_kernels.cu) serves every other shape.
 #include "kernels.h"
 #include "hist_phases.h"
 
@@ -8,6 +8,14 @@ namespace filo {
 
 __device__ __forceinline__ void h2_report(int* d_err, int code, int64_t sid) {
   if (atomicCAS(&d_err[0], 0, code) == 0) { d_err[1] = (int)(sid & 0x7fffffff); d_err[2] = (int)(sid >> 31); }
+}
+
+// record bytes global -> shared with 16-byte cp.async (LDGSTS); the caller waits with cp.async.wait_group + a CTA barrier
+__device__ __forceinline__ void h2_stage_async(uint8_t* dst, const uint8_t* __restrict__ src, uint32_t bytes, int tid) {
+  const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
+  for (uint32_t i = (uint32_t)tid * 16; i < bytes; i += H2_THREADS * 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + i), "l"(src + i) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // One CTA folds work items (runs of series of one group, positions index `order`) into the item's partial row
@@ -26,14 +34,14 @@ hist_scan2_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__
     for (int i = tid; i < q.T * nb; i += H2_THREADS) pv[i] = 0.0;
     uint32_t anyb = 0;                                   // bit j: window tid + j * H2_THREADS has a histogram
     __syncthreads();                                     // the zero fill is visible to the owners of the windows
+    bool prefetched = false;                             // the record of `pos` is already on its way (cp.async issued after the previous decode)
     for (int64_t pos = pb; pos < pe; ++pos) {
       const int64_t sid = order ? (int64_t)order[pos] : pos;
-      {                                                  // stage the record (16-byte aligned, rec_bytes a multiple of 16)
-        const uint8_t* grec = arena + rec_off[sid];
-        const uint32_t rb = reinterpret_cast<const RecordHeader*>(grec)->rec_bytes;
-        const uint4* src = reinterpret_cast<const uint4*>(grec); uint4* dst = reinterpret_cast<uint4*>(smem + X.L.rec);
-        for (uint32_t i = tid; i < (rb >> 4); i += H2_THREADS) dst[i] = src[i];
+      if (!prefetched) {                                 // stage the record (16-byte aligned, size a multiple of 16)
+        const int64_t ro = rec_off[sid];
+        h2_stage_async(smem + X.L.rec, arena + ro, (uint32_t)(rec_off[sid + 1] - ro), tid);
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
       h2_tables(tid, X, max_rows);
       __syncthreads();
@@ -44,6 +52,13 @@ hist_scan2_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__
       }
       h2_decode_rows(tid, H2_THREADS, X);
       __syncthreads();
+      // the staged record is dead from here on: fetch the next series' record behind the remaining phases
+      prefetched = pos + 1 < pe;
+      if (prefetched) {
+        const int64_t nsid = order ? (int64_t)order[pos + 1] : pos + 1;
+        const int64_t ro = rec_off[nsid];
+        h2_stage_async(smem + X.L.rec, arena + ro, (uint32_t)(rec_off[nsid + 1] - ro), tid);
+      }
       if (tid == 0 && X.ctl()->bad) h2_report(d_err, 1, sid);
       h2_add_base(tid, H2_THREADS, X);
       __syncthreads();

@@ -417,9 +417,12 @@ def _hist_series(rng, rows, nb, resets=()):
     return out
 
 
+@pytest.mark.parametrize("kernel", ["v2", "v1"])
 @pytest.mark.parametrize("scheme", ["custom", "geometric"])
-def test_hist_rate_sum_quantile(gpu, oracle, scheme):
-    """hist rate / increase (SectDelta, counter correction inside and across chunks), fused sum by group, histogram_quantile."""
+def test_hist_rate_sum_quantile(gpu, oracle, scheme, kernel, monkeypatch):
+    """hist rate / increase (SectDelta, counter correction inside and across chunks), fused sum by group, histogram_quantile.
+    kernel: the fused sum runs on hist_scan2_kernel by default; FILO_HIST_V2=0 keeps it on the first kernel."""
+    monkeypatch.setenv("FILO_HIST_V2", "1" if kernel == "v2" else "0")
     capi, ctx = gpu; o = oracle
     from oracle import hist as H
     rng = np.random.default_rng(21)
