@@ -185,7 +185,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
   double* vals = reinterpret_cast<double*>(smem + L.vals);
   double* otile = reinterpret_cast<double*>(smem + L.out);
   uint64_t* gexcl = reinterpret_cast<uint64_t*>(smem + L.gtot);        // [series][slot]: XOR of the warp's earlier group totals
-  uint64_t* gwtot = gexcl + TILE_NS * TILE_MAXG;                       // [series][warp]: XOR of the warp's 8 group totals
+  uint64_t* gwtot = gexcl + TILE_NS * TILE_GX_PITCH;                       // [series][warp]: XOR of the warp's 8 group totals
   // Tile walk.  Work items are strided over the CTAs; an item is a run of consecutive positions processed in tiles of
   // TILE_NS.  Per-series mode: item = one tile of consecutive series.  AGG mode: item = <= seg series of ONE group in
   // group-sorted order (positions index `order`), folded into one partial row per item (pval/pcnt, see scan_agg_kernel).
@@ -489,9 +489,9 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
       { const uint64_t y0 = shfl_up_u64(i0x, 16), y1 = shfl_up_u64(i1x, 16); if (lane >= 16) { i0x ^= y0; i1x ^= y1; } }
       const uint64_t tot0 = shfl_u64(i0x, 24 + ds), tot1 = shfl_u64(i1x, 24 + ds);
       excl[0] = i0x ^ d[0][7]; excl[1] = i1x ^ d[1][7] ^ tot0;
-      gexcl[ds * TILE_MAXG + warp * 8 + (lane >> 3)] = excl[0];
-      gexcl[ds * TILE_MAXG + warp * 8 + 4 + (lane >> 3)] = excl[1];
-      if (lane >= 24) gwtot[ds * 8 + warp] = tot0 ^ tot1;
+      gexcl[ds * TILE_GX_PITCH + warp * 8 + (lane >> 3)] = excl[0];
+      gexcl[ds * TILE_GX_PITCH + warp * 8 + 4 + (lane >> 3)] = excl[1];
+      if (lane >= 24) gwtot[ds * TILE_GW_PITCH + warp] = tot0 ^ tot1;
       bar_consumers();
       // value before group g of chunk c = first_c ^ (prefix at the slot) ^ (prefix at the chunk's first slot); the prefix at a
       // slot = XOR of the earlier warps' totals ^ the in-warp part
@@ -500,11 +500,11 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
       {
         const TileChunk& c0 = S.c[cc[0]]; const TileChunk& c1 = S.c[cc[1]];
         const int gb0 = act[0] ? c0.grp_base : 0, gb1 = act[1] ? c1.grp_base : 0;
-        uint64_t pre0 = c0.first ^ excl[0] ^ gexcl[ds * TILE_MAXG + gb0];
-        uint64_t pre1 = c1.first ^ excl[1] ^ gexcl[ds * TILE_MAXG + gb1];
+        uint64_t pre0 = c0.first ^ excl[0] ^ gexcl[ds * TILE_GX_PITCH + gb0];
+        uint64_t pre1 = c1.first ^ excl[1] ^ gexcl[ds * TILE_GX_PITCH + gb1];
         const int wl0 = gb0 >> 3, wl1 = gb1 >> 3;
         for (int w = 0; w < warp; ++w) {
-          const uint64_t tw = gwtot[ds * 8 + w];
+          const uint64_t tw = gwtot[ds * TILE_GW_PITCH + w];
           if (w >= wl0) pre0 ^= tw;
           if (w >= wl1) pre1 ^= tw;
         }

@@ -10,6 +10,9 @@ constexpr int TILE_LAUNCH_THREADS = TILE_THREADS + 32;   // + one producer warp 
 constexpr int TILE_MAXC = 4;             // chunks in range per series on the fast path
 constexpr int TILE_AGG_ACC = 2;           // fused aggregate: per-thread accumulators -> T <= TILE_AGG_ACC * TILE_THREADS windows
 constexpr int TILE_MAXG = 64;            // NibblePack groups per series on the fast path (64 * 8 = 512 rows)
+// pitches (in 8-byte words) of the cross-warp XOR exchange tables: lane = series + 8 * k stores slot 8 * warp + k of series
+// `series`; a pitch of 2 (mod 16) puts the 16 lanes of a half-warp into 16 different bank pairs, 9 does the same for [series][warp]
+constexpr int TILE_GX_PITCH = TILE_MAXG + 2, TILE_GW_PITCH = 9;
 
 struct TileChunk {
   int64_t init, end_time;
@@ -73,7 +76,7 @@ FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, u
   L.vals = o; o += align_up(TILE_NS * L.vals_pitch * 8, 128);
   L.out = o; o += align_up(TILE_NS * T * 8, 128);
   L.desc = o; o += 2 * align_up(TILE_NS * (uint32_t)sizeof(TileSeries), 128);      // double-buffered: setup of tile t+1 overlaps tile t
-  L.gtot = o; o += TILE_NS * TILE_MAXG * 8 + TILE_NS * (TILE_THREADS / 32) * 8;   // per-slot in-warp prefixes + per-warp totals
+  L.gtot = o; o += TILE_NS * TILE_GX_PITCH * 8 + TILE_NS * TILE_GW_PITCH * 8;     // per-slot in-warp prefixes + per-warp totals (padded pitches)
   L.meta = o; o += 2 * 128;
   L.ctr = o; L.drops = o; L.tab = o;
   if (counter_class) { o += 2 * align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileCtr), 128); L.drops = o; o += align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileDrops), 128);
