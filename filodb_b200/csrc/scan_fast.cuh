@@ -27,6 +27,17 @@ constexpr int STAGE_BYTES = (STAGE_VALS_BYTES + 256 + 127) / 128 * 128;   // + p
 constexpr int WARP_HDR_BYTES = 128;      // mbarrier slot; keeps every per-warp region 128-byte aligned (TMA destination needs 16)
 
 // ------------------------------------------------------------------------------------------------ TMA / mbarrier
+// FILO_CUSIM: the kernels compiled for the host on top of tests/cpp/cusim.h (fiber-per-thread SIMT emulation, test infrastructure);
+// the PTX helpers below are the only place where the two builds differ.
+#ifdef FILO_CUSIM
+inline void mbar_init(uint64_t* bar, int count) { cusim::mbar_init(bar, (uint32_t)count); }
+inline void mbar_fence_init() {}
+inline void mbar_arrive(uint64_t* bar) { cusim::mbar_arrive(bar); }
+inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { cusim::mbar_expect_tx(bar, bytes); }
+inline void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) { cusim::tma_load(dst, src, bytes, bar); }
+inline void mbar_wait(uint64_t* bar, uint32_t parity) { cusim::mbar_wait(bar, parity); }
+inline void mbar_wait_parked(uint64_t* bar, uint32_t parity) { cusim::mbar_wait(bar, parity); }
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -61,6 +72,8 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
   } while (!ok);
 }
+
+#endif
 
 // ------------------------------------------------------------------------------------------------ integer helpers
 // Division by the (kernel-invariant) query step: double reciprocal + one correction, exact for |a| < 2^31, d < 2^31.

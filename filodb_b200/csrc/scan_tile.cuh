@@ -19,12 +19,18 @@
 
 namespace filo {
 
+#ifdef FILO_CUSIM
+inline void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes) { cusim::tma_store(gdst, ssrc, bytes); }
+inline void tma_store_wait_read() { cusim::tma_store_wait_read(); }
+inline void fence_async_smem() {}
+#else
 __device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
 
 // compile-time specialised finish of one single-chunk window (SumFinish of scan_fast.cuh with FN known)
 template <int FN>
@@ -204,7 +210,11 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
   int64_t winDur = q.inclusive ? q.window : q.window - 1; if (winDur < 0) winDur = 0;
   const double fdiv = (double)(q.inclusive ? winDur : winDur + 1), frcp = 1.0 / fdiv;     // RateFunctions.scala:436-442
   const int64_t S0 = q.start - winDur, E0 = q.start;
+#ifdef FILO_CUSIM
+  auto bar_consumers = [] { cusim::bar_sync(1, TILE_THREADS); };
+#else
   auto bar_consumers = [] { asm volatile("bar.sync 1, %0;" ::"n"(TILE_THREADS) : "memory"); };
+#endif
   // Per tile: A = "descriptors of the tile are ready" (producer -> consumers, an mbarrier), B = "the tile's record bytes are
   // dead" (a CTA-wide barrier: consumers -> producer, the staging buffer may be refilled; decode -> windows among consumers).  The producer warp
   // loads and resolves tile t+1 while the consumers reduce the windows of tile t.

@@ -76,7 +76,7 @@ FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, u
   L.vals = o; o += align_up(TILE_NS * L.vals_pitch * 8, 128);
   L.out = o; o += align_up(TILE_NS * T * 8, 128);
   L.desc = o; o += 2 * align_up(TILE_NS * (uint32_t)sizeof(TileSeries), 128);      // double-buffered: setup of tile t+1 overlaps tile t
-  L.gtot = o; o += TILE_NS * TILE_GX_PITCH * 8 + TILE_NS * TILE_GW_PITCH * 8;     // per-slot in-warp prefixes + per-warp totals (padded pitches)
+  L.gtot = o; o += align_up(TILE_NS * TILE_GX_PITCH * 8 + TILE_NS * TILE_GW_PITCH * 8, 128);     // per-slot in-warp prefixes + per-warp totals (padded pitches)
   L.meta = o; o += 2 * 128;
   L.ctr = o; L.drops = o; L.tab = o;
   if (counter_class) { o += 2 * align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileCtr), 128); L.drops = o; o += align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileDrops), 128);
