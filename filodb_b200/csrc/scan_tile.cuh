@@ -522,7 +522,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         for (int jj = 0; jj < 2; ++jj) {
           const TileChunk& ch = jj ? c1 : c0;
           const uint64_t pre = jj ? pre1 : pre0;
-          const int g = warp * 8 + jj * 4 + (lane >> 3) - ch.grp_base;
+          const int g = act[jj] ? warp * 8 + jj * 4 + (lane >> 3) - ch.grp_base : 0;   // an inactive slot's chunk descriptor is not initialised
           uint64_t* dst = reinterpret_cast<uint64_t*>(vals + (size_t)ds * L.vals_pitch + ch.row_base) + 1 + g * 8;
           const int nleft = act[jj] ? ch.nrows - 1 - g * 8 : 0;     // rows past nrows are never read as data
 #pragma unroll

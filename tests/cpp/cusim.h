@@ -20,14 +20,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <functional>
 #include <vector>
 
 namespace cusim {
 
-struct Fiber { ucontext_t ctx; std::vector<char> stack; uint3 tid{0, 0, 0}; bool done = false; const char* waiting = nullptr; std::vector<int> my_stores; };
+struct Fiber { ucontext_t ctx; std::vector<char> stack; uint3 tid{0, 0, 0}; bool done = false; const char* waiting = nullptr; int site = 0; };
 struct NamedBar { int arrived = 0; unsigned gen = 0; };
-struct WarpState { uint64_t slot[32]; int arrived = 0; unsigned gen = 0; unsigned mask = 0; };
+struct WarpState { uint64_t slot[32]; int arrived = 0; unsigned gen = 0; unsigned mask = 0; int site = 0, first_lane = 0; };
 struct Deferred { int countdown; bool is_load; void* dst; const void* src; size_t bytes; uint64_t* bar; int owner; bool done; };
 
 struct Cta {
@@ -39,7 +40,9 @@ struct Cta {
 };
 inline Cta*& g() { static Cta* p = nullptr; return p; }
 inline uint64_t& rng_state() { static uint64_t s = 0; return s; }        // 0: round-robin; else seeded xorshift schedule
-inline int& tma_delay() { static int d = 64; return d; }                 // scheduling steps before a deferred bulk copy is performed
+inline int& tma_delay() { static int d = 1 << 30; return d; }            // fiber switches before a deferred bulk copy is performed; the default is adversarial:
+                                                                         // a copy happens as late as the program allows (when its issuer waits for it, or when
+                                                                         // every fiber is blocked)
 inline Fiber& me() { return g()->fibers[(size_t)g()->cur]; }
 inline int linear_tid() { const Fiber& f = me(); return (int)(f.tid.x + f.tid.y * g()->bdim.x + f.tid.z * g()->bdim.x * g()->bdim.y); }
 inline void progress() { ++g()->progress; }
@@ -85,7 +88,13 @@ inline void warp_barrier(unsigned mask) {
   WarpState& W = my_warp();
   const int lane = linear_tid() & 31;
   if (!((mask >> lane) & 1u)) { std::fprintf(stderr, "cusim: lane %d calls a warp collective whose mask %08x excludes it\n", lane, mask); std::abort(); }
-  if (W.arrived == 0) W.mask = mask; else if (W.mask != mask) { std::fprintf(stderr, "cusim: warp collective with differing masks %08x vs %08x\n", W.mask, mask); std::abort(); }
+  if (W.arrived == 0) { W.mask = mask; W.site = me().site; W.first_lane = lane; }
+  else if (W.mask != mask) { std::fprintf(stderr, "cusim: warp collective with differing masks %08x vs %08x\n", W.mask, mask); std::abort(); }
+  else if (W.site != me().site) {          // the lanes named in the mask must execute the SAME collective (convergence requirement of *_sync)
+    std::fprintf(stderr, "cusim: DIVERGENT warp collective in block %u warp %d: lane %d is at source line %d while lane %d is at line %d\n",
+                 g()->bidx.x, linear_tid() >> 5, W.first_lane, W.site, lane, me().site);
+    std::abort();
+  }
   const unsigned gen = W.gen;
   progress();
   if (++W.arrived == __builtin_popcount(mask)) { W.arrived = 0; ++W.gen; } else while (W.gen == gen) yield("warp collective");
@@ -113,8 +122,25 @@ inline unsigned warp_ballot(unsigned mask, int pred) {
 inline void trampoline() { g()->body(); me().done = true; progress(); swapcontext(&me().ctx, &g()->sched); }
 inline void report_deadlock() {
   std::fprintf(stderr, "cusim: DEADLOCK in block (%u,%u,%u): no fiber can make progress\n", g()->bidx.x, g()->bidx.y, g()->bidx.z);
-  int shown = 0;
-  for (size_t i = 0; i < g()->fibers.size() && shown < 40; ++i) { const Fiber& f = g()->fibers[i]; if (!f.done) { std::fprintf(stderr, "  thread %zu (warp %zu lane %zu): %s\n", i, i >> 5, i & 31, f.waiting ? f.waiting : "?"); ++shown; } }
+  for (size_t w = 0; w < g()->warps.size(); ++w) {            // per warp: how many lanes wait for what
+    const char* reasons[8]; int counts[8]; int n = 0, done = 0;
+    for (size_t l = 0; l < 32 && w * 32 + l < g()->fibers.size(); ++l) {
+      const Fiber& f = g()->fibers[w * 32 + l];
+      if (f.done) { ++done; continue; }
+      const char* r = f.waiting ? f.waiting : "?";
+      int k = 0; while (k < n && reasons[k] != r) ++k;
+      if (k == n && n < 8) { reasons[n] = r; counts[n] = 0; ++n; }
+      if (k < 8) ++counts[k];
+    }
+    std::fprintf(stderr, "  warp %zu:", w);
+    if (done) std::fprintf(stderr, " %d lanes finished;", done);
+    for (int k = 0; k < n; ++k) std::fprintf(stderr, " %d lanes in %s;", counts[k], reasons[k]);
+    for (size_t l = 0; l < 32 && w * 32 + l < g()->fibers.size(); ++l) {
+      const Fiber& f = g()->fibers[w * 32 + l];
+      if (!f.done && f.waiting && !std::strcmp(f.waiting, "warp collective")) std::fprintf(stderr, " [lane %zu: collective at source line %d]", l, f.site);
+    }
+    std::fprintf(stderr, "\n");
+  }
   std::abort();
 }
 // launch(grid, block, body): body is the kernel call; it runs once per CUDA thread
@@ -131,19 +157,25 @@ inline void launch(dim3 grid, dim3 block, const std::function<void()>& body, siz
       getcontext(&f.ctx); f.ctx.uc_stack.ss_sp = f.stack.data(); f.ctx.uc_stack.ss_size = f.stack.size(); f.ctx.uc_link = &cta.sched;
       makecontext(&f.ctx, (void (*)())trampoline, 0);
     }
-    int live = nthreads, idle = 0, next = 0; uint64_t last = cta.progress;
+    // rounds: every live fiber gets one turn per round, in index order (seed 0) or in a fresh pseudo-random permutation
+    int live = nthreads, idle_rounds = 0; uint64_t last = cta.progress;
     uint64_t& rs = rng_state();
+    std::vector<int> perm((size_t)nthreads); for (int t = 0; t < nthreads; ++t) perm[(size_t)t] = t;
     while (live > 0) {
-      int pick = next;
-      if (rs) { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; pick = (int)(rs % (uint64_t)nthreads); }
-      int tries = 0; while (cta.fibers[(size_t)pick].done && tries < nthreads) { pick = (pick + 1) % nthreads; ++tries; }
-      next = (pick + 1) % nthreads;
-      cta.cur = pick;
-      swapcontext(&cta.sched, &cta.fibers[(size_t)pick].ctx);
-      if (cta.fibers[(size_t)pick].done) --live;
-      tick_ops();
-      if (cta.progress != last) { last = cta.progress; idle = 0; }
-      else if (++idle > 8 * nthreads + 4 * tma_delay()) { bool pending = false; for (auto& o : cta.ops) pending |= !o.done; if (pending) { for (auto& o : cta.ops) run_op(o); idle = 0; } else report_deadlock(); }
+      if (rs) for (int t = nthreads - 1; t > 0; --t) { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; std::swap(perm[(size_t)t], perm[(size_t)(rs % (uint64_t)(t + 1))]); }
+      for (int t = 0; t < nthreads; ++t) {
+        const int pick = perm[(size_t)t];
+        if (cta.fibers[(size_t)pick].done) continue;
+        cta.cur = pick;
+        swapcontext(&cta.sched, &cta.fibers[(size_t)pick].ctx);
+        if (cta.fibers[(size_t)pick].done) --live;
+        tick_ops();
+      }
+      if (cta.progress != last) { last = cta.progress; idle_rounds = 0; }
+      else if (++idle_rounds > 1) {
+        bool pending = false; for (auto& o : cta.ops) pending |= !o.done && o.is_load;
+        if (pending) { for (auto& o : cta.ops) if (o.is_load) run_op(o); idle_rounds = 0; } else report_deadlock();     // stores stay pending: nobody can be blocked on them
+      }
     }
     for (auto& o : cta.ops) run_op(o);                   // bulk stores still in flight at kernel end complete
     g() = nullptr;
@@ -157,19 +189,43 @@ inline void launch(dim3 grid, dim3 block, const std::function<void()>& body, siz
 #define blockIdx (cusim::g()->bidx)
 #define blockDim (cusim::g()->bdim)
 #define gridDim (cusim::g()->gdim)
-alignas(128) inline uint8_t smem[232448];                      // `extern __shared__ ... smem[]` in the kernels binds to this (one CTA at a time)
+// dynamic shared memory: the kernels' block-scope `extern __shared__ ... smem[]` names <enclosing namespace>::smem; the harness defines it
+// (e.g. `namespace filo { alignas(128) uint8_t smem[232448]; }`) — one CTA runs at a time, so one buffer serves them all
 
 inline void __syncthreads() { cusim::bar_sync(0, (int)(blockDim.x * blockDim.y * blockDim.z)); }
-inline void __syncwarp(unsigned mask = 0xffffffffu) { cusim::warp_barrier(mask); }
-template <class T> inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) { const int lane = cusim::linear_tid() & 31; return cusim::warp_exchange(mask, v, (lane & ~(width - 1)) + (src & (width - 1))); }
-template <class T> inline T __shfl_up_sync(unsigned mask, T v, unsigned d, int width = 32) { const int lane = cusim::linear_tid() & 31; const int src = lane - (int)d; return cusim::warp_exchange(mask, v, src < (lane & ~(width - 1)) ? -1 : src); }
-template <class T> inline T __shfl_down_sync(unsigned mask, T v, unsigned d, int width = 32) { const int lane = cusim::linear_tid() & 31; const int src = lane + (int)d; return cusim::warp_exchange(mask, v, src > (lane | (width - 1)) ? -1 : src); }
-template <class T> inline T __shfl_xor_sync(unsigned mask, T v, int x, int width = 32) { const int lane = cusim::linear_tid() & 31; (void)width; return cusim::warp_exchange(mask, v, lane ^ x); }
-inline unsigned __ballot_sync(unsigned mask, int pred) { return cusim::warp_ballot(mask, pred); }
-inline int __any_sync(unsigned mask, int pred) { return cusim::warp_ballot(mask, pred) != 0; }
-inline int __all_sync(unsigned mask, int pred) { return (cusim::warp_ballot(mask, pred) & mask) == mask; }
+namespace cusim {
+inline void at(int line) { me().site = line; }
+inline void syncwarp(unsigned mask = 0xffffffffu) { warp_barrier(mask); }
+template <class T> inline T shfl(unsigned mask, T v, int src, int width = 32) { const int lane = linear_tid() & 31; return warp_exchange(mask, v, (lane & ~(width - 1)) + (src & (width - 1))); }
+template <class T> inline T shfl_up(unsigned mask, T v, unsigned d, int width = 32) { const int lane = linear_tid() & 31; const int src = lane - (int)d; return warp_exchange(mask, v, src < (lane & ~(width - 1)) ? -1 : src); }
+template <class T> inline T shfl_down(unsigned mask, T v, unsigned d, int width = 32) { const int lane = linear_tid() & 31; const int src = lane + (int)d; return warp_exchange(mask, v, src > (lane | (width - 1)) ? -1 : src); }
+template <class T> inline T shfl_xor(unsigned mask, T v, int x, int width = 32) { const int lane = linear_tid() & 31; (void)width; return warp_exchange(mask, v, lane ^ x); }
+inline unsigned ballot(unsigned mask, int pred) { return warp_ballot(mask, pred); }
+inline int any(unsigned mask, int pred) { return warp_ballot(mask, pred) != 0; }
+inline int all(unsigned mask, int pred) { return (warp_ballot(mask, pred) & mask) == mask; }
+}
+// the *_sync collectives record their source line: lanes of one collective must come from the same call site
+#define __syncwarp(...) (cusim::at(__LINE__), cusim::syncwarp(__VA_ARGS__))
+#define __shfl_sync(...) (cusim::at(__LINE__), cusim::shfl(__VA_ARGS__))
+#define __shfl_up_sync(...) (cusim::at(__LINE__), cusim::shfl_up(__VA_ARGS__))
+#define __shfl_down_sync(...) (cusim::at(__LINE__), cusim::shfl_down(__VA_ARGS__))
+#define __shfl_xor_sync(...) (cusim::at(__LINE__), cusim::shfl_xor(__VA_ARGS__))
+#define __ballot_sync(...) (cusim::at(__LINE__), cusim::ballot(__VA_ARGS__))
+#define __any_sync(...) (cusim::at(__LINE__), cusim::any(__VA_ARGS__))
+#define __all_sync(...) (cusim::at(__LINE__), cusim::all(__VA_ARGS__))
 inline unsigned __activemask() { return 0xffffffffu; }
 
+#ifdef __launch_bounds__
+#undef __launch_bounds__
+#endif
+#define __launch_bounds__(...)
+inline unsigned __double2uint_rz(double d) { return d != d || d <= 0.0 ? 0u : d >= 4294967295.0 ? 0xffffffffu : (unsigned)d; }
+inline int __double2int_rz(double d) { return d != d ? 0 : d >= 2147483647.0 ? INT32_MAX : d <= -2147483648.0 ? INT32_MIN : (int)d; }
+inline long long __double2ll_rz(double d) { return d != d ? 0 : d >= 9.2233720368547758e18 ? INT64_MAX : d <= -9.2233720368547758e18 ? INT64_MIN : (long long)d; }
+inline long long __double2ll_rd(double d) { return __double2ll_rz(std::floor(d)); }
+inline long long __double2ll_ru(double d) { return __double2ll_rz(std::ceil(d)); }
+inline long long __double2ll_rn(double d) { return __double2ll_rz(std::nearbyint(d)); }
+inline int __double2int_rn(double d) { return __double2int_rz(std::nearbyint(d)); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
@@ -207,4 +263,3 @@ template <class T> inline T atomicCAS(T* p, T cmp, T v) { const T o = *p; if (o 
 inline void __threadfence() {}
 inline void __threadfence_block() {}
 inline void __nanosleep(unsigned) { cusim::yield("nanosleep"); }
-inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)((const uint8_t*)p - smem); }

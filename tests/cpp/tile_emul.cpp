@@ -1,0 +1,189 @@
+// scan_tile_kernel on the CPU: the kernel's own source (filodb_b200/csrc/scan_tile.cuh) compiled for the host on top of the cusim
+// SIMT emulator (tests/cpp/cusim.h), fed with arena records built from the oracle's encoders and checked bit-exact against the
+// oracle's ChunkedWindowIterator.  Test infrastructure: built and run by tests/test_abi.py.
+//   tile_emul [seed]     seed 0 = round-robin schedule, otherwise a pseudo-random fiber schedule
+#define FILO_CUSIM 1
+#include "cusim.h"
+namespace filo { alignas(128) uint8_t smem[232448]; }          // `extern __shared__ ... smem[]` of the kernels
+#include "../../filodb_b200/csrc/kernels.h"
+#include "../../filodb_b200/csrc/scan_tile.cuh"
+#include "../../oracle/filo_query.hpp"
+#include <memory>
+#include <random>
+
+struct Chunk { std::vector<uint8_t> ts, vv, info; };
+struct SeriesData { std::vector<std::unique_ptr<Chunk>> chunks; std::vector<uint8_t> record; };
+
+static void build_series(SeriesData& S, std::mt19937_64& rng, int rows, const std::vector<int>& chunk_rows, int64_t t0, int step_ms, int kind /*0 gauge 1 counter*/,
+                         bool xor_enc, int nan_ppm, int reset_every) {
+  std::vector<int64_t> ts((size_t)rows); std::vector<double> v((size_t)rows);
+  std::normal_distribution<double> N(0.0, 1.0);
+  double acc = 0.0;
+  for (int r = 0; r < rows; ++r) {
+    ts[(size_t)r] = t0 + (int64_t)r * step_ms;
+    const double g = 15.0 + std::sin((double)(r + 1)) + N(rng);
+    if (kind == 0) v[(size_t)r] = g;
+    else { if (reset_every && r > 0 && rng() % (uint64_t)reset_every == 0) acc = 0.0; acc += g > 0 ? g : 0.0; v[(size_t)r] = acc; }
+  }
+  int r0 = 0;
+  for (int n : chunk_rows) {
+    auto c = std::make_unique<Chunk>();
+    std::vector<double> cv(v.begin() + r0, v.begin() + r0 + n);
+    if (nan_ppm && (int)(rng() % 1000000) < nan_ppm) cv[(size_t)n - 1] = std::nan("");          // stale marker at the chunk end
+    c->ts = fo::enc::timestamps(ts.data() + r0, n);
+    c->vv = xor_enc ? fo::enc::doublesXor(cv.data(), n, kind == 1) : fo::enc::doubles(cv.data(), n, kind == 1);
+    c->info.assign(fo::csi::OffsetVectors + 16, 0);
+    fo::setLong(c->info.data() + fo::csi::OffsetChunkID, fo::csi::chunkID(ts[(size_t)r0], (ts[(size_t)(r0 + n - 1)] + 1000) / 1000));
+    fo::setInt(c->info.data() + fo::csi::OffsetNumRows, n);
+    fo::setLong(c->info.data() + fo::csi::OffsetIngestionTime, ts[(size_t)(r0 + n - 1)] + 1000);
+    fo::setLong(c->info.data() + fo::csi::OffsetEndTime, ts[(size_t)(r0 + n - 1)]);
+    fo::setLong(c->info.data() + fo::csi::OffsetVectors, (int64_t)(uintptr_t)c->ts.data());
+    fo::setLong(c->info.data() + fo::csi::OffsetVectors + 8, (int64_t)(uintptr_t)c->vv.data());
+    S.chunks.push_back(std::move(c));
+    r0 += n;
+  }
+  // arena record (filo_record.h), as filo_load_series writes it
+  const size_t nch = S.chunks.size();
+  const size_t off = sizeof(filo::RecordHeader) + nch * sizeof(filo::ChunkEntry);
+  std::vector<filo::ChunkEntry> E(nch); std::vector<uint8_t> body; uint32_t row_base = 0, flags = filo::REC_ALL_TS_CONST;
+  for (size_t i = 0; i < nch; ++i) {
+    Chunk& c = *S.chunks[i];
+    E[i].start_time = fo::csi::startTime(c.info.data()); E[i].end_time = fo::csi::endTime(c.info.data()); E[i].num_rows = fo::csi::numRows(c.info.data());
+    auto put = [&](const std::vector<uint8_t>& x) { while ((off + body.size()) % 8) body.push_back(0); const uint32_t o = (uint32_t)(off + body.size()); body.insert(body.end(), x.begin(), x.end()); return o; };
+    E[i].ts_off = put(c.ts); E[i].val_off = put(c.vv); E[i].row_base = row_base;
+    const int twire = (int)(c.ts[4] | (c.ts[5] << 8)), vwire = (int)(c.vv[4] | (c.vv[5] << 8));
+    if (twire != filo::WIRE_DDV_CONST) flags &= ~filo::REC_ALL_TS_CONST;
+    if (c.vv[7] & 0x80) flags |= filo::REC_ANY_DROP;
+    if (vwire == filo::WIRE_XOR || vwire == filo::WIRE_DDV || vwire == filo::WIRE_DDV_CONST) flags |= filo::REC_ANY_DECODE;
+    uint32_t vlen = (uint32_t)E[i].num_rows;
+    row_base += vlen;
+  }
+  size_t total = off + body.size(); total = (total + 15) & ~(size_t)15;
+  S.record.assign(total, 0);
+  filo::RecordHeader h; h.rec_bytes = (uint32_t)total; h.n_chunks = (uint32_t)nch; h.n_rows = row_base; h.flags = flags;
+  std::memcpy(S.record.data(), &h, sizeof h);
+  std::memcpy(S.record.data() + sizeof h, E.data(), nch * sizeof(filo::ChunkEntry));
+  std::memcpy(S.record.data() + off, body.data(), body.size());
+}
+
+static bool same_bits(double a, double b) { uint64_t x, y; std::memcpy(&x, &a, 8); std::memcpy(&y, &b, 8); return x == y || (a != a && b != b); }
+
+struct Launch {
+  const uint8_t* arena; const int64_t* rec_off; int64_t S; filo::QueryParams q; double* out; filo::TileSmem L; int grid;
+  int64_t* flist; unsigned long long* fcount; unsigned long long* counters; int* derr;
+  const int32_t* order; const int64_t* item_begin; int64_t n_items; int agg_op; double* pval; uint32_t* pcnt;
+};
+template <int CLS, int FN, bool AGG> static void run_kernel(const Launch& A) {
+  cusim::launch(dim3((unsigned)A.grid), dim3(filo::TILE_LAUNCH_THREADS), [&] {
+    filo::scan_tile_kernel<CLS, FN, AGG>(A.arena, A.rec_off, A.S, A.q, A.out, A.L, A.flist, A.fcount, A.counters, A.derr, A.order, A.item_begin, A.n_items, A.agg_op, A.pval, A.pcnt);
+  });
+}
+template <bool AGG> static void dispatch(const Launch& A) {          // the instantiations launch_tile_any makes (scan_kernels.cu)
+  const int fn = A.q.fn;
+  if (filo::fn_class_of(fn, A.q.cumulative) == filo::CLASS_COUNTER) {
+    if (fn == filo::FN_RATE) run_kernel<filo::CLASS_COUNTER, filo::FN_RATE, AGG>(A);
+    else if (fn == filo::FN_INCREASE) run_kernel<filo::CLASS_COUNTER, filo::FN_INCREASE, AGG>(A);
+    else run_kernel<filo::CLASS_COUNTER, filo::FN_DELTA, AGG>(A);
+  } else if (fn == filo::FN_RATE) run_kernel<filo::CLASS_SUM, filo::FN_RATE, AGG>(A);
+  else if (fn == filo::FN_AVG) run_kernel<filo::CLASS_SUM, filo::FN_AVG, AGG>(A);
+  else if (fn == filo::FN_COUNT) run_kernel<filo::CLASS_SUM, filo::FN_COUNT, AGG>(A);
+  else run_kernel<filo::CLASS_SUM, filo::FN_SUM, AGG>(A);
+}
+static fo::RangeFn oracle_fn(int fn) {
+  switch (fn) { case filo::FN_SUM: return fo::FN_SUM_OVER_TIME; case filo::FN_AVG: return fo::FN_AVG_OVER_TIME; case filo::FN_COUNT: return fo::FN_COUNT_OVER_TIME; default: return (fo::RangeFn)fn; }
+}
+
+int main(int argc, char** argv) {
+  const uint64_t seed = argc > 1 ? std::strtoull(argv[1], nullptr, 10) : 0;
+  cusim::rng_state() = seed;
+  std::mt19937_64 rng(4242);
+  long checked = 0; int cases = 0;
+  struct Cfg { int kind; bool xor_enc; int fn; std::vector<int> chunks; int nan_ppm, reset_every; int64_t window; int nser; int inclusive; int64_t start_off, end_off; int agg_op; int grid; };
+  const std::vector<Cfg> cfgs = {
+    {0, true, filo::FN_RATE, {400, 80}, 200000, 0, 300000, 11, 1, 0, 0, 0, 2},           // C2: gauge, delta-temporality rate (CLASS_SUM), NaN stale markers
+    {0, true, filo::FN_SUM, {150, 90}, 0, 0, 300000, 37, 1, -90000, 45000, 0, 2},        // several tiles per CTA, a partial last tile, windows before / after the data
+    {0, false, filo::FN_AVG, {200, 40}, 100000, 0, 120000, 5, 0, 0, 0, 0, 1},             // raw f64 vectors, exclusive range start
+    {0, true, filo::FN_COUNT, {60, 60, 60, 60}, 300000, 0, 600000, 9, 1, 30000, 0, 0, 3}, // four chunks, long windows over several chunk junctions
+    {0, true, filo::FN_RATE, {100, 50, 50, 50, 50}, 0, 0, 300000, 10, 1, 0, 0, 0, 2},     // five chunks: declined (fallback list)
+    {1, true, filo::FN_RATE, {400, 80}, 0, 0, 300000, 10, 1, 0, 0, 0, 2},                 // counters: extrapolated rate (CLASS_COUNTER)
+    {1, true, filo::FN_INCREASE, {120, 120, 60}, 0, 41, 60000, 19, 1, -30000, 30000, 0, 2}, // resets: drop-flagged chunks, corrections across chunks
+    {1, false, filo::FN_DELTA, {200, 100}, 0, 0, 300000, 6, 0, 0, 0, 0, 1},               // delta over raw vectors
+    {0, true, filo::FN_RATE, {400, 80}, 100000, 0, 300000, 26, 1, 0, 0, filo::AGG_SUM, 2},   // fused sum: items of 5 series in shuffled order
+    {1, true, filo::FN_RATE, {240, 240}, 0, 97, 300000, 17, 1, 0, 0, filo::AGG_MAX, 2},      // fused max over counters with resets
+  };
+  for (size_t ci = 0; ci < cfgs.size(); ++ci) {
+    const Cfg& c = cfgs[ci];
+    int rows = 0; for (int n : c.chunks) rows += n;
+    const int64_t t0 = 1700000000000LL; const int step_ms = 15000;
+    std::vector<SeriesData> SS((size_t)c.nser);
+    std::vector<int64_t> rec_off((size_t)c.nser + 1, 0);
+    for (int s = 0; s < c.nser; ++s) { build_series(SS[(size_t)s], rng, rows, c.chunks, t0, step_ms, c.kind, c.xor_enc, c.nan_ppm, c.reset_every); rec_off[(size_t)s + 1] = rec_off[(size_t)s] + (int64_t)SS[(size_t)s].record.size(); }
+    std::vector<uint64_t> arena_backing((size_t)rec_off.back() / 8 + 64, 0);
+    uint8_t* arena = reinterpret_cast<uint8_t*>(arena_backing.data());
+    uint32_t max_rec = 0;
+    for (int s = 0; s < c.nser; ++s) { std::memcpy(arena + rec_off[(size_t)s], SS[(size_t)s].record.data(), SS[(size_t)s].record.size()); max_rec = std::max<uint32_t>(max_rec, (uint32_t)SS[(size_t)s].record.size()); }
+    filo::QueryParams q{};
+    q.start = t0 + c.start_off; q.step = 15000; q.end = t0 + (int64_t)(rows - 1) * step_ms + c.end_off; q.window = c.window; q.T = (int)((q.end - q.start) / q.step) + 1;
+    q.fn = c.fn; q.cumulative = c.kind == 1; q.inclusive = c.inclusive;
+    const bool ctr = filo::fn_class_of(q.fn, q.cumulative) == filo::CLASS_COUNTER;
+    const uint32_t wrows = (uint32_t)(q.window / q.step) + 1;
+    const filo::TileSmem L = filo::tile_layout(max_rec, (uint32_t)rows, (uint32_t)q.T, ctr ? 0u : 2 * wrows + 16, ctr);
+    if (L.total > sizeof(filo::smem)) { std::printf("FAIL: layout %u bytes\n", L.total); return 1; }
+    // oracle, per series
+    std::vector<double> ref((size_t)c.nser * q.T);
+    for (int s = 0; s < c.nser; ++s) {
+      fo::Series os; for (auto& ch : SS[(size_t)s].chunks) os.infos.push_back(ch->info.data());
+      fo::periodicSamples(os, oracle_fn(q.fn), q.cumulative != 0, q.start, q.step, q.end, q.window, fo::QueryConfig{q.inclusive != 0}, ref.data() + (size_t)s * q.T, nullptr);
+    }
+    std::vector<double> out((size_t)c.nser * q.T, -777.0);
+    std::vector<int64_t> flist((size_t)c.nser + 8, -1); unsigned long long fcount = 0, counters[2] = {0, 0}; int derr[4] = {0, 0, 0, 0};
+    Launch A{arena, rec_off.data(), c.nser, q, out.data(), L, c.grid, flist.data(), &fcount, counters, derr, nullptr, nullptr, 0, 0, nullptr, nullptr};
+    if (!c.agg_op) {
+      dispatch<false>(A);
+      if (derr[0]) { std::printf("FAIL cfg %zu: device error %d\n", ci, derr[0]); return 1; }
+      std::vector<char> fell((size_t)c.nser, 0);
+      for (unsigned long long i = 0; i < fcount; ++i) fell[(size_t)flist[(size_t)i]] = 1;
+      int64_t exp_rows = 0;
+      for (int s = 0; s < c.nser; ++s) {
+        if (fell[(size_t)s]) continue;                                  // declined by the tile kernel: the fallback kernel owns it
+        exp_rows += rows;
+        for (int k = 0; k < q.T; ++k) {
+          const double a = out[(size_t)s * q.T + k], r = ref[(size_t)s * q.T + k];
+          if (!same_bits(a, r)) { std::printf("FAIL cfg %zu series %d window %d: %.17g vs %.17g\n", ci, s, k, a, r); return 1; }
+          ++checked;
+        }
+      }
+      if ((int64_t)counters[0] != exp_rows) { std::printf("FAIL cfg %zu: samples_scanned %llu vs %lld\n", ci, counters[0], (long long)exp_rows); return 1; }
+      if (c.chunks.size() > (size_t)filo::TILE_MAXC && fcount != (unsigned long long)c.nser) { std::printf("FAIL cfg %zu: series with too many chunks were not declined\n", ci); return 1; }
+      std::printf("cfg %zu ok: %d series (%llu to the fallback list), T=%d\n", ci, c.nser, fcount, q.T);
+    } else {
+      // items of <= 5 series in a shuffled order (what build_groups produces for one group)
+      std::vector<int32_t> order((size_t)c.nser); for (int s = 0; s < c.nser; ++s) order[(size_t)s] = s;
+      std::shuffle(order.begin(), order.end(), rng);
+      std::vector<int64_t> item_begin; for (int64_t p = 0; p < c.nser; p += 5) item_begin.push_back(p); item_begin.push_back(c.nser);
+      const int64_t n_items = (int64_t)item_begin.size() - 1;
+      std::vector<double> pval((size_t)n_items * q.T, -777.0); std::vector<uint32_t> pcnt((size_t)n_items * q.T, 12345u);
+      A.order = order.data(); A.item_begin = item_begin.data(); A.n_items = n_items; A.agg_op = c.agg_op; A.pval = pval.data(); A.pcnt = pcnt.data(); A.out = nullptr;
+      dispatch<true>(A);
+      if (derr[0]) { std::printf("FAIL cfg %zu: device error %d\n", ci, derr[0]); return 1; }
+      std::vector<char> fell((size_t)n_items, 0);
+      for (unsigned long long i = 0; i < fcount; ++i) fell[(size_t)flist[(size_t)i]] = 1;
+      for (int64_t it = 0; it < n_items; ++it) {
+        if (fell[(size_t)it]) continue;
+        for (int k = 0; k < q.T; ++k) {
+          double a = c.agg_op == filo::AGG_MIN ? INFINITY : c.agg_op == filo::AGG_MAX ? -INFINITY : 0.0; uint32_t n = 0;
+          for (int64_t p = item_begin[(size_t)it]; p < item_begin[(size_t)it + 1]; ++p) {
+            const double v = ref[(size_t)order[(size_t)p] * q.T + k];
+            if (v == v) { if (c.agg_op == filo::AGG_MIN) a = v < a ? v : a; else if (c.agg_op == filo::AGG_MAX) a = v > a ? v : a; else if (c.agg_op != filo::AGG_COUNT) a += v; ++n; }
+          }
+          if (!same_bits(pval[(size_t)it * q.T + k], a) || pcnt[(size_t)it * q.T + k] != n) { std::printf("FAIL cfg %zu item %lld window %d: %.17g (%u) vs %.17g (%u)\n", ci, (long long)it, k, pval[(size_t)it * q.T + k], pcnt[(size_t)it * q.T + k], a, n); return 1; }
+          ++checked;
+        }
+      }
+      std::printf("cfg %zu ok: %d series in %lld items (%llu to the fallback list), T=%d\n", ci, c.nser, (long long)n_items, fcount, q.T);
+    }
+    ++cases;
+  }
+  std::printf("OK %d cases, %ld values bit-exact (schedule seed %llu)\n", cases, checked, (unsigned long long)seed);
+  return 0;
+}

@@ -100,3 +100,18 @@ def test_hist_scan2_phases_match_oracle_on_cpu(tmp_path):
     8 / 20 / 33 buckets, several series folded into one partial row; bit-exact against the oracle (tests/cpp/hist_emul.cpp)."""
     out = _build_and_run_cpp(tmp_path, "hist_emul")
     assert out.startswith("OK 72 cases") and "bit-exact" in out
+
+
+def test_tile_kernel_runs_on_the_simt_emulator(tmp_path):
+    """scan_tile_kernel itself (filodb_b200/csrc/scan_tile.cuh: producer warp, TMA + mbarriers, named barriers, warp shuffles) compiled
+    for the host on the cusim fiber emulator (tests/cpp/cusim.h) and checked bit-exact against the oracle: SUM-class and counter-class
+    functions, raw and XOR vectors, 2-5 chunks, NaN markers, counter resets, several tiles per CTA, the fused aggregate mode; under the
+    in-order schedule and a pseudo-random one.  The emulator aborts on deadlocks and on warp collectives reached from different call
+    sites, and performs bulk copies as late as the program allows."""
+    import subprocess
+    exe = str(tmp_path / "tile_emul")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes", "-I", "/usr/local/cuda/include",
+                    os.path.join(ROOT, "tests", "cpp", "tile_emul.cpp"), "-o", exe], check=True)
+    for seed in ("0", "20260922"):
+        out = subprocess.run([exe, seed], check=True, capture_output=True, text=True).stdout
+        assert "OK 10 cases" in out and "bit-exact" in out, out
