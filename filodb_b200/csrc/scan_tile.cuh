@@ -477,9 +477,11 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         const uint32_t numBits = ((hdr >> 4) + 1) * 4;
         const uint32_t tz = (hdr & 0x0f) * 4;
         const uint64_t fmask = ~0ull >> (64 - numBits);
-        const uintptr_t a0 = reinterpret_cast<uintptr_t>(gp + 2);
-        uint32_t bit = (uint32_t)(a0 & 3) * 8;
-        const uint32_t* base = reinterpret_cast<const uint32_t*>(a0 & ~(uintptr_t)3);
+        // word-aligned base of the group's fields, derived by pointer arithmetic from the staging buffer so that the loads stay in the
+        // shared window (an integer round trip made them generic loads)
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(gp + 2) & 3);
+        uint32_t bit = mis * 8;
+        const uint32_t* base = reinterpret_cast<const uint32_t*>(gp + 2 - mis);
         uint64_t x = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
