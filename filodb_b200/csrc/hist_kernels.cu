@@ -78,6 +78,19 @@ __device__ __forceinline__ int64_t ts_of(const uint8_t* tv, int twire, int r) {
   return (int64_t)ld64(tv + 8) + (int64_t)(int32_t)ld32(tv + 16) * r + (int64_t)int_apply(in, (iw >> 16) & 0x7f, (iw >> 23) & 1, r);
 }
 
+// Per-phase cycle counters of hist_scan_kernel for profiling builds (-DFILO_HIST_PROF; scratch/hist_prof.py, profiles/r1_c4_hist_phases.md).
+// Compiled out of the product build.
+#ifdef FILO_HIST_PROF
+__device__ unsigned long long g_hist_prof[16];
+#define HPROF_DECL long long hp_t0 = clock64(), hp_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define HPROF(i) { const long long hp_t1 = clock64(); hp_acc[i] += hp_t1 - hp_t0; hp_t0 = hp_t1; }
+#define HPROF_FLUSH if (threadIdx.x == 0) { for (int hp_i = 0; hp_i < 12; ++hp_i) atomicAdd(&g_hist_prof[hp_i], (unsigned long long)hp_acc[hp_i]); atomicAdd(&g_hist_prof[15], 1ull); }
+#else
+#define HPROF_DECL
+#define HPROF(i)
+#define HPROF_FLUSH
+#endif
+
 struct HistLayout { uint32_t cv, ts, pt, pd, tot, lastraw, win, acc, any, sect, rec, total; };
 __host__ __device__ inline HistLayout hist_layout(int max_rows, int nb, int T, bool agg, uint32_t max_rec) {
   HistLayout L; uint32_t o = 0;
@@ -128,6 +141,7 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
   const bool sum_mode = q.fn == FN_SUM || !q.cumulative;
   const double fdiv = (double)(q.inclusive ? winDur : winDur + 1), frcp = 1.0 / fdiv;       // windowEnd - curWindowStart
 
+  HPROF_DECL
   for (int64_t it = blockIdx.x; it < n_work; it += gridDim.x) {
     const int64_t pb = agg ? item_begin[it] : it, pe = agg ? item_begin[it + 1] : it + 1;
     if (agg) { for (int i = tid; i < q.T * nb; i += HIST_THREADS) acc[i] = 0.0; for (int i = tid; i < q.T; i += HIST_THREADS) any[i] = 0; }
@@ -141,6 +155,7 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         for (uint32_t i = tid; i < (rb >> 4); i += HIST_THREADS) dst[i] = src[i];
       }
       __syncthreads();
+      HPROF(0)                                             // record staged
       const uint8_t* rec = smem + L.rec;
       const RecordHeader* h = reinterpret_cast<const RecordHeader*>(rec);
       const ChunkEntry* E = reinterpret_cast<const ChunkEntry*>(rec + sizeof(RecordHeader));
@@ -185,6 +200,7 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         if (err) { if (atomicCAS(&d_err[0], 0, err) == 0) { d_err[1] = (int)(sid & 0x7fffffff); d_err[2] = (int)(sid >> 31); } }
       }
       __syncthreads();
+      HPROF(1)                                             // chunk range + section tables (thread 0)
       const int n = s_n, nsect = s_nsect, rows = s_rows, cLo = s_cLo;
       bool bad = false;
       // ---- timestamps of every row + section base histograms
@@ -196,6 +212,7 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
       }
       for (int si = tid; si < nsect; si += HIST_THREADS) decode_record(rec + SE[si].first_rec, nb, nullptr, cv + (size_t)SE[si].start_row * nb, bad);
       __syncthreads();
+      HPROF(2)                                             // timestamps + section bases
       // ---- remaining rows: delta from the section's first histogram (SectDeltaHistogramReader.apply, :646-666)
       for (int r = tid; r < rows; r += HIST_THREADS) {
         int si = 0; while (si + 1 < nsect && r >= SE[si + 1].start_row) ++si;
@@ -207,6 +224,7 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
       }
       if (bad) { if (atomicCAS(&d_err[0], 0, 1) == 0) { d_err[1] = (int)(sid & 0x7fffffff); d_err[2] = (int)(sid >> 31); } }
       __syncthreads();
+      HPROF(3)                                             // remaining rows decoded
       if (sum_mode) {
         // per-bucket running sums over the rows of each chunk (int64, exact): the reference adds the rows as doubles
         // (RowHistogramReader.sum, HistogramVector.scala:613-621), which is the same number while the sums stay below 2^53
@@ -266,6 +284,7 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         TOT[c * nb + b] = run; LASTRAW[c * nb + b] = prev_raw;
       }
       __syncthreads();
+      HPROF(4)                                             // in-chunk corrections
       // ---- corrections carried across chunks: detectDropAndCorrection (:673-686, Histogram.compare Histogram.scala:197-208) adds the
       //      previous chunk's last raw histogram when this chunk's first one compares lower; updateCorrection (:717-728) adds the
       //      chunk's own total.  carried(a, c) = (PT[c] - PT[a]) + (PD[c] - PD[a]) for a window whose chunk set starts at a.
@@ -326,6 +345,7 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         W[k] = w;
       }
       __syncthreads();
+      HPROF(5)                                             // carried corrections + window descriptors
       // ---- one thread per (window, bucket): extrapolatedRate on the corrected bucket values (HistogramRateFunctionBase.apply, :366-407)
       for (int i = tid; i < q.T * nb; i += HIST_THREADS) {
         const int k = i / nb, b = i - k * nb;
@@ -353,14 +373,17 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         }
       }
       __syncthreads();
+      HPROF(6)                                             // (window, bucket) rates
     }
     if (agg) {
       double* pv = pval + (size_t)it * q.T * nb; uint8_t* pa = pany + (size_t)it * q.T;
       for (int i = tid; i < q.T * nb; i += HIST_THREADS) pv[i] = acc[i];
       for (int i = tid; i < q.T; i += HIST_THREADS) pa[i] = any[i];
       __syncthreads();
+      HPROF(7)                                             // item partial written
     }
   }
+  HPROF_FLUSH
   if (rows_scanned | bytes_scanned) { atomicAdd(&d_counters[0], (unsigned long long)rows_scanned); atomicAdd(&d_counters[1], (unsigned long long)bytes_scanned); }
 }
 
@@ -409,6 +432,14 @@ __global__ void hist_merge_kernel(const double* __restrict__ pval, const uint8_t
   if (out_values) for (int b = 0; b < nb; ++b) out_values[(size_t)i * nb + b] = any ? v[b] : NaNv;
   if (out_q) out_q[i] = qv;
 }
+
+#ifdef FILO_HIST_PROF
+extern "C" int filo_debug_hist_prof(unsigned long long* out16, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out16, g_hist_prof, sizeof(unsigned long long) * 16);
+  if (e == cudaSuccess && reset) { unsigned long long z[16] = {}; e = cudaMemcpyToSymbol(g_hist_prof, z, sizeof z); }
+  return (int)e;
+}
+#endif
 
 size_t hist_smem_bytes(int max_rows, int nb, int T, bool agg, uint32_t max_rec) { return hist_layout(max_rows, nb, T, agg, max_rec).total; }
 cudaError_t launch_hist_scan(const ScanLaunch& L, int nb, int max_rows, uint32_t max_rec, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg,

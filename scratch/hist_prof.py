@@ -11,6 +11,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import filodb_b200.capi as capi
 capi.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfilo_b200_prof.so")
+os.environ["FILO_HIST_V2"] = "0"          # the hooks live in the first kernel
 from oracle import hist as H
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 400
