@@ -20,6 +20,8 @@
 namespace filo {
 
 #ifdef FILO_CUSIM
+#define FILO_NOINLINE __attribute__((noinline))
+inline long cusim_junction_blocks = 0, cusim_rest_windows = 0;
 inline void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes) { cusim::tma_store(gdst, ssrc, bytes); }
 inline void tma_store_wait_read() { cusim::tma_store_wait_read(); }
 inline void fence_async_smem() {}
@@ -30,6 +32,7 @@ __device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint3
 }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#define FILO_NOINLINE __noinline__
 #endif
 
 // compile-time specialised finish of one single-chunk window (SumFinish of scan_fast.cuh with FN known)
@@ -165,6 +168,52 @@ __device__ __forceinline__ double tile_eval_counter(const TileSeries& S, const T
   const int64_t cws = q.inclusive ? wStart : wStart - 1;               // RateFunctions.scala:270-285
   if (hiT > loT) return extrapolated_rate_tile<FN != FN_DELTA, FN == FN_RATE>(cws, wEnd, numSamples, loT, loV, hiT, hiV, fdiv, frcp, q.step, tab);
   return NaNv;
+}
+
+// One block of BLK_R windows of the junction between chunk c-1 and chunk c of a regular series (SUM class): each window's rows lie
+// in those two chunks only, both are members of its chunk set (the producer checked), so the window is the per-chunk fold of
+// tile_eval_window with the two chunk sums computed BLK_R windows at a time.  A tile with NaN / Inf rows takes the literal fold.
+template <int FN>
+__device__ FILO_NOINLINE void tile_junction_block(const TileSeries& S, int c, const double* sv, double* orow, int jb, bool any_nan, const QueryParams& q,
+                                                 int64_t winDur, double fdiv, double frcp) {
+  const TileChunk& cb = S.c[c]; const TileChunk& ca = S.c[c - 1];
+#ifdef FILO_CUSIM
+  ++cusim_junction_blocks;          // emulation statistics (tests/cpp/tile_emul.cpp)
+#endif
+  const int k0 = cb.jk0 + jb * BLK_R;
+  int nw = cb.jk0 + cb.jn - k0; if (nw > BLK_R) nw = BLK_R;
+  double* o = orow + k0;
+  if (any_nan) {
+    for (int j = 0; j < nw; ++j) {
+      const int64_t wEnd = q.start + (int64_t)(k0 + j) * q.step;
+      o[j] = tile_eval_window<FN, true>(S, sv, wEnd - winDur, wEnd, fdiv, k0 + j);
+    }
+    return;
+  }
+  const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
+  double acc[BLK_R]; int cnt[BLK_R];
+  blocked_sum<false, true, true>(sv + ca.row_base, ca.s0 + k0, ca.nrows, ca.Wr, acc, cnt);
+#pragma unroll
+  for (int j = 0; j < BLK_R; ++j) if (j < nw) o[j] = acc[j];         // chunk c-1's sums wait in the window's own output slot
+  blocked_sum<false, true, true>(sv + cb.row_base, cb.s0 + k0, cb.nrows, cb.Wr, acc, cnt);
+#pragma unroll
+  for (int j = 0; j < BLK_R; ++j) {
+    if (j < nw) {
+      int lo = ca.s0 + k0 + j; if (lo < 0) lo = 0;
+      int hi = ca.s0 + k0 + j + ca.Wr; if (hi > ca.nrows - 1) hi = ca.nrows - 1;
+      const int na = hi >= lo ? hi - lo + 1 : 0, nb = cnt[j];
+      double sum = NaNv;                                              // AggrOverTimeFunctions.scala:560-571, chunk by chunk
+      if (na) { sum = 0.0; sum += o[j]; }
+      if (nb) { if (sum != sum) sum = 0.0; sum += acc[j]; }
+      const int nn = na + nb;
+      double r;
+      if (FN == FN_RATE) r = __dmul_rn(div_invariant(sum, fdiv, frcp), 1000.0);
+      else if (FN == FN_AVG) r = nn > 0 ? sum / (double)nn : (sum != sum ? sum : 0.0);
+      else if (FN == FN_COUNT) r = nn > 0 ? (double)nn : NaNv;
+      else r = sum;
+      o[j] = r;
+    }
+  }
 }
 
 __device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) { return (uint64_t)__shfl_sync(0xffffffffu, (unsigned long long)v, src); }
@@ -327,6 +376,25 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
       // COUNTER: work item = one window of the interval (needs two samples: Wr >= 1)
       const bool blocked = ok && Wr >= (CLS == CLASS_COUNTER ? 1 : BLK_R - 1);
       const int nb = !blocked ? 0 : (CLS == CLASS_COUNTER ? nwin : (nwin + BLK_R - 1) / BLK_R);
+      // SUM class: junction with the previous chunk.  The windows between the two blocked intervals take rows from both chunks;
+      // they go through two blocked partial sums instead of the per-window fold when (a) both chunks are members of every such
+      // window's chunk set (ChunkSetInfo.scala:481-510) and (b) no other chunk has a row in them
+      int jk0 = 0, jn = 0, jb = 0;
+      {
+        const int blocked_p = __shfl_up_sync(0xffffffffu, blocked ? 1 : 0, 1);
+        const int64_t kBp = __shfl_up_sync(0xffffffffu, kB, 1);
+        const int64_t s0pp = __shfl_up_sync(0xffffffffu, s0, 2), endpp = __shfl_up_sync(0xffffffffu, end_time, 2);
+        const int nrowspp = __shfl_up_sync(0xffffffffu, nrows, 2);
+        if (CLS == CLASS_SUM && c > 0 && blocked && blocked_p) {
+          const int64_t gapA = kBp + 1, gapB = kA - 1, n_gap = gapB - gapA + 1;
+          const int64_t wStartB = S0 + gapB * q.step, wEndA = E0 + gapA * q.step;
+          bool okj = n_gap >= 1 && n_gap <= 2 * BLK_R;
+          okj = okj && !(endp < wStartB) && endp < wEndA && !(end_time < wStartB);                 // both chunks in the chunk set of every gap window
+          if (c >= 2) okj = okj && endpp < wEndA && s0pp + gapA > (int64_t)nrowspp - 1;             // chunk c-2: out of the rows
+          if (c + 1 < n) okj = okj && e0n + gapB < 0;                                               // chunk c+1: not reached yet
+          if (okj) { jk0 = (int)gapA; jn = (int)n_gap; jb = (jn + BLK_R - 1) / BLK_R; }
+        }
+      }
       // zero rows around the chunk so that blocked sums read clamped-away rows as +0.0 without a bounds check
       int lowz = 0, highz = 0;
       if (blocked && CLS == CLASS_SUM) {
@@ -341,7 +409,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
       const int row_base = xpre(lowz + nrows + highz, nrows_tot) + lowz;
       if (ngroups > TILE_MAXG || nrows_tot + 2 > (int)L.vals_pitch) { regular = false; have = false; }
       int nblocks = 0, covered = 0;
-      const int blk0 = xpre(have ? nb : 0, nblocks); (void)xpre(have && blocked ? nwin : 0, covered);
+      const int blk0 = xpre(have ? nb + jb : 0, nblocks); (void)xpre(have && blocked ? nwin + jn : 0, covered);
       int cnt_rows = 0, cnt_bytes = 0;            // this chunk's contribution to the scan counters
       if (have) {
         TileChunk& ch = S.c[c];
@@ -349,6 +417,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         ch.val_off = voff; ch.wire = vwire; ch.ngroups = ng; ch.grp_base = grp_base; ch.tlen = tlen; ch.vlen = vlen;
         ch.kA2 = (have && kA2 <= kB2) ? (int)kA2 : 0; ch.kB2 = (have && kA2 <= kB2) ? (int)kB2 : -1;
         ch.kA = blocked ? (int)kA : 0; ch.kB = blocked ? (int)kB : -1; ch.sA = (int)sA; ch.Wr = Wr; ch.blk0 = blk0; ch.blk_n = nb;
+        ch.jk0 = jk0; ch.jn = jn; ch.jblk = jb; ch.kAj = jb ? jk0 : ch.kA;
         ch.s0 = (int)s0; ch.e0 = (int)e0;
         if (vwire == WIRE_XOR) {
           const uint32_t po = w12 >> 16;
@@ -689,9 +758,13 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         for (int j = 1; j < TILE_NS; ++j) if (it >= Mc->pref[j]) s = j;
         const TileSeries& S = SDc[s];
         const int B = it - Mc->pref[s];
-        int c = 0; while (c + 1 < S.n && B >= S.c[c].blk0 + S.c[c].blk_n) ++c;
+        int c = 0; while (c + 1 < S.n && B >= S.c[c].blk0 + S.c[c].blk_n + S.c[c].jblk) ++c;
         const TileChunk& ch = S.c[c];
         const int b = B - ch.blk0;
+        if (b >= ch.blk_n) {                       // a block of the junction with the previous chunk
+          tile_junction_block<FN>(S, c, vals + (size_t)s * L.vals_pitch, otile + (size_t)s * L.out_pitch, b - ch.blk_n, any_nan, q, winDur, fdiv, frcp);
+          continue;
+        }
         const int r0 = ch.sA + b * BLK_R;
         const double* slots = vals + (size_t)s * L.vals_pitch + ch.row_base;
         double acc[BLK_R]; int cnt[BLK_R];
@@ -741,10 +814,13 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         int prev = -1; bool found = false;          // u-th window not covered by a blocked interval
         for (int c = 0; c < S.n && !found; ++c) {
           if (S.c[c].kA > S.c[c].kB) continue;
-          const int gap = S.c[c].kA - prev - 1;
+          const int gap = S.c[c].kAj - prev - 1;
           if (u < gap) found = true; else { u -= gap; prev = S.c[c].kB; }
         }
         const int k = prev + 1 + u;
+#ifdef FILO_CUSIM
+        ++cusim_rest_windows;
+#endif
         const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - winDur;
         const double* sv = vals + (size_t)s * L.vals_pitch;
         if (CLS == CLASS_COUNTER) otile[(size_t)s * L.out_pitch + k] = tile_eval_counter<FN>(S, CTc + s * TILE_MAXC, DRc + s * TILE_MAXC, sv, q, wStart, wEnd, k, fdiv, frcp, CTAB);

@@ -27,6 +27,10 @@ struct TileChunk {
   int32_t s0, e0;             // unclamped first / last row of window k = 0 (rows advance by one per window)
   int32_t lowz, highz;        // zero rows before / after the chunk's rows (clamped windows read them as +0.0)
   int32_t kA2, kB2;           // COUNTER: all single-chunk windows of the chunk, clamped ones included ([kA, kB] = unclamped)
+  // SUM class: the windows between the previous chunk's blocked interval and this chunk's (rows in both chunks) are folded as
+  // blocks of two partial sums when nothing else can contribute to them: jn windows from jk0 in jblk blocks; kAj = first window
+  // covered by a block of this chunk (jk0, or kA without a junction)
+  int32_t jk0, jn, jblk, kAj;
 };
 struct TileSeries {
   int32_t n, regular, rec_off, nblocks, nrest, ngroups, nrows, any_raw;

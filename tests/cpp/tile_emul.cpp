@@ -105,6 +105,9 @@ int main(int argc, char** argv) {
     {0, false, filo::FN_AVG, {200, 40}, 100000, 0, 120000, 5, 0, 0, 0, 0, 1},             // raw f64 vectors, exclusive range start
     {0, true, filo::FN_COUNT, {60, 60, 60, 60}, 300000, 0, 600000, 9, 1, 30000, 0, 0, 3}, // four chunks, long windows over several chunk junctions
     {0, true, filo::FN_RATE, {100, 50, 50, 50, 50}, 0, 0, 300000, 10, 1, 0, 0, 0, 2},     // five chunks: declined (fallback list)
+    {0, true, filo::FN_AVG, {100, 100, 100}, 30000, 0, 300000, 24, 1, 0, 0, 0, 2},        // two junctions per series, NaN rows in some tiles only
+    {0, true, filo::FN_COUNT, {90, 70, 50, 30}, 0, 0, 240000, 16, 0, 15000, 0, 0, 2},     // three junctions, exclusive range start, a chunk barely longer than the window
+    {0, false, filo::FN_SUM, {64, 200}, 0, 0, 420000, 9, 1, 0, 0, 0, 1},                  // raw vectors, 29-window junction (two blocks)
     {1, true, filo::FN_RATE, {400, 80}, 0, 0, 300000, 10, 1, 0, 0, 0, 2},                 // counters: extrapolated rate (CLASS_COUNTER)
     {1, true, filo::FN_INCREASE, {120, 120, 60}, 0, 41, 60000, 19, 1, -30000, 30000, 0, 2}, // resets: drop-flagged chunks, corrections across chunks
     {1, false, filo::FN_DELTA, {200, 100}, 0, 0, 300000, 6, 0, 0, 0, 0, 1},               // delta over raw vectors
@@ -155,7 +158,8 @@ int main(int argc, char** argv) {
       }
       if ((int64_t)counters[0] != exp_rows) { std::printf("FAIL cfg %zu: samples_scanned %llu vs %lld\n", ci, counters[0], (long long)exp_rows); return 1; }
       if (c.chunks.size() > (size_t)filo::TILE_MAXC && fcount != (unsigned long long)c.nser) { std::printf("FAIL cfg %zu: series with too many chunks were not declined\n", ci); return 1; }
-      std::printf("cfg %zu ok: %d series (%llu to the fallback list), T=%d\n", ci, c.nser, fcount, q.T);
+      std::printf("cfg %zu ok: %d series (%llu to the fallback list), T=%d; junction blocks %ld, literal windows %ld\n", ci, c.nser, fcount, q.T, filo::cusim_junction_blocks, filo::cusim_rest_windows);
+      filo::cusim_junction_blocks = filo::cusim_rest_windows = 0;
     } else {
       // items of <= 5 series in a shuffled order (what build_groups produces for one group)
       std::vector<int32_t> order((size_t)c.nser); for (int s = 0; s < c.nser; ++s) order[(size_t)s] = s;

@@ -114,4 +114,4 @@ def test_tile_kernel_runs_on_the_simt_emulator(tmp_path):
                     os.path.join(ROOT, "tests", "cpp", "tile_emul.cpp"), "-o", exe], check=True)
     for seed in ("0", "20260922"):
         out = subprocess.run([exe, seed], check=True, capture_output=True, text=True).stdout
-        assert "OK 10 cases" in out and "bit-exact" in out, out
+        assert "OK 13 cases" in out and "bit-exact" in out, out
