@@ -10,6 +10,7 @@ namespace filo { alignas(128) uint8_t smem[232448]; }          // `extern __shar
 #include "../../oracle/filo_query.hpp"
 #include <memory>
 #include <random>
+#include <string>
 
 struct Chunk { std::vector<uint8_t> ts, vv, info; };
 struct SeriesData { std::vector<std::unique_ptr<Chunk>> chunks; std::vector<uint8_t> record; };
@@ -114,8 +115,34 @@ int main(int argc, char** argv) {
     {0, true, filo::FN_RATE, {400, 80}, 100000, 0, 300000, 26, 1, 0, 0, filo::AGG_SUM, 2},   // fused sum: items of 5 series in shuffled order
     {1, true, filo::FN_RATE, {240, 240}, 0, 97, 300000, 17, 1, 0, 0, filo::AGG_MAX, 2},      // fused max over counters with resets
   };
-  for (size_t ci = 0; ci < cfgs.size(); ++ci) {
-    const Cfg& c = cfgs[ci];
+  // `tile_emul <seed> fuzz <n>`: n random shapes on top of the fixed list (chunk counts / sizes, windows, offsets, functions, NaN and reset rates)
+  std::vector<Cfg> all = cfgs;
+  if (argc > 3 && std::string(argv[2]) == "fuzz") {
+    std::mt19937_64 fr(seed * 7919 + 13);
+    const int n = std::atoi(argv[3]);
+    for (int i = 0; i < n; ++i) {
+      Cfg c;
+      c.kind = (int)(fr() % 3 == 0);
+      c.xor_enc = fr() % 4 != 0;
+      const int sumfns[] = {filo::FN_RATE, filo::FN_SUM, filo::FN_AVG, filo::FN_COUNT, filo::FN_INCREASE}, ctrfns[] = {filo::FN_RATE, filo::FN_INCREASE, filo::FN_DELTA};
+      c.fn = c.kind ? ctrfns[fr() % 3] : sumfns[fr() % 5];
+      const int nch = 1 + (int)(fr() % 4);
+      int rows = 0; for (int j = 0; j < nch; ++j) { const int r = 16 + (int)(fr() % 150); c.chunks.push_back(r); rows += r; }
+      c.nan_ppm = fr() % 3 == 0 ? (int)(fr() % 300000) : 0;
+      c.reset_every = c.kind && fr() % 2 ? 20 + (int)(fr() % 100) : 0;
+      c.window = 15000 * (int64_t)(1 + fr() % 45) + (fr() % 2 ? 0 : (int64_t)(fr() % 15000));
+      c.nser = 1 + (int)(fr() % 20);
+      c.inclusive = (int)(fr() % 2);
+      c.start_off = (int64_t)(fr() % 7) * 15000 - 45000 + (fr() % 3 == 0 ? (int64_t)(fr() % 15000) : 0);
+      c.end_off = (int64_t)(fr() % 5) * 15000 - 15000;
+      c.agg_op = fr() % 5 == 0 ? (fr() % 2 ? filo::AGG_SUM : filo::AGG_MIN) : 0;
+      c.grid = 1 + (int)(fr() % 3);
+      all.push_back(c);
+    }
+  }
+  const bool quiet = all.size() > cfgs.size();
+  for (size_t ci = 0; ci < all.size(); ++ci) {
+    Cfg c = all[ci];
     int rows = 0; for (int n : c.chunks) rows += n;
     const int64_t t0 = 1700000000000LL; const int step_ms = 15000;
     std::vector<SeriesData> SS((size_t)c.nser);
@@ -127,7 +154,10 @@ int main(int argc, char** argv) {
     for (int s = 0; s < c.nser; ++s) { std::memcpy(arena + rec_off[(size_t)s], SS[(size_t)s].record.data(), SS[(size_t)s].record.size()); max_rec = std::max<uint32_t>(max_rec, (uint32_t)SS[(size_t)s].record.size()); }
     filo::QueryParams q{};
     q.start = t0 + c.start_off; q.step = 15000; q.end = t0 + (int64_t)(rows - 1) * step_ms + c.end_off; q.window = c.window; q.T = (int)((q.end - q.start) / q.step) + 1;
+    if (q.end < q.start) q.end = q.start;
+    q.T = (int)((q.end - q.start) / q.step) + 1;
     q.fn = c.fn; q.cumulative = c.kind == 1; q.inclusive = c.inclusive;
+    if (c.agg_op && q.T > filo::TILE_AGG_ACC * filo::TILE_THREADS) c.agg_op = 0;      // the fused tile path serves T <= 512 (filo_query picks the other kernels beyond)
     const bool ctr = filo::fn_class_of(q.fn, q.cumulative) == filo::CLASS_COUNTER;
     const uint32_t wrows = (uint32_t)(q.window / q.step) + 1;
     const filo::TileSmem L = filo::tile_layout(max_rec, (uint32_t)rows, (uint32_t)q.T, ctr ? 0u : 2 * wrows + 16, ctr);
@@ -158,7 +188,7 @@ int main(int argc, char** argv) {
       }
       if ((int64_t)counters[0] != exp_rows) { std::printf("FAIL cfg %zu: samples_scanned %llu vs %lld\n", ci, counters[0], (long long)exp_rows); return 1; }
       if (c.chunks.size() > (size_t)filo::TILE_MAXC && fcount != (unsigned long long)c.nser) { std::printf("FAIL cfg %zu: series with too many chunks were not declined\n", ci); return 1; }
-      std::printf("cfg %zu ok: %d series (%llu to the fallback list), T=%d; junction blocks %ld, literal windows %ld\n", ci, c.nser, fcount, q.T, filo::cusim_junction_blocks, filo::cusim_rest_windows);
+      if (!quiet) std::printf("cfg %zu ok: %d series (%llu to the fallback list), T=%d; junction blocks %ld, literal windows %ld\n", ci, c.nser, fcount, q.T, filo::cusim_junction_blocks, filo::cusim_rest_windows);
       filo::cusim_junction_blocks = filo::cusim_rest_windows = 0;
     } else {
       // items of <= 5 series in a shuffled order (what build_groups produces for one group)
@@ -184,7 +214,7 @@ int main(int argc, char** argv) {
           ++checked;
         }
       }
-      std::printf("cfg %zu ok: %d series in %lld items (%llu to the fallback list), T=%d\n", ci, c.nser, (long long)n_items, fcount, q.T);
+      if (!quiet) std::printf("cfg %zu ok: %d series in %lld items (%llu to the fallback list), T=%d\n", ci, c.nser, (long long)n_items, fcount, q.T);
     }
     ++cases;
   }
