@@ -160,8 +160,8 @@ __device__ __forceinline__ void chunk_interval(ChunkDesc* D, int n, int c, const
 // are fed as +0.0 (exact no-op).  Requires Wr >= BLK_R - 1.  With CHECK_NAN, NaN rows are skipped and counted out.
 // CHECK_BOUNDS = false: the caller guarantees that every row a valid window reads outside [0, nrows) holds +0.0 and that
 // rows up to BLK_R - 1 past the last valid window are readable.  NEED_CNT = false: cnt[] is not produced.
-template <bool CHECK_NAN, bool CHECK_BOUNDS = true, bool NEED_CNT = true>
-__device__ __forceinline__ void blocked_sum(const double* __restrict__ slots, int r0, int nrows, int Wr, double acc[BLK_R], int cnt[BLK_R]) {
+template <int R, bool CHECK_NAN, bool CHECK_BOUNDS, bool NEED_CNT>
+__device__ __forceinline__ void blocked_sum_r(const double* __restrict__ slots, int r0, int nrows, int Wr, double acc[R], int cnt[R]) {
   static_assert(!CHECK_NAN || (CHECK_BOUNDS && NEED_CNT), "NaN-aware sums count rows and must not see padding");
   auto load = [&](int i, int& ok) -> double {
     const int r = r0 + i;
@@ -173,27 +173,27 @@ __device__ __forceinline__ void blocked_sum(const double* __restrict__ slots, in
     return v;
   };
 #pragma unroll
-  for (int j = 0; j < BLK_R; ++j) { acc[j] = 0.0; cnt[j] = 0; }
+  for (int j = 0; j < R; ++j) { acc[j] = 0.0; cnt[j] = 0; }
 #pragma unroll
-  for (int i = 0; i < BLK_R - 1; ++i) {                    // ramp-up: row i feeds windows 0..i
+  for (int i = 0; i < R - 1; ++i) {                    // ramp-up: row i feeds windows 0..i
     int ok; const double v = load(i, ok);
 #pragma unroll
     for (int j = 0; j <= i; ++j) { acc[j] += v; if (CHECK_NAN) cnt[j] += ok; }
   }
-  for (int i = BLK_R - 1; i <= Wr; ++i) {                  // steady state: every window
+  for (int i = R - 1; i <= Wr; ++i) {                  // steady state: every window
     int ok; const double v = load(i, ok);
 #pragma unroll
-    for (int j = 0; j < BLK_R; ++j) { acc[j] += v; if (CHECK_NAN) cnt[j] += ok; }
+    for (int j = 0; j < R; ++j) { acc[j] += v; if (CHECK_NAN) cnt[j] += ok; }
   }
 #pragma unroll
-  for (int t = 1; t < BLK_R; ++t) {                        // ramp-down: row Wr + t feeds windows t..R-1
+  for (int t = 1; t < R; ++t) {                        // ramp-down: row Wr + t feeds windows t..R-1
     int ok; const double v = load(Wr + t, ok);
 #pragma unroll
-    for (int j = t; j < BLK_R; ++j) { acc[j] += v; if (CHECK_NAN) cnt[j] += ok; }
+    for (int j = t; j < R; ++j) { acc[j] += v; if (CHECK_NAN) cnt[j] += ok; }
   }
   if (!CHECK_NAN) {
 #pragma unroll
-    for (int j = 0; j < BLK_R; ++j) {                      // rows of window j inside the chunk
+    for (int j = 0; j < R; ++j) {                      // rows of window j inside the chunk
       if (NEED_CNT) {
         int lo = r0 + j; if (lo < 0) lo = 0;
         int hi = r0 + j + Wr; if (hi > nrows - 1) hi = nrows - 1;
@@ -201,6 +201,11 @@ __device__ __forceinline__ void blocked_sum(const double* __restrict__ slots, in
       } else cnt[j] = 1;                                   // a blocked window always has a row inside its chunk
     }
   }
+}
+
+template <bool CHECK_NAN, bool CHECK_BOUNDS = true, bool NEED_CNT = true>
+__device__ __forceinline__ void blocked_sum(const double* __restrict__ slots, int r0, int nrows, int Wr, double acc[BLK_R], int cnt[BLK_R]) {
+  blocked_sum_r<BLK_R, CHECK_NAN, CHECK_BOUNDS, NEED_CNT>(slots, r0, nrows, Wr, acc, cnt);
 }
 
 template <bool IS_MIN>

@@ -170,9 +170,12 @@ __device__ __forceinline__ double tile_eval_counter(const TileSeries& S, const T
   return NaNv;
 }
 
-// One block of BLK_R windows of the junction between chunk c-1 and chunk c of a regular series (SUM class): each window's rows lie
+// One block of JUNC_R windows of the junction between chunk c-1 and chunk c of a regular series (SUM class): each window's rows lie
 // in those two chunks only, both are members of its chunk set (the producer checked), so the window is the per-chunk fold of
-// tile_eval_window with the two chunk sums computed BLK_R windows at a time.  A tile with NaN / Inf rows takes the literal fold.
+// tile_eval_window with the two chunk sums computed JUNC_R windows at a time.  JUNC_R is about half of BLK_R: a junction block (two
+// partial sums) then costs about as much as a regular block (one sum of BLK_R windows), which keeps the tile's work items even.
+// A tile with NaN / Inf rows takes the literal fold.
+constexpr int JUNC_R = 8;
 template <int FN>
 __device__ FILO_NOINLINE void tile_junction_block(const TileSeries& S, int c, const double* sv, double* orow, int jb, bool any_nan, const QueryParams& q,
                                                  int64_t winDur, double fdiv, double frcp) {
@@ -180,8 +183,8 @@ __device__ FILO_NOINLINE void tile_junction_block(const TileSeries& S, int c, co
 #ifdef FILO_CUSIM
   ++cusim_junction_blocks;          // emulation statistics (tests/cpp/tile_emul.cpp)
 #endif
-  const int k0 = cb.jk0 + jb * BLK_R;
-  int nw = cb.jk0 + cb.jn - k0; if (nw > BLK_R) nw = BLK_R;
+  const int k0 = cb.jk0 + jb * JUNC_R;
+  int nw = cb.jk0 + cb.jn - k0; if (nw > JUNC_R) nw = JUNC_R;
   double* o = orow + k0;
   if (any_nan) {
     for (int j = 0; j < nw; ++j) {
@@ -191,13 +194,13 @@ __device__ FILO_NOINLINE void tile_junction_block(const TileSeries& S, int c, co
     return;
   }
   const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
-  double acc[BLK_R]; int cnt[BLK_R];
-  blocked_sum<false, true, true>(sv + ca.row_base, ca.s0 + k0, ca.nrows, ca.Wr, acc, cnt);
+  double acc[JUNC_R]; int cnt[JUNC_R];
+  blocked_sum_r<JUNC_R, false, true, true>(sv + ca.row_base, ca.s0 + k0, ca.nrows, ca.Wr, acc, cnt);
 #pragma unroll
-  for (int j = 0; j < BLK_R; ++j) if (j < nw) o[j] = acc[j];         // chunk c-1's sums wait in the window's own output slot
-  blocked_sum<false, true, true>(sv + cb.row_base, cb.s0 + k0, cb.nrows, cb.Wr, acc, cnt);
+  for (int j = 0; j < JUNC_R; ++j) if (j < nw) o[j] = acc[j];        // chunk c-1's sums wait in the window's own output slot
+  blocked_sum_r<JUNC_R, false, true, true>(sv + cb.row_base, cb.s0 + k0, cb.nrows, cb.Wr, acc, cnt);
 #pragma unroll
-  for (int j = 0; j < BLK_R; ++j) {
+  for (int j = 0; j < JUNC_R; ++j) {
     if (j < nw) {
       int lo = ca.s0 + k0 + j; if (lo < 0) lo = 0;
       int hi = ca.s0 + k0 + j + ca.Wr; if (hi > ca.nrows - 1) hi = ca.nrows - 1;
@@ -388,11 +391,11 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         if (CLS == CLASS_SUM && c > 0 && blocked && blocked_p) {
           const int64_t gapA = kBp + 1, gapB = kA - 1, n_gap = gapB - gapA + 1;
           const int64_t wStartB = S0 + gapB * q.step, wEndA = E0 + gapA * q.step;
-          bool okj = n_gap >= 1 && n_gap <= 2 * BLK_R;
+          bool okj = n_gap >= 1 && n_gap <= 4 * JUNC_R && Wr >= JUNC_R - 1;
           okj = okj && !(endp < wStartB) && endp < wEndA && !(end_time < wStartB);                 // both chunks in the chunk set of every gap window
           if (c >= 2) okj = okj && endpp < wEndA && s0pp + gapA > (int64_t)nrowspp - 1;             // chunk c-2: out of the rows
           if (c + 1 < n) okj = okj && e0n + gapB < 0;                                               // chunk c+1: not reached yet
-          if (okj) { jk0 = (int)gapA; jn = (int)n_gap; jb = (jn + BLK_R - 1) / BLK_R; }
+          if (okj) { jk0 = (int)gapA; jn = (int)n_gap; jb = (jn + JUNC_R - 1) / JUNC_R; }
         }
       }
       // zero rows around the chunk so that blocked sums read clamped-away rows as +0.0 without a bounds check
