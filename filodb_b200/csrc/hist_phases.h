@@ -25,6 +25,7 @@ namespace filo {
 constexpr int H2_THREADS = 512;
 constexpr int H2_MAXC = 8;          // chunks in range per series
 constexpr int H2_MAXSECT = 96;      // sections per series
+constexpr int H2_BATCH = 4;         // buckets whose partial sums are loaded ahead of the arithmetic
 
 struct H2Sect { int32_t chunk, start_row /* row (over the series' chunks in range) of the section's first histogram */, n, type; uint32_t first_rec /* byte offset in record */; };
 struct H2Chunk { int32_t row_base, nrows, nsect, has_drop, sect, ts_wire; int64_t end_time; uint32_t ts_off, pad; };
@@ -355,20 +356,31 @@ FILO_HD inline bool h2_window(int k, const H2Ctx& X, double* pv) {
   const int64_t* dlo = PD + (size_t)lo_c * nb; const int64_t* dla = PD + (size_t)a * nb; const int64_t* dhi = PD + (size_t)hi_c * nb;
   const int64_t* rlo = cv + (size_t)lo_row * pitch; const int64_t* rhi = cv + (size_t)hi_row * pitch;
   const bool is_rate = q.fn == FN_RATE;
-  for (int b = 0; b < nb; ++b) {
-    const int64_t clo = (plo[b] - pla[b]) + (dlo[b] - dla[b]);
-    const int64_t chi = (phi[b] - pla[b]) + (dhi[b] - dla[b]);
-    const double lo = (double)(rlo[b] + clo), hi = (double)(rhi[b] + chi);
-    const double delta = hi - lo;
-    double ratio = ratio0;
-    if (delta > 0 && lo >= 0 && !(lo > delta * skipC)) {                  // the zero-point clamp may apply (:84-90)
-      const double dz = sI * (lo / delta);
-      const double dts = dz < dTS ? dz : dTS;
-      ratio = ((sI + (dts < thr ? dts : half)) + endpart) / sI;
+  // buckets in batches of H2_BATCH: the partial row lives in global memory (L2); loading a batch's old sums before computing keeps
+  // several loads in flight instead of one load -> add -> store chain per bucket
+  for (int b0 = 0; b0 < nb; b0 += H2_BATCH) {
+    double old[H2_BATCH];
+#pragma unroll
+    for (int j = 0; j < H2_BATCH; ++j) if (b0 + j < nb) old[j] = pv[(size_t)(b0 + j) * q.T + k];
+#pragma unroll
+    for (int j = 0; j < H2_BATCH; ++j) {
+      const int b = b0 + j;
+      if (b < nb) {
+        const int64_t clo = (plo[b] - pla[b]) + (dlo[b] - dla[b]);
+        const int64_t chi = (phi[b] - pla[b]) + (dhi[b] - dla[b]);
+        const double lo = (double)(rlo[b] + clo), hi = (double)(rhi[b] + chi);
+        const double delta = hi - lo;
+        double ratio = ratio0;
+        if (delta > 0 && lo >= 0 && !(lo > delta * skipC)) {                // the zero-point clamp may apply (:84-90)
+          const double dz = sI * (lo / delta);
+          const double dts = dz < dTS ? dz : dTS;
+          ratio = ((sI + (dts < thr ? dts : half)) + endpart) / sI;
+        }
+        const double scaled = delta * ratio;
+        const double r = is_rate ? h2_div_window(scaled, X.fdiv, X.frcp) * 1000.0 : scaled;
+        pv[(size_t)b * q.T + k] = old[j] + r;                               // MutableHistogram.addNoCorrection: NaN-seeded sums start at 0
+      }
     }
-    const double scaled = delta * ratio;
-    const double r = is_rate ? h2_div_window(scaled, X.fdiv, X.frcp) * 1000.0 : scaled;
-    pv[(size_t)b * q.T + k] += r;                                         // MutableHistogram.addNoCorrection: NaN-seeded sums start at 0
   }
   return true;
 }
