@@ -384,6 +384,7 @@ scan_agg_kernel_v2(const uint8_t* __restrict__ arena, const int64_t* __restrict_
   if (lane == 0 && (rows | bytes)) { atomicAdd(&d_counters[0], (unsigned long long)rows); atomicAdd(&d_counters[1], (unsigned long long)bytes); }
 }
 
+#ifndef FILO_CUSIM      // the launchers need nvcc; the emulation build (tests/cpp) calls the kernels through cusim::launch
 // ---------------------------------------------------------------------------------------------------------------
 // host-callable launchers
 // ---------------------------------------------------------------------------------------------------------------
@@ -511,5 +512,7 @@ cudaError_t launch_fill_items(const int64_t* group_start, const int64_t* gis, in
   fill_items_kernel<<<(n_groups + 127) / 128, 128, 0, s>>>(group_start, gis, n_groups, seg, n_items, n_series, item_begin);
   return cudaGetLastError();
 }
+
+#endif // FILO_CUSIM
 
 } // namespace filo

@@ -5,8 +5,7 @@
 #define FILO_CUSIM 1
 #include "cusim.h"
 namespace filo { alignas(128) uint8_t smem[232448]; }          // `extern __shared__ ... smem[]` of the kernels
-#include "../../filodb_b200/csrc/kernels.h"
-#include "../../filodb_b200/csrc/scan_tile.cuh"
+#include "../../filodb_b200/csrc/scan_kernels.cu"          // every scan kernel (the launchers are compiled out under FILO_CUSIM)
 #include "../../oracle/filo_query.hpp"
 #include <memory>
 #include <random>
@@ -15,14 +14,16 @@ namespace filo { alignas(128) uint8_t smem[232448]; }          // `extern __shar
 struct Chunk { std::vector<uint8_t> ts, vv, info; };
 struct SeriesData { std::vector<std::unique_ptr<Chunk>> chunks; std::vector<uint8_t> record; };
 
+static int g_jitter_ms = 0; static bool g_integral = false;      // irregular scrapes (DDV timestamps) / integral values (DoubleVector.optimize -> DDV longs)
 static void build_series(SeriesData& S, std::mt19937_64& rng, int rows, const std::vector<int>& chunk_rows, int64_t t0, int step_ms, int kind /*0 gauge 1 counter*/,
                          bool xor_enc, int nan_ppm, int reset_every) {
   std::vector<int64_t> ts((size_t)rows); std::vector<double> v((size_t)rows);
   std::normal_distribution<double> N(0.0, 1.0);
   double acc = 0.0;
   for (int r = 0; r < rows; ++r) {
-    ts[(size_t)r] = t0 + (int64_t)r * step_ms;
-    const double g = 15.0 + std::sin((double)(r + 1)) + N(rng);
+    ts[(size_t)r] = t0 + (int64_t)r * step_ms + (g_jitter_ms ? (int64_t)(rng() % (uint64_t)(2 * g_jitter_ms + 1)) - g_jitter_ms : 0);
+    double g = 15.0 + std::sin((double)(r + 1)) + N(rng);
+    if (g_integral) g = std::floor(g);
     if (kind == 0) v[(size_t)r] = g;
     else { if (reset_every && r > 0 && rng() % (uint64_t)reset_every == 0) acc = 0.0; acc += g > 0 ? g : 0.0; v[(size_t)r] = acc; }
   }
@@ -90,8 +91,31 @@ template <bool AGG> static void dispatch(const Launch& A) {          // the inst
   else if (fn == filo::FN_COUNT) run_kernel<filo::CLASS_SUM, filo::FN_COUNT, AGG>(A);
   else run_kernel<filo::CLASS_SUM, filo::FN_SUM, AGG>(A);
 }
+// the v2 warp-per-series kernel (every function / encoding; also the fallback pass over the series the tile kernel declined)
+struct V2Shape { uint32_t max_rec; int max_rows, max_chunks; bool any_nonconst_ts, any_drop; };
+static void run_v2(const Launch& A, const V2Shape& sh, const int64_t* list, const unsigned long long* list_count) {
+  const bool need_corr2 = (A.q.fn == filo::FN_RATE || A.q.fn == filo::FN_INCREASE) && A.q.cumulative && sh.any_drop;
+  uint32_t scratch = filo::align_up((uint32_t)sh.max_chunks * (uint32_t)filo::CHUNK_DESC_BYTES, 16) +
+                     ((uint32_t)sh.max_rows + (uint32_t)sh.max_chunks * 8u) * 8u * (1u + (sh.any_nonconst_ts ? 1u : 0u) + (need_corr2 ? 1u : 0u));
+  scratch = filo::align_up(scratch + 16, 128);                        // as filo_query sizes it (capi.cu)
+  const uint32_t rec_cap = filo::align_up(sh.max_rec + 16, 128);
+  const size_t smem_bytes = (size_t)(filo::WARP_HDR_BYTES + rec_cap + filo::STAGE_BYTES + scratch) * filo::FAST_WARPS;
+  if (smem_bytes > sizeof(filo::smem)) { std::printf("FAIL: v2 shared memory %zu\n", smem_bytes); std::exit(1); }
+  auto body = [&](auto cls) {
+    cusim::launch(dim3((unsigned)A.grid), dim3(filo::FAST_WARPS * 32), [&] {
+      filo::scan_series_kernel_v2<decltype(cls)::value>(A.arena, A.rec_off, A.S, A.q, A.out, rec_cap, scratch, A.counters, A.derr, list, list_count);
+    });
+  };
+  switch (filo::fn_class_of(A.q.fn, A.q.cumulative)) {
+    case filo::CLASS_SUM: body(std::integral_constant<int, filo::CLASS_SUM>{}); break;
+    case filo::CLASS_MINMAX: body(std::integral_constant<int, filo::CLASS_MINMAX>{}); break;
+    case filo::CLASS_COUNTER: body(std::integral_constant<int, filo::CLASS_COUNTER>{}); break;
+    default: body(std::integral_constant<int, filo::CLASS_POINT>{}); break;
+  }
+}
 static fo::RangeFn oracle_fn(int fn) {
-  switch (fn) { case filo::FN_SUM: return fo::FN_SUM_OVER_TIME; case filo::FN_AVG: return fo::FN_AVG_OVER_TIME; case filo::FN_COUNT: return fo::FN_COUNT_OVER_TIME; default: return (fo::RangeFn)fn; }
+  switch (fn) { case filo::FN_SUM: return fo::FN_SUM_OVER_TIME; case filo::FN_AVG: return fo::FN_AVG_OVER_TIME; case filo::FN_COUNT: return fo::FN_COUNT_OVER_TIME;
+                case filo::FN_MIN: return fo::FN_MIN_OVER_TIME; case filo::FN_MAX: return fo::FN_MAX_OVER_TIME; case filo::FN_TIMESTAMP: return fo::FN_TIMESTAMP; default: return (fo::RangeFn)fn; }
 }
 
 int main(int argc, char** argv) {
@@ -99,7 +123,8 @@ int main(int argc, char** argv) {
   cusim::rng_state() = seed;
   std::mt19937_64 rng(4242);
   long checked = 0; int cases = 0;
-  struct Cfg { int kind; bool xor_enc; int fn; std::vector<int> chunks; int nan_ppm, reset_every; int64_t window; int nser; int inclusive; int64_t start_off, end_off; int agg_op; int grid; };
+  struct Cfg { int kind = 0; bool xor_enc = true; int fn = 0; std::vector<int> chunks; int nan_ppm = 0, reset_every = 0; int64_t window = 300000; int nser = 1; int inclusive = 1;
+               int64_t start_off = 0, end_off = 0; int agg_op = 0; int grid = 1; int jitter = 0; bool integral = false; bool v2_only = false; };
   const std::vector<Cfg> cfgs = {
     {0, true, filo::FN_RATE, {400, 80}, 200000, 0, 300000, 11, 1, 0, 0, 0, 2},           // C2: gauge, delta-temporality rate (CLASS_SUM), NaN stale markers
     {0, true, filo::FN_SUM, {150, 90}, 0, 0, 300000, 37, 1, -90000, 45000, 0, 2},        // several tiles per CTA, a partial last tile, windows before / after the data
@@ -112,6 +137,16 @@ int main(int argc, char** argv) {
     {1, true, filo::FN_RATE, {400, 80}, 0, 0, 300000, 10, 1, 0, 0, 0, 2},                 // counters: extrapolated rate (CLASS_COUNTER)
     {1, true, filo::FN_INCREASE, {120, 120, 60}, 0, 41, 60000, 19, 1, -30000, 30000, 0, 2}, // resets: drop-flagged chunks, corrections across chunks
     {1, false, filo::FN_DELTA, {200, 100}, 0, 0, 300000, 6, 0, 0, 0, 0, 1},               // delta over raw vectors
+    // the v2 warp-per-series kernel on its own: every function class, irregular scrapes (DDV timestamps), integral values (DDV longs)
+    {0, true, filo::FN_MIN, {150, 90}, 100000, 0, 300000, 9, 1, -30000, 15000, 0, 2, 0, false, true},
+    {0, false, filo::FN_MAX, {64, 64, 64, 64, 64}, 0, 0, 200000, 7, 0, 0, 0, 0, 1, 0, false, true},
+    {0, true, filo::FN_LAST, {200, 40}, 50000, 0, 300000, 6, 1, 0, 0, 0, 1, 4000, false, true},
+    {0, true, filo::FN_TIMESTAMP, {100, 100}, 0, 0, 120000, 5, 1, 0, 0, 0, 1, 4000, false, true},
+    {0, true, filo::FN_SUM, {120, 120}, 30000, 0, 300000, 8, 1, 0, 0, 0, 2, 4000, false, true},
+    {1, false, filo::FN_RATE, {150, 150}, 0, 45, 300000, 8, 1, 0, 0, 0, 2, 0, true, true},         // integral counters with resets: DDV-long value vectors
+    {1, true, filo::FN_INCREASE, {100, 100, 100}, 0, 60, 60000, 8, 1, 0, 0, 0, 2, 4000, false, true},
+    // tile kernel + fallback pass: irregular scrapes make the tile kernel decline every series
+    {0, true, filo::FN_RATE, {200, 100}, 0, 0, 300000, 10, 1, 0, 0, 0, 2, 4000, false, false},
     {0, true, filo::FN_RATE, {400, 80}, 100000, 0, 300000, 26, 1, 0, 0, filo::AGG_SUM, 2},   // fused sum: items of 5 series in shuffled order
     {1, true, filo::FN_RATE, {240, 240}, 0, 97, 300000, 17, 1, 0, 0, filo::AGG_MAX, 2},      // fused max over counters with resets
   };
@@ -137,6 +172,11 @@ int main(int argc, char** argv) {
       c.end_off = (int64_t)(fr() % 5) * 15000 - 15000;
       c.agg_op = fr() % 5 == 0 ? (fr() % 2 ? filo::AGG_SUM : filo::AGG_MIN) : 0;
       c.grid = 1 + (int)(fr() % 3);
+      c.jitter = fr() % 5 == 0 ? 300 + (int)(fr() % 5000) : 0;
+      c.integral = fr() % 6 == 0; if (c.integral) c.xor_enc = false;
+      c.v2_only = fr() % 4 == 0;
+      if (c.v2_only) { const int fns[] = {filo::FN_MIN, filo::FN_MAX, filo::FN_LAST, filo::FN_TIMESTAMP, c.fn, c.fn}; c.fn = fns[fr() % 6]; c.agg_op = 0; }
+      if (c.jitter) c.agg_op = 0;
       all.push_back(c);
     }
   }
@@ -147,6 +187,7 @@ int main(int argc, char** argv) {
     const int64_t t0 = 1700000000000LL; const int step_ms = 15000;
     std::vector<SeriesData> SS((size_t)c.nser);
     std::vector<int64_t> rec_off((size_t)c.nser + 1, 0);
+    g_jitter_ms = c.jitter; g_integral = c.integral;
     for (int s = 0; s < c.nser; ++s) { build_series(SS[(size_t)s], rng, rows, c.chunks, t0, step_ms, c.kind, c.xor_enc, c.nan_ppm, c.reset_every); rec_off[(size_t)s + 1] = rec_off[(size_t)s] + (int64_t)SS[(size_t)s].record.size(); }
     std::vector<uint64_t> arena_backing((size_t)rec_off.back() / 8 + 64, 0);
     uint8_t* arena = reinterpret_cast<uint8_t*>(arena_backing.data());
@@ -163,23 +204,30 @@ int main(int argc, char** argv) {
     const filo::TileSmem L = filo::tile_layout(max_rec, (uint32_t)rows, (uint32_t)q.T, ctr ? 0u : 2 * wrows + 16, ctr);
     if (L.total > sizeof(filo::smem)) { std::printf("FAIL: layout %u bytes\n", L.total); return 1; }
     // oracle, per series
-    std::vector<double> ref((size_t)c.nser * q.T);
+    std::vector<double> ref((size_t)c.nser * q.T); std::vector<int64_t> oracle_rows((size_t)c.nser, 0);
     for (int s = 0; s < c.nser; ++s) {
       fo::Series os; for (auto& ch : SS[(size_t)s].chunks) os.infos.push_back(ch->info.data());
-      fo::periodicSamples(os, oracle_fn(q.fn), q.cumulative != 0, q.start, q.step, q.end, q.window, fo::QueryConfig{q.inclusive != 0}, ref.data() + (size_t)s * q.T, nullptr);
+      fo::QueryStats st;
+      fo::periodicSamples(os, oracle_fn(q.fn), q.cumulative != 0, q.start, q.step, q.end, q.window, fo::QueryConfig{q.inclusive != 0}, ref.data() + (size_t)s * q.T, &st);
+      oracle_rows[(size_t)s] = st.samplesScanned;
     }
     std::vector<double> out((size_t)c.nser * q.T, -777.0);
     std::vector<int64_t> flist((size_t)c.nser + 8, -1); unsigned long long fcount = 0, counters[2] = {0, 0}; int derr[4] = {0, 0, 0, 0};
     Launch A{arena, rec_off.data(), c.nser, q, out.data(), L, c.grid, flist.data(), &fcount, counters, derr, nullptr, nullptr, 0, 0, nullptr, nullptr};
     if (!c.agg_op) {
-      dispatch<false>(A);
+      V2Shape sh{max_rec, rows, (int)c.chunks.size(), false, false};
+      for (auto& S : SS) { filo::RecordHeader h; std::memcpy(&h, S.record.data(), sizeof h); sh.any_nonconst_ts |= !(h.flags & filo::REC_ALL_TS_CONST); sh.any_drop |= (h.flags & filo::REC_ANY_DROP) != 0; }
+      const int cls = filo::fn_class_of(q.fn, q.cumulative);
+      const bool tile_ok = !c.v2_only && (cls == filo::CLASS_SUM || cls == filo::CLASS_COUNTER);
+      if (tile_ok) {
+        dispatch<false>(A);
+        if (derr[0]) { std::printf("FAIL cfg %zu: device error %d (tile kernel)\n", ci, derr[0]); return 1; }
+        if (fcount) run_v2(A, sh, flist.data(), &fcount);               // the fallback pass, as filo_query chains it
+      } else run_v2(A, sh, nullptr, nullptr);
       if (derr[0]) { std::printf("FAIL cfg %zu: device error %d\n", ci, derr[0]); return 1; }
-      std::vector<char> fell((size_t)c.nser, 0);
-      for (unsigned long long i = 0; i < fcount; ++i) fell[(size_t)flist[(size_t)i]] = 1;
       int64_t exp_rows = 0;
       for (int s = 0; s < c.nser; ++s) {
-        if (fell[(size_t)s]) continue;                                  // declined by the tile kernel: the fallback kernel owns it
-        exp_rows += rows;
+        exp_rows += oracle_rows[(size_t)s];
         for (int k = 0; k < q.T; ++k) {
           const double a = out[(size_t)s * q.T + k], r = ref[(size_t)s * q.T + k];
           if (!same_bits(a, r)) { std::printf("FAIL cfg %zu series %d window %d: %.17g vs %.17g\n", ci, s, k, a, r); return 1; }
@@ -187,7 +235,7 @@ int main(int argc, char** argv) {
         }
       }
       if ((int64_t)counters[0] != exp_rows) { std::printf("FAIL cfg %zu: samples_scanned %llu vs %lld\n", ci, counters[0], (long long)exp_rows); return 1; }
-      if (c.chunks.size() > (size_t)filo::TILE_MAXC && fcount != (unsigned long long)c.nser) { std::printf("FAIL cfg %zu: series with too many chunks were not declined\n", ci); return 1; }
+      if (tile_ok && c.chunks.size() > (size_t)filo::TILE_MAXC && fcount != (unsigned long long)c.nser) { std::printf("FAIL cfg %zu: series with too many chunks were not declined\n", ci); return 1; }
       if (!quiet) std::printf("cfg %zu ok: %d series (%llu to the fallback list), T=%d; junction blocks %ld, literal windows %ld\n", ci, c.nser, fcount, q.T, filo::cusim_junction_blocks, filo::cusim_rest_windows);
       filo::cusim_junction_blocks = filo::cusim_rest_windows = 0;
     } else {

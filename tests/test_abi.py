@@ -103,10 +103,11 @@ def test_hist_scan2_phases_match_oracle_on_cpu(tmp_path):
 
 
 def test_tile_kernel_runs_on_the_simt_emulator(tmp_path):
-    """scan_tile_kernel itself (filodb_b200/csrc/scan_tile.cuh: producer warp, TMA + mbarriers, named barriers, warp shuffles) compiled
-    for the host on the cusim fiber emulator (tests/cpp/cusim.h) and checked bit-exact against the oracle: SUM-class and counter-class
-    functions, raw and XOR vectors, 2-5 chunks, NaN markers, counter resets, several tiles per CTA, the fused aggregate mode; under the
-    in-order schedule and a pseudo-random one.  The emulator aborts on deadlocks and on warp collectives reached from different call
+    """The scan kernels themselves (filodb_b200/csrc/scan_kernels.cu: scan_tile_kernel with its producer warp, TMA + mbarriers, named
+    barriers and warp shuffles; scan_series_kernel_v2, which also takes the series the tile kernel declines) compiled for the host on
+    the cusim fiber emulator (tests/cpp/cusim.h) and checked bit-exact against the oracle, scan counters included: every range
+    function, raw / XOR / DDV-long vectors, const and irregular timestamps, 1-5 chunks, NaN markers, counter resets, several tiles per
+    CTA, the fused aggregate mode; under the in-order schedule and a pseudo-random one.  The emulator aborts on deadlocks and on warp collectives reached from different call
     sites, and performs bulk copies as late as the program allows."""
     import subprocess
     exe = str(tmp_path / "tile_emul")
@@ -114,7 +115,7 @@ def test_tile_kernel_runs_on_the_simt_emulator(tmp_path):
                     os.path.join(ROOT, "tests", "cpp", "tile_emul.cpp"), "-o", exe], check=True)
     for seed in ("0", "20260922"):
         out = subprocess.run([exe, seed], check=True, capture_output=True, text=True).stdout
-        assert "OK 13 cases" in out and "bit-exact" in out, out
+        assert "OK 21 cases" in out and "bit-exact" in out, out
     # random shapes: chunk counts and sizes, windows, offsets, functions, NaN / reset rates, per-series and fused modes
     out = subprocess.run([exe, "7", "fuzz", "60"], check=True, capture_output=True, text=True).stdout
-    assert "OK 73 cases" in out and "bit-exact" in out, out
+    assert "OK 81 cases" in out and "bit-exact" in out, out
