@@ -113,6 +113,28 @@ static void run_v2(const Launch& A, const V2Shape& sh, const int64_t* list, cons
     default: body(std::integral_constant<int, filo::CLASS_POINT>{}); break;
   }
 }
+// the fused fallback: scan_agg_kernel_v2 over the items the tile kernel declined
+static void run_agg_v2(const Launch& A, const V2Shape& sh, const int64_t* list, const unsigned long long* list_count) {
+  const bool need_corr2 = (A.q.fn == filo::FN_RATE || A.q.fn == filo::FN_INCREASE) && A.q.cumulative && sh.any_drop;
+  uint32_t scratch = filo::align_up((uint32_t)sh.max_chunks * (uint32_t)filo::CHUNK_DESC_BYTES, 16) +
+                     ((uint32_t)sh.max_rows + (uint32_t)sh.max_chunks * 8u) * 8u * (1u + (sh.any_nonconst_ts ? 1u : 0u) + (need_corr2 ? 1u : 0u));
+  scratch = filo::align_up(scratch + 16, 128);
+  const uint32_t rec_cap = filo::align_up(sh.max_rec + 16, 128), acc_bytes = filo::align_up((uint32_t)A.q.T * 12u, 128);
+  const size_t smem_bytes = (size_t)(filo::WARP_HDR_BYTES + rec_cap + filo::STAGE_BYTES + acc_bytes + scratch) * filo::FAST_WARPS;
+  if (smem_bytes > sizeof(filo::smem)) { std::printf("FAIL: agg v2 shared memory %zu\n", smem_bytes); std::exit(1); }
+  auto body = [&](auto cls) {
+    cusim::launch(dim3((unsigned)A.grid), dim3(filo::FAST_WARPS * 32), [&] {
+      filo::scan_agg_kernel_v2<decltype(cls)::value>(A.arena, A.rec_off, A.order, A.item_begin, A.n_items, A.q, A.agg_op, A.pval, A.pcnt, rec_cap, scratch, acc_bytes,
+                                                     A.counters, A.derr, list, list_count);
+    });
+  };
+  switch (filo::fn_class_of(A.q.fn, A.q.cumulative)) {
+    case filo::CLASS_SUM: body(std::integral_constant<int, filo::CLASS_SUM>{}); break;
+    case filo::CLASS_MINMAX: body(std::integral_constant<int, filo::CLASS_MINMAX>{}); break;
+    case filo::CLASS_COUNTER: body(std::integral_constant<int, filo::CLASS_COUNTER>{}); break;
+    default: body(std::integral_constant<int, filo::CLASS_POINT>{}); break;
+  }
+}
 static fo::RangeFn oracle_fn(int fn) {
   switch (fn) { case filo::FN_SUM: return fo::FN_SUM_OVER_TIME; case filo::FN_AVG: return fo::FN_AVG_OVER_TIME; case filo::FN_COUNT: return fo::FN_COUNT_OVER_TIME;
                 case filo::FN_MIN: return fo::FN_MIN_OVER_TIME; case filo::FN_MAX: return fo::FN_MAX_OVER_TIME; case filo::FN_TIMESTAMP: return fo::FN_TIMESTAMP; default: return (fo::RangeFn)fn; }
@@ -248,10 +270,13 @@ int main(int argc, char** argv) {
       A.order = order.data(); A.item_begin = item_begin.data(); A.n_items = n_items; A.agg_op = c.agg_op; A.pval = pval.data(); A.pcnt = pcnt.data(); A.out = nullptr;
       dispatch<true>(A);
       if (derr[0]) { std::printf("FAIL cfg %zu: device error %d\n", ci, derr[0]); return 1; }
-      std::vector<char> fell((size_t)n_items, 0);
-      for (unsigned long long i = 0; i < fcount; ++i) fell[(size_t)flist[(size_t)i]] = 1;
+      if (fcount) {                                                     // declined items: the fused v2 kernel, as filo_query chains it
+        V2Shape sh{max_rec, rows, (int)c.chunks.size(), false, false};
+        for (auto& S : SS) { filo::RecordHeader h; std::memcpy(&h, S.record.data(), sizeof h); sh.any_nonconst_ts |= !(h.flags & filo::REC_ALL_TS_CONST); sh.any_drop |= (h.flags & filo::REC_ANY_DROP) != 0; }
+        run_agg_v2(A, sh, flist.data(), &fcount);
+        if (derr[0]) { std::printf("FAIL cfg %zu: device error %d (fused fallback)\n", ci, derr[0]); return 1; }
+      }
       for (int64_t it = 0; it < n_items; ++it) {
-        if (fell[(size_t)it]) continue;
         for (int k = 0; k < q.T; ++k) {
           double a = c.agg_op == filo::AGG_MIN ? INFINITY : c.agg_op == filo::AGG_MAX ? -INFINITY : 0.0; uint32_t n = 0;
           for (int64_t p = item_begin[(size_t)it]; p < item_begin[(size_t)it + 1]; ++p) {
