@@ -639,6 +639,8 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
     const uint32_t full_pad = ctr ? 0u : (uint32_t)std::min<uint64_t>(2 * wrows, 1u << 20) + 16;
     TL = tile_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)q.T, full_pad, ctr);
     if (((size_t)TL.total + 1024) * 2 > (size_t)228 * 1024) TL = tile_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)q.T, ctr ? 0u : 16u, ctr);
+    static const bool no_junction = [] { const char* e = std::getenv("FILO_TILE_JUNCTION"); return e && e[0] == '0'; }();   // A/B switch
+    if (no_junction) TL.opts &= ~TILE_OPT_JUNCTION;
   }
   const bool use_tile = use_v2 && !want_v2 && (fn_cls == CLASS_SUM || fn_cls == CLASS_COUNTER) && t->n_series > 0 &&
                         (size_t)TL.total + 1024 <= std::min<size_t>(ctx->max_smem_optin, 227 * 1024);

@@ -388,7 +388,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         const int64_t kBp = __shfl_up_sync(0xffffffffu, kB, 1);
         const int64_t s0pp = __shfl_up_sync(0xffffffffu, s0, 2), endpp = __shfl_up_sync(0xffffffffu, end_time, 2);
         const int nrowspp = __shfl_up_sync(0xffffffffu, nrows, 2);
-        if (CLS == CLASS_SUM && c > 0 && blocked && blocked_p) {
+        if (CLS == CLASS_SUM && (L.opts & TILE_OPT_JUNCTION) && c > 0 && blocked && blocked_p) {
           const int64_t gapA = kBp + 1, gapB = kA - 1, n_gap = gapB - gapA + 1;
           const int64_t wStartB = S0 + gapB * q.step, wEndA = E0 + gapA * q.step;
           bool okj = n_gap >= 1 && n_gap <= 4 * JUNC_R && Wr >= JUNC_R - 1;

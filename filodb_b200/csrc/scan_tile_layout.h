@@ -68,7 +68,9 @@ struct TileMeta {                         // per-tile work-list prefixes and fla
 struct TileSmem {                         // byte offsets inside dynamic shared memory (all multiples of 128)
   uint32_t rec, vals, out, desc, gtot, meta, ctr, drops, tab, total;
   uint32_t rec_cap, vals_pitch /*doubles per series*/, out_pitch /*doubles per series = T*/, desc_stride /*bytes between the two descriptor buffers*/;
+  uint32_t opts;                          // TILE_OPT_* switches (A/B measurements): set by tile_layout, cleared by the host from the environment
 };
+constexpr uint32_t TILE_OPT_JUNCTION = 1u;   // chunk-junction windows as blocks of two partial sums (FILO_TILE_JUNCTION=0 turns it off)
 FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t T, uint32_t pad_rows, bool counter_class = false) {
   TileSmem L;
   L.rec_cap = align_up(TILE_NS * max_rec_bytes + 128, 128);
@@ -86,6 +88,7 @@ FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, u
   if (counter_class) { o += 2 * align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileCtr), 128); L.drops = o; o += align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileDrops), 128);
                        L.tab = o; o += align_up((TILE_CTR_TABMAX + 1) * (uint32_t)sizeof(TileCtrTab), 128); }
   L.total = o;
+  L.opts = TILE_OPT_JUNCTION;
   return L;
 }
 

@@ -146,10 +146,11 @@ int main(int argc, char** argv) {
   std::mt19937_64 rng(4242);
   long checked = 0; int cases = 0;
   struct Cfg { int kind = 0; bool xor_enc = true; int fn = 0; std::vector<int> chunks; int nan_ppm = 0, reset_every = 0; int64_t window = 300000; int nser = 1; int inclusive = 1;
-               int64_t start_off = 0, end_off = 0; int agg_op = 0; int grid = 1; int jitter = 0; bool integral = false; bool v2_only = false; };
+               int64_t start_off = 0, end_off = 0; int agg_op = 0; int grid = 1; int jitter = 0; bool integral = false; bool v2_only = false; bool no_junction = false; };
   const std::vector<Cfg> cfgs = {
     {0, true, filo::FN_RATE, {400, 80}, 200000, 0, 300000, 11, 1, 0, 0, 0, 2},           // C2: gauge, delta-temporality rate (CLASS_SUM), NaN stale markers
     {0, true, filo::FN_SUM, {150, 90}, 0, 0, 300000, 37, 1, -90000, 45000, 0, 2},        // several tiles per CTA, a partial last tile, windows before / after the data
+    {0, true, filo::FN_SUM, {150, 90}, 0, 0, 300000, 13, 1, -90000, 45000, 0, 2, 0, false, false, true},   // the same with junction blocks switched off (FILO_TILE_JUNCTION=0)
     {0, false, filo::FN_AVG, {200, 40}, 100000, 0, 120000, 5, 0, 0, 0, 0, 1},             // raw f64 vectors, exclusive range start
     {0, true, filo::FN_COUNT, {60, 60, 60, 60}, 300000, 0, 600000, 9, 1, 30000, 0, 0, 3}, // four chunks, long windows over several chunk junctions
     {0, true, filo::FN_RATE, {100, 50, 50, 50, 50}, 0, 0, 300000, 10, 1, 0, 0, 0, 2},     // five chunks: declined (fallback list)
@@ -197,6 +198,7 @@ int main(int argc, char** argv) {
       c.jitter = fr() % 5 == 0 ? 300 + (int)(fr() % 5000) : 0;
       c.integral = fr() % 6 == 0; if (c.integral) c.xor_enc = false;
       c.v2_only = fr() % 4 == 0;
+      c.no_junction = fr() % 8 == 0;
       if (c.v2_only) { const int fns[] = {filo::FN_MIN, filo::FN_MAX, filo::FN_LAST, filo::FN_TIMESTAMP, c.fn, c.fn}; c.fn = fns[fr() % 6]; c.agg_op = 0; }
       if (c.jitter) c.agg_op = 0;
       all.push_back(c);
@@ -223,7 +225,8 @@ int main(int argc, char** argv) {
     if (c.agg_op && q.T > filo::TILE_AGG_ACC * filo::TILE_THREADS) c.agg_op = 0;      // the fused tile path serves T <= 512 (filo_query picks the other kernels beyond)
     const bool ctr = filo::fn_class_of(q.fn, q.cumulative) == filo::CLASS_COUNTER;
     const uint32_t wrows = (uint32_t)(q.window / q.step) + 1;
-    const filo::TileSmem L = filo::tile_layout(max_rec, (uint32_t)rows, (uint32_t)q.T, ctr ? 0u : 2 * wrows + 16, ctr);
+    filo::TileSmem L = filo::tile_layout(max_rec, (uint32_t)rows, (uint32_t)q.T, ctr ? 0u : 2 * wrows + 16, ctr);
+    if (c.no_junction) L.opts &= ~filo::TILE_OPT_JUNCTION;
     if (L.total > sizeof(filo::smem)) { std::printf("FAIL: layout %u bytes\n", L.total); return 1; }
     // oracle, per series
     std::vector<double> ref((size_t)c.nser * q.T); std::vector<int64_t> oracle_rows((size_t)c.nser, 0);
