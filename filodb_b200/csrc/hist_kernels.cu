@@ -433,6 +433,7 @@ __global__ void hist_merge_kernel(const double* __restrict__ pval, const uint8_t
   if (out_q) out_q[i] = qv;
 }
 
+#ifndef FILO_CUSIM      // launchers need nvcc
 #ifdef FILO_HIST_PROF
 extern "C" int filo_debug_hist_prof(unsigned long long* out16, int reset) {
   cudaError_t e = cudaMemcpyFromSymbol(out16, g_hist_prof, sizeof(unsigned long long) * 16);
@@ -458,5 +459,7 @@ cudaError_t launch_hist_merge(const double* pval, const uint8_t* pany, const int
   hist_merge_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pval, pany, gis, n_groups, T, nb, tops, q, out_values, out_q);
   return cudaGetLastError();
 }
+
+#endif // FILO_CUSIM
 
 } // namespace filo

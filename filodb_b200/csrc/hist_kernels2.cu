@@ -11,12 +11,20 @@ __device__ __forceinline__ void h2_report(int* d_err, int code, int64_t sid) {
 }
 
 // record bytes global -> shared with 16-byte cp.async (LDGSTS); the caller waits with cp.async.wait_group + a CTA barrier
+#ifdef FILO_CUSIM          // host emulation build (tests/cpp/cusim.h)
+inline void h2_stage_async(uint8_t* dst, const uint8_t* src, uint32_t bytes, int tid) {
+  for (uint32_t i = (uint32_t)tid * 16; i < bytes; i += H2_THREADS * 16) cusim::cp_async(dst + i, src + i, 16);
+}
+inline void h2_stage_wait() { cusim::cp_async_wait_all(); }
+#else
 __device__ __forceinline__ void h2_stage_async(uint8_t* dst, const uint8_t* __restrict__ src, uint32_t bytes, int tid) {
   const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
   for (uint32_t i = (uint32_t)tid * 16; i < bytes; i += H2_THREADS * 16)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + i), "l"(src + i) : "memory");
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void h2_stage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+#endif
 
 // One CTA folds work items (runs of series of one group, positions index `order`) into the item's partial row
 // pval[it][bucket][window] (bucket-major) and pany[it][window].
@@ -41,7 +49,7 @@ hist_scan2_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__
         const int64_t ro = rec_off[sid];
         h2_stage_async(smem + X.L.rec, arena + ro, (uint32_t)(rec_off[sid + 1] - ro), tid);
       }
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      h2_stage_wait();
       __syncthreads();
       h2_tables(tid, X, max_rows);
       __syncthreads();
@@ -122,6 +130,7 @@ __global__ void hist_merge2_kernel(const double* __restrict__ pval, const uint8_
   if (out_q) out_q[i] = qv;
 }
 
+#ifndef FILO_CUSIM      // launchers need nvcc
 size_t hist2_smem_bytes(int max_rows, int nb, uint32_t max_rec) { return h2_layout(max_rows, nb, max_rec).total; }
 cudaError_t launch_hist_scan2(const ScanLaunch& L, int nb, int max_rows, uint32_t max_rec, const int32_t* order, const int64_t* item_begin, int64_t n_items,
                               double* pval, uint8_t* pany) {
@@ -138,5 +147,7 @@ cudaError_t launch_hist_merge2(const double* pval, const uint8_t* pany, const in
   hist_merge2_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pval, pany, gis, n_groups, T, nb, tops, q, out_values, out_q);
   return cudaGetLastError();
 }
+
+#endif // FILO_CUSIM
 
 } // namespace filo

@@ -73,6 +73,9 @@ inline void run_op(Deferred& o) {
 inline void tick_ops() { for (auto& o : g()->ops) if (!o.done && --o.countdown <= 0) run_op(o); }
 inline void tma_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) { g()->ops.push_back(Deferred{tma_delay(), true, smem_dst, gsrc, bytes, bar, g()->cur, false}); }
 inline void tma_store(void* gdst, const void* smem_src, uint32_t bytes) { g()->ops.push_back(Deferred{tma_delay(), false, gdst, smem_src, bytes, nullptr, g()->cur, false}); }
+// cp.async (LDGSTS) global -> shared: lands when the issuing thread waits for its groups (as late as the program allows)
+inline void cp_async(void* smem_dst, const void* gsrc, uint32_t bytes) { g()->ops.push_back(Deferred{tma_delay(), false, smem_dst, gsrc, bytes, nullptr, g()->cur, false}); }
+inline void cp_async_wait_all() { for (auto& o : g()->ops) if (!o.is_load && o.owner == g()->cur) run_op(o); }
 inline void tma_store_wait_read() { for (auto& o : g()->ops) if (!o.is_load && o.owner == g()->cur) run_op(o); }     // the fiber's bulk stores have read their source
 
 // ---- CTA-level barriers
@@ -226,6 +229,7 @@ inline long long __double2ll_rd(double d) { return __double2ll_rz(std::floor(d))
 inline long long __double2ll_ru(double d) { return __double2ll_rz(std::ceil(d)); }
 inline long long __double2ll_rn(double d) { return __double2ll_rz(std::nearbyint(d)); }
 inline int __double2int_rn(double d) { return __double2int_rz(std::nearbyint(d)); }
+using std::isinf; using std::isnan;
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }

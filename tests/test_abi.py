@@ -119,3 +119,20 @@ def test_tile_kernel_runs_on_the_simt_emulator(tmp_path):
     # random shapes: chunk counts and sizes, windows, offsets, functions, NaN / reset rates, per-series and fused modes
     out = subprocess.run([exe, "7", "fuzz", "60"], check=True, capture_output=True, text=True).stdout
     assert "OK 82 cases" in out and "bit-exact" in out, out
+
+
+def test_histogram_kernels_run_on_the_simt_emulator(tmp_path):
+    """hist_scan2_kernel (with its cp.async record prefetch) + hist_merge2_kernel and hist_scan_kernel + hist_merge_kernel compiled for
+    the host on the cusim emulator: fused sum + histogram_quantile on both kernels, per-series rate / increase, sum_over_time and the
+    delta-temporality rate, SectDelta and simple vectors, resets inside chunks and at chunk starts, irregular scrapes; bit-exact
+    against the oracle (the checker folds series and items in the kernels' order)."""
+    import subprocess, sys
+    v1 = str(tmp_path / "hist_kernels_cusim.cu")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cpp", "make_cusim_src.py"), os.path.join(ROOT, "filodb_b200", "csrc", "hist_kernels.cu"), v1], check=True)
+    exe = str(tmp_path / "hist_kernel_emul")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes", "-I", "/usr/local/cuda/include",
+                    "-I", os.path.join(ROOT, "filodb_b200", "csrc"), '-DHIST_V1_SRC="%s"' % v1,
+                    os.path.join(ROOT, "tests", "cpp", "hist_kernel_emul.cpp"), "-o", exe], check=True)
+    for seed in ("0", "5"):
+        out = subprocess.run([exe, seed], check=True, capture_output=True, text=True).stdout
+        assert "OK 6 cases" in out and "bit-exact" in out, out
