@@ -5,7 +5,12 @@
 #define FILO_CUSIM 1
 #include "cusim.h"
 namespace filo { alignas(128) uint8_t smem[232448]; }          // `extern __shared__ ... smem[]` of the kernels
+#ifdef SCAN_SRC
+#include SCAN_SRC                                             // scan_kernels.cu through tests/cpp/make_cusim_src.py (function-scope __shared__ -> static)
+#define HAVE_MERGE_KERNEL 1
+#else
 #include "../../filodb_b200/csrc/scan_kernels.cu"          // every scan kernel (the launchers are compiled out under FILO_CUSIM)
+#endif
 #include "../../oracle/filo_query.hpp"
 #include <memory>
 #include <random>
@@ -290,6 +295,29 @@ int main(int argc, char** argv) {
           ++checked;
         }
       }
+#ifdef HAVE_MERGE_KERNEL
+      {   // merge_partials_kernel: one group over all items; thread (window, lane j) folds items j, j+8, ... and the 8 lanes fold in order
+        const int64_t gis[2] = {0, n_items};
+        std::vector<double> mv((size_t)q.T, -777.0); std::vector<int64_t> mc((size_t)q.T, -1);
+        const int ktiles = (q.T + 31) / 32;
+        cusim::launch(dim3((unsigned)ktiles), dim3(256), [&] { filo::merge_partials_kernel(pval.data(), pcnt.data(), gis, 1, q.T, c.agg_op, 0, mv.data(), mc.data()); });
+        for (int k = 0; k < q.T; ++k) {
+          const double ident = c.agg_op == filo::AGG_MIN ? INFINITY : c.agg_op == filo::AGG_MAX ? -INFINITY : 0.0;
+          double lane_a[8]; unsigned long long lane_c[8];
+          for (int j = 0; j < 8; ++j) {
+            double a = ident; unsigned long long n = 0;
+            for (int64_t it = j; it < n_items; it += 8) { const double v = pval[(size_t)it * q.T + k]; const uint32_t m = pcnt[(size_t)it * q.T + k];
+              if (m) { if (c.agg_op == filo::AGG_MIN) a = v < a ? v : a; else if (c.agg_op == filo::AGG_MAX) a = v > a ? v : a; else a += v; n += m; } }
+            lane_a[j] = a; lane_c[j] = n;
+          }
+          double a = lane_a[0]; unsigned long long n = lane_c[0];
+          for (int j = 1; j < 8; ++j) if (lane_c[j]) { const double v = lane_a[j]; if (c.agg_op == filo::AGG_MIN) a = v < a ? v : a; else if (c.agg_op == filo::AGG_MAX) a = v > a ? v : a; else a += v; n += lane_c[j]; }
+          const double e = n == 0 ? std::nan("") : c.agg_op == filo::AGG_AVG ? a / (double)n : c.agg_op == filo::AGG_COUNT ? (double)n : a;
+          if (!same_bits(mv[(size_t)k], e) || mc[(size_t)k] != (int64_t)n) { std::printf("FAIL cfg %zu merged window %d: %.17g (%lld) vs %.17g (%llu)\n", ci, k, mv[(size_t)k], (long long)mc[(size_t)k], e, n); return 1; }
+          ++checked;
+        }
+      }
+#endif
       if (!quiet) std::printf("cfg %zu ok: %d series in %lld items (%llu to the fallback list), T=%d\n", ci, c.nser, (long long)n_items, fcount, q.T);
     }
     ++cases;

@@ -109,9 +109,12 @@ def test_tile_kernel_runs_on_the_simt_emulator(tmp_path):
     function, raw / XOR / DDV-long vectors, const and irregular timestamps, 1-5 chunks, NaN markers, counter resets, several tiles per
     CTA, the fused aggregate mode; under the in-order schedule and a pseudo-random one.  The emulator aborts on deadlocks and on warp collectives reached from different call
     sites, and performs bulk copies as late as the program allows."""
-    import subprocess
+    import subprocess, sys
+    src = str(tmp_path / "scan_kernels_cusim.cu")          # function-scope __shared__ (merge_partials_kernel) -> static
+    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cpp", "make_cusim_src.py"), os.path.join(ROOT, "filodb_b200", "csrc", "scan_kernels.cu"), src], check=True)
     exe = str(tmp_path / "tile_emul")
     subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes", "-I", "/usr/local/cuda/include",
+                    "-I", os.path.join(ROOT, "filodb_b200", "csrc"), '-DSCAN_SRC="%s"' % src,
                     os.path.join(ROOT, "tests", "cpp", "tile_emul.cpp"), "-o", exe], check=True)
     for seed in ("0", "20260922"):
         out = subprocess.run([exe, seed], check=True, capture_output=True, text=True).stdout
