@@ -11,8 +11,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libfilo_b200.so")
-OBJ = os.path.join(HERE, "csrc", "_obj")
+# FILO_BUILD_OUT: build a variant (e.g. FILO_NVCC_EXTRA=-DFILO_HIST_PROF) into another file, with its own object directory
+OUT = os.path.abspath(os.environ["FILO_BUILD_OUT"]) if os.environ.get("FILO_BUILD_OUT") else os.path.join(HERE, "libfilo_b200.so")
+OBJ = os.path.join(HERE, "csrc", "_obj" if not os.environ.get("FILO_BUILD_OUT") else "_obj_variant")
 SOURCES = ["scan_kernels.cu", "hist_kernels.cu", "hist_kernels2.cu", "synth_kernels.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-DFILO_BUILDING"] + os.environ.get("FILO_NVCC_EXTRA", "").split()

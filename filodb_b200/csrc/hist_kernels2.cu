@@ -6,6 +6,19 @@
 
 namespace filo {
 
+// Per-phase cycle counters for profiling builds (-DFILO_HIST_PROF; scratch/hist_prof.py): thread 0 of every CTA reads clock64() after each
+// phase barrier.  Compiled out of the product build.
+#if defined(FILO_HIST_PROF) && !defined(FILO_CUSIM)
+__device__ unsigned long long g_hist2_prof[16];
+#define H2PROF_DECL long long hp_t0 = clock64(), hp_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define H2PROF(i) { const long long hp_t1 = clock64(); hp_acc[i] += hp_t1 - hp_t0; hp_t0 = hp_t1; }
+#define H2PROF_FLUSH if (threadIdx.x == 0) { for (int hp_i = 0; hp_i < 12; ++hp_i) atomicAdd(&g_hist2_prof[hp_i], (unsigned long long)hp_acc[hp_i]); atomicAdd(&g_hist2_prof[15], 1ull); }
+#else
+#define H2PROF_DECL
+#define H2PROF(i)
+#define H2PROF_FLUSH
+#endif
+
 __device__ __forceinline__ void h2_report(int* d_err, int code, int64_t sid) {
   if (atomicCAS(&d_err[0], 0, code) == 0) { d_err[1] = (int)(sid & 0x7fffffff); d_err[2] = (int)(sid >> 31); }
 }
@@ -36,6 +49,7 @@ hist_scan2_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__
   H2Ctx X; h2_ctx_init(X, smem, h2_layout(max_rows, nb, max_rec), q, nb);
   const int tid = threadIdx.x;
   int64_t rows_scanned = 0, bytes_scanned = 0;
+  H2PROF_DECL
   for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
     const int64_t pb = item_begin[it], pe = item_begin[it + 1];
     double* pv = pval + (size_t)it * q.T * nb; uint8_t* pa = pany + (size_t)it * q.T;
@@ -51,8 +65,10 @@ hist_scan2_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__
       }
       h2_stage_wait();
       __syncthreads();
+      H2PROF(0)                                           // record staged (prefetched behind the previous series)
       h2_tables(tid, X, max_rows);
       __syncthreads();
+      H2PROF(1)                                           // chunk range + section table (thread 0)
       if (tid == 0) {
         const H2Ctl* C = X.ctl();
         rows_scanned += C->rows_scanned; bytes_scanned += C->bytes_scanned;
@@ -60,6 +76,7 @@ hist_scan2_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__
       }
       h2_decode_rows(tid, H2_THREADS, X);
       __syncthreads();
+      H2PROF(2)                                           // timestamps + rows decoded
       // the staged record is dead from here on: fetch the next series' record behind the remaining phases
       prefetched = pos + 1 < pe;
       if (prefetched) {
@@ -70,18 +87,22 @@ hist_scan2_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__
       if (tid == 0 && X.ctl()->bad) h2_report(d_err, 1, sid);
       h2_add_base(tid, H2_THREADS, X);
       __syncthreads();
+      H2PROF(3)                                           // next record issued, SectDelta bases added
       h2_chunk_corrections(tid, H2_THREADS, X);
       __syncthreads();
       h2_chunk_less(tid, X);
       __syncthreads();
       h2_carried(tid, H2_THREADS, X);
       __syncthreads();
+      H2PROF(4)                                           // corrections inside and across chunks
       int j = 0;
       for (int k = tid; k < q.T; k += H2_THREADS, ++j) if (h2_window(k, X, pv)) anyb |= 1u << j;
       __syncthreads();                                   // the series' rows and record are dead
+      H2PROF(5)                                           // windows: descriptors + rates + partial-row update
     }
     { int j = 0; for (int k = tid; k < q.T; k += H2_THREADS, ++j) pa[k] = (uint8_t)((anyb >> j) & 1u); }
   }
+  H2PROF_FLUSH
   if (tid == 0 && (rows_scanned | bytes_scanned)) { atomicAdd(&d_counters[0], (unsigned long long)rows_scanned); atomicAdd(&d_counters[1], (unsigned long long)bytes_scanned); }
 }
 
@@ -131,6 +152,13 @@ __global__ void hist_merge2_kernel(const double* __restrict__ pval, const uint8_
 }
 
 #ifndef FILO_CUSIM      // launchers need nvcc
+#ifdef FILO_HIST_PROF
+extern "C" int filo_debug_hist2_prof(unsigned long long* out16, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out16, g_hist2_prof, sizeof(unsigned long long) * 16);
+  if (e == cudaSuccess && reset) { unsigned long long z[16] = {}; e = cudaMemcpyToSymbol(g_hist2_prof, z, sizeof z); }
+  return (int)e;
+}
+#endif
 size_t hist2_smem_bytes(int max_rows, int nb, uint32_t max_rec) { return h2_layout(max_rows, nb, max_rec).total; }
 cudaError_t launch_hist_scan2(const ScanLaunch& L, int nb, int max_rows, uint32_t max_rec, const int32_t* order, const int64_t* item_begin, int64_t n_items,
                               double* pval, uint8_t* pany) {

@@ -23,3 +23,5 @@ for f in sorted(glob.glob("gpurun_out/r2_*.json")):
     except Exception as e:
         print(f, "unreadable:", e)
 PY
+# 5. per-phase cycle profile of both histogram kernels (needs scratch/libfilo_b200_prof.so, see scratch/hist_prof.py)
+if [ -f scratch/libfilo_b200_prof.so ]; then timeout 120 python scratch/hist_prof.py > gpurun_out/r2_hist_phases.txt 2>&1; cat gpurun_out/r2_hist_phases.txt; fi
