@@ -385,6 +385,13 @@ scan_agg_kernel_v2(const uint8_t* __restrict__ arena, const int64_t* __restrict_
 }
 
 #ifndef FILO_CUSIM      // the launchers need nvcc; the emulation build (tests/cpp) calls the kernels through cusim::launch
+#ifdef FILO_TILE_PROF
+extern "C" int filo_debug_tile_prof(unsigned long long* out16, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out16, g_tile_prof, sizeof(unsigned long long) * 16);
+  if (e == cudaSuccess && reset) { unsigned long long z[16] = {}; e = cudaMemcpyToSymbol(g_tile_prof, z, sizeof z); }
+  return (int)e;
+}
+#endif
 // ---------------------------------------------------------------------------------------------------------------
 // host-callable launchers
 // ---------------------------------------------------------------------------------------------------------------

@@ -35,6 +35,19 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 #define FILO_NOINLINE __noinline__
 #endif
 
+// Per-phase cycle counters of the consumer side for profiling builds (-DFILO_TILE_PROF; scratch/tile_prof.py): lane 0 of every
+// consumer warp reads clock64() at the phase boundaries of a tile, summed over warps and CTAs.  Compiled out of the product build.
+#if defined(FILO_TILE_PROF) && !defined(FILO_CUSIM)
+__device__ unsigned long long g_tile_prof[16];
+#define TPROF_DECL long long tp_t0 = clock64(), tp_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define TPROF(i) { const long long tp_t1 = clock64(); tp_acc[i] += tp_t1 - tp_t0; tp_t0 = tp_t1; }
+#define TPROF_FLUSH if (lane == 0) { for (int tp_i = 0; tp_i < 10; ++tp_i) atomicAdd(&g_tile_prof[tp_i], (unsigned long long)tp_acc[tp_i]); atomicAdd(&g_tile_prof[15], 1ull); }
+#else
+#define TPROF_DECL
+#define TPROF(i)
+#define TPROF_FLUSH
+#endif
+
 // compile-time specialised finish of one single-chunk window (SumFinish of scan_fast.cuh with FN known)
 template <int FN>
 __device__ __forceinline__ double tile_finish(double cs, int nn, double div, double rcp) {
@@ -505,16 +518,19 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
   for (int j = 0; j < TILE_AGG_ACC; ++j) { aacc[j] = agg_ident; acnt[j] = 0; }
   int64_t rows_scanned = 0, bytes_scanned = 0, pend_rows = 0, pend_bytes = 0;
   uint32_t tj = 0;                      // tiles done by this CTA: buffer tj & 1, phase (tj >> 1) & 1 of its ready barrier
+  TPROF_DECL
   Walk w;
   for (bool more = walk_start(w); more; more = walk_next(w), b ^= 1) {
     const TileSeries* SDc = reinterpret_cast<const TileSeries*>(smem + L.desc + b * L.desc_stride);
     TileMeta* Mc = reinterpret_cast<TileMeta*>(smem + L.meta + b * 128);
     TileCtr* CTc = reinterpret_cast<TileCtr*>(smem + L.ctr) + b * (TILE_NS * TILE_MAXC);
     TileDrops* DRc = reinterpret_cast<TileDrops*>(smem + L.drops);
+    TPROF(9)                                                // results of the previous tile (fold / store, loop overhead)
     mbar_wait_parked(ready + b, (tj >> 1) & 1); ++tj;   // A(t): descriptors ready (no consumer-wide barrier: the windows-end barrier of the
                                                  // previous tile already separates the tiles)
     if (Mc->staged) { mbar_wait(bar, parity); parity ^= 1; }    // already complete (the producer saw it); orders the TMA writes
     const int64_t i0 = Mc->i0; const int ns = Mc->ns;
+    TPROF(0)                                                // wait: descriptors (+ tile bytes) ready
     // zero rows around the chunks (warp 0, lane = series * 4 + chunk); read by the blocked sums after the next barriers
     if (warp == 0) {
       const TileSeries& S = SDc[lane >> 2];
@@ -576,7 +592,9 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
       gexcl[ds * TILE_GX_PITCH + warp * 8 + (lane >> 3)] = excl[0];
       gexcl[ds * TILE_GX_PITCH + warp * 8 + 4 + (lane >> 3)] = excl[1];
       if (lane >= 24) gwtot[ds * TILE_GW_PITCH + warp] = tot0 ^ tot1;
+      TPROF(1)                                              // decode: field extraction + in-warp prefix
       bar_consumers();
+      TPROF(2)                                              // wait: cross-warp exchange barrier
       // value before group g of chunk c = first_c ^ (prefix at the slot) ^ (prefix at the chunk's first slot); the prefix at a
       // slot = XOR of the earlier warps' totals ^ the in-warp part
       uint32_t nz = 0x7ff00000u;
@@ -655,6 +673,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         }
       }
     }
+    TPROF(3)                                                // decode: prefixes applied, rows stored (+ raw copies)
     if (tid == 0) tma_store_wait_read();       // the previous tile's bulk store must have finished reading `otile`
     __syncthreads();            // B(t): the record bytes are dead, the producer refills the staging buffer
     // ------------------------------------------------------------------ windows: blocked single-chunk windows
@@ -754,6 +773,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
           }
         }
       }
+      TPROF(4)                                              // wait: barrier B (+ counter-class windows)
       const int nitems = CLS == CLASS_COUNTER ? 0 : Mc->pref[TILE_NS];
       for (int it = tid; it < nitems; it += TILE_THREADS) {
         int s = 0;
@@ -807,6 +827,7 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         }
       }
       // ---------------------------------------------------------------- windows: everything else (chunk junctions, short windows)
+      TPROF(5)                                              // windows: blocked and junction items
       const int nrest = CLS == CLASS_COUNTER ? 0 : Mc->rpref[TILE_NS];
       for (int it = tid; it < nrest; it += TILE_THREADS) {
         int s = 0;
@@ -831,8 +852,10 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
                                                           : tile_eval_window<FN, false>(S, sv, wStart, wEnd, fdiv, k);
       }
     }
+    TPROF(6)                                                // windows: literal per-window folds
     fence_async_smem();        // make this thread's writes to the output tile visible to the async proxy (bulk store below)
     bar_consumers();
+    TPROF(7)                                                // wait: windows-end barrier
     // tile flags of this tile stay valid until the producer's setup two tiles ahead, which waits for the next B barrier;
     // a counter series whose drop list overflowed was declared irregular during the windows
     const bool all_reg = Mc->all_regular != 0;
@@ -894,6 +917,8 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
     }
   }
   if (tid == 0) tma_store_wait_read();
+  TPROF(9)
+  TPROF_FLUSH
   if (rows_scanned | bytes_scanned) {
     atomicAdd(&d_counters[0], (unsigned long long)rows_scanned); atomicAdd(&d_counters[1], (unsigned long long)bytes_scanned);
   }

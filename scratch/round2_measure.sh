@@ -23,5 +23,8 @@ for f in sorted(glob.glob("gpurun_out/r2_*.json")):
     except Exception as e:
         print(f, "unreadable:", e)
 PY
-# 5. per-phase cycle profile of both histogram kernels (needs scratch/libfilo_b200_prof.so, see scratch/hist_prof.py)
-if [ -f scratch/libfilo_b200_prof.so ]; then timeout 120 python scratch/hist_prof.py > gpurun_out/r2_hist_phases.txt 2>&1; cat gpurun_out/r2_hist_phases.txt; fi
+# 5. per-phase cycle profiles (need scratch/libfilo_b200_prof.so: FILO_NVCC_EXTRA="-DFILO_HIST_PROF -DFILO_TILE_PROF" FILO_BUILD_OUT=scratch/libfilo_b200_prof.so python -m filodb_b200.build --force)
+if [ -f scratch/libfilo_b200_prof.so ]; then
+  timeout 120 python scratch/hist_prof.py > gpurun_out/r2_hist_phases.txt 2>&1; cat gpurun_out/r2_hist_phases.txt
+  for w in c2 c2-counter; do timeout 90 python scratch/tile_prof.py $w 2>/dev/null | tail -12 > gpurun_out/r2_tile_phases_$w.txt; cat gpurun_out/r2_tile_phases_$w.txt; done
+fi
