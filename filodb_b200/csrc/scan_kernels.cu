@@ -432,14 +432,21 @@ cudaError_t launch_scan_agg_v2(const ScanLaunch& L, const int32_t* order, const 
   }
 }
 struct TileAggArgs { const int32_t* order; const int64_t* item_begin; int64_t n_items; int agg_op; double* pval; uint32_t* pcnt; };
+template <int CLS, int FN, bool AGG, int DEC>
+static cudaError_t launch_tile_dec(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count,
+                                   const TileAggArgs& A) {
+  cudaError_t e = cudaFuncSetAttribute(scan_tile_kernel<CLS, FN, AGG, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total);
+  if (e != cudaSuccess) return e;
+  scan_tile_kernel<CLS, FN, AGG, DEC><<<L.grid, TILE_LAUNCH_THREADS, T.total, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, T, fallback_list, fallback_count,
+      L.d_counters, L.d_err, A.order, A.item_begin, A.n_items, A.agg_op, A.pval, A.pcnt);
+  return cudaGetLastError();
+}
 template <int CLS, int FN, bool AGG>
 static cudaError_t launch_tile_fn(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count,
                                   const TileAggArgs& A) {
-  cudaError_t e = cudaFuncSetAttribute(scan_tile_kernel<CLS, FN, AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T.total);
-  if (e != cudaSuccess) return e;
-  scan_tile_kernel<CLS, FN, AGG><<<L.grid, TILE_LAUNCH_THREADS, T.total, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, T, fallback_list, fallback_count,
-      L.d_counters, L.d_err, A.order, A.item_begin, A.n_items, A.agg_op, A.pval, A.pcnt);
-  return cudaGetLastError();
+  // the per-warp decode variant exists for the SUM class without the fused aggregate (experimental, TILE_OPT_WARPDEC)
+  if (CLS == CLASS_SUM && !AGG && (T.opts & TILE_OPT_WARPDEC)) return launch_tile_dec<CLS, FN, AGG, (CLS == CLASS_SUM && !AGG) ? 1 : 0>(L, out, T, fallback_list, fallback_count, A);
+  return launch_tile_dec<CLS, FN, AGG, 0>(L, out, T, fallback_list, fallback_count, A);
 }
 template <bool AGG>
 static cudaError_t launch_tile_any(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count,

@@ -239,7 +239,8 @@ __device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d) { return (uin
 // Tile kernel, no across-series aggregate.  CLS = CLASS_SUM: sum/avg/count_over_time, rate/increase on delta schemas;
 // CLS = CLASS_COUNTER: rate/increase on cumulative schemas (counter correction) and delta.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int CLS, int FN, bool AGG>
+// DEC = 1 (SUM class, TILE_OPT_WARPDEC): warp w decodes series w alone -- see the decode block
+template <int CLS, int FN, bool AGG, int DEC = 0>
 __global__ void __launch_bounds__(TILE_LAUNCH_THREADS, 2)
 scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, int64_t n_series,
                      QueryParams q, double* __restrict__ out, TileSmem L,
@@ -419,8 +420,20 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
       }
       int need = 0;
       (void)xpre(lowz + nrows + highz, need);
-      const bool padded = need + BLK_R <= (int)L.vals_pitch;
+      const bool padded = need + BLK_R + (DEC ? TILE_MAXC : 0) <= (int)L.vals_pitch;
       if (!padded) { lowz = 0; highz = 0; }
+      if (DEC) {
+        // 16-byte row stores: every chunk's rows start at an odd offset of the (even-pitch) series row, so that row 1 -- the first row
+        // of its first group -- is 16-byte aligned.  One extra zero row in front of a chunk fixes the parity; chunks in order.
+        const int t_c = have ? lowz + nrows + highz : 0;
+        const int t0 = __shfl_sync(0xffffffffu, t_c, lb), t1 = __shfl_sync(0xffffffffu, t_c, lb + 1), t2 = __shfl_sync(0xffffffffu, t_c, lb + 2);
+        const int l0 = __shfl_sync(0xffffffffu, lowz, lb), l1 = __shfl_sync(0xffffffffu, lowz, lb + 1), l2 = __shfl_sync(0xffffffffu, lowz, lb + 2), l3 = __shfl_sync(0xffffffffu, lowz, lb + 3);
+        const int e0p = ((l0) & 1) ? 0 : 1;                              // chunk 0: row_base = lowz0 (+ e)
+        const int b1 = t0 + e0p, e1p = ((b1 + l1) & 1) ? 0 : 1;
+        const int b2 = b1 + t1 + e1p, e2p = ((b2 + l2) & 1) ? 0 : 1;
+        const int b3 = b2 + t2 + e2p, e3p = ((b3 + l3) & 1) ? 0 : 1;
+        if (have) lowz += c == 0 ? e0p : c == 1 ? e1p : c == 2 ? e2p : e3p;
+      }
       int nrows_tot = 0;
       const int row_base = xpre(lowz + nrows + highz, nrows_tot) + lowz;
       if (ngroups > TILE_MAXG || nrows_tot + 2 > (int)L.vals_pitch) { regular = false; have = false; }
@@ -547,13 +560,15 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
     // Lane -> series lane & 7 (neighbouring lanes store to different series' rows: with the odd row pitch the 8-byte stores
     // of a warp spread over all banks); warp w owns the slots 8w .. 8w+7 of every series: item jj -> slot 8w + 4jj + (lane >> 3).
     {
-      const int ds = lane & 7;
+      // DEC = 1: warp w <-> series w, item jj -> slot 32 jj + lane: the whole XOR prefix stays inside the warp (no exchange through
+      // shared memory, no barrier); a lane's 8 rows leave as four 16-byte stores (lane stride 64 bytes: a quarter-warp covers all banks)
+      const int ds = DEC ? warp : (lane & 7);
       const TileSeries& S = SDc[ds];
       const bool sreg = S.regular == 1;
       uint64_t d[2][8]; uint64_t excl[2]; int cc[2]; bool act[2];
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
-        const int slot = warp * 8 + jj * 4 + (lane >> 3);
+        const int slot = DEC ? jj * 32 + lane : warp * 8 + jj * 4 + (lane >> 3);
         const bool active = sreg && slot < S.ngroups;
         const int c = (slot >= S.gb[1] ? 1 : 0) + (slot >= S.gb[2] ? 1 : 0) + (slot >= S.gb[3] ? 1 : 0);
         const TileChunk& ch = S.c[c];
@@ -583,6 +598,27 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
           d[jj][i] = x << tz;
         }
       }
+      uint64_t pre0, pre1;
+      if (DEC) {
+        // inclusive XOR scan of the group totals over the 64 slots (item 0: slots 0..31, item 1: 32..63), then the exclusive
+        // prefixes go through a per-warp table so that a lane can look up the prefix at its chunk's first slot
+        uint64_t i0x = d[0][7], i1x = d[1][7];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint64_t y0 = shfl_up_u64(i0x, o), y1 = shfl_up_u64(i1x, o);
+          if (lane >= o) { i0x ^= y0; i1x ^= y1; }
+        }
+        const uint64_t tot0 = shfl_u64(i0x, 31);
+        excl[0] = i0x ^ d[0][7]; excl[1] = i1x ^ d[1][7] ^ tot0;
+        uint64_t* wx = gexcl + warp * TILE_GX_PITCH;
+        wx[lane] = excl[0]; wx[32 + lane] = excl[1];
+        __syncwarp();
+        TPROF(1)
+        const TileChunk& c0 = S.c[cc[0]]; const TileChunk& c1 = S.c[cc[1]];
+        pre0 = c0.first ^ excl[0] ^ wx[act[0] ? c0.grp_base : 0];
+        pre1 = c1.first ^ excl[1] ^ wx[act[1] ? c1.grp_base : 0];
+        TPROF(2)
+      } else {
       // XOR of the group totals of earlier slots of the same series inside this warp (lanes ds, ds+8, ds+16, ds+24; item 0 first)
       uint64_t i0x = d[0][7], i1x = d[1][7];
       { const uint64_t y0 = shfl_up_u64(i0x, 8), y1 = shfl_up_u64(i1x, 8); if (lane >= 8) { i0x ^= y0; i1x ^= y1; } }
@@ -597,30 +633,47 @@ scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
       TPROF(2)                                              // wait: cross-warp exchange barrier
       // value before group g of chunk c = first_c ^ (prefix at the slot) ^ (prefix at the chunk's first slot); the prefix at a
       // slot = XOR of the earlier warps' totals ^ the in-warp part
-      uint32_t nz = 0x7ff00000u;
-      const bool any_drop = CLS == CLASS_COUNTER && Mc->any_drop != 0;
       {
         const TileChunk& c0 = S.c[cc[0]]; const TileChunk& c1 = S.c[cc[1]];
         const int gb0 = act[0] ? c0.grp_base : 0, gb1 = act[1] ? c1.grp_base : 0;
-        uint64_t pre0 = c0.first ^ excl[0] ^ gexcl[ds * TILE_GX_PITCH + gb0];
-        uint64_t pre1 = c1.first ^ excl[1] ^ gexcl[ds * TILE_GX_PITCH + gb1];
+        pre0 = c0.first ^ excl[0] ^ gexcl[ds * TILE_GX_PITCH + gb0];
+        pre1 = c1.first ^ excl[1] ^ gexcl[ds * TILE_GX_PITCH + gb1];
         const int wl0 = gb0 >> 3, wl1 = gb1 >> 3;
         for (int w = 0; w < warp; ++w) {
           const uint64_t tw = gwtot[ds * TILE_GW_PITCH + w];
           if (w >= wl0) pre0 ^= tw;
           if (w >= wl1) pre1 ^= tw;
         }
+      }
+      }
+      uint32_t nz = 0x7ff00000u;
+      const bool any_drop = CLS == CLASS_COUNTER && Mc->any_drop != 0;
+      {
+        const TileChunk& c0 = S.c[cc[0]]; const TileChunk& c1 = S.c[cc[1]];
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const TileChunk& ch = jj ? c1 : c0;
           const uint64_t pre = jj ? pre1 : pre0;
-          const int g = act[jj] ? warp * 8 + jj * 4 + (lane >> 3) - ch.grp_base : 0;   // an inactive slot's chunk descriptor is not initialised
+          const int g = act[jj] ? (DEC ? jj * 32 + lane : warp * 8 + jj * 4 + (lane >> 3)) - ch.grp_base : 0;   // an inactive slot's chunk descriptor is not initialised
           uint64_t* dst = reinterpret_cast<uint64_t*>(vals + (size_t)ds * L.vals_pitch + ch.row_base) + 1 + g * 8;
           const int nleft = act[jj] ? ch.nrows - 1 - g * 8 : 0;     // rows past nrows are never read as data
+          if (DEC && nleft >= 8) {                   // a full group: four 16-byte stores (dst is 16-byte aligned by construction)
+#ifdef FILO_CUSIM
+            if (reinterpret_cast<uintptr_t>(dst) & 15) { std::fprintf(stderr, "cusim: misaligned 16-byte row store (series %d chunk %d)\n", ds, cc[jj]); std::abort(); }
+#endif
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const uint64_t b0 = d[jj][i] ^ pre, b1 = d[jj][i + 1] ^ pre;
+              *reinterpret_cast<ulonglong2*>(dst + i) = make_ulonglong2(b0, b1);
+              const uint32_t e0 = ~(uint32_t)(b0 >> 32) & 0x7ff00000u, e1 = ~(uint32_t)(b1 >> 32) & 0x7ff00000u;
+              nz = e0 < nz ? e0 : nz; nz = e1 < nz ? e1 : nz;
+            }
+          } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const uint64_t b = d[jj][i] ^ pre;
             if (i < nleft) { dst[i] = b; const uint32_t e = ~(uint32_t)(b >> 32) & 0x7ff00000u; nz = e < nz ? e : nz; }
+          }
           }
           if (CLS == CLASS_COUNTER && FN != FN_DELTA && any_drop) {
             // counter drops inside a drop-flagged chunk (DoubleVector.scala:330-340): row r drops when (NaN -> 0) of it is below

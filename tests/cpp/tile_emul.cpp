@@ -81,8 +81,14 @@ struct Launch {
   const int32_t* order; const int64_t* item_begin; int64_t n_items; int agg_op; double* pval; uint32_t* pcnt;
 };
 template <int CLS, int FN, bool AGG> static void run_kernel(const Launch& A) {
+  if (CLS == filo::CLASS_SUM && !AGG && (A.L.opts & filo::TILE_OPT_WARPDEC)) {      // as launch_tile_fn picks it
+    cusim::launch(dim3((unsigned)A.grid), dim3(filo::TILE_LAUNCH_THREADS), [&] {
+      filo::scan_tile_kernel<CLS, FN, AGG, (CLS == filo::CLASS_SUM && !AGG) ? 1 : 0>(A.arena, A.rec_off, A.S, A.q, A.out, A.L, A.flist, A.fcount, A.counters, A.derr, A.order, A.item_begin, A.n_items, A.agg_op, A.pval, A.pcnt);
+    });
+    return;
+  }
   cusim::launch(dim3((unsigned)A.grid), dim3(filo::TILE_LAUNCH_THREADS), [&] {
-    filo::scan_tile_kernel<CLS, FN, AGG>(A.arena, A.rec_off, A.S, A.q, A.out, A.L, A.flist, A.fcount, A.counters, A.derr, A.order, A.item_begin, A.n_items, A.agg_op, A.pval, A.pcnt);
+    filo::scan_tile_kernel<CLS, FN, AGG, 0>(A.arena, A.rec_off, A.S, A.q, A.out, A.L, A.flist, A.fcount, A.counters, A.derr, A.order, A.item_begin, A.n_items, A.agg_op, A.pval, A.pcnt);
   });
 }
 template <bool AGG> static void dispatch(const Launch& A) {          // the instantiations launch_tile_any makes (scan_kernels.cu)
@@ -151,7 +157,7 @@ int main(int argc, char** argv) {
   std::mt19937_64 rng(4242);
   long checked = 0; int cases = 0;
   struct Cfg { int kind = 0; bool xor_enc = true; int fn = 0; std::vector<int> chunks; int nan_ppm = 0, reset_every = 0; int64_t window = 300000; int nser = 1; int inclusive = 1;
-               int64_t start_off = 0, end_off = 0; int agg_op = 0; int grid = 1; int jitter = 0; bool integral = false; bool v2_only = false; bool no_junction = false; };
+               int64_t start_off = 0, end_off = 0; int agg_op = 0; int grid = 1; int jitter = 0; bool integral = false; bool v2_only = false; bool no_junction = false; bool warp_decode = false; };
   const std::vector<Cfg> cfgs = {
     {0, true, filo::FN_RATE, {400, 80}, 200000, 0, 300000, 11, 1, 0, 0, 0, 2},           // C2: gauge, delta-temporality rate (CLASS_SUM), NaN stale markers
     {0, true, filo::FN_SUM, {150, 90}, 0, 0, 300000, 37, 1, -90000, 45000, 0, 2},        // several tiles per CTA, a partial last tile, windows before / after the data
@@ -165,6 +171,10 @@ int main(int argc, char** argv) {
     {1, true, filo::FN_RATE, {400, 80}, 0, 0, 300000, 10, 1, 0, 0, 0, 2},                 // counters: extrapolated rate (CLASS_COUNTER)
     {1, true, filo::FN_INCREASE, {120, 120, 60}, 0, 41, 60000, 19, 1, -30000, 30000, 0, 2}, // resets: drop-flagged chunks, corrections across chunks
     {1, false, filo::FN_DELTA, {200, 100}, 0, 0, 300000, 6, 0, 0, 0, 0, 1},               // delta over raw vectors
+    // the per-warp decode variant of the tile kernel (FILO_TILE_WARPDEC=1): C2 shape with NaN markers, three chunks, raw + XOR mixes
+    {0, true, filo::FN_RATE, {400, 80}, 200000, 0, 300000, 19, 1, 0, 0, 0, 2, 0, false, false, false, true},
+    {0, true, filo::FN_AVG, {100, 100, 100}, 30000, 0, 300000, 24, 1, -30000, 30000, 0, 2, 0, false, false, false, true},
+    {0, true, filo::FN_SUM, {33, 150, 7, 90}, 0, 0, 240000, 11, 0, 0, 0, 0, 3, 0, false, false, false, true},
     // the v2 warp-per-series kernel on its own: every function class, irregular scrapes (DDV timestamps), integral values (DDV longs)
     {0, true, filo::FN_MIN, {150, 90}, 100000, 0, 300000, 9, 1, -30000, 15000, 0, 2, 0, false, true},
     {0, false, filo::FN_MAX, {64, 64, 64, 64, 64}, 0, 0, 200000, 7, 0, 0, 0, 0, 1, 0, false, true},
@@ -204,6 +214,7 @@ int main(int argc, char** argv) {
       c.integral = fr() % 6 == 0; if (c.integral) c.xor_enc = false;
       c.v2_only = fr() % 4 == 0;
       c.no_junction = fr() % 8 == 0;
+      c.warp_decode = fr() % 3 == 0;
       if (c.v2_only) { const int fns[] = {filo::FN_MIN, filo::FN_MAX, filo::FN_LAST, filo::FN_TIMESTAMP, c.fn, c.fn}; c.fn = fns[fr() % 6]; c.agg_op = 0; }
       if (c.jitter) c.agg_op = 0;
       all.push_back(c);
@@ -230,7 +241,7 @@ int main(int argc, char** argv) {
     if (c.agg_op && q.T > filo::TILE_AGG_ACC * filo::TILE_THREADS) c.agg_op = 0;      // the fused tile path serves T <= 512 (filo_query picks the other kernels beyond)
     const bool ctr = filo::fn_class_of(q.fn, q.cumulative) == filo::CLASS_COUNTER;
     const uint32_t wrows = (uint32_t)(q.window / q.step) + 1;
-    filo::TileSmem L = filo::tile_layout(max_rec, (uint32_t)rows, (uint32_t)q.T, ctr ? 0u : 2 * wrows + 16, ctr);
+    filo::TileSmem L = filo::tile_layout(max_rec, (uint32_t)rows, (uint32_t)q.T, ctr ? 0u : 2 * wrows + 16, ctr, c.warp_decode && !c.agg_op);
     if (c.no_junction) L.opts &= ~filo::TILE_OPT_JUNCTION;
     if (L.total > sizeof(filo::smem)) { std::printf("FAIL: layout %u bytes\n", L.total); return 1; }
     // oracle, per series
