@@ -638,7 +638,7 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
     const uint64_t wrows = (uint64_t)(q.window / q.step) + 1;
     const uint32_t full_pad = ctr ? 0u : (uint32_t)std::min<uint64_t>(2 * wrows, 1u << 20) + 16;
     static const bool warp_decode = [] { const char* e = std::getenv("FILO_TILE_WARPDEC"); return e && e[0] == '1'; }();   // experimental
-    const bool wdec = warp_decode && !fused;
+    const bool wdec = warp_decode;
     TL = tile_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)q.T, full_pad, ctr, wdec);
     if (((size_t)TL.total + 1024) * 2 > (size_t)228 * 1024) TL = tile_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)q.T, ctr ? 0u : 16u, ctr, wdec);
     static const bool no_junction = [] { const char* e = std::getenv("FILO_TILE_JUNCTION"); return e && e[0] == '0'; }();   // A/B switch

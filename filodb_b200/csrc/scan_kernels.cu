@@ -444,8 +444,7 @@ static cudaError_t launch_tile_dec(const ScanLaunch& L, double* out, const TileS
 template <int CLS, int FN, bool AGG>
 static cudaError_t launch_tile_fn(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count,
                                   const TileAggArgs& A) {
-  // the per-warp decode variant exists for the SUM class without the fused aggregate (experimental, TILE_OPT_WARPDEC)
-  if (CLS == CLASS_SUM && !AGG && (T.opts & TILE_OPT_WARPDEC)) return launch_tile_dec<CLS, FN, AGG, (CLS == CLASS_SUM && !AGG) ? 1 : 0>(L, out, T, fallback_list, fallback_count, A);
+  if (T.opts & TILE_OPT_WARPDEC) return launch_tile_dec<CLS, FN, AGG, 1>(L, out, T, fallback_list, fallback_count, A);      // experimental per-warp decode
   return launch_tile_dec<CLS, FN, AGG, 0>(L, out, T, fallback_list, fallback_count, A);
 }
 template <bool AGG>

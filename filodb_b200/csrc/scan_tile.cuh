@@ -239,7 +239,7 @@ __device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d) { return (uin
 // Tile kernel, no across-series aggregate.  CLS = CLASS_SUM: sum/avg/count_over_time, rate/increase on delta schemas;
 // CLS = CLASS_COUNTER: rate/increase on cumulative schemas (counter correction) and delta.
 // ---------------------------------------------------------------------------------------------------------------------
-// DEC = 1 (SUM class, TILE_OPT_WARPDEC): warp w decodes series w alone -- see the decode block
+// DEC = 1 (TILE_OPT_WARPDEC): warp w decodes series w alone -- see the decode block
 template <int CLS, int FN, bool AGG, int DEC = 0>
 __global__ void __launch_bounds__(TILE_LAUNCH_THREADS, 2)
 scan_tile_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, int64_t n_series,

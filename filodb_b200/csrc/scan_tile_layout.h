@@ -71,14 +71,14 @@ struct TileSmem {                         // byte offsets inside dynamic shared 
   uint32_t opts;                          // TILE_OPT_* switches (A/B measurements): set by tile_layout, cleared by the host from the environment
 };
 constexpr uint32_t TILE_OPT_JUNCTION = 1u;   // chunk-junction windows as blocks of two partial sums (FILO_TILE_JUNCTION=0 turns it off)
-constexpr uint32_t TILE_OPT_WARPDEC = 2u;    // SUM class: warp w decodes series w alone (no cross-warp exchange barrier); needs the even row pitch
+constexpr uint32_t TILE_OPT_WARPDEC = 2u;    // warp w decodes series w alone (no cross-warp exchange barrier); needs the even row pitch
                                              // and odd chunk row offsets that tile_layout / the producer set up with it (FILO_TILE_WARPDEC=1, experimental)
 FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t T, uint32_t pad_rows, bool counter_class = false, bool warp_decode = false) {
   TileSmem L;
   L.rec_cap = align_up(TILE_NS * max_rec_bytes + 128, 128);
   L.desc_stride = align_up(TILE_NS * (uint32_t)sizeof(TileSeries), 128);
   L.vals_pitch = (max_rows + pad_rows + 2 + 1) | 1;            // odd pitch (doubles); pad_rows: zero rows for clamped windows
-  if (warp_decode && !counter_class) L.vals_pitch += TILE_MAXC + 1;   // even pitch + one parity row per chunk: 16-byte aligned row stores
+  if (warp_decode) L.vals_pitch += TILE_MAXC + 1;               // even pitch + one parity row per chunk: 16-byte aligned row stores
   L.out_pitch = T;
   uint32_t o = 128;                                            // mbarrier slot
   L.rec = o; o += L.rec_cap;
@@ -91,7 +91,7 @@ FILO_HD inline TileSmem tile_layout(uint32_t max_rec_bytes, uint32_t max_rows, u
   if (counter_class) { o += 2 * align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileCtr), 128); L.drops = o; o += align_up(TILE_NS * TILE_MAXC * (uint32_t)sizeof(TileDrops), 128);
                        L.tab = o; o += align_up((TILE_CTR_TABMAX + 1) * (uint32_t)sizeof(TileCtrTab), 128); }
   L.total = o;
-  L.opts = TILE_OPT_JUNCTION | (warp_decode && !counter_class ? TILE_OPT_WARPDEC : 0u);
+  L.opts = TILE_OPT_JUNCTION | (warp_decode ? TILE_OPT_WARPDEC : 0u);
   return L;
 }
 

@@ -11,8 +11,9 @@ timeout 150 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/r2_p
 timeout 60 $P 2>/dev/null | tail -1 > gpurun_out/r2_c2_junction_on.json
 FILO_TILE_JUNCTION=0 timeout 60 $P 2>/dev/null | tail -1 > gpurun_out/r2_c2_junction_off.json
 # 2b. experimental per-warp decode (no mid-decode barrier, 16-byte row stores): parity under the switch, then its timing
-FILO_TILE_WARPDEC=1 timeout 120 python -m pytest tests/test_gpu_parity.py -q -x -k "per_series_bit_exact or golden or edge" 2>&1 | tail -2 > gpurun_out/r2_pytest_warpdec.txt; cat gpurun_out/r2_pytest_warpdec.txt
+FILO_TILE_WARPDEC=1 timeout 120 python -m pytest tests/test_gpu_parity.py -q -x -k "per_series_bit_exact or golden or edge or aggregates" 2>&1 | tail -2 > gpurun_out/r2_pytest_warpdec.txt; cat gpurun_out/r2_pytest_warpdec.txt
 FILO_TILE_WARPDEC=1 timeout 60 $P 2>/dev/null | tail -1 > gpurun_out/r2_c2_warpdec.json
+for w in c2-counter c5; do FILO_TILE_WARPDEC=1 timeout 90 $P --workload $w 2>/dev/null | tail -1 > gpurun_out/r2_${w}_warpdec.json; done
 # 3. the other workloads, kernel only
 for w in c2-counter c2-raw c3-const c5; do timeout 90 $P --workload $w 2>/dev/null | tail -1 > gpurun_out/r2_$w.json; done
 # 4. C4 histogram kernels A/B

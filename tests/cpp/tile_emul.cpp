@@ -81,9 +81,9 @@ struct Launch {
   const int32_t* order; const int64_t* item_begin; int64_t n_items; int agg_op; double* pval; uint32_t* pcnt;
 };
 template <int CLS, int FN, bool AGG> static void run_kernel(const Launch& A) {
-  if (CLS == filo::CLASS_SUM && !AGG && (A.L.opts & filo::TILE_OPT_WARPDEC)) {      // as launch_tile_fn picks it
+  if (A.L.opts & filo::TILE_OPT_WARPDEC) {      // as launch_tile_fn picks it
     cusim::launch(dim3((unsigned)A.grid), dim3(filo::TILE_LAUNCH_THREADS), [&] {
-      filo::scan_tile_kernel<CLS, FN, AGG, (CLS == filo::CLASS_SUM && !AGG) ? 1 : 0>(A.arena, A.rec_off, A.S, A.q, A.out, A.L, A.flist, A.fcount, A.counters, A.derr, A.order, A.item_begin, A.n_items, A.agg_op, A.pval, A.pcnt);
+      filo::scan_tile_kernel<CLS, FN, AGG, 1>(A.arena, A.rec_off, A.S, A.q, A.out, A.L, A.flist, A.fcount, A.counters, A.derr, A.order, A.item_begin, A.n_items, A.agg_op, A.pval, A.pcnt);
     });
     return;
   }
@@ -175,6 +175,8 @@ int main(int argc, char** argv) {
     {0, true, filo::FN_RATE, {400, 80}, 200000, 0, 300000, 19, 1, 0, 0, 0, 2, 0, false, false, false, true},
     {0, true, filo::FN_AVG, {100, 100, 100}, 30000, 0, 300000, 24, 1, -30000, 30000, 0, 2, 0, false, false, false, true},
     {0, true, filo::FN_SUM, {33, 150, 7, 90}, 0, 0, 240000, 11, 0, 0, 0, 0, 3, 0, false, false, false, true},
+    {1, true, filo::FN_RATE, {400, 80}, 0, 61, 300000, 13, 1, 0, 0, 0, 2, 0, false, false, false, true},            // ... counters with resets
+    {1, true, filo::FN_INCREASE, {120, 120, 60}, 0, 41, 60000, 12, 1, -30000, 30000, filo::AGG_SUM, 2, 0, false, false, false, true},   // ... fused
     // the v2 warp-per-series kernel on its own: every function class, irregular scrapes (DDV timestamps), integral values (DDV longs)
     {0, true, filo::FN_MIN, {150, 90}, 100000, 0, 300000, 9, 1, -30000, 15000, 0, 2, 0, false, true},
     {0, false, filo::FN_MAX, {64, 64, 64, 64, 64}, 0, 0, 200000, 7, 0, 0, 0, 0, 1, 0, false, true},
@@ -241,7 +243,7 @@ int main(int argc, char** argv) {
     if (c.agg_op && q.T > filo::TILE_AGG_ACC * filo::TILE_THREADS) c.agg_op = 0;      // the fused tile path serves T <= 512 (filo_query picks the other kernels beyond)
     const bool ctr = filo::fn_class_of(q.fn, q.cumulative) == filo::CLASS_COUNTER;
     const uint32_t wrows = (uint32_t)(q.window / q.step) + 1;
-    filo::TileSmem L = filo::tile_layout(max_rec, (uint32_t)rows, (uint32_t)q.T, ctr ? 0u : 2 * wrows + 16, ctr, c.warp_decode && !c.agg_op);
+    filo::TileSmem L = filo::tile_layout(max_rec, (uint32_t)rows, (uint32_t)q.T, ctr ? 0u : 2 * wrows + 16, ctr, c.warp_decode);
     if (c.no_junction) L.opts &= ~filo::TILE_OPT_JUNCTION;
     if (L.total > sizeof(filo::smem)) { std::printf("FAIL: layout %u bytes\n", L.total); return 1; }
     // oracle, per series
