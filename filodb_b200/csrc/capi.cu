@@ -641,8 +641,10 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
     const bool wdec = warp_decode;
     TL = tile_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)q.T, full_pad, ctr, wdec);
     if (((size_t)TL.total + 1024) * 2 > (size_t)228 * 1024) TL = tile_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)q.T, ctr ? 0u : 16u, ctr, wdec);
-    static const bool no_junction = [] { const char* e = std::getenv("FILO_TILE_JUNCTION"); return e && e[0] == '0'; }();   // A/B switch
-    if (no_junction) TL.opts &= ~TILE_OPT_JUNCTION;
+    // junction blocks measured 64.4 ms vs 39.5 ms without them on C2 (round 2, gpurun_out/r2_c2_junction_*.json: the blocks share a
+    // strided item list with the regular blocks, so every warp runs both paths): off unless FILO_TILE_JUNCTION=1
+    static const bool junction = [] { const char* e = std::getenv("FILO_TILE_JUNCTION"); return e && e[0] == '1'; }();
+    if (!junction) TL.opts &= ~TILE_OPT_JUNCTION;
   }
   const bool use_tile = use_v2 && !want_v2 && (fn_cls == CLASS_SUM || fn_cls == CLASS_COUNTER) && t->n_series > 0 &&
                         (size_t)TL.total + 1024 <= std::min<size_t>(ctx->max_smem_optin, 227 * 1024);
