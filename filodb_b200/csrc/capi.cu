@@ -4,6 +4,7 @@
 #include "kernels.h"
 #include "host_util.h"
 #include "scan_tile_layout.h"
+#include "scan_wp_layout.h"
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <atomic>
@@ -648,6 +649,23 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
   }
   const bool use_tile = use_v2 && !want_v2 && (fn_cls == CLASS_SUM || fn_cls == CLASS_COUNTER) && t->n_series > 0 &&
                         (size_t)TL.total + 1024 <= std::min<size_t>(ctx->max_smem_optin, 227 * 1024);
+  // v4 warp-pipeline kernel (scan_wp.cuh): SUM-class functions without a fused aggregate; what it declines goes to the v2 kernel like the
+  // tile kernel's declines.  FILO_KERNEL=v3 keeps the tile kernel.
+  WpSmem WL;
+  bool use_wp = false;
+  {
+    const uint64_t wrows = (uint64_t)(q.window / q.step) + 1;
+    const bool want_v3 = force && std::string(force) == "v3";
+    if (use_tile && !want_v3 && fn_cls == CLASS_SUM && wrows <= 4096 && t->max_chunks > 0) {
+      WL = wp_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)t->max_chunks, (uint32_t)q.T, (uint32_t)wrows);
+      const size_t cap = std::min<size_t>(ctx->max_smem_optin, 227 * 1024);
+      size_t w = cap / WL.per_warp; if (w > (size_t)WP_MAX_WARPS) w = WP_MAX_WARPS;
+      static const int warps_env = [] { const char* e = std::getenv("FILO_WP_WARPS"); return e ? atoi(e) : 0; }();
+      if (warps_env > 0 && (size_t)warps_env < w) w = (size_t)warps_env;
+      WL.warps = (uint32_t)w;
+      use_wp = w >= 4;
+    }
+  }
   auto run_per_series = [&](double* outp) -> int32_t {
     if (use_tile) {
       int64_t* d_list = nullptr; unsigned long long* d_cnt = nullptr;
@@ -660,7 +678,10 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
       LT.grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * ctas_per_sm));
       static const bool dbg = std::getenv("FILO_DEBUG_SYNC") != nullptr;
       if (dbg) { fprintf(stderr, "[filo] tile kernel fn=%d T=%d grid=%d smem=%u pitch=%u\n", fn, q.T, LT.grid, TL.total, TL.vals_pitch); fflush(stderr); }
-      CUDA_TRY(ctx, launch_scan_tile(LT, outp, TL, d_list, d_cnt));
+      if (use_wp) {
+        LT.grid = (int)std::max<int64_t>(1, std::min<int64_t>((t->n_series + WL.warps - 1) / WL.warps, (int64_t)ctx->sm_count));
+        CUDA_TRY(ctx, launch_scan_wp(LT, outp, WL, d_list, d_cnt));
+      } else CUDA_TRY(ctx, launch_scan_tile(LT, outp, TL, d_list, d_cnt));
       if (dbg) { CUDA_TRY(ctx, cudaStreamSynchronize(s)); fprintf(stderr, "[filo] tile kernel done\n"); fflush(stderr); }
       ScanLaunch LF = L; LF.list = d_list; LF.list_count = d_cnt;
       CUDA_TRY(ctx, launch_scan_series_v2(LF, outp, rec_cap_used));

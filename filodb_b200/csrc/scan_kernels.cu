@@ -10,6 +10,7 @@
 #include "kernels.h"
 #include "scan_fast.cuh"
 #include "scan_tile.cuh"
+#include "scan_wp.cuh"
 
 namespace filo {
 
@@ -472,6 +473,23 @@ cudaError_t launch_scan_tile(const ScanLaunch& L, double* out, const TileSmem& T
 cudaError_t launch_scan_tile_agg(const ScanLaunch& L, const TileSmem& T, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg_op,
                                  double* pval, uint32_t* pcnt, int64_t* fallback_list, unsigned long long* fallback_count) {
   return launch_tile_any<true>(L, nullptr, T, fallback_list, fallback_count, TileAggArgs{order, item_begin, n_items, agg_op, pval, pcnt});
+}
+// v4 warp-pipeline kernel (scan_wp.cuh): one CTA of W.warps warps per SM; declined series go to fallback_list
+template <int FN>
+static cudaError_t launch_wp_fn(const ScanLaunch& L, double* out, const WpSmem& W, int64_t* fallback_list, unsigned long long* fallback_count) {
+  const size_t smem = (size_t)W.per_warp * W.warps;
+  cudaError_t e = cudaFuncSetAttribute(scan_wp_sum_kernel<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  scan_wp_sum_kernel<FN><<<L.grid, W.warps * 32, smem, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, W, fallback_list, fallback_count, L.d_counters, L.d_err);
+  return cudaGetLastError();
+}
+cudaError_t launch_scan_wp(const ScanLaunch& L, double* out, const WpSmem& W, int64_t* fallback_list, unsigned long long* fallback_count) {
+  switch (L.q.fn) {
+    case FN_RATE: return launch_wp_fn<FN_RATE>(L, out, W, fallback_list, fallback_count);
+    case FN_AVG: return launch_wp_fn<FN_AVG>(L, out, W, fallback_list, fallback_count);
+    case FN_COUNT: return launch_wp_fn<FN_COUNT>(L, out, W, fallback_list, fallback_count);
+    default: return launch_wp_fn<FN_SUM>(L, out, W, fallback_list, fallback_count);      // FN_SUM, FN_INCREASE on a delta schema
+  }
 }
 size_t v2_smem_per_warp(uint32_t rec_cap, uint32_t scratch_bytes, uint32_t acc_bytes) { return WARP_HDR_BYTES + (size_t)rec_cap + STAGE_BYTES + acc_bytes + scratch_bytes; }
 cudaError_t launch_scan_series(const ScanLaunch& L, double* out) {

@@ -1,0 +1,485 @@
+// v4 scan path ("wp": warp pipeline).  One warp owns one series end to end; warps never synchronise with each other.
+//
+// Each warp runs its own three-buffer pipeline in shared memory:
+//   R  the series' record (ChunkSetInfo entries + BinaryVectors verbatim), filled by ONE cp.async.bulk (TMA 1-D) per series that is
+//      issued as soon as the previous record has been decoded, i.e. it is in flight during the previous series' window phase;
+//   V  the decoded rows, laid out per chunk with zero rows in between so that clamped windows read +0.0 instead of testing bounds
+//      (x + 0.0 is exact for an accumulator that started at +0.0), skewed by one pad slot per 8 rows: both the 8-byte row stores of the
+//      group decode (lane stride 8 rows) and the 8-byte row loads of the window blocks (lane stride 8 windows) then walk the banks with
+//      an odd stride of 9 words -- conflict-free;
+//   O  the series' T results, leaving with one cp.async.bulk store that overlaps the next series' decode.
+// Phases of a series (all 32 lanes, only __syncwarp between them):
+//   setup    lane c = chunk c: header parse, regularity checks, window plan (touch interval, block list, row positions).  The plan
+//            depends on (init, nrows, endTime) of the chunks only, so it is reused while consecutive series share those (memo);
+//   decode   lane = NibblePack group (two groups per lane): branch-free field extraction, XOR prefix inside the group, warp-wide
+//            XOR scan over the group totals, rows stored once;
+//   windows  item = (chunk, block of 8 windows), two items per lane: register-blocked sequential sums in the reference's row order
+//            (DoubleVector.scala:243-253, AggrOverTimeFunctions.scala:560-571).  A window that takes rows from two chunks gets one
+//            partial sum from each chunk's block list; a short fix-up pass adds them in chunk order.
+// Anything outside this fast path (irregular timestamps, DDV-long values, > 4 chunks, NaN / Inf / denormal / zero values, windows
+// shorter than 9 rows, windows over three chunks ...) is appended to the fallback list and answered by the v2 kernel into the same
+// output buffer, exactly as the tile kernel does.
+#pragma once
+#include "scan_tile.cuh"
+#include "scan_wp_layout.h"
+
+namespace filo {
+
+// shared-memory word loads by byte offset (keeps the field extraction in the shared window: LDS, not generic loads)
+#ifdef FILO_CUSIM
+__device__ __forceinline__ uint32_t wp_soff(const void* p) { return (uint32_t)(reinterpret_cast<const uint8_t*>(p) - smem); }
+__device__ __forceinline__ uint32_t wp_lds32(uint32_t off) { uint32_t v; std::memcpy(&v, smem + off, 4); return v; }
+#else
+__device__ __forceinline__ uint32_t wp_soff(const void* p) { return smem_u32(p); }
+__device__ __forceinline__ uint32_t wp_lds32(uint32_t off) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(off)); return v; }
+#endif
+
+__device__ __forceinline__ int wp_vidx(int p) { return p + (p >> 3); }
+
+// finish of one window of a SUM-class function from (sum over the rows, number of rows); values are known to be finite, normal and
+// of moderate magnitude (the decode checked), so the invariant division needs no range test
+template <int FN>
+__device__ __forceinline__ double wp_finish(double cs, int nn, double div, double rcp, int nfull, double rcpn) {
+  if (FN == FN_COUNT) return (double)nn;
+  if (FN == FN_RATE) { const double q0 = __dmul_rn(cs, rcp); const double r = __fma_rn(-q0, div, cs); return __dmul_rn(__fma_rn(r, rcp, q0), 1000.0); }
+  if (FN == FN_AVG) {
+    if (nn == nfull) { const double q0 = __dmul_rn(cs, rcpn); const double r = __fma_rn(-q0, (double)nfull, cs); return __fma_rn(r, rcpn, q0); }
+    return cs / (double)nn;
+  }
+  return cs;
+}
+
+// the last two row groups of a block: rows 8q .. Wr + 7 with Wr = 8q + U.  Row t of group q feeds windows max(0, t - U) .. 7, row t < U of
+// group q + 1 feeds windows 8 + t - U .. 7 (window w takes rows w .. w + Wr of the block)
+template <int U>
+__device__ __forceinline__ void wp_block_tail(const double* __restrict__ pa, const double* __restrict__ pb, double a[WP_R], double b[WP_R]) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const double va = pa[t], vb = pb[t];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) if (w >= t - U) { a[w] += va; b[w] += vb; }
+  }
+#pragma unroll
+  for (int t = 0; t < U; ++t) {
+    const double va = pa[9 + t], vb = pb[9 + t];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) if (w >= 8 + t - U) { a[w] += va; b[w] += vb; }
+  }
+}
+
+// two blocks per lane: a[w] / b[w] = sum of rows w .. w + Wr (in row order, starting from +0.0) of the block at pa / pb.  Wr >= 8.
+__device__ __forceinline__ void wp_block_pair(const double* __restrict__ pa, const double* __restrict__ pb, int Wr, double a[WP_R], double b[WP_R]) {
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { a[w] = 0.0; b[w] = 0.0; }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {                        // group 0: row t feeds windows 0 .. t
+    const double va = pa[t], vb = pb[t];
+#pragma unroll
+    for (int w = 0; w <= t; ++w) { a[w] += va; b[w] += vb; }
+  }
+  const int q = Wr >> 3;
+  pa += 9; pb += 9;
+  for (int m = 1; m < q; ++m, pa += 9, pb += 9) {      // full groups: every window
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const double va = pa[t], vb = pb[t];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { a[w] += va; b[w] += vb; }
+    }
+  }
+  switch (Wr & 7) {
+    case 0: wp_block_tail<0>(pa, pb, a, b); break;
+    case 1: wp_block_tail<1>(pa, pb, a, b); break;
+    case 2: wp_block_tail<2>(pa, pb, a, b); break;
+    case 3: wp_block_tail<3>(pa, pb, a, b); break;
+    case 4: wp_block_tail<4>(pa, pb, a, b); break;
+    case 5: wp_block_tail<5>(pa, pb, a, b); break;
+    case 6: wp_block_tail<6>(pa, pb, a, b); break;
+    default: wp_block_tail<7>(pa, pb, a, b); break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SUM-class kernel: sum / avg / count_over_time, rate / increase on delta-temporality schemas.  No across-series aggregate.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int FN>
+__global__ void __launch_bounds__(WP_MAX_WARPS * 32, 1)
+scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, int64_t n_series, QueryParams q,
+                   double* __restrict__ out, WpSmem L, int64_t* __restrict__ fallback_list, unsigned long long* __restrict__ fallback_count,
+                   unsigned long long* d_counters, int* d_err) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* wb = smem + (size_t)warp * L.per_warp;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wb);
+  WpChunk* CD = reinterpret_cast<WpChunk*>(wb + L.desc);
+  uint64_t* xtab = reinterpret_cast<uint64_t*>(wb + L.jbuf);     // decode: exclusive XOR prefix per group slot (dead before J is written)
+  double* J = reinterpret_cast<double*>(wb + L.jbuf);
+  uint8_t* R = wb + L.rec;
+  double* V = reinterpret_cast<double*>(wb + L.vals);
+  double* O = reinterpret_cast<double*>(wb + L.out);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  __syncwarp();
+
+  int64_t winDur = q.inclusive ? q.window : q.window - 1; if (winDur < 0) winDur = 0;
+  const double fdiv = (double)(q.inclusive ? winDur : winDur + 1), frcp = 1.0 / fdiv;     // RateFunctions.scala:436-442
+  const int64_t S0 = q.start - winDur, E0 = q.start;
+  const int64_t lastEnd = q.start + (int64_t)(q.T - 1) * q.step;
+  StepDiv sd; sd.init(q.step);
+  const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
+
+  // memo of the window plan (lane c holds chunk c's key; the plan itself stays in CD)
+  int64_t m_init = 0, m_end = 0; int m_nrows = -1, m_n = -1; bool m_ok = false;
+  int p_Wr = 0, p_items = 0, p_nfull = 0; double p_rcpn = 0.0;
+  int64_t rows_scanned = 0, bytes_scanned = 0;
+  uint32_t parity = 0;
+
+  auto issue = [&](int64_t off, uint32_t sz) {            // lane 0: fetch a record into R
+    mbar_expect_tx(bar, sz);
+    tma_load_1d(R, arena + off, sz, bar);
+  };
+  int64_t cur_off = 0; uint32_t cur_sz = 0;
+  if (s < n_series) { cur_off = rec_off[s]; cur_sz = (uint32_t)(rec_off[s + 1] - cur_off); }
+  if (s < n_series && cur_sz <= L.rec_cap && lane == 0) issue(cur_off, cur_sz);
+
+  for (; s < n_series; s += nwarps) {
+    const int64_t sn = s + nwarps;
+    int64_t nxt_off = 0; uint32_t nxt_sz = 0;
+    if (sn < n_series) { nxt_off = rec_off[sn]; nxt_sz = (uint32_t)(rec_off[sn + 1] - nxt_off); }
+    const bool staged = cur_sz <= L.rec_cap;
+    if (staged) { mbar_wait(bar, parity); parity ^= 1; }
+    // ------------------------------------------------------------------------------------------------ setup (lane c = chunk c)
+    bool regular = staged;
+    int n = 0, cLo = 0;
+    if (staged) {
+      const RecordHeader* h = reinterpret_cast<const RecordHeader*>(R);
+      const ChunkEntry* Eall = reinterpret_cast<const ChunkEntry*>(R + sizeof(RecordHeader));
+      const int nch = (int)h->n_chunks;
+      regular = nch <= 32 && (h->flags & REC_ALL_TS_CONST) != 0;
+      const int64_t t1 = q.start - q.window, t2 = q.end;
+      bool below = false, within = false;
+      if (regular && lane < nch) { below = Eall[lane].end_time < t1; within = !below && Eall[lane].start_time <= t2; }
+      const unsigned mb = __ballot_sync(FULL, below), mw = __ballot_sync(FULL, within);
+      cLo = __ffs((int)~mb) - 1; if (cLo < 0) cLo = 32;                         // chunks are time-ordered: `below` is a prefix
+      const unsigned rest = cLo < 32 ? (mw >> cLo) : 0u;
+      n = __ffs((int)~rest) - 1; if (n < 0) n = 32;
+      if (n > WP_MAXC) regular = false;
+    }
+    const int c = lane;
+    bool have = regular && c < n;
+    int64_t init = 0, end_time = 0; int nrows = 0, num_rows = 0, vbytes = 0, ng = 0, vwire = 0; uint32_t voff = 0, w12 = 0;
+    bool okc = true;
+    if (have) {
+      const ChunkEntry& e = reinterpret_cast<const ChunkEntry*>(R + sizeof(RecordHeader))[cLo + c];
+      const uint8_t* tv = R + e.ts_off; const uint8_t* vv = R + e.val_off;
+      vwire = (int)(ld32(vv + 4) & 0xffff);
+      const int tlen = (int)ld32(tv + 8); init = (int64_t)ld64_a4(tv + 12); const int slope = (int)ld32(tv + 20);
+      end_time = e.end_time; num_rows = e.num_rows; voff = e.val_off;
+      vbytes = (int)ld32(tv) + 4 + (int)ld32(vv) + 4;
+      int vlen = 0;
+      if (vwire == WIRE_XOR) { vlen = (int)ld32(vv + XOR_OFF_N); w12 = ld32(vv + XOR_OFF_NGROUPS); ng = (int)(w12 & 0xffff); if (ng != (vlen + 6) / 8) okc = false; }
+      else if (vwire == WIRE_RAW64) vlen = ((int)ld32(vv) - 4) / 8;
+      else okc = false;
+      if ((int64_t)slope != q.step || tlen <= 0 || vlen <= 0 || num_rows <= 0) okc = false;
+      nrows = num_rows < tlen ? num_rows : tlen;
+      if (vlen != nrows) okc = false;                       // the decode writes every row of the vector
+      if (end_time < init + (int64_t)(nrows - 1) * q.step) okc = false;       // endTime covers the rows: a chunk with rows in a window is in its chunk set
+    }
+    {
+      const int64_t endp = __shfl_up_sync(FULL, end_time, 1);
+      if (have && c > 0 && !(endp < init)) okc = false;       // time-ordered, and the previous chunk is out of the chunk set before this one's rows
+      if (!__all_sync(FULL, okc)) regular = false;
+    }
+    have = have && regular;
+    if (!have) { ng = 0; nrows = 0; }
+    // group slots: exclusive prefix over the chunks
+    int grp_base = ng;
+    { const int a0 = __shfl_sync(FULL, ng, 0), a1 = __shfl_sync(FULL, ng, 1), a2 = __shfl_sync(FULL, ng, 2), a3 = __shfl_sync(FULL, ng, 3);
+      grp_base = (c > 0 ? a0 : 0) + (c > 1 ? a1 : 0) + (c > 2 ? a2 : 0);
+      if (a0 + a1 + a2 + a3 > WP_MAXG) regular = false; }
+    const int ngroups = __shfl_sync(FULL, grp_base + ng, WP_MAXC - 1);
+    // ---- window plan, reused while the chunk shapes repeat
+    const bool samec = !(c < n) || (init == m_init && nrows == m_nrows && end_time == m_end);
+    const bool same_all = __all_sync(FULL, samec);
+    const bool same = m_ok && n == m_n && same_all;
+    if (regular && !same) {
+      m_init = init; m_end = end_time; m_nrows = nrows; m_n = n; m_ok = false;
+      int64_t s0 = 0, e0 = 0;
+      if (have) { s0 = sd.ceil_div(S0 - init); e0 = sd.floor_div(E0 - init); }
+      const int Wr = (int)(e0 - s0);
+      int64_t kT0 = -e0; if (kT0 < 0) kT0 = 0;
+      int64_t kT1 = (int64_t)(nrows - 1) - s0; if (kT1 > q.T - 1) kT1 = q.T - 1;
+      const bool touch = have && kT0 <= kT1;
+      if (!touch) { kT0 = 0x3fffffff; kT1 = -1; }
+      const int Wr0 = __shfl_sync(FULL, Wr, 0);
+      bool okp = !have || Wr == Wr0;
+      if (Wr0 < 8 || (uint32_t)Wr0 + 1 > L.jcap) okp = false;
+      // touched chunks must be contiguous, and a window may take rows from at most two chunks
+      const unsigned tm = __ballot_sync(FULL, touch) & 0xfu;
+      if (tm != 0) { const unsigned lowbit = tm & (0u - tm); const unsigned filled = tm + lowbit; if ((filled & (filled - 1)) != 0) okp = false; }
+      const int64_t kT1p = __shfl_up_sync(FULL, kT1, 1), kT1pp = __shfl_up_sync(FULL, kT1, 2), kT0n = __shfl_down_sync(FULL, kT0, 1);
+      const bool prev_t = c > 0 && ((tm >> (c - 1)) & 1u), next_t = c + 1 < WP_MAXC && ((tm >> (c + 1)) & 1u);
+      if (touch && c >= 2 && ((tm >> (c - 2)) & 1u) && !(kT1pp < kT0)) okp = false;
+      int64_t ownLo = kT0, ownHi = kT1;
+      if (touch && prev_t && kT1p + 1 > ownLo) ownLo = kT1p + 1;
+      if (touch && next_t && kT0n - 1 < ownHi) ownHi = kT0n - 1;
+      const int hs = touch ? (int)(ownLo - kT0) : 0;
+      const int nblk = touch ? (int)((kT1 - kT0 + WP_R) / WP_R) : 0;
+      int blk0, items, joff, jtot;
+      { const int a0 = __shfl_sync(FULL, nblk, 0), a1 = __shfl_sync(FULL, nblk, 1), a2 = __shfl_sync(FULL, nblk, 2), a3 = __shfl_sync(FULL, nblk, 3);
+        blk0 = (c > 0 ? a0 : 0) + (c > 1 ? a1 : 0) + (c > 2 ? a2 : 0); items = a0 + a1 + a2 + a3; }
+      { const int a0 = __shfl_sync(FULL, hs, 0), a1 = __shfl_sync(FULL, hs, 1), a2 = __shfl_sync(FULL, hs, 2), a3 = __shfl_sync(FULL, hs, 3);
+        joff = (c > 0 ? a0 : 0) + (c > 1 ? a1 : 0) + (c > 2 ? a2 : 0); jtot = a0 + a1 + a2 + a3; }
+      if ((uint32_t)jtot > L.jcap) okp = false;
+      // row positions: chunk after chunk, Wr .. Wr + 7 zero rows in between, every chunk's block 0 at a multiple of 8
+      const int fr = touch ? (int)(s0 + kT0) : 0;              // first row of block 0 (may be negative: zero rows in front)
+      int rowpos = 0;
+      {
+        int base = 0;                                           // first position this chunk's rows may take
+#pragma unroll
+        for (int cc = 0; cc < WP_MAXC; ++cc) {
+          int x;
+          if (cc == 0) { x = fr < 0 ? -fr : ((8 - (fr & 7)) & 7); }
+          else { x = base + ((-(base + fr)) & 7); }
+          if (c == cc) rowpos = x;
+          const int nb = __shfl_sync(FULL, x + nrows + Wr0, cc);   // (lane cc's own x is the valid one)
+          base = nb;
+        }
+      }
+      const int pend = __shfl_sync(FULL, rowpos + nrows, n > 0 ? n - 1 : 0) + Wr0 + 8;
+      if ((uint32_t)(pend + (pend >> 3) + 2) > L.vcap) okp = false;
+      if (!__all_sync(FULL, okp)) regular = false;
+      if (regular) {
+        if (c < WP_MAXC) {
+          WpChunk& d = CD[c];
+          d.kT0 = (int)kT0; d.kT1 = (int)kT1; d.ownLo = (int)ownLo; d.ownHi = (int)ownHi; d.blk0 = blk0; d.nblk = nblk;
+          d.vidx0 = wp_vidx(rowpos + fr); d.rowpos = rowpos; d.nrows = nrows; d.s0 = (int)s0; d.e0 = (int)e0; d.joff = joff; d.hs = hs;
+        }
+        p_Wr = Wr0; p_items = items; p_nfull = Wr0 + 1; p_rcpn = 1.0 / (double)(Wr0 + 1);
+        __syncwarp();
+        // zero rows: in front of chunk 0, between chunks, behind the last chunk (+ slack the last block's unused windows read)
+        for (int g = 0; g <= n; ++g) {
+          const int g0 = g == 0 ? 0 : CD[g - 1].rowpos + CD[g - 1].nrows;
+          const int g1 = g == n ? pend : CD[g].rowpos;
+          for (int p = g0 + lane; p < g1; p += 32) V[wp_vidx(p)] = 0.0;
+        }
+        m_ok = true;
+      }
+    }
+    if (!regular) {
+      // declined: the v2 kernel answers this series
+      if (lane == 0) { const unsigned long long slot = atomicAdd(fallback_count, 1ull); fallback_list[slot] = s; }
+      __syncwarp();
+      if (sn < n_series && nxt_sz <= L.rec_cap && lane == 0) issue(nxt_off, nxt_sz);
+      cur_off = nxt_off; cur_sz = nxt_sz;
+      continue;
+    }
+    // per-series parts of the descriptors
+    if (c < WP_MAXC) {
+      WpChunk& d = CD[c];
+      d.grp_base = have ? grp_base : 0x7fffffff; d.ng = ng; d.wire = vwire; d.val_off = voff;
+      if (have && vwire == WIRE_XOR) { const uint32_t po = w12 >> 16; d.first = ld64(R + voff + po); d.grp_off = voff + po + 8; d.tab_off = voff + XOR_OFF_GROUPTAB; }
+      else { d.first = have ? ld64(R + voff + 8) : 0ull; d.grp_off = 0; d.tab_off = 0; }
+    }
+    // scan counters (CountingChunkInfoIterator, ChunkSetInfo.scala:336-380): every chunk in range is pulled, except one that starts
+    // after the last window end
+    int cnt_rows = 0, cnt_bytes = 0;
+    { const int64_t endp = __shfl_up_sync(FULL, end_time, 1);
+      if (have && !(c > 0 && !(endp < lastEnd))) { cnt_rows = num_rows; cnt_bytes = vbytes; } }
+#pragma unroll
+    for (int o = 1; o < WP_MAXC; o <<= 1) { cnt_rows += __shfl_xor_sync(FULL, cnt_rows, o); cnt_bytes += __shfl_xor_sync(FULL, cnt_bytes, o); }
+    __syncwarp();
+    // ------------------------------------------------------------------------------------------------ decode
+    uint32_t okbits = 0xffffffffu;        // bit 30 stays set while every value has exponent bits 10 and 9 different: 2^-511 <= |x| < 2^513
+    {
+      const int gb1 = CD[1].grp_base, gb2 = CD[2].grp_base, gb3 = CD[3].grp_base;
+      uint64_t d[2][8]; int cc[2]; bool act[2];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int slot = jj * 32 + lane;
+        const bool active = slot < ngroups;
+        const int ci = (slot >= gb1 ? 1 : 0) + (slot >= gb2 ? 1 : 0) + (slot >= gb3 ? 1 : 0);
+        const WpChunk& ch = CD[active ? ci : 0];
+        cc[jj] = active ? ci : 0; act[jj] = active;
+        const uint8_t* gp = R;
+        if (active) gp = R + ch.grp_off + reinterpret_cast<const uint16_t*>(R + ch.tab_off)[slot - ch.grp_base];
+        const uint32_t mask = active ? gp[0] : 0u;
+        const uint32_t hdr = gp[1];
+        const uint32_t numBits = ((hdr >> 4) + 1) * 4;
+        const uint32_t tz = (hdr & 0x0f) * 4;
+        const uint64_t fm = (~0ull >> (64 - numBits)) << tz;       // the field's bits in the value
+        // bit address (in shared memory) of the 64-bit window that has field 0 at bit tz
+        uint32_t xb = (wp_soff(gp + 2) << 3) - tz;
+        uint64_t x = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool on = (mask >> i) & 1u;
+          const uint32_t wa = (xb >> 3) & ~3u;
+          const uint32_t w0 = wp_lds32(wa), w1 = wp_lds32(wa + 4), w2 = wp_lds32(wa + 8);
+          const uint32_t lo = __funnelshift_r(w0, w1, xb), hi = __funnelshift_r(w1, w2, xb);
+          const uint64_t f = on ? fm : 0ull;
+          x ^= (((uint64_t)hi << 32) | lo) & f;                    // running XOR of the fields, already shifted by tz
+          xb += on ? numBits : 0u;
+          d[jj][i] = x;
+        }
+      }
+      // exclusive XOR scan of the group totals over the 64 slots
+      uint64_t i0x = d[0][7], i1x = d[1][7];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y0 = shfl_up_u64(i0x, o), y1 = shfl_up_u64(i1x, o);
+        if (lane >= o) { i0x ^= y0; i1x ^= y1; }
+      }
+      const uint64_t tot0 = shfl_u64(i0x, 31);
+      const uint64_t ex0 = i0x ^ d[0][7], ex1 = i1x ^ d[1][7] ^ tot0;
+      xtab[lane] = ex0; xtab[32 + lane] = ex1;
+      __syncwarp();
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const WpChunk& ch = CD[cc[jj]];
+        const int g = act[jj] ? jj * 32 + lane - ch.grp_base : 0;
+        // value before the group = first ^ (prefix at the slot) ^ (prefix at the chunk's first slot)
+        const uint64_t pre = ch.first ^ (jj ? ex1 : ex0) ^ xtab[act[jj] ? ch.grp_base : 0];
+        const int p = ch.rowpos + 1 + g * 8;
+        double* dst = V + wp_vidx(p);
+        const int t = p & 7;                                       // rows t' with t + t' >= 8 sit one pad slot further
+        if (act[jj]) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint64_t b = d[jj][i] ^ pre;
+            reinterpret_cast<uint64_t*>(dst)[i + ((t + i) >> 3)] = b;
+            const uint32_t h = (uint32_t)(b >> 32);
+            okbits &= h ^ (h << 1);
+          }
+          if (g == 0) { V[wp_vidx(p - 1)] = __longlong_as_double((long long)ch.first); const uint32_t h = (uint32_t)(ch.first >> 32); okbits &= h ^ (h << 1); }
+        }
+      }
+      // raw f64 vectors: plain copy
+      for (int ci = 0; ci < n; ++ci) {
+        const WpChunk& ch = CD[ci];
+        if (ch.wire != WIRE_RAW64) continue;
+        const uint64_t* src = reinterpret_cast<const uint64_t*>(R + ch.val_off + 8);
+        for (int r = lane; r < ch.nrows; r += 32) {
+          const uint64_t b = src[r];
+          reinterpret_cast<uint64_t*>(V)[wp_vidx(ch.rowpos + r)] = b;
+          const uint32_t h = (uint32_t)(b >> 32);
+          okbits &= h ^ (h << 1);
+        }
+      }
+    }
+    const bool vals_ok = __all_sync(FULL, (okbits >> 30) & 1u);
+    __syncwarp();
+    // R is dead: fetch the next record behind the window phase
+    if (sn < n_series && nxt_sz <= L.rec_cap && lane == 0) issue(nxt_off, nxt_sz);
+    cur_off = nxt_off; cur_sz = nxt_sz;
+    // the last group of an XOR chunk decodes up to 7 rows past the chunk: back to zero (lane = chunk * 8 + row)
+    {
+      const int ci = lane >> 3, i = lane & 7;
+      if (ci < n && i < 7) { const WpChunk& ch = CD[ci]; if (ch.wire == WIRE_XOR) V[wp_vidx(ch.rowpos + ch.nrows + i)] = 0.0; }
+    }
+    if (!vals_ok) {
+      // NaN / Inf / zero / denormal / very large or small values: the literal kernel answers (it needs the NaN-aware sums)
+      if (lane == 0) { const unsigned long long slot = atomicAdd(fallback_count, 1ull); fallback_list[slot] = s; }
+      __syncwarp();
+      continue;
+    }
+    if (lane == 0) { rows_scanned += cnt_rows; bytes_scanned += cnt_bytes; tma_store_wait_read(); }    // the previous series' bulk store has read O
+    __syncwarp();
+    // ------------------------------------------------------------------------------------------------ windows
+    const int osh = (int)(((int64_t)s * q.T) & 1);              // O[k + osh]: the 16-byte aligned part of the row is 16-byte aligned in O too
+    double* Oo = O + osh;
+    {
+      const int Wr = p_Wr;
+      const int b1 = CD[1].blk0, b2 = CD[2].blk0, b3 = CD[3].blk0;
+      const int n1 = CD[1].nblk, n2 = CD[2].nblk, n3 = CD[3].nblk;
+      for (int it0 = 0; it0 < p_items; it0 += 64) {
+        const double* pp[2]; int k0[2], jOwnLo[2], jOwnHi[2], jT1[2], rs0[2], nr[2]; double* jp[2];
+#pragma unroll
+        for (int X = 0; X < 2; ++X) {
+          const int it = it0 + X * 32 + lane;
+          const bool active = it < p_items;
+          // chunk of the item: the last chunk with blocks whose blk0 <= it
+          int ci = 0;
+          if (n1 > 0 && it >= b1) ci = 1;
+          if (n2 > 0 && it >= b2) ci = 2;
+          if (n3 > 0 && it >= b3) ci = 3;
+          const WpChunk& ch = CD[ci];
+          const int b = active ? it - ch.blk0 : 0;
+          pp[X] = V + ch.vidx0 + 9 * b;
+          k0[X] = ch.kT0 + WP_R * b;
+          jOwnLo[X] = active ? ch.ownLo - k0[X] : -1000; jOwnHi[X] = ch.ownHi - k0[X]; jT1[X] = active ? ch.kT1 - k0[X] : -1;
+          jp[X] = J + ch.joff + WP_R * b;
+          rs0[X] = ch.s0 + k0[X]; nr[X] = ch.nrows;
+        }
+        double a[WP_R], bb[WP_R];
+        wp_block_pair(pp[0], pp[1], Wr, a, bb);
+#pragma unroll
+        for (int X = 0; X < 2; ++X) {
+          double* op = Oo + k0[X];
+#pragma unroll
+          for (int j = 0; j < WP_R; ++j) {
+            const double raw = X ? bb[j] : a[j];
+            int nn = 1;
+            if (FN == FN_AVG || FN == FN_COUNT) {
+              int lo = rs0[X] + j; const int hi0 = lo + Wr; if (lo < 0) lo = 0;
+              const int hi = hi0 > nr[X] - 1 ? nr[X] - 1 : hi0;
+              nn = hi - lo + 1;
+            }
+            const double fin = wp_finish<FN>(raw, nn, fdiv, frcp, p_nfull, p_rcpn);
+            if (j >= jOwnLo[X] && j <= jT1[X]) op[j] = j <= jOwnHi[X] ? fin : raw;
+            if (j < jOwnLo[X]) jp[X][j] = raw;
+          }
+        }
+      }
+      __syncwarp();
+      // windows with rows from two chunks: (0 + partial of the earlier chunk) + partial of the later one, AggrOverTimeFunctions.scala:560-571
+      for (int ci = 1; ci < n; ++ci) {
+        const WpChunk& ch = CD[ci]; const WpChunk& cp = CD[ci - 1];
+        for (int i = lane; i < ch.hs; i += 32) {
+          const int k = ch.kT0 + i;
+          const double v = Oo[k] + J[ch.joff + i];
+          int nn = 1;
+          if (FN == FN_AVG || FN == FN_COUNT) {
+            int lo = cp.s0 + k; if (lo < 0) lo = 0; int hi = cp.s0 + k + Wr; if (hi > cp.nrows - 1) hi = cp.nrows - 1;
+            int lo2 = ch.s0 + k; if (lo2 < 0) lo2 = 0; int hi2 = ch.s0 + k + Wr; if (hi2 > ch.nrows - 1) hi2 = ch.nrows - 1;
+            nn = (hi - lo + 1) + (hi2 - lo2 + 1);
+          }
+          Oo[k] = wp_finish<FN>(v, nn, fdiv, frcp, p_nfull, p_rcpn);
+        }
+      }
+      // windows without rows: NaN (no chunk contributes: AggrOverTimeFunctions.scala:560-571 leaves the NaN seed)
+      {
+        int prev = -1;
+        for (int ci = 0; ci <= n; ++ci) {
+          int gend = q.T;
+          if (ci < n) { if (CD[ci].nblk == 0) continue; gend = CD[ci].kT0; }
+          for (int k = prev + 1 + lane; k < gend; k += 32) Oo[k] = NaNv;
+          if (ci < n) prev = CD[ci].kT1;
+        }
+      }
+    }
+    // ------------------------------------------------------------------------------------------------ result row
+    fence_async_smem();
+    __syncwarp();
+    {
+      double* gout = out + (size_t)s * q.T;
+      const int kb = osh, nbody = (q.T - kb) & ~1;
+      if (out_aligned && nbody > 0) {
+        if (lane == 0) tma_store_1d(gout + kb, Oo + kb, (uint32_t)nbody * 8u);
+        if (lane == 1 && kb) gout[0] = Oo[0];
+        if (lane == 2 && kb + nbody < q.T) gout[q.T - 1] = Oo[q.T - 1];
+      } else {
+        for (int k = lane; k < q.T; k += 32) gout[k] = Oo[k];
+      }
+    }
+  }
+  if (lane == 0) {
+    tma_store_wait_read();
+    if (rows_scanned | bytes_scanned) { atomicAdd(&d_counters[0], (unsigned long long)rows_scanned); atomicAdd(&d_counters[1], (unsigned long long)bytes_scanned); }
+  }
+}
+
+} // namespace filo

@@ -1,0 +1,52 @@
+// Shared-memory layout of the v4 warp-pipeline kernel (scan_wp.cuh); plain structs, usable from host code.
+#pragma once
+#include <stdint.h>
+#include "filo_record.h"
+#include "scan_params.h"
+namespace filo {
+constexpr int WP_MAXC = 4;             // chunks in range per series on this path
+constexpr int WP_MAXG = 64;            // NibblePack groups per series (two per lane)
+constexpr int WP_R = 8;                // windows per block
+constexpr int WP_MAX_WARPS = 16;       // warps per CTA (one CTA per SM)
+
+struct WpChunk {                       // per warp, per chunk in range (shared memory)
+  uint64_t first;                      // XOR vectors: bits of the first value
+  int32_t kT0, kT1;                    // windows whose (unclamped) row range meets the chunk's rows, clipped to [0, T)
+  int32_t ownLo, ownHi;                // ... of which only this chunk contributes to [ownLo, ownHi]
+  int32_t blk0, nblk;                  // block items of this chunk: [blk0, blk0 + nblk)
+  int32_t vidx0;                       // V index of the first row of block 0
+  int32_t rowpos;                      // V position (before skewing) of row 0
+  int32_t nrows, s0, e0;               // rows; unclamped first / last row of window 0
+  int32_t grp_base, ng, wire;          // group slots [grp_base, grp_base + ng)
+  uint32_t grp_off, tab_off, val_off;  // byte offsets in R: first group, u16 group table, value vector
+  int32_t joff, hs;                    // head share: windows [kT0, ownLo) also take rows from the previous chunk; partials at J[joff ..]
+  int32_t pad_;
+};
+static_assert(sizeof(WpChunk) == 88, "WpChunk");
+
+struct WpSmem {                        // byte offsets inside a warp's region, all multiples of 128
+  uint32_t desc, jbuf, rec, vals, out, per_warp;
+  uint32_t rec_cap, vcap /*doubles*/, jcap /*doubles*/, ocap /*doubles*/;
+  uint32_t warps;                      // warps per CTA
+};
+// wrows = window / step + 1: the most rows a window can span
+FILO_HD inline WpSmem wp_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t max_chunks, uint32_t T, uint32_t wrows) {
+  WpSmem L;
+  if (max_chunks > (uint32_t)WP_MAXC) max_chunks = WP_MAXC;
+  L.rec_cap = align_up(max_rec_bytes + 16, 128);
+  const uint32_t P = max_rows + (max_chunks + 1) * (wrows + 7) + 16;         // positions: rows + zero gaps + slack
+  L.vcap = align_up(P + P / 8 + 2, 16);
+  L.jcap = align_up((uint32_t)(WP_MAXC - 1) * wrows + 8, 16); if (L.jcap < 64) L.jcap = 64;    // also the XOR prefix table of the decode (64 words)
+  L.ocap = align_up(T + 2, 16);
+  uint32_t o = 128;                    // mbarrier slot
+  L.desc = o; o += align_up((uint32_t)(WP_MAXC * sizeof(WpChunk)), 128);
+  L.jbuf = o; o += align_up(L.jcap * 8, 128);
+  L.rec = o; o += L.rec_cap;
+  L.vals = o; o += align_up(L.vcap * 8, 128);
+  L.out = o; o += align_up(L.ocap * 8, 128);
+  L.per_warp = o;
+  L.warps = 0;
+  return L;
+}
+
+} // namespace filo

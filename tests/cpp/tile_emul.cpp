@@ -19,6 +19,7 @@ namespace filo { alignas(128) uint8_t smem[232448]; }          // `extern __shar
 struct Chunk { std::vector<uint8_t> ts, vv, info; };
 struct SeriesData { std::vector<std::unique_ptr<Chunk>> chunks; std::vector<uint8_t> record; };
 
+static long g_wp_declined = 0, g_wp_series = 0;
 static int g_jitter_ms = 0; static bool g_integral = false;      // irregular scrapes (DDV timestamps) / integral values (DoubleVector.optimize -> DDV longs)
 static void build_series(SeriesData& S, std::mt19937_64& rng, int rows, const std::vector<int>& chunk_rows, int64_t t0, int step_ms, int kind /*0 gauge 1 counter*/,
                          bool xor_enc, int nan_ppm, int reset_every) {
@@ -157,7 +158,7 @@ int main(int argc, char** argv) {
   std::mt19937_64 rng(4242);
   long checked = 0; int cases = 0;
   struct Cfg { int kind = 0; bool xor_enc = true; int fn = 0; std::vector<int> chunks; int nan_ppm = 0, reset_every = 0; int64_t window = 300000; int nser = 1; int inclusive = 1;
-               int64_t start_off = 0, end_off = 0; int agg_op = 0; int grid = 1; int jitter = 0; bool integral = false; bool v2_only = false; bool no_junction = false; bool warp_decode = false; };
+               int64_t start_off = 0, end_off = 0; int agg_op = 0; int grid = 1; int jitter = 0; bool integral = false; bool v2_only = false; bool no_junction = false; bool warp_decode = false; bool wp = false; };
   const std::vector<Cfg> cfgs = {
     {0, true, filo::FN_RATE, {400, 80}, 200000, 0, 300000, 11, 1, 0, 0, 0, 2},           // C2: gauge, delta-temporality rate (CLASS_SUM), NaN stale markers
     {0, true, filo::FN_SUM, {150, 90}, 0, 0, 300000, 37, 1, -90000, 45000, 0, 2},        // several tiles per CTA, a partial last tile, windows before / after the data
@@ -177,6 +178,16 @@ int main(int argc, char** argv) {
     {0, true, filo::FN_SUM, {33, 150, 7, 90}, 0, 0, 240000, 11, 0, 0, 0, 0, 3, 0, false, false, false, true},
     {1, true, filo::FN_RATE, {400, 80}, 0, 61, 300000, 13, 1, 0, 0, 0, 2, 0, false, false, false, true},            // ... counters with resets
     {1, true, filo::FN_INCREASE, {120, 120, 60}, 0, 41, 60000, 12, 1, -30000, 30000, filo::AGG_SUM, 2, 0, false, false, false, true},   // ... fused
+    // the v4 warp-pipeline kernel (scan_wp.cuh) for the SUM class, declines chained to the v2 kernel
+    {0, true, filo::FN_RATE, {400, 80}, 200000, 0, 300000, 23, 1, 0, 0, 0, 2, 0, false, false, false, false, true},                 // C2 shape, NaN stale markers (declined)
+    {0, true, filo::FN_SUM, {150, 90}, 0, 0, 300000, 37, 1, -90000, 45000, 0, 2, 0, false, false, false, false, true},              // windows before / after the data
+    {0, false, filo::FN_AVG, {200, 40}, 0, 0, 180000, 9, 0, 0, 0, 0, 1, 0, false, false, false, false, true},                       // raw f64, exclusive range start
+    {0, true, filo::FN_COUNT, {60, 60, 60, 60}, 0, 0, 600000, 9, 1, 30000, 0, 0, 3, 0, false, false, false, false, true},           // four chunks, windows over three chunks (declined)
+    {0, true, filo::FN_AVG, {100, 100, 100}, 0, 0, 300000, 24, 1, 0, 0, 0, 2, 0, false, false, false, false, true},                 // two junctions
+    {0, true, filo::FN_COUNT, {90, 70, 50, 30}, 0, 0, 240000, 16, 0, 15000, 0, 0, 2, 0, false, false, false, false, true},          // three junctions, exclusive start
+    {0, false, filo::FN_SUM, {64, 200}, 0, 0, 420000, 9, 1, 0, 0, 0, 1, 0, false, false, false, false, true},
+    {0, true, filo::FN_RATE, {100, 50, 50, 50, 50}, 0, 0, 300000, 10, 1, 0, 0, 0, 2, 0, false, false, false, false, true},          // five chunks: declined
+    {0, true, filo::FN_SUM, {33, 150, 7, 90}, 0, 0, 240000, 11, 0, 0, 0, 0, 3, 0, false, false, false, false, true},                // a 7-row chunk inside the windows
     // the v2 warp-per-series kernel on its own: every function class, irregular scrapes (DDV timestamps), integral values (DDV longs)
     {0, true, filo::FN_MIN, {150, 90}, 100000, 0, 300000, 9, 1, -30000, 15000, 0, 2, 0, false, true},
     {0, false, filo::FN_MAX, {64, 64, 64, 64, 64}, 0, 0, 200000, 7, 0, 0, 0, 0, 1, 0, false, true},
@@ -217,6 +228,7 @@ int main(int argc, char** argv) {
       c.v2_only = fr() % 4 == 0;
       c.no_junction = fr() % 8 == 0;
       c.warp_decode = fr() % 3 == 0;
+      c.wp = fr() % 2 == 0;
       if (c.v2_only) { const int fns[] = {filo::FN_MIN, filo::FN_MAX, filo::FN_LAST, filo::FN_TIMESTAMP, c.fn, c.fn}; c.fn = fns[fr() % 6]; c.agg_op = 0; }
       if (c.jitter) c.agg_op = 0;
       all.push_back(c);
@@ -262,7 +274,23 @@ int main(int argc, char** argv) {
       for (auto& S : SS) { filo::RecordHeader h; std::memcpy(&h, S.record.data(), sizeof h); sh.any_nonconst_ts |= !(h.flags & filo::REC_ALL_TS_CONST); sh.any_drop |= (h.flags & filo::REC_ANY_DROP) != 0; }
       const int cls = filo::fn_class_of(q.fn, q.cumulative);
       const bool tile_ok = !c.v2_only && (cls == filo::CLASS_SUM || cls == filo::CLASS_COUNTER);
-      if (tile_ok) {
+      if (tile_ok && c.wp && cls == filo::CLASS_SUM) {
+        filo::WpSmem W = filo::wp_layout(max_rec, (uint32_t)rows, (uint32_t)c.chunks.size(), (uint32_t)q.T, wrows);
+        W.warps = 3;
+        if ((size_t)W.per_warp * W.warps > sizeof(filo::smem)) { std::printf("FAIL: wp layout %u bytes per warp\n", W.per_warp); return 1; }
+        auto body = [&](auto fnc) {
+          cusim::launch(dim3((unsigned)A.grid), dim3(W.warps * 32), [&] {
+            filo::scan_wp_sum_kernel<decltype(fnc)::value>(A.arena, A.rec_off, A.S, A.q, A.out, W, A.flist, A.fcount, A.counters, A.derr);
+          });
+        };
+        if (q.fn == filo::FN_RATE) body(std::integral_constant<int, filo::FN_RATE>{});
+        else if (q.fn == filo::FN_AVG) body(std::integral_constant<int, filo::FN_AVG>{});
+        else if (q.fn == filo::FN_COUNT) body(std::integral_constant<int, filo::FN_COUNT>{});
+        else body(std::integral_constant<int, filo::FN_SUM>{});
+        if (derr[0]) { std::printf("FAIL cfg %zu: device error %d (wp kernel)\n", ci, derr[0]); return 1; }
+        g_wp_declined += (long)fcount; g_wp_series += c.nser;
+        if (fcount) run_v2(A, sh, flist.data(), &fcount);
+      } else if (tile_ok) {
         dispatch<false>(A);
         if (derr[0]) { std::printf("FAIL cfg %zu: device error %d (tile kernel)\n", ci, derr[0]); return 1; }
         if (fcount) run_v2(A, sh, flist.data(), &fcount);               // the fallback pass, as filo_query chains it
@@ -335,6 +363,7 @@ int main(int argc, char** argv) {
     }
     ++cases;
   }
+  std::printf("wp kernel: %ld of %ld series declined\n", g_wp_declined, g_wp_series);
   std::printf("OK %d cases, %ld values bit-exact (schedule seed %llu)\n", cases, checked, (unsigned long long)seed);
   return 0;
 }
