@@ -35,14 +35,22 @@ __device__ __forceinline__ uint32_t wp_lds32(uint32_t off) { uint32_t v; asm vol
 #endif
 
 __device__ __forceinline__ int wp_vidx(int p) { return p + (p >> 3); }
+// results are written once and not read again by the scan: streaming store
+#ifdef FILO_CUSIM
+__device__ __forceinline__ void wp_store_result(double* g, double v) { *g = v; }
+#else
+__device__ __forceinline__ void wp_store_result(double* g, double v) { __stcs(g, v); }
+#endif
 
 // finish of one window of a SUM-class function from (sum over the rows, number of rows); values are known to be finite, normal and
 // of moderate magnitude (the decode checked), so the invariant division needs no range test
 template <int FN>
-__device__ __forceinline__ double wp_finish(double cs, int nn, double div, double rcp, int nfull, double rcpn) {
+__device__ __forceinline__ double wp_finish(double cs, int nn, double div, double rcp, double scale, int nfull, double rcpn, bool raw) {
+  // raw blocks pass div = rcp = scale = 1: the sequence below then returns cs itself, bit for bit
+  if (FN == FN_RATE) { const double q0 = __dmul_rn(cs, rcp); const double r = __fma_rn(-q0, div, cs); return __dmul_rn(__fma_rn(r, rcp, q0), scale); }
   if (FN == FN_COUNT) return (double)nn;
-  if (FN == FN_RATE) { const double q0 = __dmul_rn(cs, rcp); const double r = __fma_rn(-q0, div, cs); return __dmul_rn(__fma_rn(r, rcp, q0), 1000.0); }
   if (FN == FN_AVG) {
+    if (raw) return cs;
     if (nn == nfull) { const double q0 = __dmul_rn(cs, rcpn); const double r = __fma_rn(-q0, (double)nfull, cs); return __fma_rn(r, rcpn, q0); }
     return cs / (double)nn;
   }
@@ -113,7 +121,7 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
   uint8_t* wb = smem + (size_t)warp * L.per_warp;
   uint64_t* bar = reinterpret_cast<uint64_t*>(wb);
   WpChunk* CD = reinterpret_cast<WpChunk*>(wb + L.desc);
-  uint64_t* xtab = reinterpret_cast<uint64_t*>(wb + L.jbuf);     // decode: exclusive XOR prefix per group slot (dead before J is written)
+  uint64_t* xtab = reinterpret_cast<uint64_t*>(wb + L.out);      // decode: exclusive XOR prefix per group slot (dead before O is written)
   double* J = reinterpret_cast<double*>(wb + L.jbuf);
   uint8_t* R = wb + L.rec;
   double* V = reinterpret_cast<double*>(wb + L.vals);
@@ -128,12 +136,11 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
   const int64_t S0 = q.start - winDur, E0 = q.start;
   const int64_t lastEnd = q.start + (int64_t)(q.T - 1) * q.step;
   StepDiv sd; sd.init(q.step);
-  const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
 
   // memo of the window plan (lane c holds chunk c's key; the plan itself stays in CD)
   int64_t m_init = 0, m_end = 0; int m_nrows = -1, m_n = -1; bool m_ok = false;
-  int p_Wr = 0, p_items = 0, p_nfull = 0; double p_rcpn = 0.0;
+  int p_Wr = 0, p_items = 0, p_nfull = 0, p_psi = 0; double p_rcpn = 0.0; bool p_gaps = true, p_oal = false;
   int64_t rows_scanned = 0, bytes_scanned = 0;
   uint32_t parity = 0;
 
@@ -228,11 +235,20 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
       if (touch && next_t && kT0n - 1 < ownHi) ownHi = kT0n - 1;
       const int hs = touch ? (int)(ownLo - kT0) : 0;
       const int nblk = touch ? (int)((kT1 - kT0 + WP_R) / WP_R) : 0;
-      int blk0, items, joff, jtot;
+      // whole blocks: [0, jzb) raw to J (the head share, rounded up), [tb, nblk) raw to O (from the block of ownHi + 1), own blocks in between
+      const int jzb = (hs + WP_R - 1) / WP_R;
+      const int tb = (touch && ownHi < kT1) ? (int)((ownHi + 1 - kT0) / WP_R) : nblk;
+      if (touch && jzb > tb) okp = false;
+      int blk0, items, joff, jtot, cov;
       { const int a0 = __shfl_sync(FULL, nblk, 0), a1 = __shfl_sync(FULL, nblk, 1), a2 = __shfl_sync(FULL, nblk, 2), a3 = __shfl_sync(FULL, nblk, 3);
         blk0 = (c > 0 ? a0 : 0) + (c > 1 ? a1 : 0) + (c > 2 ? a2 : 0); items = a0 + a1 + a2 + a3; }
-      { const int a0 = __shfl_sync(FULL, hs, 0), a1 = __shfl_sync(FULL, hs, 1), a2 = __shfl_sync(FULL, hs, 2), a3 = __shfl_sync(FULL, hs, 3);
+      { const int z = jzb * WP_R;
+        const int a0 = __shfl_sync(FULL, z, 0), a1 = __shfl_sync(FULL, z, 1), a2 = __shfl_sync(FULL, z, 2), a3 = __shfl_sync(FULL, z, 3);
         joff = (c > 0 ? a0 : 0) + (c > 1 ? a1 : 0) + (c > 2 ? a2 : 0); jtot = a0 + a1 + a2 + a3; }
+      { const int z = touch ? (int)(kT1 - kT0 + 1) - hs : 0;      // windows this chunk is the first to touch
+        cov = z;
+#pragma unroll
+        for (int o = 1; o < WP_MAXC; o <<= 1) cov += __shfl_xor_sync(FULL, cov, o); }
       if ((uint32_t)jtot > L.jcap) okp = false;
       // row positions: chunk after chunk, Wr .. Wr + 7 zero rows in between, every chunk's block 0 at a multiple of 8
       const int fr = touch ? (int)(s0 + kT0) : 0;              // first row of block 0 (may be negative: zero rows in front)
@@ -256,8 +272,14 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
         if (c < WP_MAXC) {
           WpChunk& d = CD[c];
           d.kT0 = (int)kT0; d.kT1 = (int)kT1; d.ownLo = (int)ownLo; d.ownHi = (int)ownHi; d.blk0 = blk0; d.nblk = nblk;
-          d.vidx0 = wp_vidx(rowpos + fr); d.rowpos = rowpos; d.nrows = nrows; d.s0 = (int)s0; d.e0 = (int)e0; d.joff = joff; d.hs = hs;
+          d.vidx0 = wp_vidx(rowpos + fr); d.rowpos = rowpos; d.nrows = nrows; d.s0 = (int)s0; d.e0 = (int)e0; d.joff = joff; d.hs = hs; d.jzb = jzb; d.tb = tb;
         }
+        p_gaps = __shfl_sync(FULL, cov, 0) != q.T;
+        // O is skewed like V (one pad slot per 8 windows, block starts of the first touched chunk on the 9-word grid): the 8-byte result
+        // stores of a warp (lane stride 8 windows) then spread over the banks.  p_oal: every chunk's blocks start on that grid
+        { const int first_t = tm ? __ffs((int)tm) - 1 : 0;
+          p_psi = (-(int)__shfl_sync(FULL, (int)(touch ? kT0 : 0), first_t)) & 7;
+          p_oal = __all_sync(FULL, !touch || (((int)kT0 + p_psi) & 7) == 0); }
         p_Wr = Wr0; p_items = items; p_nfull = Wr0 + 1; p_rcpn = 1.0 / (double)(Wr0 + 1);
         __syncwarp();
         // zero rows: in front of chunk 0, between chunks, behind the last chunk (+ slack the last block's unused windows read)
@@ -386,17 +408,17 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
       __syncwarp();
       continue;
     }
-    if (lane == 0) { rows_scanned += cnt_rows; bytes_scanned += cnt_bytes; tma_store_wait_read(); }    // the previous series' bulk store has read O
+    if (lane == 0) { rows_scanned += cnt_rows; bytes_scanned += cnt_bytes; }
     __syncwarp();
     // ------------------------------------------------------------------------------------------------ windows
-    const int osh = (int)(((int64_t)s * q.T) & 1);              // O[k + osh]: the 16-byte aligned part of the row is 16-byte aligned in O too
-    double* Oo = O + osh;
+    const int psi = p_psi;
+    auto oidx = [&](int k) -> int { return k + ((k + psi) >> 3); };
     {
       const int Wr = p_Wr;
       const int b1 = CD[1].blk0, b2 = CD[2].blk0, b3 = CD[3].blk0;
       const int n1 = CD[1].nblk, n2 = CD[2].nblk, n3 = CD[3].nblk;
       for (int it0 = 0; it0 < p_items; it0 += 64) {
-        const double* pp[2]; int k0[2], jOwnLo[2], jOwnHi[2], jT1[2], rs0[2], nr[2]; double* jp[2];
+        const double* pp[2]; double* op[2]; int jEnd[2], rs0[2], nr[2], ot[2]; bool rawm[2];
 #pragma unroll
         for (int X = 0; X < 2; ++X) {
           const int it = it0 + X * 32 + lane;
@@ -408,17 +430,20 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
           if (n3 > 0 && it >= b3) ci = 3;
           const WpChunk& ch = CD[ci];
           const int b = active ? it - ch.blk0 : 0;
+          const int k0 = ch.kT0 + WP_R * b;
           pp[X] = V + ch.vidx0 + 9 * b;
-          k0[X] = ch.kT0 + WP_R * b;
-          jOwnLo[X] = active ? ch.ownLo - k0[X] : -1000; jOwnHi[X] = ch.ownHi - k0[X]; jT1[X] = active ? ch.kT1 - k0[X] : -1;
-          jp[X] = J + ch.joff + WP_R * b;
-          rs0[X] = ch.s0 + k0[X]; nr[X] = ch.nrows;
+          const bool tojz = b < ch.jzb;                       // raw sums to J (every slot of the block exists there)
+          rawm[X] = tojz || b >= ch.tb;
+          op[X] = tojz ? J + ch.joff + WP_R * b : O + oidx(k0);
+          ot[X] = tojz ? 0 : (k0 + psi) & 7;                  // slots j with ot + j >= 8 sit one pad slot further
+          jEnd[X] = !active ? -1 : tojz ? WP_R : ch.kT1 - k0;
+          rs0[X] = ch.s0 + k0; nr[X] = ch.nrows;
         }
         double a[WP_R], bb[WP_R];
         wp_block_pair(pp[0], pp[1], Wr, a, bb);
 #pragma unroll
         for (int X = 0; X < 2; ++X) {
-          double* op = Oo + k0[X];
+          const double dv = rawm[X] ? 1.0 : fdiv, rc = rawm[X] ? 1.0 : frcp, sc = rawm[X] ? 1.0 : 1000.0;
 #pragma unroll
           for (int j = 0; j < WP_R; ++j) {
             const double raw = X ? bb[j] : a[j];
@@ -428,56 +453,70 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
               const int hi = hi0 > nr[X] - 1 ? nr[X] - 1 : hi0;
               nn = hi - lo + 1;
             }
-            const double fin = wp_finish<FN>(raw, nn, fdiv, frcp, p_nfull, p_rcpn);
-            if (j >= jOwnLo[X] && j <= jT1[X]) op[j] = j <= jOwnHi[X] ? fin : raw;
-            if (j < jOwnLo[X]) jp[X][j] = raw;
+            const double fin = wp_finish<FN>(raw, nn, dv, rc, sc, p_nfull, p_rcpn, rawm[X]);
+            if (X) bb[j] = fin; else a[j] = fin;
+          }
+        }
+        if (p_oal) {                                        // every block starts on O's 9-word grid: constant store offsets
+#pragma unroll
+          for (int j = 0; j < WP_R; ++j) { if (j <= jEnd[0]) op[0][j] = a[j]; if (j <= jEnd[1]) op[1][j] = bb[j]; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < WP_R; ++j) {
+            if (j <= jEnd[0]) op[0][j + ((ot[0] + j) >> 3)] = a[j];
+            if (j <= jEnd[1]) op[1][j + ((ot[1] + j) >> 3)] = bb[j];
           }
         }
       }
       __syncwarp();
-      // windows with rows from two chunks: (0 + partial of the earlier chunk) + partial of the later one, AggrOverTimeFunctions.scala:560-571
-      for (int ci = 1; ci < n; ++ci) {
-        const WpChunk& ch = CD[ci]; const WpChunk& cp = CD[ci - 1];
-        for (int i = lane; i < ch.hs; i += 32) {
+      // raw blocks: a window with rows from two chunks is (0 + partial of the earlier chunk) + partial of the later one
+      // (AggrOverTimeFunctions.scala:560-571); own windows that sit in a raw block are finished here as well
+      for (int ci = 0; ci < n; ++ci) {
+        const WpChunk& ch = CD[ci];
+        auto rows_in = [&](const WpChunk& x, int k) -> int {
+          int lo = x.s0 + k; if (lo < 0) lo = 0; int hi = x.s0 + k + Wr; if (hi > x.nrows - 1) hi = x.nrows - 1;
+          return hi - lo + 1;
+        };
+        // head: blocks [0, jzb)
+        const int nh = ch.jzb * WP_R < ch.kT1 - ch.kT0 + 1 ? ch.jzb * WP_R : ch.kT1 - ch.kT0 + 1;
+        for (int i = lane; i < nh; i += 32) {
           const int k = ch.kT0 + i;
-          const double v = Oo[k] + J[ch.joff + i];
+          double v = J[ch.joff + i]; int nn = 1;
+          if (FN == FN_AVG || FN == FN_COUNT) nn = rows_in(ch, k);
+          if (i < ch.hs) { v = O[oidx(k)] + v; if (FN == FN_AVG || FN == FN_COUNT) nn += rows_in(CD[ci - 1], k); }
+          O[oidx(k)] = wp_finish<FN>(v, nn, fdiv, frcp, 1000.0, p_nfull, p_rcpn, false);
+        }
+        // tail: own windows of block tb
+        for (int k = ch.kT0 + ch.tb * WP_R + lane; k <= ch.ownHi && ch.tb < ch.nblk; k += 32) {
           int nn = 1;
-          if (FN == FN_AVG || FN == FN_COUNT) {
-            int lo = cp.s0 + k; if (lo < 0) lo = 0; int hi = cp.s0 + k + Wr; if (hi > cp.nrows - 1) hi = cp.nrows - 1;
-            int lo2 = ch.s0 + k; if (lo2 < 0) lo2 = 0; int hi2 = ch.s0 + k + Wr; if (hi2 > ch.nrows - 1) hi2 = ch.nrows - 1;
-            nn = (hi - lo + 1) + (hi2 - lo2 + 1);
-          }
-          Oo[k] = wp_finish<FN>(v, nn, fdiv, frcp, p_nfull, p_rcpn);
+          if (FN == FN_AVG || FN == FN_COUNT) nn = rows_in(ch, k);
+          O[oidx(k)] = wp_finish<FN>(O[oidx(k)], nn, fdiv, frcp, 1000.0, p_nfull, p_rcpn, false);
         }
       }
       // windows without rows: NaN (no chunk contributes: AggrOverTimeFunctions.scala:560-571 leaves the NaN seed)
-      {
+      if (p_gaps) {
         int prev = -1;
         for (int ci = 0; ci <= n; ++ci) {
           int gend = q.T;
           if (ci < n) { if (CD[ci].nblk == 0) continue; gend = CD[ci].kT0; }
-          for (int k = prev + 1 + lane; k < gend; k += 32) Oo[k] = NaNv;
+          for (int k = prev + 1 + lane; k < gend; k += 32) O[oidx(k)] = NaNv;
           if (ci < n) prev = CD[ci].kT1;
         }
       }
     }
     // ------------------------------------------------------------------------------------------------ result row
-    fence_async_smem();
     __syncwarp();
     {
-      double* gout = out + (size_t)s * q.T;
-      const int kb = osh, nbody = (q.T - kb) & ~1;
-      if (out_aligned && nbody > 0) {
-        if (lane == 0) tma_store_1d(gout + kb, Oo + kb, (uint32_t)nbody * 8u);
-        if (lane == 1 && kb) gout[0] = Oo[0];
-        if (lane == 2 && kb + nbody < q.T) gout[q.T - 1] = Oo[q.T - 1];
-      } else {
-        for (int k = lane; k < q.T; k += 32) gout[k] = Oo[k];
-      }
+      // lane-consecutive windows: 256 contiguous bytes per store instruction; O index of window lane + 32 m = oidx(lane) + 36 m
+      double* gp = out + (size_t)s * q.T + lane;
+      const double* sp = O + oidx(lane);
+      int k = lane;
+#pragma unroll 4
+      for (; k < q.T; k += 32, gp += 32, sp += 36) wp_store_result(gp, *sp);
     }
+    __syncwarp();
   }
   if (lane == 0) {
-    tma_store_wait_read();
     if (rows_scanned | bytes_scanned) { atomicAdd(&d_counters[0], (unsigned long long)rows_scanned); atomicAdd(&d_counters[1], (unsigned long long)bytes_scanned); }
   }
 }

@@ -19,12 +19,14 @@ struct WpChunk {                       // per warp, per chunk in range (shared m
   int32_t nrows, s0, e0;               // rows; unclamped first / last row of window 0
   int32_t grp_base, ng, wire;          // group slots [grp_base, grp_base + ng)
   uint32_t grp_off, tab_off, val_off;  // byte offsets in R: first group, u16 group table, value vector
-  int32_t joff, hs;                    // head share: windows [kT0, ownLo) also take rows from the previous chunk; partials at J[joff ..]
+  int32_t joff, hs;                    // head share: windows [kT0, ownLo) also take rows from the previous chunk
+  int32_t jzb, tb;                     // blocks [0, jzb) (the head share rounded up to whole blocks) leave their raw sums at J[joff ..]; blocks [tb, nblk)
+                                       // (from the block that holds ownHi + 1) leave raw sums in O; the blocks in between hold own windows only
   int32_t pad_;
 };
-static_assert(sizeof(WpChunk) == 88, "WpChunk");
+static_assert(sizeof(WpChunk) == 96, "WpChunk");
 
-struct WpSmem {                        // byte offsets inside a warp's region, all multiples of 128
+struct WpSmem {                        // byte offsets inside a warp's region, all multiples of 16
   uint32_t desc, jbuf, rec, vals, out, per_warp;
   uint32_t rec_cap, vcap /*doubles*/, jcap /*doubles*/, ocap /*doubles*/;
   uint32_t warps;                      // warps per CTA
@@ -33,18 +35,19 @@ struct WpSmem {                        // byte offsets inside a warp's region, a
 FILO_HD inline WpSmem wp_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t max_chunks, uint32_t T, uint32_t wrows) {
   WpSmem L;
   if (max_chunks > (uint32_t)WP_MAXC) max_chunks = WP_MAXC;
-  L.rec_cap = align_up(max_rec_bytes + 16, 128);
+  L.rec_cap = align_up(max_rec_bytes + 16, 16);
   const uint32_t P = max_rows + (max_chunks + 1) * (wrows + 7) + 16;         // positions: rows + zero gaps + slack
-  L.vcap = align_up(P + P / 8 + 2, 16);
-  L.jcap = align_up((uint32_t)(WP_MAXC - 1) * wrows + 8, 16); if (L.jcap < 64) L.jcap = 64;    // also the XOR prefix table of the decode (64 words)
-  L.ocap = align_up(T + 2, 16);
-  uint32_t o = 128;                    // mbarrier slot
-  L.desc = o; o += align_up((uint32_t)(WP_MAXC * sizeof(WpChunk)), 128);
-  L.jbuf = o; o += align_up(L.jcap * 8, 128);
+  L.vcap = align_up(P + P / 8 + 2, 2);
+  L.jcap = align_up((max_chunks > 1 ? max_chunks - 1 : 1) * (wrows + 8) + 8, 2);
+  L.ocap = align_up(T + T / 8 + 4, 2);                                       // skewed like V: one pad slot per 8 windows
+  if (L.ocap < 64) L.ocap = 64;                                              // also the XOR prefix table of the decode (64 words)
+  uint32_t o = 16;                     // mbarrier slot
+  L.desc = o; o += (uint32_t)(WP_MAXC * sizeof(WpChunk));
+  L.jbuf = o; o += L.jcap * 8;
   L.rec = o; o += L.rec_cap;
-  L.vals = o; o += align_up(L.vcap * 8, 128);
-  L.out = o; o += align_up(L.ocap * 8, 128);
-  L.per_warp = o;
+  L.vals = o; o += L.vcap * 8;
+  L.out = o; o += L.ocap * 8;
+  L.per_warp = align_up(o, 16);
   L.warps = 0;
   return L;
 }
