@@ -107,6 +107,27 @@ __device__ __forceinline__ void wp_block_pair(const double* __restrict__ pa, con
   }
 }
 
+// window block `it` of the plan: V index of its first row, byte offset (inside the warp's region) of its first result slot, and
+// inf = (jEnd + 1) | raw << 4 | skew phase of the first slot << 5 | chunk << 8 | first window << 10, where slots 0 .. jEnd are stored
+__device__ __forceinline__ void wp_item(const WpChunk* CD, const WpSmem& L, int it, int items, int psi, int& pp, int& op, int& inf) {
+  const bool active = it < items;
+  int ci = 0;                                             // the last chunk with blocks whose blk0 <= it
+  if (CD[1].nblk > 0 && it >= CD[1].blk0) ci = 1;
+  if (CD[2].nblk > 0 && it >= CD[2].blk0) ci = 2;
+  if (CD[3].nblk > 0 && it >= CD[3].blk0) ci = 3;
+  const WpChunk& ch = CD[ci];
+  const int b = active ? it - ch.blk0 : 0;
+  const int k0 = ch.kT0 + WP_R * b;
+  pp = ch.vidx0 + 9 * b;
+  const bool tojz = b < ch.jzb;                           // raw sums to J (every slot of the block exists there)
+  const bool raw = tojz || b >= ch.tb;
+  op = tojz ? (int)L.jbuf + 8 * (ch.joff + WP_R * b) : (int)L.out + 8 * (k0 + ((k0 + psi) >> 3));
+  int jEnd = !active ? -1 : tojz ? WP_R - 1 : ch.kT1 - k0;
+  if (jEnd > WP_R - 1) jEnd = WP_R - 1;
+  const int ot = tojz ? 0 : (k0 + psi) & 7;               // slots j with ot + j >= 8 sit one pad slot further
+  inf = (jEnd + 1) | ((raw ? 1 : 0) << 4) | (ot << 5) | (ci << 8) | (k0 << 10);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // SUM-class kernel: sum / avg / count_over_time, rate / increase on delta-temporality schemas.  No across-series aggregate.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -139,7 +160,9 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
   const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
 
   // memo of the window plan (lane c holds chunk c's key; the plan itself stays in CD)
-  int64_t m_init = 0, m_end = 0; int m_nrows = -1, m_n = -1; bool m_ok = false;
+  int64_t m_init = 0, m_end = 0; int m_nrows = -1, m_n = -1, m_wire = -1; bool m_ok = false;
+  // per-lane work items of the plan: two decode slots and the two window blocks of the first pass (see the plan)
+  int dd_dst[2] = {0, 0}, dd_inf[2] = {0, 0}, wi_pp[2] = {0, 0}, wi_op[2] = {0, 0}, wi_inf[2] = {0, 0};
   int p_Wr = 0, p_items = 0, p_nfull = 0, p_psi = 0; double p_rcpn = 0.0; bool p_gaps = true, p_oal = false;
   int64_t rows_scanned = 0, bytes_scanned = 0;
   uint32_t parity = 0;
@@ -208,12 +231,13 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
       grp_base = (c > 0 ? a0 : 0) + (c > 1 ? a1 : 0) + (c > 2 ? a2 : 0);
       if (a0 + a1 + a2 + a3 > WP_MAXG) regular = false; }
     const int ngroups = __shfl_sync(FULL, grp_base + ng, WP_MAXC - 1);
+    const bool any_raw = __any_sync(FULL, have && vwire == WIRE_RAW64);
     // ---- window plan, reused while the chunk shapes repeat
-    const bool samec = !(c < n) || (init == m_init && nrows == m_nrows && end_time == m_end);
+    const bool samec = !(c < n) || (init == m_init && nrows == m_nrows && end_time == m_end && vwire == m_wire);
     const bool same_all = __all_sync(FULL, samec);
     const bool same = m_ok && n == m_n && same_all;
     if (regular && !same) {
-      m_init = init; m_end = end_time; m_nrows = nrows; m_n = n; m_ok = false;
+      m_init = init; m_end = end_time; m_nrows = nrows; m_n = n; m_wire = vwire; m_ok = false;
       int64_t s0 = 0, e0 = 0;
       if (have) { s0 = sd.ceil_div(S0 - init); e0 = sd.floor_div(E0 - init); }
       const int Wr = (int)(e0 - s0);
@@ -288,6 +312,24 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
           const int g1 = g == n ? pend : CD[g].rowpos;
           for (int p = g0 + lane; p < g1; p += 32) V[wp_vidx(p)] = 0.0;
         }
+        // this lane's work items (they stay valid with the plan): decode slots lane, lane + 32 and window blocks lane, lane + 32
+        {
+          const int gb1 = __shfl_sync(FULL, have ? grp_base : 0x7fffffff, 1), gb2 = __shfl_sync(FULL, have ? grp_base : 0x7fffffff, 2),
+                    gb3 = __shfl_sync(FULL, have ? grp_base : 0x7fffffff, 3);
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int slot = jj * 32 + lane;
+            const bool active = slot < ngroups;
+            const int ci = active ? (slot >= gb1 ? 1 : 0) + (slot >= gb2 ? 1 : 0) + (slot >= gb3 ? 1 : 0) : 0;
+            const int gbc = ci == 0 ? 0 : ci == 1 ? gb1 : ci == 2 ? gb2 : gb3;
+            const int g = active ? slot - gbc : 0;
+            const int pq = CD[ci].rowpos + 1 + g * 8;
+            dd_dst[jj] = wp_vidx(pq);
+            dd_inf[jj] = (active ? 1 : 0) | (ci << 1) | ((pq & 7) << 3) | (g << 8);      // active, chunk, skew phase of the first row, group in chunk
+          }
+#pragma unroll
+          for (int X = 0; X < 2; ++X) wp_item(CD, L, X * 32 + lane, items, p_psi, wi_pp[X], wi_op[X], wi_inf[X]);
+        }
         m_ok = true;
       }
     }
@@ -317,17 +359,13 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
     // ------------------------------------------------------------------------------------------------ decode
     uint32_t okbits = 0xffffffffu;        // bit 30 stays set while every value has exponent bits 10 and 9 different: 2^-511 <= |x| < 2^513
     {
-      const int gb1 = CD[1].grp_base, gb2 = CD[2].grp_base, gb3 = CD[3].grp_base;
-      uint64_t d[2][8]; int cc[2]; bool act[2];
+      uint64_t d[2][8];
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
-        const int slot = jj * 32 + lane;
-        const bool active = slot < ngroups;
-        const int ci = (slot >= gb1 ? 1 : 0) + (slot >= gb2 ? 1 : 0) + (slot >= gb3 ? 1 : 0);
-        const WpChunk& ch = CD[active ? ci : 0];
-        cc[jj] = active ? ci : 0; act[jj] = active;
+        const bool active = dd_inf[jj] & 1;
+        const WpChunk& ch = CD[(dd_inf[jj] >> 1) & 3];
         const uint8_t* gp = R;
-        if (active) gp = R + ch.grp_off + reinterpret_cast<const uint16_t*>(R + ch.tab_off)[slot - ch.grp_base];
+        if (active) gp = R + ch.grp_off + reinterpret_cast<const uint16_t*>(R + ch.tab_off)[dd_inf[jj] >> 8];
         const uint32_t mask = active ? gp[0] : 0u;
         const uint32_t hdr = gp[1];
         const uint32_t numBits = ((hdr >> 4) + 1) * 4;
@@ -361,26 +399,25 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
       __syncwarp();
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
-        const WpChunk& ch = CD[cc[jj]];
-        const int g = act[jj] ? jj * 32 + lane - ch.grp_base : 0;
+        const bool active = dd_inf[jj] & 1;
+        const WpChunk& ch = CD[(dd_inf[jj] >> 1) & 3];
         // value before the group = first ^ (prefix at the slot) ^ (prefix at the chunk's first slot)
-        const uint64_t pre = ch.first ^ (jj ? ex1 : ex0) ^ xtab[act[jj] ? ch.grp_base : 0];
-        const int p = ch.rowpos + 1 + g * 8;
-        double* dst = V + wp_vidx(p);
-        const int t = p & 7;                                       // rows t' with t + t' >= 8 sit one pad slot further
-        if (act[jj]) {
+        const uint64_t pre = ch.first ^ (jj ? ex1 : ex0) ^ xtab[active ? ch.grp_base : 0];
+        uint64_t* dst = reinterpret_cast<uint64_t*>(V) + dd_dst[jj];
+        const int t = (dd_inf[jj] >> 3) & 7;                       // rows t' with t + t' >= 8 sit one pad slot further
+        if (active) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const uint64_t b = d[jj][i] ^ pre;
-            reinterpret_cast<uint64_t*>(dst)[i + ((t + i) >> 3)] = b;
+            dst[i + ((t + i) >> 3)] = b;
             const uint32_t h = (uint32_t)(b >> 32);
             okbits &= h ^ (h << 1);
           }
-          if (g == 0) { V[wp_vidx(p - 1)] = __longlong_as_double((long long)ch.first); const uint32_t h = (uint32_t)(ch.first >> 32); okbits &= h ^ (h << 1); }
+          if ((dd_inf[jj] >> 8) == 0) { dst[t == 0 ? -2 : -1] = ch.first; const uint32_t h = (uint32_t)(ch.first >> 32); okbits &= h ^ (h << 1); }
         }
       }
       // raw f64 vectors: plain copy
-      for (int ci = 0; ci < n; ++ci) {
+      for (int ci = 0; any_raw && ci < n; ++ci) {
         const WpChunk& ch = CD[ci];
         if (ch.wire != WIRE_RAW64) continue;
         const uint64_t* src = reinterpret_cast<const uint64_t*>(R + ch.val_off + 8);
@@ -415,29 +452,18 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
     auto oidx = [&](int k) -> int { return k + ((k + psi) >> 3); };
     {
       const int Wr = p_Wr;
-      const int b1 = CD[1].blk0, b2 = CD[2].blk0, b3 = CD[3].blk0;
-      const int n1 = CD[1].nblk, n2 = CD[2].nblk, n3 = CD[3].nblk;
       for (int it0 = 0; it0 < p_items; it0 += 64) {
-        const double* pp[2]; double* op[2]; int jEnd[2], rs0[2], nr[2], ot[2]; bool rawm[2];
+        int ipp[2], iop[2], iinf[2];
 #pragma unroll
         for (int X = 0; X < 2; ++X) {
-          const int it = it0 + X * 32 + lane;
-          const bool active = it < p_items;
-          // chunk of the item: the last chunk with blocks whose blk0 <= it
-          int ci = 0;
-          if (n1 > 0 && it >= b1) ci = 1;
-          if (n2 > 0 && it >= b2) ci = 2;
-          if (n3 > 0 && it >= b3) ci = 3;
-          const WpChunk& ch = CD[ci];
-          const int b = active ? it - ch.blk0 : 0;
-          const int k0 = ch.kT0 + WP_R * b;
-          pp[X] = V + ch.vidx0 + 9 * b;
-          const bool tojz = b < ch.jzb;                       // raw sums to J (every slot of the block exists there)
-          rawm[X] = tojz || b >= ch.tb;
-          op[X] = tojz ? J + ch.joff + WP_R * b : O + oidx(k0);
-          ot[X] = tojz ? 0 : (k0 + psi) & 7;                  // slots j with ot + j >= 8 sit one pad slot further
-          jEnd[X] = !active ? -1 : tojz ? WP_R : ch.kT1 - k0;
-          rs0[X] = ch.s0 + k0; nr[X] = ch.nrows;
+          if (it0 == 0) { ipp[X] = wi_pp[X]; iop[X] = wi_op[X]; iinf[X] = wi_inf[X]; }
+          else wp_item(CD, L, it0 + X * 32 + lane, p_items, psi, ipp[X], iop[X], iinf[X]);
+        }
+        const double* pp[2]; double* op[2]; int jEnd[2], ot[2]; bool rawm[2];
+#pragma unroll
+        for (int X = 0; X < 2; ++X) {
+          pp[X] = V + ipp[X]; op[X] = reinterpret_cast<double*>(wb + iop[X]);
+          jEnd[X] = (iinf[X] & 15) - 1; rawm[X] = (iinf[X] >> 4) & 1; ot[X] = (iinf[X] >> 5) & 7;
         }
         double a[WP_R], bb[WP_R];
         wp_block_pair(pp[0], pp[1], Wr, a, bb);
@@ -449,8 +475,9 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
             const double raw = X ? bb[j] : a[j];
             int nn = 1;
             if (FN == FN_AVG || FN == FN_COUNT) {
-              int lo = rs0[X] + j; const int hi0 = lo + Wr; if (lo < 0) lo = 0;
-              const int hi = hi0 > nr[X] - 1 ? nr[X] - 1 : hi0;
+              const WpChunk& ch = CD[(iinf[X] >> 8) & 3];
+              int lo = ch.s0 + (iinf[X] >> 10) + j; const int hi0 = lo + Wr; if (lo < 0) lo = 0;
+              const int hi = hi0 > ch.nrows - 1 ? ch.nrows - 1 : hi0;
               nn = hi - lo + 1;
             }
             const double fin = wp_finish<FN>(raw, nn, dv, rc, sc, p_nfull, p_rcpn, rawm[X]);
@@ -473,6 +500,7 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
       // (AggrOverTimeFunctions.scala:560-571); own windows that sit in a raw block are finished here as well
       for (int ci = 0; ci < n; ++ci) {
         const WpChunk& ch = CD[ci];
+        if (ch.jzb == 0 && ch.tb >= ch.nblk) continue;
         auto rows_in = [&](const WpChunk& x, int k) -> int {
           int lo = x.s0 + k; if (lo < 0) lo = 0; int hi = x.s0 + k + Wr; if (hi > x.nrows - 1) hi = x.nrows - 1;
           return hi - lo + 1;
@@ -510,9 +538,12 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
       // lane-consecutive windows: 256 contiguous bytes per store instruction; O index of window lane + 32 m = oidx(lane) + 36 m
       double* gp = out + (size_t)s * q.T + lane;
       const double* sp = O + oidx(lane);
-      int k = lane;
-#pragma unroll 4
-      for (; k < q.T; k += 32, gp += 32, sp += 36) wp_store_result(gp, *sp);
+      int iters = (q.T - lane + 31) >> 5;
+      for (; iters >= 4; iters -= 4, gp += 128, sp += 144) {
+        const double v0 = sp[0], v1 = sp[36], v2 = sp[72], v3 = sp[108];
+        wp_store_result(gp, v0); wp_store_result(gp + 32, v1); wp_store_result(gp + 64, v2); wp_store_result(gp + 96, v3);
+      }
+      for (; iters > 0; --iters, gp += 32, sp += 36) wp_store_result(gp, *sp);
     }
     __syncwarp();
   }

@@ -158,7 +158,7 @@ int main(int argc, char** argv) {
   std::mt19937_64 rng(4242);
   long checked = 0; int cases = 0;
   struct Cfg { int kind = 0; bool xor_enc = true; int fn = 0; std::vector<int> chunks; int nan_ppm = 0, reset_every = 0; int64_t window = 300000; int nser = 1; int inclusive = 1;
-               int64_t start_off = 0, end_off = 0; int agg_op = 0; int grid = 1; int jitter = 0; bool integral = false; bool v2_only = false; bool no_junction = false; bool warp_decode = false; bool wp = false; };
+               int64_t start_off = 0, end_off = 0; int agg_op = 0; int grid = 1; int jitter = 0; bool integral = false; bool v2_only = false; bool no_junction = false; bool warp_decode = false; bool wp = false; bool hetero = false; };
   const std::vector<Cfg> cfgs = {
     {0, true, filo::FN_RATE, {400, 80}, 200000, 0, 300000, 11, 1, 0, 0, 0, 2},           // C2: gauge, delta-temporality rate (CLASS_SUM), NaN stale markers
     {0, true, filo::FN_SUM, {150, 90}, 0, 0, 300000, 37, 1, -90000, 45000, 0, 2},        // several tiles per CTA, a partial last tile, windows before / after the data
@@ -188,6 +188,9 @@ int main(int argc, char** argv) {
     {0, false, filo::FN_SUM, {64, 200}, 0, 0, 420000, 9, 1, 0, 0, 0, 1, 0, false, false, false, false, true},
     {0, true, filo::FN_RATE, {100, 50, 50, 50, 50}, 0, 0, 300000, 10, 1, 0, 0, 0, 2, 0, false, false, false, false, true},          // five chunks: declined
     {0, true, filo::FN_SUM, {33, 150, 7, 90}, 0, 0, 240000, 11, 0, 0, 0, 0, 3, 0, false, false, false, false, true},                // a 7-row chunk inside the windows
+    {0, false, filo::FN_RATE, {500, 400}, 0, 0, 300000, 7, 1, 0, 0, 0, 1, 0, false, false, false, false, true},                      // more than 64 blocks per series: second pass
+    {0, true, filo::FN_SUM, {150, 90}, 0, 0, 300000, 29, 1, -90000, 45000, 0, 2, 0, false, false, false, false, true, true},          // chunk shapes differ from series to series: the plan memo is invalidated
+    {0, false, filo::FN_AVG, {200, 100}, 0, 0, 180000, 21, 0, 0, 0, 0, 1, 0, false, false, false, false, true, true},
     // the v2 warp-per-series kernel on its own: every function class, irregular scrapes (DDV timestamps), integral values (DDV longs)
     {0, true, filo::FN_MIN, {150, 90}, 100000, 0, 300000, 9, 1, -30000, 15000, 0, 2, 0, false, true},
     {0, false, filo::FN_MAX, {64, 64, 64, 64, 64}, 0, 0, 200000, 7, 0, 0, 0, 0, 1, 0, false, true},
@@ -229,6 +232,7 @@ int main(int argc, char** argv) {
       c.no_junction = fr() % 8 == 0;
       c.warp_decode = fr() % 3 == 0;
       c.wp = fr() % 2 == 0;
+      c.hetero = fr() % 3 == 0;
       if (c.v2_only) { const int fns[] = {filo::FN_MIN, filo::FN_MAX, filo::FN_LAST, filo::FN_TIMESTAMP, c.fn, c.fn}; c.fn = fns[fr() % 6]; c.agg_op = 0; }
       if (c.jitter) c.agg_op = 0;
       all.push_back(c);
@@ -242,7 +246,15 @@ int main(int argc, char** argv) {
     std::vector<SeriesData> SS((size_t)c.nser);
     std::vector<int64_t> rec_off((size_t)c.nser + 1, 0);
     g_jitter_ms = c.jitter; g_integral = c.integral;
-    for (int s = 0; s < c.nser; ++s) { build_series(SS[(size_t)s], rng, rows, c.chunks, t0, step_ms, c.kind, c.xor_enc, c.nan_ppm, c.reset_every); rec_off[(size_t)s + 1] = rec_off[(size_t)s] + (int64_t)SS[(size_t)s].record.size(); }
+    for (int s = 0; s < c.nser; ++s) {
+      std::vector<int> cr = c.chunks; int64_t ts0 = t0; bool xe = c.xor_enc;
+      if (c.hetero) {      // series-dependent chunk split, start time and encoding (runs of equal shapes in between)
+        const int v = (s / 2) % 4;
+        if (cr.size() >= 2) { const int mv = 8 * v + (v == 3 ? 3 : 0); if (cr[0] > mv + 8) { cr[0] -= mv; cr[1] += mv; } }
+        if (v == 2) ts0 += step_ms;
+        if ((s / 3) % 3 == 1) xe = !xe;
+      }
+      build_series(SS[(size_t)s], rng, rows, cr, ts0, step_ms, c.kind, xe, c.nan_ppm, c.reset_every); rec_off[(size_t)s + 1] = rec_off[(size_t)s] + (int64_t)SS[(size_t)s].record.size(); }
     std::vector<uint64_t> arena_backing((size_t)rec_off.back() / 8 + 64, 0);
     uint8_t* arena = reinterpret_cast<uint8_t*>(arena_backing.data());
     uint32_t max_rec = 0;
