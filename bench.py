@@ -76,50 +76,109 @@ def query_range(workload):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  NVML polled from a thread of this process (the
+    library is initialised before the warm-up, so nothing starts up inside the timed region -- an `nvidia-smi` child launched right
+    before it was seen to delay the first steps on some boxes); `nvidia-smi -lms` is the fallback when pynvml is missing.  Only the
+    samples taken between mark_start() and stop() count."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.proc = None
-        self.lines = []
+        self.samples = []          # (t, sm_mhz, reasons bitmask or set)
+        self.mx = None
+        self.t0 = None
+        self._stop = False
+        self.nvml = None
 
     def start(self):
+        """Call before the warm-up."""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remaps ordinals: go through the PCI bus id of the torch device
+            import torch
+            h = None
+            try:
+                bus = torch.cuda.get_device_properties(self.idx).pci_bus_id
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hh).bus == bus:
+                        h = hh
+                        break
+            except Exception:
+                h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.nvml, self.h = pynvml, h
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nvml, self.h
+        names = (("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8)), ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                 ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)), ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((time.perf_counter(), sm, {n for n, bit in names if r & bit}))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
+            f = [x.strip() for x in line.strip().split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1])); mx = float(f[2])
+                sm = float(f[1]); self.mx = float(f[2])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+            rs = {name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]) if v.lower().startswith("active")}
+            self.samples.append((time.perf_counter(), sm, rs))
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def stop(self):
+        t1 = time.perf_counter()
+        if self.nvml is None and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml / nvidia-smi unavailable"]}
+        if self.nvml is None:
+            time.sleep(0.1)
+        self._stop = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [x for x in self.samples if t0 <= x[0] <= t1 + 0.2]
+        sm = [x[1] for x in inside]
+        reasons = set()
+        for x in inside:
+            reasons |= x[2]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+
 
 
 def measured_peak():
@@ -307,10 +366,10 @@ def run_c4(args, rank, world, local_rank):
         return ctx.last_stats
     st0 = one()
     assert st0["samples_scanned"] == ti.n_samples, (st0, ti.n_samples)
+    sampler = ClockSampler(local_rank); sampler.start()
     for _ in range(args.warmup): one()
-    sampler = ClockSampler(local_rank)
     if dist: dist.barrier()
-    torch.cuda.synchronize(); sampler.start()
+    torch.cuda.synchronize(); sampler.mark_start()
     kns = [one()["kernel_ns"] for _ in range(args.steps)]          # device time of the step's kernels (CUDA events on the launching stream)
     torch.cuda.synchronize()
     if dist: dist.barrier()
@@ -420,6 +479,7 @@ def main():
     st = ctx.query_device(tab, fn, start, step, end, window, out.data_ptr(), aux.data_ptr() if aux is not None else 0,
                           aggr=aggr, flags=flags, stream=stream, want_stats=True)
     assert st["samples_scanned"] == ti.n_samples, (st, ti.n_samples)
+    sampler = ClockSampler(local_rank); sampler.start()      # started before the warm-up: nothing spins up inside the timed region
     for _ in range(args.warmup):
         step_fn()
     torch.cuda.synchronize()
@@ -427,10 +487,9 @@ def main():
     for _ in range(3):
         kern_ns.append(ctx.query_device(tab, fn, start, step, end, window, out.data_ptr(), aux.data_ptr() if aux is not None else 0,
                                         aggr=aggr, flags=flags, stream=stream, want_stats=True)["kernel_ns"])
-    sampler = ClockSampler(local_rank)
     if dist: dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
+    sampler.mark_start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):

@@ -4,7 +4,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfilo_b200.so")
+LIB_PATH = os.environ.get("FILO_LIB_PATH") or os.path.join(_HERE, "libfilo_b200.so")      # FILO_LIB_PATH: A/B runs of a variant build (developer switch)
 
 FN_LAST, FN_RATE, FN_INCREASE, FN_DELTA, FN_SUM_OVER_TIME, FN_AVG_OVER_TIME, FN_COUNT_OVER_TIME, \
     FN_MIN_OVER_TIME, FN_MAX_OVER_TIME, FN_TIMESTAMP = range(10)

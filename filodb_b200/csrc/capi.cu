@@ -105,6 +105,16 @@ int32_t filo_ctx_create(int32_t device, const filo_cfg* cfg, filo_ctx** out) {
   c->sm_count = p.multiProcessorCount;
   c->max_smem_optin = p.sharedMemPerBlockOptin;
   CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    // per-query temporaries come from the stream-ordered pool: keep freed blocks in the pool instead of returning them to the OS at every
+    // synchronisation (the default release threshold of 0 makes the first allocation after a sync a driver call)
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+      uint64_t thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+  }
   *out = c;
   return FILO_OK;
 }
