@@ -667,10 +667,13 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
     const uint64_t wrows = (uint64_t)(q.window / q.step) + 1;
     const bool want_v3 = force && std::string(force) == "v3";
     if (use_tile && !want_v3 && fn_cls == CLASS_SUM && wrows <= 4096 && t->max_chunks > 0) {
-      WL = wp_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)t->max_chunks, (uint32_t)q.T, (uint32_t)wrows);
       const size_t cap = std::min<size_t>(ctx->max_smem_optin, 227 * 1024);
-      size_t w = cap / WL.per_warp; if (w > (size_t)WP_MAX_WARPS) w = WP_MAX_WARPS;
       static const int warps_env = [] { const char* e = std::getenv("FILO_WP_WARPS"); return e ? atoi(e) : 0; }();
+      static const bool no_alias = [] { const char* e = std::getenv("FILO_WP_ALIAS"); return e && e[0] == '0'; }();
+      // O in V's place (more warps per SM) when every series is summed in one pass of <= 64 blocks
+      const bool alias = !no_alias && wp_max_items((uint32_t)t->max_chunks, (uint32_t)q.T, (uint32_t)wrows) <= 64;
+      WL = wp_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)t->max_chunks, (uint32_t)q.T, (uint32_t)wrows, alias);
+      size_t w = cap / WL.per_warp; const size_t wmax = alias ? WP_MAX_WARPS_ALIAS : WP_MAX_WARPS; if (w > wmax) w = wmax;
       if (warps_env > 0 && (size_t)warps_env < w) w = (size_t)warps_env;
       WL.warps = (uint32_t)w;
       use_wp = w >= 4;

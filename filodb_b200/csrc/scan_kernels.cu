@@ -475,13 +475,19 @@ cudaError_t launch_scan_tile_agg(const ScanLaunch& L, const TileSmem& T, const i
   return launch_tile_any<true>(L, nullptr, T, fallback_list, fallback_count, TileAggArgs{order, item_begin, n_items, agg_op, pval, pcnt});
 }
 // v4 warp-pipeline kernel (scan_wp.cuh): one CTA of W.warps warps per SM; declined series go to fallback_list
+template <int FN, int NW>
+static cudaError_t launch_wp_nw(const ScanLaunch& L, double* out, const WpSmem& W, int64_t* fallback_list, unsigned long long* fallback_count) {
+  const size_t smem = (size_t)W.per_warp * W.warps;
+  cudaError_t e = cudaFuncSetAttribute(scan_wp_sum_kernel<FN, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  scan_wp_sum_kernel<FN, NW><<<L.grid, W.warps * 32, smem, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, W, fallback_list, fallback_count, L.d_counters, L.d_err);
+  return cudaGetLastError();
+}
 template <int FN>
 static cudaError_t launch_wp_fn(const ScanLaunch& L, double* out, const WpSmem& W, int64_t* fallback_list, unsigned long long* fallback_count) {
-  const size_t smem = (size_t)W.per_warp * W.warps;
-  cudaError_t e = cudaFuncSetAttribute(scan_wp_sum_kernel<FN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  scan_wp_sum_kernel<FN><<<L.grid, W.warps * 32, smem, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, W, fallback_list, fallback_count, L.d_counters, L.d_err);
-  return cudaGetLastError();
+  // the register budget follows the warps per CTA: 128 registers up to 16 warps, 96 up to 20
+  if (W.warps <= (uint32_t)WP_MAX_WARPS) return launch_wp_nw<FN, WP_MAX_WARPS>(L, out, W, fallback_list, fallback_count);
+  return launch_wp_nw<FN, WP_MAX_WARPS_ALIAS>(L, out, W, fallback_list, fallback_count);
 }
 cudaError_t launch_scan_wp(const ScanLaunch& L, double* out, const WpSmem& W, int64_t* fallback_list, unsigned long long* fallback_count) {
   switch (L.q.fn) {

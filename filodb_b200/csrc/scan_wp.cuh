@@ -131,8 +131,8 @@ __device__ __forceinline__ void wp_item(const WpChunk* CD, const WpSmem& L, int 
 // ---------------------------------------------------------------------------------------------------------------------
 // SUM-class kernel: sum / avg / count_over_time, rate / increase on delta-temporality schemas.  No across-series aggregate.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int FN>
-__global__ void __launch_bounds__(WP_MAX_WARPS * 32, 1)
+template <int FN, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, int64_t n_series, QueryParams q,
                    double* __restrict__ out, WpSmem L, int64_t* __restrict__ fallback_list, unsigned long long* __restrict__ fallback_count,
                    unsigned long long* d_counters, int* d_err) {
@@ -142,7 +142,7 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
   uint8_t* wb = smem + (size_t)warp * L.per_warp;
   uint64_t* bar = reinterpret_cast<uint64_t*>(wb);
   WpChunk* CD = reinterpret_cast<WpChunk*>(wb + L.desc);
-  uint64_t* xtab = reinterpret_cast<uint64_t*>(wb + L.out);      // decode: exclusive XOR prefix per group slot (dead before O is written)
+  uint64_t* xtab = reinterpret_cast<uint64_t*>(wb + L.jbuf);     // decode: exclusive XOR prefix per group slot (dead before J is written)
   double* J = reinterpret_cast<double*>(wb + L.jbuf);
   uint8_t* R = wb + L.rec;
   double* V = reinterpret_cast<double*>(wb + L.vals);
@@ -163,6 +163,7 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
   int64_t m_init = 0, m_end = 0; int m_nrows = -1, m_n = -1, m_wire = -1; bool m_ok = false;
   // per-lane work items of the plan: two decode slots and the two window blocks of the first pass (see the plan)
   int dd_dst[2] = {0, 0}, dd_inf[2] = {0, 0}, wi_pp[2] = {0, 0}, wi_op[2] = {0, 0}, wi_inf[2] = {0, 0};
+  int gz[3] = {-1, -1, -1}; bool gz_all = true;      // this lane's zero rows (V indices) when the plan has at most 96 of them
   int p_Wr = 0, p_items = 0, p_nfull = 0, p_psi = 0; double p_rcpn = 0.0; bool p_gaps = true, p_oal = false;
   int64_t rows_scanned = 0, bytes_scanned = 0;
   uint32_t parity = 0;
@@ -274,6 +275,7 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
 #pragma unroll
         for (int o = 1; o < WP_MAXC; o <<= 1) cov += __shfl_xor_sync(FULL, cov, o); }
       if ((uint32_t)jtot > L.jcap) okp = false;
+      if (L.alias && items > 64) okp = false;                 // O takes V's place: every block is summed before the first result is stored
       // row positions: chunk after chunk, Wr .. Wr + 7 zero rows in between, every chunk's block 0 at a multiple of 8
       const int fr = touch ? (int)(s0 + kT0) : 0;              // first row of block 0 (may be negative: zero rows in front)
       int rowpos = 0;
@@ -306,11 +308,19 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
           p_oal = __all_sync(FULL, !touch || (((int)kT0 + p_psi) & 7) == 0); }
         p_Wr = Wr0; p_items = items; p_nfull = Wr0 + 1; p_rcpn = 1.0 / (double)(Wr0 + 1);
         __syncwarp();
-        // zero rows: in front of chunk 0, between chunks, behind the last chunk (+ slack the last block's unused windows read)
-        for (int g = 0; g <= n; ++g) {
-          const int g0 = g == 0 ? 0 : CD[g - 1].rowpos + CD[g - 1].nrows;
-          const int g1 = g == n ? pend : CD[g].rowpos;
-          for (int p = g0 + lane; p < g1; p += 32) V[wp_vidx(p)] = 0.0;
+        // zero rows: in front of chunk 0, between chunks, behind the last chunk (+ slack the last block's unused windows read).  They are
+        // written again for every series (the group decode runs up to 7 rows past a chunk; with O in V's place the results land on them)
+        {
+          int tot = 0;
+          gz[0] = gz[1] = gz[2] = -1;
+          for (int g = 0; g <= n; ++g) {
+            const int g0 = g == 0 ? 0 : CD[g - 1].rowpos + CD[g - 1].nrows;
+            const int g1 = g == n ? pend : CD[g].rowpos;
+#pragma unroll
+            for (int u = 0; u < 3; ++u) { const int i = u * 32 + lane - tot; if (i >= 0 && i < g1 - g0) gz[u] = wp_vidx(g0 + i); }
+            tot += g1 - g0;
+          }
+          gz_all = tot <= 96;
         }
         // this lane's work items (they stay valid with the plan): decode slots lane, lane + 32 and window blocks lane, lane + 32
         {
@@ -434,10 +444,17 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
     // R is dead: fetch the next record behind the window phase
     if (sn < n_series && nxt_sz <= L.rec_cap && lane == 0) issue(nxt_off, nxt_sz);
     cur_off = nxt_off; cur_sz = nxt_sz;
-    // the last group of an XOR chunk decodes up to 7 rows past the chunk: back to zero (lane = chunk * 8 + row)
-    {
-      const int ci = lane >> 3, i = lane & 7;
-      if (ci < n && i < 7) { const WpChunk& ch = CD[ci]; if (ch.wire == WIRE_XOR) V[wp_vidx(ch.rowpos + ch.nrows + i)] = 0.0; }
+    // zero rows (the last group of an XOR chunk decoded up to 7 rows past the chunk; results of the previous series when O is in V's place)
+    if (gz_all) {
+#pragma unroll
+      for (int u = 0; u < 3; ++u) if (gz[u] >= 0) V[gz[u]] = 0.0;
+    } else {
+      const int pend = CD[n - 1].rowpos + CD[n - 1].nrows + p_Wr + 8;
+      for (int g = 0; g <= n; ++g) {
+        const int g0 = g == 0 ? 0 : CD[g - 1].rowpos + CD[g - 1].nrows;
+        const int g1 = g == n ? pend : CD[g].rowpos;
+        for (int pz = g0 + lane; pz < g1; pz += 32) V[wp_vidx(pz)] = 0.0;
+      }
     }
     if (!vals_ok) {
       // NaN / Inf / zero / denormal / very large or small values: the literal kernel answers (it needs the NaN-aware sums)
@@ -467,6 +484,7 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
         }
         double a[WP_R], bb[WP_R];
         wp_block_pair(pp[0], pp[1], Wr, a, bb);
+        __syncwarp();                                       // (O may sit on V: every lane has read its rows)
 #pragma unroll
         for (int X = 0; X < 2; ++X) {
           const double dv = rawm[X] ? 1.0 : fdiv, rc = rawm[X] ? 1.0 : frcp, sc = rawm[X] ? 1.0 : 1000.0;

@@ -7,7 +7,8 @@ namespace filo {
 constexpr int WP_MAXC = 4;             // chunks in range per series on this path
 constexpr int WP_MAXG = 64;            // NibblePack groups per series (two per lane)
 constexpr int WP_R = 8;                // windows per block
-constexpr int WP_MAX_WARPS = 16;       // warps per CTA (one CTA per SM)
+constexpr int WP_MAX_WARPS = 16;       // warps per CTA (one CTA per SM) when O has its own region
+constexpr int WP_MAX_WARPS_ALIAS = 20; // ... when O takes V's place (single-pass plans): bounded by 96 registers per thread
 
 struct WpChunk {                       // per warp, per chunk in range (shared memory)
   uint64_t first;                      // XOR vectors: bits of the first value
@@ -30,26 +31,35 @@ struct WpSmem {                        // byte offsets inside a warp's region, a
   uint32_t desc, jbuf, rec, vals, out, per_warp;
   uint32_t rec_cap, vcap /*doubles*/, jcap /*doubles*/, ocap /*doubles*/;
   uint32_t warps;                      // warps per CTA
+  uint32_t alias;                      // O lives in V's region: every block of a series is summed (one pass of <= 64 blocks) before the first result is stored
 };
 // wrows = window / step + 1: the most rows a window can span
-FILO_HD inline WpSmem wp_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t max_chunks, uint32_t T, uint32_t wrows) {
+FILO_HD inline WpSmem wp_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t max_chunks, uint32_t T, uint32_t wrows, bool alias) {
   WpSmem L;
   if (max_chunks > (uint32_t)WP_MAXC) max_chunks = WP_MAXC;
   L.rec_cap = align_up(max_rec_bytes + 16, 16);
   const uint32_t P = max_rows + (max_chunks + 1) * (wrows + 7) + 16;         // positions: rows + zero gaps + slack
   L.vcap = align_up(P + P / 8 + 2, 2);
   L.jcap = align_up((max_chunks > 1 ? max_chunks - 1 : 1) * (wrows + 8) + 8, 2);
+  if (L.jcap < 64) L.jcap = 64;                                              // also the XOR prefix table of the decode (64 words)
   L.ocap = align_up(T + T / 8 + 4, 2);                                       // skewed like V: one pad slot per 8 windows
-  if (L.ocap < 64) L.ocap = 64;                                              // also the XOR prefix table of the decode (64 words)
+  if (alias && L.vcap < L.ocap) L.vcap = L.ocap;
   uint32_t o = 16;                     // mbarrier slot
   L.desc = o; o += (uint32_t)(WP_MAXC * sizeof(WpChunk));
   L.jbuf = o; o += L.jcap * 8;
   L.rec = o; o += L.rec_cap;
   L.vals = o; o += L.vcap * 8;
-  L.out = o; o += L.ocap * 8;
+  if (alias) L.out = L.vals; else { L.out = o; o += L.ocap * 8; }
   L.per_warp = align_up(o, 16);
   L.warps = 0;
+  L.alias = alias ? 1u : 0u;
   return L;
+}
+// an upper bound of the blocks of a series: sum over chunks of ceil(touched windows / 8), with at most wrows - 1 windows shared per junction
+FILO_HD inline uint32_t wp_max_items(uint32_t max_chunks, uint32_t T, uint32_t wrows) {
+  if (max_chunks > (uint32_t)WP_MAXC) max_chunks = WP_MAXC;
+  if (max_chunks == 0) max_chunks = 1;
+  return (T + (max_chunks - 1) * (wrows - 1) + 7 * max_chunks) / 8;
 }
 
 } // namespace filo

@@ -287,12 +287,13 @@ int main(int argc, char** argv) {
       const int cls = filo::fn_class_of(q.fn, q.cumulative);
       const bool tile_ok = !c.v2_only && (cls == filo::CLASS_SUM || cls == filo::CLASS_COUNTER);
       if (tile_ok && c.wp && cls == filo::CLASS_SUM) {
-        filo::WpSmem W = filo::wp_layout(max_rec, (uint32_t)rows, (uint32_t)c.chunks.size(), (uint32_t)q.T, wrows);
+        const bool alias = filo::wp_max_items((uint32_t)c.chunks.size(), (uint32_t)q.T, wrows) <= 64 && !(ci % 5 == 0);      // as filo_query decides (every fifth case keeps O apart)
+        filo::WpSmem W = filo::wp_layout(max_rec, (uint32_t)rows, (uint32_t)c.chunks.size(), (uint32_t)q.T, wrows, alias);
         W.warps = 3;
         if ((size_t)W.per_warp * W.warps > sizeof(filo::smem)) { std::printf("FAIL: wp layout %u bytes per warp\n", W.per_warp); return 1; }
         auto body = [&](auto fnc) {
           cusim::launch(dim3((unsigned)A.grid), dim3(W.warps * 32), [&] {
-            filo::scan_wp_sum_kernel<decltype(fnc)::value>(A.arena, A.rec_off, A.S, A.q, A.out, W, A.flist, A.fcount, A.counters, A.derr);
+            filo::scan_wp_sum_kernel<decltype(fnc)::value, 16>(A.arena, A.rec_off, A.S, A.q, A.out, W, A.flist, A.fcount, A.counters, A.derr);
           });
         };
         if (q.fn == filo::FN_RATE) body(std::integral_constant<int, filo::FN_RATE>{});
