@@ -121,7 +121,7 @@ __device__ __forceinline__ void wp_item(const WpChunk* CD, const WpSmem& L, int 
   pp = ch.vidx0 + 9 * b;
   const bool tojz = b < ch.jzb;                           // raw sums to J (every slot of the block exists there)
   const bool raw = tojz || b >= ch.tb;
-  op = tojz ? (int)L.jbuf + 8 * (ch.joff + WP_R * b) : (int)L.out + 8 * (k0 + ((k0 + psi) >> 3));
+  op = tojz ? (int)WP_OFF_J + 8 * (ch.joff + WP_R * b) : (int)L.out + 8 * (k0 + ((k0 + psi) >> 3));
   int jEnd = !active ? -1 : tojz ? WP_R - 1 : ch.kT1 - k0;
   if (jEnd > WP_R - 1) jEnd = WP_R - 1;
   const int ot = tojz ? 0 : (k0 + psi) & 7;               // slots j with ot + j >= 8 sit one pad slot further
@@ -141,10 +141,10 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t* wb = smem + (size_t)warp * L.per_warp;
   uint64_t* bar = reinterpret_cast<uint64_t*>(wb);
-  WpChunk* CD = reinterpret_cast<WpChunk*>(wb + L.desc);
-  uint64_t* xtab = reinterpret_cast<uint64_t*>(wb + L.jbuf);     // decode: exclusive XOR prefix per group slot (dead before J is written)
-  double* J = reinterpret_cast<double*>(wb + L.jbuf);
-  uint8_t* R = wb + L.rec;
+  WpChunk* CD = reinterpret_cast<WpChunk*>(wb + WP_OFF_DESC);
+  uint64_t* xtab = reinterpret_cast<uint64_t*>(wb + WP_OFF_J);     // decode: exclusive XOR prefix per group slot (dead before J is written)
+  double* J = reinterpret_cast<double*>(wb + WP_OFF_J);
+  uint8_t* R = wb + WP_OFF_REC;
   double* V = reinterpret_cast<double*>(wb + L.vals);
   double* O = reinterpret_cast<double*>(wb + L.out);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);

@@ -27,6 +27,8 @@ struct WpChunk {                       // per warp, per chunk in range (shared m
 };
 static_assert(sizeof(WpChunk) == 96, "WpChunk");
 
+// fixed part of a warp's region: mbarrier, descriptors, J -- compile-time offsets keep the kernel's address arithmetic in immediates
+constexpr uint32_t WP_OFF_DESC = 16, WP_OFF_J = WP_OFF_DESC + WP_MAXC * 96, WP_J_DOUBLES = 128, WP_OFF_REC = WP_OFF_J + WP_J_DOUBLES * 8;
 struct WpSmem {                        // byte offsets inside a warp's region, all multiples of 16
   uint32_t desc, jbuf, rec, vals, out, per_warp;
   uint32_t rec_cap, vcap /*doubles*/, jcap /*doubles*/, ocap /*doubles*/;
@@ -40,13 +42,13 @@ FILO_HD inline WpSmem wp_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint3
   L.rec_cap = align_up(max_rec_bytes + 16, 16);
   const uint32_t P = max_rows + (max_chunks + 1) * (wrows + 7) + 16;         // positions: rows + zero gaps + slack
   L.vcap = align_up(P + P / 8 + 2, 2);
-  L.jcap = align_up((max_chunks > 1 ? max_chunks - 1 : 1) * (wrows + 8) + 8, 2);
-  if (L.jcap < 64) L.jcap = 64;                                              // also the XOR prefix table of the decode (64 words)
+  L.jcap = WP_J_DOUBLES;               // raw sums of the windows two chunks share (a plan that needs more is declined); also the XOR prefix table of the decode (64 words)
+  (void)wrows;
   L.ocap = align_up(T + T / 8 + 4, 2);                                       // skewed like V: one pad slot per 8 windows
   if (alias && L.vcap < L.ocap) L.vcap = L.ocap;
-  uint32_t o = 16;                     // mbarrier slot
-  L.desc = o; o += (uint32_t)(WP_MAXC * sizeof(WpChunk));
-  L.jbuf = o; o += L.jcap * 8;
+  static_assert(sizeof(WpChunk) == 96, "WP_OFF_J");
+  uint32_t o = WP_OFF_REC;
+  L.desc = WP_OFF_DESC; L.jbuf = WP_OFF_J;
   L.rec = o; o += L.rec_cap;
   L.vals = o; o += L.vcap * 8;
   if (alias) L.out = L.vals; else { L.out = o; o += L.ocap * 8; }

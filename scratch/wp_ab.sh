@@ -8,6 +8,7 @@ if [ "${FULL:-0}" = "1" ]; then timeout 300 python -m pytest tests -m gpu -x -q 
 for r in 1 2; do
   FILO_LIB_PATH=$PWD/scratch/base_wp.so timeout 90 $P 2>/dev/null | tail -1 > gpurun_out/ab_base_$r.json
   timeout 90 $P 2>gpurun_out/ab.err | tail -1 > gpurun_out/ab_new_$r.json
+  if [ -n "${VARIANT:-}" ]; then env $VARIANT timeout 90 $P 2>/dev/null | tail -1 > gpurun_out/ab_var_$r.json; fi
 done
 python - <<PY
 import json, glob
