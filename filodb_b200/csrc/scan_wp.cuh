@@ -107,6 +107,181 @@ __device__ __forceinline__ void wp_block_pair(const double* __restrict__ pa, con
   }
 }
 
+// per-series parse, lane c = chunk c of the chunks in range: what the record says about the chunk, and whether the series qualifies
+struct WpParsed {
+  bool regular, have, any_raw; int n, cLo;
+  int64_t init, end_time; int nrows, num_rows, vbytes, ng, vwire, dropped, tlen, grp_base, ngroups; uint32_t voff, w12;
+};
+// STRICT (SUM class): endTime covers the chunk's rows and lies before the next chunk's first row, so that "has a row in the window" and
+// "is in the window's chunk set" (ChunkSetInfo.scala:481-510) coincide; the counter class evaluates the chunk set itself
+template <bool STRICT>
+__device__ __forceinline__ WpParsed wp_parse(const uint8_t* R, const QueryParams& q, bool staged, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  WpParsed P;
+  bool regular = staged;
+  int n = 0, cLo = 0;
+  if (staged) {
+    const RecordHeader* h = reinterpret_cast<const RecordHeader*>(R);
+    const ChunkEntry* Eall = reinterpret_cast<const ChunkEntry*>(R + sizeof(RecordHeader));
+    const int nch = (int)h->n_chunks;
+    regular = nch <= 32 && (h->flags & REC_ALL_TS_CONST) != 0;
+    const int64_t t1 = q.start - q.window, t2 = q.end;
+    bool below = false, within = false;
+    if (regular && lane < nch) { below = Eall[lane].end_time < t1; within = !below && Eall[lane].start_time <= t2; }
+    const unsigned mb = __ballot_sync(FULL, below), mw = __ballot_sync(FULL, within);
+    cLo = __ffs((int)~mb) - 1; if (cLo < 0) cLo = 32;                         // chunks are time-ordered: `below` is a prefix
+    const unsigned rest = cLo < 32 ? (mw >> cLo) : 0u;
+    n = __ffs((int)~rest) - 1; if (n < 0) n = 32;
+    if (n > WP_MAXC) regular = false;
+  }
+  const int c = lane;
+  bool have = regular && c < n;
+  int64_t init = 0, end_time = 0; int nrows = 0, num_rows = 0, vbytes = 0, ng = 0, vwire = 0, dropped = 0, tlen = 0; uint32_t voff = 0, w12 = 0;
+  bool okc = true;
+  if (have) {
+    const ChunkEntry& e = reinterpret_cast<const ChunkEntry*>(R + sizeof(RecordHeader))[cLo + c];
+    const uint8_t* tv = R + e.ts_off; const uint8_t* vv = R + e.val_off;
+    const uint32_t vw4 = ld32(vv + 4);
+    vwire = (int)(vw4 & 0xffff); dropped = (int)((vw4 >> 31) & 1);
+    tlen = (int)ld32(tv + 8); init = (int64_t)ld64_a4(tv + 12); const int slope = (int)ld32(tv + 20);
+    end_time = e.end_time; num_rows = e.num_rows; voff = e.val_off;
+    vbytes = (int)ld32(tv) + 4 + (int)ld32(vv) + 4;
+    int vlen = 0;
+    if (vwire == WIRE_XOR) { vlen = (int)ld32(vv + XOR_OFF_N); w12 = ld32(vv + XOR_OFF_NGROUPS); ng = (int)(w12 & 0xffff); if (ng != (vlen + 6) / 8) okc = false; }
+    else if (vwire == WIRE_RAW64) vlen = ((int)ld32(vv) - 4) / 8;
+    else okc = false;
+    if ((int64_t)slope != q.step || tlen <= 0 || vlen <= 0 || num_rows <= 0) okc = false;
+    nrows = num_rows < tlen ? num_rows : tlen;
+    if (vlen != nrows) okc = false;                       // the decode writes every row of the vector
+    if (STRICT && end_time < init + (int64_t)(nrows - 1) * q.step) okc = false;
+  }
+  {
+    const int64_t endp = __shfl_up_sync(FULL, end_time, 1);
+    if (STRICT && have && c > 0 && !(endp < init)) okc = false;
+    if (!__all_sync(FULL, okc)) regular = false;
+  }
+  have = have && regular;
+  if (!have) { ng = 0; nrows = 0; }
+  // group slots: exclusive prefix over the chunks
+  int grp_base = ng;
+  { const int a0 = __shfl_sync(FULL, ng, 0), a1 = __shfl_sync(FULL, ng, 1), a2 = __shfl_sync(FULL, ng, 2), a3 = __shfl_sync(FULL, ng, 3);
+    grp_base = (c > 0 ? a0 : 0) + (c > 1 ? a1 : 0) + (c > 2 ? a2 : 0);
+    if (a0 + a1 + a2 + a3 > WP_MAXG) regular = false; }
+  P.ngroups = __shfl_sync(FULL, grp_base + ng, WP_MAXC - 1);
+  P.any_raw = __any_sync(FULL, have && vwire == WIRE_RAW64);
+  P.regular = regular; P.have = have && regular; P.n = n; P.cLo = cLo; P.init = init; P.end_time = end_time; P.nrows = nrows; P.num_rows = num_rows;
+  P.vbytes = vbytes; P.ng = ng; P.vwire = vwire; P.dropped = dropped; P.tlen = tlen; P.grp_base = grp_base; P.voff = voff; P.w12 = w12;
+  return P;
+}
+
+// Decode of a series into V: lane = NibblePack group (slots lane and lane + 32, described by dd_dst / dd_inf, see the plan); raw f64
+// vectors are copied.  Returns the AND over every value v of hi(v) ^ (hi(v) << 1): bit 30 is set while every value has exponent bits
+// 10 and 9 different, i.e. 2^-511 <= |v| < 2^513 (finite, normal, not zero).  DROPS (counter class): counter drops inside drop-flagged
+// chunks (DoubleVector.scala:330-340) are recorded as (row, amount) in DR[chunk]; row r drops when (NaN -> 0) of it is below
+// (NaN -> 0) of row r - 1, the amount is the value before the drop.
+template <bool DROPS>
+__device__ __forceinline__ uint32_t wp_decode(const uint8_t* R, double* V, const WpChunk* CD, uint64_t* xtab, const int dd_dst[2], const int dd_inf[2],
+                                              int n, bool any_raw, int lane, TileDrops* DR) {
+  uint32_t okbits = 0xffffffffu;
+  uint64_t d[2][8];
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    const bool active = dd_inf[jj] & 1;
+    const WpChunk& ch = CD[(dd_inf[jj] >> 1) & 3];
+    const uint8_t* gp = R;
+    if (active) gp = R + ch.grp_off + reinterpret_cast<const uint16_t*>(R + ch.tab_off)[dd_inf[jj] >> 8];
+    const uint32_t mask = active ? gp[0] : 0u;
+    const uint32_t hdr = gp[1];
+    const uint32_t numBits = ((hdr >> 4) + 1) * 4;
+    const uint32_t tz = (hdr & 0x0f) * 4;
+    const uint64_t fm = (~0ull >> (64 - numBits)) << tz;       // the field's bits in the value
+    // bit address (in shared memory) of the 64-bit window that has field 0 at bit tz
+    uint32_t xb = (wp_soff(gp + 2) << 3) - tz;
+    uint64_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool on = (mask >> i) & 1u;
+      const uint32_t wa = (xb >> 3) & ~3u;
+      const uint32_t w0 = wp_lds32(wa), w1 = wp_lds32(wa + 4), w2 = wp_lds32(wa + 8);
+      const uint32_t lo = __funnelshift_r(w0, w1, xb), hi = __funnelshift_r(w1, w2, xb);
+      const uint64_t f = on ? fm : 0ull;
+      x ^= (((uint64_t)hi << 32) | lo) & f;                    // running XOR of the fields, already shifted by tz
+      xb += on ? numBits : 0u;
+      d[jj][i] = x;
+    }
+  }
+  // exclusive XOR scan of the group totals over the 64 slots
+  uint64_t i0x = d[0][7], i1x = d[1][7];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t y0 = shfl_up_u64(i0x, o), y1 = shfl_up_u64(i1x, o);
+    if (lane >= o) { i0x ^= y0; i1x ^= y1; }
+  }
+  const uint64_t tot0 = shfl_u64(i0x, 31);
+  const uint64_t ex0 = i0x ^ d[0][7], ex1 = i1x ^ d[1][7] ^ tot0;
+  xtab[lane] = ex0; xtab[32 + lane] = ex1;
+  __syncwarp();
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    const bool active = dd_inf[jj] & 1;
+    const int ci = (dd_inf[jj] >> 1) & 3;
+    const WpChunk& ch = CD[ci];
+    // value before the group = first ^ (prefix at the slot) ^ (prefix at the chunk's first slot)
+    const uint64_t pre = ch.first ^ (jj ? ex1 : ex0) ^ xtab[active ? ch.grp_base : 0];
+    uint64_t* dst = reinterpret_cast<uint64_t*>(V) + dd_dst[jj];
+    const int t = (dd_inf[jj] >> 3) & 7;                       // rows t' with t + t' >= 8 sit one pad slot further
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint64_t b = d[jj][i] ^ pre;
+        dst[i + ((t + i) >> 3)] = b;
+        const uint32_t h = (uint32_t)(b >> 32);
+        okbits &= h ^ (h << 1);
+      }
+      if ((dd_inf[jj] >> 8) == 0) { dst[t == 0 ? -2 : -1] = ch.first; const uint32_t h = (uint32_t)(ch.first >> 32); okbits &= h ^ (h << 1); }
+      if (DROPS && ch.dropped) {
+        const int g = dd_inf[jj] >> 8;
+        const int nleft = ch.nrows - 1 - g * 8;                // rows past the chunk are not data
+        double prevv = nan0(__longlong_as_double((long long)pre));
+        uint32_t dm = 0;                                       // bit i: row i of the group drops
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const double cur = nan0(__longlong_as_double((long long)(d[jj][i] ^ pre)));
+          dm |= (i < nleft && cur < prevv) ? (1u << i) : 0u;
+          prevv = cur;
+        }
+        while (dm) {                                           // rare: record position and amount (the value before the drop)
+          const int i = __ffs(dm) - 1; dm &= dm - 1;
+          uint64_t prevbits = pre;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (j == i - 1) prevbits = d[jj][j] ^ pre;
+          TileDrops& D = DR[ci];
+          const int at = atomicAdd(&D.n, 1);
+          if (at < TILE_MAXDROP) { D.pos[at] = 1 + g * 8 + i; D.amt[at] = nan0(__longlong_as_double((long long)prevbits)); }
+        }
+      }
+    }
+  }
+  // raw f64 vectors: plain copy
+  for (int ci = 0; any_raw && ci < n; ++ci) {
+    const WpChunk& ch = CD[ci];
+    if (ch.wire != WIRE_RAW64) continue;
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(R + ch.val_off + 8);
+    const bool drp = DROPS && ch.dropped;
+    for (int r = lane; r < ch.nrows; r += 32) {
+      const uint64_t b = src[r];
+      reinterpret_cast<uint64_t*>(V)[wp_vidx(ch.rowpos + r)] = b;
+      const uint32_t h = (uint32_t)(b >> 32);
+      okbits &= h ^ (h << 1);
+      if (drp && r > 0) {
+        const double cur = nan0(__longlong_as_double((long long)b)), prevv = nan0(__longlong_as_double((long long)src[r - 1]));
+        if (cur < prevv) { TileDrops& D = DR[ci]; const int at = atomicAdd(&D.n, 1); if (at < TILE_MAXDROP) { D.pos[at] = r; D.amt[at] = prevv; } }
+      }
+    }
+  }
+  return okbits;
+}
+
 // window block `it` of the plan: V index of its first row, byte offset (inside the warp's region) of its first result slot, and
 // inf = (jEnd + 1) | raw << 4 | skew phase of the first slot << 5 | chunk << 8 | first window << 10, where slots 0 .. jEnd are stored
 __device__ __forceinline__ void wp_item(const WpChunk* CD, const WpSmem& L, int it, int items, int psi, int& pp, int& op, int& inf) {
@@ -183,56 +358,12 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
     const bool staged = cur_sz <= L.rec_cap;
     if (staged) { mbar_wait(bar, parity); parity ^= 1; }
     // ------------------------------------------------------------------------------------------------ setup (lane c = chunk c)
-    bool regular = staged;
-    int n = 0, cLo = 0;
-    if (staged) {
-      const RecordHeader* h = reinterpret_cast<const RecordHeader*>(R);
-      const ChunkEntry* Eall = reinterpret_cast<const ChunkEntry*>(R + sizeof(RecordHeader));
-      const int nch = (int)h->n_chunks;
-      regular = nch <= 32 && (h->flags & REC_ALL_TS_CONST) != 0;
-      const int64_t t1 = q.start - q.window, t2 = q.end;
-      bool below = false, within = false;
-      if (regular && lane < nch) { below = Eall[lane].end_time < t1; within = !below && Eall[lane].start_time <= t2; }
-      const unsigned mb = __ballot_sync(FULL, below), mw = __ballot_sync(FULL, within);
-      cLo = __ffs((int)~mb) - 1; if (cLo < 0) cLo = 32;                         // chunks are time-ordered: `below` is a prefix
-      const unsigned rest = cLo < 32 ? (mw >> cLo) : 0u;
-      n = __ffs((int)~rest) - 1; if (n < 0) n = 32;
-      if (n > WP_MAXC) regular = false;
-    }
-    const int c = lane;
-    bool have = regular && c < n;
-    int64_t init = 0, end_time = 0; int nrows = 0, num_rows = 0, vbytes = 0, ng = 0, vwire = 0; uint32_t voff = 0, w12 = 0;
-    bool okc = true;
-    if (have) {
-      const ChunkEntry& e = reinterpret_cast<const ChunkEntry*>(R + sizeof(RecordHeader))[cLo + c];
-      const uint8_t* tv = R + e.ts_off; const uint8_t* vv = R + e.val_off;
-      vwire = (int)(ld32(vv + 4) & 0xffff);
-      const int tlen = (int)ld32(tv + 8); init = (int64_t)ld64_a4(tv + 12); const int slope = (int)ld32(tv + 20);
-      end_time = e.end_time; num_rows = e.num_rows; voff = e.val_off;
-      vbytes = (int)ld32(tv) + 4 + (int)ld32(vv) + 4;
-      int vlen = 0;
-      if (vwire == WIRE_XOR) { vlen = (int)ld32(vv + XOR_OFF_N); w12 = ld32(vv + XOR_OFF_NGROUPS); ng = (int)(w12 & 0xffff); if (ng != (vlen + 6) / 8) okc = false; }
-      else if (vwire == WIRE_RAW64) vlen = ((int)ld32(vv) - 4) / 8;
-      else okc = false;
-      if ((int64_t)slope != q.step || tlen <= 0 || vlen <= 0 || num_rows <= 0) okc = false;
-      nrows = num_rows < tlen ? num_rows : tlen;
-      if (vlen != nrows) okc = false;                       // the decode writes every row of the vector
-      if (end_time < init + (int64_t)(nrows - 1) * q.step) okc = false;       // endTime covers the rows: a chunk with rows in a window is in its chunk set
-    }
-    {
-      const int64_t endp = __shfl_up_sync(FULL, end_time, 1);
-      if (have && c > 0 && !(endp < init)) okc = false;       // time-ordered, and the previous chunk is out of the chunk set before this one's rows
-      if (!__all_sync(FULL, okc)) regular = false;
-    }
-    have = have && regular;
-    if (!have) { ng = 0; nrows = 0; }
-    // group slots: exclusive prefix over the chunks
-    int grp_base = ng;
-    { const int a0 = __shfl_sync(FULL, ng, 0), a1 = __shfl_sync(FULL, ng, 1), a2 = __shfl_sync(FULL, ng, 2), a3 = __shfl_sync(FULL, ng, 3);
-      grp_base = (c > 0 ? a0 : 0) + (c > 1 ? a1 : 0) + (c > 2 ? a2 : 0);
-      if (a0 + a1 + a2 + a3 > WP_MAXG) regular = false; }
-    const int ngroups = __shfl_sync(FULL, grp_base + ng, WP_MAXC - 1);
-    const bool any_raw = __any_sync(FULL, have && vwire == WIRE_RAW64);
+    const WpParsed P = wp_parse<true>(R, q, staged, lane);
+    bool regular = P.regular;
+    const bool have = P.have; const int n = P.n, c = lane;
+    const int64_t init = P.init, end_time = P.end_time;
+    const int nrows = P.nrows, num_rows = P.num_rows, vbytes = P.vbytes, ng = P.ng, vwire = P.vwire, grp_base = P.grp_base, ngroups = P.ngroups;
+    const uint32_t voff = P.voff, w12 = P.w12; const bool any_raw = P.any_raw;
     // ---- window plan, reused while the chunk shapes repeat
     const bool samec = !(c < n) || (init == m_init && nrows == m_nrows && end_time == m_end && vwire == m_wire);
     const bool same_all = __all_sync(FULL, samec);
@@ -354,7 +485,7 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
     // per-series parts of the descriptors
     if (c < WP_MAXC) {
       WpChunk& d = CD[c];
-      d.grp_base = have ? grp_base : 0x7fffffff; d.ng = ng; d.wire = vwire; d.val_off = voff;
+      d.grp_base = have ? grp_base : 0x7fffffff; d.ng = ng; d.wire = vwire; d.val_off = voff; d.dropped = P.dropped;
       if (have && vwire == WIRE_XOR) { const uint32_t po = w12 >> 16; d.first = ld64(R + voff + po); d.grp_off = voff + po + 8; d.tab_off = voff + XOR_OFF_GROUPTAB; }
       else { d.first = have ? ld64(R + voff + 8) : 0ull; d.grp_off = 0; d.tab_off = 0; }
     }
@@ -367,78 +498,7 @@ scan_wp_sum_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
     for (int o = 1; o < WP_MAXC; o <<= 1) { cnt_rows += __shfl_xor_sync(FULL, cnt_rows, o); cnt_bytes += __shfl_xor_sync(FULL, cnt_bytes, o); }
     __syncwarp();
     // ------------------------------------------------------------------------------------------------ decode
-    uint32_t okbits = 0xffffffffu;        // bit 30 stays set while every value has exponent bits 10 and 9 different: 2^-511 <= |x| < 2^513
-    {
-      uint64_t d[2][8];
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const bool active = dd_inf[jj] & 1;
-        const WpChunk& ch = CD[(dd_inf[jj] >> 1) & 3];
-        const uint8_t* gp = R;
-        if (active) gp = R + ch.grp_off + reinterpret_cast<const uint16_t*>(R + ch.tab_off)[dd_inf[jj] >> 8];
-        const uint32_t mask = active ? gp[0] : 0u;
-        const uint32_t hdr = gp[1];
-        const uint32_t numBits = ((hdr >> 4) + 1) * 4;
-        const uint32_t tz = (hdr & 0x0f) * 4;
-        const uint64_t fm = (~0ull >> (64 - numBits)) << tz;       // the field's bits in the value
-        // bit address (in shared memory) of the 64-bit window that has field 0 at bit tz
-        uint32_t xb = (wp_soff(gp + 2) << 3) - tz;
-        uint64_t x = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const bool on = (mask >> i) & 1u;
-          const uint32_t wa = (xb >> 3) & ~3u;
-          const uint32_t w0 = wp_lds32(wa), w1 = wp_lds32(wa + 4), w2 = wp_lds32(wa + 8);
-          const uint32_t lo = __funnelshift_r(w0, w1, xb), hi = __funnelshift_r(w1, w2, xb);
-          const uint64_t f = on ? fm : 0ull;
-          x ^= (((uint64_t)hi << 32) | lo) & f;                    // running XOR of the fields, already shifted by tz
-          xb += on ? numBits : 0u;
-          d[jj][i] = x;
-        }
-      }
-      // exclusive XOR scan of the group totals over the 64 slots
-      uint64_t i0x = d[0][7], i1x = d[1][7];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t y0 = shfl_up_u64(i0x, o), y1 = shfl_up_u64(i1x, o);
-        if (lane >= o) { i0x ^= y0; i1x ^= y1; }
-      }
-      const uint64_t tot0 = shfl_u64(i0x, 31);
-      const uint64_t ex0 = i0x ^ d[0][7], ex1 = i1x ^ d[1][7] ^ tot0;
-      xtab[lane] = ex0; xtab[32 + lane] = ex1;
-      __syncwarp();
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const bool active = dd_inf[jj] & 1;
-        const WpChunk& ch = CD[(dd_inf[jj] >> 1) & 3];
-        // value before the group = first ^ (prefix at the slot) ^ (prefix at the chunk's first slot)
-        const uint64_t pre = ch.first ^ (jj ? ex1 : ex0) ^ xtab[active ? ch.grp_base : 0];
-        uint64_t* dst = reinterpret_cast<uint64_t*>(V) + dd_dst[jj];
-        const int t = (dd_inf[jj] >> 3) & 7;                       // rows t' with t + t' >= 8 sit one pad slot further
-        if (active) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint64_t b = d[jj][i] ^ pre;
-            dst[i + ((t + i) >> 3)] = b;
-            const uint32_t h = (uint32_t)(b >> 32);
-            okbits &= h ^ (h << 1);
-          }
-          if ((dd_inf[jj] >> 8) == 0) { dst[t == 0 ? -2 : -1] = ch.first; const uint32_t h = (uint32_t)(ch.first >> 32); okbits &= h ^ (h << 1); }
-        }
-      }
-      // raw f64 vectors: plain copy
-      for (int ci = 0; any_raw && ci < n; ++ci) {
-        const WpChunk& ch = CD[ci];
-        if (ch.wire != WIRE_RAW64) continue;
-        const uint64_t* src = reinterpret_cast<const uint64_t*>(R + ch.val_off + 8);
-        for (int r = lane; r < ch.nrows; r += 32) {
-          const uint64_t b = src[r];
-          reinterpret_cast<uint64_t*>(V)[wp_vidx(ch.rowpos + r)] = b;
-          const uint32_t h = (uint32_t)(b >> 32);
-          okbits &= h ^ (h << 1);
-        }
-      }
-    }
+    const uint32_t okbits = wp_decode<false>(R, V, CD, xtab, dd_dst, dd_inf, n, any_raw, lane, nullptr);
     const bool vals_ok = __all_sync(FULL, (okbits >> 30) & 1u);
     __syncwarp();
     // R is dead: fetch the next record behind the window phase

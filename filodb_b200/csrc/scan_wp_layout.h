@@ -23,7 +23,7 @@ struct WpChunk {                       // per warp, per chunk in range (shared m
   int32_t joff, hs;                    // head share: windows [kT0, ownLo) also take rows from the previous chunk
   int32_t jzb, tb;                     // blocks [0, jzb) (the head share rounded up to whole blocks) leave their raw sums at J[joff ..]; blocks [tb, nblk)
                                        // (from the block that holds ownHi + 1) leave raw sums in O; the blocks in between hold own windows only
-  int32_t pad_;
+  int32_t dropped;                     // counter drop flag of the value vector (PrimitiveVectorReader.dropped, BinaryVector.scala:530-531)
 };
 static_assert(sizeof(WpChunk) == 96, "WpChunk");
 
