@@ -679,6 +679,19 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
       use_wp = w >= 4;
     }
   }
+  // v4 counter-class kernel (scan_wp_ctr.cuh), per-series rows or fused partial rows
+  auto wp_ctr_plan = [&](bool agg_mode, WpCtrSmem& W) -> bool {
+    const bool want_v3 = force && std::string(force) == "v3";
+    if (!use_tile || want_v3 || fn_cls != CLASS_COUNTER || t->max_chunks <= 0) return false;
+    W = wp_ctr_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)t->max_chunks, (uint32_t)q.T, agg_mode);
+    const size_t cap = std::min<size_t>(ctx->max_smem_optin, 227 * 1024) - sizeof(TileCtrTab) * (TILE_CTR_TABMAX + 1) - 64;
+    size_t w = cap / W.per_warp; if (w > (size_t)WP_CTR_MAX_WARPS) w = WP_CTR_MAX_WARPS;
+    static const int warps_env = [] { const char* e = std::getenv("FILO_WP_WARPS"); return e ? atoi(e) : 0; }();
+    if (warps_env > 0 && (size_t)warps_env < w) w = (size_t)warps_env;
+    if (w < 4) return false;
+    W.warps = (uint32_t)w; W.tab = (uint32_t)(W.per_warp * w);
+    return true;
+  };
   auto run_per_series = [&](double* outp) -> int32_t {
     if (use_tile) {
       int64_t* d_list = nullptr; unsigned long long* d_cnt = nullptr;
@@ -691,9 +704,13 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
       LT.grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * ctas_per_sm));
       static const bool dbg = std::getenv("FILO_DEBUG_SYNC") != nullptr;
       if (dbg) { fprintf(stderr, "[filo] tile kernel fn=%d T=%d grid=%d smem=%u pitch=%u\n", fn, q.T, LT.grid, TL.total, TL.vals_pitch); fflush(stderr); }
+      WpCtrSmem WC;
       if (use_wp) {
         LT.grid = (int)std::max<int64_t>(1, std::min<int64_t>((t->n_series + WL.warps - 1) / WL.warps, (int64_t)ctx->sm_count));
         CUDA_TRY(ctx, launch_scan_wp(LT, outp, WL, d_list, d_cnt));
+      } else if (wp_ctr_plan(false, WC)) {
+        LT.grid = (int)std::max<int64_t>(1, std::min<int64_t>((t->n_series + WC.warps - 1) / WC.warps, (int64_t)ctx->sm_count));
+        CUDA_TRY(ctx, launch_scan_wp_ctr(LT, outp, WC, d_list, d_cnt));
       } else CUDA_TRY(ctx, launch_scan_tile(LT, outp, TL, d_list, d_cnt));
       if (dbg) { CUDA_TRY(ctx, cudaStreamSynchronize(s)); fprintf(stderr, "[filo] tile kernel done\n"); fflush(stderr); }
       ScanLaunch LF = L; LF.list = d_list; LF.list_count = d_cnt;
@@ -730,7 +747,11 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
       ScanLaunch LT = L;
       const int ctas_per_sm = ((size_t)TL.total + 1024) * 2 <= (size_t)228 * 1024 ? 2 : 1;
       LT.grid = (int)std::max<int64_t>(1, std::min<int64_t>(t->n_items, (int64_t)ctx->sm_count * ctas_per_sm));
-      CUDA_TRY(ctx, launch_scan_tile_agg(LT, TL, order, t->d_item_begin, t->n_items, agg, pval, pcnt, d_list, d_cnt));
+      WpCtrSmem WC;
+      if (wp_ctr_plan(true, WC)) {
+        LT.grid = (int)std::max<int64_t>(1, std::min<int64_t>((t->n_items + WC.warps - 1) / WC.warps, (int64_t)ctx->sm_count));
+        CUDA_TRY(ctx, launch_scan_wp_ctr_agg(LT, WC, order, t->d_item_begin, t->n_items, agg, pval, pcnt, d_list, d_cnt));
+      } else CUDA_TRY(ctx, launch_scan_tile_agg(LT, TL, order, t->d_item_begin, t->n_items, agg, pval, pcnt, d_list, d_cnt));
       ScanLaunch LF = L; LF.list = d_list; LF.list_count = d_cnt;
       CUDA_TRY(ctx, launch_scan_agg_v2(LF, order, t->d_item_begin, t->n_items, agg, pval, pcnt, acc_bytes, rec_cap_used));
       launches += 1;

@@ -46,6 +46,10 @@ cudaError_t launch_topk(const double* per_series, const int32_t* order, const in
                         double* out_val, int64_t* out_id, cudaStream_t s);
 struct WpSmem;
 cudaError_t launch_scan_wp(const ScanLaunch& L, double* out, const WpSmem& W, int64_t* fallback_list, unsigned long long* fallback_count);
+struct WpCtrSmem;
+cudaError_t launch_scan_wp_ctr(const ScanLaunch& L, double* out, const WpCtrSmem& W, int64_t* fallback_list, unsigned long long* fallback_count);
+cudaError_t launch_scan_wp_ctr_agg(const ScanLaunch& L, const WpCtrSmem& W, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg_op,
+                                   double* pval, uint32_t* pcnt, int64_t* fallback_list, unsigned long long* fallback_count);
 size_t hist_smem_bytes(int max_rows, int nb, int T, bool agg, uint32_t max_rec);
 cudaError_t launch_hist_scan(const ScanLaunch& L, int nb, int max_rows, uint32_t max_rec, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg,
                              double* out, double* pval, uint8_t* pany);

@@ -11,6 +11,7 @@
 #include "scan_fast.cuh"
 #include "scan_tile.cuh"
 #include "scan_wp.cuh"
+#include "scan_wp_ctr.cuh"
 
 namespace filo {
 
@@ -496,6 +497,37 @@ cudaError_t launch_scan_wp(const ScanLaunch& L, double* out, const WpSmem& W, in
     case FN_COUNT: return launch_wp_fn<FN_COUNT>(L, out, W, fallback_list, fallback_count);
     default: return launch_wp_fn<FN_SUM>(L, out, W, fallback_list, fallback_count);      // FN_SUM, FN_INCREASE on a delta schema
   }
+}
+// v4 counter-class kernel (scan_wp_ctr.cuh): per-series rows (order == nullptr, n_items == 0) or one partial row per work item
+template <int FN, bool AGG, int NW>
+static cudaError_t launch_wp_ctr_nw(const ScanLaunch& L, double* out, const WpCtrSmem& W, int64_t* fallback_list, unsigned long long* fallback_count,
+                                    const TileAggArgs& A) {
+  const size_t smem = (size_t)W.per_warp * W.warps + sizeof(TileCtrTab) * (TILE_CTR_TABMAX + 1);
+  cudaError_t e = cudaFuncSetAttribute(scan_wp_ctr_kernel<FN, AGG, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  scan_wp_ctr_kernel<FN, AGG, NW><<<L.grid, W.warps * 32, smem, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, W, fallback_list, fallback_count,
+      L.d_counters, L.d_err, A.order, A.item_begin, A.n_items, A.agg_op, A.pval, A.pcnt);
+  return cudaGetLastError();
+}
+template <int FN, bool AGG>
+static cudaError_t launch_wp_ctr_fn(const ScanLaunch& L, double* out, const WpCtrSmem& W, int64_t* fallback_list, unsigned long long* fallback_count, const TileAggArgs& A) {
+  if (W.warps <= 16) return launch_wp_ctr_nw<FN, AGG, 16>(L, out, W, fallback_list, fallback_count, A);
+  return launch_wp_ctr_nw<FN, AGG, WP_CTR_MAX_WARPS>(L, out, W, fallback_list, fallback_count, A);
+}
+template <bool AGG>
+static cudaError_t launch_wp_ctr_any(const ScanLaunch& L, double* out, const WpCtrSmem& W, int64_t* fallback_list, unsigned long long* fallback_count, const TileAggArgs& A) {
+  switch (L.q.fn) {
+    case FN_RATE: return launch_wp_ctr_fn<FN_RATE, AGG>(L, out, W, fallback_list, fallback_count, A);
+    case FN_INCREASE: return launch_wp_ctr_fn<FN_INCREASE, AGG>(L, out, W, fallback_list, fallback_count, A);
+    default: return launch_wp_ctr_fn<FN_DELTA, AGG>(L, out, W, fallback_list, fallback_count, A);
+  }
+}
+cudaError_t launch_scan_wp_ctr(const ScanLaunch& L, double* out, const WpCtrSmem& W, int64_t* fallback_list, unsigned long long* fallback_count) {
+  return launch_wp_ctr_any<false>(L, out, W, fallback_list, fallback_count, TileAggArgs{nullptr, nullptr, 0, 0, nullptr, nullptr});
+}
+cudaError_t launch_scan_wp_ctr_agg(const ScanLaunch& L, const WpCtrSmem& W, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg_op,
+                                   double* pval, uint32_t* pcnt, int64_t* fallback_list, unsigned long long* fallback_count) {
+  return launch_wp_ctr_any<true>(L, nullptr, W, fallback_list, fallback_count, TileAggArgs{order, item_begin, n_items, agg_op, pval, pcnt});
 }
 size_t v2_smem_per_warp(uint32_t rec_cap, uint32_t scratch_bytes, uint32_t acc_bytes) { return WARP_HDR_BYTES + (size_t)rec_cap + STAGE_BYTES + acc_bytes + scratch_bytes; }
 cudaError_t launch_scan_series(const ScanLaunch& L, double* out) {

@@ -3,6 +3,7 @@
 #include <stdint.h>
 #include "filo_record.h"
 #include "scan_params.h"
+#include "scan_tile_layout.h"
 namespace filo {
 constexpr int WP_MAXC = 4;             // chunks in range per series on this path
 constexpr int WP_MAXG = 64;            // NibblePack groups per series (two per lane)
@@ -62,6 +63,38 @@ FILO_HD inline uint32_t wp_max_items(uint32_t max_chunks, uint32_t T, uint32_t w
   if (max_chunks > (uint32_t)WP_MAXC) max_chunks = WP_MAXC;
   if (max_chunks == 0) max_chunks = 1;
   return (T + (max_chunks - 1) * (wrows - 1) + 7 * max_chunks) / 8;
+}
+
+constexpr int WP_CTR_MAX_WARPS = 20;   // counter kernel: warps per CTA at the lower register budget
+struct WpCtrChunk {                    // per warp, per chunk in range: plan (window intervals, extrapolation constants)
+  int64_t init, end_time;
+  int32_t nrows, s0, e0, rowpos;
+  int32_t kA, kB;                      // unclamped single-chunk windows with at least two samples ([0, -1] if none)
+  int32_t kA2, kB2;                    // every single-chunk window of the chunk, clamped ones included
+  TileCtr kc;                          // per-series: kc.dropped
+};
+static_assert(sizeof(WpCtrChunk) == 112, "WpCtrChunk");
+
+struct WpCtrSmem {                     // byte offsets inside a warp's region (multiples of 16); R sits at WP_OFF_REC, xtab at WP_OFF_J, drops behind it
+  uint32_t vals, kc, acc, nbad, per_warp, tab /* per CTA, behind the warps' regions */;
+  uint32_t rec_cap, vcap /*doubles*/, warps, agg;
+};
+constexpr uint32_t WP_OFF_DROPS = WP_OFF_J + 64 * 8;          // TileDrops[WP_MAXC] behind the 64-word XOR prefix table
+static_assert(WP_OFF_DROPS + WP_MAXC * sizeof(TileDrops) <= WP_OFF_REC, "drops fit in front of the record");
+FILO_HD inline WpCtrSmem wp_ctr_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t max_chunks, uint32_t T, bool agg) {
+  WpCtrSmem L;
+  if (max_chunks > (uint32_t)WP_MAXC) max_chunks = WP_MAXC;
+  L.rec_cap = align_up(max_rec_bytes + 16, 16);
+  const uint32_t P = max_rows + 8 * max_chunks + 8;            // 8 spare rows behind every chunk: the group decode runs up to 7 rows past it
+  L.vcap = align_up(P + P / 8 + 2, 2);
+  uint32_t o = WP_OFF_REC + L.rec_cap;
+  L.vals = o; o += L.vcap * 8;
+  L.kc = o; o += (uint32_t)(WP_MAXC * sizeof(WpCtrChunk));
+  L.acc = o; L.nbad = o;
+  if (agg) { o += T * 8; L.nbad = o; o += align_up(T * 2, 16); }
+  L.per_warp = align_up(o, 16);
+  L.tab = 0; L.warps = 0; L.agg = agg ? 1u : 0u;
+  return L;
 }
 
 } // namespace filo

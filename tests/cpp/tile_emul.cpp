@@ -191,6 +191,15 @@ int main(int argc, char** argv) {
     {0, false, filo::FN_RATE, {500, 400}, 0, 0, 300000, 7, 1, 0, 0, 0, 1, 0, false, false, false, false, true},                      // more than 64 blocks per series: second pass
     {0, true, filo::FN_SUM, {150, 90}, 0, 0, 300000, 29, 1, -90000, 45000, 0, 2, 0, false, false, false, false, true, true},          // chunk shapes differ from series to series: the plan memo is invalidated
     {0, false, filo::FN_AVG, {200, 100}, 0, 0, 180000, 21, 0, 0, 0, 0, 1, 0, false, false, false, false, true, true},
+    // the v4 counter-class kernel (scan_wp_ctr.cuh): per-series and fused, resets (drop lists), raw vectors, delta
+    {1, true, filo::FN_RATE, {400, 80}, 0, 0, 300000, 10, 1, 0, 0, 0, 2, 0, false, false, false, false, true},
+    {1, true, filo::FN_INCREASE, {120, 120, 60}, 0, 41, 60000, 19, 1, -30000, 30000, 0, 2, 0, false, false, false, false, true},
+    {1, false, filo::FN_DELTA, {200, 100}, 0, 0, 300000, 6, 0, 0, 0, 0, 1, 0, false, false, false, false, true},
+    {1, true, filo::FN_RATE, {400, 80}, 200000, 61, 300000, 13, 1, 0, 0, 0, 2, 0, false, false, false, false, true},                  // NaN markers + resets
+    {1, true, filo::FN_RATE, {150, 90}, 0, 7, 300000, 21, 1, 0, 0, 0, 2, 0, false, false, false, false, true, true},                   // frequent resets (drop list overflow -> declined), shapes differ
+    {1, true, filo::FN_INCREASE, {120, 120, 60}, 0, 41, 60000, 12, 1, -30000, 30000, filo::AGG_SUM, 2, 0, false, false, false, false, true},   // fused
+    {1, true, filo::FN_RATE, {240, 240}, 0, 97, 300000, 17, 1, 0, 0, filo::AGG_MAX, 2, 0, false, false, false, false, true},
+    {1, true, filo::FN_RATE, {100, 50, 50, 50, 50}, 0, 0, 300000, 12, 1, 0, 0, filo::AGG_SUM, 2, 0, false, false, false, false, true},  // fused, every item declined
     // the v2 warp-per-series kernel on its own: every function class, irregular scrapes (DDV timestamps), integral values (DDV longs)
     {0, true, filo::FN_MIN, {150, 90}, 100000, 0, 300000, 9, 1, -30000, 15000, 0, 2, 0, false, true},
     {0, false, filo::FN_MAX, {64, 64, 64, 64, 64}, 0, 0, 200000, 7, 0, 0, 0, 0, 1, 0, false, true},
@@ -303,6 +312,21 @@ int main(int argc, char** argv) {
         if (derr[0]) { std::printf("FAIL cfg %zu: device error %d (wp kernel)\n", ci, derr[0]); return 1; }
         g_wp_declined += (long)fcount; g_wp_series += c.nser;
         if (fcount) run_v2(A, sh, flist.data(), &fcount);
+      } else if (tile_ok && c.wp && cls == filo::CLASS_COUNTER) {
+        filo::WpCtrSmem W = filo::wp_ctr_layout(max_rec, (uint32_t)rows, (uint32_t)c.chunks.size(), (uint32_t)q.T, false);
+        W.warps = 3; W.tab = W.per_warp * W.warps;
+        if ((size_t)W.tab + 4096 > sizeof(filo::smem)) { std::printf("FAIL: wp ctr layout %u bytes per warp\n", W.per_warp); return 1; }
+        auto body = [&](auto fnc) {
+          cusim::launch(dim3((unsigned)A.grid), dim3(W.warps * 32), [&] {
+            filo::scan_wp_ctr_kernel<decltype(fnc)::value, false, 16>(A.arena, A.rec_off, A.S, A.q, A.out, W, A.flist, A.fcount, A.counters, A.derr, nullptr, nullptr, 0, 0, nullptr, nullptr);
+          });
+        };
+        if (q.fn == filo::FN_RATE) body(std::integral_constant<int, filo::FN_RATE>{});
+        else if (q.fn == filo::FN_INCREASE) body(std::integral_constant<int, filo::FN_INCREASE>{});
+        else body(std::integral_constant<int, filo::FN_DELTA>{});
+        if (derr[0]) { std::printf("FAIL cfg %zu: device error %d (wp ctr kernel)\n", ci, derr[0]); return 1; }
+        g_wp_declined += (long)fcount; g_wp_series += c.nser;
+        if (fcount) run_v2(A, sh, flist.data(), &fcount);
       } else if (tile_ok) {
         dispatch<false>(A);
         if (derr[0]) { std::printf("FAIL cfg %zu: device error %d (tile kernel)\n", ci, derr[0]); return 1; }
@@ -330,7 +354,19 @@ int main(int argc, char** argv) {
       const int64_t n_items = (int64_t)item_begin.size() - 1;
       std::vector<double> pval((size_t)n_items * q.T, -777.0); std::vector<uint32_t> pcnt((size_t)n_items * q.T, 12345u);
       A.order = order.data(); A.item_begin = item_begin.data(); A.n_items = n_items; A.agg_op = c.agg_op; A.pval = pval.data(); A.pcnt = pcnt.data(); A.out = nullptr;
-      dispatch<true>(A);
+      if (c.wp && filo::fn_class_of(q.fn, q.cumulative) == filo::CLASS_COUNTER) {
+        filo::WpCtrSmem W = filo::wp_ctr_layout(max_rec, (uint32_t)rows, (uint32_t)c.chunks.size(), (uint32_t)q.T, true);
+        W.warps = 3; W.tab = W.per_warp * W.warps;
+        if ((size_t)W.tab + 4096 > sizeof(filo::smem)) { std::printf("FAIL: wp ctr layout %u bytes per warp\n", W.per_warp); return 1; }
+        auto body = [&](auto fnc) {
+          cusim::launch(dim3((unsigned)A.grid), dim3(W.warps * 32), [&] {
+            filo::scan_wp_ctr_kernel<decltype(fnc)::value, true, 16>(A.arena, A.rec_off, A.S, A.q, nullptr, W, A.flist, A.fcount, A.counters, A.derr, A.order, A.item_begin, A.n_items, A.agg_op, A.pval, A.pcnt);
+          });
+        };
+        if (q.fn == filo::FN_RATE) body(std::integral_constant<int, filo::FN_RATE>{});
+        else if (q.fn == filo::FN_INCREASE) body(std::integral_constant<int, filo::FN_INCREASE>{});
+        else body(std::integral_constant<int, filo::FN_DELTA>{});
+      } else dispatch<true>(A);
       if (derr[0]) { std::printf("FAIL cfg %zu: device error %d\n", ci, derr[0]); return 1; }
       if (fcount) {                                                     // declined items: the fused v2 kernel, as filo_query chains it
         V2Shape sh{max_rec, rows, (int)c.chunks.size(), false, false};
