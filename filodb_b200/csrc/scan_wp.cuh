@@ -243,21 +243,15 @@ __device__ __forceinline__ uint32_t wp_decode(const uint8_t* R, double* V, const
         const int g = dd_inf[jj] >> 8;
         const int nleft = ch.nrows - 1 - g * 8;                // rows past the chunk are not data
         double prevv = nan0(__longlong_as_double((long long)pre));
-        uint32_t dm = 0;                                       // bit i: row i of the group drops
+        TileDrops& D = DR[ci];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const double cur = nan0(__longlong_as_double((long long)(d[jj][i] ^ pre)));
-          dm |= (i < nleft && cur < prevv) ? (1u << i) : 0u;
+          if (i < nleft && cur < prevv) {                      // rare: position and amount (the value before the drop)
+            const int at = atomicAdd(&D.n, 1);
+            if (at < TILE_MAXDROP) { D.pos[at] = 1 + g * 8 + i; D.amt[at] = prevv; }
+          }
           prevv = cur;
-        }
-        while (dm) {                                           // rare: record position and amount (the value before the drop)
-          const int i = __ffs(dm) - 1; dm &= dm - 1;
-          uint64_t prevbits = pre;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) if (j == i - 1) prevbits = d[jj][j] ^ pre;
-          TileDrops& D = DR[ci];
-          const int at = atomicAdd(&D.n, 1);
-          if (at < TILE_MAXDROP) { D.pos[at] = 1 + g * 8 + i; D.amt[at] = nan0(__longlong_as_double((long long)prevbits)); }
         }
       }
     }

@@ -28,7 +28,7 @@ __device__ __forceinline__ double wp_ctr_value(const double* V, const WpCtrChunk
 
 // literal per-chunk fold of the counter functions for one window: tile_eval_counter (scan_tile.cuh) over the skewed V layout
 template <int FN>
-__device__ __forceinline__ double wp_eval_counter(int n, const WpCtrChunk* K, const WpChunk* CD, const TileDrops* DR, const double* V, const QueryParams& q,
+__device__ FILO_NOINLINE double wp_eval_counter(int n, const WpCtrChunk* K, const WpChunk* CD, const TileDrops* DR, const double* V, int64_t qstep, int qinclusive,
                                                   int64_t wStart, int64_t wEnd, int k, double fdiv, double frcp, const TileCtrTab* tab) {
   const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
   int32_t numSamples = 0; int64_t loT = INT64_MAX, hiT = 0; double loV = NaNv, hiV = NaNv;
@@ -42,7 +42,7 @@ __device__ __forceinline__ double wp_eval_counter(int n, const WpCtrChunk* K, co
     const double first = __longlong_as_double((long long)CD[c].first);
     if (FN != FN_DELTA && some) { if (first != first || first < corrLast) corr = corr + corrLast; }
     if (su <= eu) {
-      const int64_t tS = ch.init + (int64_t)su * q.step, tE = ch.init + (int64_t)eu * q.step;
+      const int64_t tS = ch.init + (int64_t)su * qstep, tE = ch.init + (int64_t)eu * qstep;
       const bool skip = FN != FN_DELTA && su == 0 && eu == 0 && first != first;      // RateFunctions.scala:255-256
       if (!skip && (tS < loT || tE > hiT)) {
         numSamples += eu - su + 1;
@@ -61,9 +61,22 @@ __device__ __forceinline__ double wp_eval_counter(int n, const WpCtrChunk* K, co
     }
     some = true;
   }
-  const int64_t cws = q.inclusive ? wStart : wStart - 1;               // RateFunctions.scala:270-285
-  if (hiT > loT) return extrapolated_rate_tile<FN != FN_DELTA, FN == FN_RATE>(cws, wEnd, numSamples, loT, loV, hiT, hiV, fdiv, frcp, q.step, tab);
+  const int64_t cws = qinclusive ? wStart : wStart - 1;                // RateFunctions.scala:270-285
+  if (hiT > loT) return extrapolated_rate_tile<FN != FN_DELTA, FN == FN_RATE>(cws, wEnd, numSamples, loT, loV, hiT, hiV, fdiv, frcp, qstep, tab);
   return NaNv;
+}
+
+// one clamped single-chunk window (kept out of line: one or two warp iterations per series go through it)
+template <int FN>
+__device__ FILO_NOINLINE double wp_clamped_window(const double* V, const WpCtrChunk& ch, const TileDrops& D, bool drp, int kk, int64_t wEnd, int64_t cws, int64_t qstep,
+                                                   double fdiv, double frcp, const TileCtrTab* tab) {
+  int r1 = ch.s0 + kk; if (r1 < 0) r1 = 0;
+  int r2 = ch.e0 + kk; if (r2 > ch.nrows - 1) r2 = ch.nrows - 1;
+  if (!(r2 > r1)) return __longlong_as_double(0x7ff8000000000000LL);      // highestTime > lowestTime (RateFunctions.scala:271,284)
+  double v1 = wp_row(V, ch, r1), v2 = wp_row(V, ch, r2);
+  if (drp) { v1 = nan0(v1) + drops_cum(D, r1); v2 = nan0(v2) + drops_cum(D, r2); }
+  return extrapolated_rate_tile<FN != FN_DELTA, FN == FN_RATE>(cws, wEnd, r2 - r1 + 1, ch.init + (int64_t)r1 * qstep, v1, ch.init + (int64_t)r2 * qstep, v2,
+                                                              fdiv, frcp, qstep, tab);
 }
 
 template <int FN, bool AGG, int NW>
@@ -117,34 +130,30 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
   uint32_t parity = 0;
 
   // ---- walk: per-series mode = series gw, gw + nwarps, ...; AGG = items gw, gw + nwarps, ..., positions item_begin[it] .. item_begin[it + 1]
-  struct Pos { int64_t it, p, pe; };
-  auto item_seek = [&](Pos& w) -> bool {                   // first non-empty item at or after w.it
-    while (w.it < n_items) { w.p = item_begin[w.it]; w.pe = item_begin[w.it + 1]; if (w.p < w.pe) return true; w.it += nwarps; }
-    return false;
-  };
-  auto pos_start = [&](Pos& w) -> bool {
-    if (AGG) { w.it = gw; return item_seek(w); }
-    w.it = 0; w.p = gw; w.pe = n_series; return w.p < n_series;
-  };
-  auto pos_next = [&](Pos& w, bool skip_item) -> bool {    // successor of w (skip_item: the rest of the item is not wanted)
-    if (AGG) { if (!skip_item && w.p + 1 < w.pe) { w.p += 1; return true; } w.it += nwarps; return item_seek(w); }
-    w.p += nwarps; return w.p < n_series;
-  };
-  auto sid_of = [&](const Pos& w) -> int64_t { return (AGG && order) ? (int64_t)order[w.p] : w.p; };
+  // walk position = (item, position, item end); plain scalars (a struct handed to the helpers by reference ends up in local memory)
+  int64_t c_it = 0, c_p = 0, c_pe = 0, x_it = 0, x_p = 0, x_pe = 0;
+#define WP_ITEM_SEEK(it, p, pe, ok) { ok = false; while (it < n_items) { p = item_begin[it]; pe = item_begin[it + 1]; if (p < pe) { ok = true; break; } it += nwarps; } }
+  // successor of (it, p, pe) into (it, p, pe); skip_item: the rest of the item is not wanted
+#define WP_POS_NEXT(it, p, pe, skip_item, ok) { \
+    if (AGG) { if (!(skip_item) && p + 1 < pe) { p += 1; ok = true; } else { it += nwarps; WP_ITEM_SEEK(it, p, pe, ok) } } \
+    else { p += nwarps; ok = p < n_series; } }
+  auto sid_at = [&](int64_t p) -> int64_t { return (AGG && order) ? (int64_t)order[p] : p; };
   auto issue = [&](int64_t off, uint32_t sz) { mbar_expect_tx(bar, sz); tma_load_1d(R, arena + off, sz, bar); };
 
-  Pos cur; bool more = pos_start(cur);
+  bool more;
+  if (AGG) { c_it = gw; WP_ITEM_SEEK(c_it, c_p, c_pe, more) } else { c_p = gw; c_pe = n_series; more = c_p < n_series; }
   int64_t cur_sid = 0, cur_off = 0; uint32_t cur_sz = 0;
-  if (more) { cur_sid = sid_of(cur); cur_off = rec_off[cur_sid]; cur_sz = (uint32_t)(rec_off[cur_sid + 1] - cur_off); }
+  if (more) { cur_sid = sid_at(c_p); cur_off = rec_off[cur_sid]; cur_sz = (uint32_t)(rec_off[cur_sid + 1] - cur_off); }
   if (more && cur_sz <= L.rec_cap && lane == 0) issue(cur_off, cur_sz);
   bool item_bad = false; int item_nser = 0;
   if (AGG) { for (int k = lane; k < q.T; k += 32) { ACC[k] = agg_ident; NBAD[k] = 0; } __syncwarp(); }
 
   while (more) {
     // successor in walk order (its record is fetched as soon as R is dead)
-    Pos nxt = cur; bool nmore = pos_next(nxt, false);
+    x_it = c_it; x_p = c_p; x_pe = c_pe; bool nmore;
+    WP_POS_NEXT(x_it, x_p, x_pe, false, nmore)
     int64_t nxt_sid = 0, nxt_off = 0; uint32_t nxt_sz = 0;
-    if (nmore) { nxt_sid = sid_of(nxt); nxt_off = rec_off[nxt_sid]; nxt_sz = (uint32_t)(rec_off[nxt_sid + 1] - nxt_off); }
+    if (nmore) { nxt_sid = sid_at(x_p); nxt_off = rec_off[nxt_sid]; nxt_sz = (uint32_t)(rec_off[nxt_sid + 1] - nxt_off); }
     const bool staged = cur_sz <= L.rec_cap;
     if (staged) { mbar_wait(bar, parity); parity ^= 1; }
     const int64_t s = cur_sid;
@@ -245,8 +254,9 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
     }
     // R is dead: fetch the successor's record behind the window phase
     if (AGG && (declined || item_bad) && !skip) {          // the item fails here: its remaining series are not wanted
-      nxt = cur; nmore = pos_next(nxt, true);
-      if (nmore) { nxt_sid = sid_of(nxt); nxt_off = rec_off[nxt_sid]; nxt_sz = (uint32_t)(rec_off[nxt_sid + 1] - nxt_off); }
+      x_it = c_it; x_p = c_p; x_pe = c_pe;
+      WP_POS_NEXT(x_it, x_p, x_pe, true, nmore)
+      if (nmore) { nxt_sid = sid_at(x_p); nxt_off = rec_off[nxt_sid]; nxt_sz = (uint32_t)(rec_off[nxt_sid + 1] - nxt_off); }
     }
     __syncwarp();
     if (nmore && nxt_sz <= L.rec_cap && lane == 0) issue(nxt_off, nxt_sz);
@@ -298,10 +308,13 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
         const int dn = drp ? D.n : 0;
         const int dpos0 = dn >= 1 ? D.pos[0] : 0x7fffffff;
         const double damt0 = dn >= 1 ? D.amt[0] : 0.0;
-        for (int kk = ch.kA + lane; hasfast && kk <= ch.kB; kk += 32) {
-          const int r1 = ch.s0 + kk, r2 = ch.e0 + kk;
-          double v1 = wp_row(V, ch, r1), v2 = wp_row(V, ch, r2);
+        // V index of row r0 + 32 m = index of row r0 + 36 m (one pad slot per 8 rows)
+        const double* p1 = V + wp_vidx(ch.rowpos + ch.s0 + ch.kA + lane);
+        const double* p2 = V + wp_vidx(ch.rowpos + ch.e0 + ch.kA + lane);
+        for (int kk = ch.kA + lane; hasfast && kk <= ch.kB; kk += 32, p1 += 36, p2 += 36) {
+          double v1 = *p1, v2 = *p2;
           if (drp) {
+            const int r1 = ch.s0 + kk, r2 = ch.e0 + kk;
             if (dn <= 1) { v1 = nan0(v1) + (r1 >= dpos0 ? damt0 : 0.0); v2 = nan0(v2) + (r2 >= dpos0 ? damt0 : 0.0); }
             else { v1 = nan0(v1) + drops_cum(D, r1); v2 = nan0(v2) + drops_cum(D, r2); }     // sorted running sums
           }
@@ -321,17 +334,8 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
         const int nlo = hasfast ? ch.kA - ch.kA2 : ch.kB2 - ch.kA2 + 1, nhi = hasfast ? ch.kB2 - ch.kB : 0;
         for (int u = lane; u < nlo + nhi; u += 32) {
           const int kk = u < nlo ? ch.kA2 + u : ch.kB + 1 + (u - nlo);
-          int r1 = ch.s0 + kk; if (r1 < 0) r1 = 0;
-          int r2 = ch.e0 + kk; if (r2 > ch.nrows - 1) r2 = ch.nrows - 1;
-          double res = NaNv;
-          if (r2 > r1) {                                   // highestTime > lowestTime (RateFunctions.scala:271,284)
-            double v1 = wp_row(V, ch, r1), v2 = wp_row(V, ch, r2);
-            if (drp) { v1 = nan0(v1) + drops_cum(D, r1); v2 = nan0(v2) + drops_cum(D, r2); }
-            const int64_t wEnd = q.start + (int64_t)kk * q.step, cws = wEnd - winDur - (q.inclusive ? 0 : 1);
-            res = extrapolated_rate_tile<FN != FN_DELTA, FN == FN_RATE>(cws, wEnd, r2 - r1 + 1, ch.init + (int64_t)r1 * q.step, v1,
-                                                                        ch.init + (int64_t)r2 * q.step, v2, fdiv, frcp, q.step, CTAB);
-          }
-          emit(kk, res);
+          const int64_t wEnd = q.start + (int64_t)kk * q.step, cws = wEnd - winDur - (q.inclusive ? 0 : 1);
+          emit(kk, wp_clamped_window<FN>(V, ch, D, drp, kk, wEnd, cws, q.step, fdiv, frcp, CTAB));
         }
       }
       // windows outside every chunk's single-chunk interval (chunk junctions, no data): literal fold, lanes over the gaps
@@ -342,7 +346,7 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
           if (ci < n) { if (KC[ci].kA2 > KC[ci].kB2) continue; gend = KC[ci].kA2; }
           for (int k = prev + 1 + lane; k < gend; k += 32) {
             const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - winDur;
-            emit(k, wp_eval_counter<FN>(n, KC, CD, DR, V, q, wStart, wEnd, k, fdiv, frcp, CTAB));
+            emit(k, wp_eval_counter<FN>(n, KC, CD, DR, V, q.step, q.inclusive, wStart, wEnd, k, fdiv, frcp, CTAB));
           }
           if (ci < n) prev = KC[ci].kB2;
         }
@@ -352,26 +356,29 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
     }
     // ---------------------------------------------------------------------------------------------- item end (AGG)
     if (AGG) {
-      const bool last_of_item = !nmore || nxt.it != cur.it;
+      const bool last_of_item = !nmore || x_it != c_it;
       if (last_of_item) {
         __syncwarp();
         if (!item_bad) {
-          double* pv = pval + (size_t)cur.it * q.T; uint32_t* pc = pcnt + (size_t)cur.it * q.T;
+          double* pv = pval + (size_t)c_it * q.T; uint32_t* pc = pcnt + (size_t)c_it * q.T;
           for (int k = lane; k < q.T; k += 32) { pv[k] = ACC[k]; pc[k] = (uint32_t)(item_nser - (int)NBAD[k]); }
           if (lane == 0) { rows_scanned += pend_rows; bytes_scanned += pend_bytes; }
         } else if (lane == 0) {
-          const unsigned long long slot = atomicAdd(fallback_count, 1ull); fallback_list[slot] = cur.it;
+          const unsigned long long slot = atomicAdd(fallback_count, 1ull); fallback_list[slot] = c_it;
         }
         for (int k = lane; k < q.T; k += 32) { ACC[k] = agg_ident; NBAD[k] = 0; }
         pend_rows = 0; pend_bytes = 0; item_bad = false; item_nser = 0;
       }
     }
     __syncwarp();
-    cur = nxt; more = nmore; cur_sid = nxt_sid; cur_off = nxt_off; cur_sz = nxt_sz;
+    c_it = x_it; c_p = x_p; c_pe = x_pe; more = nmore; cur_sid = nxt_sid; cur_off = nxt_off; cur_sz = nxt_sz;
   }
   if (lane == 0 && (rows_scanned | bytes_scanned)) {
     atomicAdd(&d_counters[0], (unsigned long long)rows_scanned); atomicAdd(&d_counters[1], (unsigned long long)bytes_scanned);
   }
 }
+
+#undef WP_ITEM_SEEK
+#undef WP_POS_NEXT
 
 } // namespace filo
