@@ -99,12 +99,19 @@ struct StepDiv {
 // x / y for a loop-invariant y, with rcp = RN(1/y) precomputed: q0 = RN(x*rcp); r = x - q0*y (exact, FMA); q = RN(q0 + r*rcp).
 // This is the final correction step of the IEEE division sequence (Markstein) and returns the correctly rounded quotient
 // whenever q0 is a normal number well inside the exponent range; anything else takes the real division.  y > 0 is assumed.
+// IEEE division kept out of line: at the call sites below it is the rare branch, and an inlined division (about 40 instructions) gets
+// if-converted into the common path, where it is issued for every window with its results predicated off
+#ifdef FILO_CUSIM
+inline double ddiv_rare(double x, double y) { return x / y; }
+#else
+static __device__ __noinline__ double ddiv_rare(double x, double y) { return x / y; }
+#endif
 __device__ __forceinline__ double div_invariant(double x, double y, double rcp) {
   const double q0 = __dmul_rn(x, rcp);
   const uint32_t ex = ((uint32_t)__double2hiint(q0) >> 20) & 0x7ff;     // biased exponent
   if (ex > 64u && ex < 1983u) { const double r = __fma_rn(-q0, y, x); return __fma_rn(r, rcp, q0); }
   if (x == 0.0) return q0;                 // +-0 / y (y > 0, finite): the product already has the quotient's sign
-  return x / y;
+  return ddiv_rare(x, y);
 }
 
 // Single-chunk window interval [kA, kB] of chunk c (const-DDV timestamps with 0 < slope == step).  Window k belongs to it

@@ -122,20 +122,20 @@ __device__ __forceinline__ double extrapolated_rate_tile(int64_t windowStart, in
     sampledInterval = e.sI; extrapolationThreshold = e.thr; half = e.half; rcpSI = e.rcpSI;
   } else {
     sampledInterval = div_invariant((double)si_ms, 1000.0, 0.001);
-    const double averageDurationBetweenSamples = sampledInterval / ((double)numSamples - 1.0);
+    const double averageDurationBetweenSamples = ddiv_rare(sampledInterval, (double)numSamples - 1.0);
     extrapolationThreshold = averageDurationBetweenSamples * 1.1; half = averageDurationBetweenSamples / 2.0; rcpSI = 0.0;
   }
   const double delta = v2 - v1;
   if (IS_COUNTER && delta > 0 && v1 >= 0) {
     if (!(v1 * sampledInterval > 2.0 * durationToStart * delta)) {
-      const double durationToZero = sampledInterval * (v1 / delta);
+      const double durationToZero = sampledInterval * ddiv_rare(v1, delta);
       if (durationToZero < durationToStart) durationToStart = durationToZero;
     }
   }
   double extrapolateToInterval = sampledInterval;
   extrapolateToInterval += (durationToStart < extrapolationThreshold) ? durationToStart : half;
   extrapolateToInterval += (durationToEnd < extrapolationThreshold) ? durationToEnd : half;
-  const double ratio = rcpSI != 0.0 ? div_invariant(extrapolateToInterval, sampledInterval, rcpSI) : extrapolateToInterval / sampledInterval;
+  const double ratio = rcpSI != 0.0 ? div_invariant(extrapolateToInterval, sampledInterval, rcpSI) : ddiv_rare(extrapolateToInterval, sampledInterval);
   const double scaledDelta = delta * ratio;
   return IS_RATE ? __dmul_rn(div_invariant(scaledDelta, fdiv, frcp), 1000.0) : scaledDelta;
 }

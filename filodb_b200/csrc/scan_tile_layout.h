@@ -48,7 +48,7 @@ struct TileCtr {
 };
 // TileDrops (consumers, per tile): counter drops of a drop-flagged chunk, found while its rows are decoded
 // (CorrectingDoubleVectorReader.corrected, DoubleVector.scala:325-342): row position and the amount added to the correction
-constexpr int TILE_MAXDROP = 4;
+constexpr int TILE_MAXDROP = 8;
 // per-query table of the extrapolation terms that depend only on (numSamples - 1) = m when the samples are m steps apart
 constexpr int TILE_CTR_TABMAX = 64;
 struct TileCtrTab { double sI, thr, half, rcpSI; };      // sampledInterval, 1.1 * average interval, average / 2, RN(1 / sI)

@@ -28,7 +28,7 @@ __device__ __forceinline__ double wp_ctr_value(const double* V, const WpCtrChunk
 
 // literal per-chunk fold of the counter functions for one window: tile_eval_counter (scan_tile.cuh) over the skewed V layout
 template <int FN>
-__device__ FILO_NOINLINE double wp_eval_counter(int n, const WpCtrChunk* K, const WpChunk* CD, const TileDrops* DR, const double* V, int64_t qstep, int qinclusive,
+__device__ __forceinline__ double wp_eval_counter(int n, const WpCtrChunk* K, const WpChunk* CD, const TileDrops* DR, const double* V, int64_t qstep, int qinclusive,
                                                   int64_t wStart, int64_t wEnd, int k, double fdiv, double frcp, const TileCtrTab* tab) {
   const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
   int32_t numSamples = 0; int64_t loT = INT64_MAX, hiT = 0; double loV = NaNv, hiV = NaNv;
@@ -66,9 +66,15 @@ __device__ FILO_NOINLINE double wp_eval_counter(int n, const WpCtrChunk* K, cons
   return NaNv;
 }
 
+// NaN results are counted per window (rare: kept out of line so that the read-modify-write is not predicated into the common path)
+#ifdef FILO_CUSIM
+inline void wp_bump_u16(uint16_t* p) { *p = (uint16_t)(*p + 1); }
+#else
+static __device__ __noinline__ void wp_bump_u16(uint16_t* p) { *p = (uint16_t)(*p + 1); }
+#endif
 // one clamped single-chunk window (kept out of line: one or two warp iterations per series go through it)
 template <int FN>
-__device__ FILO_NOINLINE double wp_clamped_window(const double* V, const WpCtrChunk& ch, const TileDrops& D, bool drp, int kk, int64_t wEnd, int64_t cws, int64_t qstep,
+__device__ __forceinline__ double wp_clamped_window(const double* V, const WpCtrChunk& ch, const TileDrops& D, bool drp, int kk, int64_t wEnd, int64_t cws, int64_t qstep,
                                                    double fdiv, double frcp, const TileCtrTab* tab) {
   int r1 = ch.s0 + kk; if (r1 < 0) r1 = 0;
   int r2 = ch.e0 + kk; if (r2 > ch.nrows - 1) r2 = ch.nrows - 1;
@@ -289,13 +295,13 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
       __syncwarp();
       // ---------------------------------------------------------------------------------------------- windows
       double* gout = AGG ? nullptr : out + (size_t)s * q.T;
+      const bool agg_add = agg_op == AGG_SUM || agg_op == AGG_AVG;
       auto emit = [&](int k, double v) {
         if (!AGG) { wp_store_result(gout + k, v); return; }
         if (v == v) {                                        // RowAggregators skip NaN (SumRowAggregator.scala:22-29 ...)
-          double a = ACC[k];
-          if (agg_op == AGG_MIN) a = v < a ? v : a; else if (agg_op == AGG_MAX) a = v > a ? v : a; else if (agg_op != AGG_COUNT) a += v;
-          ACC[k] = a;
-        } else NBAD[k] = (uint16_t)(NBAD[k] + 1);
+          if (agg_add) ACC[k] += v;
+          else if (agg_op != AGG_COUNT) { const double a = ACC[k]; if (agg_op == AGG_MIN ? v < a : v > a) ACC[k] = v; }
+        } else wp_bump_u16(NBAD + k);
       };
       for (int ci = 0; ci < n; ++ci) {
         const WpCtrChunk& ch = KC[ci];
@@ -321,10 +327,10 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
           const double delta = v2 - v1;
           double ratio = kc.ratio0;
           if (FN != FN_DELTA && delta > 0 && v1 >= 0 && !(v1 > delta * kc.skipC)) {      // zero-point clamp may apply (:84-90)
-            const double dz = kc.sI * (v1 / delta);
+            const double dz = kc.sI * ddiv_rare(v1, delta);
             const double dts = dz < kc.dTS ? dz : kc.dTS;
             const double eTI = (kc.sI + (dts < kc.thr ? dts : kc.half)) + kc.endpart;
-            ratio = eTI / kc.sI;
+            ratio = ddiv_rare(eTI, kc.sI);
           }
           const double scaled = delta * ratio;
           emit(kk, FN == FN_RATE ? __dmul_rn(div_invariant(scaled, fdiv, frcp), 1000.0) : scaled);
