@@ -75,6 +75,32 @@ def query_range(workload):
     return T0_MS, STEP, T0_MS + 7200000, window
 
 
+def host_cores():
+    """Threads this process may actually run on: scheduler affinity capped by the cgroup CPU quota (os.cpu_count() ignores both, and a
+    128-thread run inside an 8-CPU lease is how the round-1 CPU baseline moved 5x between boxes)."""
+    visible = os.cpu_count() or 1
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = visible
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:                      # cgroup v2: "<quota|max> <period>"
+            q, per = f.read().split()[:2]
+            if q != "max":
+                quota = float(q) / float(per)
+    except Exception:
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f: q = float(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f: per = float(f.read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            quota = None
+    usable = aff if quota is None else max(1, min(aff, int(quota + 0.999)))
+    return {"cores_visible": visible, "cores_affinity": aff, "cpu_quota": quota, "cores_usable": usable}
+
+
 class ClockSampler:
     """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  NVML polled from a thread of this process (the
     library is initialised before the warm-up, so nothing starts up inside the timed region -- an `nvidia-smi` child launched right
@@ -249,6 +275,8 @@ def measured_traffic(workload, S):
             rec = json.load(f).get(workload)
         if rec and int(rec["series"]) == int(S):
             return float(rec["dram_bytes_per_launch"])
+        if rec and "dram_bytes_per_series" in rec:      # captured at another series count: every series is read and written once, traffic scales with S
+            return float(rec["dram_bytes_per_series"]) * int(S)
     except (OSError, ValueError, KeyError):
         pass
     return None
@@ -290,7 +318,8 @@ def run_reference(args, rank, world):
         return
     synth, fn_name, aggr_name, n_groups, desc = WORKLOADS[args.workload]
     S = min(args.series, args.cpu_series)
-    cores = os.cpu_count() or 1
+    hc = host_cores()
+    cores = hc["cores_usable"]
     st = o.Store()
     st.add_synth(S, ROWS, ROWS_PER_CHUNK, T0_MS, INTERVAL, seed=42, threads=cores, **synth)   # same rows/bytes as the GPU generator
     start, step, end, window = query_range(args.workload)
@@ -314,8 +343,8 @@ def run_reference(args, rank, world):
             "config": {"workload": desc.format(S=args.series) + " (per GPU; series sharded by id across GPUs)", "series_per_gpu": args.series, "rows": ROWS,
                        "windows": int(o.num_windows(start, step, end)), "window_ms": window, "step_ms": step,
                        "sample": "%d of %d series per step" % (S, args.series)},
-            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": "%d series (%.1f%% of the workload) per step, all %d host threads, oracle C++ restatement of ChunkedWindowIteratorD" % (S, 100.0 * S / args.series, cores)},
+            "cpu_baseline": dict({"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": "%d series (%.1f%% of the workload) per step, %d host threads (= usable cores), oracle C++ restatement of ChunkedWindowIteratorD" % (S, 100.0 * S / args.series, cores)}, **hc),
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -519,7 +548,7 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "scan_tile_kernel (CTA-tile scan; + v2 fallback pass" + ("" if aggr == capi.AGG_NONE else " + merge_partials") + ")",
+                         "traffic": traffic, "kernel": "scan_wp_*_kernel (warp-pipeline scan, scan_wp.cuh / scan_wp_ctr.cuh; + v2 fallback pass over declined series" + ("" if aggr == capi.AGG_NONE else " + merge_partials") + ")",
                          "kernel_ms": kern_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src}}
 
     # ---- end-to-end through the C-ABI with host buffers (load + query + result read-back every step)
@@ -529,7 +558,7 @@ def main():
         # default: all series on one GPU; with several ranks on one host each rank takes a 1/world share (the host gather, the pinned
         # result buffers and PCIe are shared by the ranks of a box)
         Se = (S if world == 1 else max(1_000_000, S // world)) if args.e2e_series < 0 else min(S, args.e2e_series)
-        os.environ.setdefault("FILO_HOST_THREADS", str(max(4, min(64, (os.cpu_count() or 8) // world))))   # host gather threads per rank
+        os.environ.setdefault("FILO_HOST_THREADS", str(max(4, min(64, host_cores()["cores_usable"] // world))))   # host gather threads per rank
         arena, rec_off = tab.read_arena(0, Se)
         nch, addrs, keep = host_chunk_infos(arena, rec_off, Se)
         n_out = Se * T if aggr == capi.AGG_NONE else n_groups * T
@@ -578,7 +607,8 @@ def main():
         Sc = min(S, args.cpu_series)
         arena, rec_off = tab.read_arena(0, Sc)
         ost = o.Store(); ost.add_from_arena(arena, rec_off, Sc)
-        cores = os.cpu_count() or 1
+        hc = host_cores()
+        cores = hc["cores_usable"]
         cumulative = bool(synth.get("schema_flags", 0) & 1)
         gids = None
         if n_groups:
@@ -586,12 +616,39 @@ def main():
         dts = []
         for _ in range(3):        # first run also pays page faults / allocator warm-up; report the best
             t0 = time.perf_counter()
-            ost.query(getattr(o, fn_name), start, step, end, window, cumulative=cumulative, aggr=getattr(o, aggr_name), group_ids=gids,
-                      n_groups=max(n_groups, 1), threads=cores, reuse_out=True)
+            exp = ost.query(getattr(o, fn_name), start, step, end, window, cumulative=cumulative, aggr=getattr(o, aggr_name), group_ids=gids,
+                            n_groups=max(n_groups, 1), threads=cores, reuse_out=True)
             dts.append(time.perf_counter() - t0)
         dt = min(dts)
-        line["cpu_baseline"] = {"value": Sc * ROWS / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-                                "sample": "%d of %d series (%.1f s wall on %d threads); C++ restatement of ChunkedWindowIteratorD + range functions, not a JVM number" % (Sc, S, dt, cores)}
+        line["cpu_baseline"] = dict({"value": Sc * ROWS / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+                                     "sample": "%d of %d series (%.1f s wall on %d threads = usable cores); C++ restatement of ChunkedWindowIteratorD + range functions, not a JVM number" % (Sc, S, dt, cores)}, **hc)
+        # ---- parity at bench scale (outside every timed region): the oracle's answer for these Sc series against the CUDA path on a table
+        # of the same Sc series (same generator, same seed): bit-exact per series, 1e-9 relative for across-series aggregates
+        try:
+            tab2 = ctx.synth_table(Sc, ROWS, ROWS_PER_CHUNK, T0_MS, INTERVAL, n_groups=n_groups, seed=42, series_id_base=0, **synth)
+            got = ctx.query(tab2, fn, start, step, end, window, aggr=aggr)
+            if isinstance(got, tuple): got = got[0]
+            if isinstance(exp, tuple): exp = exp[0]
+            got = np.asarray(got).reshape(-1); expf = np.asarray(exp).reshape(-1)
+            if aggr == capi.AGG_NONE:
+                bad = 0
+                CH = 1 << 26
+                for i0 in range(0, got.size, CH):
+                    a = got[i0:i0 + CH]; b = expf[i0:i0 + CH]
+                    if not np.array_equal(a.view(np.uint64), b.view(np.uint64)):
+                        bad += int((~((a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b)))).sum())
+                line["parity_check"] = {"series": int(Sc), "windows": int(T), "values": int(got.size), "bit_exact": bad == 0, "mismatches": bad,
+                                        "against": "oracle (C++ restatement of the reference path) on the same chunk bytes"}
+            else:
+                nanmis = int((np.isnan(got) != np.isnan(expf)).sum())
+                m = ~np.isnan(expf) & ~np.isnan(got)
+                rel = float(np.max(np.abs(got[m] - expf[m]) / np.maximum(np.abs(expf[m]), 1e-300))) if m.any() else 0.0
+                line["parity_check"] = {"series": int(Sc), "groups": int(n_groups), "windows": int(T), "max_rel_err": rel, "tolerance": 1e-9,
+                                        "within_tolerance": bool(rel <= 1e-9 and nanmis == 0), "nan_mismatches": nanmis,
+                                        "against": "oracle (C++ restatement of the reference path) on the same chunk bytes"}
+            tab2.free()
+        except Exception as e:      # the check must not take the measurement down; its failure is reported
+            line["parity_check"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     tab.free(); ctx.close()
