@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-staged", action="store_true", help="e2e leg: stage inputs through pinned slabs on the host instead of the registered-memory gather")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 sub-record (sum(rate) by(cluster) with the NCCL all-reduce) of the default C2 run")
     return ap.parse_args()
 
 
@@ -350,6 +351,72 @@ def run_reference(args, rank, world):
 
 
 
+def run_c5_sub(args, ctx, rank, world, dist, stream, peak):
+    """BASELINE C5 beside the headline workload: sum(rate(counter[5m])) by (cluster), 100 clusters, 128 shards over the GPUs of the box,
+    every rank folds its shards into [G x T] partials (FILO_Q_PARTIAL), ONE NCCL all-reduce merges them (the plan's only fan-in,
+    ReduceAggregateExec), filo_present_partials finishes.  The collective is inside the timed region.  Shards -> GPUs by
+    shard.shards_of_rank (ShardMapper.scala:93-102,122-130); a shard is a block of S * N / 128 consecutive series ids."""
+    import torch
+    import filodb_b200.capi as capi
+    from filodb_b200 import shard
+    synth, fn_name, aggr_name, G, desc = WORKLOADS["c5"]
+    fn, aggr = getattr(capi, fn_name), getattr(capi, aggr_name)
+    S = args.series
+    NSH = 128
+    my_shards = shard.shards_of_rank(NSH, rank, world)
+    tab = ctx.synth_table(S, ROWS, ROWS_PER_CHUNK, T0_MS, INTERVAL, n_groups=G, seed=42, series_id_base=rank * S, **synth)
+    torch.cuda.synchronize()
+    ti = tab.info()
+    start, step, end, window = query_range("c5")
+    T = capi.num_windows(start, step, end)
+    out = torch.empty(G * T, dtype=torch.float64, device="cuda")
+    aux = torch.empty(G * T, dtype=torch.int64, device="cuda")
+    final = torch.empty(G * T, dtype=torch.float64, device="cuda")
+    flags = capi.Q_PARTIAL if world > 1 else 0
+
+    def step_fn():
+        ctx.query_device(tab, fn, start, step, end, window, out.data_ptr(), aux.data_ptr(), aggr=aggr, flags=flags, stream=stream, want_stats=False)
+        if world > 1:
+            shard.merge_partials(out, aux, aggr, dist)
+            ctx.present_partials(aggr, G * T, out.data_ptr(), aux.data_ptr(), final.data_ptr(), stream=stream)
+    st = ctx.query_device(tab, fn, start, step, end, window, out.data_ptr(), aux.data_ptr(), aggr=aggr, flags=flags, stream=stream, want_stats=True)
+    assert st["samples_scanned"] == ti.n_samples, (st, ti.n_samples)
+    for _ in range(max(3, args.warmup)):
+        step_fn()
+    torch.cuda.synchronize()
+    kern_ns = [ctx.query_device(tab, fn, start, step, end, window, out.data_ptr(), aux.data_ptr(), aggr=aggr, flags=flags, stream=stream, want_stats=True)["kernel_ns"]
+               for _ in range(3)]
+    if dist: dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist: dist.barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    ms_per_rank = [ms]
+    if dist:
+        tl = [torch.zeros(1, device="cuda") for _ in range(world)]
+        dist.all_gather(tl, torch.tensor([ms], device="cuda", dtype=torch.float32))
+        ms_per_rank = [float(x.item()) for x in tl]
+        ms = max(ms_per_rank)
+    kern_ms = float(np.median(kern_ns)) / 1e6
+    alg_bytes = ti.algorithmic_bytes + S * 4 + G * T * 8
+    achieved = alg_bytes / (kern_ms / 1e3) / 1e9
+    rec = {"workload": desc + "; %d series per GPU, %d series in all; 128 shards, GPU g owns shards {s : s mod N == g} (shard.shards_of_rank)" % (S, S * world),
+           "value": ti.n_samples * world / (ms / 1e3), "unit": "samples/s", "n_gpus": world, "ms_per_step": ms, "ms_per_rank": [round(x, 3) for x in ms_per_rank],
+           "steps": args.steps, "scaling": "weak", "collective": "NCCL all-reduce of [G x T] sums and counts + filo_present_partials, inside the timed region" if world > 1 else "none (one GPU)",
+           "shards_of_rank0": my_shards if rank == 0 else None, "groups": G, "windows": T,
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "kernel_ms": kern_ms, "algorithmic_bytes": alg_bytes,
+                        "kernel": "scan_wp_ctr_kernel<rate, fused> + v2 fallback over declined items + merge_partials"}}
+    del out, aux, final
+    tab.free()
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_c4(args, rank, world, local_rank):
     """C4: histogram_quantile(0.99, sum(rate(h[5m]))) over SectDelta histogram series (20 custom buckets 2*3^i, +Inf:
     gateway/.../TestTimeseriesProducer.scala:229-235).  The chunks are produced by the oracle's restatement of the reference
@@ -528,8 +595,12 @@ def main():
     if dist: dist.barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
+    ms_per_rank = [ms]
     if dist:
-        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        tl = [torch.zeros(1, device="cuda") for _ in range(world)]
+        dist.all_gather(tl, torch.tensor([ms], device="cuda", dtype=torch.float32))
+        ms_per_rank = [float(x.item()) for x in tl]
+        ms = max(ms_per_rank)
     samples_step = ti.n_samples * world
     value = samples_step / (ms / 1e3)
     peak, peak_src = measured_peak()
@@ -546,6 +617,7 @@ def main():
                        "window_ms": window, "step_ms": step, "l2": "inputs (%.1f GB arena) far larger than the 126 MB L2; no flush needed" % (ti.arena_bytes / 1e9),
                        "table_gen_s": round(t_gen, 2), "arena_bytes": ti.arena_bytes},
             "gpu_launches": launches_per_step * args.steps,
+            "ms_per_rank": [round(x, 3) for x in ms_per_rank],
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "scan_wp_*_kernel (warp-pipeline scan, scan_wp.cuh / scan_wp_ctr.cuh; + v2 fallback pass over declined series" + ("" if aggr == capi.AGG_NONE else " + merge_partials") + ")",
@@ -554,6 +626,11 @@ def main():
     # ---- end-to-end through the C-ABI with host buffers (load + query + result read-back every step)
     del out
     torch.cuda.empty_cache()
+    if args.workload == "c2" and not args.no_c5:
+        try:
+            line["c5"] = run_c5_sub(args, ctx, rank, world, dist, stream, peak)
+        except Exception as e:
+            line["c5"] = {"error": repr(e)}
     if not args.no_e2e:
         # default: all series on one GPU; with several ranks on one host each rank takes a 1/world share (the host gather, the pinned
         # result buffers and PCIe are shared by the ranks of a box)
