@@ -40,6 +40,7 @@ struct filo_ctx {
     void* d_gch = nullptr; size_t d_gch_cap = 0;
     void* h_gs = nullptr; size_t h_gs_cap = 0;           // pinned: per-series gather headers
     void* d_gs = nullptr; size_t d_gs_cap = 0;
+    uint8_t* d_stage = nullptr; size_t d_stage_cap = 0;  // device copy of the host span that holds a batch's vectors (dense batches: one DMA instead of zero-copy reads)
     cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
   };
   std::mutex scan_mu;
@@ -127,7 +128,7 @@ void filo_ctx_destroy(filo_ctx* ctx) {
   for (auto& sl : ctx->scan) {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
     cudaFreeHost(sl.h_in); cudaFreeHost(sl.h_off); cudaFreeHost(sl.h_sink); cudaFree(sl.d_in); cudaFree(sl.d_off); cudaFree(sl.d_out);
-    cudaFreeHost(sl.h_gch); cudaFreeHost(sl.h_gs); cudaFree(sl.d_gch); cudaFree(sl.d_gs);
+    cudaFreeHost(sl.h_gch); cudaFreeHost(sl.h_gs); cudaFree(sl.d_gch); cudaFree(sl.d_gs); cudaFree(sl.d_stage);
     if (sl.done) cudaEventDestroy(sl.done);
     if (sl.stream) cudaStreamDestroy(sl.stream);
   }
@@ -838,8 +839,10 @@ __device__ __forceinline__ void copy_bytes_warp(uint8_t* dst, const uint8_t* src
   }
 }
 // warp per series: record header, chunk entries, vectors verbatim (same bytes fill_record writes on the host)
+// rebase: added to every source address (0: read the registered host memory directly; otherwise the span was copied to the device
+// and the sources are rebased into that copy)
 __global__ void __launch_bounds__(256) gather_records_kernel(const GatherSeries* __restrict__ gs, const GatherChunk* __restrict__ gc,
-                                                             const int64_t* __restrict__ rec_off, int64_t n, uint8_t* __restrict__ arena) {
+                                                             const int64_t* __restrict__ rec_off, int64_t n, uint8_t* __restrict__ arena, int64_t rebase) {
   const int lane = threadIdx.x & 31;
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = w; i < n; i += nw) {
@@ -854,8 +857,8 @@ __global__ void __launch_bounds__(256) gather_records_kernel(const GatherSeries*
         ChunkEntry ce; ce.start_time = G.start_time; ce.end_time = G.end_time; ce.num_rows = G.num_rows; ce.ts_off = ts_off; ce.val_off = val_off; ce.row_base = row_base;
         reinterpret_cast<ChunkEntry*>(rec + sizeof(RecordHeader))[c] = ce;
       }
-      copy_bytes_warp(rec + ts_off, reinterpret_cast<const uint8_t*>(G.ts_src), G.ts_bytes, lane);
-      copy_bytes_warp(rec + val_off, reinterpret_cast<const uint8_t*>(G.val_src), G.val_bytes, lane);
+      copy_bytes_warp(rec + ts_off, reinterpret_cast<const uint8_t*>(G.ts_src + (uint64_t)rebase), G.ts_bytes, lane);
+      copy_bytes_warp(rec + val_off, reinterpret_cast<const uint8_t*>(G.val_src + (uint64_t)rebase), G.val_bytes, lane);
       if (lane < (int)(ts_pad - G.ts_bytes)) rec[ts_off + G.ts_bytes + lane] = 0;
       if (lane < (int)(val_pad - G.val_bytes)) rec[val_off + G.val_bytes + lane] = 0;
       __syncwarp();
@@ -1018,7 +1021,9 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
       GatherSeries* gs = reinterpret_cast<GatherSeries*>(sl.h_gs); GatherChunk* gc = reinterpret_cast<GatherChunk*>(sl.h_gch);
       int64_t cb = 0;
       for (int64_t j = 0; j < nb; ++j) { const SeriesPlan& p = plan[(size_t)(B.s0 + j)]; gs[j] = GatherSeries{p.rec_bytes, p.n_chunks, p.n_rows, p.flags, cb}; cb += p.n_chunks; }
+      std::atomic<uint64_t> span_lo{~0ull}, span_hi{0};       // host span that holds the batch's vectors
       host_pool().run(nb, [&](int, int64_t b, int64_t e) {
+        uint64_t lo = ~0ull, hi = 0;
         for (int64_t j = b; j < e; ++j) {
           const int64_t i = B.s0 + j; GatherChunk* o = gc + gs[j].first_chunk;
           for (int32_t jj = 0; jj < n_chunks[i]; ++jj) {
@@ -1034,17 +1039,34 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
             g.num_rows = numRows; g.ts_bytes = tv.total; g.val_bytes = vv.total; g.val_len = vv.len;
             g.drop_patch = vv.drop_patch ? (vv.drop ? 1 : 2) : 0; g.pad = 0;
             *o++ = g;
+            lo = std::min(lo, std::min(g.ts_src, g.val_src));
+            hi = std::max(hi, std::max(g.ts_src + (uint64_t)tv.total, g.val_src + (uint64_t)vv.total));
           }
         }
+        uint64_t cur = span_lo.load(); while (lo < cur && !span_lo.compare_exchange_weak(cur, lo)) {}
+        cur = span_hi.load(); while (hi > cur && !span_hi.compare_exchange_weak(cur, hi)) {}
       });
       t_fill += ms_since(t_f0);
+      // dense batch (the vectors fill most of one host span, e.g. consecutive series of a block): ONE copy-engine transfer of the span
+      // at full PCIe rate, the gather then runs device to device; sparse batches keep the zero-copy reads of the registered memory
+      int64_t rebase = 0;
+      {
+        static const bool no_span = [] { const char* e = std::getenv("FILO_SCAN_SPAN"); return e && e[0] == '0'; }();
+        const uint64_t lo = span_lo.load() & ~(uint64_t)15, hi = span_hi.load();
+        if (!no_span && hi > lo && (hi - lo) <= (uint64_t)B.bytes + (uint64_t)B.bytes / 2 + (1u << 20) && in_ranges(reinterpret_cast<const uint8_t*>((uintptr_t)lo), (size_t)(hi - lo))) {
+          if (int32_t rcg = grow_device(ctx, sl.d_stage, sl.d_stage_cap, (size_t)(hi - lo) + 64)) return rcg;
+          ce = cudaMemcpyAsync(sl.d_stage, reinterpret_cast<const void*>((uintptr_t)lo), (size_t)(hi - lo), cudaMemcpyHostToDevice, sl.stream);
+          rebase = (int64_t)((uint64_t)(uintptr_t)sl.d_stage - lo);
+        }
+      }
+      if (ce == cudaSuccess)
       ce = cudaMemcpyAsync(sl.d_gs, sl.h_gs, (size_t)nb * sizeof(GatherSeries), cudaMemcpyHostToDevice, sl.stream);
       if (ce == cudaSuccess) ce = cudaMemcpyAsync(sl.d_gch, sl.h_gch, (size_t)B.chunks * sizeof(GatherChunk), cudaMemcpyHostToDevice, sl.stream);
       if (ce == cudaSuccess) ce = cudaMemcpyAsync(sl.d_off, sl.h_off, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, sl.stream);
       if (ce == cudaSuccess) {
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nb + 7) / 8, (int64_t)ctx->sm_count * 8));
         gather_records_kernel<<<grid, 256, 0, sl.stream>>>(reinterpret_cast<const GatherSeries*>(sl.d_gs), reinterpret_cast<const GatherChunk*>(sl.d_gch),
-                                                           sl.d_off, nb, sl.d_in);
+                                                           sl.d_off, nb, sl.d_in, rebase);
         ce = cudaGetLastError();
       }
       if (ce == cudaSuccess) ce = cudaMemsetAsync(sl.d_in + B.bytes, 0, 64, sl.stream);
