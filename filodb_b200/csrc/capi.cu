@@ -388,7 +388,21 @@ inline void fill_record(const LoadIn& in, int64_t i, const SeriesPlan& p, uint8_
   }
   if (off < p.rec_bytes) std::memset(rec + off, 0, p.rec_bytes - off);
 }
-// pass 1 over all series (pool); fills plan[] and the totals, returns 0 or the first error with its series
+// pass 1 over the series [s_begin, s_end) (pool); fills plan[] and the totals, returns 0 or the first error with its series
+inline int plan_range(const LoadIn& in, int64_t s_begin, int64_t s_end, std::vector<SeriesPlan>& plan, PlanTotals& tot, int64_t& err_series_out) {
+  HostPool& pool = host_pool();
+  std::vector<PlanTotals> part((size_t)pool.size());
+  std::atomic<int> err_code{0}; std::atomic<int64_t> err_series{-1};
+  pool.run(s_end - s_begin, [&](int w, int64_t b, int64_t e) {
+    for (int64_t i = s_begin + b; i < s_begin + e && !err_code.load(std::memory_order_relaxed); ++i) {
+      const int rc = plan_series(in, i, plan[(size_t)i], part[(size_t)w]);
+      if (rc) { int z = 0; if (err_code.compare_exchange_strong(z, rc)) err_series = i; return; }
+    }
+  });
+  for (auto& p : part) merge_totals(tot, p);
+  err_series_out = err_series.load();
+  return err_code.load();
+}
 inline int plan_all(const LoadIn& in, std::vector<SeriesPlan>& plan, PlanTotals& tot, int64_t& err_series_out) {
   HostPool& pool = host_pool();
   std::vector<PlanTotals> part((size_t)pool.size());
@@ -929,68 +943,24 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
   auto ms_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
   const auto t_begin = now();
   double t_fill = 0, t_retire = 0, t_enq = 0;
-  // ---- pass 1: validate + size (same rules as filo_load_series)
+  // The series are planned (validated + sized, same rules as filo_load_series) in chunks of PLAN_CHUNK series right before their batches
+  // are enqueued, so that the host walk of chunk k + 1 runs while the GPU still works on the batches of chunk k.
   std::vector<SeriesPlan> plan((size_t)n_series);
   const LoadIn in{n_series, n_chunks, addrs, chunk_base.data(), ts_col, val_col};
-  PlanTotals tot; int64_t err_series = -1;
-  if (const int err_code = plan_all(in, plan, tot, err_series)) {
-    const char* what = err_code == FILO_ERR_UNSUPPORTED ? "chunks of a series are not in increasing time order (unsupported on the device path)"
-                                                       : "CorruptVector: unknown or inconsistent BinaryVector wire format";
-    return fail(ctx, err_code, std::string(what) + " at series " + std::to_string(err_series));
-  }
-  if (ctx->cfg.max_data_per_shard_query > 0 && tot.alg > ctx->cfg.max_data_per_shard_query)
-    return fail(ctx, FILO_ERR_QUERY_LIMIT, "raw data bytes scanned exceeds max-data-per-shard-query");
-  if (tot.hist_def) return fail(ctx, FILO_ERR_UNSUPPORTED, "filo_scan_series: histogram columns go through filo_load_series + filo_query_hist");
-  const double t_plan = ms_since(t_begin);
-  // ---- batches: consecutive series, <= SLAB bytes of records and a bounded result block
+  const int64_t PLAN_CHUNK = 65536;
   const size_t SLAB = (size_t)192 << 20;
   const int64_t max_rows_out = std::max<int64_t>(1, (int64_t)(((size_t)256 << 20) / ((size_t)std::max(T, 1) * 8)));
   struct Batch { int64_t s0, s1; size_t bytes; int64_t chunks; };
-  std::vector<Batch> batches;
-  size_t max_bytes = 0; int64_t max_n = 0, max_chunks = 0;
-  for (int64_t s0 = 0; s0 < n_series;) {
-    int64_t s1 = s0; size_t bytes = 0; int64_t chunks = 0;
-    while (s1 < n_series && s1 - s0 < max_rows_out && (s1 == s0 || bytes + plan[(size_t)s1].rec_bytes <= SLAB)) { bytes += plan[(size_t)s1].rec_bytes; chunks += plan[(size_t)s1].n_chunks; ++s1; }
-    batches.push_back(Batch{s0, s1, bytes, chunks});
-    max_bytes = std::max(max_bytes, bytes); max_n = std::max(max_n, s1 - s0); max_chunks = std::max(max_chunks, chunks);
-    s0 = s1;
-  }
-  // zero-copy gather when every vector of the call lies in memory registered with filo_host_register (checked per series below)
   std::vector<filo_ctx::HostRange> ranges = ctx->ranges;
   auto in_ranges = [&](const uint8_t* p, size_t n) { for (auto& r : ranges) if ((uintptr_t)p >= r.base && (uintptr_t)p + n <= r.base + r.bytes) return true; return false; };
-  bool use_gather = !ranges.empty();
-  if (use_gather) {
-    std::atomic<bool> all_in{true};
-    host_pool().run(n_series, [&](int, int64_t b, int64_t e) {
-      for (int64_t i = b; i < e && all_in.load(std::memory_order_relaxed); ++i)
-        for (int32_t j = 0; j < n_chunks[i]; ++j) {
-          const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)addrs[chunk_base[(size_t)i] + j]);
-          if (rd32(info + 8) <= 0) continue;
-          VecInfo tv, vv;
-          classify_ts(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * ts_col)), tv);
-          classify_val(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * val_col)), vv);
-          if (!in_ranges(tv.p, (size_t)tv.total) || !in_ranges(vv.p, (size_t)vv.total)) { all_in = false; break; }
-        }
-    });
-    use_gather = all_in.load();
-  }
   const int NSLOT = 3;
   for (int i = 0; i < NSLOT; ++i) {
     filo_ctx::ScanSlot& sl = ctx->scan[i];
     if (!sl.stream) { CUDA_TRY(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)); CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)); }
     if (!sl.h_sink) CUDA_TRY(ctx, cudaHostAlloc(&sl.h_sink, sizeof(AsyncSink), cudaHostAllocDefault));
-    if (!use_gather) { if (int32_t rc = grow_pinned(ctx, sl.h_in, sl.h_in_cap, max_bytes + 64)) return rc; }
-    else {
-      if (int32_t rc = grow_pinned(ctx, sl.h_gch, sl.h_gch_cap, (size_t)(max_chunks + 1) * sizeof(GatherChunk))) return rc;
-      if (int32_t rc = grow_device(ctx, sl.d_gch, sl.d_gch_cap, (size_t)(max_chunks + 1) * sizeof(GatherChunk))) return rc;
-      if (int32_t rc = grow_pinned(ctx, sl.h_gs, sl.h_gs_cap, (size_t)(max_n + 1) * sizeof(GatherSeries))) return rc;
-      if (int32_t rc = grow_device(ctx, sl.d_gs, sl.d_gs_cap, (size_t)(max_n + 1) * sizeof(GatherSeries))) return rc;
-    }
-    if (int32_t rc = grow_pinned(ctx, sl.h_off, sl.h_off_cap, (size_t)(max_n + 1) * 8)) return rc;
-    if (int32_t rc = grow_device(ctx, sl.d_in, sl.d_in_cap, max_bytes + 64)) return rc;
-    if (int32_t rc = grow_device(ctx, sl.d_off, sl.d_off_cap, (size_t)(max_n + 1) * 8)) return rc;
-    if (int32_t rc = grow_device(ctx, sl.d_out, sl.d_out_cap, (size_t)max_n * (size_t)std::max(T, 1) * 8)) return rc;
   }
+  double t_plan = 0;
+  int64_t alg_total = 0; size_t n_batches = 0;
   // ---- pipeline: gather batch b (host pool) while the GPU copies/scans batch b-1 and returns batch b-2
   filo_stats acc{};
   struct InFlight { int64_t s0 = -1; } fl[3];
@@ -1005,13 +975,66 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
     if (k->herr[0]) return report_device_error(ctx, k->herr, base);
     return FILO_OK;
   };
-  for (size_t bi = 0; bi < batches.size() && rc == FILO_OK; ++bi) {
+  for (int64_t c0 = 0; c0 < n_series && rc == FILO_OK; c0 += PLAN_CHUNK) {
+    const int64_t c1 = std::min<int64_t>(n_series, c0 + PLAN_CHUNK);
+    const auto t_p0 = now();
+    PlanTotals tot; int64_t err_series = -1;
+    if (const int err_code = plan_range(in, c0, c1, plan, tot, err_series)) {
+      const char* what = err_code == FILO_ERR_UNSUPPORTED ? "chunks of a series are not in increasing time order (unsupported on the device path)"
+                                                         : "CorruptVector: unknown or inconsistent BinaryVector wire format";
+      rc = fail(ctx, err_code, std::string(what) + " at series " + std::to_string(err_series)); break;
+    }
+    alg_total += tot.alg;
+    if (ctx->cfg.max_data_per_shard_query > 0 && alg_total > ctx->cfg.max_data_per_shard_query) { rc = fail(ctx, FILO_ERR_QUERY_LIMIT, "raw data bytes scanned exceeds max-data-per-shard-query"); break; }
+    if (tot.hist_def) { rc = fail(ctx, FILO_ERR_UNSUPPORTED, "filo_scan_series: histogram columns go through filo_load_series + filo_query_hist"); break; }
+    // zero-copy gather when every vector of the chunk lies in memory registered with filo_host_register
+    bool use_gather = !ranges.empty();
+    if (use_gather) {
+      std::atomic<bool> all_in{true};
+      host_pool().run(c1 - c0, [&](int, int64_t b, int64_t e) {
+        for (int64_t i = c0 + b; i < c0 + e && all_in.load(std::memory_order_relaxed); ++i)
+          for (int32_t j = 0; j < n_chunks[i]; ++j) {
+            const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)addrs[chunk_base[(size_t)i] + j]);
+            if (rd32(info + 8) <= 0) continue;
+            VecInfo tv, vv;
+            classify_ts(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * ts_col)), tv);
+            classify_val(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * val_col)), vv);
+            if (!in_ranges(tv.p, (size_t)tv.total) || !in_ranges(vv.p, (size_t)vv.total)) { all_in = false; break; }
+          }
+      });
+      use_gather = all_in.load();
+    }
+    // batches of the chunk: consecutive series, <= SLAB bytes of records and a bounded result block
+    std::vector<Batch> batches;
+    for (int64_t s0 = c0; s0 < c1;) {
+      int64_t s1 = s0; size_t bytes = 0; int64_t chunks = 0;
+      while (s1 < c1 && s1 - s0 < max_rows_out && (s1 == s0 || bytes + plan[(size_t)s1].rec_bytes <= SLAB)) { bytes += plan[(size_t)s1].rec_bytes; chunks += plan[(size_t)s1].n_chunks; ++s1; }
+      batches.push_back(Batch{s0, s1, bytes, chunks});
+      s0 = s1;
+    }
+    t_plan += ms_since(t_p0);
+  for (size_t bi = 0; bi < batches.size() && rc == FILO_OK; ++bi, ++n_batches) {
     const Batch& B = batches[bi];
-    const int si = (int)(bi % NSLOT);
+    const int si = (int)(n_batches % NSLOT);
     filo_ctx::ScanSlot& sl = ctx->scan[si];
     { const auto t0 = now(); rc = retire(si); t_retire += ms_since(t0); }
     if (rc != FILO_OK) break;
     const int64_t nb = B.s1 - B.s0;
+    {   // the slot is idle: its buffers may grow to this batch's needs
+      int32_t rg = FILO_OK;
+      if (!use_gather) rg = grow_pinned(ctx, sl.h_in, sl.h_in_cap, B.bytes + 64);
+      else {
+        rg = grow_pinned(ctx, sl.h_gch, sl.h_gch_cap, (size_t)(B.chunks + 1) * sizeof(GatherChunk));
+        if (!rg) rg = grow_device(ctx, sl.d_gch, sl.d_gch_cap, (size_t)(B.chunks + 1) * sizeof(GatherChunk));
+        if (!rg) rg = grow_pinned(ctx, sl.h_gs, sl.h_gs_cap, (size_t)(nb + 1) * sizeof(GatherSeries));
+        if (!rg) rg = grow_device(ctx, sl.d_gs, sl.d_gs_cap, (size_t)(nb + 1) * sizeof(GatherSeries));
+      }
+      if (!rg) rg = grow_pinned(ctx, sl.h_off, sl.h_off_cap, (size_t)(nb + 1) * 8);
+      if (!rg) rg = grow_device(ctx, sl.d_in, sl.d_in_cap, B.bytes + 64);
+      if (!rg) rg = grow_device(ctx, sl.d_off, sl.d_off_cap, (size_t)(nb + 1) * 8);
+      if (!rg) rg = grow_device(ctx, sl.d_out, sl.d_out_cap, (size_t)nb * (size_t)std::max(T, 1) * 8);
+      if (rg) { rc = rg; break; }
+    }
     const auto t_f0 = now();
     sl.h_off[0] = 0;
     for (int64_t j = 0; j < nb; ++j) sl.h_off[j + 1] = sl.h_off[j] + plan[(size_t)(B.s0 + j)].rec_bytes;
@@ -1095,10 +1118,11 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
     t_enq += ms_since(t_e0);
     acc.h2d_bytes += (int64_t)B.bytes + (nb + 1) * 8 + (use_gather ? (int64_t)(nb * sizeof(GatherSeries) + B.chunks * sizeof(GatherChunk)) : 0); acc.d2h_bytes += nb * (int64_t)T * 8;
   }
+  }
   for (int i = 0; i < NSLOT; ++i) { const int32_t r2 = retire(i); if (rc == FILO_OK) rc = r2; }
   if (rc != FILO_OK) { for (int i = 0; i < NSLOT; ++i) if (ctx->scan[i].stream) cudaStreamSynchronize(ctx->scan[i].stream); return rc; }
   if (timing) fprintf(stderr, "[filo] scan_series: %lld series, %zu batches, total %.1f ms: plan %.1f, fill %.1f, enqueue %.1f, slot waits %.1f\n",
-                      (long long)n_series, batches.size(), ms_since(t_begin), t_plan, t_fill, t_enq, t_retire);
+                      (long long)n_series, n_batches, ms_since(t_begin), t_plan, t_fill, t_enq, t_retire);
   if (stats) *stats = acc;
   return FILO_OK;
 }
