@@ -245,7 +245,50 @@ struct LongReader {
     }
     return 0;
   }
+  // changes(): number of value changes in [start, end] and the last value seen.  Every reader has its own treatment of `prev`
+  // (the last value of the previous chunk) -- kept as they are in the reference.
+  std::pair<int64_t, int64_t> changes(Ptr v, int start, int end, int64_t prev, bool ignorePrev = false) const {
+    if (!(start >= 0 && end < length(v))) throw std::invalid_argument("long changes out of bounds");
+    switch (kind) {
+      case DDV: {                                                               // DeltaDeltaVector.scala:212-227
+        int64_t prevVector = prev, ch = 0;
+        for (int i = start; i <= end; ++i) {
+          int64_t cur = apply(v, i);
+          if (i == start && ignorePrev) prevVector = cur;
+          if (prevVector != cur) ch += 1;
+          prevVector = cur;
+        }
+        return {ch, prevVector};
+      }
+      case DDV_CONST: {                                                         // :280-288
+        int64_t firstValue = apply(v, start), lastValue = apply(v, end);
+        int64_t ch = (!ignorePrev && prev != firstValue) ? 1 : 0;
+        if (getInt(v + 20) == 0) return {ch, lastValue};
+        return {(int64_t)(end - start) + ch, lastValue};
+      }
+      case MASKED: { Ptr s = subvect(v); return of(s).changes(s, start, end, prev); }   // LongBinaryVector.scala:290-292 (ignorePrev not forwarded)
+      case RAW64: {                                                             // :248-265: the first element always re-seeds prev
+        int64_t prevVector = prev, ch = 0;
+        for (int i = start; i <= end; ++i) {
+          int64_t cur = getLong(v + 8 + (int64_t)i * 8);
+          if (i == start) prevVector = cur;
+          if (prevVector != cur) ch += 1;
+          prevVector = cur;
+        }
+        return {ch, prevVector};
+      }
+    }
+    return {0, prev};
+  }
 };
+
+// JVM d2l: NaN -> 0, saturating
+inline int64_t d2l(double d) {
+  if (d != d) return 0;
+  if (d >= 9223372036854775807.0) return INT64_MAX;
+  if (d <= -9223372036854775808.0) return INT64_MIN;
+  return (int64_t)d;
+}
 
 // =====================================================================================
 // NibblePack  (NibblePack.scala)
@@ -556,6 +599,28 @@ struct DoubleReader {
       }
     }
     return 0;
+  }
+  // DoubleVectorDataReader64.changes :283-303; masked :414-416; DoubleLongWrapDataReader.changes :559-566
+  std::pair<double, double> changes(int start, int end, double prev) const {
+    switch (kind) {
+      case LONGWRAP: {
+        bool ignorePrev = std::isnan(prev);
+        auto c = LongReader::of(vect).changes(vect, start, end, d2l(prev), ignorePrev);
+        return {(double)c.first, (double)c.second};
+      }
+      case MASKED: { Ptr s = vect + getInt(vect + 8); return DoubleReader::of(s).changes(start, end, prev); }
+      case RAW64: case XOR: {
+        if (!(start >= 0 && end < length())) throw std::invalid_argument("double changes out of bounds");
+        double ch = 0, prevVector = prev;
+        for (int r = start; r <= end; ++r) {
+          double nextDbl = apply(r);
+          if (!std::isnan(nextDbl) && prevVector != nextDbl && !std::isnan(prevVector)) ch += 1;
+          prevVector = nextDbl;
+        }
+        return {ch, prevVector};
+      }
+    }
+    return {0, prev};
   }
   // ---- counter-correction API
   // detectDropAndCorrection, DoubleVector.scala:177-187 (same for Correcting wrapper: not overridden)

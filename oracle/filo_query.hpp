@@ -24,7 +24,24 @@ enum RangeFn : int32_t {
   FN_SUM_OVER_TIME = 4, FN_AVG_OVER_TIME = 5, FN_COUNT_OVER_TIME = 6,
   FN_MIN_OVER_TIME = 7, FN_MAX_OVER_TIME = 8,
   FN_TIMESTAMP = 9,
+  // the remaining chunked range functions of RangeFunction.doubleChunkedFunction / longChunkedFunction (RangeFunction.scala:319-375)
+  FN_STDDEV_OVER_TIME = 10, FN_STDVAR_OVER_TIME = 11, FN_CHANGES = 12,
+  FN_QUANTILE_OVER_TIME = 13,     // param0 = q
+  FN_ZSCORE = 14,
+  FN_HOLT_WINTERS = 15,           // param0 = sf, param1 = tf
+  FN_PREDICT_LINEAR = 16,         // param0 = duration (s)
+  FN_MAD_OVER_TIME = 17,          // MedianAbsoluteDeviationOverTime
+  FN_PRESENT_OVER_TIME = 18,
 };
+// which functions RangeFunction.longChunkedFunction (RangeFunction.scala:319-339) has a chunked implementation for
+inline bool longColumnSupports(int fn) {
+  switch (fn) {
+    case FN_LAST: case FN_COUNT_OVER_TIME: case FN_SUM_OVER_TIME: case FN_AVG_OVER_TIME: case FN_MIN_OVER_TIME: case FN_MAX_OVER_TIME:
+    case FN_STDDEV_OVER_TIME: case FN_STDVAR_OVER_TIME: case FN_CHANGES: case FN_QUANTILE_OVER_TIME: case FN_PREDICT_LINEAR:
+    case FN_MAD_OVER_TIME: return true;
+    default: return false;
+  }
+}
 enum AggrOp : int32_t { AGG_NONE = 0, AGG_SUM = 1, AGG_AVG = 2, AGG_MIN = 3, AGG_MAX = 4, AGG_COUNT = 5, AGG_TOPK = 6, AGG_BOTTOMK = 7 };
 
 // QueryUtils.scala:109-123
@@ -60,6 +77,7 @@ struct InfoReader {
   Ptr tsVec = nullptr; Ptr valVec = nullptr;
   LongReader tsReader{LongReader::RAW64};
   DoubleReader valReader;
+  LongReader valLong{LongReader::RAW64};   // value reader of a Long column (valueReader.asLongReader)
   int32_t numRows() const { return csi::numRows(info); }
   int64_t startTime() const { return csi::startTime(info); }
   int64_t endTime() const { return csi::endTime(info); }
@@ -69,6 +87,7 @@ struct InfoReader {
 struct Series {
   std::vector<Ptr> infos;
   int tsCol = 0, valCol = 1;
+  bool longCol = false;          // the value column is a LongColumn (RangeFunction.scala:300-304 picks the L variants)
 };
 
 struct QueryConfig { bool inclusiveRange = true; };   // filodb.query.inclusive-range, filodb-defaults.conf:590
@@ -107,7 +126,8 @@ struct WindowedChunkIterator {
         r->tsVec = csi::vectorPtr(nextInfo, rv.tsCol);
         r->tsReader = LongReader::of(r->tsVec);
         r->valVec = csi::vectorPtr(nextInfo, rv.valCol);
-        r->valReader = DoubleReader::of(r->valVec);
+        if (rv.longCol) r->valLong = LongReader::of(r->valVec);
+        else r->valReader = DoubleReader::of(r->valVec);
         windowInfos.push_back(r);
         lastEndTime = std::max(r->endTime(), lastEndTime);
       }
@@ -118,21 +138,56 @@ struct WindowedChunkIterator {
 };
 
 // ---- chunked range functions (state machine per window)
+// java.util.Arrays.sort(double[]) order: Double.compare (-0.0 < 0.0, NaN last)
+inline bool javaDoubleLess(double a, double b) {
+  if (a < b) return true;
+  if (a > b) return false;
+  if (a == b) { if (a != 0.0) return false; return std::signbit(a) && !std::signbit(b); }
+  return !std::isnan(a) && std::isnan(b);      // at least one NaN
+}
+// QuantileOverTimeFunction.calculateRank, AggrOverTimeFunctions.scala:399-407
+inline void calculateRank(double q, int counter, double& weight, int& upperIndex, int& lowerIndex) {
+  double rank = q * (double)(counter - 1);
+  double lower = std::max(0.0, std::floor(rank));
+  double upper = std::min((double)(counter - 1), lower + 1);
+  weight = rank - std::floor(rank);
+  upperIndex = (int)upper; lowerIndex = (int)lower;
+}
+
 struct ChunkedFn {
   RangeFn fn; bool cumulative; bool inclusiveRange;
+  bool longCol = false;                 // value column is a LongColumn: the *L function variants
+  double p0 = 0, p1 = 0;                // static function arguments (funcParams: Seq[StaticFuncArgs])
   // SumOverTimeChunkedFunctionD (AggrOverTimeFunctions.scala:553-572) / Avg (:992-1015) / Count (:940-958) / Min,Max (:40-97)
   double sum = NaN; int32_t count = 0; double countD = NaN; double mn = NaN, mx = NaN;
+  int64_t mnL = INT64_MAX, mxL = INT64_MIN;    // Min/MaxOverTimeChunkedFunctionL :60-116
   // LastSampleChunkedFunctionD (RangeFunction.scala:595-627, 684-693)
   int64_t lastTs = -1; double lastVal = NaN;
   // ChunkedRateFunctionBase (RateFunctions.scala:230-285)
   int32_t numSamples = 0; int64_t lowestTime = INT64_MAX; double lowestValue = NaN; int64_t highestTime = 0; double highestValue = NaN;
   DoubleCorrection correctionMeta;      // CounterChunkedRangeFunction (RangeFunction.scala:131-136)
   double tsVal = NaN;                   // TimestampChunkedFunction (RangeFunction.scala:705-724)
+  // VarOverTimeChunkedFunctionD/L (:1082-1183), ZScoreChunkedFunctionD (:1592-1604): lastSample is NOT cleared by reset()
+  double squaredSum = NaN, lastSample = NaN;
+  // ChangesChunkedFunction (:1185-1225)
+  double changes = NaN, prev = NaN;
+  // Quantile / MAD (:1227-1359)
+  double quantileResult = NaN; std::vector<double> values;
+  // HoltWintersChunkedFunctionD (:1361-1453)
+  double b0 = NaN, s0 = NaN, nextvalue = NaN, smoothedResult = NaN;
+  // PredictLinearChunkedFunction (:1496-1590)
+  double sumX = NaN, sumY = NaN, sumXY = NaN, sumX2 = NaN; int32_t counter = 0;
 
   void reset() {
     sum = NaN; count = 0; countD = NaN; mn = NaN; mx = NaN; lastTs = -1; lastVal = NaN;
     numSamples = 0; lowestTime = INT64_MAX; lowestValue = NaN; highestTime = 0; highestValue = NaN;
     correctionMeta = DoubleCorrection{}; tsVal = NaN;
+    mnL = INT64_MAX; mxL = INT64_MIN;
+    squaredSum = NaN;
+    if (longCol && (fn == FN_STDDEV_OVER_TIME || fn == FN_STDVAR_OVER_TIME)) { sum = 0; squaredSum = 0; }    // VarOverTimeChunkedFunctionL.reset :1147
+    changes = NaN; prev = NaN; quantileResult = NaN; values.clear();
+    b0 = NaN; s0 = NaN; nextvalue = NaN; smoothedResult = NaN;
+    sumX = NaN; sumY = NaN; sumXY = NaN; sumX2 = NaN; counter = 0;
   }
   bool isCounterPath() const { return (fn == FN_RATE || fn == FN_INCREASE) ? cumulative : (fn == FN_DELTA); }
 
@@ -141,19 +196,124 @@ struct ChunkedFn {
     if (!std::isnan(chunkSum) && std::isnan(sum)) sum = 0;
     sum += chunkSum;
   }
+  // ---- Long-column variants (ChunkedLongRangeFunction, RangeFunction.scala:224-242)
+  void addTimeLongChunks(InfoReader& ir, int s, int e) {
+    const LongReader& lr = ir.valLong; Ptr v = ir.valVec;
+    switch (fn) {
+      case FN_SUM_OVER_TIME: if (std::isnan(sum)) sum = 0; sum += lr.sum(v, s, e); break;                  // :574-585
+      case FN_AVG_OVER_TIME: sum += lr.sum(v, s, e); count += (e - s + 1); break;                          // :1019-1028 (sum starts as NaN and stays NaN)
+      case FN_COUNT_OVER_TIME: count += (e - s + 1); break;                                                // CountOverTimeChunkedFunction :924-938
+      case FN_MIN_OVER_TIME: for (int r = s; r <= e; ++r) mnL = std::min(mnL, lr.apply(v, r)); break;      // :60-77
+      case FN_MAX_OVER_TIME: for (int r = s; r <= e; ++r) mxL = std::max(mxL, lr.apply(v, r)); break;      // :99-116
+      case FN_STDDEV_OVER_TIME: case FN_STDVAR_OVER_TIME: {                                                // :1144-1167
+        double _sum = 0, _sqSum = 0;
+        for (int r = s; r <= e; ++r) { double nextValue = (double)lr.apply(v, r); _sum += nextValue; _sqSum += nextValue * nextValue; }
+        count += (e - s + 1); sum += _sum; squaredSum += _sqSum;
+        break;
+      }
+      case FN_CHANGES: {                                                                                   // :1211-1225
+        if (std::isnan(changes)) changes = 0;
+        auto c = lr.changes(v, s, e, d2l(prev));
+        changes += (double)c.first; prev = (double)c.second;
+        break;
+      }
+      case FN_QUANTILE_OVER_TIME:                                                                          // :1322-1344
+        if (p0 < 0) quantileResult = -std::numeric_limits<double>::infinity();
+        else if (p0 > 1) quantileResult = std::numeric_limits<double>::infinity();
+        else for (int r = s; r <= e; ++r) values.push_back((double)lr.apply(v, r));
+        break;
+      case FN_MAD_OVER_TIME: for (int r = s; r <= e; ++r) values.push_back((double)lr.apply(v, r)); break; // :1346-1359
+      default: break;
+    }
+  }
+  void addVar(DoubleReader& r, int s, int e) {           // VarOverTimeChunkedFunctionD.addTimeDoubleChunks :1087-1115
+    double chunkSum = NaN, chunkSquaredSum = NaN; int chunkCount = 0;
+    for (int elemNo = s; elemNo <= e; ++elemNo) {
+      double nextValue = r.apply(elemNo);
+      if (!std::isnan(nextValue)) {
+        if (std::isnan(chunkSum)) chunkSum = 0;
+        if (std::isnan(chunkSquaredSum)) chunkSquaredSum = 0;
+        if (elemNo == e) lastSample = nextValue;
+        chunkSum += nextValue;
+        chunkSquaredSum += nextValue * nextValue;
+        chunkCount += 1;
+      }
+    }
+    if (!std::isnan(chunkSum) && std::isnan(sum)) sum = 0;
+    sum += chunkSum;
+    if (!std::isnan(chunkSquaredSum) && std::isnan(squaredSum)) squaredSum = 0;
+    squaredSum += chunkSquaredSum;
+    count += chunkCount;
+  }
+  // HoltWintersChunkedFunctionD.addTimeDoubleChunks :1413-1452.  The reference reads its value iterator one element past
+  // endRowNum on every chunk and, on a continuation chunk, drops that chunk's first row in favour of the stale over-read
+  // (undefined memory past the previous vector).  That is not reproducible; restated here with the evident intent: every
+  // row of the window is consumed once, in order.  Single-chunk windows (all of the reference's tests) are literal.
+  void addHoltWinters(DoubleReader& r, int s, int e) {
+    const double sf = p0, tf = p1;
+    int pos = s;                                           // iterator position
+    auto getNextValue = [&](int startRowNum, double& res) -> int {     // :1399-1411
+      res = NaN; int currRowNum = startRowNum;
+      while (currRowNum <= e && std::isnan(res)) { double nv = r.apply(pos++); if (!std::isnan(nv)) res = nv; currRowNum += 1; }
+      return currRowNum;
+    };
+    int rowNum = s;
+    if (std::isnan(s0) && std::isnan(b0)) {
+      double _s0, _b0; int firstrow = getNextValue(s, _s0); int currRow = getNextValue(firstrow, _b0);
+      nextvalue = _b0; b0 = _b0 - _s0; rowNum = currRow - 1; s0 = _s0;
+    } else if (std::isnan(b0)) {
+      double _b0; int currRow = getNextValue(s, _b0);
+      nextvalue = _b0; b0 = _b0 - s0; rowNum = currRow - 1;
+    } else {
+      nextvalue = r.apply(pos++);                          // (intent) first row of the continuation chunk
+    }
+    if (!std::isnan(b0)) {
+      while (rowNum <= e) {
+        if (!std::isnan(nextvalue)) {
+          double _s0 = sf * nextvalue + (1 - sf) * (s0 + b0);
+          b0 = tf * (_s0 - s0) + (1 - tf) * b0;
+          s0 = _s0;
+        }
+        nextvalue = (pos <= e) ? r.apply(pos) : NaN; pos++;      // the reference's over-read past endRowNum is never used
+        rowNum += 1;
+      }
+      smoothedResult = s0;
+    }
+  }
   void addChunks(InfoReader& ir, int64_t startTime, int64_t endTime) {
     LongReader& ts = ir.tsReader; DoubleReader& val = ir.valReader;
-    if (fn == FN_LAST || fn == FN_TIMESTAMP) {            // RangeFunction.scala:603-613 / :708-716
+    if (fn == FN_LAST || fn == FN_TIMESTAMP || fn == FN_PRESENT_OVER_TIME) {            // RangeFunction.scala:603-613 / :708-716 / :725-748
       int32_t endRowNum = std::min(ts.ceilingIndex(ir.tsVec, endTime), ir.numRows() - 1);
       if (endRowNum >= 0) {
         int64_t t = ts.apply(ir.tsVec, endRowNum);
         if (fn == FN_TIMESTAMP) { tsVal = (double)t / (double)1000.0f; }
-        else if (t >= startTime && t > lastTs) { lastTs = t; lastVal = val.apply(endRowNum); }
+        else if (t >= startTime && t > lastTs) {
+          if (fn == FN_LAST) { lastTs = t; lastVal = longCol ? (double)ir.valLong.apply(ir.valVec, endRowNum) : val.apply(endRowNum); }
+          else {                                             // PresentOverTimeChunkedFunctionD.updateValue
+            double doubleVal = val.apply(endRowNum);
+            if (std::isnan(doubleVal)) {
+              if (endRowNum > 0) { lastTs = t; double lv = val.apply(endRowNum - 1); lastVal = std::isnan(lv) ? NaN : 1.0; }
+            } else { lastTs = t; lastVal = 1.0; }
+          }
+        }
       }
       return;
     }
     int32_t startRowNum = ts.binarySearch(ir.tsVec, startTime) & 0x7fffffff;       // RangeFunction.scala:185-190 / :141-142
     int32_t endRowNum = std::min(ts.ceilingIndex(ir.tsVec, endTime), ir.numRows() - 1);
+    if (fn == FN_PREDICT_LINEAR) {                          // PredictLinearChunkedFunctionD/L.addChunks :1524-1553 / :1560-1588
+      for (int r = startRowNum; r <= endRowNum; ++r) {
+        double nextvalue_ = longCol ? (double)ir.valLong.apply(ir.valVec, r) : val.apply(r);
+        int64_t nexttime = ts.apply(ir.tsVec, r);
+        if (longCol || !std::isnan(nextvalue_)) {
+          double x = (double)(nexttime - endTime) / 1000.0;
+          if (std::isnan(sumY)) { sumY = nextvalue_; sumX = x; sumXY = x * nextvalue_; sumX2 = x * x; }
+          else { sumY += nextvalue_; sumX += x; sumXY += x * nextvalue_; sumX2 += x * x; }
+          counter += 1;
+        }
+      }
+      return;
+    }
     if (isCounterPath()) {                                 // CounterChunkedRangeFunction.addChunks, RangeFunction.scala:138-163
       correctionMeta = val.detectDropAndCorrection(correctionMeta);
       if (startRowNum <= endRowNum)
@@ -162,12 +322,29 @@ struct ChunkedFn {
       return;
     }
     if (!(startRowNum <= endRowNum)) return;
+    if (longCol) { addTimeLongChunks(ir, startRowNum, endRowNum); return; }
     switch (fn) {
       case FN_RATE: case FN_INCREASE: case FN_SUM_OVER_TIME: addSum(val, startRowNum, endRowNum); break;   // delta branch: RateFunctions.scala:424-445
       case FN_AVG_OVER_TIME: addSum(val, startRowNum, endRowNum); count += val.count(startRowNum, endRowNum); break;
       case FN_COUNT_OVER_TIME: if (std::isnan(countD)) countD = 0; countD += val.count(startRowNum, endRowNum); break;
       case FN_MIN_OVER_TIME: for (int r = startRowNum; r <= endRowNum; ++r) mn = minIgnoreNaN(mn, val.apply(r)); break;
       case FN_MAX_OVER_TIME: for (int r = startRowNum; r <= endRowNum; ++r) mx = maxIgnoreNaN(mx, val.apply(r)); break;
+      case FN_STDDEV_OVER_TIME: case FN_STDVAR_OVER_TIME: case FN_ZSCORE: addVar(val, startRowNum, endRowNum); break;
+      case FN_CHANGES: {                                     // ChangesChunkedFunctionD :1193-1208
+        if (std::isnan(changes)) changes = 0;
+        auto c = val.changes(startRowNum, endRowNum, prev);
+        changes += c.first; prev = c.second;
+        break;
+      }
+      case FN_QUANTILE_OVER_TIME:                            // QuantileOverTimeChunkedFunctionD :1272-1300
+        if (p0 < 0) quantileResult = -std::numeric_limits<double>::infinity();
+        else if (p0 > 1) quantileResult = std::numeric_limits<double>::infinity();
+        else for (int r = startRowNum; r <= endRowNum; ++r) { double nv = val.apply(r); if (!std::isnan(nv)) values.push_back(nv); }
+        break;
+      case FN_MAD_OVER_TIME:                                 // :1302-1320
+        for (int r = startRowNum; r <= endRowNum; ++r) { double nv = val.apply(r); if (!std::isnan(nv)) values.push_back(nv); }
+        break;
+      case FN_HOLT_WINTERS: addHoltWinters(val, startRowNum, endRowNum); break;
       default: break;
     }
   }
@@ -187,15 +364,62 @@ struct ChunkedFn {
       if (endTime > highestTime) { highestTime = endTime; highestValue = r.correctedValue(e, correctionMeta); }
     }
   }
-  double apply(int64_t windowStart, int64_t windowEnd) const {
+  double apply(int64_t windowStart, int64_t windowEnd) {
     switch (fn) {
-      case FN_LAST: return lastVal;
+      case FN_LAST: case FN_PRESENT_OVER_TIME: return lastVal;
       case FN_TIMESTAMP: return tsVal;
       case FN_SUM_OVER_TIME: return sum;
       case FN_AVG_OVER_TIME: return count > 0 ? sum / count : (std::isnan(sum) ? sum : 0.0);    // AggrOverTimeFunctions.scala:1000
-      case FN_COUNT_OVER_TIME: return countD;
-      case FN_MIN_OVER_TIME: return mn;
-      case FN_MAX_OVER_TIME: return mx;
+      case FN_COUNT_OVER_TIME: return longCol ? (double)count : countD;
+      case FN_MIN_OVER_TIME: return longCol ? (double)mnL : mn;
+      case FN_MAX_OVER_TIME: return longCol ? (double)mxL : mx;
+      case FN_STDDEV_OVER_TIME: case FN_STDVAR_OVER_TIME: {
+        if (longCol) {                                      // StdDev/StdVarOverTimeChunkedFunctionL :1169-1183
+          double avg = count > 0 ? sum / count : 0.0;
+          double var = squaredSum / count - avg * avg;
+          return fn == FN_STDDEV_OVER_TIME ? std::sqrt(var) : var;
+        }
+        if (count > 0) {                                    // :1118-1142
+          double avg = sum / count;
+          double var = (squaredSum / count) - (avg * avg);
+          return fn == FN_STDDEV_OVER_TIME ? std::sqrt(var) : var;
+        }
+        return std::isnan(sum) ? sum : 0.0;
+      }
+      case FN_ZSCORE: {                                     // :1592-1604
+        if (count > 0) { double avg = sum / count; double stdDev = std::sqrt(squaredSum / count - avg * avg); return (lastSample - avg) / stdDev; }
+        return std::isnan(sum) ? sum : 0.0;
+      }
+      case FN_CHANGES: return changes;
+      case FN_QUANTILE_OVER_TIME: {                         // QuantileOverTimeChunkedFunction.apply :1232-1244
+        int cnt = (int)values.size();
+        std::sort(values.begin(), values.end(), javaDoubleLess);
+        double weight; int upperIndex, lowerIndex; calculateRank(p0, cnt, weight, upperIndex, lowerIndex);
+        if (cnt > 0) quantileResult = values[lowerIndex] * (1 - weight) + values[upperIndex] * weight;
+        return quantileResult;
+      }
+      case FN_MAD_OVER_TIME: {                              // MedianAbsoluteDeviationOverTimeChunkedFunction.apply :1252-1268
+        int size = (int)values.size();
+        double weight; int upperIndex, lowerIndex; calculateRank(0.5, size, weight, upperIndex, lowerIndex);
+        std::sort(values.begin(), values.end(), javaDoubleLess);
+        double res = NaN;
+        if (size > 0) {
+          double median = values[lowerIndex] * (1 - weight) + values[upperIndex] * weight;
+          std::vector<double> diff; diff.reserve(values.size());
+          for (double v : values) diff.push_back(std::fabs(median - v));
+          std::sort(diff.begin(), diff.end(), javaDoubleLess);
+          res = diff[lowerIndex] * (1 - weight) + diff[upperIndex] * weight;
+        }
+        return res;
+      }
+      case FN_HOLT_WINTERS: return smoothedResult;
+      case FN_PREDICT_LINEAR: {                             // PredictLinearChunkedFunction.apply :1507-1517
+        double covXY = sumXY - sumX * sumY / counter;
+        double varX = sumX2 - sumX * sumX / counter;
+        double slope = covXY / varX;
+        double intercept = sumY / counter - slope * sumX / counter;
+        return counter >= 2 ? slope * p0 + intercept : NaN;
+      }
       case FN_RATE: case FN_INCREASE: case FN_DELTA: {
         int64_t curWindowStart = inclusiveRange ? windowStart : windowStart - 1;
         if (isCounterPath()) {                              // RateFunctions.scala:270-285
@@ -222,9 +446,11 @@ inline int numWindows(int64_t start, int64_t step, int64_t end) {
 
 // ChunkedWindowIteratorD, PeriodicSamplesMapper.scala:293-330 — all windows of one series
 inline void periodicSamples(const Series& s, RangeFn fn, bool cumulative, int64_t start, int64_t step, int64_t end, int64_t window,
-                            const QueryConfig& cfg, double* out /*[T]*/, QueryStats* stats = nullptr) {
+                            const QueryConfig& cfg, double* out /*[T]*/, QueryStats* stats = nullptr, double p0 = 0, double p1 = 0) {
+  if (s.longCol && !longColumnSupports(fn)) throw std::invalid_argument("no chunked function for this range function on a Long column");
   WindowedChunkIterator wit(s, start, step, end, window, cfg.inclusiveRange);
   ChunkedFn f{fn, cumulative, cfg.inclusiveRange};
+  f.longCol = s.longCol; f.p0 = p0; f.p1 = p1;
   int k = 0;
   while (wit.hasMoreWindows()) {
     f.reset();

@@ -14,7 +14,8 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libfilo_oracle.so")
 
 # RangeFn / AggrOp numbering == include/filo_b200.h
 FN_LAST, FN_RATE, FN_INCREASE, FN_DELTA, FN_SUM_OVER_TIME, FN_AVG_OVER_TIME, FN_COUNT_OVER_TIME, \
-    FN_MIN_OVER_TIME, FN_MAX_OVER_TIME, FN_TIMESTAMP = range(10)
+    FN_MIN_OVER_TIME, FN_MAX_OVER_TIME, FN_TIMESTAMP, FN_STDDEV_OVER_TIME, FN_STDVAR_OVER_TIME, FN_CHANGES, FN_QUANTILE_OVER_TIME, \
+    FN_ZSCORE, FN_HOLT_WINTERS, FN_PREDICT_LINEAR, FN_MAD_OVER_TIME, FN_PRESENT_OVER_TIME = range(19)
 AGG_NONE, AGG_SUM, AGG_AVG, AGG_MIN, AGG_MAX, AGG_COUNT, AGG_TOPK, AGG_BOTTOMK = range(8)
 VAL_OPTIMIZE, VAL_XOR, VAL_RAW = 0, 1, 2
 TS_OPTIMIZE, TS_RAW = 0, 2
@@ -76,6 +77,8 @@ def _sig(L):
         ("fo_store_vector_bytes", i64, [vp, i64, i32, i32, vp, i64]),
         ("fo_store_algorithmic_bytes", i64, [vp]),
         ("fo_query", i32, [vp, i32, i32, i64, i64, i64, i64, i32, i32, i32, vp, i32, i32, i64, i64, vp, vp, vp]),
+        ("fo_query2", i32, [vp, i32, i32, f64, f64, i64, i64, i64, i64, i32, i32, i32, vp, i32, i32, i64, i64, vp, vp, vp]),
+        ("fo_store_add_chunk_longs", i32, [vp, i64, vp, vp, i32, i32, i32]),
         ("fo_num_windows", i32, [i64, i64, i64]),
         ("fo_sliding", None, [vp, vp, i64, i32, i32, i64, i64, i64, i64, vp]),
     ]:
@@ -258,6 +261,13 @@ class Store:
         if lib().fo_store_add_chunk(self.h, series, _p(ts), _p(vals), ts.size, val_mode, int(detect_drops), ts_mode) != 0:
             raise RuntimeError(last_error())
 
+    def add_chunk_longs(self, series, ts, vals, raw=False, ts_mode=TS_OPTIMIZE):
+        """Long-column chunk: values through LongBinaryVector's appender + optimize() (DDV / const DDV / raw i64)."""
+        ts = np.ascontiguousarray(ts, np.int64); vals = np.ascontiguousarray(vals, np.int64)
+        assert ts.size == vals.size and ts.size > 0
+        if lib().fo_store_add_chunk_longs(self.h, series, _p(ts), _p(vals), ts.size, int(raw), ts_mode) != 0:
+            raise RuntimeError(last_error())
+
     def add_chunk_raw(self, series, start_time, end_time, num_rows, ts_bytes, val_bytes):
         t = np.ascontiguousarray(ts_bytes, np.uint8); v = np.ascontiguousarray(val_bytes, np.uint8)
         lib().fo_store_add_chunk_raw(self.h, series, start_time, end_time, num_rows, _p(t), t.size, _p(v), v.size)
@@ -309,7 +319,7 @@ class Store:
     def algorithmic_bytes(self): return lib().fo_store_algorithmic_bytes(self.h)
 
     def query(self, fn, start, step, end, window, cumulative=False, inclusive=True, aggr=AGG_NONE, k=0,
-              group_ids=None, n_groups=1, threads=1, series_begin=0, series_end=-1, reuse_out=False):
+              group_ids=None, n_groups=1, threads=1, series_begin=0, series_end=-1, reuse_out=False, long_column=False, params=(0.0, 0.0)):
         S = (self.num_series if series_end < 0 else series_end) - series_begin
         T = num_windows(start, step, end)
         if aggr == AGG_NONE:
@@ -326,8 +336,9 @@ class Store:
             aux = np.zeros((n_groups, T), np.int64) if aggr == AGG_AVG else None
         g = np.ascontiguousarray(group_ids, np.int32) if group_ids is not None else None
         stats = np.zeros(3, np.int64)
-        rc = lib().fo_query(self.h, fn, int(cumulative), start, step, end, window, int(inclusive), aggr, k,
-                            _p(g), n_groups, threads, series_begin, series_end, _p(out), _p(aux), _p(stats))
+        pr = tuple(params) + (0.0, 0.0)
+        rc = lib().fo_query2(self.h, fn, int(bool(cumulative)) | (2 if long_column else 0), float(pr[0]), float(pr[1]), start, step, end, window,
+                             int(inclusive), aggr, k, _p(g), n_groups, threads, series_begin, series_end, _p(out), _p(aux), _p(stats))
         if rc != 0:
             raise RuntimeError("oracle query failed: %s" % last_error())
         self.last_stats = {"samples_scanned": int(stats[0]), "bytes_scanned": int(stats[1]), "elapsed_ns": int(stats[2])}

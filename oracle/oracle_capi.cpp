@@ -148,6 +148,19 @@ int32_t fo_store_add_chunk(void* sp, int64_t series, const int64_t* ts, const do
     return 0;
   } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
+// Long-column chunk: the value vector comes from LongBinaryVector.appendingVectorNoNA(...).optimize() (enc::longs), masked != 0 wraps
+// neither: masked vectors are injected with fo_store_add_chunk_raw.
+int32_t fo_store_add_chunk_longs(void* sp, int64_t series, const int64_t* ts, const int64_t* vals, int32_t n, int32_t valRaw, int32_t tsMode) {
+  Store* s = (Store*)sp;
+  try {
+    auto c = std::make_unique<Chunk>();
+    c->ts = (tsMode == 2) ? enc::rawLongs(ts, n) : enc::timestamps(ts, n);
+    c->val = valRaw ? enc::rawLongs(vals, n) : enc::longs(vals, n);
+    finishChunk(*c, ts[0], ts[n - 1], n, ts[n - 1] + 1000);
+    s->series[series]->chunks.push_back(std::move(c));
+    return 0;
+  } catch (std::exception& e) { g_err = e.what(); return -1; }
+}
 // Adds a chunk from pre-encoded vector bytes (lets tests inject arbitrary/corrupt vectors and metadata).
 int32_t fo_store_add_chunk_raw(void* sp, int64_t series, int64_t startTime, int64_t endTime, int32_t numRows,
                                const uint8_t* tsBytes, int32_t tsLen, const uint8_t* valBytes, int32_t valLen) {
@@ -273,12 +286,28 @@ int64_t fo_store_algorithmic_bytes(void* sp) {
 // ---------------- query: PeriodicSamplesMapper (+ optional AggregateMapReduce) over the store
 // out_values: AGG_NONE -> [S*T]; else [G*T] (topk: [G*T*k]).  out_aux: avg counts [G*T] / topk ids [G*T*k] (may be null).
 // stats: {samplesScanned, bytesScanned, elapsed_ns}
+// schemaFlags: bit 0 = cumulative temporality (detectDrops column), bit 1 = the value column is a LongColumn.  p0, p1: static function
+// arguments (quantile; sf, tf; duration).
+int32_t fo_query2(void* sp, int32_t fn, int32_t schemaFlags, double p0, double p1, int64_t start, int64_t step, int64_t end, int64_t window,
+                  int32_t inclusiveRange, int32_t aggrOp, int32_t k, const int32_t* groupIds, int32_t nGroups,
+                  int32_t nThreads, int64_t seriesBegin, int64_t seriesEnd,
+                  double* out_values, int64_t* out_aux, int64_t* stats);
 int32_t fo_query(void* sp, int32_t fn, int32_t cumulative, int64_t start, int64_t step, int64_t end, int64_t window,
                  int32_t inclusiveRange, int32_t aggrOp, int32_t k, const int32_t* groupIds, int32_t nGroups,
                  int32_t nThreads, int64_t seriesBegin, int64_t seriesEnd,
                  double* out_values, int64_t* out_aux, int64_t* stats) {
+  return fo_query2(sp, fn, cumulative ? 1 : 0, 0.0, 0.0, start, step, end, window, inclusiveRange, aggrOp, k, groupIds, nGroups, nThreads,
+                   seriesBegin, seriesEnd, out_values, out_aux, stats);
+}
+int32_t fo_query2(void* sp, int32_t fn, int32_t schemaFlags, double p0, double p1, int64_t start, int64_t step, int64_t end, int64_t window,
+                  int32_t inclusiveRange, int32_t aggrOp, int32_t k, const int32_t* groupIds, int32_t nGroups,
+                  int32_t nThreads, int64_t seriesBegin, int64_t seriesEnd,
+                  double* out_values, int64_t* out_aux, int64_t* stats) {
   Store* s = (Store*)sp;
+  const int32_t cumulative = schemaFlags & 1;
+  const bool longCol = (schemaFlags & 2) != 0;
   try {
+    if (fn == FN_HOLT_WINTERS && !(p0 >= 0 && p0 <= 1 && p1 >= 0 && p1 <= 1)) throw std::invalid_argument("Sf/tf should be in between 0 and 1");
     if (seriesEnd < 0) seriesEnd = (int64_t)s->series.size();
     int64_t S = seriesEnd - seriesBegin;
     int T = numWindows(start, step, end);
@@ -298,7 +327,8 @@ int32_t fo_query(void* sp, int32_t fn, int32_t cumulative, int64_t start, int64_
           int64_t i1 = std::min<int64_t>(S, i0 + 64);
           for (int64_t i = i0; i < i1; ++i) {
             Series se; for (auto& c : s->series[seriesBegin + i]->chunks) se.infos.push_back(c->info.data());
-            periodicSamples(se, (RangeFn)fn, cumulative != 0, start, step, end, window, cfg, perSeries + (size_t)i * T, &qs);
+            se.longCol = longCol;
+            periodicSamples(se, (RangeFn)fn, cumulative != 0, start, step, end, window, cfg, perSeries + (size_t)i * T, &qs, p0, p1);
           }
         }
       } catch (std::exception& e) { if (!failed.exchange(true)) err = e.what(); }
