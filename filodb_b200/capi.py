@@ -7,13 +7,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FILO_LIB_PATH") or os.path.join(_HERE, "libfilo_b200.so")      # FILO_LIB_PATH: A/B runs of a variant build (developer switch)
 
 FN_LAST, FN_RATE, FN_INCREASE, FN_DELTA, FN_SUM_OVER_TIME, FN_AVG_OVER_TIME, FN_COUNT_OVER_TIME, \
-    FN_MIN_OVER_TIME, FN_MAX_OVER_TIME, FN_TIMESTAMP = range(10)
+    FN_MIN_OVER_TIME, FN_MAX_OVER_TIME, FN_TIMESTAMP, FN_STDDEV_OVER_TIME, FN_STDVAR_OVER_TIME, FN_CHANGES, FN_QUANTILE_OVER_TIME, \
+    FN_ZSCORE, FN_HOLT_WINTERS, FN_PREDICT_LINEAR, FN_MAD_OVER_TIME, FN_PRESENT_OVER_TIME = range(19)
 AGG_NONE, AGG_SUM, AGG_AVG, AGG_MIN, AGG_MAX, AGG_COUNT, AGG_TOPK, AGG_BOTTOMK = range(8)
 SCHEMA_CUMULATIVE = 1
+SCHEMA_LONG_VALUES = 2
 Q_PARTIAL = 1
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CORRUPT_VECTOR, ERR_UNSUPPORTED, ERR_QUERY_LIMIT, ERR_BAD_QUERY, ERR_OOM = 0, -1, -2, -3, -4, -5, -6, -7
 
-EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_last_error", "filo_load_series", "filo_synth_table",
+EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_ctx_set_fn_args", "filo_last_error", "filo_load_series", "filo_synth_table",
            "filo_table_set_groups", "filo_table_get_info", "filo_table_read_record", "filo_table_read_arena", "filo_table_free",
            "filo_num_windows", "filo_query", "filo_query_device", "filo_scan_series", "filo_query_hist", "filo_host_register", "filo_host_unregister", "filo_present_partials"]
 
@@ -70,6 +72,7 @@ def _sig(L):
     i32, i64, vp = C.c_int32, C.c_int64, C.c_void_p
     L.filo_ctx_create.restype = i32; L.filo_ctx_create.argtypes = [i32, C.POINTER(Cfg), C.POINTER(vp)]
     L.filo_ctx_destroy.restype = None; L.filo_ctx_destroy.argtypes = [vp]
+    L.filo_ctx_set_fn_args.restype = i32; L.filo_ctx_set_fn_args.argtypes = [vp, C.c_double, C.c_double]
     L.filo_last_error.restype = i32; L.filo_last_error.argtypes = [vp, C.c_char_p, i32]
     L.filo_load_series.restype = i32
     L.filo_load_series.argtypes = [vp, i64, vp, vp, i32, i32, vp, i32, i32, C.POINTER(vp)]
@@ -182,6 +185,10 @@ class Context:
             buf = C.create_string_buffer(1024)
             lib().filo_last_error(self.h, buf, 1024)
             raise FiloError(rc, buf.value.decode())
+
+    def set_fn_args(self, arg0=0.0, arg1=0.0):
+        """funcParams of the following queries (quantile; sf, tf; duration)."""
+        self._check(lib().filo_ctx_set_fn_args(self.h, float(arg0), float(arg1)))
 
     def load_series(self, n_chunks, info_addrs, ts_col=0, val_col=1, group_ids=None, n_groups=0, schema_flags=0):
         nch = np.ascontiguousarray(n_chunks, np.int32)

@@ -28,6 +28,7 @@ struct filo_ctx {
   size_t max_smem_optin = 0;
   std::mutex err_mu;
   std::string err;
+  double fn_args[2] = {0.0, 0.0};      // static arguments of the range function (filo_ctx_set_fn_args)
   // filo_scan_series pipeline slots (pinned staging + device buffers), kept across calls
   struct ScanSlot {
     uint8_t* h_in = nullptr; size_t h_in_cap = 0;        // pinned: records of the batch
@@ -117,6 +118,12 @@ int32_t filo_ctx_create(int32_t device, const filo_cfg* cfg, filo_ctx** out) {
     cudaGetLastError();
   }
   *out = c;
+  return FILO_OK;
+}
+
+int32_t filo_ctx_set_fn_args(filo_ctx* ctx, double arg0, double arg1) {
+  if (!ctx) return fail(nullptr, FILO_ERR_INVALID_ARG, "ctx is null");
+  ctx->fn_args[0] = arg0; ctx->fn_args[1] = arg1;
   return FILO_OK;
 }
 
@@ -250,7 +257,9 @@ inline int32_t rd32(const uint8_t* p) { int32_t v; std::memcpy(&v, p, 4); return
 inline int64_t rd64(const uint8_t* p) { int64_t v; std::memcpy(&v, p, 8); return v; }
 
 // IntBinaryVector.simple validity (MatchError otherwise), IntBinaryVector.scala:120-137
-inline bool inner_ok(const uint8_t* in, int32_t& len) {
+inline bool inner_ok(const uint8_t* in, int32_t& len, int32_t outer_total) {
+  const int32_t inner_bytes = rd32(in);
+  if (inner_bytes < 4 || (int64_t)20 + 4 + inner_bytes > outer_total) return false;      // the inner vector lies inside the outer one
   int nbits = in[6] & 0x7f; bool sgn = in[6] & 0x80; int bs = in[7] & 0x3f;
   bool ok = sgn ? (nbits == 32 || nbits == 16 || nbits == 8) : (nbits == 32 || nbits == 16 || nbits == 8 || nbits == 4 || nbits == 2);
   if (!ok) return false;
@@ -263,9 +272,10 @@ int classify_ts(const uint8_t* v, VecInfo& o) {
   int wire = (uint16_t)(v[4] | (v[5] << 8));
   if (wire == WIRE_MASKED) { v = v + rd32(v + 8); wire = (uint16_t)(v[4] | (v[5] << 8)); if (wire == WIRE_MASKED) return FILO_ERR_CORRUPT_VECTOR; }
   o.p = v; o.total = rd32(v) + 4; o.drop_patch = false; o.drop = false;
+  if (o.total < 8 || o.total > (1 << 28)) return FILO_ERR_CORRUPT_VECTOR;      // numBytes is a positive Int far below the block size
   if (wire == WIRE_DDV_CONST) { if (o.total != 24) return FILO_ERR_CORRUPT_VECTOR; o.len = rd32(v + 8); }
   else if (wire == WIRE_RAW64) o.len = (rd32(v) - 4) / 8;
-  else if (wire == WIRE_DDV) { if (o.total < 28 || !inner_ok(v + 20, o.len)) return FILO_ERR_CORRUPT_VECTOR; }
+  else if (wire == WIRE_DDV) { if (o.total < 28 || !inner_ok(v + 20, o.len, o.total)) return FILO_ERR_CORRUPT_VECTOR; }
   else return FILO_ERR_CORRUPT_VECTOR;
   return (o.total >= 8 && o.len >= 0) ? 0 : FILO_ERR_CORRUPT_VECTOR;
 }
@@ -275,9 +285,10 @@ int classify_val(const uint8_t* v, VecInfo& o) {
   bool masked = false;
   if (wire == WIRE_MASKED) { masked = true; v = v + rd32(v + 8); wire = (uint16_t)(v[4] | (v[5] << 8)); if (wire == WIRE_MASKED) return FILO_ERR_CORRUPT_VECTOR; }
   o.p = v; o.total = rd32(v) + 4; o.drop_patch = masked; o.drop = outer_drop;
+  if (o.total < 8 || o.total > (1 << 28)) return FILO_ERR_CORRUPT_VECTOR;
   if (wire == WIRE_RAW64) o.len = (rd32(v) - 4) / 8;
   else if (wire == WIRE_DDV_CONST) { if (o.total != 24) return FILO_ERR_CORRUPT_VECTOR; o.len = rd32(v + 8); }
-  else if (wire == WIRE_DDV) { if (o.total < 28 || !inner_ok(v + 20, o.len)) return FILO_ERR_CORRUPT_VECTOR; }
+  else if (wire == WIRE_DDV) { if (o.total < 28 || !inner_ok(v + 20, o.len, o.total)) return FILO_ERR_CORRUPT_VECTOR; }
   else if (wire == WIRE_XOR) {
     o.len = rd32(v + XOR_OFF_N);
     int ng = (uint16_t)(v[12] | (v[13] << 8)), po = (uint16_t)(v[14] | (v[15] << 8));
@@ -286,7 +297,7 @@ int classify_val(const uint8_t* v, VecInfo& o) {
     if (masked || o.total < 13) return FILO_ERR_CORRUPT_VECTOR;
     o.len = (uint16_t)(v[6] | (v[7] << 8)); o.drop = false; o.hist = true;
     const int fmt = v[8], defBytes = (uint16_t)(v[9] | (v[10] << 8));
-    if (o.len > 0 && (!(fmt == 3 || fmt == 4 || fmt == 5) || 11 + defBytes > o.total)) return fmt == 9 || fmt == 0x10 ? FILO_ERR_UNSUPPORTED : FILO_ERR_CORRUPT_VECTOR;
+    if (o.len > 0 && (!(fmt == 3 || fmt == 4 || fmt == 5) || 11 + defBytes > o.total)) return (fmt == 8 || fmt == 9 || fmt == 0x0a || fmt == 0x10) ? FILO_ERR_UNSUPPORTED : FILO_ERR_CORRUPT_VECTOR;
   } else return FILO_ERR_CORRUPT_VECTOR;
   return (o.total >= 8 && o.len >= 0) ? 0 : FILO_ERR_CORRUPT_VECTOR;
 }
@@ -587,8 +598,15 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
                                  int32_t agg, int32_t k, int32_t flags, void* d_out_values, void* d_out_aux, void* cuda_stream,
                                  filo_stats* stats, AsyncSink* sink) {
   if (!ctx || !t || !d_out_values) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_query: null argument");
-  if (fn < FILO_FN_LAST || fn > FILO_FN_TIMESTAMP) return fail(ctx, FILO_ERR_INVALID_ARG, "unknown range function");
+  if (fn < FILO_FN_LAST || fn > FILO_FN_PRESENT_OVER_TIME) return fail(ctx, FILO_ERR_INVALID_ARG, "unknown range function");
   if (t->hist) return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram table: use filo_query_hist");
+  const bool long_values = (t->schema_flags & FILO_SCHEMA_LONG_VALUES) != 0;
+  // RangeFunction.longChunkedFunction (RangeFunction.scala:319-339): the other functions fall back to the iterating (row-wise) path
+  if (long_values && !fn_long_column_ok(fn)) return fail(ctx, FILO_ERR_UNSUPPORTED, "no chunked range function for this function on a Long column");
+  if (fn == FILO_FN_HOLT_WINTERS) {                        // HoltWintersChunkedFunction.parseParameters, AggrOverTimeFunctions.scala:1374-1384
+    if (!(ctx->fn_args[0] >= 0 && ctx->fn_args[0] <= 1)) return fail(ctx, FILO_ERR_INVALID_ARG, "Sf should be in between 0 and 1");
+    if (!(ctx->fn_args[1] >= 0 && ctx->fn_args[1] <= 1)) return fail(ctx, FILO_ERR_INVALID_ARG, "tf should be in between 0 and 1");
+  }
   if (agg < FILO_AGG_NONE || agg > FILO_AGG_BOTTOMK) return fail(ctx, FILO_ERR_INVALID_ARG, "unknown aggregation operator");
   // PeriodicSamplesMapper.scala:45-49, 67-68
   if (start > end) return fail(ctx, FILO_ERR_INVALID_ARG, "start should be <= end");
@@ -607,6 +625,7 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
   QueryParams q{};
   q.start = start; q.step = adjustedStep; q.end = end; q.window = window; q.T = filo_num_windows(start, adjustedStep, end);
   q.fn = fn; q.cumulative = (t->schema_flags & FILO_SCHEMA_CUMULATIVE) ? 1 : 0; q.inclusive = ctx->cfg.inclusive_range ? 1 : 0;
+  q.long_values = long_values ? 1 : 0; q.p0 = ctx->fn_args[0]; q.p1 = ctx->fn_args[1];
   const bool need_corr = (fn == FILO_FN_RATE || fn == FILO_FN_INCREASE) && q.cumulative;
   const bool fused = (agg != FILO_AGG_NONE && agg != FILO_AGG_TOPK && agg != FILO_AGG_BOTTOMK);
 
@@ -655,7 +674,7 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
   // v3 tile kernel (scan_tile.cuh): SUM-class functions over regular series; irregular series are appended to a list that the
   // v2 kernel processes right after, into the same output buffer.  FILO_KERNEL=v2 disables the tile kernel.
   const bool want_v2 = force && std::string(force) == "v2";
-  const int fn_cls = fn_class_of(fn, q.cumulative);
+  const int fn_cls = fn_class_of(fn, q.cumulative, q.long_values);
   // zero rows around a chunk let clamped windows run without bounds checks: a window spans at most window/step + 1 rows
   // at either end; when that does not leave room for two CTAs per SM the tile kernel falls back to checked loads
   TileSmem TL;

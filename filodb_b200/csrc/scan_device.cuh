@@ -43,8 +43,9 @@ struct __align__(16) ChunkDesc {
   int32_t Wr;                   // last row - first row of every window in [kA, kB]
   int32_t blk0, blk_n;          // blocked-reduction work list: first block index / number of blocks of this chunk
   int32_t nrows_eff;            // min(num_rows, ts_len, val_len)
-  int32_t pad_;
+  int32_t val_kind;             // VK_F64 / VK_DDV / VK_DDV_CONST / VK_RAW_I64 (reader-specific behaviour: changes(), Long sums)
 };
+enum { VK_F64 = 0, VK_DDV = 1, VK_DDV_CONST = 2, VK_RAW_I64 = 3 };
 static_assert(sizeof(ChunkDesc) == 144, "ChunkDesc size");
 
 // ------------------------------------------------------------------------------------------------ loads
@@ -156,7 +157,7 @@ __device__ __forceinline__ double slot_value(const ChunkDesc& c, int r) {
 // Resolves chunk `e` of the record into `d`; decodes into scratch as needed.  Returns an error code (0 = ok).
 // All lanes call it with identical arguments; stores to *d are done by lane 0 and published with __syncwarp.
 __device__ __forceinline__ int resolve_chunk(const uint8_t* rec, const ChunkEntry* e, ChunkDesc* d, ScratchCursor& sc,
-                                             bool need_corrected, int lane, bool copy_all = false) {
+                                             bool need_corrected, int lane, bool copy_all = false, bool long_col = false) {
   bool lane_nan = false; bool nan_known = false;
   const uint8_t* tv = rec + e->ts_off;
   const uint8_t* vv = rec + e->val_off;
@@ -187,7 +188,19 @@ __device__ __forceinline__ int resolve_chunk(const uint8_t* rec, const ChunkEntr
   // ---- values (DoubleVector.scala:62-71)
   const void* val_slots = nullptr; int64_t val_init = 0; int32_t val_slope = 0; int32_t val_len = 0; bool is_long = false;
   const bool dropped = (vw >> 31) & 1;                   // PrimitiveVectorReader.dropped, BinaryVector.scala:530-531
-  if (vwire == WIRE_RAW64) {
+  int val_kind = VK_F64;
+  if (vwire == WIRE_XOR && long_col) err = err ? err : FILO_DEV_ERR_VAL_WIRE;      // not a LongBinaryVector
+  else if (vwire == WIRE_RAW64 && long_col) {            // LongVectorDataReader64: 64-bit longs (LongBinaryVector.scala:192-206)
+    is_long = true; val_kind = VK_RAW_I64; nan_known = true;
+    val_len = ((int32_t)ld32(vv) - 4) / 8;
+    if (!copy_all) val_slots = vv + 8;
+    else {
+      uint64_t* slots = reinterpret_cast<uint64_t*>(sc.p);
+      const uint64_t* src = reinterpret_cast<const uint64_t*>(vv + 8);
+      for (int r = lane; r < val_len; r += 32) slots[r] = src[r];
+      val_slots = slots; sc.p += (size_t)val_len * 8;
+    }
+  } else if (vwire == WIRE_RAW64) {
     val_len = ((int32_t)ld32(vv) - 4) / 8;
     if (!copy_all) val_slots = vv + 8;                   // addressable in place
     else {                                               // the staged record buffer is recycled right after resolve
@@ -198,12 +211,12 @@ __device__ __forceinline__ int resolve_chunk(const uint8_t* rec, const ChunkEntr
       val_slots = slots; sc.p += (size_t)val_len * 8;
     }
   } else if (vwire == WIRE_DDV_CONST) {
-    is_long = true; val_len = (int32_t)ld32(vv + 8); val_init = (int64_t)ld64_a4(vv + 12); val_slope = (int32_t)ld32(vv + 20);
+    is_long = true; val_kind = VK_DDV_CONST; val_len = (int32_t)ld32(vv + 8); val_init = (int64_t)ld64_a4(vv + 12); val_slope = (int32_t)ld32(vv + 20);
     int64_t* slots = reinterpret_cast<int64_t*>(sc.p);
     for (int r = lane; r < val_len; r += 32) slots[r] = val_init + (int64_t)(int32_t)((uint32_t)val_slope * (uint32_t)r);
     val_slots = slots; sc.p += (size_t)val_len * 8; nan_known = true;
   } else if (vwire == WIRE_DDV) {
-    is_long = true;
+    is_long = true; val_kind = VK_DDV;
     const uint8_t* in = vv + 20;
     const uint32_t iw = ld32(in + 4);
     const int nbits = (iw >> 16) & 0x7f; const bool sgn = (iw >> 23) & 1;
@@ -228,7 +241,7 @@ __device__ __forceinline__ int resolve_chunk(const uint8_t* rec, const ChunkEntr
     d->ts_init = ts_init; d->val_init = val_init; d->ts_slope = ts_slope; d->val_slope = val_slope;
     d->num_rows = e->num_rows; d->ts_len = ts_len; d->val_len = val_len;
     d->val_is_long = is_long; d->dropped = dropped; d->has_nan = (uint8_t)((!nan_known || nan_ballot != 0) ? 1 : 0);
-    d->kA = 0; d->kB = -1; d->sA = 0; d->Wr = 0; d->blk0 = 0; d->blk_n = 0; d->nrows_eff = 0;
+    d->kA = 0; d->kB = -1; d->sA = 0; d->Wr = 0; d->blk0 = 0; d->blk_n = 0; d->nrows_eff = 0; d->val_kind = val_kind;
     // row search may use 32-bit arithmetic when no Int wrap can occur in slope * n (DeltaDeltaVector.scala:241-253)
     d->fast32 = (ts_slots == nullptr && ts_slope > 0 && (int64_t)ts_slope * ((int64_t)ts_len + 1) < 0x7fffffffLL) ? 1 : 0;
     d->upd_last = 0; d->upd_corr = 0;
@@ -316,6 +329,13 @@ __device__ __forceinline__ double slope_sum(int64_t initVal, int32_t slope, int 
 
 // chunk sum over rows [s,e] (DoubleVectorDataReader64.sum / DoubleLongWrapDataReader.sum); *cnt = non-NaN count
 __device__ __forceinline__ double chunk_sum(const ChunkDesc& c, int s, int e, int& cnt) {
+  if (c.val_kind == VK_RAW_I64) {                         // LongVectorDataReader64.sum: sequential double adds (LongBinaryVector.scala:211-222)
+    const int64_t* lv = reinterpret_cast<const int64_t*>(c.val_slots);
+    double sum = 0.0;
+    for (int r = s; r <= e; ++r) sum += (double)lv[r];
+    cnt = e - s + 1;
+    return sum;
+  }
   if (c.val_is_long) {
     const int64_t* lv = reinterpret_cast<const int64_t*>(c.val_slots);
     int64_t resid = 0;
@@ -351,6 +371,290 @@ __device__ __forceinline__ double extrapolated_rate(int64_t windowStart, int64_t
   return isRate ? (scaledDelta / (double)(windowEnd - windowStart) * 1000.0) : scaledDelta;
 }
 
+// ------------------------------------------------------------------------------------------------ extended functions
+// The remaining chunked range functions (AggrOverTimeFunctions.scala:1082-1604, RangeFunction.scala:725-748) and the Long-column
+// variants (AggrOverTimeFunctions.scala:60-116,574-585,924-938,1019-1028,1144-1183,1211-1225,1322-1359; RangeFunction.scala:696-703).
+// Out of line: the hot kernels keep their register budget; these functions run window by window (one lane per window).
+__device__ __forceinline__ bool chunk_rows(const ChunkDesc& c, int64_t wStart, int64_t wEnd, int& s, int& e) {
+  bool ex; s = ts_search(c, wStart, ex);
+  const int idx = ts_search(c, wEnd, ex);
+  e = ex ? idx : idx - 1; if (e > c.num_rows - 1) e = c.num_rows - 1;
+  return s <= e;
+}
+__device__ __forceinline__ void window_chunk_set(const ChunkDesc* D, int cLo, int cHi, int64_t wStart, int64_t wEnd, int& a, int& f) {
+  a = cLo;
+  while (a < cHi && D[a].end_time < wStart) ++a;
+  f = a; while (f < cHi - 1 && D[f].end_time < wEnd) ++f;
+}
+__device__ __forceinline__ int64_t d2l_jvm(double d) {       // JVM d2l: NaN -> 0, saturating
+  if (d != d) return 0;
+  if (d >= 9223372036854775807.0) return INT64_MAX;
+  if (d <= -9223372036854775808.0) return INT64_MIN;
+  return (int64_t)d;
+}
+__device__ __forceinline__ int64_t slot_long(const ChunkDesc& c, int r) { return reinterpret_cast<const int64_t*>(c.val_slots)[r]; }
+// LongVectorDataReader.changes per reader (DeltaDeltaVector.scala:212-227, 280-288; LongBinaryVector.scala:248-265)
+__device__ __forceinline__ void long_changes(const ChunkDesc& c, int s, int e, int64_t prev, bool ignorePrev, int64_t& ch, int64_t& last) {
+  if (c.val_kind == VK_DDV_CONST) {
+    const int64_t firstValue = slot_long(c, s); last = slot_long(c, e);
+    ch = (!ignorePrev && prev != firstValue) ? 1 : 0;
+    if (c.val_slope != 0) ch += (int64_t)(e - s);
+    return;
+  }
+  int64_t prevVector = prev; ch = 0;
+  for (int i = s; i <= e; ++i) {
+    const int64_t cur = slot_long(c, i);
+    if (i == s && (ignorePrev || c.val_kind == VK_RAW_I64)) prevVector = cur;      // the raw 64-bit reader always re-seeds prev
+    if (prevVector != cur) ch += 1;
+    prevVector = cur;
+  }
+  last = prevVector;
+}
+// order-preserving key of a double (Double.compare order: -0.0 < 0.0, NaN above +Inf) and its inverse
+__device__ __forceinline__ uint64_t dkey(double v) { const uint64_t b = (uint64_t)__double_as_longlong(v); return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull); }
+__device__ __forceinline__ double dkey_inv(uint64_t k) { const uint64_t b = (k >> 63) ? (k ^ 0x8000000000000000ull) : ~k; return __longlong_as_double((long long)b); }
+
+// values of a window: every row of the chunks' row ranges, NaN dropped for double columns.  MODE 0: the value, MODE 1: |ref - value|
+template <int MODE>
+__device__ __forceinline__ void win_count_le(const ChunkDesc* D, int a, int f, int cHi, int64_t wStart, int64_t wEnd, bool long_col, double ref,
+                                             uint64_t K, int& n_le, uint64_t& next_above) {
+  n_le = 0; next_above = ~0ull;
+  for (int ci = a; ci <= f && ci < cHi; ++ci) {
+    const ChunkDesc& c = D[ci]; int s, e;
+    if (!chunk_rows(c, wStart, wEnd, s, e)) continue;
+    for (int r = s; r <= e; ++r) {
+      double v = slot_value(c, r);
+      if (!long_col && is_nan(v)) continue;
+      if (MODE == 1) v = fabs(ref - v);
+      const uint64_t kk = dkey(v);
+      if (kk <= K) ++n_le; else if (kk < next_above) next_above = kk;
+    }
+  }
+}
+// the values with sorted indices lo and hi = min(n - 1, lo + 1) (java.util.Arrays.sort order) by bisection over the key space
+template <int MODE>
+__device__ __forceinline__ void win_select(const ChunkDesc* D, int a, int f, int cHi, int64_t wStart, int64_t wEnd, bool long_col, double ref,
+                                           int lo, int hi, double& vlo, double& vhi) {
+  uint64_t L = 0, H = ~0ull; int n_le; uint64_t above;
+  while (L < H) {                                        // smallest K with count(key <= K) >= lo + 1
+    const uint64_t M = L + ((H - L) >> 1);
+    win_count_le<MODE>(D, a, f, cHi, wStart, wEnd, long_col, ref, M, n_le, above);
+    if (n_le >= lo + 1) H = M; else L = M + 1;
+  }
+  win_count_le<MODE>(D, a, f, cHi, wStart, wEnd, long_col, ref, L, n_le, above);
+  vlo = dkey_inv(L);
+  vhi = (hi == lo || n_le >= hi + 1) ? vlo : dkey_inv(above);
+}
+
+#ifdef FILO_CUSIM
+inline double eval_window_ext(
+#else
+static __device__ __noinline__ double eval_window_ext(
+#endif
+    const ChunkDesc* D, int cLo, int cHi, const QueryParams& q, int k, int a, int f,
+                                               int64_t wStart, int64_t wEnd) {
+  const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
+  const int fn = q.fn;
+  const bool lng = q.long_values != 0;
+  switch (fn) {
+    case FN_LAST: case FN_PRESENT: {                      // LastSampleChunkedFunctionL :696-703; PresentOverTimeChunkedFunctionD :725-748
+      int64_t lastTs = -1; double lastVal = NaNv;
+      for (int ci = a; ci <= f && ci < cHi; ++ci) {
+        const ChunkDesc& c = D[ci];
+        bool ex; const int idx = ts_search(c, wEnd, ex);
+        int e = ex ? idx : idx - 1; if (e > c.num_rows - 1) e = c.num_rows - 1;
+        if (e < 0) continue;
+        const int64_t t = ts_apply(c, e);
+        if (!(t >= wStart && t > lastTs)) continue;
+        if (fn == FN_LAST) { lastTs = t; lastVal = slot_value(c, e); }
+        else {
+          const double dv = slot_value(c, e);
+          if (is_nan(dv)) { if (e > 0) { lastTs = t; lastVal = is_nan(slot_value(c, e - 1)) ? NaNv : 1.0; } }
+          else { lastTs = t; lastVal = 1.0; }
+        }
+      }
+      return lastVal;
+    }
+    case FN_COUNT: {                                      // CountOverTimeChunkedFunction :924-938 (Long columns)
+      int32_t count = 0;
+      for (int ci = a; ci <= f && ci < cHi; ++ci) { int s, e; if (chunk_rows(D[ci], wStart, wEnd, s, e)) count += e - s + 1; }
+      return (double)count;
+    }
+    case FN_SUM: case FN_AVG: {                           // SumOverTimeChunkedFunctionL :574-585; AvgOverTimeChunkedFunctionL :1019-1028
+      double sum = NaNv; int32_t count = 0;
+      for (int ci = a; ci <= f && ci < cHi; ++ci) {
+        int s, e; if (!chunk_rows(D[ci], wStart, wEnd, s, e)) continue;
+        int cnt; const double cs = chunk_sum(D[ci], s, e, cnt);
+        if (fn == FN_SUM && is_nan(sum)) sum = 0.0;       // the Avg variant never clears its NaN seed: avg_over_time of a Long column is NaN
+        sum += cs; count += e - s + 1;
+      }
+      if (fn == FN_SUM) return sum;
+      return count > 0 ? sum / (double)count : (is_nan(sum) ? sum : 0.0);
+    }
+    case FN_MIN: case FN_MAX: {                           // Min/MaxOverTimeChunkedFunctionL :60-116
+      int64_t m = fn == FN_MIN ? INT64_MAX : INT64_MIN;
+      for (int ci = a; ci <= f && ci < cHi; ++ci) {
+        int s, e; if (!chunk_rows(D[ci], wStart, wEnd, s, e)) continue;
+        for (int r = s; r <= e; ++r) { const int64_t v = slot_long(D[ci], r); m = fn == FN_MIN ? (v < m ? v : m) : (v > m ? v : m); }
+      }
+      return (double)m;
+    }
+    case FN_STDDEV: case FN_STDVAR: case FN_ZSCORE: {
+      if (lng) {                                          // VarOverTimeChunkedFunctionL :1144-1183
+        double sum = 0.0, sq = 0.0; int32_t count = 0;
+        for (int ci = a; ci <= f && ci < cHi; ++ci) {
+          int s, e; if (!chunk_rows(D[ci], wStart, wEnd, s, e)) continue;
+          double _sum = 0.0, _sq = 0.0;
+          for (int r = s; r <= e; ++r) { const double v = (double)slot_long(D[ci], r); _sum += v; _sq += v * v; }
+          count += e - s + 1; sum += _sum; sq += _sq;
+        }
+        const double avg = count > 0 ? sum / (double)count : 0.0;
+        const double var = sq / (double)count - avg * avg;
+        return fn == FN_STDDEV ? sqrt(var) : var;
+      }
+      double sum = NaNv, sq = NaNv; int32_t count = 0;    // VarOverTimeChunkedFunctionD :1082-1142, ZScoreChunkedFunctionD :1592-1604
+      double lastSample = NaNv; bool haveLast = false;
+      for (int ci = a; ci <= f && ci < cHi; ++ci) {
+        int s, e; if (!chunk_rows(D[ci], wStart, wEnd, s, e)) continue;
+        double cs = NaNv, cq = NaNv; int cc = 0;
+        for (int r = s; r <= e; ++r) {
+          const double v = slot_value(D[ci], r);
+          if (!is_nan(v)) {
+            if (is_nan(cs)) cs = 0.0;
+            if (is_nan(cq)) cq = 0.0;
+            if (r == e) { lastSample = v; haveLast = true; }
+            cs += v; cq += v * v; cc += 1;
+          }
+        }
+        if (!is_nan(cs) && is_nan(sum)) sum = 0.0;
+        sum += cs;
+        if (!is_nan(cq) && is_nan(sq)) sq = 0.0;
+        sq += cq;
+        count += cc;
+      }
+      if (count <= 0) return is_nan(sum) ? sum : 0.0;
+      const double avg = sum / (double)count;
+      if (fn == FN_STDVAR) return (sq / (double)count) - (avg * avg);
+      if (fn == FN_STDDEV) return sqrt((sq / (double)count) - (avg * avg));
+      // zscore: lastSample is not cleared between windows (reset() leaves it): when this window's end rows are all NaN the value of the
+      // closest earlier window that saw a number at a chunk's end row is still there
+      for (int kk = k - 1; kk >= 0 && !haveLast; --kk) {
+        const int64_t we = q.start + (int64_t)kk * q.step, ws = we - (wEnd - wStart);
+        int a2, f2; window_chunk_set(D, cLo, cHi, ws, we, a2, f2);
+        for (int ci = a2; ci <= f2 && ci < cHi; ++ci) {
+          int s, e; if (!chunk_rows(D[ci], ws, we, s, e)) continue;
+          const double v = slot_value(D[ci], e);
+          if (!is_nan(v)) { lastSample = v; haveLast = true; }
+        }
+      }
+      const double stdDev = sqrt(sq / (double)count - avg * avg);
+      return (lastSample - avg) / stdDev;
+    }
+    case FN_CHANGES: {                                    // ChangesChunkedFunctionD / L :1185-1225
+      double changes = NaNv, prev = NaNv;
+      for (int ci = a; ci <= f && ci < cHi; ++ci) {
+        const ChunkDesc& c = D[ci];
+        int s, e; if (!chunk_rows(c, wStart, wEnd, s, e)) continue;
+        if (is_nan(changes)) changes = 0.0;
+        if (c.val_is_long) {                              // Long column, or the DoubleLongWrap reader of a double column (DoubleVector.scala:559-566)
+          int64_t ch, last;
+          long_changes(c, s, e, d2l_jvm(prev), lng ? false : is_nan(prev), ch, last);
+          changes += (double)ch; prev = (double)last;
+        } else {                                          // DoubleVectorDataReader64.changes, DoubleVector.scala:283-303
+          double ch = 0.0, pv = prev;
+          for (int r = s; r <= e; ++r) {
+            const double v = slot_value(c, r);
+            if (!is_nan(v) && pv != v && !is_nan(pv)) ch += 1.0;
+            pv = v;
+          }
+          changes += ch; prev = pv;
+        }
+      }
+      return changes;
+    }
+    case FN_QUANTILE: case FN_MAD: {                      // Quantile :1227-1344, MedianAbsoluteDeviation :1248-1359
+      int n = 0; bool visited = false;
+      for (int ci = a; ci <= f && ci < cHi; ++ci) {
+        const ChunkDesc& c = D[ci]; int s, e;
+        if (!chunk_rows(c, wStart, wEnd, s, e)) continue;
+        visited = true;
+        if (lng) n += e - s + 1;
+        else for (int r = s; r <= e; ++r) n += is_nan(slot_value(c, r)) ? 0 : 1;
+      }
+      const double qv = fn == FN_MAD ? 0.5 : q.p0;
+      if (fn == FN_QUANTILE && qv < 0) return visited ? __longlong_as_double(0xfff0000000000000LL) : NaNv;
+      if (fn == FN_QUANTILE && qv > 1) return visited ? __longlong_as_double(0x7ff0000000000000LL) : NaNv;
+      if (n == 0) return NaNv;
+      const double rank = qv * (double)(n - 1);           // QuantileOverTimeFunction.calculateRank :399-407
+      const double fl = floor(rank);
+      const double lower = fl > 0.0 ? fl : 0.0;
+      const double upper = (lower + 1 < (double)(n - 1)) ? lower + 1 : (double)(n - 1);
+      const double weight = rank - fl;
+      const int lo = (int)lower, hi = (int)upper;
+      double vlo, vhi;
+      win_select<0>(D, a, f, cHi, wStart, wEnd, lng, 0.0, lo, hi, vlo, vhi);
+      const double res = vlo * (1 - weight) + vhi * weight;
+      if (fn == FN_QUANTILE) return res;
+      double dlo, dhi;
+      win_select<1>(D, a, f, cHi, wStart, wEnd, lng, res, lo, hi, dlo, dhi);
+      return dlo * (1 - weight) + dhi * weight;
+    }
+    case FN_HOLT_WINTERS: {                               // HoltWintersChunkedFunctionD :1393-1453 (see oracle/filo_query.hpp addHoltWinters)
+      const double sf = q.p0, tf = q.p1;
+      double b0 = NaNv, s0 = NaNv, nextvalue = NaNv, smoothed = NaNv;
+      for (int ci = a; ci <= f && ci < cHi; ++ci) {
+        const ChunkDesc& c = D[ci];
+        int s, e; if (!chunk_rows(c, wStart, wEnd, s, e)) continue;
+        int pos = s, rowNum = s;
+        if (is_nan(s0) && is_nan(b0)) {
+          double _s0 = NaNv, _b0 = NaNv; int cur = s;
+          while (cur <= e && is_nan(_s0)) { const double nv = slot_value(c, pos++); if (!is_nan(nv)) _s0 = nv; ++cur; }
+          while (cur <= e && is_nan(_b0)) { const double nv = slot_value(c, pos++); if (!is_nan(nv)) _b0 = nv; ++cur; }
+          nextvalue = _b0; b0 = _b0 - _s0; rowNum = cur - 1; s0 = _s0;
+        } else if (is_nan(b0)) {
+          double _b0 = NaNv; int cur = s;
+          while (cur <= e && is_nan(_b0)) { const double nv = slot_value(c, pos++); if (!is_nan(nv)) _b0 = nv; ++cur; }
+          nextvalue = _b0; b0 = _b0 - s0; rowNum = cur - 1;
+        } else nextvalue = slot_value(c, pos++);
+        if (!is_nan(b0)) {
+          while (rowNum <= e) {
+            if (!is_nan(nextvalue)) {
+              const double _s0 = sf * nextvalue + (1 - sf) * (s0 + b0);
+              b0 = tf * (_s0 - s0) + (1 - tf) * b0;
+              s0 = _s0;
+            }
+            nextvalue = (pos <= e) ? slot_value(c, pos) : NaNv; ++pos;
+            ++rowNum;
+          }
+          smoothed = s0;
+        }
+      }
+      return smoothed;
+    }
+    case FN_PREDICT_LINEAR: {                             // PredictLinearChunkedFunctionD / L :1496-1590
+      double sumX = NaNv, sumY = NaNv, sumXY = NaNv, sumX2 = NaNv; int32_t counter = 0;
+      for (int ci = a; ci <= f && ci < cHi; ++ci) {
+        const ChunkDesc& c = D[ci];
+        int s, e; if (!chunk_rows(c, wStart, wEnd, s, e)) continue;
+        for (int r = s; r <= e; ++r) {
+          const double v = slot_value(c, r);
+          if (!lng && is_nan(v)) continue;
+          const double x = (double)(ts_apply(c, r) - wEnd) / 1000.0;
+          if (is_nan(sumY)) { sumY = v; sumX = x; sumXY = x * v; sumX2 = x * x; }
+          else { sumY += v; sumX += x; sumXY += x * v; sumX2 += x * x; }
+          counter += 1;
+        }
+      }
+      const double covXY = sumXY - sumX * sumY / (double)counter;
+      const double varX = sumX2 - sumX * sumX / (double)counter;
+      const double slope = covXY / varX;
+      const double intercept = sumY / (double)counter - slope * sumX / (double)counter;
+      return counter >= 2 ? slope * q.p0 + intercept : NaNv;
+    }
+  }
+  return NaNv;
+}
+
 // One output window of one series.  D[cLo..cHi) are the chunks that intersect [start - window, end].
 __device__ __forceinline__ double eval_window(const ChunkDesc* D, int cLo, int cHi, const QueryParams& q, int k) {
   const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
@@ -368,6 +672,7 @@ __device__ __forceinline__ double eval_window(const ChunkDesc* D, int cLo, int c
     f = lo < cHi - 1 ? lo : cHi - 1;
   }
   const int fn = q.fn;
+  if (fn >= FN_STDDEV || q.long_values) return eval_window_ext(D, cLo, cHi, q, k, a, f, wStart, wEnd);
   const bool counterPath = ((fn == FN_RATE || fn == FN_INCREASE) && q.cumulative) || fn == FN_DELTA;
 
   if (fn == FN_LAST || fn == FN_TIMESTAMP) {              // RangeFunction.scala:603-613, 708-716

@@ -282,7 +282,7 @@ __device__ __forceinline__ void process_series(const uint8_t* rec, const QueryPa
       }
     }
     for (int c = 0; c < n; ++c) {
-      const int e = resolve_chunk(rec, &E[cLo + c], &D[c], sc, need_corrected, lane, true);
+      const int e = resolve_chunk(rec, &E[cLo + c], &D[c], sc, need_corrected, lane, true, q.long_values != 0);
       if (e) { err = e; return; }
     }
     if (lane == 0) {                                        // CountingChunkInfoIterator, ChunkSetInfo.scala:336-380

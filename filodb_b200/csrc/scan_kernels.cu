@@ -40,7 +40,7 @@ __device__ __forceinline__ int resolve_series(const uint8_t* rec, const QueryPar
   uint32_t need = (uint32_t)(sc.p - scratch) + (uint32_t)h->n_rows * 8u * (need_corrected ? 3u : 2u);
   if (need > scratch_bytes) { err = FILO_DEV_ERR_SCRATCH; return 0; }
   for (int c = 0; c < n; ++c) {
-    int e = resolve_chunk(rec, &E[cLo + c], &D[c], sc, need_corrected, lane);
+    int e = resolve_chunk(rec, &E[cLo + c], &D[c], sc, need_corrected, lane, false, q.long_values != 0);
     if (e) { err = e; return 0; }
   }
   // CountingChunkInfoIterator (ChunkSetInfo.scala:336-380): chunks pulled by the window iterator
@@ -407,7 +407,7 @@ static cudaError_t launch_series_v2_cls(const ScanLaunch& L, double* out, uint32
 }
 cudaError_t launch_scan_series_v2(const ScanLaunch& L, double* out, uint32_t rec_cap) {
   const size_t smem = (size_t)(WARP_HDR_BYTES + rec_cap + STAGE_BYTES + L.scratch_bytes) * FAST_WARPS;
-  switch (fn_class_of(L.q.fn, L.q.cumulative)) {
+  switch (fn_class_of(L.q.fn, L.q.cumulative, L.q.long_values)) {
     case CLASS_SUM: return launch_series_v2_cls<CLASS_SUM>(L, out, rec_cap, smem);
     case CLASS_MINMAX: return launch_series_v2_cls<CLASS_MINMAX>(L, out, rec_cap, smem);
     case CLASS_COUNTER: return launch_series_v2_cls<CLASS_COUNTER>(L, out, rec_cap, smem);
@@ -426,7 +426,7 @@ static cudaError_t launch_agg_v2_cls(const ScanLaunch& L, const int32_t* order, 
 cudaError_t launch_scan_agg_v2(const ScanLaunch& L, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg_op,
                                double* pval, uint32_t* pcnt, uint32_t acc_bytes, uint32_t rec_cap) {
   const size_t smem = (size_t)(WARP_HDR_BYTES + rec_cap + STAGE_BYTES + acc_bytes + L.scratch_bytes) * FAST_WARPS;
-  switch (fn_class_of(L.q.fn, L.q.cumulative)) {
+  switch (fn_class_of(L.q.fn, L.q.cumulative, L.q.long_values)) {
     case CLASS_SUM: return launch_agg_v2_cls<CLASS_SUM>(L, order, item_begin, n_items, agg_op, pval, pcnt, acc_bytes, rec_cap, smem);
     case CLASS_MINMAX: return launch_agg_v2_cls<CLASS_MINMAX>(L, order, item_begin, n_items, agg_op, pval, pcnt, acc_bytes, rec_cap, smem);
     case CLASS_COUNTER: return launch_agg_v2_cls<CLASS_COUNTER>(L, order, item_begin, n_items, agg_op, pval, pcnt, acc_bytes, rec_cap, smem);
@@ -452,7 +452,7 @@ static cudaError_t launch_tile_fn(const ScanLaunch& L, double* out, const TileSm
 template <bool AGG>
 static cudaError_t launch_tile_any(const ScanLaunch& L, double* out, const TileSmem& T, int64_t* fallback_list, unsigned long long* fallback_count,
                                    const TileAggArgs& A) {
-  if (fn_class_of(L.q.fn, L.q.cumulative) == CLASS_COUNTER) {
+  if (fn_class_of(L.q.fn, L.q.cumulative, L.q.long_values) == CLASS_COUNTER) {
     switch (L.q.fn) {
       case FN_RATE: return launch_tile_fn<CLASS_COUNTER, FN_RATE, AGG>(L, out, T, fallback_list, fallback_count, A);
       case FN_INCREASE: return launch_tile_fn<CLASS_COUNTER, FN_INCREASE, AGG>(L, out, T, fallback_list, fallback_count, A);

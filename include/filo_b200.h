@@ -65,7 +65,18 @@ enum {
   FILO_FN_COUNT_OVER_TIME = 6,
   FILO_FN_MIN_OVER_TIME = 7,
   FILO_FN_MAX_OVER_TIME = 8,
-  FILO_FN_TIMESTAMP = 9
+  FILO_FN_TIMESTAMP = 9,
+  /* the other chunked range functions of RangeFunction.doubleChunkedFunction (RangeFunction.scala:341-375); static arguments
+   * (funcParams) come from filo_ctx_set_fn_args */
+  FILO_FN_STDDEV_OVER_TIME = 10,    /* StdDevOverTimeChunkedFunctionD / L   AggrOverTimeFunctions.scala:1082-1183 */
+  FILO_FN_STDVAR_OVER_TIME = 11,
+  FILO_FN_CHANGES = 12,             /* ChangesChunkedFunctionD / L          :1185-1225 */
+  FILO_FN_QUANTILE_OVER_TIME = 13,  /* arg0 = q                             :1227-1344 */
+  FILO_FN_ZSCORE = 14,              /* ZScoreChunkedFunctionD               :1592-1604 */
+  FILO_FN_HOLT_WINTERS = 15,        /* arg0 = sf, arg1 = tf, both in [0,1]  :1361-1453 */
+  FILO_FN_PREDICT_LINEAR = 16,      /* arg0 = duration in seconds           :1496-1590 */
+  FILO_FN_MAD_OVER_TIME = 17,       /* MedianAbsoluteDeviationOverTime      :1248-1359 */
+  FILO_FN_PRESENT_OVER_TIME = 18    /* PresentOverTimeChunkedFunctionD      RangeFunction.scala:725-748 */
 };
 
 /* AggregationOperator subset (query/src/main/scala/filodb/query/PlanEnums.scala:99-114) */
@@ -76,7 +87,9 @@ enum {
 
 /* schema_flags of filo_load_series */
 enum {
-  FILO_SCHEMA_CUMULATIVE = 1        /* schema.hasCumulativeTemporalityColumn (detectDrops column), Schemas.scala:190-193 */
+  FILO_SCHEMA_CUMULATIVE = 1,       /* schema.hasCumulativeTemporalityColumn (detectDrops column), Schemas.scala:190-193 */
+  FILO_SCHEMA_LONG_VALUES = 2       /* the value column is a LongColumn: LongBinaryVector readers and the *L chunked functions
+                                       (RangeFunction.scala:300-339); functions without an L variant answer FILO_ERR_UNSUPPORTED */
 };
 
 /* query flags */
@@ -140,6 +153,10 @@ typedef struct {
 
 int32_t filo_ctx_create(int32_t device_ordinal, const filo_cfg* cfg /* NULL = defaults */, filo_ctx** out);
 void    filo_ctx_destroy(filo_ctx* ctx);
+/* Static arguments of the range function of the following queries on this ctx -- the reference's funcParams: Seq[StaticFuncArgs]
+ * (RangeFunction.generatorFor, RangeFunction.scala:283-313): quantile_over_time(arg0), holt_winters(arg0 = sf, arg1 = tf),
+ * predict_linear(arg0 = seconds).  Other functions ignore them. */
+int32_t filo_ctx_set_fn_args(filo_ctx* ctx, double arg0, double arg1);
 /* Copies the last error message of this ctx (thread-local when ctx is NULL) into buf; returns its length. */
 int32_t filo_last_error(filo_ctx* ctx, char* buf, int32_t len);
 

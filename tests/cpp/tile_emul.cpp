@@ -20,6 +20,7 @@ struct Chunk { std::vector<uint8_t> ts, vv, info; };
 struct SeriesData { std::vector<std::unique_ptr<Chunk>> chunks; std::vector<uint8_t> record; };
 
 static long g_wp_declined = 0, g_wp_series = 0;
+static int g_long_col = 0;          // 1: Long value column through LongBinaryVector.optimize (DDV / const DDV), 2: raw 64-bit longs
 static int g_jitter_ms = 0; static bool g_integral = false;      // irregular scrapes (DDV timestamps) / integral values (DoubleVector.optimize -> DDV longs)
 static void build_series(SeriesData& S, std::mt19937_64& rng, int rows, const std::vector<int>& chunk_rows, int64_t t0, int step_ms, int kind /*0 gauge 1 counter*/,
                          bool xor_enc, int nan_ppm, int reset_every) {
@@ -39,6 +40,11 @@ static void build_series(SeriesData& S, std::mt19937_64& rng, int rows, const st
     std::vector<double> cv(v.begin() + r0, v.begin() + r0 + n);
     if (nan_ppm && (int)(rng() % 1000000) < nan_ppm) cv[(size_t)n - 1] = std::nan("");          // stale marker at the chunk end
     c->ts = fo::enc::timestamps(ts.data() + r0, n);
+    if (g_long_col) {
+      std::vector<int64_t> lv((size_t)n);
+      for (int i = 0; i < n; ++i) lv[(size_t)i] = (int64_t)std::floor(v[(size_t)(r0 + i)] * (g_long_col == 2 ? 1e15 : (r0 % 3 == 1 ? 0.0 : 1.0)));      // some chunks constant (const DDV, slope 0)
+      c->vv = g_long_col == 2 ? fo::enc::rawLongs(lv.data(), n) : fo::enc::longs(lv.data(), n);
+    } else
     c->vv = xor_enc ? fo::enc::doublesXor(cv.data(), n, kind == 1) : fo::enc::doubles(cv.data(), n, kind == 1);
     c->info.assign(fo::csi::OffsetVectors + 16, 0);
     fo::setLong(c->info.data() + fo::csi::OffsetChunkID, fo::csi::chunkID(ts[(size_t)r0], (ts[(size_t)(r0 + n - 1)] + 1000) / 1000));
@@ -118,7 +124,7 @@ static void run_v2(const Launch& A, const V2Shape& sh, const int64_t* list, cons
       filo::scan_series_kernel_v2<decltype(cls)::value>(A.arena, A.rec_off, A.S, A.q, A.out, rec_cap, scratch, A.counters, A.derr, list, list_count);
     });
   };
-  switch (filo::fn_class_of(A.q.fn, A.q.cumulative)) {
+  switch (filo::fn_class_of(A.q.fn, A.q.cumulative, A.q.long_values)) {
     case filo::CLASS_SUM: body(std::integral_constant<int, filo::CLASS_SUM>{}); break;
     case filo::CLASS_MINMAX: body(std::integral_constant<int, filo::CLASS_MINMAX>{}); break;
     case filo::CLASS_COUNTER: body(std::integral_constant<int, filo::CLASS_COUNTER>{}); break;
@@ -140,7 +146,7 @@ static void run_agg_v2(const Launch& A, const V2Shape& sh, const int64_t* list, 
                                                      A.counters, A.derr, list, list_count);
     });
   };
-  switch (filo::fn_class_of(A.q.fn, A.q.cumulative)) {
+  switch (filo::fn_class_of(A.q.fn, A.q.cumulative, A.q.long_values)) {
     case filo::CLASS_SUM: body(std::integral_constant<int, filo::CLASS_SUM>{}); break;
     case filo::CLASS_MINMAX: body(std::integral_constant<int, filo::CLASS_MINMAX>{}); break;
     case filo::CLASS_COUNTER: body(std::integral_constant<int, filo::CLASS_COUNTER>{}); break;
@@ -158,7 +164,8 @@ int main(int argc, char** argv) {
   std::mt19937_64 rng(4242);
   long checked = 0; int cases = 0;
   struct Cfg { int kind = 0; bool xor_enc = true; int fn = 0; std::vector<int> chunks; int nan_ppm = 0, reset_every = 0; int64_t window = 300000; int nser = 1; int inclusive = 1;
-               int64_t start_off = 0, end_off = 0; int agg_op = 0; int grid = 1; int jitter = 0; bool integral = false; bool v2_only = false; bool no_junction = false; bool warp_decode = false; bool wp = false; bool hetero = false; };
+               int64_t start_off = 0, end_off = 0; int agg_op = 0; int grid = 1; int jitter = 0; bool integral = false; bool v2_only = false; bool no_junction = false; bool warp_decode = false; bool wp = false; bool hetero = false; int long_col = 0; double p0 = 0, p1 = 0; };
+  std::vector<Cfg> all_ext;
   const std::vector<Cfg> cfgs = {
     {0, true, filo::FN_RATE, {400, 80}, 200000, 0, 300000, 11, 1, 0, 0, 0, 2},           // C2: gauge, delta-temporality rate (CLASS_SUM), NaN stale markers
     {0, true, filo::FN_SUM, {150, 90}, 0, 0, 300000, 37, 1, -90000, 45000, 0, 2},        // several tiles per CTA, a partial last tile, windows before / after the data
@@ -213,8 +220,34 @@ int main(int argc, char** argv) {
     {0, true, filo::FN_RATE, {400, 80}, 100000, 0, 300000, 26, 1, 0, 0, filo::AGG_SUM, 2},   // fused sum: items of 5 series in shuffled order
     {1, true, filo::FN_RATE, {240, 240}, 0, 97, 300000, 17, 1, 0, 0, filo::AGG_MAX, 2},      // fused max over counters with resets
   };
+  // the remaining chunked range functions and the Long-column variants: window by window on the v2 kernel (eval_window_ext)
+  {
+    auto ext = [&](int fn, std::vector<int> chunks, int nan_ppm, int64_t window, int nser, int jitter, bool xor_enc, bool integral, int long_col, double p0, double p1, int inclusive = 1) {
+      Cfg c; c.kind = 0; c.xor_enc = xor_enc; c.fn = fn; c.chunks = chunks; c.nan_ppm = nan_ppm; c.window = window; c.nser = nser; c.inclusive = inclusive;
+      c.start_off = -30000; c.end_off = 30000; c.grid = 2; c.jitter = jitter; c.integral = integral; c.v2_only = true; c.long_col = long_col; c.p0 = p0; c.p1 = p1;
+      all_ext.push_back(c);
+    };
+    const int fns[] = {filo::FN_STDDEV, filo::FN_STDVAR, filo::FN_ZSCORE, filo::FN_CHANGES, filo::FN_QUANTILE, filo::FN_MAD, filo::FN_HOLT_WINTERS, filo::FN_PREDICT_LINEAR, filo::FN_PRESENT};
+    for (int fn : fns) {
+      const double p0 = fn == filo::FN_QUANTILE ? 0.73 : fn == filo::FN_HOLT_WINTERS ? 0.3 : 600.0, p1 = 0.1;
+      ext(fn, {100, 60, 40}, 400000, 300000, 5, 0, true, false, 0, p0, p1);                   // XOR doubles, NaN markers at chunk ends, windows over two chunks
+      ext(fn, {64, 64}, 0, 120000, 4, 3000, false, false, 0, p0, p1, 0);                        // raw doubles, jittered (DDV) timestamps, exclusive range start
+      ext(fn, {90, 50}, 0, 200000, 4, 0, false, true, 0, p0, p1);                               // integral doubles: DoubleLongWrap readers (DDV / const DDV)
+    }
+    ext(filo::FN_QUANTILE, {80, 80}, 300000, 300000, 3, 0, true, false, 0, -0.5, 0);          // q < 0 / q > 1
+    ext(filo::FN_QUANTILE, {80, 80}, 300000, 300000, 3, 0, true, false, 0, 1.5, 0);
+    ext(filo::FN_QUANTILE, {80, 80}, 0, 300000, 3, 0, true, false, 0, 0.0, 0);
+    ext(filo::FN_QUANTILE, {80, 80}, 0, 300000, 3, 0, true, false, 0, 1.0, 0);
+    const int lfns[] = {filo::FN_LAST, filo::FN_COUNT, filo::FN_SUM, filo::FN_AVG, filo::FN_MIN, filo::FN_MAX, filo::FN_STDDEV, filo::FN_STDVAR, filo::FN_CHANGES, filo::FN_QUANTILE,
+                        filo::FN_PREDICT_LINEAR, filo::FN_MAD};
+    for (int fn : lfns) {
+      ext(fn, {70, 50, 40}, 0, 240000, 4, 0, false, false, 1, fn == filo::FN_QUANTILE ? 0.4 : 120.0, 0);     // LongBinaryVector.optimize: DDV / const DDV
+      ext(fn, {70, 50}, 0, 150000, 3, 2000, false, false, 2, fn == filo::FN_QUANTILE ? 0.9 : 120.0, 0);       // raw 64-bit longs, jittered timestamps
+    }
+  }
   // `tile_emul <seed> fuzz <n>`: n random shapes on top of the fixed list (chunk counts / sizes, windows, offsets, functions, NaN and reset rates)
   std::vector<Cfg> all = cfgs;
+  all.insert(all.end(), all_ext.begin(), all_ext.end());
   if (argc > 3 && std::string(argv[2]) == "fuzz") {
     std::mt19937_64 fr(seed * 7919 + 13);
     const int n = std::atoi(argv[3]);
@@ -254,7 +287,7 @@ int main(int argc, char** argv) {
     const int64_t t0 = 1700000000000LL; const int step_ms = 15000;
     std::vector<SeriesData> SS((size_t)c.nser);
     std::vector<int64_t> rec_off((size_t)c.nser + 1, 0);
-    g_jitter_ms = c.jitter; g_integral = c.integral;
+    g_jitter_ms = c.jitter; g_integral = c.integral; g_long_col = c.long_col;
     for (int s = 0; s < c.nser; ++s) {
       std::vector<int> cr = c.chunks; int64_t ts0 = t0; bool xe = c.xor_enc;
       if (c.hetero) {      // series-dependent chunk split, start time and encoding (runs of equal shapes in between)
@@ -272,9 +305,9 @@ int main(int argc, char** argv) {
     q.start = t0 + c.start_off; q.step = 15000; q.end = t0 + (int64_t)(rows - 1) * step_ms + c.end_off; q.window = c.window; q.T = (int)((q.end - q.start) / q.step) + 1;
     if (q.end < q.start) q.end = q.start;
     q.T = (int)((q.end - q.start) / q.step) + 1;
-    q.fn = c.fn; q.cumulative = c.kind == 1; q.inclusive = c.inclusive;
+    q.fn = c.fn; q.cumulative = c.kind == 1; q.inclusive = c.inclusive; q.long_values = c.long_col ? 1 : 0; q.p0 = c.p0; q.p1 = c.p1;
     if (c.agg_op && q.T > filo::TILE_AGG_ACC * filo::TILE_THREADS) c.agg_op = 0;      // the fused tile path serves T <= 512 (filo_query picks the other kernels beyond)
-    const bool ctr = filo::fn_class_of(q.fn, q.cumulative) == filo::CLASS_COUNTER;
+    const bool ctr = filo::fn_class_of(q.fn, q.cumulative, q.long_values) == filo::CLASS_COUNTER;
     const uint32_t wrows = (uint32_t)(q.window / q.step) + 1;
     filo::TileSmem L = filo::tile_layout(max_rec, (uint32_t)rows, (uint32_t)q.T, ctr ? 0u : 2 * wrows + 16, ctr, c.warp_decode);
     if (c.no_junction) L.opts &= ~filo::TILE_OPT_JUNCTION;
@@ -283,8 +316,9 @@ int main(int argc, char** argv) {
     std::vector<double> ref((size_t)c.nser * q.T); std::vector<int64_t> oracle_rows((size_t)c.nser, 0);
     for (int s = 0; s < c.nser; ++s) {
       fo::Series os; for (auto& ch : SS[(size_t)s].chunks) os.infos.push_back(ch->info.data());
+      os.longCol = c.long_col != 0;
       fo::QueryStats st;
-      fo::periodicSamples(os, oracle_fn(q.fn), q.cumulative != 0, q.start, q.step, q.end, q.window, fo::QueryConfig{q.inclusive != 0}, ref.data() + (size_t)s * q.T, &st);
+      fo::periodicSamples(os, oracle_fn(q.fn), q.cumulative != 0, q.start, q.step, q.end, q.window, fo::QueryConfig{q.inclusive != 0}, ref.data() + (size_t)s * q.T, &st, q.p0, q.p1);
       oracle_rows[(size_t)s] = st.samplesScanned;
     }
     std::vector<double> out((size_t)c.nser * q.T, -777.0);
@@ -293,7 +327,7 @@ int main(int argc, char** argv) {
     if (!c.agg_op) {
       V2Shape sh{max_rec, rows, (int)c.chunks.size(), false, false};
       for (auto& S : SS) { filo::RecordHeader h; std::memcpy(&h, S.record.data(), sizeof h); sh.any_nonconst_ts |= !(h.flags & filo::REC_ALL_TS_CONST); sh.any_drop |= (h.flags & filo::REC_ANY_DROP) != 0; }
-      const int cls = filo::fn_class_of(q.fn, q.cumulative);
+      const int cls = filo::fn_class_of(q.fn, q.cumulative, q.long_values);
       const bool tile_ok = !c.v2_only && (cls == filo::CLASS_SUM || cls == filo::CLASS_COUNTER);
       if (tile_ok && c.wp && cls == filo::CLASS_SUM) {
         const bool alias = filo::wp_max_items((uint32_t)c.chunks.size(), (uint32_t)q.T, wrows) <= 64 && !(ci % 5 == 0);      // as filo_query decides (every fifth case keeps O apart)

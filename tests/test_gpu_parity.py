@@ -4,6 +4,7 @@ Per-series results (PeriodicSamplesMapper) must be BIT-EXACT: the kernels follow
 compiled without FMA contraction.  Across-series aggregates: min/max/count bit-exact; sum/avg within 1e-9 relative (the
 reference folds in arrival order, the device folds per work item then per group — SURVEY.md §7 "FP parity")."""
 import math
+import zlib
 import numpy as np
 import pytest
 
@@ -85,7 +86,7 @@ CASES = [
 def test_per_series_bit_exact(gpu, oracle, case):
     capi, ctx = gpu; o = oracle
     kind, val_mode, jitter, cumulative, nan_frac = case
-    rng = np.random.default_rng(hash(case) & 0xffff)
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()))      # reproducible across processes (str hashes are salted)
     st = build_store(o, rng, 40, kind, val_mode, jitter, cumulative, nan_frac)
     nch, addrs = st.all_info_addrs()
     tab = ctx.load_series(nch, addrs, schema_flags=capi.SCHEMA_CUMULATIVE if cumulative else 0)
@@ -521,3 +522,128 @@ def test_hist_sum_over_time_and_delta_schema(gpu, oracle):
         np.testing.assert_allclose(agot[m], aexp[m], rtol=1e-9, atol=0)
         np.testing.assert_allclose(qgot[~np.isnan(qexp)], qexp[~np.isnan(qexp)], rtol=1e-9, atol=0)
     tab2.free()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the remaining chunked range functions, Long value columns, masked vectors
+# ------------------------------------------------------------------------------------------------------------------
+EXT_FNS = [("FN_STDDEV_OVER_TIME", ()), ("FN_STDVAR_OVER_TIME", ()), ("FN_ZSCORE", ()), ("FN_CHANGES", ()), ("FN_QUANTILE_OVER_TIME", (0.73,)),
+           ("FN_QUANTILE_OVER_TIME", (0.0,)), ("FN_QUANTILE_OVER_TIME", (1.0,)), ("FN_QUANTILE_OVER_TIME", (-0.1,)), ("FN_QUANTILE_OVER_TIME", (1.5,)),
+           ("FN_MAD_OVER_TIME", ()), ("FN_HOLT_WINTERS", (0.3, 0.1)), ("FN_PREDICT_LINEAR", (600.0,)), ("FN_PRESENT_OVER_TIME", ())]
+EXT_CASES = [("gauge", 1, 0, False, 0.05), ("gauge", 2, 3000, False, 0.02), ("intcounter", 0, 0, False, 0.0), ("linear", 0, 200, False, 0.0)]
+
+
+@pytest.mark.parametrize("case", EXT_CASES, ids=[("%s-v%d-j%d-%s-nan%g" % c) for c in EXT_CASES])
+def test_extended_range_functions(gpu, oracle, case):
+    """stddev / stdvar / zscore / changes / quantile / mad / holt_winters / predict_linear / present_over_time
+    (AggrOverTimeFunctions.scala:1082-1604, RangeFunction.scala:725-748): bit-exact per series against the oracle."""
+    capi, ctx = gpu; o = oracle
+    kind, val_mode, jitter, cumulative, nan_frac = case
+    rng = np.random.default_rng(zlib.crc32(repr(case).encode()))
+    st = build_store(o, rng, 12, kind, val_mode, jitter, cumulative, nan_frac, rows=300, chunks=(140, 100, 60))
+    nch, addrs = st.all_info_addrs()
+    tab = ctx.load_series(nch, addrs)
+    t0 = 1_700_000_000_000
+    queries = [(t0 + 300000, 15000, t0 + 299 * 15000, 300000), (t0 - 50000, 47000, t0 + 320 * 15000, 111111)]
+    try:
+        for (start, step, end, window) in queries:
+            for name, args in EXT_FNS:
+                ctx.set_fn_args(*args)
+                got = ctx.query(tab, getattr(capi, name), start, step, end, window)
+                exp = st.query(getattr(o, name), start, step, end, window, params=args)
+                assert_same(got, exp, "%s %s%s q=%s" % (case, name, args, (start, step, end, window)))
+                assert ctx.last_stats["samples_scanned"] == st.last_stats["samples_scanned"]
+        ctx.set_fn_args(1.5, 0.1)
+        with pytest.raises(capi.FiloError) as ei:
+            ctx.query(tab, capi.FN_HOLT_WINTERS, *queries[0])
+        assert ei.value.code == capi.ERR_INVALID_ARG
+    finally:
+        ctx.set_fn_args(0.0, 0.0)
+        tab.free()
+
+
+LONG_FNS = [("FN_LAST", ()), ("FN_COUNT_OVER_TIME", ()), ("FN_SUM_OVER_TIME", ()), ("FN_AVG_OVER_TIME", ()), ("FN_MIN_OVER_TIME", ()), ("FN_MAX_OVER_TIME", ()),
+            ("FN_STDDEV_OVER_TIME", ()), ("FN_STDVAR_OVER_TIME", ()), ("FN_CHANGES", ()), ("FN_QUANTILE_OVER_TIME", (0.4,)), ("FN_PREDICT_LINEAR", (120.0,)),
+            ("FN_MAD_OVER_TIME", ())]
+
+
+@pytest.mark.parametrize("shape", ["ddv", "const", "flat", "raw"])
+def test_long_column_functions(gpu, oracle, shape):
+    """Long value columns: LongBinaryVector readers (DDV, const DDV, raw 64-bit) and the *L chunked functions
+    (AggrOverTimeFunctions.scala:60-116,574-585,924-938,1019-1028,1144-1183,1211-1225,1322-1359), bit-exact."""
+    capi, ctx = gpu; o = oracle
+    rng = np.random.default_rng({"ddv": 1, "const": 2, "flat": 3, "raw": 4}[shape])
+    t0 = 1_700_000_000_000; rows = 260
+    st = o.Store()
+    for s in range(10):
+        ts = t0 + np.arange(rows, dtype=np.int64) * 15000 + (rng.integers(-2000, 2001, rows) if s % 2 else 0)
+        if shape == "ddv": v = (np.cumsum(rng.integers(0, 50, rows)) + 1000 * s).astype(np.int64)
+        elif shape == "const": v = (7 * s + (3 + s) * np.arange(rows)).astype(np.int64)
+        elif shape == "flat": v = np.full(rows, 42 + s, np.int64)
+        else: v = rng.integers(-2 ** 62, 2 ** 62, rows).astype(np.int64)
+        si = st.add_series()
+        for a, b in ((0, 120), (120, 200), (200, rows)):
+            st.add_chunk_longs(si, ts[a:b], v[a:b], raw=(shape == "raw"))
+    nch, addrs = st.all_info_addrs()
+    tab = ctx.load_series(nch, addrs, schema_flags=capi.SCHEMA_LONG_VALUES)
+    try:
+        for (start, step, end, window) in [(t0 + 300000, 15000, t0 + (rows - 1) * 15000, 300000), (t0 - 50000, 47000, t0 + (rows + 20) * 15000, 111111)]:
+            for name, args in LONG_FNS:
+                ctx.set_fn_args(*args)
+                got = ctx.query(tab, getattr(capi, name), start, step, end, window)
+                exp = st.query(getattr(o, name), start, step, end, window, long_column=True, params=args)
+                assert_same(got, exp, "long %s %s%s q=%s" % (shape, name, args, (start, step, end, window)))
+        with pytest.raises(capi.FiloError) as ei:      # no chunked L variant: the caller keeps the iterating JVM path
+            ctx.query(tab, capi.FN_RATE, t0, 15000, t0 + 600000, 300000)
+        assert ei.value.code == capi.ERR_UNSUPPORTED
+    finally:
+        ctx.set_fn_args(0.0, 0.0)
+        tab.free()
+
+
+def _masked(inner, n, na_rows=()):
+    """BitmapMaskAppendableVector layout (BinaryVector.scala:614-660): +0 numBytes, +4 wire BINSIMPLE/PRIMITIVE, +8 offset of the
+    subvector (12 + bitmap bytes), +12 NA bitmap in 64-bit words, then the subvector."""
+    inner = np.ascontiguousarray(inner, np.uint8)
+    bm = np.zeros((n + 63) // 64, np.uint64)
+    for r in na_rows: bm[r >> 6] |= np.uint64(1) << np.uint64(r & 63)
+    hdr = np.zeros(12, np.uint8)
+    hdr[0:4] = np.frombuffer(np.int32(8 + bm.nbytes + inner.size).tobytes(), np.uint8)
+    hdr[4] = 0x06; hdr[5] = 0x00
+    hdr[8:12] = np.frombuffer(np.int32(12 + bm.nbytes).tobytes(), np.uint8)
+    return np.concatenate([hdr, bm.view(np.uint8), inner])
+
+
+def test_masked_vectors(gpu, oracle):
+    """Masked (NA-bitmap) vectors: MaskedDoubleDataReader / MaskedLongDataReader delegate to the subvector (DoubleVector.scala:397-417,
+    LongBinaryVector.scala:270-293, BinaryVector.scala:193-227); the counter drop bit lives on the outer vector."""
+    capi, ctx = gpu; o = oracle
+    rng = np.random.default_rng(77)
+    t0 = 1_700_000_000_000; rows = 200
+    st = o.Store()
+    for s in range(8):
+        ts = t0 + np.arange(rows, dtype=np.int64) * 15000 + (rng.integers(-1500, 1501, rows) if s % 2 else 0)
+        v = np.cumsum(np.maximum(0, 15 + rng.normal(0, 3, rows)))
+        if s % 3 == 0:
+            v[120:] = v[120:] - v[120] + 1.0                       # a counter reset inside the second chunk
+        v[rng.random(rows) < 0.03] = NaN
+        si = st.add_series()
+        for a, b in ((0, 110), (110, rows)):
+            tsv = o.encode_timestamps(ts[a:b]) if s % 4 else _masked(o.encode_timestamps(ts[a:b]), b - a)
+            inner = o.encode_doubles(v[a:b], detect_drops=True, mode=o.VAL_RAW)
+            drop = bool(o.Vec(inner).dropped())
+            inner = np.array(inner, np.uint8); inner[7] &= 0x7f        # the appender marks the drop on the OUTER vector
+            mv = _masked(inner, b - a, na_rows=[int(i) for i in np.nonzero(np.isnan(v[a:b]))[0]])
+            if drop: mv[7] |= 0x80
+            st.add_chunk_raw(si, int(ts[a]), int(ts[b - 1]), b - a, tsv, mv)
+    nch, addrs = st.all_info_addrs()
+    tab = ctx.load_series(nch, addrs, schema_flags=capi.SCHEMA_CUMULATIVE)
+    try:
+        for (start, step, end, window) in [(t0 + 300000, 15000, t0 + (rows - 1) * 15000, 300000), (t0 - 50000, 47000, t0 + (rows + 20) * 15000, 111111)]:
+            for name in ALL_FNS:
+                got = ctx.query(tab, getattr(capi, name), start, step, end, window)
+                exp = st.query(getattr(o, name), start, step, end, window, cumulative=True)
+                assert_same(got, exp, "masked %s q=%s" % (name, (start, step, end, window)))
+                assert ctx.last_stats["samples_scanned"] == st.last_stats["samples_scanned"]
+    finally:
+        tab.free()
