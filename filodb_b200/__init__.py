@@ -6,3 +6,4 @@ mirrors the reference's operator surface (PeriodicSamplesMapper / AggregateMapRe
 There is no CPU fallback: importing `capi` without the built library raises.
 """
 from . import capi  # noqa: F401
+from . import exec as exec_  # noqa: F401  (operator mirror: PeriodicSamplesMapper / AggregateMapReduce / FusedGpuExec)

@@ -15,9 +15,10 @@ SCHEMA_LONG_VALUES = 2
 Q_PARTIAL = 1
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CORRUPT_VECTOR, ERR_UNSUPPORTED, ERR_QUERY_LIMIT, ERR_BAD_QUERY, ERR_OOM = 0, -1, -2, -3, -4, -5, -6, -7
 
-EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_ctx_set_fn_args", "filo_last_error", "filo_load_series", "filo_synth_table",
+EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_ctx_set_fn_args", "filo_ctx_check", "filo_last_error", "filo_load_series", "filo_synth_table",
            "filo_table_set_groups", "filo_table_get_info", "filo_table_read_record", "filo_table_read_arena", "filo_table_free",
-           "filo_num_windows", "filo_query", "filo_query_device", "filo_scan_series", "filo_query_hist", "filo_host_register", "filo_host_unregister", "filo_present_partials"]
+           "filo_num_windows", "filo_query", "filo_query_device", "filo_scan_series", "filo_query_hist", "filo_host_register", "filo_host_unregister", "filo_present_partials",
+           "filo_result_max_containers", "filo_encode_result_device", "filo_encode_result"]
 
 
 class Cfg(C.Structure):
@@ -72,6 +73,11 @@ def _sig(L):
     i32, i64, vp = C.c_int32, C.c_int64, C.c_void_p
     L.filo_ctx_create.restype = i32; L.filo_ctx_create.argtypes = [i32, C.POINTER(Cfg), C.POINTER(vp)]
     L.filo_ctx_destroy.restype = None; L.filo_ctx_destroy.argtypes = [vp]
+    L.filo_ctx_check.restype = i32; L.filo_ctx_check.argtypes = [vp]
+    L.filo_result_max_containers.restype = i64; L.filo_result_max_containers.argtypes = [i64, i32]
+    L.filo_encode_result.restype = i32; L.filo_encode_result.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, vp, vp, vp, C.POINTER(i64), C.POINTER(i64)]
+    L.filo_encode_result_device.restype = i32
+    L.filo_encode_result_device.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, vp, vp, vp, C.POINTER(i64), C.POINTER(i64), vp]
     L.filo_ctx_set_fn_args.restype = i32; L.filo_ctx_set_fn_args.argtypes = [vp, C.c_double, C.c_double]
     L.filo_last_error.restype = i32; L.filo_last_error.argtypes = [vp, C.c_char_p, i32]
     L.filo_load_series.restype = i32
@@ -185,6 +191,21 @@ class Context:
             buf = C.create_string_buffer(1024)
             lib().filo_last_error(self.h, buf, 1024)
             raise FiloError(rc, buf.value.decode())
+
+    def check(self):
+        """filo_ctx_check: waits for the stats-less device queries of this ctx and raises their first device-side error."""
+        self._check(lib().filo_ctx_check(self.h))
+
+    def encode_result(self, values, start, step, end, container_ts_ms=0):
+        """filo_encode_result: rows of `values` [n_rows, T] -> (containers uint8[n, 4096], rows_serialized, start_record_no, first_container)."""
+        v = np.ascontiguousarray(values, np.float64)
+        n, T = v.shape
+        cap = int(lib().filo_result_max_containers(n, T))
+        out = np.zeros((max(cap, 1), 4096), np.uint8)
+        rs = np.zeros(n, np.int32); sr = np.zeros(n, np.int32); fc = np.zeros(n, np.int64)
+        nc = C.c_int64(); nr = C.c_int64()
+        self._check(lib().filo_encode_result(self.h, _p(v), n, start, step, end, container_ts_ms, _p(out), out.size, _p(rs), _p(sr), _p(fc), C.byref(nc), C.byref(nr)))
+        return out[:nc.value].copy(), rs, sr, fc
 
     def set_fn_args(self, arg0=0.0, arg1=0.0):
         """funcParams of the following queries (quantile; sf, tf; duration)."""

@@ -29,6 +29,12 @@ struct filo_ctx {
   std::mutex err_mu;
   std::string err;
   double fn_args[2] = {0.0, 0.0};      // static arguments of the range function (filo_ctx_set_fn_args)
+  // device error words of non-synchronising queries (filo_query_device with stats == NULL): copied into pinned slots on the query's
+  // stream and surfaced by the next call on this ctx that finds them complete, or by filo_ctx_check
+  struct ErrSlot { int* h = nullptr; cudaEvent_t ev = nullptr; bool pending = false; };
+  std::mutex errslot_mu;
+  ErrSlot errslots[16];
+  int errslot_next = 0;
   // filo_scan_series pipeline slots (pinned staging + device buffers), kept across calls
   struct ScanSlot {
     uint8_t* h_in = nullptr; size_t h_in_cap = 0;        // pinned: records of the batch
@@ -131,6 +137,7 @@ void filo_ctx_destroy(filo_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  for (auto& sl : ctx->errslots) { if (sl.ev) { cudaEventSynchronize(sl.ev); cudaEventDestroy(sl.ev); } if (sl.h) cudaFreeHost(sl.h); }
   for (auto& r : ctx->ranges) cudaHostUnregister((void*)r.base);
   for (auto& sl : ctx->scan) {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
@@ -589,6 +596,31 @@ extern "C" int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t
                                      filo_stats* stats) {
   return query_device_impl(ctx, t, fn, start, step, end, window, agg, k, flags, d_out_values, d_out_aux, cuda_stream, stats, nullptr);
 }
+namespace {
+struct EventPair {      // timing events of one query, destroyed on every return path
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ~EventPair() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+};
+}
+static int32_t report_device_error(filo_ctx* ctx, const int herr[4], int64_t series_base);
+// completed error words of earlier non-synchronising queries; wait = also wait for the ones still in flight
+static int32_t poll_async_errors(filo_ctx* ctx, bool wait) {
+  std::lock_guard<std::mutex> g(ctx->errslot_mu);
+  int32_t rc = FILO_OK;
+  for (auto& sl : ctx->errslots) {
+    if (!sl.pending) continue;
+    cudaError_t e = wait ? cudaEventSynchronize(sl.ev) : cudaEventQuery(sl.ev);
+    if (e == cudaErrorNotReady) { cudaGetLastError(); continue; }
+    sl.pending = false;
+    if (e != cudaSuccess) { if (rc == FILO_OK) rc = fail(ctx, FILO_ERR_CUDA, std::string("asynchronous query: ") + cudaGetErrorString(e)); continue; }
+    if (sl.h[0] && rc == FILO_OK) rc = report_device_error(ctx, sl.h, 0);
+  }
+  return rc;
+}
+extern "C" int32_t filo_ctx_check(filo_ctx* ctx) {
+  if (!ctx) return fail(nullptr, FILO_ERR_INVALID_ARG, "ctx is null");
+  return poll_async_errors(ctx, true);
+}
 static int32_t report_device_error(filo_ctx* ctx, const int herr[4], int64_t series_base) {
   const char* what = herr[0] == 4 ? "series needs more decode scratch than the table statistics promised" : "CorruptVector on device";
   return fail(ctx, FILO_ERR_CORRUPT_VECTOR, std::string(what) + " (code " + std::to_string(herr[0]) + ") at series " +
@@ -621,6 +653,7 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
   if ((flags & FILO_Q_PARTIAL) && agg != FILO_AGG_NONE && agg != FILO_AGG_TOPK && agg != FILO_AGG_BOTTOMK && !d_out_aux)
     return fail(ctx, FILO_ERR_INVALID_ARG, "partial aggregates need out_aux (counts)");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  { const int32_t prc = poll_async_errors(ctx, false); if (prc != FILO_OK) return prc; }      // an earlier stats == NULL query failed on the device
   cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
   QueryParams q{};
   q.start = start; q.step = adjustedStep; q.end = end; q.window = window; q.T = filo_num_windows(start, adjustedStep, end);
@@ -633,8 +666,9 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
   int* d_err = nullptr; unsigned long long* d_counters = nullptr;
   CUDA_TRY(ctx, tmp.alloc((void**)&d_err, 16)); CUDA_TRY(ctx, tmp.alloc((void**)&d_counters, 16));
   CUDA_TRY(ctx, cudaMemsetAsync(d_err, 0, 16, s)); CUDA_TRY(ctx, cudaMemsetAsync(d_counters, 0, 16, s));
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (stats) { CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1)); }
+  EventPair evp;
+  if (stats) { CUDA_TRY(ctx, cudaEventCreate(&evp.e0)); CUDA_TRY(ctx, cudaEventCreate(&evp.e1)); }
+  cudaEvent_t& e0 = evp.e0; cudaEvent_t& e1 = evp.e1;
 
   // ---- kernel selection.  v2 (TMA-staged, blocked reductions) needs its whole per-warp working set in shared memory;
   //      v1 (generic, global-memory record reads, optional global scratch) takes everything else.  FILO_KERNEL=v1 forces v1.
@@ -803,10 +837,23 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
     CUDA_TRY(ctx, cudaMemcpyAsync(herr, d_err, 16, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaMemcpyAsync(hc, d_counters, 16, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     stats->kernel_ns = (int64_t)((double)ms * 1e6); stats->samples_scanned = (int64_t)hc[0]; stats->bytes_scanned = (int64_t)hc[1];
     stats->kernel_launches = launches; stats->h2d_bytes = 0; stats->d2h_bytes = 0;
     if (herr[0]) return report_device_error(ctx, herr, 0);
+  }
+  if (!stats && !sink) {      // non-synchronising call: the error word still reaches the caller (next call on this ctx, or filo_ctx_check)
+    std::lock_guard<std::mutex> g(ctx->errslot_mu);
+    filo_ctx::ErrSlot& sl = ctx->errslots[ctx->errslot_next];
+    ctx->errslot_next = (ctx->errslot_next + 1) % 16;
+    if (!sl.h) { CUDA_TRY(ctx, cudaMallocHost((void**)&sl.h, 16)); CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming)); }
+    if (sl.pending) {           // the ring wrapped: the oldest query must have finished by now
+      CUDA_TRY(ctx, cudaEventSynchronize(sl.ev)); sl.pending = false;
+      if (sl.h[0]) return report_device_error(ctx, sl.h, 0);
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(sl.h, d_err, 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaEventRecord(sl.ev, s));
+    sl.pending = true;
   }
   if (sink) {           // asynchronous caller: the words land in pinned memory when the stream reaches this point
     sink->launches = launches;
@@ -1178,7 +1225,8 @@ extern "C" int32_t filo_query_hist(filo_ctx* ctx, const filo_table* t, int32_t f
   int* d_err = nullptr; unsigned long long* d_counters = nullptr;
   CUDA_TRY(ctx, tmp.alloc((void**)&d_err, 16)); CUDA_TRY(ctx, tmp.alloc((void**)&d_counters, 16));
   CUDA_TRY(ctx, cudaMemsetAsync(d_err, 0, 16, s)); CUDA_TRY(ctx, cudaMemsetAsync(d_counters, 0, 16, s));
-  cudaEvent_t e0, e1; CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1));
+  EventPair evp; CUDA_TRY(ctx, cudaEventCreate(&evp.e0)); CUDA_TRY(ctx, cudaEventCreate(&evp.e1));
+  cudaEvent_t& e0 = evp.e0; cudaEvent_t& e1 = evp.e1;
   const int64_t work = fused ? t->n_items : t->n_series;
   ScanLaunch L{t->d_arena, t->d_rec_off, t->n_series, q, nullptr, 0, 0, d_counters, d_err, 1, s};
   const int ctas_per_sm = (int)std::max<size_t>(1, (size_t)(228 * 1024) / (smem + 2048));
@@ -1214,7 +1262,7 @@ extern "C" int32_t filo_query_hist(filo_ctx* ctx, const filo_table* t, int32_t f
   if (out_values) CUDA_TRY(ctx, cudaMemcpyAsync(out_values, d_out, (size_t)rows * T * nb * 8, cudaMemcpyDeviceToHost, s));
   if (out_quantile) CUDA_TRY(ctx, cudaMemcpyAsync(out_quantile, d_q, (size_t)rows * T * 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(ctx, cudaStreamSynchronize(s));
-  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
   if (stats) {
     stats->kernel_ns = (int64_t)((double)ms * 1e6); stats->samples_scanned = (int64_t)hc[0]; stats->bytes_scanned = (int64_t)hc[1];
     stats->kernel_launches = fused ? 2 : 1; stats->h2d_bytes = 0;

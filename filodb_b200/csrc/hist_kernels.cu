@@ -262,7 +262,15 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
           }
           if (has && q.fn == FN_RATE) for (int b = 0; b < nb; ++b) hv[b] = hv[b] / (double)(wEnd - wStart) * 1000.0;   // RateFunctions.scala:481 (raw windowStart)
           if (!agg) { double* o = out + ((size_t)sid * q.T + k) * nb; for (int b = 0; b < nb; ++b) o[b] = has ? hv[b] : NaNv; }
-          else if (has) { for (int b = 0; b < nb; ++b) acc[(size_t)k * nb + b] += hv[b]; any[k] = 1; }
+          else if (has) {                                                     // HistSumRowAggregator: copy the first, MutableHistogram.add the others
+            const bool firstm = any[k] == 0; double mx = 0.0;
+            for (int b = 0; b < nb; ++b) {
+              double nv = acc[(size_t)k * nb + b] + hv[b];
+              if (!firstm) { if (nv < mx || nv != nv) nv = mx; else if (nv > mx) mx = nv; }
+              acc[(size_t)k * nb + b] = nv;
+            }
+            any[k] = firstm ? 1 : 2;
+          }
         }
         __syncthreads();
         continue;
@@ -369,16 +377,25 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
         if (!agg) out[((size_t)sid * q.T + k) * nb + b] = r;                  // an empty histogram is returned as NaN buckets
         else if (has) {                                                       // HistSumRowAggregator: empty histograms are skipped
           acc[i] += r;                                                        // (MutableHistogram.addNoCorrection: NaN-seeded sums start at 0)
-          if (b == 0) any[k] = 1;
+          if (b == 0) any[k] = any[k] ? 2 : 1;                                // 1: the item's first histogram for this window (copied), 2: a further one
         }
       }
       __syncthreads();
+      if (agg) {      // MutableHistogram.add = addNoCorrection + makeMonotonic for every histogram but the first (Histogram.scala:428-449)
+        for (int k = tid; k < q.T; k += HIST_THREADS) {
+          if (any[k] == 2 && W[k].hi_t > W[k].lo_t) {
+            double mx = 0.0; double* a = acc + (size_t)k * nb;
+            for (int b = 0; b < nb; ++b) { if (a[b] < mx || a[b] != a[b]) a[b] = mx; else if (a[b] > mx) mx = a[b]; }
+          }
+        }
+        __syncthreads();
+      }
       HPROF(6)                                             // (window, bucket) rates
     }
     if (agg) {
       double* pv = pval + (size_t)it * q.T * nb; uint8_t* pa = pany + (size_t)it * q.T;
       for (int i = tid; i < q.T * nb; i += HIST_THREADS) pv[i] = acc[i];
-      for (int i = tid; i < q.T; i += HIST_THREADS) pa[i] = any[i];
+      for (int i = tid; i < q.T; i += HIST_THREADS) pa[i] = any[i] ? 1 : 0;
       __syncthreads();
       HPROF(7)                                             // item partial written
     }
@@ -388,8 +405,8 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
 }
 
 
-// Fold the partial rows of each group in item order (deterministic), then MutableHistogram.makeMonotonic (Histogram.scala:440-449)
-// and Histogram.quantile (:65-108, non-exponential buckets).  Thread per (group, window).
+// Fold the partial rows of each group in item order (deterministic), MutableHistogram.add per item (Histogram.scala:428-449),
+// then Histogram.quantile (:65-108, non-exponential buckets).  Thread per (group, window).
 __global__ void hist_merge_kernel(const double* __restrict__ pval, const uint8_t* __restrict__ pany, const int64_t* __restrict__ gis,
                                   int n_groups, int T, int nb, const double* __restrict__ tops, double qtl,
                                   double* __restrict__ out_values /* [G][T][nb] or null */, double* __restrict__ out_q /* [G][T] or null */) {
@@ -399,16 +416,17 @@ __global__ void hist_merge_kernel(const double* __restrict__ pval, const uint8_t
   const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
   double v[64]; bool any = false;
   for (int b = 0; b < nb; ++b) v[b] = 0.0;
+  // ReduceAggregateExec over the items' partial aggregates with the same reduceAggregate: the first one is copied, every further one
+  // is added and the sum made monotonic (HistSumRowAggregator.scala:25-36, Histogram.scala:428-449)
   for (int64_t it = gis[g]; it < gis[g + 1]; ++it) {
     if (!pany[(size_t)it * T + k]) continue;
-    any = true;
     const double* pv = pval + ((size_t)it * T + k) * nb;
-    for (int b = 0; b < nb; ++b) v[b] += pv[b];
+    if (!any) { for (int b = 0; b < nb; ++b) v[b] = pv[b]; any = true; continue; }
+    double mx = 0.0;
+    for (int b = 0; b < nb; ++b) { double nv = v[b] + pv[b]; if (nv < mx || nv != nv) nv = mx; else if (nv > mx) mx = nv; v[b] = nv; }
   }
   double qv = NaNv;
   if (any) {
-    double mx = 0.0;                                                         // makeMonotonic
-    for (int b = 0; b < nb; ++b) { if (v[b] < mx || v[b] != v[b]) v[b] = mx; else if (v[b] > mx) mx = v[b]; }
     if (qtl == qtl) {                                                        // Histogram.quantile
       const double top = v[nb - 1];
       if (qtl < 0) qv = __longlong_as_double(0xfff0000000000000LL);

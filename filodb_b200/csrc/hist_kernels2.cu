@@ -96,7 +96,7 @@ hist_scan2_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__
       __syncthreads();
       H2PROF(4)                                           // corrections inside and across chunks
       int j = 0;
-      for (int k = tid; k < q.T; k += H2_THREADS, ++j) if (h2_window(k, X, pv)) anyb |= 1u << j;
+      for (int k = tid; k < q.T; k += H2_THREADS, ++j) if (h2_window(k, X, pv, !((anyb >> j) & 1u))) anyb |= 1u << j;
       __syncthreads();                                   // the series' rows and record are dead
       H2PROF(5)                                           // windows: descriptors + rates + partial-row update
     }
@@ -106,8 +106,8 @@ hist_scan2_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__
   if (tid == 0 && (rows_scanned | bytes_scanned)) { atomicAdd(&d_counters[0], (unsigned long long)rows_scanned); atomicAdd(&d_counters[1], (unsigned long long)bytes_scanned); }
 }
 
-// Fold the partial rows of each group in item order (deterministic), then MutableHistogram.makeMonotonic (Histogram.scala:440-449)
-// and Histogram.quantile (:65-108, non-exponential buckets).  Thread per (group, window); partial rows are bucket-major.
+// Fold the partial rows of each group in item order (deterministic), MutableHistogram.add per item (Histogram.scala:428-449),
+// then Histogram.quantile (:65-108, non-exponential buckets).  Thread per (group, window); partial rows are bucket-major.
 __global__ void hist_merge2_kernel(const double* __restrict__ pval, const uint8_t* __restrict__ pany, const int64_t* __restrict__ gis,
                                    int n_groups, int T, int nb, const double* __restrict__ tops, double qtl,
                                    double* __restrict__ out_values /* [G][T][nb] or null */, double* __restrict__ out_q /* [G][T] or null */) {
@@ -117,16 +117,17 @@ __global__ void hist_merge2_kernel(const double* __restrict__ pval, const uint8_
   const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
   double v[64]; bool any = false;
   for (int b = 0; b < nb; ++b) v[b] = 0.0;
+  // ReduceAggregateExec over the items' partial aggregates with the same reduceAggregate: the first one is copied, every further one
+  // is added and the sum made monotonic (HistSumRowAggregator.scala:25-36, Histogram.scala:428-449)
   for (int64_t it = gis[g]; it < gis[g + 1]; ++it) {
     if (!pany[(size_t)it * T + k]) continue;
-    any = true;
     const double* pv = pval + (size_t)it * T * nb + k;
-    for (int b = 0; b < nb; ++b) v[b] += pv[(size_t)b * T];
+    if (!any) { for (int b = 0; b < nb; ++b) v[b] = pv[(size_t)b * T]; any = true; continue; }
+    double mx = 0.0;
+    for (int b = 0; b < nb; ++b) { double nv = v[b] + pv[(size_t)b * T]; if (nv < mx || nv != nv) nv = mx; else if (nv > mx) mx = nv; v[b] = nv; }
   }
   double qv = NaNv;
   if (any) {
-    double mx = 0.0;                                                         // makeMonotonic
-    for (int b = 0; b < nb; ++b) { if (v[b] < mx || v[b] != v[b]) v[b] = mx; else if (v[b] > mx) mx = v[b]; }
     if (qtl == qtl) {                                                        // Histogram.quantile
       const double top = v[nb - 1];
       if (qtl < 0) qv = __longlong_as_double(0xfff0000000000000LL);

@@ -317,8 +317,8 @@ FILO_HDI double h2_div_window(double x, double fdiv, double frcp) {
 
 // P7 (thread per window): chunk set, row ranges, lowest / highest sample (HistogramRateFunctionBase.addTimeChunks, RateFunctions.scala:349-364),
 // then extrapolatedRate per bucket (:72-111, :366-407) folded into the item's partial row pv[b * T + k] (HistSumRowAggregator: empty
-// histograms are skipped).  Returns true when the window produced a histogram.
-FILO_HD inline bool h2_window(int k, const H2Ctx& X, double* pv) {
+// histograms are skipped; `first`: no series of the item has produced a histogram for this window yet).  Returns true when the window produced a histogram.
+FILO_HD inline bool h2_window(int k, const H2Ctx& X, double* pv, bool first) {
   const H2Ctl* C = X.ctl(); const int64_t* cv = X.cv(); const int64_t* tss = X.ts(); const int64_t* PT = X.PT(); const int64_t* PD = X.PD();
   const QueryParams& q = X.q; const int n = C->n, nb = X.nb, pitch = X.L.pitch;
   const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - X.winDur;
@@ -358,6 +358,9 @@ FILO_HD inline bool h2_window(int k, const H2Ctx& X, double* pv) {
   const bool is_rate = q.fn == FN_RATE;
   // buckets in batches of H2_BATCH: the partial row lives in global memory (L2); loading a batch's old sums before computing keeps
   // several loads in flight instead of one load -> add -> store chain per bucket
+  // HistSumRowAggregator.reduceAggregate (HistSumRowAggregator.scala:25-36): the first histogram of the partial row is copied, every
+  // further one goes through MutableHistogram.add = addNoCorrection + makeMonotonic (Histogram.scala:428-449): running maximum mx
+  double mx = 0.0;
   for (int b0 = 0; b0 < nb; b0 += H2_BATCH) {
     double old[H2_BATCH];
 #pragma unroll
@@ -378,7 +381,9 @@ FILO_HD inline bool h2_window(int k, const H2Ctx& X, double* pv) {
         }
         const double scaled = delta * ratio;
         const double r = is_rate ? h2_div_window(scaled, X.fdiv, X.frcp) * 1000.0 : scaled;
-        pv[(size_t)b * q.T + k] = old[j] + r;                               // MutableHistogram.addNoCorrection: NaN-seeded sums start at 0
+        double nv = old[j] + r;                                             // MutableHistogram.addNoCorrection: NaN-seeded sums start at 0
+        if (!first) { if (nv < mx || nv != nv) nv = mx; else if (nv > mx) mx = nv; }
+        pv[(size_t)b * q.T + k] = nv;
       }
     }
   }

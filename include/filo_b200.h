@@ -157,6 +157,10 @@ void    filo_ctx_destroy(filo_ctx* ctx);
  * (RangeFunction.generatorFor, RangeFunction.scala:283-313): quantile_over_time(arg0), holt_winters(arg0 = sf, arg1 = tf),
  * predict_linear(arg0 = seconds).  Other functions ignore them. */
 int32_t filo_ctx_set_fn_args(filo_ctx* ctx, double arg0, double arg1);
+/* Waits for the non-synchronising queries issued on this ctx (filo_query_device with stats == NULL) and returns the first device-side
+ * error among them (CorruptVector, scratch overflow), FILO_OK otherwise.  Such errors are also returned by the next call on the ctx
+ * that finds them complete. */
+int32_t filo_ctx_check(filo_ctx* ctx);
 /* Copies the last error message of this ctx (thread-local when ctx is NULL) into buf; returns its length. */
 int32_t filo_last_error(filo_ctx* ctx, char* buf, int32_t len);
 
@@ -207,10 +211,10 @@ int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t range_fn,
  *   (aggregator/HistSumRowAggregator.scala) over the table's groups and HistogramQuantileImpl (InstantFunction.scala:362-368).
  *  aggr NONE: out_values [n_series * T * buckets] (an empty histogram = NaN buckets), out_quantile must be NULL
  *  aggr SUM : out_values [n_groups * T * buckets] or NULL, out_quantile [n_groups * T] or NULL (quantile in [0,1])
- * Partial sums of a group are folded in a fixed order and made monotonic once at the end.  The reference re-runs
- * makeMonotonic after every add, which makes its own result depend on the arrival order of the series whenever a member
- * histogram is not monotonic over its buckets (extrapolation around a counter reset): such cells agree only approximately;
- * all other cells agree to 1e-9 relative (tests/test_gpu_parity.py::test_hist_rate_sum_quantile). */
+ * The sum follows HistSumRowAggregator.reduceAggregate (HistSumRowAggregator.scala:25-36): the first histogram of a partial aggregate
+ * is copied, every further one goes through MutableHistogram.add = addNoCorrection + makeMonotonic (Histogram.scala:428-449).  That
+ * holds inside a work item (a run of series of one group, in series order) and across the items of a group (item order) -- the
+ * same two-level reduction the reference runs (per-shard AggregateMapReduce, then ReduceAggregateExec), with a fixed tree. */
 int32_t filo_query_hist(filo_ctx* ctx, const filo_table* t, int32_t range_fn,
                         int64_t start_ms, int64_t step_ms, int64_t end_ms, int64_t window_ms,
                         int32_t aggr_op, double quantile, double* out_values, double* out_quantile, filo_stats* stats);
@@ -235,6 +239,23 @@ int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32_t* n_chunk
 /* RowAggregator "present" after a cross-GPU merge: n = n_groups*T cells; writes NaN where count == 0, Σ/n for AVG. */
 int32_t filo_present_partials(filo_ctx* ctx, int32_t aggr_op, int64_t n, void* d_values, void* d_counts,
                               void* d_out_values, void* cuda_stream);
+
+/* Result wire format: the rows (start + k*step, values[row][k]) of a query result encoded as BinaryRecord v2 records in 4096-byte
+ * RecordContainers -- the bytes SerializedRangeVector.apply writes through ONE RecordBuilder shared by all range vectors of a result
+ * (core/src/main/scala/filodb.core/query/RangeVector.scala:427-476,511-586; binaryrecord2/RecordBuilder.scala:109-175,461-480,589-621;
+ * RecordContainer.scala:13-57).  NaN rows are not encoded unless start == end (canRemoveEmptyRows); 204 records of 20 bytes per
+ * container.  Range vector i is (rows_serialized[i], start_record_no[i], first_container[i]): its records are records
+ * [start_record_no, start_record_no + rows_serialized) of the containers from first_container on.  container_ts_ms is the server
+ * timestamp of the container headers.  The *_device form reads and writes device memory on cuda_stream (containers: capacity
+ * filo_result_max_containers(n_rows, T) * 4096 bytes always suffices; bytes of the last container past its records are not written). */
+int64_t filo_result_max_containers(int64_t n_rows, int32_t n_windows);
+int32_t filo_encode_result_device(filo_ctx* ctx, const void* d_values, int64_t n_rows, int64_t start_ms, int64_t step_ms, int64_t end_ms,
+                                  int64_t container_ts_ms, void* d_containers, int64_t containers_cap_bytes,
+                                  void* d_rows_serialized /* int32[n_rows] */, void* d_start_record_no /* int32[n_rows] */,
+                                  void* d_first_container /* int64[n_rows] */, int64_t* n_containers_out, int64_t* n_records_out, void* cuda_stream);
+int32_t filo_encode_result(filo_ctx* ctx, const double* values, int64_t n_rows, int64_t start_ms, int64_t step_ms, int64_t end_ms,
+                           int64_t container_ts_ms, uint8_t* out_containers, int64_t containers_cap_bytes, int32_t* rows_serialized,
+                           int32_t* start_record_no, int64_t* first_container, int64_t* n_containers_out, int64_t* n_records_out);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,8 @@ def _sig(L):
         ("fo_query2", i32, [vp, i32, i32, f64, f64, i64, i64, i64, i64, i32, i32, i32, vp, i32, i32, i64, i64, vp, vp, vp]),
         ("fo_store_add_chunk_longs", i32, [vp, i64, vp, vp, i32, i32, i32]),
         ("fo_num_windows", i32, [i64, i64, i64]),
+        ("fo_serialize_result", i64, [vp, i64, i32, i64, i64, i64, i64, vp, i64, vp, vp, vp]),
+        ("fo_result_rows", i64, [vp, i64, i32, i32, i64, i64, i64, i64, vp, vp, i64]),
         ("fo_sliding", None, [vp, vp, i64, i32, i32, i64, i64, i64, i64, vp]),
     ]:
         f = getattr(L, name)
@@ -356,3 +358,27 @@ def synth_group_ids(seed, series_id_base, n, n_groups):
     out = np.zeros(n, np.int32)
     lib().fo_synth_group_ids(seed, series_id_base, n, n_groups, _p(out))
     return out
+
+
+def serialize_result(values, start, step, end, now_ms=0):
+    """SerializedRangeVector.apply over one shared RecordBuilder for the rows of `values` [n_rows, T] ->
+    (containers uint8[n_containers, 4096], rows_serialized int32[n], start_record_no int32[n], first_container int64[n])."""
+    v = np.ascontiguousarray(values, np.float64)
+    n, T = v.shape
+    cap = (n * T + 203) // 204 + 1
+    out = np.zeros((cap, 4096), np.uint8)
+    rs = np.zeros(n, np.int32); sr = np.zeros(n, np.int32); fc = np.zeros(n, np.int64)
+    nc = lib().fo_serialize_result(_p(v), n, T, start, step, end, now_ms, _p(out), cap, _p(rs), _p(sr), _p(fc))
+    if nc < 0:
+        raise RuntimeError("fo_serialize_result: %s" % last_error())
+    return out[:nc].copy(), rs, sr, fc
+
+
+def result_rows(containers, rows_serialized, start_record_no, first_container, start, step, end):
+    """SerializedRangeVector.rows of one range vector -> (ts int64[], values float64[])."""
+    c = np.ascontiguousarray(containers, np.uint8)
+    cap = max(int(rows_serialized), (end - start) // max(step, 1) + 1) + 1
+    ts = np.zeros(cap, np.int64); vals = np.zeros(cap, np.float64)
+    n = lib().fo_result_rows(_p(c), c.shape[0] if c.ndim == 2 else c.size // 4096, int(rows_serialized), int(start_record_no), int(first_container),
+                             start, step, end, _p(ts), _p(vals), cap)
+    return ts[:n].copy(), vals[:n].copy()

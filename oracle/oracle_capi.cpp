@@ -3,6 +3,7 @@
 // Nothing under filodb_b200/ may link or load this library.
 #include "filo_format.hpp"
 #include "filo_query.hpp"
+#include "filo_result.hpp"
 #include <thread>
 #include <atomic>
 #include <chrono>
@@ -351,6 +352,34 @@ int32_t fo_query2(void* sp, int32_t fn, int32_t schemaFlags, double p0, double p
   } catch (std::exception& e) { g_err = e.what(); return -1; }
 }
 int32_t fo_num_windows(int64_t start, int64_t step, int64_t end) { return numWindows(start, step, end); }
+
+// ---------------- result wire format (SerializedRangeVector over one shared RecordBuilder)
+// values [nRows][T] -> containers (4096 bytes each, concatenated; returns their count or -needed when cap is too small) + per range vector
+// numRowsSerialized / startRecordNo / firstContainer
+int64_t fo_serialize_result(const double* values, int64_t nRows, int32_t T, int64_t start, int64_t step, int64_t end, int64_t nowMs,
+                            uint8_t* outContainers, int64_t capContainers, int32_t* rowsSerialized, int32_t* startRecordNo, int64_t* firstContainer) {
+  try {
+    result::RecordBuilder b(result::MaxContainerSize, nowMs);
+    for (int64_t i = 0; i < nRows; ++i) {
+      const result::SerializedRangeVector srv = result::serialize(b, values + (size_t)i * T, T, start, step, end);
+      rowsSerialized[i] = srv.numRowsSerialized; startRecordNo[i] = srv.startRecordNo; firstContainer[i] = srv.firstContainer;
+    }
+    const int64_t n = (int64_t)b.containers.size();
+    if (n > capContainers) return -n;
+    for (int64_t c = 0; c < n; ++c) std::memcpy(outContainers + c * result::MaxContainerSize, b.containers[(size_t)c]->bytes.data(), result::MaxContainerSize);
+    return n;
+  } catch (std::exception& e) { g_err = e.what(); return INT64_MIN; }
+}
+// SerializedRangeVector.rows of one range vector: fills ts / vals (cap entries), returns the row count
+int64_t fo_result_rows(const uint8_t* containers, int64_t nContainers, int32_t rowsSerialized, int32_t startRecordNo, int64_t firstContainer,
+                       int64_t start, int64_t step, int64_t end, int64_t* ts, double* vals, int64_t cap) {
+  result::SerializedRangeVector srv; srv.numRowsSerialized = rowsSerialized; srv.startRecordNo = startRecordNo; srv.firstContainer = firstContainer;
+  std::vector<int64_t> t; std::vector<double> v;
+  result::rows(containers, nContainers, srv, start, step, end, t, v);
+  const int64_t n = (int64_t)t.size();
+  for (int64_t i = 0; i < n && i < cap; ++i) { ts[i] = t[(size_t)i]; vals[i] = v[(size_t)i]; }
+  return n;
+}
 
 // Row-wise sliding cross-check for one series given raw rows.
 void fo_sliding(const int64_t* ts, const double* vals, int64_t n, int32_t fn, int32_t cumulative,

@@ -85,7 +85,7 @@ static int run_series(const Series& S, const filo::H2Ctx& X, int max_rows, doubl
   for (int t = 0; t < NT; ++t) filo::h2_chunk_corrections(t, NT, X);
   for (int t = 0; t < NT; ++t) filo::h2_chunk_less(t, X);
   for (int t = 0; t < NT; ++t) filo::h2_carried(t, NT, X);
-  for (int t = 0; t < NT; ++t) for (int k = t; k < X.q.T; k += NT) if (filo::h2_window(k, X, pv)) any[(size_t)k] = 1;
+  for (int t = 0; t < NT; ++t) for (int k = t; k < X.q.T; k += NT) if (filo::h2_window(k, X, pv, any[(size_t)k] == 0)) any[(size_t)k] = 1;
   return 0;
 }
 
@@ -129,8 +129,14 @@ int main() {
         if ((int)out.size() != q.T) { std::printf("FAIL cfg %d q %d: T %d vs %zu\n", cfg, qi, q.T, out.size()); return 1; }
         for (int k = 0; k < q.T; ++k) {
           if (out[(size_t)k].numBuckets() == 0) continue;
+          const bool firstm = !rany[(size_t)k];                    // HistSumRowAggregator: copy the first, MutableHistogram.add (sum + makeMonotonic) the others
           rany[(size_t)k] = 1;
-          for (int i = 0; i < nb; ++i) ref[(size_t)i * q.T + k] += out[(size_t)k].values[(size_t)i];
+          double mx = 0.0;
+          for (int i = 0; i < nb; ++i) {
+            double nv = ref[(size_t)i * q.T + k] + out[(size_t)k].values[(size_t)i];
+            if (!firstm) { if (nv < mx || nv != nv) nv = mx; else if (nv > mx) mx = nv; }
+            ref[(size_t)i * q.T + k] = nv;
+          }
         }
         // scan counters of the series
         int64_t rows_in = 0; for (int n : chunk_rows) rows_in += n;

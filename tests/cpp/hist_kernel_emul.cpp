@@ -106,21 +106,25 @@ int main(int argc, char** argv) {
     std::vector<int64_t> item_begin; for (int64_t p = 0; p < c.nser; p += c.seg) item_begin.push_back(p); item_begin.push_back(c.nser);
     const int64_t n_items = (int64_t)item_begin.size() - 1; const int64_t gis[2] = {0, n_items};
     std::vector<double> tops((size_t)nb); for (int i = 0; i < nb; ++i) tops[(size_t)i] = b.bucketTop(i);
-    // expected fused result: the kernels' two-level fold (series inside an item, items inside the group), makeMonotonic once, quantile
+    // expected fused result: HistSumRowAggregator.reduceAggregate at both levels (series inside an item, items inside the group): the first
+    // histogram is copied, every further one goes through MutableHistogram.add (sum, then makeMonotonic); then the quantile
     std::vector<double> exp_vals((size_t)T * nb, 0.0), exp_q((size_t)T, 0.0); std::vector<char> exp_any((size_t)T, 0);
     for (int k = 0; k < T; ++k) {
-      H::MutHist tot; tot.buckets = b; tot.values.assign((size_t)nb, 0.0); bool any = false;
+      H::MutHist tot; bool any = false;
       for (int64_t it = 0; it < n_items; ++it) {
-        std::vector<double> part((size_t)nb, 0.0); bool iany = false;
+        H::MutHist part; bool iany = false;
         for (int64_t p = item_begin[(size_t)it]; p < item_begin[(size_t)it + 1]; ++p) {
           const H::MutHist& h = ref[(size_t)order[(size_t)p]][(size_t)k];
           if (h.numBuckets() == 0) continue;
-          iany = true; for (int i = 0; i < nb; ++i) part[(size_t)i] += h.values[(size_t)i];
+          if (!iany) { part = h; iany = true; }
+          else { for (int i = 0; i < nb; ++i) part.values[(size_t)i] += h.values[(size_t)i]; part.makeMonotonic(); }
         }
-        if (iany) { any = true; for (int i = 0; i < nb; ++i) tot.values[(size_t)i] += part[(size_t)i]; }
+        if (!iany) continue;
+        if (!any) { tot = part; any = true; }
+        else { for (int i = 0; i < nb; ++i) tot.values[(size_t)i] += part.values[(size_t)i]; tot.makeMonotonic(); }
       }
       exp_any[(size_t)k] = any;
-      if (any) { tot.makeMonotonic(); exp_q[(size_t)k] = tot.quantile(0.9); for (int i = 0; i < nb; ++i) exp_vals[(size_t)k * nb + i] = tot.values[(size_t)i]; }
+      if (any) { exp_q[(size_t)k] = tot.quantile(0.9); for (int i = 0; i < nb; ++i) exp_vals[(size_t)k * nb + i] = tot.values[(size_t)i]; }
     }
     const bool counter_mode = c.cumulative && (c.fn == filo::FN_RATE || c.fn == filo::FN_INCREASE);
     unsigned long long counters[2]; int derr[4];

@@ -139,3 +139,24 @@ def test_histogram_kernels_run_on_the_simt_emulator(tmp_path):
     for seed in ("0", "5"):
         out = subprocess.run([exe, seed], check=True, capture_output=True, text=True).stdout
         assert "OK 6 cases" in out and "bit-exact" in out, out
+
+
+def test_jni_shim_exports_the_reference_naming():
+    """filodb_b200/libfilo_b200_jni.so (csrc/jni_shim.cpp) exports one Java_filodb_gpu_FiloB200NativeMethods_00024_<method> per @native
+    method of INTEGRATION.md §2 -- the naming of the reference's own JNI crate for Scala objects (simd_vectors.rs:164,186) -- and
+    nothing else; it needs the C-ABI library only."""
+    import subprocess
+    from filodb_b200 import build as b
+    b.build()
+    so = b.JNI_OUT if os.path.exists(b.JNI_OUT) else b.build_jni()
+    syms = subprocess.run(["nm", "-D", "--defined-only", so], check=True, capture_output=True, text=True).stdout.split("\n")
+    names = sorted(l.split()[-1] for l in syms if " T " in l)
+    want = sorted("Java_filodb_gpu_FiloB200NativeMethods_00024_" + m for m in
+                  ("ctxCreate", "ctxDestroy", "ctxSetFnArgs", "ctxCheck", "hostRegister", "hostUnregister", "loadSeries", "tableFree", "numWindows",
+                   "query", "queryHist", "scanSeries"))
+    assert names == want, names
+    needed = subprocess.run(["readelf", "-d", so], check=True, capture_output=True, text=True).stdout
+    assert "libfilo_b200.so" in needed
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for m in ("ctxCreate", "loadSeries", "query", "scanSeries", "queryHist", "tableFree"):
+        assert "def %s(" % m in doc, m

@@ -305,3 +305,27 @@ def test_long_column_variants(oracle):
     st = o.Store(); si = st.add_series(); st.add_chunk_longs(si, ts, cases["ddv"])
     with pytest.raises(RuntimeError):
         st.query(o.FN_RATE, T0, PUB, T0 + 10 * PUB, 5 * PUB, long_column=True)
+
+
+def test_serialized_range_vector_known_answers(oracle):
+    # core/src/test/scala/filodb.core/query/SerializedRangeVectorSpec.scala:40-66,68-94,124-146
+    o = oracle
+    vals = np.array([[NaN, 1.0, NaN, 3.0, NaN, 5.0, 6.0, NaN, NaN, NaN, NaN]])
+    c, rs, sr, fc = o.serialize_result(vals, 0, 100, 1000)
+    assert rs[0] == 4 and sr[0] == 0 and c.shape[0] == 1                   # numRowsSerialized 4
+    assert int(c[0, :4].view(np.int32)[0]) == 12 + 4 * 20                   # estimateSerializedRowBytes 80: 4 records of 20 bytes
+    assert int(c[0, 4:8].view(np.int32)[0]) == 1 << 24                      # version word
+    ts, v = o.result_rows(c, rs[0], sr[0], fc[0], 0, 100, 1000)
+    assert list(ts) == list(range(0, 1001, 100)) and [x for x in v if not math.isnan(x)] == [1.0, 3.0, 5.0, 6.0] and len(v) == 11
+    # instant query (start == end): NaN rows are kept.  The spec feeds 11 raw rows with RvRange(1000, 100, 1000); the restatement takes rows on
+    # the output grid, so the same rule is exercised with one row
+    c1, rs1, _, _ = o.serialize_result(np.array([[NaN]]), 1000, 100, 1000)
+    assert rs1[0] == 1 and int(c1[0, :4].view(np.int32)[0]) == 12 + 20
+    # 201 range vectors through one shared builder: each keeps its own row count; containers hold 204 records
+    many = np.tile(vals, (201, 1))
+    c, rs, sr, fc = o.serialize_result(many, 0, 100, 1000)
+    assert (rs == 4).all() and c.shape[0] == (201 * 4 + 203) // 204
+    for i in (0, 50, 51, 52, 102, 200):
+        ts, v = o.result_rows(c, rs[i], sr[i], fc[i], 0, 100, 1000)
+        assert [x for x in v if not math.isnan(x)] == [1.0, 3.0, 5.0, 6.0] and len(v) == 11
+    assert sr[51] == 204 and fc[51] == 0 and sr[52] == 4 and fc[52] == 1      # vector 51 starts after a full container: startRecordNo = its record count
