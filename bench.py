@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="filo", choices=["filo", "reference"])
     ap.add_argument("--series", type=int, default=10_000_000, help="series per GPU")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c2-raw", "c2-counter", "c3", "c3-const", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c2-raw", "c2-counter", "c3", "c3-const", "c4", "c5"])
     ap.add_argument("--e2e-series", type=int, default=-1, help="series in the end-to-end leg (-1 = all)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-series", type=int, default=2_000_000, help="bounded sample for the CPU baseline legs")
@@ -56,6 +56,8 @@ def parse_args():
 
 WORKLOADS = {
     # name: (synth kwargs, fn, aggr, n_groups, description)
+    "c1": (dict(value_kind=0, value_enc=1, nan_per_million=1000), "FN_SUM_OVER_TIME", "AGG_NONE", 0,
+           "C1: {S} series x 1h@15s (240 rows, one chunk), const-DDV ts, XOR-NibblePack doubles, sum_over_time[5m] step 15s (BASELINE configs[0]: the reference's own CPU-runnable case)"),
     "c2": (dict(value_kind=0, value_enc=1, nan_per_million=1000), "FN_RATE", "AGG_NONE", 0,
            "C2: {S} series x 2h@15s (480 rows, chunks 400+80), const-DDV ts, XOR-NibblePack gauge, rate()[5m] step 15s, T=481, no aggregate"),
     "c2-raw": (dict(value_kind=0, value_enc=0, nan_per_million=1000), "FN_RATE", "AGG_NONE", 0,
@@ -73,7 +75,7 @@ WORKLOADS = {
 
 def query_range(workload):
     window = 60000 if workload.startswith("c3") else WINDOW
-    return T0_MS, STEP, T0_MS + 7200000, window
+    return T0_MS, STEP, T0_MS + (ROWS * INTERVAL), window
 
 
 def host_cores():
@@ -510,6 +512,23 @@ def run_c4(args, rank, world, local_rank):
         line["cpu_baseline"] = {"value": K * ROWS / dtc, "unit": "samples/s", "cores": 1, "kind": "port",
                                 "sample": "%d of %d series (%.1f s on 1 thread); C++ restatement of ChunkedWindowIteratorH + HistRateFunction + HistSum + quantile" % (K, S, dtc)}
         del sub
+        # ---- parity at bench scale (outside the timed region): the K distinct series as one group, fused sum + quantile against the oracle
+        try:
+            avals, aempty, aq = st.query(o.FN_RATE, start, step, end, window, aggr=True, group_ids=np.zeros(K, np.int32), n_groups=1, q=0.99)
+            tabk = ctx.load_series(nch_k, addrs_k, schema_flags=capi.SCHEMA_CUMULATIVE)
+            gv, gq = ctx.query_hist(tabk, capi.FN_RATE, start, step, end, window, aggr=capi.AGG_SUM, quantile=0.99)
+            tabk.free()
+            live = ~aempty.reshape(-1)
+            gv2 = np.asarray(gv).reshape(-1, nb)[live]; av2 = avals.reshape(-1, nb)[live]
+            rel = np.abs(gv2 - av2) / np.maximum(np.abs(av2), 1e-300)
+            qrel = np.abs(np.asarray(gq).reshape(-1)[live] - aq.reshape(-1)[live]) / np.maximum(np.abs(aq.reshape(-1)[live]), 1e-300)
+            line["parity_check"] = {"series": int(K), "windows": int(T), "buckets": nb, "cells": int(rel.size), "max_rel_err_sum": float(rel.max()) if rel.size else 0.0,
+                                    "max_rel_err_quantile": float(qrel.max()) if qrel.size else 0.0, "tolerance": 1e-9,
+                                    "within_tolerance": bool((rel.max() if rel.size else 0.0) <= 1e-9 and (qrel.max() if qrel.size else 0.0) <= 1e-9),
+                                    "nan_mismatches": int((np.isnan(np.asarray(gq).reshape(-1)) != np.isnan(aq.reshape(-1))).sum()),
+                                    "against": "oracle: HistSumRowAggregator fold (copy + MutableHistogram.add per series) + Histogram.quantile; the device folds the same way inside work items and across them"}
+        except Exception as e:
+            line["parity_check"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     tab.free()
@@ -517,7 +536,11 @@ def run_c4(args, rank, world, local_rank):
 
 
 def main():
+    global ROWS
     args = parse_args()
+    if args.workload == "c1":                       # BASELINE configs[0]: 1k series x 1h@15s
+        ROWS = 240
+        args.series = min(args.series, 1000)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":

@@ -15,7 +15,7 @@ SCHEMA_LONG_VALUES = 2
 Q_PARTIAL = 1
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CORRUPT_VECTOR, ERR_UNSUPPORTED, ERR_QUERY_LIMIT, ERR_BAD_QUERY, ERR_OOM = 0, -1, -2, -3, -4, -5, -6, -7
 
-EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_ctx_set_fn_args", "filo_ctx_check", "filo_last_error", "filo_load_series", "filo_synth_table",
+EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_ctx_set_fn_args", "filo_ctx_check", "filo_last_error", "filo_load_series", "filo_table_append", "filo_synth_table",
            "filo_table_set_groups", "filo_table_get_info", "filo_table_read_record", "filo_table_read_arena", "filo_table_free",
            "filo_num_windows", "filo_query", "filo_query_device", "filo_scan_series", "filo_query_hist", "filo_host_register", "filo_host_unregister", "filo_present_partials",
            "filo_result_max_containers", "filo_encode_result_device", "filo_encode_result"]
@@ -74,6 +74,7 @@ def _sig(L):
     L.filo_ctx_create.restype = i32; L.filo_ctx_create.argtypes = [i32, C.POINTER(Cfg), C.POINTER(vp)]
     L.filo_ctx_destroy.restype = None; L.filo_ctx_destroy.argtypes = [vp]
     L.filo_ctx_check.restype = i32; L.filo_ctx_check.argtypes = [vp]
+    L.filo_table_append.restype = i32; L.filo_table_append.argtypes = [vp, vp, vp, vp, i32, i32]
     L.filo_result_max_containers.restype = i64; L.filo_result_max_containers.argtypes = [i64, i32]
     L.filo_encode_result.restype = i32; L.filo_encode_result.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, vp, vp, vp, C.POINTER(i64), C.POINTER(i64)]
     L.filo_encode_result_device.restype = i32
@@ -122,6 +123,13 @@ class Table:
         ti = TableInfo()
         self.ctx._check(lib().filo_table_get_info(self.h, C.byref(ti)))
         return ti
+
+    def append(self, n_chunks, info_addrs, ts_col=0, val_col=1):
+        """filo_table_append: new chunks of the table's series (n_chunks[i] may be 0); only they cross PCIe."""
+        nch = np.ascontiguousarray(n_chunks, np.int32)
+        addrs = np.ascontiguousarray(info_addrs, np.uint64)
+        if addrs.size == 0: addrs = np.zeros(1, np.uint64)
+        self.ctx._check(lib().filo_table_append(self.ctx.h, self.h, _p(nch), _p(addrs), ts_col, val_col))
 
     def set_groups(self, group_ids, n_groups):
         g = np.ascontiguousarray(group_ids, np.int32) if group_ids is not None else None

@@ -558,6 +558,114 @@ extern "C" int64_t filo_table_read_record(filo_ctx* ctx, const filo_table* t, in
   return n;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// incremental arena: new chunks of a resident table (TimeSeriesPartition.switchBuffers / encodeOneChunkset hand a shard's freshly
+// encoded chunks over, core/src/main/scala/filodb.core/memstore/TimeSeriesPartition.scala:251-288).  Only the new chunks cross PCIe
+// (loaded like a table of their own); the records are re-packed on the device: record = header + old entries + new entries + old
+// vectors + new vectors, which is byte for byte what filo_load_series writes for all the chunks.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+// bytes of a record's vector region that hold vectors (the record itself is padded to 16): end of the last chunk's value vector
+__device__ __forceinline__ uint32_t rec_used_vectors(const uint8_t* r) {
+  const RecordHeader h = *reinterpret_cast<const RecordHeader*>(r);
+  const uint32_t v0 = (uint32_t)sizeof(RecordHeader) + 32u * h.n_chunks;
+  if (h.n_chunks == 0) return 0;
+  const ChunkEntry& e = reinterpret_cast<const ChunkEntry*>(r + sizeof(RecordHeader))[h.n_chunks - 1];
+  const uint32_t vt = *reinterpret_cast<const uint32_t*>(r + e.val_off) + 4u;
+  return align_up(e.val_off + vt, 8) - v0;
+}
+__global__ void append_size_kernel(const uint8_t* __restrict__ ar_o, const int64_t* __restrict__ off_o, const uint8_t* __restrict__ ar_d, const int64_t* __restrict__ off_d,
+                                   int64_t n, int64_t* __restrict__ sz) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint8_t* ro = ar_o + off_o[i]; const uint8_t* rd = ar_d + off_d[i];
+    const uint32_t nn = reinterpret_cast<const RecordHeader*>(ro)->n_chunks + reinterpret_cast<const RecordHeader*>(rd)->n_chunks;
+    sz[i] = (int64_t)align_up((uint32_t)sizeof(RecordHeader) + 32u * nn + rec_used_vectors(ro) + rec_used_vectors(rd), 16);
+  }
+  if (i == n) sz[i] = 0;
+}
+// warp per series; stats: [0] max record bytes, [1] max rows, [2] max chunks, [3] order violations
+__global__ void __launch_bounds__(256) append_merge_kernel(const uint8_t* __restrict__ ar_o, const int64_t* __restrict__ off_o, const uint8_t* __restrict__ ar_d,
+                                                           const int64_t* __restrict__ off_d, const int64_t* __restrict__ off_n, int64_t n,
+                                                           uint8_t* __restrict__ ar_n, unsigned int* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n) return;
+  const uint8_t* ro = ar_o + off_o[i]; const uint8_t* rd = ar_d + off_d[i]; uint8_t* rn = ar_n + off_n[i];
+  const RecordHeader ho = *reinterpret_cast<const RecordHeader*>(ro), hd = *reinterpret_cast<const RecordHeader*>(rd);
+  const uint32_t no = ho.n_chunks, nd = hd.n_chunks, nn = no + nd;
+  const uint32_t vo0 = (uint32_t)sizeof(RecordHeader) + 32u * no, vd0 = (uint32_t)sizeof(RecordHeader) + 32u * nd, vn0 = (uint32_t)sizeof(RecordHeader) + 32u * nn;
+  const uint32_t Lo = rec_used_vectors(ro), Ld = rec_used_vectors(rd);          // multiples of 8
+  const uint32_t rec_bytes = align_up(vn0 + Lo + Ld, 16);
+  if (lane == 0) {
+    RecordHeader hn; hn.rec_bytes = rec_bytes; hn.n_chunks = nn; hn.n_rows = ho.n_rows + hd.n_rows;
+    hn.flags = ((ho.flags & hd.flags) & REC_ALL_TS_CONST) | ((ho.flags | hd.flags) & ~REC_ALL_TS_CONST);
+    *reinterpret_cast<RecordHeader*>(rn) = hn;
+    atomicMax(&stats[0], hn.rec_bytes); atomicMax(&stats[1], hn.n_rows); atomicMax(&stats[2], nn);
+    if (no && nd) {                                         // chunks stay in time order (the loader's rule, plan_series)
+      const ChunkEntry& lo = reinterpret_cast<const ChunkEntry*>(ro + sizeof(RecordHeader))[no - 1];
+      const ChunkEntry& fd = reinterpret_cast<const ChunkEntry*>(rd + sizeof(RecordHeader))[0];
+      if (fd.start_time < lo.start_time || fd.end_time < lo.end_time) atomicAdd(&stats[3], 1u);
+    }
+    if ((vn0 + Lo + Ld) & 8u) *reinterpret_cast<uint64_t*>(rn + vn0 + Lo + Ld) = 0ull;      // the record's tail pad
+  }
+  for (uint32_t c = lane; c < nn; c += 32) {
+    ChunkEntry e;
+    if (c < no) { e = reinterpret_cast<const ChunkEntry*>(ro + sizeof(RecordHeader))[c]; e.ts_off += 32u * nd; e.val_off += 32u * nd; }
+    else { e = reinterpret_cast<const ChunkEntry*>(rd + sizeof(RecordHeader))[c - no]; e.ts_off += 32u * no + Lo; e.val_off += 32u * no + Lo; e.row_base += ho.n_rows; }
+    reinterpret_cast<ChunkEntry*>(rn + sizeof(RecordHeader))[c] = e;
+  }
+  // vector regions: multiples of 8 bytes at 8-byte aligned offsets
+  const uint64_t* so = reinterpret_cast<const uint64_t*>(ro + vo0); uint64_t* dn = reinterpret_cast<uint64_t*>(rn + vn0);
+  for (uint32_t q = lane; q < Lo / 8; q += 32) dn[q] = so[q];
+  const uint64_t* sd = reinterpret_cast<const uint64_t*>(rd + vd0); dn = reinterpret_cast<uint64_t*>(rn + vn0 + Lo);
+  for (uint32_t q = lane; q < Ld / 8; q += 32) dn[q] = sd[q];
+}
+}  // namespace
+
+extern "C" int32_t filo_table_append(filo_ctx* ctx, filo_table* t, const int32_t* n_chunks, const uint64_t* chunk_info_addrs, int32_t ts_col, int32_t val_col) {
+  if (!ctx || !t || !n_chunks || !chunk_info_addrs) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_table_append: null argument");
+  if (t->hist) return fail(ctx, FILO_ERR_UNSUPPORTED, "filo_table_append: histogram tables are rebuilt with filo_load_series");
+  const int64_t S = t->n_series;
+  filo_table* d = nullptr;
+  { const int32_t rc = filo_load_series(ctx, S, n_chunks, chunk_info_addrs, ts_col, val_col, nullptr, 0, t->schema_flags, &d); if (rc != FILO_OK) return rc; }
+  struct FreeT { filo_ctx* c; filo_table* t; ~FreeT() { filo_table_free(c, t); } } guard{ctx, d};
+  if (d->hist) return fail(ctx, FILO_ERR_UNSUPPORTED, "filo_table_append: histogram vectors");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  int64_t *d_sz = nullptr, *d_off = nullptr; unsigned int* d_stats = nullptr; void* tmp = nullptr; uint8_t* d_arena = nullptr;
+  struct FreeD { std::vector<void*> p; ~FreeD() { for (void* x : p) cudaFree(x); } } tmps;
+  CUDA_TRY(ctx, cudaMalloc(&d_sz, (size_t)(S + 1) * 8)); tmps.p.push_back(d_sz);
+  CUDA_TRY(ctx, cudaMalloc(&d_off, (size_t)(S + 1) * 8));
+  CUDA_TRY(ctx, cudaMalloc(&d_stats, 16)); tmps.p.push_back(d_stats);
+  CUDA_TRY(ctx, cudaMemsetAsync(d_stats, 0, 16, s));
+  append_size_kernel<<<(unsigned)((S + 1 + 255) / 256), 256, 0, s>>>(t->d_arena, t->d_rec_off, d->d_arena, d->d_rec_off, S, d_sz);
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_sz, d_off, (int)(S + 1), s);
+  if (cudaMalloc(&tmp, tmp_bytes + 16) != cudaSuccess) { cudaFree(d_off); return fail(ctx, FILO_ERR_OOM, "filo_table_append: scan storage"); }
+  tmps.p.push_back(tmp);
+  if (cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_sz, d_off, (int)(S + 1), s) != cudaSuccess) { cudaFree(d_off); return fail(ctx, FILO_ERR_CUDA, "filo_table_append: scan"); }
+  int64_t arena_bytes = 0;
+  if (cudaMemcpyAsync(&arena_bytes, d_off + S, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) { cudaFree(d_off); return fail(ctx, FILO_ERR_CUDA, "filo_table_append: sizes"); }
+  if (cudaMalloc(&d_arena, (size_t)arena_bytes + 64) != cudaSuccess) { cudaFree(d_off); return fail(ctx, FILO_ERR_OOM, "filo_table_append: the new arena does not fit beside the old one"); }
+  cudaMemsetAsync(d_arena + arena_bytes, 0, 64, s);
+  if (S > 0) append_merge_kernel<<<(unsigned)((S * 32 + 255) / 256), 256, 0, s>>>(t->d_arena, t->d_rec_off, d->d_arena, d->d_rec_off, d_off, S, d_arena, d_stats);
+  unsigned int st[4] = {0, 0, 0, 0};
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(st, d_stats, 16, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { cudaFree(d_off); cudaFree(d_arena); return fail(ctx, FILO_ERR_CUDA, std::string("filo_table_append: ") + cudaGetErrorString(e)); }
+  if (st[3]) { cudaFree(d_off); cudaFree(d_arena); return fail(ctx, FILO_ERR_UNSUPPORTED, "filo_table_append: new chunks must follow the resident ones in time (unsupported on the device path)"); }
+  // swap the arena in; the table handle, its grouping and its series ordinals stay
+  cudaFree(t->d_arena); cudaFree(t->d_rec_off);
+  t->d_arena = d_arena; t->d_rec_off = d_off;
+  t->n_chunks += d->n_chunks; t->n_samples += d->n_samples; t->algorithmic_bytes += d->algorithmic_bytes;
+  t->arena_bytes = arena_bytes + (S + 1) * 8;
+  t->max_rec_bytes = st[0]; t->max_rows = (int32_t)st[1]; t->max_chunks = (int32_t)st[2];
+  t->any_nonconst_ts = t->any_nonconst_ts || (d->n_chunks > 0 && d->any_nonconst_ts); t->any_drop = t->any_drop || d->any_drop;
+  return FILO_OK;
+}
+
 extern "C" int64_t filo_table_read_arena(filo_ctx* ctx, const filo_table* t, int64_t first, int64_t n, uint8_t* out, int64_t cap,
                                          int64_t* rec_off_out) {
   if (!ctx || !t || first < 0 || n < 0 || first + n > t->n_series || !rec_off_out) return fail(ctx, FILO_ERR_INVALID_ARG, "bad range");

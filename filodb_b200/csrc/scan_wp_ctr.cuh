@@ -27,8 +27,15 @@ __device__ __forceinline__ double wp_ctr_value(const double* V, const WpCtrChunk
 }
 
 // literal per-chunk fold of the counter functions for one window: tile_eval_counter (scan_tile.cuh) over the skewed V layout
+// FILO_WP_CTR_OUTLINE: the junction fold and the clamped windows as real calls (one or two warp iterations per series go through them;
+// inlined they sit between the decode and the fast loop of every series and push the kernel's hot code out of the instruction cache)
+#if defined(FILO_WP_CTR_OUTLINE) && !defined(FILO_CUSIM)
+#define WP_CTR_RARE static __device__ __noinline__
+#else
+#define WP_CTR_RARE __device__ __forceinline__
+#endif
 template <int FN>
-__device__ __forceinline__ double wp_eval_counter(int n, const WpCtrChunk* K, const WpChunk* CD, const TileDrops* DR, const double* V, int64_t qstep, int qinclusive,
+WP_CTR_RARE double wp_eval_counter(int n, const WpCtrChunk* K, const WpChunk* CD, const TileDrops* DR, const double* V, int64_t qstep, int qinclusive,
                                                   int64_t wStart, int64_t wEnd, int k, double fdiv, double frcp, const TileCtrTab* tab) {
   const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
   int32_t numSamples = 0; int64_t loT = INT64_MAX, hiT = 0; double loV = NaNv, hiV = NaNv;
@@ -74,7 +81,7 @@ static __device__ __noinline__ void wp_bump_u16(uint16_t* p) { *p = (uint16_t)(*
 #endif
 // one clamped single-chunk window (kept out of line: one or two warp iterations per series go through it)
 template <int FN>
-__device__ __forceinline__ double wp_clamped_window(const double* V, const WpCtrChunk& ch, const TileDrops& D, bool drp, int kk, int64_t wEnd, int64_t cws, int64_t qstep,
+WP_CTR_RARE double wp_clamped_window(const double* V, const WpCtrChunk& ch, const TileDrops& D, bool drp, int kk, int64_t wEnd, int64_t cws, int64_t qstep,
                                                    double fdiv, double frcp, const TileCtrTab* tab) {
   int r1 = ch.s0 + kk; if (r1 < 0) r1 = 0;
   int r2 = ch.e0 + kk; if (r2 > ch.nrows - 1) r2 = ch.nrows - 1;

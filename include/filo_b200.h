@@ -172,6 +172,13 @@ int32_t filo_last_error(filo_ctx* ctx, char* buf, int32_t len);
 int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32_t* n_chunks, const uint64_t* chunk_info_addrs,
                          int32_t ts_col, int32_t val_col, const int32_t* group_ids, int32_t n_groups,
                          int32_t schema_flags, filo_table** out);
+/* Incremental arena: appends new chunks to the series of a resident table (same series, in the table's order; n_chunks[i] may be 0) --
+ * what TimeSeriesPartition.switchBuffers / encodeOneChunkset produce at a flush (TimeSeriesPartition.scala:251-288).  Only the new
+ * chunks cross PCIe; the records are re-packed on the device into a new arena that is byte-identical to filo_load_series over all the
+ * chunks (old arena + new arena are resident during the call).  New chunks must follow the resident ones in time (else
+ * FILO_ERR_UNSUPPORTED and the table is unchanged).  The handle, its grouping and queries in flight on other streams: the caller
+ * serialises appends against queries of the same table. */
+int32_t filo_table_append(filo_ctx* ctx, filo_table* t, const int32_t* n_chunks, const uint64_t* chunk_info_addrs, int32_t ts_col, int32_t val_col);
 int32_t filo_synth_table(filo_ctx* ctx, const filo_synth_spec* spec, filo_table** out);
 int32_t filo_table_set_groups(filo_ctx* ctx, filo_table* t, const int32_t* group_ids, int32_t n_groups);
 int32_t filo_table_get_info(const filo_table* t, filo_table_info* out);

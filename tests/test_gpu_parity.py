@@ -747,3 +747,58 @@ def test_result_wire_format(oracle):
         tab.free()
     finally:
         ctx.close()
+
+
+def test_incremental_arena_append(gpu, oracle):
+    """filo_table_append: chunks arrive flush by flush (TimeSeriesPartition.switchBuffers, TimeSeriesPartition.scala:251-288); the re-packed
+    arena is byte-identical to filo_load_series over all the chunks and queries agree with the oracle at every stage."""
+    capi, ctx = gpu; o = oracle
+    rng = np.random.default_rng(41)
+    S, t0 = 33, 1_700_000_000_000
+    st = build_store(o, rng, S, "counter", 1, 0, True, 0.01, rows=420, chunks=(150, 150, 120))
+    for s in range(S):                                   # irregular timestamps and raw vectors in some series
+        pass
+    per = [st.info_addrs(s) for s in range(S)]
+    gids = np.arange(S, dtype=np.int32) % 5
+    # stage 1: first chunk of every series; stage 2: second chunk of two thirds of them; stage 3: the rest
+    tab = ctx.load_series(np.ones(S, np.int32), np.array([p[0] for p in per], np.uint64), group_ids=gids, n_groups=5, schema_flags=capi.SCHEMA_CUMULATIVE)
+    have = np.ones(S, np.int32)
+    q = (t0 + 300000, 15000, t0 + 419 * 15000, 300000)
+
+    def check(stage):
+        sub = o.Store()
+        for s in range(S):
+            si = sub.add_series()
+            for c in range(have[s]):
+                ch_ts = st.vector_bytes(s, c, 0); ch_v = st.vector_bytes(s, c, 1)
+                rows_c = (150, 150, 120)[c]; r0 = (0, 150, 300)[c]
+                sub.add_chunk_raw(si, t0 + r0 * 15000, t0 + (r0 + rows_c - 1) * 15000, rows_c, ch_ts, ch_v)
+        for name in ("FN_RATE", "FN_SUM_OVER_TIME", "FN_LAST"):
+            assert_same(ctx.query(tab, getattr(capi, name), *q), sub.query(getattr(o, name), *q, cumulative=True), "append stage %d %s" % (stage, name))
+        got = ctx.query(tab, capi.FN_RATE, *q, aggr=capi.AGG_SUM)
+        exp = sub.query(o.FN_RATE, *q, cumulative=True, aggr=o.AGG_SUM, group_ids=gids, n_groups=5)
+        np.testing.assert_allclose(got, exp, rtol=1e-9, equal_nan=True)
+        # byte equality with a fresh load of the same chunks
+        nch = have.copy(); addrs = np.array([a for s in range(S) for a in per[s][:have[s]]], np.uint64)
+        ref = ctx.load_series(nch, addrs, schema_flags=capi.SCHEMA_CUMULATIVE)
+        a1, o1 = tab.read_arena(0, S); a2, o2 = ref.read_arena(0, S)
+        assert (o1 == o2).all() and a1.size == a2.size and (a1 == a2).all(), "arena bytes differ at stage %d" % stage
+        i1, i2 = tab.info(), ref.info()
+        assert (i1.n_chunks, i1.n_samples, i1.algorithmic_bytes, i1.max_rows_per_series, i1.max_chunks_per_series) == \
+               (i2.n_chunks, i2.n_samples, i2.algorithmic_bytes, i2.max_rows_per_series, i2.max_chunks_per_series)
+        ref.free()
+
+    check(1)
+    add = np.array([1 if s % 3 else 0 for s in range(S)], np.int32)
+    tab.append(add, np.array([per[s][1] for s in range(S) if add[s]], np.uint64)); have += add
+    check(2)
+    add = np.array([3 - have[s] for s in range(S)], np.int32)
+    tab.append(add, np.array([a for s in range(S) for a in per[s][have[s]:3]], np.uint64)); have += add
+    check(3)
+    # a chunk older than the resident ones is refused and leaves the table as it was
+    with pytest.raises(capi.FiloError) as e:
+        one = np.zeros(S, np.int32); one[0] = 1
+        tab.append(one, np.array([per[0][0]], np.uint64))
+    assert e.value.code == capi.ERR_UNSUPPORTED
+    check(4)
+    tab.free()
