@@ -700,6 +700,24 @@ def main():
                                 if aggr == capi.AGG_NONE else
                                 "filo_load_series (walk ChunkSetInfo blocks in host memory, gather into pinned slabs, H2D) + filo_query (kernels + D2H) + filo_table_free, per step")}
         if registered: ctx.host_unregister(arena)
+        # ---- the same query against the RESIDENT table (an incremental arena keeps a shard's chunks on the device, filo_table_append):
+        # no input crosses PCIe, the result is read back into the pinned host buffer every step
+        if aggr == capi.AGG_NONE and Se == S:
+            try:
+                def res_step():
+                    st_ = capi.Stats()
+                    ctx._check(L.filo_query(ctx.h, tab.h, fn, start, step, end, window, aggr, 0, 0, hout_np.ctypes.data_as(C.c_void_p), None, C.byref(st_)))
+                res_step()
+                if dist: dist.barrier()
+                t0 = time.perf_counter()
+                for _ in range(args.e2e_steps): res_step()
+                dtr = (time.perf_counter() - t0) / args.e2e_steps
+                if dist:
+                    t = torch.tensor([dtr], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dtr = float(t.item())
+                line["e2e_resident"] = {"value": Se * ROWS * world / dtr, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(n_out * 8), "s_per_step": dtr,
+                                        "what": "filo_query over the resident table (chunks already in the device arena, as after filo_table_append): kernels + D2H of the [series x T] result into pinned host memory"}
+            except Exception as e_:
+                line["e2e_resident"] = {"error": repr(e_)}
         del arena, keep, hout
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample, all host threads
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -9,7 +9,10 @@ constexpr int WP_MAXC = 4;             // chunks in range per series on this pat
 constexpr int WP_MAXG = 64;            // NibblePack groups per series (two per lane)
 constexpr int WP_R = 8;                // windows per block
 constexpr int WP_MAX_WARPS = 16;       // warps per CTA (one CTA per SM) when O has its own region
-constexpr int WP_MAX_WARPS_ALIAS = 20; // ... when O takes V's place (single-pass plans): bounded by 96 registers per thread
+#ifndef FILO_WP_MAX_WARPS_ALIAS
+#define FILO_WP_MAX_WARPS_ALIAS 20
+#endif
+constexpr int WP_MAX_WARPS_ALIAS = FILO_WP_MAX_WARPS_ALIAS; // ... when O takes V's place (single-pass plans): 20 warps = 96 registers per thread (22 = 88 registers, spills: A/B in profiles/r2)
 
 struct WpChunk {                       // per warp, per chunk in range (shared memory)
   uint64_t first;                      // XOR vectors: bits of the first value
