@@ -15,7 +15,7 @@ SCHEMA_LONG_VALUES = 2
 Q_PARTIAL = 1
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CORRUPT_VECTOR, ERR_UNSUPPORTED, ERR_QUERY_LIMIT, ERR_BAD_QUERY, ERR_OOM = 0, -1, -2, -3, -4, -5, -6, -7
 
-EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_ctx_set_fn_args", "filo_ctx_check", "filo_last_error", "filo_load_series", "filo_table_append", "filo_synth_table",
+EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_ctx_set_fn_args", "filo_ctx_check", "filo_last_error", "filo_load_series", "filo_table_append", "filo_synth_table", "filo_encode_table",
            "filo_table_set_groups", "filo_table_get_info", "filo_table_read_record", "filo_table_read_arena", "filo_table_free",
            "filo_num_windows", "filo_query", "filo_query_device", "filo_scan_series", "filo_query_hist", "filo_host_register", "filo_host_unregister", "filo_present_partials",
            "filo_result_max_containers", "filo_encode_result_device", "filo_encode_result"]
@@ -74,6 +74,7 @@ def _sig(L):
     L.filo_ctx_create.restype = i32; L.filo_ctx_create.argtypes = [i32, C.POINTER(Cfg), C.POINTER(vp)]
     L.filo_ctx_destroy.restype = None; L.filo_ctx_destroy.argtypes = [vp]
     L.filo_ctx_check.restype = i32; L.filo_ctx_check.argtypes = [vp]
+    L.filo_encode_table.restype = i32; L.filo_encode_table.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, vp, i32, C.POINTER(vp)]
     L.filo_table_append.restype = i32; L.filo_table_append.argtypes = [vp, vp, vp, vp, i32, i32]
     L.filo_result_max_containers.restype = i64; L.filo_result_max_containers.argtypes = [i64, i32]
     L.filo_encode_result.restype = i32; L.filo_encode_result.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, vp, vp, vp, C.POINTER(i64), C.POINTER(i64)]
@@ -225,6 +226,15 @@ class Context:
         g = np.ascontiguousarray(group_ids, np.int32) if group_ids is not None else None
         h = C.c_void_p()
         self._check(lib().filo_load_series(self.h, nch.size, _p(nch), _p(addrs), ts_col, val_col, _p(g), n_groups, schema_flags, C.byref(h)))
+        return Table(self, h)
+
+    def encode_table(self, timestamps, values, rows_per_chunk=400, value_enc=1, schema_flags=0, group_ids=None, n_groups=0):
+        """filo_encode_table: raw samples [n_series, rows] -> chunks encoded on the device -> resident table."""
+        ts = np.ascontiguousarray(timestamps, np.int64); v = np.ascontiguousarray(values, np.float64)
+        assert ts.shape == v.shape and ts.ndim == 2
+        g = np.ascontiguousarray(group_ids, np.int32) if group_ids is not None else None
+        h = C.c_void_p()
+        self._check(lib().filo_encode_table(self.h, _p(ts), _p(v), ts.shape[0], ts.shape[1], rows_per_chunk, value_enc, schema_flags, _p(g), n_groups, C.byref(h)))
         return Table(self, h)
 
     def synth_table(self, n_series, rows_per_series, rows_per_chunk=400, t0_ms=1_700_000_000_000, interval_ms=15000,

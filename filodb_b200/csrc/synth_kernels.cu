@@ -31,6 +31,8 @@ struct SynthParams {
   int64_t n_series; int32_t rows, rows_per_chunk; int64_t t0; int32_t interval, jitter;
   int32_t value_kind, value_enc, reset_period, nan_ppm, n_groups, cumulative;
   uint64_t seed; int64_t gid_base; const double* sin_table; double noise_scale;
+  // external samples (filo_encode_table): row-major [n_series][rows]; when set, `key` is the series ordinal and nothing is generated
+  const int64_t* ext_ts = nullptr; const double* ext_vals = nullptr;
 };
 
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -53,6 +55,7 @@ __device__ __forceinline__ double gauge_sample(const SynthParams& P, uint64_t ke
   return __dadd_rn(__dadd_rn(15.0, P.sin_table[row]), noise);
 }
 __device__ __forceinline__ double gen_value(const SynthParams& P, uint64_t key, int row, bool last_in_chunk, Gen& g) {
+  if (P.ext_vals) return P.ext_vals[(size_t)key * (size_t)P.rows + (size_t)row];
   if (last_in_chunk && P.nan_ppm > 0 && (int)(row_hash(key, row, 1) % 1000000ull) < P.nan_ppm)
     return __longlong_as_double(0x7ff8000000000000LL);
   const double s = gauge_sample(P, key, row);
@@ -64,6 +67,7 @@ __device__ __forceinline__ double gen_value(const SynthParams& P, uint64_t key, 
   return g.v;
 }
 __device__ __forceinline__ int64_t gen_ts(const SynthParams& P, uint64_t key, int row) {
+  if (P.ext_ts) return P.ext_ts[(size_t)key * (size_t)P.rows + (size_t)row];
   int64_t t = P.t0 + (int64_t)row * P.interval;
   if (P.jitter > 0) t += (int64_t)(row_hash(key, row, 3) % (uint64_t)(2 * P.jitter + 1)) - P.jitter;
   return t;
@@ -215,7 +219,7 @@ __global__ void synth_size_kernel(SynthParams P, uint32_t* rec_bytes, int32_t* g
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n_series) return;
   const uint64_t gid = (uint64_t)(P.gid_base + i);
-  const uint64_t key = series_key(P.seed, gid);
+  const uint64_t key = P.ext_vals ? (uint64_t)i : series_key(P.seed, gid);
   const int nch = (P.rows + P.rows_per_chunk - 1) / P.rows_per_chunk;
   uint32_t bytes = sizeof(RecordHeader) + (uint32_t)nch * sizeof(ChunkEntry);
   Gen g; g.v = 0.0;
@@ -233,7 +237,7 @@ __global__ void synth_fill_kernel(SynthParams P, const int64_t* rec_off, uint8_t
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n_series) return;
   const uint64_t gid = (uint64_t)(P.gid_base + i);
-  const uint64_t key = series_key(P.seed, gid);
+  const uint64_t key = P.ext_vals ? (uint64_t)i : series_key(P.seed, gid);
   const int nch = (P.rows + P.rows_per_chunk - 1) / P.rows_per_chunk;
   uint8_t* rec = arena + rec_off[i];
   const uint32_t rec_bytes = (uint32_t)(rec_off[i + 1] - rec_off[i]);
@@ -320,19 +324,57 @@ using namespace filo;
 #define S_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { std::string m = std::string(#expr) + ": " + cudaGetErrorString(_e); \
   return filo_internal_fail(ctx, _e == cudaErrorMemoryAllocation ? FILO_ERR_OOM : FILO_ERR_CUDA, m.c_str()); } } while (0)
 
+static int32_t synth_build(filo_ctx* ctx, const filo_synth_spec* sp, const int64_t* d_ext_ts, const double* d_ext_vals, const int32_t* h_group_ids, bool any_nonconst_ts, filo_table** out);
 extern "C" int32_t filo_synth_table(filo_ctx* ctx, const filo_synth_spec* sp, filo_table** out) {
   if (!ctx || !sp || !out) return filo_internal_fail(ctx, FILO_ERR_INVALID_ARG, "filo_synth_table: null argument");
   if (sp->n_series < 0 || sp->rows_per_series <= 0 || sp->rows_per_chunk <= 0 || sp->interval_ms <= 0 || !sp->sin_table ||
       sp->ts_jitter_ms < 0 || 2 * (int64_t)sp->ts_jitter_ms >= sp->interval_ms || sp->value_kind < 0 || sp->value_kind > 2 ||
       sp->value_enc < 0 || sp->value_enc > 2 || sp->rows_per_chunk > 4096)
     return filo_internal_fail(ctx, FILO_ERR_INVALID_ARG, "filo_synth_table: bad spec");
+  return synth_build(ctx, sp, nullptr, nullptr, nullptr, sp->ts_jitter_ms > 250, out);
+}
+
+// GPU-side encode of an ingest batch: raw samples (row-major [n_series][rows] timestamps and values in HOST memory) are copied to the
+// device and encoded there into the chunk vectors FiloDB's appenders + optimize() would write -- timestamps through
+// DeltaDeltaVector.fromLongVector with the +-250 ms approximate-const rule (DeltaDeltaVector.scala:20-80), values as raw doubles /
+// this repo's XOR-NibblePack container / DoubleVector.optimize (integral values -> DDV longs, DoubleVector.scala:86-96), the counter
+// drop flag from DoubleCounterAppender (DoubleVector.scala:456-466) -- chunked every rows_per_chunk rows, straight into a resident table.
+extern "C" int32_t filo_encode_table(filo_ctx* ctx, const int64_t* timestamps, const double* values, int64_t n_series, int32_t rows_per_series,
+                                     int32_t rows_per_chunk, int32_t value_enc, int32_t schema_flags, const int32_t* group_ids, int32_t n_groups,
+                                     filo_table** out) {
+  if (!ctx || !timestamps || !values || !out) return filo_internal_fail(ctx, FILO_ERR_INVALID_ARG, "filo_encode_table: null argument");
+  if (n_series < 0 || rows_per_series <= 0 || rows_per_chunk <= 0 || rows_per_chunk > 4096 || value_enc < 0 || value_enc > 2 || (group_ids && n_groups <= 0))
+    return filo_internal_fail(ctx, FILO_ERR_INVALID_ARG, "filo_encode_table: bad arguments");
+  for (int64_t i = 0; group_ids && i < n_series; ++i) if (group_ids[i] < 0 || group_ids[i] >= n_groups) return filo_internal_fail(ctx, FILO_ERR_INVALID_ARG, "group id out of range");
+  S_TRY(cudaSetDevice(filo_internal_device(ctx)));
+  cudaStream_t s = filo_internal_stream(ctx);
+  const size_t n = (size_t)n_series * (size_t)rows_per_series;
+  int64_t* d_ts = nullptr; double* d_v = nullptr;
+  S_TRY(cudaMalloc(&d_ts, std::max<size_t>(n, 1) * 8));
+  if (cudaMalloc(&d_v, std::max<size_t>(n, 1) * 8) != cudaSuccess) { cudaFree(d_ts); return filo_internal_fail(ctx, FILO_ERR_OOM, "filo_encode_table: staging"); }
+  struct FreeIn { void* a; void* b; ~FreeIn() { cudaFree(a); cudaFree(b); } } guard{d_ts, d_v};
+  S_TRY(cudaMemcpyAsync(d_ts, timestamps, n * 8, cudaMemcpyHostToDevice, s));
+  S_TRY(cudaMemcpyAsync(d_v, values, n * 8, cudaMemcpyHostToDevice, s));
+  // timestamps must increase inside a series (TimeSeriesPartition.ingest drops out-of-order samples, TimeSeriesPartition.scala:135-136)
+  for (int64_t i = 0; i < n_series; ++i)
+    for (int32_t r = 1; r < rows_per_series; ++r)
+      if (!(timestamps[(size_t)i * rows_per_series + r] > timestamps[(size_t)i * rows_per_series + r - 1]))
+        return filo_internal_fail(ctx, FILO_ERR_INVALID_ARG, "filo_encode_table: timestamps of a series must be strictly increasing");
+  filo_synth_spec sp{};
+  sp.n_series = n_series; sp.rows_per_series = rows_per_series; sp.rows_per_chunk = rows_per_chunk; sp.t0_ms = 0; sp.interval_ms = 1; sp.ts_jitter_ms = 0;
+  sp.value_kind = 0; sp.value_enc = value_enc; sp.reset_period = 0; sp.nan_per_million = 0; sp.n_groups = group_ids ? n_groups : 0; sp.schema_flags = schema_flags;
+  sp.seed = 0; sp.series_id_base = 0; sp.sin_table = nullptr;
+  return synth_build(ctx, &sp, d_ts, d_v, group_ids, true, out);
+}
+
+static int32_t synth_build(filo_ctx* ctx, const filo_synth_spec* sp, const int64_t* d_ext_ts, const double* d_ext_vals, const int32_t* h_group_ids, bool any_nonconst_ts, filo_table** out) {
   S_TRY(cudaSetDevice(filo_internal_device(ctx)));
   cudaStream_t s = filo_internal_stream(ctx);
   const int64_t S = sp->n_series;
   double* d_sin = nullptr; uint32_t* d_bytes = nullptr; int32_t* d_gid = nullptr; int64_t* d_off = nullptr; int64_t* d_wide = nullptr;
   unsigned long long* d_alg = nullptr; uint8_t* d_arena = nullptr;
   S_TRY(cudaMalloc(&d_sin, (size_t)sp->rows_per_series * 8));
-  S_TRY(cudaMemcpyAsync(d_sin, sp->sin_table, (size_t)sp->rows_per_series * 8, cudaMemcpyHostToDevice, s));
+  if (sp->sin_table) S_TRY(cudaMemcpyAsync(d_sin, sp->sin_table, (size_t)sp->rows_per_series * 8, cudaMemcpyHostToDevice, s));
   S_TRY(cudaMalloc(&d_bytes, (size_t)(S + 1) * 4)); S_TRY(cudaMalloc(&d_wide, (size_t)(S + 1) * 8)); S_TRY(cudaMalloc(&d_off, (size_t)(S + 1) * 8));
   S_TRY(cudaMemsetAsync(d_bytes, 0, (size_t)(S + 1) * 4, s));
   if (sp->n_groups > 0) S_TRY(cudaMalloc(&d_gid, (size_t)std::max<int64_t>(S, 1) * 4));
@@ -340,8 +382,10 @@ extern "C" int32_t filo_synth_table(filo_ctx* ctx, const filo_synth_spec* sp, fi
   SynthParams P{S, sp->rows_per_series, sp->rows_per_chunk, sp->t0_ms, sp->interval_ms, sp->ts_jitter_ms, sp->value_kind, sp->value_enc,
                 sp->reset_period, sp->nan_per_million, sp->n_groups, (sp->schema_flags & FILO_SCHEMA_CUMULATIVE) ? 1 : 0,
                 sp->seed, sp->series_id_base, d_sin, 1.0 / 37837.22772881784};
+  P.ext_ts = d_ext_ts; P.ext_vals = d_ext_vals;
   const unsigned blocks = (unsigned)((S + 127) / 128);
   if (S > 0) { synth_size_kernel<<<blocks, 128, 0, s>>>(P, d_bytes, d_gid); S_TRY(cudaGetLastError()); }
+  if (h_group_ids && d_gid && S > 0) S_TRY(cudaMemcpyAsync(d_gid, h_group_ids, (size_t)S * 4, cudaMemcpyHostToDevice, s));      // the caller's grouping replaces the generator's
   widen_kernel<<<(unsigned)((S + 1 + 255) / 256), 256, 0, s>>>(d_bytes, d_wide, S + 1); S_TRY(cudaGetLastError());
   size_t tmpb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tmpb, d_wide, d_off, (int)(S + 1), s);
   void* tmp = nullptr; S_TRY(cudaMalloc(&tmp, tmpb + 16));
@@ -370,7 +414,7 @@ extern "C" int32_t filo_synth_table(filo_ctx* ctx, const filo_synth_spec* sp, fi
   filo_table* t = filo_internal_new_table();
   filo_internal_set_arena(t, d_arena, d_off, S, S * nch, S * (int64_t)sp->rows_per_series, arena_bytes + (S + 1) * 8, (int64_t)alg,
                           sp->rows_per_series, nch, sp->schema_flags);
-  filo_internal_set_layout(t, max_rec, sp->ts_jitter_ms > 250, (sp->schema_flags & FILO_SCHEMA_CUMULATIVE) != 0);
+  filo_internal_set_layout(t, max_rec, any_nonconst_ts, (sp->schema_flags & FILO_SCHEMA_CUMULATIVE) != 0);
   int32_t rc = filo_internal_finish_table(ctx, t, d_gid, sp->n_groups > 0 ? sp->n_groups : 1);
   cudaFree(d_gid);
   if (rc) { filo_table_free(ctx, t); return rc; }

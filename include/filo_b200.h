@@ -180,6 +180,15 @@ int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32_t* n_chunk
  * serialises appends against queries of the same table. */
 int32_t filo_table_append(filo_ctx* ctx, filo_table* t, const int32_t* n_chunks, const uint64_t* chunk_info_addrs, int32_t ts_col, int32_t val_col);
 int32_t filo_synth_table(filo_ctx* ctx, const filo_synth_spec* spec, filo_table** out);
+/* GPU-side encode of an ingest batch: raw samples -- timestamps / values row-major [n_series][rows_per_series] in HOST memory, strictly
+ * increasing timestamps per series -- are encoded on the device into the chunk vectors the reference's appenders + optimize() write
+ * (timestamps: DeltaDeltaVector.fromLongVector incl. the +-250 ms approximate-const rule, DeltaDeltaVector.scala:20-80; values by
+ * value_enc: 0 raw doubles, 1 XOR-NibblePack container, 2 DoubleVector.optimize, DoubleVector.scala:86-96; counter drop flag with
+ * FILO_SCHEMA_CUMULATIVE, DoubleVector.scala:456-466), one chunk per rows_per_chunk rows, into a resident table (same bytes as
+ * filo_load_series over the JVM-encoded chunks).  group_ids may be NULL. */
+int32_t filo_encode_table(filo_ctx* ctx, const int64_t* timestamps, const double* values, int64_t n_series, int32_t rows_per_series,
+                          int32_t rows_per_chunk, int32_t value_enc, int32_t schema_flags, const int32_t* group_ids, int32_t n_groups,
+                          filo_table** out);
 int32_t filo_table_set_groups(filo_ctx* ctx, filo_table* t, const int32_t* group_ids, int32_t n_groups);
 int32_t filo_table_get_info(const filo_table* t, filo_table_info* out);
 /* Copies the device arena record of one series back to the host (tests: byte parity of the GPU encoder). */

@@ -802,3 +802,42 @@ def test_incremental_arena_append(gpu, oracle):
     assert e.value.code == capi.ERR_UNSUPPORTED
     check(4)
     tab.free()
+
+
+@pytest.mark.parametrize("value_enc", [0, 1, 2])
+def test_encode_ingest_batch_on_gpu(gpu, oracle, value_enc):
+    """filo_encode_table: raw samples encoded on the device into the appenders' bytes (DeltaDeltaVector.fromLongVector incl. the +-250 ms
+    rule, DoubleVector.optimize / raw / XOR container, counter drop flag), byte for byte the oracle's encoders; queries agree."""
+    capi, ctx = gpu; o = oracle
+    rng = np.random.default_rng(50 + value_enc)
+    S, rows, rpc, t0 = 21, 230, 100, 1_700_000_000_000
+    ts = np.zeros((S, rows), np.int64); vals = np.zeros((S, rows), np.float64)
+    for s in range(S):
+        jit = (0, 100, 3000)[s % 3]
+        ts[s] = t0 + np.arange(rows) * 15000 + (rng.integers(-jit, jit + 1, rows) if jit else 0)
+        if s % 2: v = np.cumsum(rng.integers(0, 30, rows)).astype(float)              # integral counters (DDV longs under optimize)
+        else: v = np.cumsum(np.maximum(0, 15 + rng.normal(0, 2, rows)))
+        for r in np.nonzero(rng.random(rows) < 0.01)[0]:
+            if r > 0: v[r:] = v[r:] - v[r] + 1.0                                       # counter resets
+        if s % 5 == 0: v[rng.random(rows) < 0.02] = NaN
+        vals[s] = v
+    gids = np.arange(S, dtype=np.int32) % 4
+    tab = ctx.encode_table(ts, vals, rows_per_chunk=rpc, value_enc=value_enc, schema_flags=capi.SCHEMA_CUMULATIVE, group_ids=gids, n_groups=4)
+    val_mode = {0: o.VAL_RAW, 1: o.VAL_XOR, 2: o.VAL_OPTIMIZE}[value_enc]
+    st = o.Store()
+    chunk_rows = [100, 100, 30]
+    for s in range(S):
+        st.add_series_rows(ts[s], vals[s], chunk_rows, val_mode=val_mode, detect_drops=True)
+    ref = ctx.load_series(*st.all_info_addrs(), schema_flags=capi.SCHEMA_CUMULATIVE)
+    a1, o1 = tab.read_arena(0, S); a2, o2 = ref.read_arena(0, S)
+    assert (o1 == o2).all() and (a1 == a2).all(), "device-encoded arena differs from the appenders' bytes"
+    assert tab.info().algorithmic_bytes == st.algorithmic_bytes()
+    q = (t0 + 300000, 15000, t0 + (rows - 1) * 15000, 300000)
+    for name in ("FN_RATE", "FN_SUM_OVER_TIME", "FN_LAST"):
+        assert_same(ctx.query(tab, getattr(capi, name), *q), st.query(getattr(o, name), *q, cumulative=True), "encoded table %s" % name)
+    got = ctx.query(tab, capi.FN_RATE, *q, aggr=capi.AGG_SUM)
+    np.testing.assert_allclose(got, st.query(o.FN_RATE, *q, cumulative=True, aggr=o.AGG_SUM, group_ids=gids, n_groups=4), rtol=1e-9, equal_nan=True)
+    with pytest.raises(capi.FiloError):
+        bad = ts.copy(); bad[0, 5] = bad[0, 4]
+        ctx.encode_table(bad, vals)
+    tab.free(); ref.free()
