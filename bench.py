@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-staged", action="store_true", help="e2e leg: stage inputs through pinned slabs on the host instead of the registered-memory gather")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the kernel-only sub-records of the other BASELINE configs (C1, C3, C3-const, C4) of the default single-GPU C2 run")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 sub-record (sum(rate) by(cluster) with the NCCL all-reduce) of the default C2 run")
     return ap.parse_args()
 
@@ -767,9 +768,25 @@ def main():
             tab2.free()
         except Exception as e:      # the check must not take the measurement down; its failure is reported
             line["parity_check"] = {"error": repr(e)}
+    tab.free(); ctx.close()
+    # ---- the other BASELINE configs beside the headline one (single GPU, default workload only): each runs kernel-only in a child
+    # process of this script after this process has released the device memory; their lines are attached as sub-records
+    if rank == 0 and world == 1 and args.workload == "c2" and not args.no_extra:
+        torch.cuda.empty_cache()
+        extra = {}
+        for wl, steps in (("c1", 20), ("c3-const", 6), ("c3", 3), ("c4", 4)):
+            try:
+                cmd = [sys.executable, os.path.abspath(__file__), "--workload", wl, "--steps", str(steps), "--warmup", "3", "--no-e2e", "--no-c5", "--no-extra", "--no-cpu"]
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+                d = json.loads(r.stdout.strip().splitlines()[-1])
+                extra[wl] = {"workload": d["config"]["workload"], "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "steps": d["steps"],
+                             "roofline": {k: d["roofline"].get(k) for k in ("achieved", "peak", "frac", "kernel_ms", "algorithmic_bytes", "kernel")},
+                             "parity_check": d.get("parity_check")}
+            except Exception as e_:
+                extra[wl] = {"error": repr(e_)}
+        line["other_configs"] = extra
     if rank == 0:
         print(json.dumps(line), flush=True)
-    tab.free(); ctx.close()
     if dist: dist.destroy_process_group()
 
 
