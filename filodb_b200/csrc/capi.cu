@@ -258,6 +258,14 @@ int32_t filo_internal_fail(filo_ctx* ctx, int32_t code, const char* msg) { retur
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
 
+struct GatherChunk {            // one chunk with rows, in series order
+  uint64_t ts_src, val_src;     // host addresses (UVA) of the vectors to copy
+  int64_t start_time, end_time;
+  int32_t num_rows, ts_bytes, val_bytes, val_len;
+  int32_t drop_patch, pad;      // 0: keep, 1: set, 2: clear the counter drop bit (masked wrappers carry it on the outer vector)
+};
+struct GatherSeries { uint32_t rec_bytes, n_chunks, n_rows, flags; int64_t first_chunk; };
+
 struct VecInfo { const uint8_t* p; int32_t total; int32_t len; bool drop_patch; bool drop; bool hist = false; };
 
 inline int32_t rd32(const uint8_t* p) { int32_t v; std::memcpy(&v, p, 4); return v; }
@@ -311,9 +319,12 @@ int classify_val(const uint8_t* v, VecInfo& o) {
 
 struct SeriesPlan { uint32_t rec_bytes; uint32_t n_chunks; uint32_t n_rows; uint32_t flags; };
 
-struct LoadIn { int64_t n_series; const int32_t* n_chunks; const uint64_t* addrs; const int64_t* chunk_base; int32_t ts_col, val_col; };
+struct LoadIn { int64_t n_series; const int32_t* n_chunks; const uint64_t* addrs; const int64_t* chunk_base; int32_t ts_col, val_col;
+                // filo_scan_series: the one walk over the ChunkSetInfo blocks also leaves the gather entries of the chunks with rows (entry k of
+                // series i at gc_out[chunk_base[i] - gc_base + k]) and checks the vectors against the registered host ranges
+                GatherChunk* gc_out = nullptr; int64_t gc_base = 0; const std::vector<filo_ctx::HostRange>* ranges = nullptr; };
 struct PlanTotals { int64_t chunks = 0, samples = 0, alg = 0; int32_t maxrows = 0, maxch = 0; uint32_t max_rec = 0, f_or = 0, f_and = ~0u;
-                    const uint8_t* hist_def = nullptr; bool any_scalar = false, hist_mismatch = false; };
+                    const uint8_t* hist_def = nullptr; bool any_scalar = false, hist_mismatch = false; bool all_in_ranges = true; };
 // same bucket scheme: format code, definition length and bytes of two HistogramVector headers (HistogramVector.matchBucketDef, :262-268)
 inline bool same_hist_def(const uint8_t* a, const uint8_t* b) {
   const int da = (uint16_t)(a[9] | (a[10] << 8)), db = (uint16_t)(b[9] | (b[10] << 8));
@@ -345,6 +356,17 @@ inline int plan_series(const LoadIn& in, int64_t i, SeriesPlan& out, PlanTotals&
     if (vv.hist) { flags |= REC_HIST; if (!tot.hist_def) tot.hist_def = vv.p; else if (vv.len > 0 && !same_hist_def(tot.hist_def, vv.p)) tot.hist_mismatch = true; }
     else tot.any_scalar = true;
     tot.samples += numRows; tot.alg += 28 + 16 + tv.total + vv.total;
+    if (in.gc_out) {
+      GatherChunk g;
+      g.ts_src = (uint64_t)(uintptr_t)tv.p; g.val_src = (uint64_t)(uintptr_t)vv.p; g.start_time = startT; g.end_time = endT;
+      g.num_rows = numRows; g.ts_bytes = tv.total; g.val_bytes = vv.total; g.val_len = vv.len;
+      g.drop_patch = vv.drop_patch ? (vv.drop ? 1 : 2) : 0; g.pad = 0;
+      in.gc_out[in.chunk_base[i] - in.gc_base + (int64_t)nch - 1] = g;
+      if (in.ranges && tot.all_in_ranges) {
+        auto inr = [&](const uint8_t* p, size_t n) { for (auto& r : *in.ranges) if ((uintptr_t)p >= r.base && (uintptr_t)p + n <= r.base + r.bytes) return true; return false; };
+        if (!inr(tv.p, (size_t)tv.total) || !inr(vv.p, (size_t)vv.total)) tot.all_in_ranges = false;
+      }
+    }
   }
   out = SeriesPlan{align_up(bytes, 16), nch, rows, flags};
   tot.chunks += nch; tot.maxrows = std::max<int32_t>(tot.maxrows, (int32_t)rows); tot.maxch = std::max<int32_t>(tot.maxch, (int32_t)nch);
@@ -355,7 +377,7 @@ inline void merge_totals(PlanTotals& a, const PlanTotals& b) {
   a.chunks += b.chunks; a.samples += b.samples; a.alg += b.alg; a.maxrows = std::max(a.maxrows, b.maxrows); a.maxch = std::max(a.maxch, b.maxch);
   a.max_rec = std::max(a.max_rec, b.max_rec); a.f_or |= b.f_or; a.f_and &= b.f_and;
   if (!a.hist_def) a.hist_def = b.hist_def; else if (b.hist_def && !same_hist_def(a.hist_def, b.hist_def)) a.hist_mismatch = true;
-  a.any_scalar |= b.any_scalar; a.hist_mismatch |= b.hist_mismatch;
+  a.any_scalar |= b.any_scalar; a.hist_mismatch |= b.hist_mismatch; a.all_in_ranges = a.all_in_ranges && b.all_in_ranges;
 }
 // host NibblePack.unpackDoubleXOR (NibblePack.scala:374-447) for the custom bucket tops of a table (a few dozen values)
 inline bool host_unpack_double_xor(const uint8_t* buf, int cap, double* out, int n) {
@@ -859,7 +881,7 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
   auto wp_ctr_plan = [&](bool agg_mode, WpCtrSmem& W) -> bool {
     const bool want_v3 = force && std::string(force) == "v3";
     if (!use_tile || want_v3 || fn_cls != CLASS_COUNTER || t->max_chunks <= 0) return false;
-    W = wp_ctr_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)t->max_chunks, (uint32_t)q.T, agg_mode);
+    W = wp_ctr_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)t->max_chunks, (uint32_t)q.T, agg_mode, t->any_nonconst_ts);
     const size_t cap = std::min<size_t>(ctx->max_smem_optin, 227 * 1024) - sizeof(TileCtrTab) * (TILE_CTR_TABMAX + 1) - 64;
     size_t w = cap / W.per_warp; if (w > (size_t)WP_CTR_MAX_WARPS) w = WP_CTR_MAX_WARPS;
     static const int warps_env = [] { const char* e = std::getenv("FILO_WP_WARPS"); return e ? atoi(e) : 0; }();
@@ -1006,13 +1028,6 @@ extern "C" int32_t filo_query(filo_ctx* ctx, const filo_table* t, int32_t fn, in
 // zero-copy gather: the GPU reads chunk vectors straight out of registered (pinned, mapped) host memory
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
-struct GatherChunk {            // one chunk with rows, in series order
-  uint64_t ts_src, val_src;     // host addresses (UVA) of the vectors to copy
-  int64_t start_time, end_time;
-  int32_t num_rows, ts_bytes, val_bytes, val_len;
-  int32_t drop_patch, pad;      // 0: keep, 1: set, 2: clear the counter drop bit (masked wrappers carry it on the outer vector)
-};
-struct GatherSeries { uint32_t rec_bytes, n_chunks, n_rows, flags; int64_t first_chunk; };
 
 __device__ __forceinline__ void copy_bytes_warp(uint8_t* dst, const uint8_t* src, int n, int lane) {
   // dst is 8-byte aligned; BinaryVectors are allocated word aligned (32-bit loads measured faster than 64-bit ones over PCIe)
@@ -1120,8 +1135,9 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
   // The series are planned (validated + sized, same rules as filo_load_series) in chunks of PLAN_CHUNK series right before their batches
   // are enqueued, so that the host walk of chunk k + 1 runs while the GPU still works on the batches of chunk k.
   std::vector<SeriesPlan> plan((size_t)n_series);
-  const LoadIn in{n_series, n_chunks, addrs, chunk_base.data(), ts_col, val_col};
+  LoadIn in{n_series, n_chunks, addrs, chunk_base.data(), ts_col, val_col};
   const int64_t PLAN_CHUNK = 65536;
+  std::vector<GatherChunk> gc_walk;                     // gather entries of the plan chunk, written by the planning walk
   const size_t SLAB = (size_t)192 << 20;
   const int64_t max_rows_out = std::max<int64_t>(1, (int64_t)(((size_t)256 << 20) / ((size_t)std::max(T, 1) * 8)));
   struct Batch { int64_t s0, s1; size_t bytes; int64_t chunks; };
@@ -1153,6 +1169,10 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
     const int64_t c1 = std::min<int64_t>(n_series, c0 + PLAN_CHUNK);
     const auto t_p0 = now();
     PlanTotals tot; int64_t err_series = -1;
+    if (!ranges.empty()) {                              // one walk: plan + gather entries + range check
+      gc_walk.resize((size_t)(chunk_base[(size_t)c1] - chunk_base[(size_t)c0]) + 1);
+      in.gc_out = gc_walk.data(); in.gc_base = chunk_base[(size_t)c0]; in.ranges = &ranges;
+    }
     if (const int err_code = plan_range(in, c0, c1, plan, tot, err_series)) {
       const char* what = err_code == FILO_ERR_UNSUPPORTED ? "chunks of a series are not in increasing time order (unsupported on the device path)"
                                                          : "CorruptVector: unknown or inconsistent BinaryVector wire format";
@@ -1161,23 +1181,8 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
     alg_total += tot.alg;
     if (ctx->cfg.max_data_per_shard_query > 0 && alg_total > ctx->cfg.max_data_per_shard_query) { rc = fail(ctx, FILO_ERR_QUERY_LIMIT, "raw data bytes scanned exceeds max-data-per-shard-query"); break; }
     if (tot.hist_def) { rc = fail(ctx, FILO_ERR_UNSUPPORTED, "filo_scan_series: histogram columns go through filo_load_series + filo_query_hist"); break; }
-    // zero-copy gather when every vector of the chunk lies in memory registered with filo_host_register
-    bool use_gather = !ranges.empty();
-    if (use_gather) {
-      std::atomic<bool> all_in{true};
-      host_pool().run(c1 - c0, [&](int, int64_t b, int64_t e) {
-        for (int64_t i = c0 + b; i < c0 + e && all_in.load(std::memory_order_relaxed); ++i)
-          for (int32_t j = 0; j < n_chunks[i]; ++j) {
-            const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)addrs[chunk_base[(size_t)i] + j]);
-            if (rd32(info + 8) <= 0) continue;
-            VecInfo tv, vv;
-            classify_ts(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * ts_col)), tv);
-            classify_val(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * val_col)), vv);
-            if (!in_ranges(tv.p, (size_t)tv.total) || !in_ranges(vv.p, (size_t)vv.total)) { all_in = false; break; }
-          }
-      });
-      use_gather = all_in.load();
-    }
+    // zero-copy gather when every vector of the chunk lies in memory registered with filo_host_register (checked by the planning walk)
+    const bool use_gather = !ranges.empty() && tot.all_in_ranges;
     // batches of the chunk: consecutive series, <= SLAB bytes of records and a bounded result block
     std::vector<Batch> batches;
     for (int64_t s0 = c0; s0 < c1;) {
@@ -1219,25 +1224,16 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
       int64_t cb = 0;
       for (int64_t j = 0; j < nb; ++j) { const SeriesPlan& p = plan[(size_t)(B.s0 + j)]; gs[j] = GatherSeries{p.rec_bytes, p.n_chunks, p.n_rows, p.flags, cb}; cb += p.n_chunks; }
       std::atomic<uint64_t> span_lo{~0ull}, span_hi{0};       // host span that holds the batch's vectors
-      host_pool().run(nb, [&](int, int64_t b, int64_t e) {
+      host_pool().run(nb, [&](int, int64_t b, int64_t e) {     // the walk's entries, compacted into the batch's list
         uint64_t lo = ~0ull, hi = 0;
         for (int64_t j = b; j < e; ++j) {
           const int64_t i = B.s0 + j; GatherChunk* o = gc + gs[j].first_chunk;
-          for (int32_t jj = 0; jj < n_chunks[i]; ++jj) {
-            const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)addrs[chunk_base[(size_t)i] + jj]);
-            const int32_t numRows = rd32(info + 8);
-            if (numRows <= 0) continue;
-            VecInfo tv, vv;
-            classify_ts(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * ts_col)), tv);
-            classify_val(reinterpret_cast<const uint8_t*>((uintptr_t)rd64(info + 28 + 8 * val_col)), vv);
-            GatherChunk g;
-            g.ts_src = (uint64_t)(uintptr_t)tv.p; g.val_src = (uint64_t)(uintptr_t)vv.p;
-            g.start_time = (int64_t)(((1ull << 63) ^ (uint64_t)rd64(info)) >> 22); g.end_time = rd64(info + 20);
-            g.num_rows = numRows; g.ts_bytes = tv.total; g.val_bytes = vv.total; g.val_len = vv.len;
-            g.drop_patch = vv.drop_patch ? (vv.drop ? 1 : 2) : 0; g.pad = 0;
+          const GatherChunk* src = gc_walk.data() + (chunk_base[(size_t)i] - in.gc_base);
+          for (uint32_t jj = 0; jj < gs[j].n_chunks; ++jj) {
+            const GatherChunk g = src[jj];
             *o++ = g;
             lo = std::min(lo, std::min(g.ts_src, g.val_src));
-            hi = std::max(hi, std::max(g.ts_src + (uint64_t)tv.total, g.val_src + (uint64_t)vv.total));
+            hi = std::max(hi, std::max(g.ts_src + (uint64_t)g.ts_bytes, g.val_src + (uint64_t)g.val_bytes));
           }
         }
         uint64_t cur = span_lo.load(); while (lo < cur && !span_lo.compare_exchange_weak(cur, lo)) {}

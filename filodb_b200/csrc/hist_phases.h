@@ -25,7 +25,10 @@ namespace filo {
 constexpr int H2_THREADS = 512;
 constexpr int H2_MAXC = 8;          // chunks in range per series
 constexpr int H2_MAXSECT = 96;      // sections per series
-constexpr int H2_BATCH = 4;         // buckets whose partial sums are loaded ahead of the arithmetic
+#ifndef FILO_H2_BATCH
+#define FILO_H2_BATCH 4
+#endif
+constexpr int H2_BATCH = FILO_H2_BATCH;         // buckets whose partial sums are loaded ahead of the arithmetic
 
 struct H2Sect { int32_t chunk, start_row /* row (over the series' chunks in range) of the section's first histogram */, n, type; uint32_t first_rec /* byte offset in record */; };
 struct H2Chunk { int32_t row_base, nrows, nsect, has_drop, sect, ts_wire; int64_t end_time; uint32_t ts_off, pad; };

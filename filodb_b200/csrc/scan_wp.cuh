@@ -109,12 +109,14 @@ __device__ __forceinline__ void wp_block_pair(const double* __restrict__ pa, con
 
 // per-series parse, lane c = chunk c of the chunks in range: what the record says about the chunk, and whether the series qualifies
 struct WpParsed {
-  bool regular, have, any_raw; int n, cLo;
+  bool regular, have, any_raw; bool irr;            // irr: some chunk's timestamps are not on the query's step grid (DDV residuals or slope != step)
+  int tslope; uint32_t toff;                         // timestamp vector: slope, byte offset in R
+  int n, cLo;
   int64_t init, end_time; int nrows, num_rows, vbytes, ng, vwire, dropped, tlen, grp_base, ngroups; uint32_t voff, w12;
 };
 // STRICT (SUM class): endTime covers the chunk's rows and lies before the next chunk's first row, so that "has a row in the window" and
 // "is in the window's chunk set" (ChunkSetInfo.scala:481-510) coincide; the counter class evaluates the chunk set itself
-template <bool STRICT>
+template <bool STRICT, bool IRR = false>
 __device__ __forceinline__ WpParsed wp_parse(const uint8_t* R, const QueryParams& q, bool staged, int lane) {
   const unsigned FULL = 0xffffffffu;
   WpParsed P;
@@ -124,7 +126,7 @@ __device__ __forceinline__ WpParsed wp_parse(const uint8_t* R, const QueryParams
     const RecordHeader* h = reinterpret_cast<const RecordHeader*>(R);
     const ChunkEntry* Eall = reinterpret_cast<const ChunkEntry*>(R + sizeof(RecordHeader));
     const int nch = (int)h->n_chunks;
-    regular = nch <= 32 && (h->flags & REC_ALL_TS_CONST) != 0;
+    regular = nch <= 32 && (IRR || (h->flags & REC_ALL_TS_CONST) != 0);
     const int64_t t1 = q.start - q.window, t2 = q.end;
     bool below = false, within = false;
     if (regular && lane < nch) { below = Eall[lane].end_time < t1; within = !below && Eall[lane].start_time <= t2; }
@@ -137,20 +139,28 @@ __device__ __forceinline__ WpParsed wp_parse(const uint8_t* R, const QueryParams
   const int c = lane;
   bool have = regular && c < n;
   int64_t init = 0, end_time = 0; int nrows = 0, num_rows = 0, vbytes = 0, ng = 0, vwire = 0, dropped = 0, tlen = 0; uint32_t voff = 0, w12 = 0;
-  bool okc = true;
+  bool okc = true, irrc = false; int slope = 0; uint32_t toff = 0;
   if (have) {
     const ChunkEntry& e = reinterpret_cast<const ChunkEntry*>(R + sizeof(RecordHeader))[cLo + c];
     const uint8_t* tv = R + e.ts_off; const uint8_t* vv = R + e.val_off;
     const uint32_t vw4 = ld32(vv + 4);
     vwire = (int)(vw4 & 0xffff); dropped = (int)((vw4 >> 31) & 1);
-    tlen = (int)ld32(tv + 8); init = (int64_t)ld64_a4(tv + 12); const int slope = (int)ld32(tv + 20);
+    toff = e.ts_off;
+    const int twire = (int)(ld32(tv + 4) & 0xffff);
+    if (!IRR || twire == WIRE_DDV_CONST) { tlen = (int)ld32(tv + 8); init = (int64_t)ld64_a4(tv + 12); slope = (int)ld32(tv + 20); if (IRR && twire != WIRE_DDV_CONST) okc = false; }
+    else if (twire == WIRE_DDV) {                          // DeltaDeltaVector.scala:138-156: +8 init, +16 slope, +20 IntBinaryVector of residuals
+      init = (int64_t)ld64(tv + 8); slope = (int)ld32(tv + 16); tlen = int_length(tv + 20); irrc = true;
+      const int nb = (int)((ld32(tv + 24) >> 16) & 0x7f);
+      if (!(nb == 2 || nb == 4 || nb == 8 || nb == 16 || nb == 32)) okc = false;
+    } else okc = false;
+    if (IRR && (int64_t)slope != q.step) irrc = true;
     end_time = e.end_time; num_rows = e.num_rows; voff = e.val_off;
     vbytes = (int)ld32(tv) + 4 + (int)ld32(vv) + 4;
     int vlen = 0;
     if (vwire == WIRE_XOR) { vlen = (int)ld32(vv + XOR_OFF_N); w12 = ld32(vv + XOR_OFF_NGROUPS); ng = (int)(w12 & 0xffff); if (ng != (vlen + 6) / 8) okc = false; }
     else if (vwire == WIRE_RAW64) vlen = ((int)ld32(vv) - 4) / 8;
     else okc = false;
-    if ((int64_t)slope != q.step || tlen <= 0 || vlen <= 0 || num_rows <= 0) okc = false;
+    if ((!IRR && (int64_t)slope != q.step) || slope <= 0 || tlen <= 0 || vlen <= 0 || num_rows <= 0) okc = false;
     nrows = num_rows < tlen ? num_rows : tlen;
     if (vlen != nrows) okc = false;                       // the decode writes every row of the vector
     if (STRICT && end_time < init + (int64_t)(nrows - 1) * q.step) okc = false;
@@ -169,6 +179,7 @@ __device__ __forceinline__ WpParsed wp_parse(const uint8_t* R, const QueryParams
     if (a0 + a1 + a2 + a3 > WP_MAXG) regular = false; }
   P.ngroups = __shfl_sync(FULL, grp_base + ng, WP_MAXC - 1);
   P.any_raw = __any_sync(FULL, have && vwire == WIRE_RAW64);
+  P.irr = IRR && __any_sync(FULL, have && irrc); P.tslope = slope; P.toff = toff;
   P.regular = regular; P.have = have && regular; P.n = n; P.cLo = cLo; P.init = init; P.end_time = end_time; P.nrows = nrows; P.num_rows = num_rows;
   P.vbytes = vbytes; P.ng = ng; P.vwire = vwire; P.dropped = dropped; P.tlen = tlen; P.grp_base = grp_base; P.voff = voff; P.w12 = w12;
   return P;

@@ -73,6 +73,60 @@ WP_CTR_RARE double wp_eval_counter(int n, const WpCtrChunk* K, const WpChunk* CD
   return NaNv;
 }
 
+// ---- irregular timestamps (DDV with residuals, or a scrape interval that differs from the query step): row times live in TSR as int32
+// offsets from the chunk's first timestamp (TSR[rowpos + r] = ts(r) - init); row ranges by a guess on the chunk's slope + a short walk
+// (exact for any data: the walk ends at the first row with ts >= t)
+__device__ __forceinline__ int wp_irr_lower(const int32_t* TSR, const WpCtrChunk& ch, int64_t t) {
+  const int64_t d = t - ch.init;
+  if (d <= 0) return 0;
+  const int32_t* p = TSR + ch.rowpos;
+  if (d > (int64_t)p[ch.nrows - 1]) return ch.nrows;
+  int g = (int)((double)d * ch.kc.sI);                     // kc.sI holds 1 / slope for an irregular series
+  if (g > ch.nrows - 1) g = ch.nrows - 1;
+  while (g < ch.nrows && (int64_t)p[g] < d) ++g;
+  while (g > 0 && (int64_t)p[g - 1] >= d) --g;
+  return g;
+}
+// the literal fold of wp_eval_counter with searched row ranges and stored sample times
+template <int FN>
+__device__ __forceinline__ double wp_eval_counter_irr(int n, const WpCtrChunk* K, const WpChunk* CD, const TileDrops* DR, const double* V, const int32_t* TSR,
+                                                      int64_t qstep, int qinclusive, int64_t wStart, int64_t wEnd, double fdiv, double frcp, const TileCtrTab* tab) {
+  const double NaNv = __longlong_as_double(0x7ff8000000000000LL);
+  int32_t numSamples = 0; int64_t loT = INT64_MAX, hiT = 0; double loV = NaNv, hiV = NaNv;
+  bool some = false; double corrLast = 0.0, corr = 0.0;
+  for (int c = 0; c < n; ++c) {
+    const WpCtrChunk& ch = K[c];
+    if (ch.end_time < wStart) continue;                                // ChunkSetInfo.scala:481-510
+    if (c > 0 && !(K[c - 1].end_time < wEnd)) continue;
+    const int su = wp_irr_lower(TSR, ch, wStart);
+    int eu = wp_irr_lower(TSR, ch, wEnd + 1) - 1; if (eu > ch.nrows - 1) eu = ch.nrows - 1;
+    const double first = __longlong_as_double((long long)CD[c].first);
+    if (FN != FN_DELTA && some) { if (first != first || first < corrLast) corr = corr + corrLast; }
+    if (su <= eu) {
+      const int64_t tS = ch.init + (int64_t)TSR[ch.rowpos + su], tE = ch.init + (int64_t)TSR[ch.rowpos + eu];
+      const bool skip = FN != FN_DELTA && su == 0 && eu == 0 && first != first;      // RateFunctions.scala:255-256
+      if (!skip && (tS < loT || tE > hiT)) {
+        numSamples += eu - su + 1;
+        const bool drp = FN != FN_DELTA && ch.kc.dropped;
+        if (tS < loT) { loT = tS; const double b = wp_ctr_value(V, ch, su, DR[c], drp); loV = (FN != FN_DELTA && some) ? b + corr : b; }
+        if (tE > hiT) { hiT = tE; const double b = wp_ctr_value(V, ch, eu, DR[c], drp); hiV = (FN != FN_DELTA && some) ? b + corr : b; }
+      }
+    }
+    if (FN != FN_DELTA) {
+      if (ch.kc.dropped) {                                               // CorrectingDoubleVectorReader.updateCorrection, :375-391
+        int idx = ch.nrows - 1; double lastValue = 0.0;
+        do { lastValue = wp_row(V, ch, idx); idx -= 1; } while (lastValue != lastValue && idx >= 0);
+        corrLast = nan0(lastValue); corr = (some ? corr : 0.0) + drops_cum(DR[c], ch.nrows - 1);
+      }
+      else { corrLast = wp_row(V, ch, ch.nrows - 1); corr = some ? corr : 0.0; }
+    }
+    some = true;
+  }
+  const int64_t cws = qinclusive ? wStart : wStart - 1;                // RateFunctions.scala:270-285
+  if (hiT > loT) return extrapolated_rate_tile<FN != FN_DELTA, FN == FN_RATE>(cws, wEnd, numSamples, loT, loV, hiT, hiV, fdiv, frcp, qstep, tab);
+  return NaNv;
+}
+
 // NaN results are counted per window (rare: kept out of line so that the read-modify-write is not predicated into the common path)
 #ifdef FILO_CUSIM
 inline void wp_bump_u16(uint16_t* p) { *p = (uint16_t)(*p + 1); }
@@ -112,6 +166,8 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
   WpCtrChunk* KC = reinterpret_cast<WpCtrChunk*>(wb + L.kc);
   double* ACC = reinterpret_cast<double*>(wb + L.acc);
   uint16_t* NBAD = reinterpret_cast<uint16_t*>(wb + L.nbad);
+  int32_t* TSR = reinterpret_cast<int32_t*>(wb + L.tsr);                 // (L.tsr == 0: tables with const-DDV timestamps only; never read then)
+  const bool allow_irr = L.tsr != 0;
   TileCtrTab* CTAB = reinterpret_cast<TileCtrTab*>(smem + L.tab);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -172,19 +228,20 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
     const int64_t s = cur_sid;
     const bool skip = AGG && item_bad;                     // the item already failed: this record was in flight, drop it
     // ------------------------------------------------------------------------------------------------ setup
-    const WpParsed P = wp_parse<false>(R, q, staged && !skip, lane);
+    const WpParsed P = allow_irr ? wp_parse<false, true>(R, q, staged && !skip, lane) : wp_parse<false, false>(R, q, staged && !skip, lane);
     bool regular = P.regular;
+    const bool irr = P.irr;
     const bool have = P.have; const int n = P.n, c = lane;
     const bool samec = !(c < n) || (P.init == m_init && P.nrows == m_nrows && P.end_time == m_end && P.vwire == m_wire && P.tlen == m_tlen);
     const bool same_all = __all_sync(FULL, samec);
-    const bool same = m_ok && n == m_n && same_all;
+    const bool same = m_ok && n == m_n && same_all && !irr;
     if (regular && !same) {
       m_init = P.init; m_end = P.end_time; m_nrows = P.nrows; m_n = n; m_wire = P.vwire; m_tlen = P.tlen; m_ok = false;
       const int64_t init = P.init, end_time = P.end_time; const int nrows = P.nrows, tlen = P.tlen;
       // three divisions per chunk: s0, e0 = unclamped first / last row of window 0; v4 = last window whose start is <= endTime.
       // (interval logic of the tile kernel's producer, scan_tile.cuh; chunk c = lane c)
       int64_t s0 = 0, e0 = 0, v4 = 0;
-      if (have) { s0 = sd.ceil_div(S0 - init); e0 = sd.floor_div(E0 - init); v4 = sd.floor_div(end_time - S0); }
+      if (have && !irr) { s0 = sd.ceil_div(S0 - init); e0 = sd.floor_div(E0 - init); v4 = sd.floor_div(end_time - S0); }
       const int64_t s0p = __shfl_up_sync(FULL, s0, 1), v4p = __shfl_up_sync(FULL, v4, 1), e0n = __shfl_down_sync(FULL, e0, 1);
       const int tlenp = __shfl_up_sync(FULL, tlen, 1);
       int64_t kA = -e0;
@@ -198,7 +255,7 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
       if (-s0 > kA) kA = -s0;              // [kA, kB]: only windows whose row range is not clamped by the chunk's ends
       { const int64_t x = (int64_t)(nrows - 1) - e0; if (x < kB) kB = x; }
       const int64_t sA = s0 + kA, eA = e0 + kA;
-      const bool ok = have && kA <= kB && eA >= sA;
+      const bool ok = have && !irr && kA <= kB && eA >= sA;
       const int Wr = ok ? (int)(eA - sA) : 0;
       const bool blocked = ok && Wr >= 1;  // two samples
       // row positions: 8 spare rows behind every chunk
@@ -213,7 +270,8 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
           WpCtrChunk& d = KC[c];
           d.init = init; d.end_time = end_time; d.nrows = nrows; d.s0 = (int)s0; d.e0 = (int)e0; d.rowpos = rowpos;
           d.kA = blocked ? (int)kA : 0; d.kB = blocked ? (int)kB : -1;
-          d.kA2 = (have && kA2 <= kB2) ? (int)kA2 : 0; d.kB2 = (have && kA2 <= kB2) ? (int)kB2 : -1;
+          d.kA2 = (have && !irr && kA2 <= kB2) ? (int)kA2 : 0; d.kB2 = (have && !irr && kA2 <= kB2) ? (int)kB2 : -1;      // irregular: every window takes the literal fold
+          if (irr) d.kc.sI = have ? 1.0 / (double)P.tslope : 0.0;
           if (blocked) {
             // RateFunctions.extrapolatedRate (RateFunctions.scala:72-111) for the chunk's unclamped single-chunk windows: the sample
             // times move with the window, so durationToStart / End, sampledInterval, numSamples are window-invariant
@@ -243,7 +301,7 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
             dd_inf[jj] = (active ? 1 : 0) | (ci << 1) | ((pq & 7) << 3) | (g << 8);
           }
         }
-        m_ok = true;
+        m_ok = !irr;
       }
     }
     bool declined = !regular && !skip;
@@ -259,6 +317,18 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
       }
       __syncwarp();
       (void)wp_decode<FN != FN_DELTA>(R, V, CD, xtab, dd_dst, dd_inf, n, P.any_raw, lane, DR);
+      if (irr) {                                           // row times: init + slope * r + residual (DeltaDeltaVector.scala:153-156), const chunks without residuals
+        for (int ci = 0; ci < n; ++ci) {
+          const uint32_t toff = __shfl_sync(FULL, P.toff, ci); const int tsl = __shfl_sync(FULL, P.tslope, ci);
+          const uint8_t* tv = R + toff;
+          const int nr = KC[ci].nrows; int32_t* dst = TSR + KC[ci].rowpos;
+          if ((int)(ld32(tv + 4) & 0xffff) == WIRE_DDV) {
+            const uint8_t* in = tv + 20; const uint32_t iw = ld32(in + 4);
+            const int nbits = (iw >> 16) & 0x7f; const bool sgn = (iw >> 23) & 1;
+            for (int r = lane; r < nr; r += 32) dst[r] = tsl * r + int_apply(in, nbits, sgn, r);
+          } else for (int r = lane; r < nr; r += 32) dst[r] = tsl * r;
+        }
+      }
       __syncwarp();
       // more drops in one chunk than the list holds: the generic kernel takes the series
       bool overflow = false;
@@ -359,7 +429,8 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
           if (ci < n) { if (KC[ci].kA2 > KC[ci].kB2) continue; gend = KC[ci].kA2; }
           for (int k = prev + 1 + lane; k < gend; k += 32) {
             const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - winDur;
-            emit(k, wp_eval_counter<FN>(n, KC, CD, DR, V, q.step, q.inclusive, wStart, wEnd, k, fdiv, frcp, CTAB));
+            emit(k, irr ? wp_eval_counter_irr<FN>(n, KC, CD, DR, V, TSR, q.step, q.inclusive, wStart, wEnd, fdiv, frcp, CTAB)
+                        : wp_eval_counter<FN>(n, KC, CD, DR, V, q.step, q.inclusive, wStart, wEnd, k, fdiv, frcp, CTAB));
           }
           if (ci < n) prev = KC[ci].kB2;
         }

@@ -81,10 +81,11 @@ static_assert(sizeof(WpCtrChunk) == 112, "WpCtrChunk");
 struct WpCtrSmem {                     // byte offsets inside a warp's region (multiples of 16); R sits at WP_OFF_REC, xtab at WP_OFF_J, drops behind it
   uint32_t vals, kc, acc, nbad, per_warp, tab /* per CTA, behind the warps' regions */;
   uint32_t rec_cap, vcap /*doubles*/, warps, agg;
+  uint32_t tsr;                        // irregular timestamps: int32 row times relative to the chunk's first (0: the table has const-DDV timestamps only)
 };
 constexpr uint32_t WP_OFF_DROPS = WP_OFF_J + 64 * 8;          // TileDrops[WP_MAXC] behind the 64-word XOR prefix table
 static_assert(WP_OFF_DROPS + WP_MAXC * sizeof(TileDrops) <= WP_OFF_REC, "drops fit in front of the record");
-FILO_HD inline WpCtrSmem wp_ctr_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t max_chunks, uint32_t T, bool agg) {
+FILO_HD inline WpCtrSmem wp_ctr_layout(uint32_t max_rec_bytes, uint32_t max_rows, uint32_t max_chunks, uint32_t T, bool agg, bool irr = false) {
   WpCtrSmem L;
   if (max_chunks > (uint32_t)WP_MAXC) max_chunks = WP_MAXC;
   L.rec_cap = align_up(max_rec_bytes + 16, 16);
@@ -93,6 +94,8 @@ FILO_HD inline WpCtrSmem wp_ctr_layout(uint32_t max_rec_bytes, uint32_t max_rows
   uint32_t o = WP_OFF_REC + L.rec_cap;
   L.vals = o; o += L.vcap * 8;
   L.kc = o; o += (uint32_t)(WP_MAXC * sizeof(WpCtrChunk));
+  L.tsr = 0;
+  if (irr) { L.tsr = o; o += align_up(P * 4, 16); }
   L.acc = o; L.nbad = o;
   if (agg) { o += T * 8; L.nbad = o; o += align_up(T * 2, 16); }
   L.per_warp = align_up(o, 16);

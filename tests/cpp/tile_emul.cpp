@@ -207,6 +207,12 @@ int main(int argc, char** argv) {
     {1, true, filo::FN_INCREASE, {120, 120, 60}, 0, 41, 60000, 12, 1, -30000, 30000, filo::AGG_SUM, 2, 0, false, false, false, false, true},   // fused
     {1, true, filo::FN_RATE, {240, 240}, 0, 97, 300000, 17, 1, 0, 0, filo::AGG_MAX, 2, 0, false, false, false, false, true},
     {1, true, filo::FN_RATE, {100, 50, 50, 50, 50}, 0, 0, 300000, 12, 1, 0, 0, filo::AGG_SUM, 2, 0, false, false, false, false, true},  // fused, every item declined
+    // irregular scrapes (DDV timestamps with residuals) on the v4 counter kernel: searched row ranges, literal fold per window
+    {1, true, filo::FN_RATE, {400, 80}, 0, 61, 300000, 9, 1, 0, 0, 0, 2, 2000, false, false, false, false, true},
+    {1, true, filo::FN_INCREASE, {120, 120, 60}, 50000, 41, 60000, 11, 0, -30000, 30000, 0, 2, 4000, false, false, false, false, true},
+    {1, false, filo::FN_DELTA, {200, 100}, 0, 0, 300000, 6, 1, 0, 0, 0, 1, 700, false, false, false, false, true},
+    {1, true, filo::FN_INCREASE, {150, 150}, 0, 45, 60000, 14, 1, 0, 0, filo::AGG_SUM, 2, 2000, false, false, false, false, true},      // fused (BASELINE C3 shape)
+    {1, true, filo::FN_RATE, {240, 240}, 100000, 97, 300000, 13, 1, 15000, 0, filo::AGG_MAX, 2, 3000, false, false, false, false, true, true},
     // the v2 warp-per-series kernel on its own: every function class, irregular scrapes (DDV timestamps), integral values (DDV longs)
     {0, true, filo::FN_MIN, {150, 90}, 100000, 0, 300000, 9, 1, -30000, 15000, 0, 2, 0, false, true},
     {0, false, filo::FN_MAX, {64, 64, 64, 64, 64}, 0, 0, 200000, 7, 0, 0, 0, 0, 1, 0, false, true},
@@ -276,7 +282,6 @@ int main(int argc, char** argv) {
       c.wp = fr() % 2 == 0;
       c.hetero = fr() % 3 == 0;
       if (c.v2_only) { const int fns[] = {filo::FN_MIN, filo::FN_MAX, filo::FN_LAST, filo::FN_TIMESTAMP, c.fn, c.fn}; c.fn = fns[fr() % 6]; c.agg_op = 0; }
-      if (c.jitter) c.agg_op = 0;
       all.push_back(c);
     }
   }
@@ -347,7 +352,7 @@ int main(int argc, char** argv) {
         g_wp_declined += (long)fcount; g_wp_series += c.nser;
         if (fcount) run_v2(A, sh, flist.data(), &fcount);
       } else if (tile_ok && c.wp && cls == filo::CLASS_COUNTER) {
-        filo::WpCtrSmem W = filo::wp_ctr_layout(max_rec, (uint32_t)rows, (uint32_t)c.chunks.size(), (uint32_t)q.T, false);
+        filo::WpCtrSmem W = filo::wp_ctr_layout(max_rec, (uint32_t)rows, (uint32_t)c.chunks.size(), (uint32_t)q.T, false, c.jitter != 0);
         W.warps = 3; W.tab = W.per_warp * W.warps;
         if ((size_t)W.tab + 4096 > sizeof(filo::smem)) { std::printf("FAIL: wp ctr layout %u bytes per warp\n", W.per_warp); return 1; }
         auto body = [&](auto fnc) {
@@ -389,7 +394,7 @@ int main(int argc, char** argv) {
       std::vector<double> pval((size_t)n_items * q.T, -777.0); std::vector<uint32_t> pcnt((size_t)n_items * q.T, 12345u);
       A.order = order.data(); A.item_begin = item_begin.data(); A.n_items = n_items; A.agg_op = c.agg_op; A.pval = pval.data(); A.pcnt = pcnt.data(); A.out = nullptr;
       if (c.wp && filo::fn_class_of(q.fn, q.cumulative) == filo::CLASS_COUNTER) {
-        filo::WpCtrSmem W = filo::wp_ctr_layout(max_rec, (uint32_t)rows, (uint32_t)c.chunks.size(), (uint32_t)q.T, true);
+        filo::WpCtrSmem W = filo::wp_ctr_layout(max_rec, (uint32_t)rows, (uint32_t)c.chunks.size(), (uint32_t)q.T, true, c.jitter != 0);
         W.warps = 3; W.tab = W.per_warp * W.warps;
         if ((size_t)W.tab + 4096 > sizeof(filo::smem)) { std::printf("FAIL: wp ctr layout %u bytes per warp\n", W.per_warp); return 1; }
         auto body = [&](auto fnc) {
