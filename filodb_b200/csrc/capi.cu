@@ -884,6 +884,7 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
     W = wp_ctr_layout(t->max_rec_bytes, (uint32_t)t->max_rows, (uint32_t)t->max_chunks, (uint32_t)q.T, agg_mode, t->any_nonconst_ts);
     const size_t cap = std::min<size_t>(ctx->max_smem_optin, 227 * 1024) - sizeof(TileCtrTab) * (TILE_CTR_TABMAX + 1) - 64;
     size_t w = cap / W.per_warp; if (w > (size_t)WP_CTR_MAX_WARPS) w = WP_CTR_MAX_WARPS;
+    if (W.tsr != 0 && w > 16) w = 16;                     // the irregular-timestamp instantiation is built for <= 16 warps
     static const int warps_env = [] { const char* e = std::getenv("FILO_WP_WARPS"); return e ? atoi(e) : 0; }();
     if (warps_env > 0 && (size_t)warps_env < w) w = (size_t)warps_env;
     if (w < 4) return false;

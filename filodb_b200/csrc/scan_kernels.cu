@@ -499,20 +499,21 @@ cudaError_t launch_scan_wp(const ScanLaunch& L, double* out, const WpSmem& W, in
   }
 }
 // v4 counter-class kernel (scan_wp_ctr.cuh): per-series rows (order == nullptr, n_items == 0) or one partial row per work item
-template <int FN, bool AGG, int NW>
+template <int FN, bool AGG, int NW, bool IRR>
 static cudaError_t launch_wp_ctr_nw(const ScanLaunch& L, double* out, const WpCtrSmem& W, int64_t* fallback_list, unsigned long long* fallback_count,
                                     const TileAggArgs& A) {
   const size_t smem = (size_t)W.per_warp * W.warps + sizeof(TileCtrTab) * (TILE_CTR_TABMAX + 1);
-  cudaError_t e = cudaFuncSetAttribute(scan_wp_ctr_kernel<FN, AGG, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(scan_wp_ctr_kernel<FN, AGG, NW, IRR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  scan_wp_ctr_kernel<FN, AGG, NW><<<L.grid, W.warps * 32, smem, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, W, fallback_list, fallback_count,
+  scan_wp_ctr_kernel<FN, AGG, NW, IRR><<<L.grid, W.warps * 32, smem, L.stream>>>(L.arena, L.rec_off, L.n_series, L.q, out, W, fallback_list, fallback_count,
       L.d_counters, L.d_err, A.order, A.item_begin, A.n_items, A.agg_op, A.pval, A.pcnt);
   return cudaGetLastError();
 }
 template <int FN, bool AGG>
 static cudaError_t launch_wp_ctr_fn(const ScanLaunch& L, double* out, const WpCtrSmem& W, int64_t* fallback_list, unsigned long long* fallback_count, const TileAggArgs& A) {
-  if (W.warps <= 16) return launch_wp_ctr_nw<FN, AGG, 16>(L, out, W, fallback_list, fallback_count, A);
-  return launch_wp_ctr_nw<FN, AGG, WP_CTR_MAX_WARPS>(L, out, W, fallback_list, fallback_count, A);
+  if (W.tsr != 0) return launch_wp_ctr_nw<FN, AGG, 16, true>(L, out, W, fallback_list, fallback_count, A);      // irregular timestamps: the larger shared-memory footprint keeps it at <= 16 warps
+  if (W.warps <= 16) return launch_wp_ctr_nw<FN, AGG, 16, false>(L, out, W, fallback_list, fallback_count, A);
+  return launch_wp_ctr_nw<FN, AGG, WP_CTR_MAX_WARPS, false>(L, out, W, fallback_list, fallback_count, A);
 }
 template <bool AGG>
 static cudaError_t launch_wp_ctr_any(const ScanLaunch& L, double* out, const WpCtrSmem& W, int64_t* fallback_list, unsigned long long* fallback_count, const TileAggArgs& A) {

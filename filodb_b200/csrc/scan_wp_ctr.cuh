@@ -146,7 +146,8 @@ WP_CTR_RARE double wp_clamped_window(const double* V, const WpCtrChunk& ch, cons
                                                               fdiv, frcp, qstep, tab);
 }
 
-template <int FN, bool AGG, int NW>
+// IRR: the table has timestamp vectors off the step grid (its own instantiation: the regular kernel keeps its code and register budget)
+template <int FN, bool AGG, int NW, bool IRR = false>
 __global__ void __launch_bounds__(NW * 32, 1)
 scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ rec_off, int64_t n_series, QueryParams q,
                    double* __restrict__ out, WpCtrSmem L, int64_t* __restrict__ fallback_list, unsigned long long* __restrict__ fallback_count,
@@ -167,7 +168,7 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
   double* ACC = reinterpret_cast<double*>(wb + L.acc);
   uint16_t* NBAD = reinterpret_cast<uint16_t*>(wb + L.nbad);
   int32_t* TSR = reinterpret_cast<int32_t*>(wb + L.tsr);                 // (L.tsr == 0: tables with const-DDV timestamps only; never read then)
-  const bool allow_irr = L.tsr != 0;
+  constexpr bool allow_irr = IRR;
   TileCtrTab* CTAB = reinterpret_cast<TileCtrTab*>(smem + L.tab);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -228,9 +229,9 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
     const int64_t s = cur_sid;
     const bool skip = AGG && item_bad;                     // the item already failed: this record was in flight, drop it
     // ------------------------------------------------------------------------------------------------ setup
-    const WpParsed P = allow_irr ? wp_parse<false, true>(R, q, staged && !skip, lane) : wp_parse<false, false>(R, q, staged && !skip, lane);
+    const WpParsed P = wp_parse<false, IRR>(R, q, staged && !skip, lane);
     bool regular = P.regular;
-    const bool irr = P.irr;
+    const bool irr = IRR && P.irr;
     const bool have = P.have; const int n = P.n, c = lane;
     const bool samec = !(c < n) || (P.init == m_init && P.nrows == m_nrows && P.end_time == m_end && P.vwire == m_wire && P.tlen == m_tlen);
     const bool same_all = __all_sync(FULL, samec);
@@ -317,7 +318,7 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
       }
       __syncwarp();
       (void)wp_decode<FN != FN_DELTA>(R, V, CD, xtab, dd_dst, dd_inf, n, P.any_raw, lane, DR);
-      if (irr) {                                           // row times: init + slope * r + residual (DeltaDeltaVector.scala:153-156), const chunks without residuals
+      if (IRR && irr) {                                    // row times: init + slope * r + residual (DeltaDeltaVector.scala:153-156), const chunks without residuals
         for (int ci = 0; ci < n; ++ci) {
           const uint32_t toff = __shfl_sync(FULL, P.toff, ci); const int tsl = __shfl_sync(FULL, P.tslope, ci);
           const uint8_t* tv = R + toff;
@@ -429,8 +430,8 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
           if (ci < n) { if (KC[ci].kA2 > KC[ci].kB2) continue; gend = KC[ci].kA2; }
           for (int k = prev + 1 + lane; k < gend; k += 32) {
             const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - winDur;
-            emit(k, irr ? wp_eval_counter_irr<FN>(n, KC, CD, DR, V, TSR, q.step, q.inclusive, wStart, wEnd, fdiv, frcp, CTAB)
-                        : wp_eval_counter<FN>(n, KC, CD, DR, V, q.step, q.inclusive, wStart, wEnd, k, fdiv, frcp, CTAB));
+            if (IRR && irr) emit(k, wp_eval_counter_irr<FN>(n, KC, CD, DR, V, TSR, q.step, q.inclusive, wStart, wEnd, fdiv, frcp, CTAB));
+            else emit(k, wp_eval_counter<FN>(n, KC, CD, DR, V, q.step, q.inclusive, wStart, wEnd, k, fdiv, frcp, CTAB));
           }
           if (ci < n) prev = KC[ci].kB2;
         }

@@ -357,7 +357,8 @@ int main(int argc, char** argv) {
         if ((size_t)W.tab + 4096 > sizeof(filo::smem)) { std::printf("FAIL: wp ctr layout %u bytes per warp\n", W.per_warp); return 1; }
         auto body = [&](auto fnc) {
           cusim::launch(dim3((unsigned)A.grid), dim3(W.warps * 32), [&] {
-            filo::scan_wp_ctr_kernel<decltype(fnc)::value, false, 16>(A.arena, A.rec_off, A.S, A.q, A.out, W, A.flist, A.fcount, A.counters, A.derr, nullptr, nullptr, 0, 0, nullptr, nullptr);
+            if (W.tsr) filo::scan_wp_ctr_kernel<decltype(fnc)::value, false, 16, true>(A.arena, A.rec_off, A.S, A.q, A.out, W, A.flist, A.fcount, A.counters, A.derr, nullptr, nullptr, 0, 0, nullptr, nullptr);
+            else filo::scan_wp_ctr_kernel<decltype(fnc)::value, false, 16, false>(A.arena, A.rec_off, A.S, A.q, A.out, W, A.flist, A.fcount, A.counters, A.derr, nullptr, nullptr, 0, 0, nullptr, nullptr);
           });
         };
         if (q.fn == filo::FN_RATE) body(std::integral_constant<int, filo::FN_RATE>{});
@@ -399,7 +400,8 @@ int main(int argc, char** argv) {
         if ((size_t)W.tab + 4096 > sizeof(filo::smem)) { std::printf("FAIL: wp ctr layout %u bytes per warp\n", W.per_warp); return 1; }
         auto body = [&](auto fnc) {
           cusim::launch(dim3((unsigned)A.grid), dim3(W.warps * 32), [&] {
-            filo::scan_wp_ctr_kernel<decltype(fnc)::value, true, 16>(A.arena, A.rec_off, A.S, A.q, nullptr, W, A.flist, A.fcount, A.counters, A.derr, A.order, A.item_begin, A.n_items, A.agg_op, A.pval, A.pcnt);
+            if (W.tsr) filo::scan_wp_ctr_kernel<decltype(fnc)::value, true, 16, true>(A.arena, A.rec_off, A.S, A.q, nullptr, W, A.flist, A.fcount, A.counters, A.derr, A.order, A.item_begin, A.n_items, A.agg_op, A.pval, A.pcnt);
+            else filo::scan_wp_ctr_kernel<decltype(fnc)::value, true, 16, false>(A.arena, A.rec_off, A.S, A.q, nullptr, W, A.flist, A.fcount, A.counters, A.derr, A.order, A.item_begin, A.n_items, A.agg_op, A.pval, A.pcnt);
           });
         };
         if (q.fn == filo::FN_RATE) body(std::integral_constant<int, filo::FN_RATE>{});
