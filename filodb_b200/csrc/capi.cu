@@ -461,7 +461,7 @@ inline int plan_all(const LoadIn& in, std::vector<SeriesPlan>& plan, PlanTotals&
 
 } // namespace
 
-extern "C" int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32_t* n_chunks, const uint64_t* addrs,
+static int32_t filo_load_series_impl(filo_ctx* ctx, int64_t n_series, const int32_t* n_chunks, const uint64_t* addrs,
                                     int32_t ts_col, int32_t val_col, const int32_t* group_ids, int32_t n_groups,
                                     int32_t schema_flags, filo_table** out) {
   if (!ctx || !out || n_series < 0 || (n_series > 0 && (!n_chunks || !addrs)) || ts_col < 0 || val_col < 0)
@@ -506,8 +506,9 @@ extern "C" int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32
     int64_t s1 = s0; const int64_t base = rec_off[s0];
     while (s1 < n_series && (size_t)(rec_off[s1 + 1] - base) <= SLAB) ++s1;
     if (s1 == s0) {   // a single record larger than the slab: grow this slab
-      cudaFreeHost(slab[which]); size_t need = (size_t)plan[s0].rec_bytes;
-      CUDA_TRY(ctx, cudaEventSynchronize(ev[which]));
+      const size_t need = (size_t)plan[s0].rec_bytes;
+      CUDA_TRY(ctx, cudaEventSynchronize(ev[which]));          // the previous copy out of this slab has finished
+      cudaFreeHost(slab[which]); slab[which] = nullptr;
       CUDA_TRY(ctx, cudaHostAlloc(&slab[which], need + (1 << 20), cudaHostAllocDefault)); s1 = s0 + 1;
     }
     CUDA_TRY(ctx, cudaEventSynchronize(ev[which]));
@@ -551,6 +552,13 @@ extern "C" int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32
   if (rc) { filo_table_free(ctx, t); return rc; }
   *out = t;
   return FILO_OK;
+}
+extern "C" int32_t filo_load_series(filo_ctx* ctx, int64_t n_series, const int32_t* n_chunks, const uint64_t* addrs,
+                                    int32_t ts_col, int32_t val_col, const int32_t* group_ids, int32_t n_groups,
+                                    int32_t schema_flags, filo_table** out) {
+  try { return filo_load_series_impl(ctx, n_series, n_chunks, addrs, ts_col, val_col, group_ids, n_groups, schema_flags, out); }
+  catch (const std::bad_alloc&) { return fail(ctx, FILO_ERR_OOM, "filo_load_series: host allocation failed"); }
+  catch (const std::exception& e) { return fail(ctx, FILO_ERR_INVALID_ARG, std::string("filo_load_series: ") + e.what()); }
 }
 
 extern "C" int32_t filo_table_set_groups(filo_ctx* ctx, filo_table* t, const int32_t* group_ids, int32_t n_groups) {
@@ -645,7 +653,7 @@ __global__ void __launch_bounds__(256) append_merge_kernel(const uint8_t* __rest
 }
 }  // namespace
 
-extern "C" int32_t filo_table_append(filo_ctx* ctx, filo_table* t, const int32_t* n_chunks, const uint64_t* chunk_info_addrs, int32_t ts_col, int32_t val_col) {
+static int32_t filo_table_append_impl(filo_ctx* ctx, filo_table* t, const int32_t* n_chunks, const uint64_t* chunk_info_addrs, int32_t ts_col, int32_t val_col) {
   if (!ctx || !t || !n_chunks || !chunk_info_addrs) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_table_append: null argument");
   if (t->hist) return fail(ctx, FILO_ERR_UNSUPPORTED, "filo_table_append: histogram tables are rebuilt with filo_load_series");
   const int64_t S = t->n_series;
@@ -686,6 +694,11 @@ extern "C" int32_t filo_table_append(filo_ctx* ctx, filo_table* t, const int32_t
   t->max_rec_bytes = st[0]; t->max_rows = (int32_t)st[1]; t->max_chunks = (int32_t)st[2];
   t->any_nonconst_ts = t->any_nonconst_ts || (d->n_chunks > 0 && d->any_nonconst_ts); t->any_drop = t->any_drop || d->any_drop;
   return FILO_OK;
+}
+extern "C" int32_t filo_table_append(filo_ctx* ctx, filo_table* t, const int32_t* n_chunks, const uint64_t* chunk_info_addrs, int32_t ts_col, int32_t val_col) {
+  try { return filo_table_append_impl(ctx, t, n_chunks, chunk_info_addrs, ts_col, val_col); }
+  catch (const std::bad_alloc&) { return fail(ctx, FILO_ERR_OOM, "filo_table_append: host allocation failed"); }
+  catch (const std::exception& e) { return fail(ctx, FILO_ERR_INVALID_ARG, std::string("filo_table_append: ") + e.what()); }
 }
 
 extern "C" int64_t filo_table_read_arena(filo_ctx* ctx, const filo_table* t, int64_t first, int64_t n, uint8_t* out, int64_t cap,
@@ -994,7 +1007,7 @@ static int32_t query_device_impl(filo_ctx* ctx, const filo_table* t, int32_t fn,
   return FILO_OK;
 }
 
-extern "C" int32_t filo_query(filo_ctx* ctx, const filo_table* t, int32_t fn, int64_t start, int64_t step, int64_t end, int64_t window,
+static int32_t filo_query_impl(filo_ctx* ctx, const filo_table* t, int32_t fn, int64_t start, int64_t step, int64_t end, int64_t window,
                               int32_t agg, int32_t k, int32_t flags, double* out_values, int64_t* out_aux, filo_stats* stats) {
   if (!ctx || !t || !out_values) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_query: null argument");
   if (start > end) return fail(ctx, FILO_ERR_INVALID_ARG, "start should be <= end");
@@ -1021,6 +1034,12 @@ extern "C" int32_t filo_query(filo_ctx* ctx, const filo_table* t, int32_t fn, in
   cudaFreeAsync(d_vals, s); if (d_aux) cudaFreeAsync(d_aux, s);
   if (stats) *stats = st;
   return rc;
+}
+extern "C" int32_t filo_query(filo_ctx* ctx, const filo_table* t, int32_t fn, int64_t start, int64_t step, int64_t end, int64_t window,
+                              int32_t agg, int32_t k, int32_t flags, double* out_values, int64_t* out_aux, filo_stats* stats) {
+  try { return filo_query_impl(ctx, t, fn, start, step, end, window, agg, k, flags, out_values, out_aux, stats); }
+  catch (const std::bad_alloc&) { return fail(ctx, FILO_ERR_OOM, "filo_query: host allocation failed"); }
+  catch (const std::exception& e) { return fail(ctx, FILO_ERR_INVALID_ARG, std::string("filo_query: ") + e.what()); }
 }
 
 
@@ -1112,7 +1131,7 @@ template <class T> int32_t grow_device(filo_ctx* ctx, T*& p, size_t& cap, size_t
 }
 }
 
-extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32_t* n_chunks, const uint64_t* addrs,
+static int32_t filo_scan_series_impl(filo_ctx* ctx, int64_t n_series, const int32_t* n_chunks, const uint64_t* addrs,
                                     int32_t ts_col, int32_t val_col, int32_t schema_flags,
                                     int32_t fn, int64_t start, int64_t step, int64_t end, int64_t window,
                                     double* out_values, filo_stats* stats) {
@@ -1297,12 +1316,20 @@ extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32
   if (stats) *stats = acc;
   return FILO_OK;
 }
+extern "C" int32_t filo_scan_series(filo_ctx* ctx, int64_t n_series, const int32_t* n_chunks, const uint64_t* addrs,
+                                    int32_t ts_col, int32_t val_col, int32_t schema_flags,
+                                    int32_t fn, int64_t start, int64_t step, int64_t end, int64_t window,
+                                    double* out_values, filo_stats* stats) {
+  try { return filo_scan_series_impl(ctx, n_series, n_chunks, addrs, ts_col, val_col, schema_flags, fn, start, step, end, window, out_values, stats); }
+  catch (const std::bad_alloc&) { return fail(ctx, FILO_ERR_OOM, "filo_scan_series: host allocation failed"); }
+  catch (const std::exception& e) { return fail(ctx, FILO_ERR_INVALID_ARG, std::string("filo_scan_series: ") + e.what()); }
+}
 
 
 // ------------------------------------------------------------------------------------------------------------------
 // filo_query_hist: PeriodicSamplesMapper over a histogram column (+ HistSumRowAggregator, + histogram_quantile)
 // ------------------------------------------------------------------------------------------------------------------
-extern "C" int32_t filo_query_hist(filo_ctx* ctx, const filo_table* t, int32_t fn, int64_t start, int64_t step, int64_t end, int64_t window,
+static int32_t filo_query_hist_impl(filo_ctx* ctx, const filo_table* t, int32_t fn, int64_t start, int64_t step, int64_t end, int64_t window,
                                    int32_t agg, double quantile, double* out_values, double* out_quantile, filo_stats* stats) {
   if (!ctx || !t || (!out_values && !out_quantile)) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_query_hist: null argument");
   if (!t->hist) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_query_hist: not a histogram table");
@@ -1377,6 +1404,12 @@ extern "C" int32_t filo_query_hist(filo_ctx* ctx, const filo_table* t, int32_t f
                                 std::to_string((int64_t)herr[1] | ((int64_t)herr[2] << 31)));
   if (herr[0]) return report_device_error(ctx, herr, 0);
   return FILO_OK;
+}
+extern "C" int32_t filo_query_hist(filo_ctx* ctx, const filo_table* t, int32_t fn, int64_t start, int64_t step, int64_t end, int64_t window,
+                                   int32_t agg, double quantile, double* out_values, double* out_quantile, filo_stats* stats) {
+  try { return filo_query_hist_impl(ctx, t, fn, start, step, end, window, agg, quantile, out_values, out_quantile, stats); }
+  catch (const std::bad_alloc&) { return fail(ctx, FILO_ERR_OOM, "filo_query_hist: host allocation failed"); }
+  catch (const std::exception& e) { return fail(ctx, FILO_ERR_INVALID_ARG, std::string("filo_query_hist: ") + e.what()); }
 }
 
 extern "C" int32_t filo_present_partials(filo_ctx* ctx, int32_t agg, int64_t n, void* d_values, void* d_counts, void* d_out, void* cuda_stream) {
