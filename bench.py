@@ -417,17 +417,56 @@ def run_c5_sub(args, ctx, rank, world, dist, stream, peak):
     del out, aux, final
     tab.free()
     torch.cuda.empty_cache()
+    # ---- parity at bench scale (outside the timed region, one GPU): the fused device result for the first Sc series against the oracle's
+    # fold of its own per-series rates, every (cluster, window) cell within 1e-9 relative
+    if world == 1 and rank == 0 and not args.no_cpu:
+        try:
+            from oracle import oracle as o
+            Sc = min(S, args.cpu_series)
+            tab2 = ctx.synth_table(Sc, ROWS, ROWS_PER_CHUNK, T0_MS, INTERVAL, n_groups=G, seed=42, series_id_base=0, **synth)
+            got = np.asarray(ctx.query(tab2, fn, start, step, end, window, aggr=aggr)).reshape(-1)
+            arena, rec_off = tab2.read_arena(0, Sc)
+            ost = o.Store(); ost.add_from_arena(arena, rec_off, Sc)
+            gids = synth_group_ids(42, 0, Sc, G)
+            exp = ost.query(getattr(o, fn_name), start, step, end, window, cumulative=True, aggr=getattr(o, aggr_name), group_ids=gids, n_groups=G,
+                            threads=host_cores()["cores_usable"])
+            if isinstance(exp, tuple): exp = exp[0]
+            expf = np.asarray(exp).reshape(-1)
+            m = ~np.isnan(expf) & ~np.isnan(got)
+            rel = float(np.max(np.abs(got[m] - expf[m]) / np.maximum(np.abs(expf[m]), 1e-300))) if m.any() else 0.0
+            nanmis = int((np.isnan(got) != np.isnan(expf)).sum())
+            rec["parity_check"] = {"series": int(Sc), "groups": int(G), "windows": int(T), "max_rel_err": rel, "tolerance": 1e-9,
+                                   "within_tolerance": bool(rel <= 1e-9 and nanmis == 0), "nan_mismatches": nanmis,
+                                   "against": "oracle (C++ restatement of ChunkedRateFunction + SumRowAggregator) on the same chunk bytes"}
+            tab2.free(); del arena
+        except Exception as e:
+            rec["parity_check"] = {"error": repr(e)}
     return rec
 
 
+def gen_hist_series_np(seed, gid, rows, nb, reset_period):
+    """numpy model of the device histogram generator (hist_row in filodb_b200/csrc/synth_kernels.cu): cumulative bucket counts [rows, nb]."""
+    with np.errstate(over="ignore"):
+        key = _splitmix64_np(np.uint64(seed) ^ (np.uint64(gid) * np.uint64(0xD1342543DE82EF95)))
+        r = np.arange(rows, dtype=np.uint64)
+        h = _splitmix64_np(key + (r << np.uint64(3)) + np.uint64(7))
+    inc = 1 + (h % np.uint64(3)).astype(np.int64)
+    obs = np.zeros((rows, nb), np.int64)
+    obs[np.arange(rows), (np.arange(rows) + gid) % nb] = inc
+    cnt = np.cumsum(obs, axis=0)
+    if reset_period > 0 and gid % reset_period == 0:
+        r0 = (rows * 5) // 8
+        cnt[r0:] = np.cumsum(obs[r0:], axis=0)
+    return np.cumsum(cnt, axis=1)
+
+
 def run_c4(args, rank, world, local_rank):
-    """C4: histogram_quantile(0.99, sum(rate(h[5m]))) over SectDelta histogram series (20 custom buckets 2*3^i, +Inf:
-    gateway/.../TestTimeseriesProducer.scala:229-235).  The chunks are produced by the oracle's restatement of the reference
-    appenders for a few thousand distinct series and replicated to the requested series count (the GPU generator does not write
-    histogram vectors yet); the query path is filo_load_series + filo_query_hist."""
+    """C4: histogram_quantile(0.99, sum(rate(h[5m]))) over SectDelta histogram series, 20 geometric buckets 2 * 3^i (the tops of
+    gateway/.../TestTimeseriesProducer.scala:229-235).  The table is generated AND encoded on the device (filo_synth_hist_table: the same
+    SectDelta encoder an ingest batch goes through); the query path is filo_query_hist.  The oracle only appears in the cpu_baseline /
+    parity_check leg."""
     import torch
     import filodb_b200.capi as capi
-    from oracle import hist as H, oracle as o
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -438,23 +477,11 @@ def run_c4(args, rank, world, local_rank):
     S = min(args.series, 1_000_000)
     K = min(S, 2048)
     nb = 20
-    b = H.Buckets.custom([2.0 * 3 ** i for i in range(nb - 1)] + [float("inf")])
-    rng = np.random.default_rng(42 + rank)
-    st = H.HistStore(b)
-    ts = T0_MS + np.arange(ROWS, dtype=np.int64) * INTERVAL
-    for s in range(K):
-        obs = np.zeros((ROWS, nb), np.int64)
-        obs[np.arange(ROWS), (np.arange(ROWS) + s) % nb] = 1 + rng.integers(0, 3, ROWS)      # bucket n % B incremented each row (:244-248)
-        rows = np.cumsum(np.cumsum(obs, axis=1), axis=0)
-        if s % 97 == 0: rows[300:] = np.cumsum(np.cumsum(obs[300:], axis=1), axis=0)          # a counter reset
-        st.add_series(ts, rows, [ROWS_PER_CHUNK, ROWS - ROWS_PER_CHUNK])
-    nch_k, addrs_k = st.all_info_addrs()
-    reps = (S + K - 1) // K
-    nch = np.tile(nch_k, reps)[:S].copy()
-    addrs = np.tile(addrs_k.reshape(K, -1), (reps, 1))[:S].reshape(-1).copy()
+    bdef, bfmt = capi.geometric_bucket_def(2.0, 3.0, nb)
     ctx = capi.Context(local_rank)
     t_gen = time.perf_counter()
-    tab = ctx.load_series(nch, addrs, schema_flags=capi.SCHEMA_CUMULATIVE)
+    tab = ctx.synth_hist_table(S, ROWS, bdef, bfmt, nb, rows_per_chunk=ROWS_PER_CHUNK, t0_ms=T0_MS, interval_ms=INTERVAL, reset_period=97, seed=42, series_id_base=rank * S)
+    torch.cuda.synchronize()
     t_gen = time.perf_counter() - t_gen
     ti = tab.info()
     start, step, end, window = T0_MS, STEP, T0_MS + 7200000, WINDOW
@@ -482,17 +509,18 @@ def run_c4(args, rank, world, local_rank):
     line = {"metric": "samples/s scanned+aggregated (rate over 10M series); % HBM roofline", "value": ti.n_samples * world / (ms / 1e3), "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "i64 bucket counts -> f64 rates", "data": "synthetic",
-            "config": {"workload": "C4: %d histogram series x 2h@15s (480 rows, chunks 400+80), SectDelta vectors, 20 custom buckets, "
-                                   "histogram_quantile(0.99, sum(rate(h[5m]))) step 15s, T=%d (per GPU; %d distinct series replicated; shards are independent, no cross-GPU merge)" % (S, T, K),
+            "config": {"workload": "C4: %d histogram series x 2h@15s (480 rows, chunks 400+80), SectDelta vectors encoded on the device, 20 geometric buckets 2*3^i, "
+                                   "histogram_quantile(0.99, sum(rate(h[5m]))) step 15s, T=%d (per GPU; shards are independent, no cross-GPU merge)" % (S, T),
                        "series_per_gpu": S, "rows": ROWS, "windows": T, "buckets": nb, "window_ms": window, "step_ms": step,
-                       "l2": "inputs (%.1f GB arena) larger than the 126 MB L2" % (ti.arena_bytes / 1e9), "table_load_s": round(t_gen, 2)},
+                       "l2": "inputs (%.1f GB arena) larger than the 126 MB L2" % (ti.arena_bytes / 1e9), "table_gen_s": round(t_gen, 2)},
             "gpu_launches": int(st0["kernel_launches"]) * args.steps, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": alg_bytes / (kern_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg_bytes / (kern_ms / 1e3) / 1e9 / peak,
                          "traffic": None, "kernel": "hist_scan_kernel (+ hist_merge_kernel)", "kernel_ms": kern_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src}}
     # end to end: load (host gather + H2D) + query + quantile read-back per step, bounded number of series
     if not args.no_e2e:
         Se = min(S, 200_000 if args.e2e_series < 0 else args.e2e_series)
-        nche, addrse = nch[:Se], addrs[:int(nch[:Se].sum())]
+        harena, hrec_off = tab.read_arena(0, Se)                      # host mirror of the chunk memory a shard would hold off-heap
+        nche, addrse, hkeep = host_chunk_infos(harena, hrec_off, Se)
         def e2e_step():
             tb = ctx.load_series(nche, addrse, schema_flags=capi.SCHEMA_CUMULATIVE)
             ctx.query_hist(tb, capi.FN_RATE, start, step, end, window, aggr=capi.AGG_SUM, quantile=0.99, want_values=False)
@@ -504,19 +532,21 @@ def run_c4(args, rank, world, local_rank):
         line["e2e"] = {"value": Se * ROWS * world / dt, "unit": "samples/s", "h2d_bytes_per_step": int(ti.arena_bytes * Se / S), "d2h_bytes_per_step": T * 8,
                        "s_per_step": dt, "series_per_gpu": Se, "what": "filo_load_series + filo_query_hist + filo_table_free per step"}
     if rank == 0 and world == 1 and not args.no_cpu:
-        Sc = min(K, 1024)
-        sub = H.HistStore(b)
-        # the oracle store of the first Sc distinct series is `st` itself when Sc == K; query it single-threaded
+        from oracle import hist as H, oracle as o
+        b = H.Buckets.geometric(2.0, 3.0, nb)
+        st = H.HistStore(b)
+        ts = T0_MS + np.arange(ROWS, dtype=np.int64) * INTERVAL
+        for s_ in range(K):                                           # the first K series of the device table, rebuilt from the generator's model
+            st.add_series(ts, gen_hist_series_np(42, s_, ROWS, nb, 97), [ROWS_PER_CHUNK, ROWS - ROWS_PER_CHUNK])
         t0 = time.perf_counter()
         st.query(o.FN_RATE, start, step, end, window, aggr=True, group_ids=np.zeros(K, np.int32), n_groups=1, q=0.99)
         dtc = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": K * ROWS / dtc, "unit": "samples/s", "cores": 1, "kind": "port",
                                 "sample": "%d of %d series (%.1f s on 1 thread); C++ restatement of ChunkedWindowIteratorH + HistRateFunction + HistSum + quantile" % (K, S, dtc)}
-        del sub
         # ---- parity at bench scale (outside the timed region): the K distinct series as one group, fused sum + quantile against the oracle
         try:
             avals, aempty, aq = st.query(o.FN_RATE, start, step, end, window, aggr=True, group_ids=np.zeros(K, np.int32), n_groups=1, q=0.99)
-            tabk = ctx.load_series(nch_k, addrs_k, schema_flags=capi.SCHEMA_CUMULATIVE)
+            tabk = ctx.synth_hist_table(K, ROWS, bdef, bfmt, nb, rows_per_chunk=ROWS_PER_CHUNK, t0_ms=T0_MS, interval_ms=INTERVAL, reset_period=97, seed=42, series_id_base=0)
             gv, gq = ctx.query_hist(tabk, capi.FN_RATE, start, step, end, window, aggr=capi.AGG_SUM, quantile=0.99)
             tabk.free()
             live = ~aempty.reshape(-1)

@@ -15,7 +15,7 @@ SCHEMA_LONG_VALUES = 2
 Q_PARTIAL = 1
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CORRUPT_VECTOR, ERR_UNSUPPORTED, ERR_QUERY_LIMIT, ERR_BAD_QUERY, ERR_OOM = 0, -1, -2, -3, -4, -5, -6, -7
 
-EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_ctx_set_fn_args", "filo_ctx_check", "filo_last_error", "filo_load_series", "filo_table_append", "filo_synth_table", "filo_encode_table",
+EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_ctx_set_fn_args", "filo_ctx_check", "filo_last_error", "filo_load_series", "filo_table_append", "filo_synth_table", "filo_encode_table", "filo_encode_hist_table", "filo_synth_hist_table",
            "filo_table_set_groups", "filo_table_get_info", "filo_table_read_record", "filo_table_read_arena", "filo_table_free",
            "filo_num_windows", "filo_query", "filo_query_device", "filo_scan_series", "filo_query_hist", "filo_host_register", "filo_host_unregister", "filo_present_partials",
            "filo_result_max_containers", "filo_encode_result_device", "filo_encode_result"]
@@ -75,6 +75,8 @@ def _sig(L):
     L.filo_ctx_destroy.restype = None; L.filo_ctx_destroy.argtypes = [vp]
     L.filo_ctx_check.restype = i32; L.filo_ctx_check.argtypes = [vp]
     L.filo_encode_table.restype = i32; L.filo_encode_table.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, vp, i32, C.POINTER(vp)]
+    L.filo_encode_hist_table.restype = i32; L.filo_encode_hist_table.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, vp, i32, i32, vp, i32, C.POINTER(vp)]
+    L.filo_synth_hist_table.restype = i32; L.filo_synth_hist_table.argtypes = [vp, i64, i32, i32, i64, i32, i32, i32, vp, i32, i32, i32, C.c_uint64, i64, C.POINTER(vp)]
     L.filo_table_append.restype = i32; L.filo_table_append.argtypes = [vp, vp, vp, vp, i32, i32]
     L.filo_result_max_containers.restype = i64; L.filo_result_max_containers.argtypes = [i64, i32]
     L.filo_encode_result.restype = i32; L.filo_encode_result.argtypes = [vp, vp, i64, i64, i64, i64, i64, vp, i64, vp, vp, vp, C.POINTER(i64), C.POINTER(i64)]
@@ -110,6 +112,12 @@ def _p(a):
 
 def num_windows(start, step, end):
     return lib().filo_num_windows(start, step, end)
+
+
+def geometric_bucket_def(first, mult, n):
+    """GeometricBuckets.serialize (Histogram.scala:609-617): u16 length, i16 numBuckets, f64 firstBucket, f64 multiplier; format code 0x03."""
+    import struct
+    return np.frombuffer(struct.pack("<Hhdd", 18, n, float(first), float(mult)), np.uint8).copy(), 3
 
 
 def sin_table(rows):
@@ -235,6 +243,25 @@ class Context:
         g = np.ascontiguousarray(group_ids, np.int32) if group_ids is not None else None
         h = C.c_void_p()
         self._check(lib().filo_encode_table(self.h, _p(ts), _p(v), ts.shape[0], ts.shape[1], rows_per_chunk, value_enc, schema_flags, _p(g), n_groups, C.byref(h)))
+        return Table(self, h)
+
+    def encode_hist_table(self, timestamps, bucket_counts, bucket_def, format_code, rows_per_chunk=400, schema_flags=SCHEMA_CUMULATIVE, group_ids=None, n_groups=0):
+        """filo_encode_hist_table: cumulative bucket counts [n_series, rows, nb] -> SectDelta HistogramVectors encoded on the device."""
+        ts = np.ascontiguousarray(timestamps, np.int64); b = np.ascontiguousarray(bucket_counts, np.int64)
+        assert b.ndim == 3 and ts.shape == b.shape[:2]
+        d = np.ascontiguousarray(bucket_def, np.uint8)
+        g = np.ascontiguousarray(group_ids, np.int32) if group_ids is not None else None
+        h = C.c_void_p()
+        self._check(lib().filo_encode_hist_table(self.h, _p(ts), _p(b), b.shape[0], b.shape[1], rows_per_chunk, b.shape[2], format_code, _p(d), d.size,
+                                                 schema_flags, _p(g), n_groups, C.byref(h)))
+        return Table(self, h)
+
+    def synth_hist_table(self, n_series, rows_per_series, bucket_def, format_code, n_buckets, rows_per_chunk=400, t0_ms=1_700_000_000_000, interval_ms=15000,
+                         reset_period=0, n_groups=0, seed=42, series_id_base=0):
+        d = np.ascontiguousarray(bucket_def, np.uint8)
+        h = C.c_void_p()
+        self._check(lib().filo_synth_hist_table(self.h, n_series, rows_per_series, rows_per_chunk, t0_ms, interval_ms, n_buckets, format_code, _p(d), d.size,
+                                                reset_period, n_groups, seed, series_id_base, C.byref(h)))
         return Table(self, h)
 
     def synth_table(self, n_series, rows_per_series, rows_per_chunk=400, t0_ms=1_700_000_000_000, interval_ms=15000,

@@ -461,6 +461,23 @@ inline int plan_all(const LoadIn& in, std::vector<SeriesPlan>& plan, PlanTotals&
 
 } // namespace
 
+// histogram table: one bucket scheme for all series; hd = a HistogramVector header (format code at +8, definition at +9) in host memory
+int32_t filo_internal_set_hist(filo_ctx* ctx, filo_table* t, const uint8_t* hd) {
+  const int fmt = hd[8], nb = (uint16_t)(hd[11] | (hd[12] << 8));
+  t->hist = true; t->hist_nb = nb; t->hist_tops.assign((size_t)std::max(nb, 0), 0.0);
+  bool ok = nb > 0 && nb <= 64;
+  if (ok && (fmt == 3 || fmt == 4)) {                // GeometricBuckets.bucketTop, Histogram.scala:606
+    double first, mult; std::memcpy(&first, hd + 13, 8); std::memcpy(&mult, hd + 21, 8);
+    for (int i = 0; i < nb; ++i) t->hist_tops[(size_t)i] = first * std::pow(mult, (double)i) + (fmt == 4 ? -1.0 : 0.0);
+  } else if (ok && fmt == 5) {                        // CustomBuckets: u16 n + NibblePack.packDoubles(les), Histogram.scala:878-884
+    const int defBytes = (uint16_t)(hd[9] | (hd[10] << 8));
+    ok = host_unpack_double_xor(hd + 13, defBytes - 2, t->hist_tops.data(), nb);
+  } else ok = false;
+  if (!ok) return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram bucket scheme not supported on the device path (1..64 geometric or custom buckets)");
+  CUDA_TRY(ctx, cudaMalloc(&t->d_hist_tops, (size_t)nb * 8));
+  CUDA_TRY(ctx, cudaMemcpy(t->d_hist_tops, t->hist_tops.data(), (size_t)nb * 8, cudaMemcpyHostToDevice));
+  return FILO_OK;
+}
 static int32_t filo_load_series_impl(filo_ctx* ctx, int64_t n_series, const int32_t* n_chunks, const uint64_t* addrs,
                                     int32_t ts_col, int32_t val_col, const int32_t* group_ids, int32_t n_groups,
                                     int32_t schema_flags, filo_table** out) {
@@ -525,20 +542,8 @@ static int32_t filo_load_series_impl(filo_ctx* ctx, int64_t n_series, const int3
   filo_internal_set_arena(t, d_arena, d_rec_off, n_series, tot.chunks, tot.samples, arena_bytes + (n_series + 1) * 8, tot.alg, tot.maxrows, tot.maxch, schema_flags);
   filo_internal_set_layout(t, tot.max_rec, n_series > 0 && !(tot.f_and & REC_ALL_TS_CONST), (tot.f_or & REC_ANY_DROP) != 0);
   if (tot.hist_def) {                                  // histogram table: one bucket scheme, tops kept for histogram_quantile
-    const uint8_t* hd = tot.hist_def;
-    const int fmt = hd[8], nb = (uint16_t)(hd[11] | (hd[12] << 8));
-    t->hist = true; t->hist_nb = nb; t->hist_tops.assign((size_t)nb, 0.0);
-    bool ok = nb > 0 && nb <= 64;
-    if (ok && (fmt == 3 || fmt == 4)) {                // GeometricBuckets.bucketTop, Histogram.scala:606
-      double first, mult; std::memcpy(&first, hd + 13, 8); std::memcpy(&mult, hd + 21, 8);
-      for (int i = 0; i < nb; ++i) t->hist_tops[(size_t)i] = first * std::pow(mult, (double)i) + (fmt == 4 ? -1.0 : 0.0);
-    } else if (ok && fmt == 5) {                        // CustomBuckets: u16 n + NibblePack.packDoubles(les), Histogram.scala:878-884
-      const int defBytes = (uint16_t)(hd[9] | (hd[10] << 8));
-      ok = host_unpack_double_xor(hd + 13, defBytes - 2, t->hist_tops.data(), nb);
-    } else ok = false;
-    if (!ok) { filo_table_free(ctx, t); return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram bucket scheme not supported on the device path (1..64 geometric or custom buckets)"); }
-    CUDA_TRY(ctx, cudaMalloc(&t->d_hist_tops, (size_t)nb * 8));
-    CUDA_TRY(ctx, cudaMemcpy(t->d_hist_tops, t->hist_tops.data(), (size_t)nb * 8, cudaMemcpyHostToDevice));
+    const int32_t rch = filo_internal_set_hist(ctx, t, tot.hist_def);
+    if (rch != FILO_OK) { filo_table_free(ctx, t); return rch; }
   }
   // groups
   int32_t* d_gid = nullptr;

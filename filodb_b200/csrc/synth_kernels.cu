@@ -24,6 +24,7 @@ void filo_internal_set_layout(filo_table* t, uint32_t max_rec_bytes, bool any_no
 cudaStream_t filo_internal_stream(filo_ctx* ctx);
 int filo_internal_device(filo_ctx* ctx);
 int32_t filo_internal_fail(filo_ctx* ctx, int32_t code, const char* msg);
+int32_t filo_internal_set_hist(filo_ctx* ctx, filo_table* t, const uint8_t* hist_vector_header);
 
 namespace filo {
 
@@ -314,6 +315,141 @@ __global__ void synth_fill_kernel(SynthParams P, const int64_t* rec_off, uint8_t
   atomicAdd(alg_bytes, alg);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Histogram columns: SectDelta HistogramVectors written on the device (AppendableSectDeltaHistVector.appendHist, HistogramVector.scala:
+// 489-545; SectionWriter, Section.scala:91-145; DeltaSectDiffPackSink, NibblePack.scala:296-345; BinaryHistogram delta formats :84-200).
+// Vector = [+0 i32 numBytes][+4 u16 wire H_SECTDELTA][+6 u16 numHistograms][+8 u8 formatCode][+9 u16 bucketDefBytes][+11 bucket def]
+// sections...; section = [u16 bytes][u8 elems][u8 type (1 = drop)] records...; record = [u16 len] NibblePack groups.  The first record of a
+// section holds the histogram's bucket deltas (NibblePack.packDelta), the others the difference to that record's deltas; a histogram with a
+// bucket delta below the previous histogram's opens a Drop section.  Thread per series, sequential (generator / encoder, not a hot path).
+// ---------------------------------------------------------------------------------------------------------------------
+struct HistSynthParams {
+  int64_t n_series; int32_t rows, rows_per_chunk; int64_t t0; int32_t interval;
+  int32_t nb, format_code, def_bytes; const uint8_t* def;          // bucket definition (u16 length prefix + body) as BinaryHistogram carries it
+  int32_t reset_period, n_groups; uint64_t seed; int64_t gid_base;
+  const int64_t* ext_ts; const int64_t* ext_buckets;               // external samples: [n_series][rows] and [n_series][rows][nb] cumulative counts
+};
+constexpr int HS_MAXNB = 64;
+// cumulative (over rows) per-bucket counts of the generator: row r adds 1 + (hash % 3) observations to bucket (r + series) % nb
+// (gateway/src/main/scala/filodb/timeseries/TestTimeseriesProducer.scala:229-248); series with gid % reset_period == 0 restart at 5/8 of the rows
+struct HistGen { int64_t cnt[HS_MAXNB]; };
+__device__ __forceinline__ void hist_row(const HistSynthParams& P, int64_t si, uint64_t key, uint64_t gid, int row, HistGen& g, int64_t v[HS_MAXNB]) {
+  if (P.ext_buckets) { const int64_t* src = P.ext_buckets + ((size_t)si * (size_t)P.rows + (size_t)row) * (size_t)P.nb; for (int b = 0; b < P.nb; ++b) v[b] = src[b]; return; }
+  if (P.reset_period > 0 && (gid % (uint64_t)P.reset_period) == 0 && row == (P.rows * 5) / 8) for (int b = 0; b < P.nb; ++b) g.cnt[b] = 0;
+  g.cnt[(int)(((uint64_t)row + gid) % (uint64_t)P.nb)] += 1 + (int64_t)(row_hash(key, row, 7) % 3ull);
+  int64_t run = 0;
+  for (int b = 0; b < P.nb; ++b) { run += g.cnt[b]; v[b] = run; }
+}
+__device__ __forceinline__ int64_t hist_ts(const HistSynthParams& P, int64_t si, int row) {
+  return P.ext_ts ? P.ext_ts[(size_t)si * (size_t)P.rows + (size_t)row] : P.t0 + (int64_t)row * P.interval;
+}
+// NibblePack.pack8 of the nb values of `in` (groups of 8, zero padded) into out; returns the byte count
+__device__ __forceinline__ int hs_pack_groups(const uint64_t* in, int nb, uint8_t* out, bool emit) {
+  int len = 0;
+  for (int i = 0; i < nb; i += 8) {
+    uint64_t arr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) arr[j] = (i + j < nb) ? in[i + j] : 0ull;
+    if (!emit) { len += (int)pack8_size(arr); continue; }
+    uint64_t tmp[10]; Writer w; w.init(reinterpret_cast<uint8_t*>(tmp));
+    pack8_emit(w, arr);
+    const int n = (int)w.pos(); w.pad8();
+    const uint8_t* tb = reinterpret_cast<const uint8_t*>(tmp);
+    for (int k = 0; k < n; ++k) out[len + k] = tb[k];
+    len += n;
+  }
+  return len;
+}
+// one chunk's histogram vector at dst (EMIT) or its size only; g is advanced over the chunk's rows
+template <bool EMIT>
+__device__ uint32_t hist_encode_chunk(const HistSynthParams& P, int64_t si, uint64_t key, uint64_t gid, int r0, int n, HistGen& g, uint8_t* dst) {
+  const int nb = P.nb;
+  auto put16 = [&](uint32_t off, uint32_t v) { if (EMIT) { dst[off] = (uint8_t)v; dst[off + 1] = (uint8_t)(v >> 8); } };
+  auto put8 = [&](uint32_t off, uint32_t v) { if (EMIT) dst[off] = (uint8_t)v; };
+  if (EMIT) {
+    put16(4, (uint32_t)WIRE_H_SECTDELTA); put16(6, (uint32_t)n); put8(8, (uint32_t)P.format_code); put16(9, (uint32_t)P.def_bytes);
+    for (int k = 0; k < P.def_bytes; ++k) dst[11 + k] = P.def[k];
+  }
+  uint32_t cur = 11u + (uint32_t)P.def_bytes, secBytes = 0, secElems = 0;      // SectionWriter state
+  put16(cur, 0); put8(cur + 2, 0); put8(cur + 3, 0);
+  int64_t orig[HS_MAXNB], last[HS_MAXNB];
+  for (int b = 0; b < nb; ++b) { orig[b] = 0; last[b] = 0; }
+  uint8_t ob[8 * 66], rb[8 * 66];
+  auto need_new = [&](int bytes) { return secElems >= 16u || secBytes + (uint32_t)bytes >= 65536u; };
+  auto new_section = [&](int type) { cur = cur + 4 + secBytes; secBytes = 0; secElems = 0; put16(cur, 0); put8(cur + 2, 0); put8(cur + 3, (uint32_t)type); };
+  auto add_blob = [&](const uint8_t* blob, int len) {
+    const uint32_t w = cur + 4 + secBytes;
+    put16(w, (uint32_t)len);
+    if (EMIT) for (int k = 0; k < len; ++k) dst[w + 2 + k] = blob[k];
+    secBytes += (uint32_t)len + 2; secElems += 1;
+    put16(cur, secBytes); put8(cur + 2, secElems);
+  };
+  for (int i = 0; i < n; ++i) {
+    int64_t v[HS_MAXNB]; uint64_t d[HS_MAXNB], pk[HS_MAXNB];
+    hist_row(P, si, key, gid, r0 + i, g, v);
+    bool dropped = false; int64_t prev = 0;
+    for (int b = 0; b < nb; ++b) {                          // NibblePack.packDelta: delta to the previous bucket, 0 when it decreases
+      const int64_t dl = v[b] >= prev ? v[b] - prev : 0; prev = v[b];
+      d[b] = (uint64_t)dl; if (dl < last[b]) dropped = true;
+      pk[b] = (uint64_t)dl - (uint64_t)orig[b];
+    }
+    for (int b = 0; b < nb; ++b) last[b] = (int64_t)d[b];
+    const int olen = hs_pack_groups(d, nb, ob, EMIT);
+    if (dropped) { for (int b = 0; b < nb; ++b) orig[b] = last[b]; new_section(1); add_blob(ob, olen); }
+    else if (i == 0 || need_new(olen)) { for (int b = 0; b < nb; ++b) orig[b] = last[b]; if (need_new(olen)) new_section(0); add_blob(ob, olen); }
+    else { const int rlen = hs_pack_groups(pk, nb, rb, EMIT); if (need_new(rlen)) new_section(0); add_blob(rb, rlen); }
+  }
+  const uint32_t total = cur + 4 + secBytes;
+  if (EMIT) { const uint32_t nbytes = total - 4; dst[0] = (uint8_t)nbytes; dst[1] = (uint8_t)(nbytes >> 8); dst[2] = (uint8_t)(nbytes >> 16); dst[3] = (uint8_t)(nbytes >> 24); }
+  return total;
+}
+__device__ __forceinline__ LongPlan hist_ts_plan(const HistSynthParams& P, int64_t si, int r0, int n) {
+  auto ts_seq = [&](auto&& f) { for (int i = 0; i < n; ++i) f(i, hist_ts(P, si, r0 + i)); };
+  return plan_longs(n, true, ts_seq);
+}
+__global__ void hist_synth_size_kernel(HistSynthParams P, uint32_t* rec_bytes, int32_t* group_ids) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n_series) return;
+  const uint64_t gid = (uint64_t)(P.gid_base + i), key = series_key(P.seed, gid);
+  const int nch = (P.rows + P.rows_per_chunk - 1) / P.rows_per_chunk;
+  uint32_t bytes = sizeof(RecordHeader) + (uint32_t)nch * sizeof(ChunkEntry);
+  HistGen g; for (int b = 0; b < HS_MAXNB; ++b) g.cnt[b] = 0;
+  for (int c = 0; c < nch; ++c) {
+    const int r0 = c * P.rows_per_chunk, n = min(P.rows_per_chunk, P.rows - r0);
+    bytes += align_up(hist_ts_plan(P, i, r0, n).total, 8) + align_up(hist_encode_chunk<false>(P, i, key, gid, r0, n, g, nullptr), 8);
+  }
+  rec_bytes[i] = align_up(bytes, 16);
+  if (group_ids) group_ids[i] = P.n_groups > 0 ? (int32_t)(splitmix64(P.seed ^ 0xA5A5A5A5ull ^ (gid * 0x9E3779B97F4A7C15ull)) % (uint64_t)P.n_groups) : 0;
+}
+__global__ void hist_synth_fill_kernel(HistSynthParams P, const int64_t* rec_off, uint8_t* arena, unsigned long long* alg_bytes) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n_series) return;
+  const uint64_t gid = (uint64_t)(P.gid_base + i), key = series_key(P.seed, gid);
+  const int nch = (P.rows + P.rows_per_chunk - 1) / P.rows_per_chunk;
+  uint8_t* rec = arena + rec_off[i];
+  const uint32_t rec_bytes = (uint32_t)(rec_off[i + 1] - rec_off[i]);
+  for (uint32_t k = 0; k < rec_bytes; k += 8) *reinterpret_cast<uint64_t*>(rec + k) = 0ull;      // padding and gaps are zero
+  uint32_t off = sizeof(RecordHeader) + (uint32_t)nch * sizeof(ChunkEntry), flags = REC_ALL_TS_CONST | REC_HIST | REC_ANY_DECODE, row_base = 0;
+  unsigned long long alg = 0;
+  HistGen g; for (int b = 0; b < HS_MAXNB; ++b) g.cnt[b] = 0;
+  for (int c = 0; c < nch; ++c) {
+    const int r0 = c * P.rows_per_chunk, n = min(P.rows_per_chunk, P.rows - r0);
+    const LongPlan tsp = hist_ts_plan(P, i, r0, n);
+    if (tsp.kind != 1) flags &= ~REC_ALL_TS_CONST;
+    ChunkEntry e; e.start_time = hist_ts(P, i, r0); e.end_time = hist_ts(P, i, r0 + n - 1); e.num_rows = n; e.ts_off = off; e.row_base = row_base;
+    { Writer w; w.init(rec + off); auto ts_seq = [&](auto&& f) { for (int k = 0; k < n; ++k) f(k, hist_ts(P, i, r0 + k)); }; write_longs(w, tsp, n, false, false, ts_seq); w.pad8(); }
+    off += align_up(tsp.total, 8);
+    e.val_off = off;
+    const uint32_t vt = hist_encode_chunk<true>(P, i, key, gid, r0, n, g, rec + off);
+    off += align_up(vt, 8); row_base += (uint32_t)n;
+    reinterpret_cast<ChunkEntry*>(rec + sizeof(RecordHeader))[c] = e;
+    alg += 28 + 16 + tsp.total + vt;
+  }
+  RecordHeader h; h.rec_bytes = rec_bytes; h.n_chunks = (uint32_t)nch; h.n_rows = (uint32_t)P.rows; h.flags = flags;
+  *reinterpret_cast<RecordHeader*>(rec) = h;
+  atomicAdd(alg_bytes, alg);
+}
+
 __global__ void widen_kernel(const uint32_t* in, int64_t* out, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = in[i];
 }
@@ -420,4 +556,100 @@ static int32_t synth_build(filo_ctx* ctx, const filo_synth_spec* sp, const int64
   if (rc) { filo_table_free(ctx, t); return rc; }
   *out = t;
   return FILO_OK;
+}
+
+
+// ---- histogram tables: generator (bench / tests) and encoder of raw bucket counts (ingest batches)
+static int32_t hist_build(filo_ctx* ctx, HistSynthParams P, const uint8_t* h_def, int32_t schema_flags, const int32_t* h_group_ids, filo_table** out) {
+  S_TRY(cudaSetDevice(filo_internal_device(ctx)));
+  cudaStream_t s = filo_internal_stream(ctx);
+  const int64_t S = P.n_series;
+  uint8_t* d_def = nullptr; uint32_t* d_bytes = nullptr; int32_t* d_gid = nullptr; int64_t* d_off = nullptr; int64_t* d_wide = nullptr;
+  unsigned long long* d_alg = nullptr; uint8_t* d_arena = nullptr;
+  S_TRY(cudaMalloc(&d_def, (size_t)P.def_bytes + 16));
+  S_TRY(cudaMemcpyAsync(d_def, h_def, (size_t)P.def_bytes, cudaMemcpyHostToDevice, s));
+  P.def = d_def;
+  S_TRY(cudaMalloc(&d_bytes, (size_t)(S + 1) * 4)); S_TRY(cudaMalloc(&d_wide, (size_t)(S + 1) * 8)); S_TRY(cudaMalloc(&d_off, (size_t)(S + 1) * 8));
+  S_TRY(cudaMemsetAsync(d_bytes, 0, (size_t)(S + 1) * 4, s));
+  if (P.n_groups > 0) S_TRY(cudaMalloc(&d_gid, (size_t)std::max<int64_t>(S, 1) * 4));
+  S_TRY(cudaMalloc(&d_alg, 8)); S_TRY(cudaMemsetAsync(d_alg, 0, 8, s));
+  const unsigned blocks = (unsigned)((S + 63) / 64);
+  if (S > 0) { hist_synth_size_kernel<<<blocks, 64, 0, s>>>(P, d_bytes, d_gid); S_TRY(cudaGetLastError()); }
+  if (h_group_ids && d_gid && S > 0) S_TRY(cudaMemcpyAsync(d_gid, h_group_ids, (size_t)S * 4, cudaMemcpyHostToDevice, s));
+  widen_kernel<<<(unsigned)((S + 1 + 255) / 256), 256, 0, s>>>(d_bytes, d_wide, S + 1); S_TRY(cudaGetLastError());
+  size_t tmpb = 0; cub::DeviceScan::ExclusiveSum(nullptr, tmpb, d_wide, d_off, (int)(S + 1), s);
+  void* tmp = nullptr; S_TRY(cudaMalloc(&tmp, tmpb + 16));
+  S_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmpb, d_wide, d_off, (int)(S + 1), s));
+  int64_t arena_bytes = 0;
+  S_TRY(cudaMemcpyAsync(&arena_bytes, d_off + S, 8, cudaMemcpyDeviceToHost, s));
+  S_TRY(cudaStreamSynchronize(s));
+  S_TRY(cudaMalloc(&d_arena, (size_t)arena_bytes + 64));
+  S_TRY(cudaMemsetAsync(d_arena + arena_bytes, 0, 64, s));
+  if (S > 0) { hist_synth_fill_kernel<<<blocks, 64, 0, s>>>(P, d_off, d_arena, d_alg); S_TRY(cudaGetLastError()); }
+  unsigned long long alg = 0;
+  S_TRY(cudaMemcpyAsync(&alg, d_alg, 8, cudaMemcpyDeviceToHost, s));
+  S_TRY(cudaStreamSynchronize(s));
+  uint32_t max_rec = 0;
+  if (S > 0) {
+    uint32_t* d_max = nullptr; S_TRY(cudaMalloc(&d_max, 4));
+    size_t tb = 0; cub::DeviceReduce::Max(nullptr, tb, d_bytes, d_max, (int)S, s);
+    void* t2 = nullptr; S_TRY(cudaMalloc(&t2, tb + 16));
+    S_TRY(cub::DeviceReduce::Max(t2, tb, d_bytes, d_max, (int)S, s));
+    S_TRY(cudaMemcpyAsync(&max_rec, d_max, 4, cudaMemcpyDeviceToHost, s));
+    S_TRY(cudaStreamSynchronize(s));
+    cudaFree(t2); cudaFree(d_max);
+  }
+  cudaFree(tmp); cudaFree(d_bytes); cudaFree(d_wide); cudaFree(d_alg); cudaFree(d_def);
+  const int nch = (P.rows + P.rows_per_chunk - 1) / P.rows_per_chunk;
+  filo_table* t = filo_internal_new_table();
+  filo_internal_set_arena(t, d_arena, d_off, S, S * nch, S * (int64_t)P.rows, arena_bytes + (S + 1) * 8, (int64_t)alg, P.rows, nch, schema_flags);
+  filo_internal_set_layout(t, max_rec, P.ext_ts != nullptr, false);
+  std::vector<uint8_t> hd((size_t)11 + (size_t)P.def_bytes + 32, 0);       // a HistogramVector header for the table's bucket scheme
+  hd[8] = (uint8_t)P.format_code; hd[9] = (uint8_t)P.def_bytes; hd[10] = (uint8_t)(P.def_bytes >> 8);
+  std::memcpy(hd.data() + 11, h_def, (size_t)P.def_bytes);
+  int32_t rc = filo_internal_set_hist(ctx, t, hd.data());
+  if (rc == FILO_OK) rc = filo_internal_finish_table(ctx, t, d_gid, P.n_groups > 0 ? P.n_groups : 1);
+  cudaFree(d_gid);
+  if (rc) { filo_table_free(ctx, t); return rc; }
+  *out = t;
+  return FILO_OK;
+}
+static bool hist_def_ok(int32_t n_buckets, int32_t format_code, const uint8_t* def, int32_t def_bytes) {
+  if (!def || n_buckets <= 0 || n_buckets > HS_MAXNB || def_bytes < 4 || def_bytes > 1024) return false;
+  if (!(format_code == 3 || format_code == 4 || format_code == 5)) return false;
+  const int len = def[0] | (def[1] << 8), n = def[2] | (def[3] << 8);
+  return len + 2 == def_bytes && n == n_buckets;
+}
+extern "C" int32_t filo_synth_hist_table(filo_ctx* ctx, int64_t n_series, int32_t rows_per_series, int32_t rows_per_chunk, int64_t t0_ms, int32_t interval_ms,
+                                         int32_t n_buckets, int32_t format_code, const uint8_t* bucket_def, int32_t bucket_def_bytes,
+                                         int32_t reset_period, int32_t n_groups, uint64_t seed, int64_t series_id_base, filo_table** out) {
+  if (!ctx || !out) return filo_internal_fail(ctx, FILO_ERR_INVALID_ARG, "filo_synth_hist_table: null argument");
+  if (n_series < 0 || rows_per_series <= 0 || rows_per_chunk <= 0 || rows_per_chunk > 4096 || interval_ms <= 0 || !hist_def_ok(n_buckets, format_code, bucket_def, bucket_def_bytes))
+    return filo_internal_fail(ctx, FILO_ERR_INVALID_ARG, "filo_synth_hist_table: bad arguments (1..64 geometric or custom buckets)");
+  HistSynthParams P{n_series, rows_per_series, rows_per_chunk, t0_ms, interval_ms, n_buckets, format_code, bucket_def_bytes, nullptr, reset_period, n_groups, seed, series_id_base, nullptr, nullptr};
+  return hist_build(ctx, P, bucket_def, FILO_SCHEMA_CUMULATIVE, nullptr, out);
+}
+// GPU-side encode of a histogram ingest batch: cumulative bucket counts [n_series][rows][n_buckets] and timestamps [n_series][rows] in HOST memory
+extern "C" int32_t filo_encode_hist_table(filo_ctx* ctx, const int64_t* timestamps, const int64_t* bucket_counts, int64_t n_series, int32_t rows_per_series,
+                                          int32_t rows_per_chunk, int32_t n_buckets, int32_t format_code, const uint8_t* bucket_def, int32_t bucket_def_bytes,
+                                          int32_t schema_flags, const int32_t* group_ids, int32_t n_groups, filo_table** out) {
+  if (!ctx || !timestamps || !bucket_counts || !out) return filo_internal_fail(ctx, FILO_ERR_INVALID_ARG, "filo_encode_hist_table: null argument");
+  if (n_series < 0 || rows_per_series <= 0 || rows_per_chunk <= 0 || rows_per_chunk > 4096 || (group_ids && n_groups <= 0) || !hist_def_ok(n_buckets, format_code, bucket_def, bucket_def_bytes))
+    return filo_internal_fail(ctx, FILO_ERR_INVALID_ARG, "filo_encode_hist_table: bad arguments (1..64 geometric or custom buckets)");
+  for (int64_t i = 0; group_ids && i < n_series; ++i) if (group_ids[i] < 0 || group_ids[i] >= n_groups) return filo_internal_fail(ctx, FILO_ERR_INVALID_ARG, "group id out of range");
+  for (int64_t i = 0; i < n_series; ++i)
+    for (int32_t r = 1; r < rows_per_series; ++r)
+      if (!(timestamps[(size_t)i * rows_per_series + r] > timestamps[(size_t)i * rows_per_series + r - 1]))
+        return filo_internal_fail(ctx, FILO_ERR_INVALID_ARG, "filo_encode_hist_table: timestamps of a series must be strictly increasing");
+  S_TRY(cudaSetDevice(filo_internal_device(ctx)));
+  cudaStream_t s = filo_internal_stream(ctx);
+  const size_t n = (size_t)n_series * (size_t)rows_per_series;
+  int64_t* d_ts = nullptr; int64_t* d_b = nullptr;
+  S_TRY(cudaMalloc(&d_ts, std::max<size_t>(n, 1) * 8));
+  if (cudaMalloc(&d_b, std::max<size_t>(n * (size_t)n_buckets, 1) * 8) != cudaSuccess) { cudaFree(d_ts); return filo_internal_fail(ctx, FILO_ERR_OOM, "filo_encode_hist_table: staging"); }
+  struct FreeIn { void* a; void* b; ~FreeIn() { cudaFree(a); cudaFree(b); } } guard{d_ts, d_b};
+  S_TRY(cudaMemcpyAsync(d_ts, timestamps, n * 8, cudaMemcpyHostToDevice, s));
+  S_TRY(cudaMemcpyAsync(d_b, bucket_counts, n * (size_t)n_buckets * 8, cudaMemcpyHostToDevice, s));
+  HistSynthParams P{n_series, rows_per_series, rows_per_chunk, 0, 1, n_buckets, format_code, bucket_def_bytes, nullptr, 0, group_ids ? n_groups : 0, 0, 0, d_ts, d_b};
+  return hist_build(ctx, P, bucket_def, schema_flags, group_ids, out);
 }

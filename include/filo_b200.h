@@ -189,6 +189,19 @@ int32_t filo_synth_table(filo_ctx* ctx, const filo_synth_spec* spec, filo_table*
 int32_t filo_encode_table(filo_ctx* ctx, const int64_t* timestamps, const double* values, int64_t n_series, int32_t rows_per_series,
                           int32_t rows_per_chunk, int32_t value_enc, int32_t schema_flags, const int32_t* group_ids, int32_t n_groups,
                           filo_table** out);
+/* Histogram columns written on the device: SectDelta HistogramVectors (AppendableSectDeltaHistVector.appendHist, HistogramVector.scala:
+ * 489-545; Section.scala:91-145; NibblePack.scala:296-345), byte-identical to the JVM appender.  bucket_def = the bucket definition as a
+ * BinaryHistogram carries it (u16 length prefix + body; format_code 0x03 / 0x04 geometric, 0x05 custom), 1..64 buckets.
+ *   filo_encode_hist_table: an ingest batch -- cumulative bucket counts [n_series][rows][n_buckets] and timestamps [n_series][rows] in HOST
+ *     memory -- encoded into a resident table (one chunk per rows_per_chunk rows);
+ *   filo_synth_hist_table: the bench / test generator (row r adds 1 + hash % 3 observations to bucket (r + series) % n_buckets,
+ *     TestTimeseriesProducer.scala:229-248; series with id % reset_period == 0 restart at 5/8 of the rows), counter schema. */
+int32_t filo_encode_hist_table(filo_ctx* ctx, const int64_t* timestamps, const int64_t* bucket_counts, int64_t n_series, int32_t rows_per_series,
+                               int32_t rows_per_chunk, int32_t n_buckets, int32_t format_code, const uint8_t* bucket_def, int32_t bucket_def_bytes,
+                               int32_t schema_flags, const int32_t* group_ids, int32_t n_groups, filo_table** out);
+int32_t filo_synth_hist_table(filo_ctx* ctx, int64_t n_series, int32_t rows_per_series, int32_t rows_per_chunk, int64_t t0_ms, int32_t interval_ms,
+                              int32_t n_buckets, int32_t format_code, const uint8_t* bucket_def, int32_t bucket_def_bytes,
+                              int32_t reset_period, int32_t n_groups, uint64_t seed, int64_t series_id_base, filo_table** out);
 int32_t filo_table_set_groups(filo_ctx* ctx, filo_table* t, const int32_t* group_ids, int32_t n_groups);
 int32_t filo_table_get_info(const filo_table* t, filo_table_info* out);
 /* Copies the device arena record of one series back to the host (tests: byte parity of the GPU encoder). */

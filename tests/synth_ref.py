@@ -65,3 +65,17 @@ def chunk_rows(rows, rows_per_chunk):
         out.append(min(rows_per_chunk, rows - r))
         r += rows_per_chunk
     return out
+
+
+def gen_hist_series(seed, gid, rows, nb, reset_period):
+    """Cumulative bucket counts [rows, nb] of the histogram generator (hist_row in synth_kernels.cu): row r adds 1 + hash % 3 observations to
+    bucket (r + gid) % nb; series with gid % reset_period == 0 restart at 5/8 of the rows."""
+    key = series_key(seed, gid)
+    cnt = np.zeros(nb, np.int64)
+    out = np.zeros((rows, nb), np.int64)
+    for r in range(rows):
+        if reset_period > 0 and gid % reset_period == 0 and r == (rows * 5) // 8:
+            cnt[:] = 0
+        cnt[(r + gid) % nb] += 1 + int(row_hash(key, r, 7) % 3)
+        out[r] = np.cumsum(cnt)
+    return out

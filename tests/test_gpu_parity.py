@@ -841,3 +841,52 @@ def test_encode_ingest_batch_on_gpu(gpu, oracle, value_enc):
         bad = ts.copy(); bad[0, 5] = bad[0, 4]
         ctx.encode_table(bad, vals)
     tab.free(); ref.free()
+
+
+@pytest.mark.parametrize("scheme", ["geometric", "custom"])
+def test_histogram_vectors_encoded_on_gpu(gpu, oracle, scheme):
+    """filo_encode_hist_table / filo_synth_hist_table: SectDelta HistogramVectors written on the device are byte for byte the JVM appender's
+    (AppendableSectDeltaHistVector.appendHist incl. section roll-over every 16 records and Drop sections; oracle restatement), and queries agree."""
+    capi, ctx = gpu; o = oracle
+    from oracle import hist as H
+    from tests import synth_ref as sr
+    rng = np.random.default_rng(61)
+    t0, rows, rpc, nb = 1_700_000_000_000, 230, 100, (20 if scheme == "geometric" else 13)
+    if scheme == "geometric":
+        b = H.Buckets.geometric(2.0, 3.0, nb); bdef, fmt = capi.geometric_bucket_def(2.0, 3.0, nb)
+        assert (bdef == b.serialize()).all()
+    else:
+        b = H.Buckets.custom([0.5 * 2 ** i for i in range(nb - 1)] + [float("inf")]); bdef, fmt = b.serialize(), 5
+    S = 17
+    ts = np.zeros((S, rows), np.int64); counts = np.zeros((S, rows, nb), np.int64)
+    for s in range(S):
+        ts[s] = t0 + np.arange(rows) * 15000 + (rng.integers(-300, 301, rows) if s % 4 == 1 else 0)
+        counts[s] = _hist_series(rng, rows, nb, () if s % 3 else (int(rng.integers(20, 90)), int(rng.integers(120, 220))))
+    gids = np.arange(S, dtype=np.int32) % 3
+    tab = ctx.encode_hist_table(ts, counts, bdef, fmt, rows_per_chunk=rpc, group_ids=gids, n_groups=3)
+    st = H.HistStore(b)
+    for s in range(S):
+        st.add_series(ts[s], counts[s], [100, 100, 30])
+    ref = ctx.load_series(*st.all_info_addrs(), schema_flags=capi.SCHEMA_CUMULATIVE)
+    a1, o1 = tab.read_arena(0, S); a2, o2 = ref.read_arena(0, S)
+    assert (o1 == o2).all() and (a1 == a2).all(), "device-encoded histogram vectors differ from the appender's bytes"
+    assert tab.info().hist_buckets == nb and tab.info().algorithmic_bytes == ref.info().algorithmic_bytes
+    q = (t0 + 300000, 15000, t0 + (rows - 1) * 15000, 300000)
+    exp, empty = st.query(o.FN_RATE, *q)
+    exp = exp.copy(); exp[empty] = NaN
+    assert_same(ctx.query_hist(tab, capi.FN_RATE, *q), exp, "rate over device-encoded histograms")
+    aexp, aempty, qexp = st.query(o.FN_RATE, *q, aggr=True, group_ids=gids, n_groups=3, q=0.9)
+    agot, qgot = ctx.query_hist(tab, capi.FN_RATE, *q, aggr=capi.AGG_SUM, quantile=0.9)
+    np.testing.assert_allclose(qgot[~aempty], qexp[~aempty], rtol=1e-9)
+    tab.free(); ref.free()
+    # the generator: same encoder over hash-generated rows
+    S2, seed, base = 11, 5, 194
+    gtab = ctx.synth_hist_table(S2, rows, bdef, fmt, nb, rows_per_chunk=rpc, t0_ms=t0, reset_period=97, seed=seed, series_id_base=base)
+    st2 = H.HistStore(b)
+    tsr = t0 + np.arange(rows, dtype=np.int64) * 15000
+    for s in range(S2):
+        st2.add_series(tsr, sr.gen_hist_series(seed, base + s, rows, nb, 97), [100, 100, 30])
+    ref2 = ctx.load_series(*st2.all_info_addrs(), schema_flags=capi.SCHEMA_CUMULATIVE)
+    a1, o1 = gtab.read_arena(0, S2); a2, o2 = ref2.read_arena(0, S2)
+    assert (o1 == o2).all() and (a1 == a2).all(), "generated histogram table differs from the appender's bytes"
+    gtab.free(); ref2.free()
