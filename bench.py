@@ -461,8 +461,8 @@ def gen_hist_series_np(seed, gid, rows, nb, reset_period):
 
 
 def run_c4(args, rank, world, local_rank):
-    """C4: histogram_quantile(0.99, sum(rate(h[5m]))) over SectDelta histogram series, 20 geometric buckets 2 * 3^i (the tops of
-    gateway/.../TestTimeseriesProducer.scala:229-235).  The table is generated AND encoded on the device (filo_synth_hist_table: the same
+    """C4: histogram_quantile(0.99, sum(rate(h[5m]))) over SectDelta histogram series, 20 custom buckets 2 * 3^i, +Inf
+    (gateway/.../TestTimeseriesProducer.scala:229-235).  The table is generated AND encoded on the device (filo_synth_hist_table: the same
     SectDelta encoder an ingest batch goes through); the query path is filo_query_hist.  The oracle only appears in the cpu_baseline /
     parity_check leg."""
     import torch
@@ -477,7 +477,7 @@ def run_c4(args, rank, world, local_rank):
     S = min(args.series, 1_000_000)
     K = min(S, 2048)
     nb = 20
-    bdef, bfmt = capi.geometric_bucket_def(2.0, 3.0, nb)
+    bdef, bfmt = capi.custom_bucket_def([2.0 * 3 ** i for i in range(nb - 1)] + [float("inf")])      # TestTimeseriesProducer.scala:229-235
     ctx = capi.Context(local_rank)
     t_gen = time.perf_counter()
     tab = ctx.synth_hist_table(S, ROWS, bdef, bfmt, nb, rows_per_chunk=ROWS_PER_CHUNK, t0_ms=T0_MS, interval_ms=INTERVAL, reset_period=97, seed=42, series_id_base=rank * S)
@@ -509,7 +509,7 @@ def run_c4(args, rank, world, local_rank):
     line = {"metric": "samples/s scanned+aggregated (rate over 10M series); % HBM roofline", "value": ti.n_samples * world / (ms / 1e3), "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "i64 bucket counts -> f64 rates", "data": "synthetic",
-            "config": {"workload": "C4: %d histogram series x 2h@15s (480 rows, chunks 400+80), SectDelta vectors encoded on the device, 20 geometric buckets 2*3^i, "
+            "config": {"workload": "C4: %d histogram series x 2h@15s (480 rows, chunks 400+80), SectDelta vectors encoded on the device, 20 custom buckets 2*3^i .. +Inf, "
                                    "histogram_quantile(0.99, sum(rate(h[5m]))) step 15s, T=%d (per GPU; shards are independent, no cross-GPU merge)" % (S, T),
                        "series_per_gpu": S, "rows": ROWS, "windows": T, "buckets": nb, "window_ms": window, "step_ms": step,
                        "l2": "inputs (%.1f GB arena) larger than the 126 MB L2" % (ti.arena_bytes / 1e9), "table_gen_s": round(t_gen, 2)},
@@ -533,7 +533,7 @@ def run_c4(args, rank, world, local_rank):
                        "s_per_step": dt, "series_per_gpu": Se, "what": "filo_load_series + filo_query_hist + filo_table_free per step"}
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import hist as H, oracle as o
-        b = H.Buckets.geometric(2.0, 3.0, nb)
+        b = H.Buckets.custom([2.0 * 3 ** i for i in range(nb - 1)] + [float("inf")])
         st = H.HistStore(b)
         ts = T0_MS + np.arange(ROWS, dtype=np.int64) * INTERVAL
         for s_ in range(K):                                           # the first K series of the device table, rebuilt from the generator's model

@@ -120,6 +120,42 @@ def geometric_bucket_def(first, mult, n):
     return np.frombuffer(struct.pack("<Hhdd", 18, n, float(first), float(mult)), np.uint8).copy(), 3
 
 
+def _pack8(vals8):
+    """NibblePack.pack8 (NibblePack.scala:108-183) of eight u64: bitmask byte, then for a non-zero mask the nibble-count byte and the
+    set values as little-endian bit-packed fields of numNibbles * 4 bits each."""
+    mask = 0; orv = 0; mintz = 64
+    for i, v in enumerate(vals8):
+        if v:
+            mask |= 1 << i; orv |= v
+            mintz = min(mintz, (v & -v).bit_length() - 1)
+    out = bytearray([mask])
+    if not mask:
+        return bytes(out)
+    lz = 64 - orv.bit_length()
+    trailing = mintz // 4; nnib = 16 - lz // 4 - trailing; nbits = nnib * 4
+    out.append(((nnib - 1) << 4) | trailing)
+    acc = 0; pos = 0
+    for v in vals8:
+        if v:
+            acc |= ((v >> (trailing * 4)) & ((1 << nbits) - 1)) << pos; pos += nbits
+    out += acc.to_bytes((pos + 7) // 8, "little")
+    return bytes(out)
+
+
+def custom_bucket_def(les):
+    """CustomBuckets.serialize (Histogram.scala:878-884): u16 length, u16 numBuckets, NibblePack.packDoubles(les) = the first value's bits
+    followed by groups of eight XOR-with-previous values; format code 0x05."""
+    import struct
+    bits = [struct.unpack("<Q", struct.pack("<d", float(x)))[0] for x in les]
+    body = bytearray(struct.pack("<Q", bits[0]))
+    xs = [bits[i + 1] ^ bits[i] for i in range(len(bits) - 1)]
+    for g in range(0, len(xs), 8):
+        grp = xs[g:g + 8]; grp += [0] * (8 - len(grp))
+        body += _pack8(grp)
+    d = struct.pack("<HH", 2 + len(body), len(les)) + bytes(body)
+    return np.frombuffer(d, np.uint8).copy(), 5
+
+
 def sin_table(rows):
     return np.sin(np.arange(1, rows + 1, dtype=np.float64))
 

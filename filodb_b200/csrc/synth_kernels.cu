@@ -318,7 +318,7 @@ __global__ void synth_fill_kernel(SynthParams P, const int64_t* rec_off, uint8_t
 // ---------------------------------------------------------------------------------------------------------------------
 // Histogram columns: SectDelta HistogramVectors written on the device (AppendableSectDeltaHistVector.appendHist, HistogramVector.scala:
 // 489-545; SectionWriter, Section.scala:91-145; DeltaSectDiffPackSink, NibblePack.scala:296-345; BinaryHistogram delta formats :84-200).
-// Vector = [+0 i32 numBytes][+4 u16 wire H_SECTDELTA][+6 u16 numHistograms][+8 u8 formatCode][+9 u16 bucketDefBytes][+11 bucket def]
+// Vector = [+0 i32 numBytes][+4 u16 wire H_SECTDELTA][+6 u16 numHistograms][+8 u8 formatCode][+9 u16 bucketDefBytes][+11 bucket def body]
 // sections...; section = [u16 bytes][u8 elems][u8 type (1 = drop)] records...; record = [u16 len] NibblePack groups.  The first record of a
 // section holds the histogram's bucket deltas (NibblePack.packDelta), the others the difference to that record's deltas; a histogram with a
 // bucket delta below the previous histogram's opens a Drop section.  Thread per series, sequential (generator / encoder, not a hot path).
@@ -367,10 +367,10 @@ __device__ uint32_t hist_encode_chunk(const HistSynthParams& P, int64_t si, uint
   auto put16 = [&](uint32_t off, uint32_t v) { if (EMIT) { dst[off] = (uint8_t)v; dst[off + 1] = (uint8_t)(v >> 8); } };
   auto put8 = [&](uint32_t off, uint32_t v) { if (EMIT) dst[off] = (uint8_t)v; };
   if (EMIT) {
-    put16(4, (uint32_t)WIRE_H_SECTDELTA); put16(6, (uint32_t)n); put8(8, (uint32_t)P.format_code); put16(9, (uint32_t)P.def_bytes);
-    for (int k = 0; k < P.def_bytes; ++k) dst[11 + k] = P.def[k];
+    put16(4, (uint32_t)WIRE_H_SECTDELTA); put16(6, (uint32_t)n); put8(8, (uint32_t)P.format_code);
+    for (int k = 0; k < P.def_bytes; ++k) dst[9 + k] = P.def[k];          // the serialized definition's u16 length IS the header's bucketDefBytes at +9, its body sits at +11
   }
-  uint32_t cur = 11u + (uint32_t)P.def_bytes, secBytes = 0, secElems = 0;      // SectionWriter state
+  uint32_t cur = 9u + (uint32_t)P.def_bytes, secBytes = 0, secElems = 0;       // SectionWriter state
   put16(cur, 0); put8(cur + 2, 0); put8(cur + 3, 0);
   int64_t orig[HS_MAXNB], last[HS_MAXNB];
   for (int b = 0; b < nb; ++b) { orig[b] = 0; last[b] = 0; }
@@ -605,8 +605,8 @@ static int32_t hist_build(filo_ctx* ctx, HistSynthParams P, const uint8_t* h_def
   filo_internal_set_arena(t, d_arena, d_off, S, S * nch, S * (int64_t)P.rows, arena_bytes + (S + 1) * 8, (int64_t)alg, P.rows, nch, schema_flags);
   filo_internal_set_layout(t, max_rec, P.ext_ts != nullptr, false);
   std::vector<uint8_t> hd((size_t)11 + (size_t)P.def_bytes + 32, 0);       // a HistogramVector header for the table's bucket scheme
-  hd[8] = (uint8_t)P.format_code; hd[9] = (uint8_t)P.def_bytes; hd[10] = (uint8_t)(P.def_bytes >> 8);
-  std::memcpy(hd.data() + 11, h_def, (size_t)P.def_bytes);
+  hd[8] = (uint8_t)P.format_code;
+  std::memcpy(hd.data() + 9, h_def, (size_t)P.def_bytes);
   int32_t rc = filo_internal_set_hist(ctx, t, hd.data());
   if (rc == FILO_OK) rc = filo_internal_finish_table(ctx, t, d_gid, P.n_groups > 0 ? P.n_groups : 1);
   cudaFree(d_gid);

@@ -33,7 +33,10 @@ struct QueryError : std::runtime_error {
 enum class InternalRangeFunction : int32_t {
   LastSample = FILO_FN_LAST, Rate = FILO_FN_RATE, Increase = FILO_FN_INCREASE, Delta = FILO_FN_DELTA,
   SumOverTime = FILO_FN_SUM_OVER_TIME, AvgOverTime = FILO_FN_AVG_OVER_TIME, CountOverTime = FILO_FN_COUNT_OVER_TIME,
-  MinOverTime = FILO_FN_MIN_OVER_TIME, MaxOverTime = FILO_FN_MAX_OVER_TIME, Timestamp = FILO_FN_TIMESTAMP
+  MinOverTime = FILO_FN_MIN_OVER_TIME, MaxOverTime = FILO_FN_MAX_OVER_TIME, Timestamp = FILO_FN_TIMESTAMP,
+  StdDevOverTime = FILO_FN_STDDEV_OVER_TIME, StdVarOverTime = FILO_FN_STDVAR_OVER_TIME, Changes = FILO_FN_CHANGES,
+  QuantileOverTime = FILO_FN_QUANTILE_OVER_TIME, ZScore = FILO_FN_ZSCORE, HoltWinters = FILO_FN_HOLT_WINTERS,
+  PredictLinear = FILO_FN_PREDICT_LINEAR, MedianAbsoluteDeviationOverTime = FILO_FN_MAD_OVER_TIME, PresentOverTime = FILO_FN_PRESENT_OVER_TIME
 };
 // AggregationOperator (query/src/main/scala/filodb/query/PlanEnums.scala) subset
 enum class AggregationOperator : int32_t {
@@ -54,8 +57,10 @@ struct PeriodicSamplesMapper : RangeVectorTransformer {
   int64_t startMs, stepMs, endMs;
   std::optional<int64_t> window;
   std::optional<InternalRangeFunction> functionId;
-  PeriodicSamplesMapper(int64_t start, int64_t step, int64_t end, std::optional<int64_t> windowMs, std::optional<InternalRangeFunction> fn)
-      : startMs(start), stepMs(step), endMs(end), window(windowMs), functionId(fn) {
+  std::vector<double> funcParams;              // StaticFuncArgs scalars: quantile_over_time(q), holt_winters(sf, tf), predict_linear(seconds)
+  PeriodicSamplesMapper(int64_t start, int64_t step, int64_t end, std::optional<int64_t> windowMs, std::optional<InternalRangeFunction> fn,
+                        std::vector<double> params = {})
+      : startMs(start), stepMs(step), endMs(end), window(windowMs), functionId(fn), funcParams(std::move(params)) {
     // PeriodicSamplesMapper.scala:45-49
     if (!(start <= end)) throw std::invalid_argument("requirement failed: start " + std::to_string(start) + " should be <= end " + std::to_string(end));
     if (!(start == end || step > 0)) throw std::invalid_argument("requirement failed: step should be > 0 for range query");
@@ -109,6 +114,7 @@ class FusedGpuExec {
     struct Free { filo_ctx* c; filo_table* t; ~Free() { filo_table_free(c, t); } } guard{ctx_, t};
     const int32_t fn = (int32_t)psm.functionId.value_or(InternalRangeFunction::LastSample);
     const int64_t window = psm.window.value_or(0);
+    check(filo_ctx_set_fn_args(ctx_, psm.funcParams.size() > 0 ? psm.funcParams[0] : 0.0, psm.funcParams.size() > 1 ? psm.funcParams[1] : 0.0));
     QueryResult r; r.windows = filo_num_windows(psm.startMs, psm.stepMs, psm.endMs);
     if (histogram) {
       filo_table_info ti{}; filo_table_get_info(t, &ti);

@@ -856,7 +856,9 @@ def test_histogram_vectors_encoded_on_gpu(gpu, oracle, scheme):
         b = H.Buckets.geometric(2.0, 3.0, nb); bdef, fmt = capi.geometric_bucket_def(2.0, 3.0, nb)
         assert (bdef == b.serialize()).all()
     else:
-        b = H.Buckets.custom([0.5 * 2 ** i for i in range(nb - 1)] + [float("inf")]); bdef, fmt = b.serialize(), 5
+        les = [0.5 * 2 ** i for i in range(nb - 1)] + [float("inf")]
+        b = H.Buckets.custom(les); bdef, fmt = capi.custom_bucket_def(les)
+        assert (bdef == b.serialize()).all()
     S = 17
     ts = np.zeros((S, rows), np.int64); counts = np.zeros((S, rows, nb), np.int64)
     for s in range(S):
