@@ -179,10 +179,24 @@ static bool hist_v2_enabled() { const char* e = getenv("FILO_HIST_V2"); return !
 // ------------------------------------------------------------------------------------------------------------------
 // grouping: stable sort of series by group id on the device, group bounds, work items of <= seg series of one group
 // ------------------------------------------------------------------------------------------------------------------
+static int32_t build_groups_new(filo_ctx* ctx, filo_table* t, const int32_t* d_group_ids, int32_t n_groups);
+// the new grouping replaces the old one only when it has been built completely: a failure leaves the table as it was
 static int32_t build_groups(filo_ctx* ctx, filo_table* t, const int32_t* d_group_ids /* device, may be null */, int32_t n_groups) {
-  cudaStream_t s = ctx->stream;
-  cudaFree(t->d_order); cudaFree(t->d_group_start); cudaFree(t->d_gis); cudaFree(t->d_item_begin);
+  int32_t* o_order = t->d_order; int64_t* o_gs = t->d_group_start; int64_t* o_gis = t->d_gis; int64_t* o_ib = t->d_item_begin;
+  const int32_t o_ng = t->n_groups; const bool o_grouped = t->grouped; const int64_t o_items = t->n_items; const int o_seg = t->seg;
   t->d_order = nullptr; t->d_group_start = t->d_gis = t->d_item_begin = nullptr;
+  const int32_t rc = build_groups_new(ctx, t, d_group_ids, n_groups);
+  if (rc != FILO_OK) {
+    cudaFree(t->d_order); cudaFree(t->d_group_start); cudaFree(t->d_gis); cudaFree(t->d_item_begin);
+    t->d_order = o_order; t->d_group_start = o_gs; t->d_gis = o_gis; t->d_item_begin = o_ib;
+    t->n_groups = o_ng; t->grouped = o_grouped; t->n_items = o_items; t->seg = o_seg;
+    return rc;
+  }
+  cudaFree(o_order); cudaFree(o_gs); cudaFree(o_gis); cudaFree(o_ib);
+  return FILO_OK;
+}
+static int32_t build_groups_new(filo_ctx* ctx, filo_table* t, const int32_t* d_group_ids /* device, may be null */, int32_t n_groups) {
+  cudaStream_t s = ctx->stream;
   const int64_t S = t->n_series;
   if (n_groups <= 0) n_groups = 1;
   t->n_groups = n_groups;
@@ -509,14 +523,23 @@ static int32_t filo_load_series_impl(filo_ctx* ctx, int64_t n_series, const int3
   if (tot.hist_def && tot.any_scalar) return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram and scalar value vectors in one table");
   if (tot.hist_mismatch) return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram bucket schemes differ inside the table (unsupported on the device path)");
   // ---- pass 2: fill pinned slabs, copy
-  auto* t = new filo_table();
-  uint8_t* d_arena = nullptr; int64_t* d_rec_off = nullptr;
+  // everything allocated below is released on every early return (CUDA_TRY) until the table owns the arena
+  struct LoadGuard {
+    filo_table* t = nullptr; uint8_t* d_arena = nullptr; int64_t* d_rec_off = nullptr; uint8_t* slab[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool owns_table = true;
+    ~LoadGuard() {
+      for (int b = 0; b < 2; ++b) { if (ev[b]) { cudaEventSynchronize(ev[b]); cudaEventDestroy(ev[b]); } if (slab[b]) cudaFreeHost(slab[b]); }
+      if (owns_table) { cudaFree(d_arena); cudaFree(d_rec_off); delete t; }
+    }
+  } lg;
+  lg.t = new filo_table();
+  filo_table*& t = lg.t; uint8_t*& d_arena = lg.d_arena; int64_t*& d_rec_off = lg.d_rec_off;
   CUDA_TRY(ctx, cudaMalloc(&d_arena, (size_t)arena_bytes + 64));
   CUDA_TRY(ctx, cudaMalloc(&d_rec_off, (size_t)(n_series + 1) * 8));
   CUDA_TRY(ctx, cudaMemsetAsync(d_arena + arena_bytes, 0, 64, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(d_rec_off, rec_off.data(), (size_t)(n_series + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   const size_t SLAB = std::min<size_t>((size_t)256 << 20, std::max<size_t>((size_t)arena_bytes, 1 << 16));
-  uint8_t* slab[2] = {nullptr, nullptr}; cudaEvent_t ev[2];
+  uint8_t** slab = lg.slab; cudaEvent_t* ev = lg.ev;
   for (int b = 0; b < 2; ++b) { CUDA_TRY(ctx, cudaHostAlloc(&slab[b], SLAB + (1 << 20), cudaHostAllocDefault)); CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming)); }
   int64_t s0 = 0; int which = 0;
   while (s0 < n_series) {
@@ -538,7 +561,7 @@ static int32_t filo_load_series_impl(filo_ctx* ctx, int64_t n_series, const int3
     which ^= 1; s0 = s1;
   }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  for (int b = 0; b < 2; ++b) { cudaFreeHost(slab[b]); cudaEventDestroy(ev[b]); }
+  lg.owns_table = false;                               // from here on the table owns the arena; later failures go through filo_table_free
   filo_internal_set_arena(t, d_arena, d_rec_off, n_series, tot.chunks, tot.samples, arena_bytes + (n_series + 1) * 8, tot.alg, tot.maxrows, tot.maxch, schema_flags);
   filo_internal_set_layout(t, tot.max_rec, n_series > 0 && !(tot.f_and & REC_ALL_TS_CONST), (tot.f_or & REC_ANY_DROP) != 0);
   if (tot.hist_def) {                                  // histogram table: one bucket scheme, tops kept for histogram_quantile
