@@ -74,17 +74,19 @@ WP_CTR_RARE double wp_eval_counter(int n, const WpCtrChunk* K, const WpChunk* CD
 }
 
 // ---- irregular timestamps (DDV with residuals, or a scrape interval that differs from the query step): row times live in TSR as int32
-// offsets from the chunk's first timestamp (TSR[rowpos + r] = ts(r) - init); row ranges by a guess on the chunk's slope + a short walk
+// offsets from the chunk's first timestamp (TSR[rowpos + r] = ts(r) - init); row ranges by a (float) guess on the chunk's slope + a short walk
 // (exact for any data: the walk ends at the first row with ts >= t)
 __device__ __forceinline__ int wp_irr_lower(const int32_t* TSR, const WpCtrChunk& ch, int64_t t) {
-  const int64_t d = t - ch.init;
-  if (d <= 0) return 0;
+  const int64_t d64 = t - ch.init;
+  if (d64 <= 0) return 0;
   const int32_t* p = TSR + ch.rowpos;
-  if (d > (int64_t)p[ch.nrows - 1]) return ch.nrows;
-  int g = (int)((double)d * ch.kc.sI);                     // kc.sI holds 1 / slope for an irregular series
-  if (g > ch.nrows - 1) g = ch.nrows - 1;
-  while (g < ch.nrows && (int64_t)p[g] < d) ++g;
-  while (g > 0 && (int64_t)p[g - 1] >= d) --g;
+  const int nr = ch.nrows;
+  if (d64 > (int64_t)p[nr - 1]) return nr;
+  const int32_t d = (int32_t)d64;                          // 0 < d <= last row's offset: 32-bit from here on
+  int g = (int)((float)d * __int_as_float(ch.kc.pad));     // kc.pad holds the bits of (float)(1 / slope) for an irregular series; the walk makes it exact
+  if (g > nr - 1) g = nr - 1;
+  while (g < nr && p[g] < d) ++g;
+  while (g > 0 && p[g - 1] >= d) --g;
   return g;
 }
 // the literal fold of wp_eval_counter with searched row ranges and stored sample times
@@ -272,7 +274,7 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
           d.init = init; d.end_time = end_time; d.nrows = nrows; d.s0 = (int)s0; d.e0 = (int)e0; d.rowpos = rowpos;
           d.kA = blocked ? (int)kA : 0; d.kB = blocked ? (int)kB : -1;
           d.kA2 = (have && !irr && kA2 <= kB2) ? (int)kA2 : 0; d.kB2 = (have && !irr && kA2 <= kB2) ? (int)kB2 : -1;      // irregular: every window takes the literal fold
-          if (irr) d.kc.sI = have ? 1.0 / (double)P.tslope : 0.0;
+          if (irr) d.kc.pad = __float_as_int(have ? 1.0f / (float)P.tslope : 0.0f);
           if (blocked) {
             // RateFunctions.extrapolatedRate (RateFunctions.scala:72-111) for the chunk's unclamped single-chunk windows: the sample
             // times move with the window, so durationToStart / End, sampledInterval, numSamples are window-invariant
