@@ -397,8 +397,8 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
         // V index of row r0 + 32 m = index of row r0 + 36 m (one pad slot per 8 rows)
         const double* p1 = V + wp_vidx(ch.rowpos + ch.s0 + ch.kA + lane);
         const double* p2 = V + wp_vidx(ch.rowpos + ch.e0 + ch.kA + lane);
-        for (int kk = ch.kA + lane; hasfast && kk <= ch.kB; kk += 32, p1 += 36, p2 += 36) {
-          double v1 = *p1, v2 = *p2;
+        // one window from its two samples (extrapolatedRate with the chunk's window-invariant terms)
+        auto fast_one = [&](int kk, double v1, double v2) -> double {
           if (drp) {
             const int r1 = ch.s0 + kk, r2 = ch.e0 + kk;
             if (dn <= 1) { v1 = nan0(v1) + (r1 >= dpos0 ? damt0 : 0.0); v2 = nan0(v2) + (r2 >= dpos0 ? damt0 : 0.0); }
@@ -413,8 +413,23 @@ scan_wp_ctr_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict_
             ratio = ddiv_rare(eTI, kc.sI);
           }
           const double scaled = delta * ratio;
-          emit(kk, FN == FN_RATE ? __dmul_rn(div_invariant(scaled, fdiv, frcp), 1000.0) : scaled);
+          return FN == FN_RATE ? __dmul_rn(div_invariant(scaled, fdiv, frcp), 1000.0) : scaled;
+        };
+#ifdef FILO_WP_CTR_PAIR
+        // two windows per lane and iteration (kk and kk + 32): the kernel is latency bound (profiles/r2/r2_ctr_ab.md), two independent
+        // dependency chains per warp overlap
+        for (int kk = ch.kA + lane; hasfast && kk <= ch.kB; kk += 64, p1 += 72, p2 += 72) {
+          const bool two = kk + 32 <= ch.kB;
+          const double a1 = *p1, a2 = *p2;
+          const double b1 = two ? p1[36] : 0.0, b2 = two ? p2[36] : 0.0;
+          const double ra = fast_one(kk, a1, a2);
+          const double rb = two ? fast_one(kk + 32, b1, b2) : 0.0;
+          emit(kk, ra);
+          if (two) emit(kk + 32, rb);
         }
+#else
+        for (int kk = ch.kA + lane; hasfast && kk <= ch.kB; kk += 32, p1 += 36, p2 += 36) emit(kk, fast_one(kk, *p1, *p2));
+#endif
         // the chunk's clamped single-chunk windows (window start before its first row or end after its last): the sample distance
         // varies with the window, the table supplies the terms that depend on it
         const int nlo = hasfast ? ch.kA - ch.kA2 : ch.kB2 - ch.kA2 + 1, nhi = hasfast ? ch.kB2 - ch.kB : 0;
