@@ -12,12 +12,14 @@ pytestmark = pytest.mark.gpu
 NaN = float("nan")
 
 
-@pytest.fixture(scope="module", params=["v3", "v2", "v1"])
+@pytest.fixture(scope="module", params=["v4", "v3", "v2", "v1"])
 def gpu(request):
-    """Every test runs against both kernel generations: v2 (TMA-staged, blocked reductions; the default) and v1 (generic)."""
+    """Every test runs against every kernel generation: v4 (the default: warp-pipeline kernels scan_wp_sum / scan_wp_ctr, with the v2 kernel
+    behind them for what they decline), v3 (round-1 tile kernel), v2 (TMA-staged warp per series), v1 (generic, global-memory reads)."""
     import os
     import filodb_b200.capi as capi
-    os.environ["FILO_KERNEL"] = request.param
+    if request.param == "v4": os.environ.pop("FILO_KERNEL", None)
+    else: os.environ["FILO_KERNEL"] = request.param
     ctx = capi.Context(0)
     yield capi, ctx
     ctx.close()
