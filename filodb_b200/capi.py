@@ -120,6 +120,13 @@ def geometric_bucket_def(first, mult, n):
     return np.frombuffer(struct.pack("<Hhdd", 18, n, float(first), float(mult)), np.uint8).copy(), 3
 
 
+def exp_bucket_def(scale, start_index, num_positive):
+    """Base2ExpHistogramBuckets.serialize (Histogram.scala:729-752): u16 length 16, u16 numBuckets (= num_positive + 1, the zero bucket first),
+    i16 scale, i32 startIndexPositiveBuckets, u16 numPositiveBuckets, i32 / u16 of the unused negative range; format code 0x09."""
+    import struct
+    return np.frombuffer(struct.pack("<HHhiHiH", 16, num_positive + 1, scale, start_index, num_positive, 0, 0), np.uint8).copy(), 9
+
+
 def _pack8(vals8):
     """NibblePack.pack8 (NibblePack.scala:108-183) of eight u64: bitmask byte, then for a non-zero mask the nibble-count byte and the
     set values as little-endian bit-packed fields of numNibbles * 4 bits each."""

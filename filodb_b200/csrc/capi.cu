@@ -75,7 +75,7 @@ struct filo_table {
   int64_t n_items = 0;
   int seg = 1;
   // histogram tables (value column = HistogramVector): one bucket scheme for the whole table
-  bool hist = false; int hist_nb = 0;
+  bool hist = false, hist_exp = false; int hist_nb = 0;     // hist_exp: Base2ExpHistogramBuckets (histogram_quantile interpolates in log space)
   std::vector<double> hist_tops; double* d_hist_tops = nullptr;
 };
 
@@ -326,8 +326,10 @@ int classify_val(const uint8_t* v, VecInfo& o) {
     if (masked || o.total < 13) return FILO_ERR_CORRUPT_VECTOR;
     o.len = (uint16_t)(v[6] | (v[7] << 8)); o.drop = false; o.hist = true;
     const int fmt = v[8], defBytes = (uint16_t)(v[9] | (v[10] << 8));
-    if (o.len > 0 && (!(fmt == 3 || fmt == 4 || fmt == 5) || 11 + defBytes > o.total)) return (fmt == 8 || fmt == 9 || fmt == 0x0a || fmt == 0x10) ? FILO_ERR_UNSUPPORTED : FILO_ERR_CORRUPT_VECTOR;
-  } else return FILO_ERR_CORRUPT_VECTOR;
+    if (o.len > 0 && (!(fmt == 3 || fmt == 4 || fmt == 5 || fmt == 9) || 11 + defBytes > o.total || (fmt == 9 && defBytes != 16)))
+      return (fmt == 8 || fmt == 0x0a || fmt == 0x10 || fmt == 9) ? FILO_ERR_UNSUPPORTED : FILO_ERR_CORRUPT_VECTOR;
+  } else if (wire == WIRE_H_EXP_SIMPLE) return FILO_ERR_UNSUPPORTED;        // ExpHistogramVector.scala: row-wise schemes (no counter reader in the reference either)
+  else return FILO_ERR_CORRUPT_VECTOR;
   return (o.total >= 8 && o.len >= 0) ? 0 : FILO_ERR_CORRUPT_VECTOR;
 }
 
@@ -486,8 +488,20 @@ int32_t filo_internal_set_hist(filo_ctx* ctx, filo_table* t, const uint8_t* hd) 
   } else if (ok && fmt == 5) {                        // CustomBuckets: u16 n + NibblePack.packDoubles(les), Histogram.scala:878-884
     const int defBytes = (uint16_t)(hd[9] | (hd[10] << 8));
     ok = host_unpack_double_xor(hd + 13, defBytes - 2, t->hist_tops.data(), nb);
+  } else if (ok && fmt == 9) {                        // Base2ExpHistogramBuckets (otel exponential), Histogram.scala:729-752: i16 scale, i32 startIndexPositiveBuckets,
+    // u16 numPositiveBuckets (+ the unused negative pair); numBuckets = numPositive + 1 (the zero bucket).  Tops as bucketTop computes them (:716-727,
+    // base / logBase tables :647-658) with the host's libm, the same calls the oracle makes
+    const int scale = (int16_t)(hd[13] | (hd[14] << 8)), numPos = (uint16_t)(hd[19] | (hd[20] << 8));
+    int32_t startIdx; std::memcpy(&startIdx, hd + 15, 4);
+    ok = scale >= -20 && scale <= 20 && numPos == nb - 1;
+    if (ok) {
+      const double logBase = std::log(std::pow(2.0, std::pow(2.0, (double)-scale)));
+      t->hist_tops[0] = 0.0;
+      for (int i = 1; i < nb; ++i) t->hist_tops[(size_t)i] = std::exp((double)(startIdx + i) * logBase);
+      t->hist_exp = true;
+    }
   } else ok = false;
-  if (!ok) return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram bucket scheme not supported on the device path (1..64 geometric or custom buckets)");
+  if (!ok) return fail(ctx, FILO_ERR_UNSUPPORTED, "histogram bucket scheme not supported on the device path (1..64 geometric, custom or otel exponential buckets)");
   CUDA_TRY(ctx, cudaMalloc(&t->d_hist_tops, (size_t)nb * 8));
   CUDA_TRY(ctx, cudaMemcpy(t->d_hist_tops, t->hist_tops.data(), (size_t)nb * 8, cudaMemcpyHostToDevice));
   return FILO_OK;
@@ -1406,12 +1420,12 @@ static int32_t filo_query_hist_impl(filo_ctx* ctx, const filo_table* t, int32_t 
     CUDA_TRY(ctx, tmp.alloc((void**)&pval, (size_t)t->n_items * T * nb * 8));
     CUDA_TRY(ctx, tmp.alloc((void**)&pany, (size_t)t->n_items * T + 16));
     CUDA_TRY(ctx, launch_hist_scan2(L, nb, t->max_rows, t->max_rec_bytes, t->grouped ? t->d_order : nullptr, t->d_item_begin, t->n_items, pval, pany));
-    CUDA_TRY(ctx, launch_hist_merge2(pval, pany, t->d_gis, t->n_groups, T, nb, t->d_hist_tops, out_quantile ? quantile : std::nan(""), d_out, d_q, s));
+    CUDA_TRY(ctx, launch_hist_merge2(pval, pany, t->d_gis, t->n_groups, T, nb, t->hist_exp ? 1 : 0, t->d_hist_tops, out_quantile ? quantile : std::nan(""), d_out, d_q, s));
   } else if (fused) {
     CUDA_TRY(ctx, tmp.alloc((void**)&pval, (size_t)t->n_items * T * nb * 8));
     CUDA_TRY(ctx, tmp.alloc((void**)&pany, (size_t)t->n_items * T + 16));
     CUDA_TRY(ctx, launch_hist_scan(L, nb, t->max_rows, t->max_rec_bytes, t->grouped ? t->d_order : nullptr, t->d_item_begin, t->n_items, 1, nullptr, pval, pany));
-    CUDA_TRY(ctx, launch_hist_merge(pval, pany, t->d_gis, t->n_groups, T, nb, t->d_hist_tops, out_quantile ? quantile : std::nan(""), d_out, d_q, s));
+    CUDA_TRY(ctx, launch_hist_merge(pval, pany, t->d_gis, t->n_groups, T, nb, t->hist_exp ? 1 : 0, t->d_hist_tops, out_quantile ? quantile : std::nan(""), d_out, d_q, s));
   } else {
     CUDA_TRY(ctx, launch_hist_scan(L, nb, t->max_rows, t->max_rec_bytes, nullptr, nullptr, 0, 0, d_out, nullptr, nullptr));
   }

@@ -43,6 +43,7 @@ constexpr int WIRE_MASKED     = (0x00 << 8) | 0x06;   // BINSIMPLE / PRIMITIVE
 constexpr int WIRE_RAW64      = (0x05 << 8) | 0x06;   // BINSIMPLE / PRIMITIVE_NOMASK
 constexpr int WIRE_XOR        = (0x21 << 8) | 0x06;
 constexpr int WIRE_H_SIMPLE   = (0x10 << 8) | 0x09;   // HISTOGRAM / H_SIMPLE   (WireFormat.scala:17,35)
+constexpr int WIRE_H_EXP_SIMPLE = (0x13 << 8) | 0x09; // HISTOGRAM / H_EXP_SIMPLE (WireFormat.scala:38): a blob with its own scheme per row; declined
 constexpr int WIRE_H_SECTDELTA = (0x12 << 8) | 0x09;  // HISTOGRAM / H_SECTDELTA (WireFormat.scala:37)   // BINSIMPLE / XOR_NIBBLE (this repo's container)
 
 // XOR container header (oracle/filo_format.hpp documents the same layout):

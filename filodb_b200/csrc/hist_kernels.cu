@@ -14,6 +14,7 @@
 #include "kernels.h"
 #include "scan_device.cuh"
 #include "scan_fast.cuh"
+#include "hist_phases.h"
 
 namespace filo {
 
@@ -406,9 +407,9 @@ hist_scan_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__ 
 
 
 // Fold the partial rows of each group in item order (deterministic), MutableHistogram.add per item (Histogram.scala:428-449),
-// then Histogram.quantile (:65-108, non-exponential buckets).  Thread per (group, window).
+// then Histogram.quantile (:65-108, hist_quantile in hist_phases.h).  Thread per (group, window).
 __global__ void hist_merge_kernel(const double* __restrict__ pval, const uint8_t* __restrict__ pany, const int64_t* __restrict__ gis,
-                                  int n_groups, int T, int nb, const double* __restrict__ tops, double qtl,
+                                  int n_groups, int T, int nb, int exp_buckets, const double* __restrict__ tops, double qtl,
                                   double* __restrict__ out_values /* [G][T][nb] or null */, double* __restrict__ out_q /* [G][T] or null */) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)n_groups * T) return;
@@ -425,28 +426,7 @@ __global__ void hist_merge_kernel(const double* __restrict__ pval, const uint8_t
     double mx = 0.0;
     for (int b = 0; b < nb; ++b) { double nv = v[b] + pv[b]; if (nv < mx || nv != nv) nv = mx; else if (nv > mx) mx = nv; v[b] = nv; }
   }
-  double qv = NaNv;
-  if (any) {
-    if (qtl == qtl) {                                                        // Histogram.quantile
-      const double top = v[nb - 1];
-      if (qtl < 0) qv = __longlong_as_double(0xfff0000000000000LL);
-      else if (qtl > 1) qv = __longlong_as_double(0x7ff0000000000000LL);
-      else if (nb < 2 || !(top > 0)) qv = NaNv;
-      else {
-        double rank = qtl * top;
-        int bucket = 0; while (v[bucket] < rank) ++bucket;
-        double bucketStart = bucket == 0 ? 0.0 : tops[bucket - 1];
-        const double bucketEnd = tops[bucket];
-        if (bucket == nb - 1 && isinf(bucketEnd) && bucketEnd > 0) qv = tops[nb - 2];
-        else if (bucket == 0 && tops[0] <= 0) qv = tops[0];
-        else {
-          const double count = bucket == 0 ? v[bucket] : v[bucket] - v[bucket - 1];
-          rank -= (bucket == 0 ? 0.0 : v[bucket - 1]);
-          qv = bucketStart + (bucketEnd - bucketStart) * (rank / count);
-        }
-      }
-    }
-  }
+  const double qv = (any && qtl == qtl) ? hist_quantile(v, nb, tops, qtl, exp_buckets != 0) : NaNv;
   if (out_values) for (int b = 0; b < nb; ++b) out_values[(size_t)i * nb + b] = any ? v[b] : NaNv;
   if (out_q) out_q[i] = qv;
 }
@@ -470,11 +450,11 @@ cudaError_t launch_hist_scan(const ScanLaunch& L, int nb, int max_rows, uint32_t
                                                              out, pval, pany, L.d_counters, L.d_err);
   return cudaGetLastError();
 }
-cudaError_t launch_hist_merge(const double* pval, const uint8_t* pany, const int64_t* gis, int n_groups, int T, int nb, const double* tops, double q,
+cudaError_t launch_hist_merge(const double* pval, const uint8_t* pany, const int64_t* gis, int n_groups, int T, int nb, int exp_buckets, const double* tops, double q,
                               double* out_values, double* out_q, cudaStream_t s) {
   const int64_t n = (int64_t)n_groups * T;
   if (n <= 0) return cudaSuccess;
-  hist_merge_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pval, pany, gis, n_groups, T, nb, tops, q, out_values, out_q);
+  hist_merge_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pval, pany, gis, n_groups, T, nb, exp_buckets, tops, q, out_values, out_q);
   return cudaGetLastError();
 }
 

@@ -107,9 +107,9 @@ hist_scan2_kernel(const uint8_t* __restrict__ arena, const int64_t* __restrict__
 }
 
 // Fold the partial rows of each group in item order (deterministic), MutableHistogram.add per item (Histogram.scala:428-449),
-// then Histogram.quantile (:65-108, non-exponential buckets).  Thread per (group, window); partial rows are bucket-major.
+// then Histogram.quantile (:65-108, hist_quantile in hist_phases.h).  Thread per (group, window); partial rows are bucket-major.
 __global__ void hist_merge2_kernel(const double* __restrict__ pval, const uint8_t* __restrict__ pany, const int64_t* __restrict__ gis,
-                                   int n_groups, int T, int nb, const double* __restrict__ tops, double qtl,
+                                   int n_groups, int T, int nb, int exp_buckets, const double* __restrict__ tops, double qtl,
                                    double* __restrict__ out_values /* [G][T][nb] or null */, double* __restrict__ out_q /* [G][T] or null */) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)n_groups * T) return;
@@ -126,28 +126,7 @@ __global__ void hist_merge2_kernel(const double* __restrict__ pval, const uint8_
     double mx = 0.0;
     for (int b = 0; b < nb; ++b) { double nv = v[b] + pv[(size_t)b * T]; if (nv < mx || nv != nv) nv = mx; else if (nv > mx) mx = nv; v[b] = nv; }
   }
-  double qv = NaNv;
-  if (any) {
-    if (qtl == qtl) {                                                        // Histogram.quantile
-      const double top = v[nb - 1];
-      if (qtl < 0) qv = __longlong_as_double(0xfff0000000000000LL);
-      else if (qtl > 1) qv = __longlong_as_double(0x7ff0000000000000LL);
-      else if (nb < 2 || !(top > 0)) qv = NaNv;
-      else {
-        double rank = qtl * top;
-        int bucket = 0; while (v[bucket] < rank) ++bucket;
-        const double bucketStart = bucket == 0 ? 0.0 : tops[bucket - 1];
-        const double bucketEnd = tops[bucket];
-        if (bucket == nb - 1 && isinf(bucketEnd) && bucketEnd > 0) qv = tops[nb - 2];
-        else if (bucket == 0 && tops[0] <= 0) qv = tops[0];
-        else {
-          const double count = bucket == 0 ? v[bucket] : v[bucket] - v[bucket - 1];
-          rank -= (bucket == 0 ? 0.0 : v[bucket - 1]);
-          qv = bucketStart + (bucketEnd - bucketStart) * (rank / count);
-        }
-      }
-    }
-  }
+  const double qv = (any && qtl == qtl) ? hist_quantile(v, nb, tops, qtl, exp_buckets != 0) : NaNv;
   if (out_values) for (int b = 0; b < nb; ++b) out_values[(size_t)i * nb + b] = any ? v[b] : NaNv;
   if (out_q) out_q[i] = qv;
 }
@@ -169,11 +148,11 @@ cudaError_t launch_hist_scan2(const ScanLaunch& L, int nb, int max_rows, uint32_
   hist_scan2_kernel<<<L.grid, H2_THREADS, smem, L.stream>>>(L.arena, L.rec_off, L.q, nb, max_rows, max_rec, order, item_begin, n_items, pval, pany, L.d_counters, L.d_err);
   return cudaGetLastError();
 }
-cudaError_t launch_hist_merge2(const double* pval, const uint8_t* pany, const int64_t* gis, int n_groups, int T, int nb, const double* tops, double q,
+cudaError_t launch_hist_merge2(const double* pval, const uint8_t* pany, const int64_t* gis, int n_groups, int T, int nb, int exp_buckets, const double* tops, double q,
                                double* out_values, double* out_q, cudaStream_t s) {
   const int64_t n = (int64_t)n_groups * T;
   if (n <= 0) return cudaSuccess;
-  hist_merge2_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pval, pany, gis, n_groups, T, nb, tops, q, out_values, out_q);
+  hist_merge2_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(pval, pany, gis, n_groups, T, nb, exp_buckets, tops, q, out_values, out_q);
   return cudaGetLastError();
 }
 

@@ -16,6 +16,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <cmath>
 #include "filo_record.h"
 #include "scan_params.h"
 #include "hist_decode.h"
@@ -391,6 +392,28 @@ FILO_HD inline bool h2_window(int k, const H2Ctx& X, double* pv, bool first) {
     }
   }
   return true;
+}
+
+// Histogram.quantile (vectors/Histogram.scala:65-108; min = 0, max = +Inf, evenDistribution = false) over cumulative bucket sums v[nb] with
+// bucket tops tops[nb]; exp_buckets: Base2ExpHistogramBuckets interpolate in log2 space except in the zero bucket (:97-104, log2 :111)
+FILO_HD inline double hist_quantile(const double* v, int nb, const double* tops, double qtl, bool exp_buckets) {
+  const double NaNv = h2_nan(), Inf = HUGE_VAL;
+  const double top = v[nb - 1];
+  if (qtl < 0) return -Inf;
+  if (qtl > 1) return Inf;
+  if (nb < 2 || !(top > 0)) return NaNv;
+  double rank = qtl * top;
+  int bucket = 0; while (v[bucket] < rank) ++bucket;
+  const double bucketStart = bucket == 0 ? 0.0 : tops[bucket - 1];
+  const double bucketEnd = tops[bucket];
+  if (bucket == nb - 1 && bucketEnd == Inf) return tops[nb - 2];
+  if (bucket == 0 && tops[0] <= 0) return tops[0];
+  const double count = bucket == 0 ? v[bucket] : v[bucket] - v[bucket - 1];
+  rank -= (bucket == 0 ? 0.0 : v[bucket - 1]);
+  const double fraction = rank / count;
+  if (!exp_buckets || bucketStart == 0) return bucketStart + (bucketEnd - bucketStart) * fraction;
+  const double ln2 = log(2.0), logEnd = log(bucketEnd) / ln2, logStart = log(bucketStart) / ln2;
+  return pow(2.0, logStart + (logEnd - logStart) * fraction);
 }
 
 } // namespace filo

@@ -53,13 +53,13 @@ cudaError_t launch_scan_wp_ctr_agg(const ScanLaunch& L, const WpCtrSmem& W, cons
 size_t hist_smem_bytes(int max_rows, int nb, int T, bool agg, uint32_t max_rec);
 cudaError_t launch_hist_scan(const ScanLaunch& L, int nb, int max_rows, uint32_t max_rec, const int32_t* order, const int64_t* item_begin, int64_t n_items, int agg,
                              double* out, double* pval, uint8_t* pany);
-cudaError_t launch_hist_merge(const double* pval, const uint8_t* pany, const int64_t* gis, int n_groups, int T, int nb, const double* tops, double q,
+cudaError_t launch_hist_merge(const double* pval, const uint8_t* pany, const int64_t* gis, int n_groups, int T, int nb, int exp_buckets, const double* tops, double q,
                               double* out_values, double* out_q, cudaStream_t s);
 // second version of the histogram scan (hist_kernels2.cu): fused sum of rate / increase over cumulative SectDelta histograms
 size_t hist2_smem_bytes(int max_rows, int nb, uint32_t max_rec);
 cudaError_t launch_hist_scan2(const ScanLaunch& L, int nb, int max_rows, uint32_t max_rec, const int32_t* order, const int64_t* item_begin, int64_t n_items,
                               double* pval, uint8_t* pany);
-cudaError_t launch_hist_merge2(const double* pval, const uint8_t* pany, const int64_t* gis, int n_groups, int T, int nb, const double* tops, double q,
+cudaError_t launch_hist_merge2(const double* pval, const uint8_t* pany, const int64_t* gis, int n_groups, int T, int nb, int exp_buckets, const double* tops, double q,
                                double* out_values, double* out_q, cudaStream_t s);
 cudaError_t launch_iota(int32_t* a, int64_t n, cudaStream_t s);
 cudaError_t launch_group_bounds(const int32_t* sorted_keys, int64_t n, int n_groups, int64_t* group_start, cudaStream_t s);

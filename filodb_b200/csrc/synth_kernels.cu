@@ -616,7 +616,7 @@ static int32_t hist_build(filo_ctx* ctx, HistSynthParams P, const uint8_t* h_def
 }
 static bool hist_def_ok(int32_t n_buckets, int32_t format_code, const uint8_t* def, int32_t def_bytes) {
   if (!def || n_buckets <= 0 || n_buckets > HS_MAXNB || def_bytes < 4 || def_bytes > 1024) return false;
-  if (!(format_code == 3 || format_code == 4 || format_code == 5)) return false;
+  if (!(format_code == 3 || format_code == 4 || format_code == 5 || format_code == 9)) return false;   // 9: otel exponential, an 18-byte definition
   const int len = def[0] | (def[1] << 8), n = def[2] | (def[3] << 8);
   return len + 2 == def_bytes && n == n_buckets;
 }

@@ -191,7 +191,7 @@ int32_t filo_encode_table(filo_ctx* ctx, const int64_t* timestamps, const double
                           filo_table** out);
 /* Histogram columns written on the device: SectDelta HistogramVectors (AppendableSectDeltaHistVector.appendHist, HistogramVector.scala:
  * 489-545; Section.scala:91-145; NibblePack.scala:296-345), byte-identical to the JVM appender.  bucket_def = the bucket definition as a
- * BinaryHistogram carries it (u16 length prefix + body; format_code 0x03 / 0x04 geometric, 0x05 custom), 1..64 buckets.
+ * BinaryHistogram carries it (u16 length prefix + body; format_code 0x03 / 0x04 geometric, 0x05 custom, 0x09 otel exponential), 1..64 buckets.
  *   filo_encode_hist_table: an ingest batch -- cumulative bucket counts [n_series][rows][n_buckets] and timestamps [n_series][rows] in HOST
  *     memory -- encoded into a resident table (one chunk per rows_per_chunk rows);
  *   filo_synth_hist_table: the bench / test generator (row r adds 1 + hash % 3 observations to bucket (r + series) % n_buckets,
@@ -233,8 +233,11 @@ int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t range_fn,
                           int32_t aggr_op, int32_t k, int32_t flags,
                           void* d_out_values, void* d_out_aux, void* cuda_stream, filo_stats* stats);
 /* Histogram value columns (HistogramVector.scala: H_SIMPLE / H_SECTDELTA vectors).  filo_load_series accepts them as the value
- * column when every series of the table uses ONE bucket scheme (1..64 geometric or custom buckets; otel exponential buckets are
- * declined with FILO_ERR_UNSUPPORTED); filo_table_info.schema_flags keeps the caller's flags.  filo_query_hist runs
+ * column when every series of the table uses ONE bucket scheme: 1..64 geometric, custom or otel exponential buckets
+ * (Base2ExpHistogramBuckets stored in these vectors, format code 0x09: what a counter=true histogram column holds,
+ * TimeSeriesStore.scala:278-285; histogram_quantile then interpolates in log2 space, Histogram.scala:97-104).  Row-wise
+ * ExpHistogramVector columns (wire 0x1309, a scheme per row) and the XOR-packed codes 0x08 / 0x0a / 0x10 are declined with
+ * FILO_ERR_UNSUPPORTED; filo_table_info.schema_flags keeps the caller's flags.  filo_query_hist runs
  *   HistRateFunction / HistIncreaseFunction (RateFunctions.scala:330-418) over cumulative SectDelta histograms with counter
  *   correction (SectDeltaHistogramReader, HistogramVector.scala:628-738), optionally HistSumRowAggregator
  *   (aggregator/HistSumRowAggregator.scala) over the table's groups and HistogramQuantileImpl (InstantFunction.scala:362-368).

@@ -72,7 +72,7 @@ int main(int argc, char** argv) {
   cusim::rng_state() = argc > 1 ? std::strtoull(argv[1], nullptr, 10) : 0;
   std::mt19937_64 rng(99);
   long checked = 0; int cases = 0;
-  struct Cfg { int nb; bool geometric; std::vector<int> chunks; int jitter, reset_every; bool sect, cumulative; int fn; int64_t window, step; int nser, seg; int inclusive; };
+  struct Cfg { int nb; bool geometric; std::vector<int> chunks; int jitter, reset_every; bool sect, cumulative; int fn; int64_t window, step; int nser, seg; int inclusive; int exp_scale = -100; /* > -100: otel exponential buckets (scale, start index -5) */ };
   const std::vector<Cfg> cfgs = {
     {20, false, {400, 80}, 0, 0, true, true, filo::FN_RATE, 300000, 15000, 7, 3, 1},          // C4 shape
     {8, true, {70, 50, 40}, 3000, 37, true, true, filo::FN_INCREASE, 120000, 15000, 9, 4, 1},  // resets inside chunks and at chunk starts, irregular scrapes
@@ -80,11 +80,13 @@ int main(int argc, char** argv) {
     {12, true, {80, 40}, 0, 0, false, false, filo::FN_SUM, 300000, 15000, 6, 3, 1},            // delta temporality, simple (row) vectors: sum_over_time
     {12, true, {80, 40}, 2000, 0, false, false, filo::FN_RATE, 200000, 30000, 6, 6, 1},        // ... and rate = window sum / window length
     {16, false, {100, 60}, 0, 0, true, true, filo::FN_SUM, 300000, 15000, 4, 2, 1},            // sum_over_time over cumulative SectDelta vectors
+    {12, false, {90, 70}, 0, 41, true, true, filo::FN_RATE, 300000, 15000, 6, 2, 1, 3},        // otel exponential buckets (scale 3) in SectDelta vectors: log-space quantile
+    {24, false, {50, 50, 30}, 1500, 0, true, true, filo::FN_INCREASE, 200000, 20000, 5, 5, 1, -1},  // ... scale -1 (base 4)
   };
   for (size_t ci = 0; ci < cfgs.size(); ++ci) {
     const Cfg& c = cfgs[ci];
     std::vector<double> les; for (int i = 0; i < c.nb - 1; ++i) les.push_back(2.0 * std::pow(3.0, i)); les.push_back(INFINITY);
-    const H::Buckets b = c.geometric ? H::Buckets::geometric(2.0, 2.0, c.nb) : H::Buckets::custom(les.data(), c.nb);
+    const H::Buckets b = c.exp_scale > -100 ? H::Buckets::exponential(c.exp_scale, -5, c.nb - 1) : c.geometric ? H::Buckets::geometric(2.0, 2.0, c.nb) : H::Buckets::custom(les.data(), c.nb);
     int rows = 0; for (int n : c.chunks) rows += n;
     const int64_t t0 = 1700000000000LL;
     std::vector<Series> SS((size_t)c.nser); std::vector<int64_t> rec_off((size_t)c.nser + 1, 0); uint32_t max_rec = 0;
@@ -142,7 +144,7 @@ int main(int argc, char** argv) {
       counters[0] = counters[1] = 0; std::memset(derr, 0, sizeof derr);
       cusim::launch(dim3(2), dim3(filo::H2_THREADS), [&] { filo::hist_scan2_kernel(arena, rec_off.data(), q, nb, rows, max_rec, order.data(), item_begin.data(), n_items, pval.data(), pany.data(), counters, derr); });
       if (derr[0]) { std::printf("FAIL cfg %zu: v2 device error %d\n", ci, derr[0]); return 1; }
-      cusim::launch(dim3((unsigned)((T + 127) / 128)), dim3(128), [&] { filo::hist_merge2_kernel(pval.data(), pany.data(), gis, 1, T, nb, tops.data(), 0.9, ov.data(), oq.data()); });
+      cusim::launch(dim3((unsigned)((T + 127) / 128)), dim3(128), [&] { filo::hist_merge2_kernel(pval.data(), pany.data(), gis, 1, T, nb, b.kind == H::Buckets::EXP ? 1 : 0, tops.data(), 0.9, ov.data(), oq.data()); });
       if (!check_fused("v2", ov, oq)) return 1;
       if ((int64_t)counters[0] != (int64_t)c.nser * rows) { std::printf("FAIL cfg %zu: v2 samples_scanned %llu\n", ci, counters[0]); return 1; }
     }
@@ -152,7 +154,7 @@ int main(int argc, char** argv) {
       counters[0] = counters[1] = 0; std::memset(derr, 0, sizeof derr);
       cusim::launch(dim3(2), dim3(filo::HIST_THREADS), [&] { filo::hist_scan_kernel(arena, rec_off.data(), c.nser, q, nb, rows, max_rec, order.data(), item_begin.data(), n_items, 1, nullptr, pval.data(), pany.data(), counters, derr); }, 128 * 1024);
       if (derr[0]) { std::printf("FAIL cfg %zu: v1 device error %d\n", ci, derr[0]); return 1; }
-      cusim::launch(dim3((unsigned)((T + 127) / 128)), dim3(128), [&] { filo::hist_merge_kernel(pval.data(), pany.data(), gis, 1, T, nb, tops.data(), 0.9, ov.data(), oq.data()); });
+      cusim::launch(dim3((unsigned)((T + 127) / 128)), dim3(128), [&] { filo::hist_merge_kernel(pval.data(), pany.data(), gis, 1, T, nb, b.kind == H::Buckets::EXP ? 1 : 0, tops.data(), 0.9, ov.data(), oq.data()); });
       if (!check_fused("v1", ov, oq)) return 1;
     }
     // ---- first kernel, per series (NaN buckets = empty histogram)

@@ -442,7 +442,7 @@ def _hist_series(rng, rows, nb, resets=()):
 
 
 @pytest.mark.parametrize("kernel", ["v2", "v1"])
-@pytest.mark.parametrize("scheme", ["custom", "geometric"])
+@pytest.mark.parametrize("scheme", ["custom", "geometric", "otel"])
 def test_hist_rate_sum_quantile(gpu, oracle, scheme, kernel, monkeypatch):
     """hist rate / increase (SectDelta, counter correction inside and across chunks), fused sum by group, histogram_quantile.
     kernel: the fused sum runs on hist_scan2_kernel by default; FILO_HIST_V2=0 keeps it on the first kernel."""
@@ -453,6 +453,10 @@ def test_hist_rate_sum_quantile(gpu, oracle, scheme, kernel, monkeypatch):
     t0, rows = 1_700_000_000_000, 240
     if scheme == "custom":
         b = H.Buckets.custom([2.0 * 3 ** i for i in range(19)] + [float("inf")])      # TestTimeseriesProducer.scala:229-235
+    elif scheme == "otel":
+        # Base2ExpHistogramBuckets in SectDelta vectors (format code 0x09): what a `counter = true` histogram column holds for otel
+        # exponential histograms (TimeSeriesStore.scala:278-285); scale 3, buckets 0 | 2^(-4/8) .. 2^(10/8)
+        b = H.Buckets.exponential(3, -5, 15)
     else:
         b = H.Buckets.geometric(2.0, 2.0, 12)
     st = H.HistStore(b)
@@ -499,6 +503,24 @@ def test_hist_rate_sum_quantile(gpu, oracle, scheme, kernel, monkeypatch):
     with pytest.raises(capi.FiloError):
         ctx.query_hist(tab, capi.FN_MIN_OVER_TIME, *queries[0])
     tab.free()
+
+
+def test_row_wise_exp_histogram_vectors_are_declined(gpu, oracle):
+    """ExpHistogramVector (wire 0x1309: a BinaryHistogram blob with its own scheme per row, ExpHistogramVector.scala:19-35) is not on the
+    device path: the load answers FILO_ERR_UNSUPPORTED and the caller keeps the JVM path (the reference has no counter reader for it and
+    its rate over differing schemes is unimplemented, RateFunctions.scala:387-399)."""
+    capi, ctx = gpu; o = oracle
+    from oracle import hist as H
+    app = H.Appender(2, 1024)                                                   # sect == 2: AppendableExpHistogramVector
+    for sch, vals in (((3, -3, 1), [0, 3]), ((20, -3, 9), [0, 4, 5, 6, 7, 8, 9, 10, 11, 12])):
+        assert app.add(H.Buckets.exponential(*sch).write_delta(vals)) == H.ACK
+    hv = app.bytes()
+    st = o.Store(); st.add_series()
+    tsv = o.Store(); tsv.add_series(); tsv.add_chunk(0, np.array([1000, 2000], np.int64), np.zeros(2))
+    st.add_chunk_raw(0, 1000, 2000, 2, tsv.vector_bytes(0, 0, 0), hv)
+    with pytest.raises(capi.FiloError) as e:
+        ctx.load_series(*st.all_info_addrs())
+    assert e.value.code == capi.ERR_UNSUPPORTED
 
 
 def test_hist_sum_over_time_and_delta_schema(gpu, oracle):
@@ -845,7 +867,7 @@ def test_encode_ingest_batch_on_gpu(gpu, oracle, value_enc):
     tab.free(); ref.free()
 
 
-@pytest.mark.parametrize("scheme", ["geometric", "custom"])
+@pytest.mark.parametrize("scheme", ["geometric", "custom", "otel"])
 def test_histogram_vectors_encoded_on_gpu(gpu, oracle, scheme):
     """filo_encode_hist_table / filo_synth_hist_table: SectDelta HistogramVectors written on the device are byte for byte the JVM appender's
     (AppendableSectDeltaHistVector.appendHist incl. section roll-over every 16 records and Drop sections; oracle restatement), and queries agree."""
@@ -856,6 +878,9 @@ def test_histogram_vectors_encoded_on_gpu(gpu, oracle, scheme):
     t0, rows, rpc, nb = 1_700_000_000_000, 230, 100, (20 if scheme == "geometric" else 13)
     if scheme == "geometric":
         b = H.Buckets.geometric(2.0, 3.0, nb); bdef, fmt = capi.geometric_bucket_def(2.0, 3.0, nb)
+        assert (bdef == b.serialize()).all()
+    elif scheme == "otel":
+        b = H.Buckets.exponential(-1, -3, nb - 1); bdef, fmt = capi.exp_bucket_def(-1, -3, nb - 1)       # base 4, tops 0 | 4^-2 .. 4^9
         assert (bdef == b.serialize()).all()
     else:
         les = [0.5 * 2 ** i for i in range(nb - 1)] + [float("inf")]
