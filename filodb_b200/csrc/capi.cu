@@ -51,7 +51,8 @@ struct filo_ctx {
     cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
   };
   std::mutex scan_mu;
-  ScanSlot scan[3];
+  static constexpr int MAX_SCAN_SLOTS = 8;
+  ScanSlot scan[MAX_SCAN_SLOTS];
   // host memory registered for device access (filo_host_register): chunk vectors inside these ranges are gathered by the GPU
   struct HostRange { uintptr_t base; size_t bytes; };
   std::vector<HostRange> ranges;
@@ -335,10 +336,11 @@ int classify_val(const uint8_t* v, VecInfo& o) {
 
 struct SeriesPlan { uint32_t rec_bytes; uint32_t n_chunks; uint32_t n_rows; uint32_t flags; };
 
-struct LoadIn { int64_t n_series; const int32_t* n_chunks; const uint64_t* addrs; const int64_t* chunk_base; int32_t ts_col, val_col;
+struct LoadIn { int64_t n_series; const int32_t* n_chunks; const uint64_t* addrs; const int64_t* chunk_base /* entry of series i at [i - cb0] */; int32_t ts_col, val_col;
                 // filo_scan_series: the one walk over the ChunkSetInfo blocks also leaves the gather entries of the chunks with rows (entry k of
                 // series i at gc_out[chunk_base[i] - gc_base + k]) and checks the vectors against the registered host ranges
-                GatherChunk* gc_out = nullptr; int64_t gc_base = 0; const std::vector<filo_ctx::HostRange>* ranges = nullptr; };
+                GatherChunk* gc_out = nullptr; int64_t gc_base = 0; const std::vector<filo_ctx::HostRange>* ranges = nullptr;
+                int64_t cb0 = 0; };
 struct PlanTotals { int64_t chunks = 0, samples = 0, alg = 0; int32_t maxrows = 0, maxch = 0; uint32_t max_rec = 0, f_or = 0, f_and = ~0u;
                     const uint8_t* hist_def = nullptr; bool any_scalar = false, hist_mismatch = false; bool all_in_ranges = true; };
 // same bucket scheme: format code, definition length and bytes of two HistogramVector headers (HistogramVector.matchBucketDef, :262-268)
@@ -352,7 +354,7 @@ inline int plan_series(const LoadIn& in, int64_t i, SeriesPlan& out, PlanTotals&
   uint32_t bytes = sizeof(RecordHeader), rows = 0, nch = 0, flags = REC_ALL_TS_CONST;
   int64_t prev_start = INT64_MIN, prev_end = INT64_MIN;
   for (int32_t j = 0; j < in.n_chunks[i]; ++j) {
-    const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)in.addrs[in.chunk_base[i] + j]);
+    const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)in.addrs[in.chunk_base[i - in.cb0] + j]);
     const int32_t numRows = rd32(info + 8);
     if (numRows <= 0) continue;                                   // skipped by WindowedChunkIterator (ChunkSetInfo.scala:493)
     const int64_t startT = (int64_t)(((1ull << 63) ^ (uint64_t)rd64(info)) >> 22), endT = rd64(info + 20);
@@ -377,7 +379,7 @@ inline int plan_series(const LoadIn& in, int64_t i, SeriesPlan& out, PlanTotals&
       g.ts_src = (uint64_t)(uintptr_t)tv.p; g.val_src = (uint64_t)(uintptr_t)vv.p; g.start_time = startT; g.end_time = endT;
       g.num_rows = numRows; g.ts_bytes = tv.total; g.val_bytes = vv.total; g.val_len = vv.len;
       g.drop_patch = vv.drop_patch ? (vv.drop ? 1 : 2) : 0; g.pad = 0;
-      in.gc_out[in.chunk_base[i] - in.gc_base + (int64_t)nch - 1] = g;
+      in.gc_out[in.chunk_base[i - in.cb0] - in.gc_base + (int64_t)nch - 1] = g;
       if (in.ranges && tot.all_in_ranges) {
         auto inr = [&](const uint8_t* p, size_t n) { for (auto& r : *in.ranges) if ((uintptr_t)p >= r.base && (uintptr_t)p + n <= r.base + r.bytes) return true; return false; };
         if (!inr(tv.p, (size_t)tv.total) || !inr(vv.p, (size_t)vv.total)) tot.all_in_ranges = false;
@@ -426,7 +428,7 @@ inline void fill_record(const LoadIn& in, int64_t i, const SeriesPlan& p, uint8_
   uint32_t off = sizeof(RecordHeader) + p.n_chunks * (uint32_t)sizeof(ChunkEntry);
   uint32_t c = 0, row_base = 0;
   for (int32_t j = 0; j < in.n_chunks[i]; ++j) {
-    const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)in.addrs[in.chunk_base[i] + j]);
+    const uint8_t* info = reinterpret_cast<const uint8_t*>((uintptr_t)in.addrs[in.chunk_base[i - in.cb0] + j]);
     const int32_t numRows = rd32(info + 8);
     if (numRows <= 0) continue;
     VecInfo tv, vv;
@@ -445,13 +447,13 @@ inline void fill_record(const LoadIn& in, int64_t i, const SeriesPlan& p, uint8_
   if (off < p.rec_bytes) std::memset(rec + off, 0, p.rec_bytes - off);
 }
 // pass 1 over the series [s_begin, s_end) (pool); fills plan[] and the totals, returns 0 or the first error with its series
-inline int plan_range(const LoadIn& in, int64_t s_begin, int64_t s_end, std::vector<SeriesPlan>& plan, PlanTotals& tot, int64_t& err_series_out) {
+inline int plan_range(const LoadIn& in, int64_t s_begin, int64_t s_end, std::vector<SeriesPlan>& plan, PlanTotals& tot, int64_t& err_series_out, int64_t plan_base = 0) {
   HostPool& pool = host_pool();
   std::vector<PlanTotals> part((size_t)pool.size());
   std::atomic<int> err_code{0}; std::atomic<int64_t> err_series{-1};
   pool.run(s_end - s_begin, [&](int w, int64_t b, int64_t e) {
     for (int64_t i = s_begin + b; i < s_begin + e && !err_code.load(std::memory_order_relaxed); ++i) {
-      const int rc = plan_series(in, i, plan[(size_t)i], part[(size_t)w]);
+      const int rc = plan_series(in, i, plan[(size_t)(i - plan_base)], part[(size_t)w]);
       if (rc) { int z = 0; if (err_code.compare_exchange_strong(z, rc)) err_series = i; return; }
     }
   });
@@ -1184,11 +1186,6 @@ static int32_t filo_scan_series_impl(filo_ctx* ctx, int64_t n_series, const int3
   std::lock_guard<std::mutex> one(ctx->scan_mu);          // the slots are shared: one streaming scan per context at a time
   const int64_t adjustedStep = step > 0 ? step : step + 1;
   const int T = filo_num_windows(start, adjustedStep, end);
-  std::vector<int64_t> chunk_base((size_t)n_series + 1, 0);
-  for (int64_t i = 0; i < n_series; ++i) {
-    if (n_chunks[i] < 0) return fail(ctx, FILO_ERR_INVALID_ARG, "negative n_chunks");
-    chunk_base[i + 1] = chunk_base[i] + n_chunks[i];
-  }
   static const bool timing = std::getenv("FILO_DEBUG_TIMING") != nullptr;
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
@@ -1196,16 +1193,24 @@ static int32_t filo_scan_series_impl(filo_ctx* ctx, int64_t n_series, const int3
   double t_fill = 0, t_retire = 0, t_enq = 0;
   // The series are planned (validated + sized, same rules as filo_load_series) in chunks of PLAN_CHUNK series right before their batches
   // are enqueued, so that the host walk of chunk k + 1 runs while the GPU still works on the batches of chunk k.
-  std::vector<SeriesPlan> plan((size_t)n_series);
-  LoadIn in{n_series, n_chunks, addrs, chunk_base.data(), ts_col, val_col};
-  const int64_t PLAN_CHUNK = 65536;
+  // (per-call state is sized by the plan chunk, not by n_series: the first batch is on its way after one chunk's walk)
+  std::vector<SeriesPlan> plan;
+  std::vector<int64_t> chunk_base;                      // ChunkSetInfo list positions of the plan chunk's series (+ one past the end)
+  int64_t chunks_before = 0;                            // ... of the series before the chunk
+  LoadIn in{n_series, n_chunks, addrs, nullptr, ts_col, val_col};
+  auto env_int = [](const char* name, long dflt, long lo, long hi) { const char* e = std::getenv(name); if (!e || !*e) return dflt; const long v = std::atol(e); return v < lo ? lo : v > hi ? hi : v; };
+  const int64_t PLAN_CHUNK = env_int("FILO_SCAN_PLAN_CHUNK", 65536, 1024, 1 << 24);
   std::vector<GatherChunk> gc_walk;                     // gather entries of the plan chunk, written by the planning walk
-  const size_t SLAB = (size_t)192 << 20;
-  const int64_t max_rows_out = std::max<int64_t>(1, (int64_t)(((size_t)256 << 20) / ((size_t)std::max(T, 1) * 8)));
+  const size_t SLAB = (size_t)env_int("FILO_SCAN_SLAB_MB", 192, 1, 4096) << 20;
+  const int64_t max_rows_out = std::max<int64_t>(1, (int64_t)(((size_t)env_int("FILO_SCAN_OUT_MB", 256, 1, 4096) << 20) / ((size_t)std::max(T, 1) * 8)));
+  // FILO_SCAN_TRACE=<file>: device timeline of every batch (ms since the first batch was enqueued): start, inputs on the device, kernels done, result on the host
+  const char* trace_path = std::getenv("FILO_SCAN_TRACE");
+  struct TraceRow { int64_t nb; size_t bytes; double host_ms; cudaEvent_t ev[4]; };
+  std::vector<TraceRow> trace; cudaEvent_t trace_t0 = nullptr;
   struct Batch { int64_t s0, s1; size_t bytes; int64_t chunks; };
   std::vector<filo_ctx::HostRange> ranges = ctx->ranges;
   auto in_ranges = [&](const uint8_t* p, size_t n) { for (auto& r : ranges) if ((uintptr_t)p >= r.base && (uintptr_t)p + n <= r.base + r.bytes) return true; return false; };
-  const int NSLOT = 3;
+  const int NSLOT = (int)env_int("FILO_SCAN_SLOTS", 6, 2, filo_ctx::MAX_SCAN_SLOTS);   // 3 drain while the host walks the next plan chunk; 3 / 4 / 6 slots: 0.98 / 0.97 / 0.93 s per C2 step (profiles/r2/r2_e2e_stages.md)
   for (int i = 0; i < NSLOT; ++i) {
     filo_ctx::ScanSlot& sl = ctx->scan[i];
     if (!sl.stream) { CUDA_TRY(ctx, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)); CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)); }
@@ -1215,7 +1220,7 @@ static int32_t filo_scan_series_impl(filo_ctx* ctx, int64_t n_series, const int3
   int64_t alg_total = 0; size_t n_batches = 0;
   // ---- pipeline: gather batch b (host pool) while the GPU copies/scans batch b-1 and returns batch b-2
   filo_stats acc{};
-  struct InFlight { int64_t s0 = -1; } fl[3];
+  struct InFlight { int64_t s0 = -1; } fl[filo_ctx::MAX_SCAN_SLOTS];
   int32_t rc = FILO_OK;
   auto retire = [&](int i) -> int32_t {             // the slot's previous batch has completed: collect its counters / errors
     filo_ctx::ScanSlot& sl = ctx->scan[i];
@@ -1231,11 +1236,20 @@ static int32_t filo_scan_series_impl(filo_ctx* ctx, int64_t n_series, const int3
     const int64_t c1 = std::min<int64_t>(n_series, c0 + PLAN_CHUNK);
     const auto t_p0 = now();
     PlanTotals tot; int64_t err_series = -1;
-    if (!ranges.empty()) {                              // one walk: plan + gather entries + range check
-      gc_walk.resize((size_t)(chunk_base[(size_t)c1] - chunk_base[(size_t)c0]) + 1);
-      in.gc_out = gc_walk.data(); in.gc_base = chunk_base[(size_t)c0]; in.ranges = &ranges;
+    plan.resize((size_t)(c1 - c0)); chunk_base.resize((size_t)(c1 - c0) + 1);
+    chunk_base[0] = chunks_before;
+    for (int64_t i = c0; i < c1; ++i) {
+      if (n_chunks[i] < 0) { rc = fail(ctx, FILO_ERR_INVALID_ARG, "negative n_chunks"); break; }
+      chunk_base[(size_t)(i - c0) + 1] = chunk_base[(size_t)(i - c0)] + n_chunks[i];
     }
-    if (const int err_code = plan_range(in, c0, c1, plan, tot, err_series)) {
+    if (rc != FILO_OK) break;
+    chunks_before = chunk_base[(size_t)(c1 - c0)];
+    in.chunk_base = chunk_base.data(); in.cb0 = c0;
+    if (!ranges.empty()) {                              // one walk: plan + gather entries + range check
+      gc_walk.resize((size_t)(chunk_base[(size_t)(c1 - c0)] - chunk_base[0]) + 1);
+      in.gc_out = gc_walk.data(); in.gc_base = chunk_base[0]; in.ranges = &ranges;
+    }
+    if (const int err_code = plan_range(in, c0, c1, plan, tot, err_series, c0)) {
       const char* what = err_code == FILO_ERR_UNSUPPORTED ? "chunks of a series are not in increasing time order (unsupported on the device path)"
                                                          : "CorruptVector: unknown or inconsistent BinaryVector wire format";
       rc = fail(ctx, err_code, std::string(what) + " at series " + std::to_string(err_series)); break;
@@ -1247,9 +1261,12 @@ static int32_t filo_scan_series_impl(filo_ctx* ctx, int64_t n_series, const int3
     const bool use_gather = !ranges.empty() && tot.all_in_ranges;
     // batches of the chunk: consecutive series, <= SLAB bytes of records and a bounded result block
     std::vector<Batch> batches;
+    size_t chunk_bytes = 0; for (int64_t i = c0; i < c1; ++i) chunk_bytes += plan[(size_t)(i - c0)].rec_bytes;
+    const size_t parts = std::max<size_t>((chunk_bytes + SLAB - 1) / SLAB, (size_t)((c1 - c0 + max_rows_out - 1) / max_rows_out));
+    const size_t part_bytes = std::min(SLAB, chunk_bytes / std::max<size_t>(parts, 1) + (size_t)tot.max_rec);   // even parts: equal transfers keep both copy engines busy
     for (int64_t s0 = c0; s0 < c1;) {
       int64_t s1 = s0; size_t bytes = 0; int64_t chunks = 0;
-      while (s1 < c1 && s1 - s0 < max_rows_out && (s1 == s0 || bytes + plan[(size_t)s1].rec_bytes <= SLAB)) { bytes += plan[(size_t)s1].rec_bytes; chunks += plan[(size_t)s1].n_chunks; ++s1; }
+      while (s1 < c1 && s1 - s0 < max_rows_out && (s1 == s0 || bytes + plan[(size_t)(s1 - c0)].rec_bytes <= part_bytes)) { bytes += plan[(size_t)(s1 - c0)].rec_bytes; chunks += plan[(size_t)(s1 - c0)].n_chunks; ++s1; }
       batches.push_back(Batch{s0, s1, bytes, chunks});
       s0 = s1;
     }
@@ -1276,21 +1293,28 @@ static int32_t filo_scan_series_impl(filo_ctx* ctx, int64_t n_series, const int3
       if (!rg) rg = grow_device(ctx, sl.d_out, sl.d_out_cap, (size_t)nb * (size_t)std::max(T, 1) * 8);
       if (rg) { rc = rg; break; }
     }
+    if (trace_path) {
+      TraceRow tr{nb, B.bytes, ms_since(t_begin), {nullptr, nullptr, nullptr, nullptr}};
+      for (auto& e : tr.ev) cudaEventCreate(&e);
+      if (!trace_t0) { cudaEventCreate(&trace_t0); cudaEventRecord(trace_t0, sl.stream); }
+      cudaEventRecord(tr.ev[0], sl.stream);
+      trace.push_back(tr);
+    }
     const auto t_f0 = now();
     sl.h_off[0] = 0;
-    for (int64_t j = 0; j < nb; ++j) sl.h_off[j + 1] = sl.h_off[j] + plan[(size_t)(B.s0 + j)].rec_bytes;
+    for (int64_t j = 0; j < nb; ++j) sl.h_off[j + 1] = sl.h_off[j] + plan[(size_t)(B.s0 + j - c0)].rec_bytes;
     cudaError_t ce = cudaSuccess;
     if (use_gather) {
       // gather list: per series header + per chunk source addresses; the GPU copies the vectors out of the registered memory
       GatherSeries* gs = reinterpret_cast<GatherSeries*>(sl.h_gs); GatherChunk* gc = reinterpret_cast<GatherChunk*>(sl.h_gch);
       int64_t cb = 0;
-      for (int64_t j = 0; j < nb; ++j) { const SeriesPlan& p = plan[(size_t)(B.s0 + j)]; gs[j] = GatherSeries{p.rec_bytes, p.n_chunks, p.n_rows, p.flags, cb}; cb += p.n_chunks; }
+      for (int64_t j = 0; j < nb; ++j) { const SeriesPlan& p = plan[(size_t)(B.s0 + j - c0)]; gs[j] = GatherSeries{p.rec_bytes, p.n_chunks, p.n_rows, p.flags, cb}; cb += p.n_chunks; }
       std::atomic<uint64_t> span_lo{~0ull}, span_hi{0};       // host span that holds the batch's vectors
       host_pool().run(nb, [&](int, int64_t b, int64_t e) {     // the walk's entries, compacted into the batch's list
         uint64_t lo = ~0ull, hi = 0;
         for (int64_t j = b; j < e; ++j) {
           const int64_t i = B.s0 + j; GatherChunk* o = gc + gs[j].first_chunk;
-          const GatherChunk* src = gc_walk.data() + (chunk_base[(size_t)i] - in.gc_base);
+          const GatherChunk* src = gc_walk.data() + (chunk_base[(size_t)(i - c0)] - in.gc_base);
           for (uint32_t jj = 0; jj < gs[j].n_chunks; ++jj) {
             const GatherChunk g = src[jj];
             *o++ = g;
@@ -1327,7 +1351,7 @@ static int32_t filo_scan_series_impl(filo_ctx* ctx, int64_t n_series, const int3
       if (ce == cudaSuccess) ce = cudaMemsetAsync(sl.d_in + B.bytes, 0, 64, sl.stream);
     } else {
       host_pool().run(nb, [&](int, int64_t b, int64_t e) {
-        for (int64_t j = b; j < e; ++j) fill_record(in, B.s0 + j, plan[(size_t)(B.s0 + j)], sl.h_in + sl.h_off[j]);
+        for (int64_t j = b; j < e; ++j) fill_record(in, B.s0 + j, plan[(size_t)(B.s0 + j - c0)], sl.h_in + sl.h_off[j]);
       });
       std::memset(sl.h_in + B.bytes, 0, 64);
       t_fill += ms_since(t_f0);
@@ -1336,6 +1360,7 @@ static int32_t filo_scan_series_impl(filo_ctx* ctx, int64_t n_series, const int3
     }
     const auto t_e0 = now();
     if (ce != cudaSuccess) { rc = fail(ctx, FILO_ERR_CUDA, std::string("scan H2D: ") + cudaGetErrorString(ce)); break; }
+    if (trace_path) cudaEventRecord(trace.back().ev[1], sl.stream);
     filo_table view;                                    // a table over the slot's buffers (not owned)
     view.n_series = nb; view.d_arena = sl.d_in; view.d_rec_off = sl.d_off; view.max_rows = tot.maxrows; view.max_chunks = tot.maxch;
     view.max_rec_bytes = tot.max_rec; view.any_nonconst_ts = !(tot.f_and & REC_ALL_TS_CONST); view.any_drop = (tot.f_or & REC_ANY_DROP) != 0;
@@ -1343,7 +1368,9 @@ static int32_t filo_scan_series_impl(filo_ctx* ctx, int64_t n_series, const int3
     rc = query_device_impl(ctx, &view, fn, start, step, end, window, FILO_AGG_NONE, 0, 0, sl.d_out, nullptr, sl.stream, nullptr,
                            reinterpret_cast<AsyncSink*>(sl.h_sink));
     if (rc != FILO_OK) break;
+    if (trace_path) cudaEventRecord(trace.back().ev[2], sl.stream);
     ce = cudaMemcpyAsync(out_values + (size_t)B.s0 * T, sl.d_out, (size_t)nb * T * 8, cudaMemcpyDeviceToHost, sl.stream);
+    if (trace_path) cudaEventRecord(trace.back().ev[3], sl.stream);
     if (ce == cudaSuccess) ce = cudaEventRecord(sl.done, sl.stream);
     if (ce != cudaSuccess) { rc = fail(ctx, FILO_ERR_CUDA, std::string("scan D2H: ") + cudaGetErrorString(ce)); break; }
     fl[si].s0 = B.s0;
@@ -1353,6 +1380,19 @@ static int32_t filo_scan_series_impl(filo_ctx* ctx, int64_t n_series, const int3
   }
   for (int i = 0; i < NSLOT; ++i) { const int32_t r2 = retire(i); if (rc == FILO_OK) rc = r2; }
   if (rc != FILO_OK) { for (int i = 0; i < NSLOT; ++i) if (ctx->scan[i].stream) cudaStreamSynchronize(ctx->scan[i].stream); return rc; }
+  if (trace_path) {
+    if (FILE* f = std::fopen(trace_path, "w")) {
+      std::fprintf(f, "batch,series,bytes,host_enqueue_ms,start_ms,h2d_done_ms,kernels_done_ms,d2h_done_ms\n");
+      for (size_t i = 0; i < trace.size(); ++i) {
+        float t[4] = {0, 0, 0, 0};
+        for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], trace_t0, trace[i].ev[j]);
+        std::fprintf(f, "%zu,%lld,%zu,%.3f,%.3f,%.3f,%.3f,%.3f\n", i, (long long)trace[i].nb, trace[i].bytes, trace[i].host_ms, t[0], t[1], t[2], t[3]);
+      }
+      std::fclose(f);
+    }
+    for (auto& r : trace) for (auto& e : r.ev) cudaEventDestroy(e);
+    if (trace_t0) cudaEventDestroy(trace_t0);
+  }
   if (timing) fprintf(stderr, "[filo] scan_series: %lld series, %zu batches, total %.1f ms: plan %.1f, fill %.1f, enqueue %.1f, slot waits %.1f\n",
                       (long long)n_series, n_batches, ms_since(t_begin), t_plan, t_fill, t_enq, t_retire);
   if (stats) *stats = acc;
