@@ -35,9 +35,10 @@ def run(env, steps=2, trace=None):
         os.environ["FILO_SCAN_TRACE"] = trace; one(); os.environ.pop("FILO_SCAN_TRACE")
     return dt
 res = []
-for i, env in enumerate([{}, {"FILO_SCAN_SLOTS": 3}, {"FILO_SCAN_SLOTS": 4}, {"FILO_SCAN_SLOTS": 8}]):
-    dt = run(env, steps=3, trace=("gpurun_out/scan_trace_%d.csv" % i) if i == 0 else None)
-    res.append({"env": env, "s_per_step": round(dt, 4), "G_samples_per_s": round(S * bench.ROWS / dt / 1e9, 3)})
+tag = os.environ.get("SWEEP_TAG", "d")
+for i, env in enumerate([{}, {"FILO_SCAN_SLOTS": 4}] if tag != "full" else [{}, {"FILO_SCAN_SLOTS": 3}, {"FILO_SCAN_SLOTS": 4}, {"FILO_SCAN_SLOTS": 8}]):
+    dt = run(env, steps=3, trace=("gpurun_out/scan_trace_%s%d.csv" % (tag, i)) if i == 0 else None)
+    res.append({"tag": tag, "CUDA_DEVICE_MAX_CONNECTIONS": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), "env": env, "s_per_step": round(dt, 4), "G_samples_per_s": round(S * bench.ROWS / dt / 1e9, 3)})
     print(res[-1], flush=True)
-json.dump(res, open("gpurun_out/e2e_sweep.json", "w"), indent=1)
+json.dump(res, open("gpurun_out/e2e_sweep_%s.json" % tag, "w"), indent=1)
 ctx.host_unregister(arena)
