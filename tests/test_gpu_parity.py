@@ -430,6 +430,40 @@ def test_scan_series_zero_copy_gather(gpu, oracle):
     tab.free()
 
 
+@pytest.mark.parametrize("slots", [2, 3, 6])
+def test_scan_series_many_plan_chunks_and_batches(gpu, oracle, slots, monkeypatch):
+    """The pipeline of filo_scan_series with small bounds: several plan chunks (1,024 series each), several batches per chunk (1 MB of
+    records), 2 / 3 / 6 slots in flight -- staged and zero-copy -- returns what the resident table returns, with the same counters; an
+    error in a later plan chunk surfaces after the batches in flight have drained."""
+    capi, ctx = gpu
+    monkeypatch.setenv("FILO_SCAN_PLAN_CHUNK", "1024"); monkeypatch.setenv("FILO_SCAN_SLAB_MB", "1"); monkeypatch.setenv("FILO_SCAN_SLOTS", str(slots))
+    t0, S = 1_700_000_000_000, 3500
+    tab = ctx.synth_table(S, 480, 400, t0, 15000, value_kind=1, value_enc=1, reset_period=173, nan_per_million=5000, schema_flags=1, seed=11)
+    arena, rec_off = tab.read_arena(0, S)
+    import bench
+    nch, addrs, keep = bench.host_chunk_infos(arena, rec_off, S)
+    q = (t0 + 60000, 15000, t0 + 7200000, 300000)
+    exp = {name: ctx.query(tab, getattr(capi, name), *q) for name in ("FN_RATE", "FN_SUM_OVER_TIME")}
+    want = dict(ctx.last_stats)
+    for registered in (False, True):
+        if registered: ctx.host_register(arena)
+        try:
+            for name in exp:
+                got = ctx.scan_series(nch, addrs, getattr(capi, name), *q, schema_flags=capi.SCHEMA_CUMULATIVE)
+                assert_same(got, exp[name], "scan_series slots=%d registered=%s %s" % (slots, registered, name))
+                assert ctx.last_stats["samples_scanned"] == want["samples_scanned"] and ctx.last_stats["bytes_scanned"] == want["bytes_scanned"]
+                assert ctx.last_stats["d2h_bytes"] == got.size * 8
+            bad = nch.copy(); bad[2500] = -1                                  # third plan chunk
+            with pytest.raises(capi.FiloError) as e:
+                ctx.scan_series(bad, addrs, capi.FN_RATE, *q, schema_flags=capi.SCHEMA_CUMULATIVE)
+            assert e.value.code == capi.ERR_INVALID_ARG
+            got = ctx.scan_series(nch, addrs, capi.FN_RATE, *q, schema_flags=capi.SCHEMA_CUMULATIVE)     # the context is usable afterwards
+            assert_same(got, exp["FN_RATE"], "scan_series after an error")
+        finally:
+            if registered: ctx.host_unregister(arena)
+    tab.free()
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # histogram columns (SURVEY §8 A8 / A16 / A18 HistSum / A19)
 # ---------------------------------------------------------------------------------------------------------------------
