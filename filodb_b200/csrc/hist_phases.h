@@ -247,8 +247,9 @@ FILO_HD inline void h2_decode_rows(int tid, int nthreads, const H2Ctx& X) {
 FILO_HD inline void h2_add_base(int tid, int nthreads, const H2Ctx& X) {
   const H2Ctl* C = X.ctl(); int64_t* cv = X.cv(); const uint16_t* rsec = X.rsec();
   const int rows = C->rows, nb = X.nb, pitch = X.L.pitch;
+  const uint32_t magic = (uint32_t)((0x100000000ull + (uint32_t)nb - 1) / (uint32_t)nb);     // i / nb = (i * magic) >> 32 for i * nb < 2^32 / nb (rows * nb <= 2^16 * 64 here)
   for (int i = tid; i < rows * nb; i += nthreads) {
-    const int r = i / nb, b = i - r * nb;
+    const int r = (int)(((uint64_t)(uint32_t)i * magic) >> 32), b = i - r * nb;
     const int r0 = rsec[r];
     if (r0 != r) cv[(size_t)r * pitch + b] += cv[(size_t)r0 * pitch + b];
   }
@@ -289,7 +290,7 @@ FILO_HD inline void h2_chunk_less(int tid, const H2Ctx& X) {
   }
   C->less[c] = less ? 1 : 0;
 }
-// P6 (thread per bucket): corrections carried across chunks.  carried(a, c) = (PT[c] - PT[a]) + (PD[c] - PD[a]) for a window whose
+// P6 (thread per bucket): corrections carried across chunks.  carried(a, c) = (PT[c] - PT[a]) + (PD[c] - PD[a]) (stored summed, see below) for a window whose
 // chunk set starts at a (updateCorrection :717-728 adds the chunk's own total, detectDropAndCorrection the previous last raw value)
 FILO_HD inline void h2_carried(int tid, int nthreads, const H2Ctx& X) {
   const H2Ctl* C = X.ctl(); int64_t* PT = X.PT(); int64_t* PD = X.PD(); const int64_t* TOT = X.TOT(); const int64_t* LASTRAW = X.LASTRAW();
@@ -300,7 +301,7 @@ FILO_HD inline void h2_carried(int tid, int nthreads, const H2Ctx& X) {
     for (int c = 0; c < n; ++c) {
       if (c > 0 && C->less[c]) pd += LASTRAW[(c - 1) * nb + b];
       PD[(size_t)c * nb + b] = pd;
-      PT[(size_t)c * nb + b] = pt;
+      PT[(size_t)c * nb + b] = (int64_t)((uint64_t)pt + (uint64_t)pd);   // one table: (PT[c] - PT[a]) + (PD[c] - PD[a]) = (PT + PD)[c] - (PT + PD)[a] in the JVM's wrapping long arithmetic
       pt += TOT[c * nb + b];
     }
   }
@@ -319,11 +320,24 @@ FILO_HDI double h2_div_window(double x, double fdiv, double frcp) {
 #endif
 }
 
+// extrapolation ratio of a bucket whose zero point may lie inside the window (RateFunctions.scala:84-90: durationToZero = sampledInterval *
+// (startValue / delta), durationToStart clamped to it).  Two IEEE divisions, needed for a few buckets near a series' start or a reset:
+// kept out of line on the device (inline, the compiler if-converts them into every bucket of every window)
+#if defined(__CUDACC__) && !defined(FILO_CUSIM)
+static __host__ __device__ __noinline__ double h2_clamped_ratio(double sI, double lo, double delta, double dTS, double thr, double half, double endpart) {
+#else
+inline double h2_clamped_ratio(double sI, double lo, double delta, double dTS, double thr, double half, double endpart) {
+#endif
+  const double dz = sI * (lo / delta);
+  const double dts = dz < dTS ? dz : dTS;
+  return ((sI + (dts < thr ? dts : half)) + endpart) / sI;
+}
+
 // P7 (thread per window): chunk set, row ranges, lowest / highest sample (HistogramRateFunctionBase.addTimeChunks, RateFunctions.scala:349-364),
 // then extrapolatedRate per bucket (:72-111, :366-407) folded into the item's partial row pv[b * T + k] (HistSumRowAggregator: empty
 // histograms are skipped; `first`: no series of the item has produced a histogram for this window yet).  Returns true when the window produced a histogram.
 FILO_HD inline bool h2_window(int k, const H2Ctx& X, double* pv, bool first) {
-  const H2Ctl* C = X.ctl(); const int64_t* cv = X.cv(); const int64_t* tss = X.ts(); const int64_t* PT = X.PT(); const int64_t* PD = X.PD();
+  const H2Ctl* C = X.ctl(); const int64_t* cv = X.cv(); const int64_t* tss = X.ts(); const int64_t* PT = X.PT();
   const QueryParams& q = X.q; const int n = C->n, nb = X.nb, pitch = X.L.pitch;
   const int64_t wEnd = q.start + (int64_t)k * q.step, wStart = wEnd - X.winDur;
   int a = -1, num_samples = 0, lo_row = 0, hi_row = 0, lo_c = 0, hi_c = 0; int64_t lo_t = INT64_MAX, hi_t = 0;
@@ -356,8 +370,8 @@ FILO_HD inline bool h2_window(int k, const H2Ctx& X, double* pv, bool first) {
   const double endpart = dTE < thr ? dTE : half;
   const double eTI = (sI + (dTS < thr ? dTS : half)) + endpart;
   const double ratio0 = eTI / sI, skipC = 2.0 * dTS / sI;
-  const int64_t* plo = PT + (size_t)lo_c * nb; const int64_t* pla = PT + (size_t)a * nb; const int64_t* phi = PT + (size_t)hi_c * nb;
-  const int64_t* dlo = PD + (size_t)lo_c * nb; const int64_t* dla = PD + (size_t)a * nb; const int64_t* dhi = PD + (size_t)hi_c * nb;
+  const uint64_t* plo = reinterpret_cast<const uint64_t*>(PT) + (size_t)lo_c * nb; const uint64_t* pla = reinterpret_cast<const uint64_t*>(PT) + (size_t)a * nb;
+  const uint64_t* phi = reinterpret_cast<const uint64_t*>(PT) + (size_t)hi_c * nb;
   const int64_t* rlo = cv + (size_t)lo_row * pitch; const int64_t* rhi = cv + (size_t)hi_row * pitch;
   const bool is_rate = q.fn == FN_RATE;
   // buckets in batches of H2_BATCH: the partial row lives in global memory (L2); loading a batch's old sums before computing keeps
@@ -365,29 +379,27 @@ FILO_HD inline bool h2_window(int k, const H2Ctx& X, double* pv, bool first) {
   // HistSumRowAggregator.reduceAggregate (HistSumRowAggregator.scala:25-36): the first histogram of the partial row is copied, every
   // further one goes through MutableHistogram.add = addNoCorrection + makeMonotonic (Histogram.scala:428-449): running maximum mx
   double mx = 0.0;
-  for (int b0 = 0; b0 < nb; b0 += H2_BATCH) {
+  double* pk = pv + k;                                                      // bucket b of window k at pk[b * T]
+  const size_t Tq = (size_t)q.T;
+  for (int b0 = 0; b0 < nb; b0 += H2_BATCH, pk += (size_t)H2_BATCH * Tq) {
     double old[H2_BATCH];
 #pragma unroll
-    for (int j = 0; j < H2_BATCH; ++j) if (b0 + j < nb) old[j] = pv[(size_t)(b0 + j) * q.T + k];
+    for (int j = 0; j < H2_BATCH; ++j) if (b0 + j < nb) old[j] = pk[(size_t)j * Tq];
 #pragma unroll
     for (int j = 0; j < H2_BATCH; ++j) {
       const int b = b0 + j;
       if (b < nb) {
-        const int64_t clo = (plo[b] - pla[b]) + (dlo[b] - dla[b]);
-        const int64_t chi = (phi[b] - pla[b]) + (dhi[b] - dla[b]);
+        const int64_t clo = (int64_t)(plo[b] - pla[b]), chi = (int64_t)(phi[b] - pla[b]);
         const double lo = (double)(rlo[b] + clo), hi = (double)(rhi[b] + chi);
         const double delta = hi - lo;
         double ratio = ratio0;
-        if (delta > 0 && lo >= 0 && !(lo > delta * skipC)) {                // the zero-point clamp may apply (:84-90)
-          const double dz = sI * (lo / delta);
-          const double dts = dz < dTS ? dz : dTS;
-          ratio = ((sI + (dts < thr ? dts : half)) + endpart) / sI;
-        }
+        if (delta > 0 && lo >= 0 && !(lo > delta * skipC))                  // the zero-point clamp may apply (:84-90): rare, out of line
+          ratio = h2_clamped_ratio(sI, lo, delta, dTS, thr, half, endpart);
         const double scaled = delta * ratio;
         const double r = is_rate ? h2_div_window(scaled, X.fdiv, X.frcp) * 1000.0 : scaled;
         double nv = old[j] + r;                                             // MutableHistogram.addNoCorrection: NaN-seeded sums start at 0
-        if (!first) { if (nv < mx || nv != nv) nv = mx; else if (nv > mx) mx = nv; }
-        pv[(size_t)b * q.T + k] = nv;
+        if (!first) { nv = nv >= mx ? nv : mx; mx = nv > mx ? nv : mx; }    // makeMonotonic: below the running maximum (or NaN) -> the maximum
+        pk[(size_t)j * Tq] = nv;
       }
     }
   }
