@@ -32,7 +32,7 @@ constexpr int H2_MAXSECT = 96;      // sections per series
 constexpr int H2_BATCH = FILO_H2_BATCH;         // buckets whose partial sums are loaded ahead of the arithmetic
 
 struct H2Sect { int32_t chunk, start_row /* row (over the series' chunks in range) of the section's first histogram */, n, type; uint32_t first_rec /* byte offset in record */; };
-struct H2Chunk { int32_t row_base, nrows, nsect, has_drop, sect, ts_wire; int64_t end_time; uint32_t ts_off, pad; };
+struct H2Chunk { int32_t row_base, nrows, nsect, has_drop, sect, ts_wire; int64_t end_time; uint32_t ts_off, pad /* slope of const-DDV timestamps when the closed-form row search applies, else 0 */; };
 // control block (shared memory): written by thread 0 in h2_tables, read by everyone afterwards
 struct H2Ctl {
   H2Chunk ch[H2_MAXC];
@@ -200,6 +200,10 @@ FILO_HD inline void h2_tables(int tid, const H2Ctx& X, int max_rows) {
     if (wire != WIRE_H_SECTDELTA || vnb != nb || numHist < e.num_rows) { err = 1; break; }
     H2Chunk d; d.sect = 1; d.pad = 0; d.row_base = rows; d.nrows = e.num_rows; d.nsect = 0; d.has_drop = 0; d.end_time = e.end_time;
     d.ts_off = e.ts_off; d.ts_wire = (int)(h2_ld32(rec + e.ts_off + 4) & 0xffff);
+    if (d.ts_wire == WIRE_DDV_CONST) {                    // regular timestamps: the window's row range in closed form (h2_window); slope kept when no int32 wrap can occur
+      const int32_t slope = (int32_t)h2_ld32(rec + e.ts_off + 20);
+      if (slope > 0 && (int64_t)slope * (int64_t)(e.num_rows > 0 ? e.num_rows - 1 : 0) < 0x7fffffffLL) d.pad = (uint32_t)slope;
+    }
     const uint8_t* endp = hv + (int32_t)h2_ld32(hv) + 4;
     const uint8_t* s = hv + 11 + defBytes; int start = 0;
     while (s + 4 <= endp && start < numHist) {
@@ -347,12 +351,20 @@ FILO_HD inline bool h2_window(int k, const H2Ctx& X, double* pv, bool first) {
     if (c > 0 && !(C->ch[c - 1].end_time < wEnd)) continue;
     if (a < 0) a = c;
     const int64_t* t = tss + d.row_base;
-    int lo = 0, hi = d.nrows;                                           // first row with ts >= wStart (binarySearch & 0x7fffffff)
-    while (lo < hi) { const int m = (lo + hi) >> 1; if (t[m] < wStart) lo = m + 1; else hi = m; }
-    const int s = lo;
-    lo = 0; hi = d.nrows;                                               // rows with ts <= wEnd: ceilingIndex = count - 1
-    while (lo < hi) { const int m = (lo + hi) >> 1; if (t[m] <= wEnd) lo = m + 1; else hi = m; }
-    int e = lo - 1; if (e > d.nrows - 1) e = d.nrows - 1;
+    int s, e;
+    if (d.pad != 0 && d.nrows > 0) {                                    // t[r] = t[0] + slope * r: the same two row numbers without the searches
+      const uint32_t slope = d.pad; const int64_t t0 = t[0], span = (int64_t)slope * (int64_t)(d.nrows - 1);
+      const int64_t ds = wStart - t0, de = wEnd - t0;
+      s = ds <= 0 ? 0 : ds > span ? d.nrows : (int)(((uint32_t)ds + slope - 1) / slope);
+      e = de < 0 ? -1 : de >= span ? d.nrows - 1 : (int)((uint32_t)de / slope);
+    } else {
+      int lo = 0, hi = d.nrows;                                         // first row with ts >= wStart (binarySearch & 0x7fffffff)
+      while (lo < hi) { const int m = (lo + hi) >> 1; if (t[m] < wStart) lo = m + 1; else hi = m; }
+      s = lo;
+      lo = 0; hi = d.nrows;                                             // rows with ts <= wEnd: ceilingIndex = count - 1
+      while (lo < hi) { const int m = (lo + hi) >> 1; if (t[m] <= wEnd) lo = m + 1; else hi = m; }
+      e = lo - 1; if (e > d.nrows - 1) e = d.nrows - 1;
+    }
     if (s <= e) {
       const int64_t tS = t[s], tE = t[e];
       if (tS < lo_t || tE > hi_t) {
@@ -374,6 +386,7 @@ FILO_HD inline bool h2_window(int k, const H2Ctx& X, double* pv, bool first) {
   const uint64_t* phi = reinterpret_cast<const uint64_t*>(PT) + (size_t)hi_c * nb;
   const int64_t* rlo = cv + (size_t)lo_row * pitch; const int64_t* rhi = cv + (size_t)hi_row * pitch;
   const bool is_rate = q.fn == FN_RATE;
+  const bool carried = (lo_c != a) | (hi_c != a);                         // false for a window inside one chunk: both differences are 0
   // buckets in batches of H2_BATCH: the partial row lives in global memory (L2); loading a batch's old sums before computing keeps
   // several loads in flight instead of one load -> add -> store chain per bucket
   // HistSumRowAggregator.reduceAggregate (HistSumRowAggregator.scala:25-36): the first histogram of the partial row is copied, every
@@ -389,7 +402,8 @@ FILO_HD inline bool h2_window(int k, const H2Ctx& X, double* pv, bool first) {
     for (int j = 0; j < H2_BATCH; ++j) {
       const int b = b0 + j;
       if (b < nb) {
-        const int64_t clo = (int64_t)(plo[b] - pla[b]), chi = (int64_t)(phi[b] - pla[b]);
+        int64_t clo = 0, chi = 0;                                          // corrections carried from earlier chunks of the window's chunk set
+        if (carried) { const uint64_t base = pla[b]; clo = (int64_t)(plo[b] - base); chi = (int64_t)(phi[b] - base); }
         const double lo = (double)(rlo[b] + clo), hi = (double)(rhi[b] + chi);
         const double delta = hi - lo;
         double ratio = ratio0;
