@@ -17,7 +17,7 @@ OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CORRUPT_VECTOR, ERR_UNSUPPORTED, ERR_QUERY_LI
 
 EXPORTS = ["filo_ctx_create", "filo_ctx_destroy", "filo_ctx_set_fn_args", "filo_ctx_check", "filo_last_error", "filo_load_series", "filo_table_append", "filo_synth_table", "filo_encode_table", "filo_encode_hist_table", "filo_synth_hist_table",
            "filo_table_set_groups", "filo_table_get_info", "filo_table_read_record", "filo_table_read_arena", "filo_table_free",
-           "filo_num_windows", "filo_query", "filo_query_device", "filo_scan_series", "filo_query_hist", "filo_host_register", "filo_host_unregister", "filo_present_partials",
+           "filo_num_windows", "filo_query", "filo_query_device", "filo_scan_series", "filo_query_hist", "filo_query_avg_sum_count", "filo_host_register", "filo_host_unregister", "filo_present_partials",
            "filo_result_max_containers", "filo_encode_result_device", "filo_encode_result"]
 
 
@@ -101,6 +101,7 @@ def _sig(L):
     L.filo_scan_series.argtypes = [vp, i64, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, vp, C.POINTER(Stats)]
     L.filo_query_hist.restype = i32
     L.filo_query_hist.argtypes = [vp, vp, i32, i64, i64, i64, i64, i32, C.c_double, vp, vp, C.POINTER(Stats)]
+    L.filo_query_avg_sum_count.restype = i32; L.filo_query_avg_sum_count.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, C.POINTER(Stats)]
     L.filo_host_register.restype = i32; L.filo_host_register.argtypes = [vp, vp, i64]
     L.filo_host_unregister.restype = i32; L.filo_host_unregister.argtypes = [vp, vp]
     L.filo_present_partials.restype = i32; L.filo_present_partials.argtypes = [vp, i32, i64, vp, vp, vp, vp]
@@ -357,6 +358,15 @@ class Context:
 
     def host_unregister(self, arr):
         self._check(lib().filo_host_unregister(self.h, arr.ctypes.data))
+
+    def query_avg_sum_count(self, t_sum, t_count, start, step, end, window):
+        """filo_query_avg_sum_count: avg_over_time over downsampled data (AvgWithSumAndCountOverTimeFuncD / FuncL) -> [n_series, T]."""
+        T = num_windows(start, step, end)
+        out = np.zeros((t_sum.info().n_series, T), np.float64)
+        st = Stats()
+        self._check(lib().filo_query_avg_sum_count(self.h, t_sum.h, t_count.h, start, step, end, window, _p(out), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return out
 
     def scan_series(self, n_chunks, info_addrs, fn, start, step, end, window, ts_col=0, val_col=1, schema_flags=0, out=None):
         """filo_scan_series: ingest + query + read-back of host-resident chunks in one pipelined call -> [n_series, T].

@@ -1088,6 +1088,55 @@ extern "C" int32_t filo_query(filo_ctx* ctx, const filo_table* t, int32_t fn, in
 
 
 
+// AvgWithSumAndCountOverTimeFuncD / FuncL (AggrOverTimeFunctions.scala:820-893): avg_over_time over downsampled data
+namespace {
+__global__ void ratio_kernel(double* __restrict__ num, const double* __restrict__ den, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) num[i] = num[i] / den[i];   // sumFunc.sum / countFunc.sum (IEEE)
+}
+}
+static int32_t filo_query_avg_sum_count_impl(filo_ctx* ctx, const filo_table* t_sum, const filo_table* t_count, int64_t start, int64_t step, int64_t end,
+                                             int64_t window, double* out_values, filo_stats* stats) {
+  if (!ctx || !t_sum || !t_count || !out_values) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_query_avg_sum_count: null argument");
+  if (start > end) return fail(ctx, FILO_ERR_INVALID_ARG, "start should be <= end");
+  if (t_sum->hist || t_count->hist) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_query_avg_sum_count: scalar columns only");
+  if (t_sum->n_series != t_count->n_series) return fail(ctx, FILO_ERR_INVALID_ARG, "filo_query_avg_sum_count: the two tables hold different numbers of series");
+  if (t_count->schema_flags & FILO_SCHEMA_LONG_VALUES) return fail(ctx, FILO_ERR_UNSUPPORTED, "filo_query_avg_sum_count: the count column is read as a DoubleVector (AggrOverTimeFunctions.scala:851,890)");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int64_t adjustedStep = step > 0 ? step : step + 1;
+  const int T = filo_num_windows(start, adjustedStep, end);
+  const size_t n = (size_t)t_sum->n_series * (size_t)T;
+  cudaStream_t s = ctx->stream;
+  Temp tmp(s);
+  double *d_num = nullptr, *d_den = nullptr;
+  CUDA_TRY(ctx, tmp.alloc((void**)&d_num, n * 8));
+  CUDA_TRY(ctx, tmp.alloc((void**)&d_den, n * 8));
+  // FuncD: both columns through SumOverTimeChunkedFunctionD; FuncL (Long sum column): SumOverTimeChunkedFunctionL over the sum column and
+  // CountOverTimeChunkedFunction over the count column -- the row range of a window comes from the shared timestamp column either way
+  const bool long_sum = (t_sum->schema_flags & FILO_SCHEMA_LONG_VALUES) != 0;
+  filo_stats a{}, b{};
+  int32_t rc = filo_query_device(ctx, t_sum, FILO_FN_SUM_OVER_TIME, start, step, end, window, FILO_AGG_NONE, 0, 0, d_num, nullptr, s, &a);
+  if (rc == FILO_OK) rc = filo_query_device(ctx, t_count, long_sum ? FILO_FN_COUNT_OVER_TIME : FILO_FN_SUM_OVER_TIME, start, step, end, window, FILO_AGG_NONE, 0, 0, d_den, nullptr, s, &b);
+  if (rc != FILO_OK) return rc;
+  if (n) {
+    ratio_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16), 256, 0, s>>>(d_num, d_den, (int64_t)n);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_values, d_num, n * 8, cudaMemcpyDeviceToHost, s));
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  if (stats) {
+    *stats = a;
+    stats->bytes_scanned += b.bytes_scanned; stats->samples_scanned += b.samples_scanned; stats->kernel_ns += b.kernel_ns;
+    stats->kernel_launches += b.kernel_launches + 1; stats->d2h_bytes = (int64_t)(n * 8);
+  }
+  return FILO_OK;
+}
+extern "C" int32_t filo_query_avg_sum_count(filo_ctx* ctx, const filo_table* t_sum, const filo_table* t_count, int64_t start, int64_t step, int64_t end,
+                                            int64_t window, double* out_values, filo_stats* stats) {
+  try { return filo_query_avg_sum_count_impl(ctx, t_sum, t_count, start, step, end, window, out_values, stats); }
+  catch (const std::bad_alloc&) { return fail(ctx, FILO_ERR_OOM, "filo_query_avg_sum_count: host allocation failed"); }
+  catch (const std::exception& e) { return fail(ctx, FILO_ERR_INVALID_ARG, std::string("filo_query_avg_sum_count: ") + e.what()); }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // zero-copy gather: the GPU reads chunk vectors straight out of registered (pinned, mapped) host memory
 // ------------------------------------------------------------------------------------------------------------------

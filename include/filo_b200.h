@@ -232,6 +232,13 @@ int32_t filo_query_device(filo_ctx* ctx, const filo_table* t, int32_t range_fn,
                           int64_t start_ms, int64_t step_ms, int64_t end_ms, int64_t window_ms,
                           int32_t aggr_op, int32_t k, int32_t flags,
                           void* d_out_values, void* d_out_aux, void* cuda_stream, filo_stats* stats);
+/* AvgWithSumAndCountOverTimeFuncD / FuncL (query/exec/rangefn/AggrOverTimeFunctions.scala:820-893): avg_over_time over downsampled data
+ * (RangeFunction.downsampleRangeFunction, RangeFunction.scala:272-279) = sum_over_time(sum column) / sum_over_time(count column); with a
+ * Long sum column (FILO_SCHEMA_LONG_VALUES on t_sum) the divisor is count_over_time of the count column, as FuncL has it.  t_sum and
+ * t_count are the two value columns of the same series, loaded as two tables over the same ChunkSetInfo lists (filo_load_series with
+ * val_col = the sum / the count column): the windows' row ranges come from the shared timestamp column.  out_values [n_series * T]. */
+int32_t filo_query_avg_sum_count(filo_ctx* ctx, const filo_table* t_sum, const filo_table* t_count,
+                                 int64_t start_ms, int64_t step_ms, int64_t end_ms, int64_t window_ms, double* out_values, filo_stats* stats);
 /* Histogram value columns (HistogramVector.scala: H_SIMPLE / H_SECTDELTA vectors).  filo_load_series accepts them as the value
  * column when every series of the table uses ONE bucket scheme: 1..64 geometric, custom or otel exponential buckets
  * (Base2ExpHistogramBuckets stored in these vectors, format code 0x09: what a counter=true histogram column holds,

@@ -464,6 +464,54 @@ def test_scan_series_many_plan_chunks_and_batches(gpu, oracle, slots, monkeypatc
     tab.free()
 
 
+@pytest.mark.parametrize("long_sum", [False, True])
+def test_avg_with_sum_and_count_over_downsampled_columns(gpu, oracle, long_sum):
+    """AvgWithSumAndCountOverTimeFuncD / FuncL (AggrOverTimeFunctions.scala:820-893): avg_over_time over a downsample schema = the window sum
+    of the `sum` column over the window sum of the `count` column (FuncL: a Long sum column over count_over_time of the count column), both
+    over the row range of the shared timestamp column.  The ChunkSetInfos here hold three vectors (timestamp, sum, count); the two value
+    columns are loaded as two tables (val_col 1 and 2).  Expected: the oracle's two chunked functions, divided (the reference's apply())."""
+    import ctypes
+    capi, ctx = gpu; o = oracle
+    rng = np.random.default_rng(77)
+    t0, rows, S = 1_700_000_000_000, 200, 40
+    a, b = o.Store(), o.Store()
+    for s in range(S):
+        a.add_series(); b.add_series()
+        ts = t0 + np.arange(rows, dtype=np.int64) * 60000 + (rng.integers(-900, 901, rows) if s % 3 == 1 else 0)
+        cnt = rng.integers(1, 5, rows).astype(np.float64)
+        if s % 5 == 2: cnt[rng.integers(0, rows, 6)] = NaN                     # rows the count column does not have
+        sums = np.round(rng.normal(50, 20, rows) * cnt, 3)
+        if s % 7 == 3: sums[rng.integers(0, rows, 4)] = NaN
+        for lo, hi in ((0, 90), (90, 150), (150, rows)):
+            if long_sum: a.add_chunk_longs(s, ts[lo:hi], np.nan_to_num(sums[lo:hi]).astype(np.int64))
+            else: a.add_chunk(s, ts[lo:hi], sums[lo:hi])
+            b.add_chunk(s, ts[lo:hi], cnt[lo:hi])
+    nch, addr_a = a.all_info_addrs(); _, addr_b = b.all_info_addrs()
+    # three-column ChunkSetInfo blocks: the 28 header bytes and the two vector pointers of store a, then store b's value vector
+    infos = np.zeros((addr_a.size, 52), np.uint8)
+    for i in range(addr_a.size):
+        infos[i, :44] = np.frombuffer(ctypes.string_at(int(addr_a[i]), 44), np.uint8)
+        infos[i, 44:52] = np.frombuffer(ctypes.string_at(int(addr_b[i]) + 36, 8), np.uint8)
+    addrs = (infos.ctypes.data + 52 * np.arange(addr_a.size)).astype(np.uint64)
+    t_sum = ctx.load_series(nch, addrs, ts_col=0, val_col=1, schema_flags=capi.SCHEMA_LONG_VALUES if long_sum else 0)
+    t_cnt = ctx.load_series(nch, addrs, ts_col=0, val_col=2)
+    seen_finite = seen_nan = False
+    try:
+        for (start, step, end, window) in [(t0 + 600000, 60000, t0 + (rows - 1) * 60000, 300000), (t0 - 3000000, 171000, t0 + (rows + 5) * 60000, 1234567)]:
+            num = a.query(o.FN_SUM_OVER_TIME, start, step, end, window, long_column=long_sum)
+            den = b.query(o.FN_COUNT_OVER_TIME if long_sum else o.FN_SUM_OVER_TIME, start, step, end, window)
+            with np.errstate(all="ignore"):
+                exp = num / den
+            got = ctx.query_avg_sum_count(t_sum, t_cnt, start, step, end, window)
+            assert_same(got, exp, "avg over sum/count columns long_sum=%s q=%s" % (long_sum, (start, step, end, window)))
+            seen_finite |= bool(np.isfinite(got).any()); seen_nan |= bool(np.isnan(got).any())
+        assert seen_finite and seen_nan                                        # windows without samples (NaN / NaN) are part of the data
+        with pytest.raises(capi.FiloError):
+            ctx.query_avg_sum_count(t_sum, ctx.load_series(nch[:3], addrs[:int(nch[:3].sum())], val_col=2), t0, 60000, t0 + 600000, 300000)
+    finally:
+        t_sum.free(); t_cnt.free()
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # histogram columns (SURVEY §8 A8 / A16 / A18 HistSum / A19)
 # ---------------------------------------------------------------------------------------------------------------------
