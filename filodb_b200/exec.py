@@ -28,6 +28,9 @@ class RawDataRangeVector:
     group: int = 0
 
 
+FN_AVG_WITH_SUM_AND_COUNT_OVER_TIME = 1000      # InternalRangeFunction.AvgWithSumAndCountOverTime: not a scan function id, served by filo_query_avg_sum_count
+
+
 @dataclass
 class PeriodicSamplesMapper(RangeVectorTransformer):
     startMs: int
@@ -86,6 +89,20 @@ class FusedGpuExec:
         flags = (capi.SCHEMA_CUMULATIVE if cumulative else 0) | (capi.SCHEMA_LONG_VALUES if longValues else 0)
         fn = capi.FN_LAST if psm.functionId is None else psm.functionId
         window = psm.window or 0
+        if psm.functionId == FN_AVG_WITH_SUM_AND_COUNT_OVER_TIME:
+            # AvgWithSumAndCountOverTimeFuncD / FuncL(schema.colIDs(2)) (RangeFunction.scala:325-326,360-362): sum column = valueColumn, count column next to it
+            if aggr is not None or histogram:
+                raise capi.FiloError(capi.ERR_UNSUPPORTED, "AvgWithSumAndCountOverTime: per-series rows of scalar columns only")
+            t_sum = self.ctx.load_series(nch, addrs, val_col=valueColumn, schema_flags=capi.SCHEMA_LONG_VALUES if longValues else 0)
+            try:
+                t_cnt = self.ctx.load_series(nch, addrs, val_col=valueColumn + 1)
+                try:
+                    out = self.ctx.query_avg_sum_count(t_sum, t_cnt, psm.startMs, psm.stepMs, psm.endMs, window)
+                    return QueryResult(out, None, dict(self.ctx.last_stats))
+                finally:
+                    t_cnt.free()
+            finally:
+                t_sum.free()
         self.ctx.set_fn_args(*(tuple(psm.funcParams) + (0.0, 0.0))[:2])
         try:
             if aggr is None and not histogram:          # bare PeriodicSamplesMapper: the pipelined load + scan + read-back call

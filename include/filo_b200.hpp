@@ -36,7 +36,8 @@ enum class InternalRangeFunction : int32_t {
   MinOverTime = FILO_FN_MIN_OVER_TIME, MaxOverTime = FILO_FN_MAX_OVER_TIME, Timestamp = FILO_FN_TIMESTAMP,
   StdDevOverTime = FILO_FN_STDDEV_OVER_TIME, StdVarOverTime = FILO_FN_STDVAR_OVER_TIME, Changes = FILO_FN_CHANGES,
   QuantileOverTime = FILO_FN_QUANTILE_OVER_TIME, ZScore = FILO_FN_ZSCORE, HoltWinters = FILO_FN_HOLT_WINTERS,
-  PredictLinear = FILO_FN_PREDICT_LINEAR, MedianAbsoluteDeviationOverTime = FILO_FN_MAD_OVER_TIME, PresentOverTime = FILO_FN_PRESENT_OVER_TIME
+  PredictLinear = FILO_FN_PREDICT_LINEAR, MedianAbsoluteDeviationOverTime = FILO_FN_MAD_OVER_TIME, PresentOverTime = FILO_FN_PRESENT_OVER_TIME,
+  AvgWithSumAndCountOverTime = 1000     // downsample schemas (RangeFunction.downsampleRangeFunction): two value columns, filo_query_avg_sum_count
 };
 // AggregationOperator (query/src/main/scala/filodb/query/PlanEnums.scala) subset
 enum class AggregationOperator : int32_t {
@@ -108,6 +109,19 @@ class FusedGpuExec {
     std::vector<int32_t> nChunks; std::vector<uint64_t> addrs; std::vector<int32_t> groups;
     for (const auto& rv : source) { nChunks.push_back((int32_t)rv.chunkInfoAddrs.size()); addrs.insert(addrs.end(), rv.chunkInfoAddrs.begin(), rv.chunkInfoAddrs.end()); groups.push_back(rv.group); }
     const int32_t nGroups = aggr ? aggr->numGroups : 0;
+    if (psm.functionId == InternalRangeFunction::AvgWithSumAndCountOverTime) {
+      // AvgWithSumAndCountOverTimeFuncD(schema.colIDs(2)) (RangeFunction.scala:360-362): sum column = valueColumn, count column = the next one
+      if (aggr || histogram) throw QueryError(FILO_ERR_UNSUPPORTED, "AvgWithSumAndCountOverTime: per-series rows of double columns only");
+      filo_table *ts = nullptr, *tc = nullptr;
+      check(filo_load_series(ctx_, (int64_t)source.size(), nChunks.data(), addrs.data(), 0, valueColumn, nullptr, 0, 0, &ts));
+      struct Free { filo_ctx* c; filo_table* t; ~Free() { filo_table_free(c, t); } } gs{ctx_, ts};
+      check(filo_load_series(ctx_, (int64_t)source.size(), nChunks.data(), addrs.data(), 0, valueColumn + 1, nullptr, 0, 0, &tc));
+      Free gc{ctx_, tc};
+      QueryResult r; r.windows = filo_num_windows(psm.startMs, psm.stepMs, psm.endMs); r.rows = (int32_t)source.size();
+      r.values.assign((size_t)r.rows * r.windows, 0.0);
+      check(filo_query_avg_sum_count(ctx_, ts, tc, psm.startMs, psm.stepMs, psm.endMs, psm.window.value_or(0), r.values.data(), &r.stats));
+      return r;
+    }
     filo_table* t = nullptr;
     check(filo_load_series(ctx_, (int64_t)source.size(), nChunks.data(), addrs.data(), 0, valueColumn, aggr ? groups.data() : nullptr, nGroups,
                            cumulative ? FILO_SCHEMA_CUMULATIVE : 0, &t));

@@ -506,6 +506,15 @@ def test_avg_with_sum_and_count_over_downsampled_columns(gpu, oracle, long_sum):
             assert_same(got, exp, "avg over sum/count columns long_sum=%s q=%s" % (long_sum, (start, step, end, window)))
             seen_finite |= bool(np.isfinite(got).any()); seen_nan |= bool(np.isnan(got).any())
         assert seen_finite and seen_nan                                        # windows without samples (NaN / NaN) are part of the data
+        # the operator mirror: PeriodicSamplesMapper(functionId = AvgWithSumAndCountOverTime) over the three-column range vectors
+        from filodb_b200 import exec as X
+        ex = X.FusedGpuExec.__new__(X.FusedGpuExec); ex.ctx = ctx
+        src, pos = [], 0
+        for n_ in nch:
+            src.append(X.RawDataRangeVector([int(x) for x in addrs[pos:pos + int(n_)]])); pos += int(n_)
+        psm = X.PeriodicSamplesMapper(start, step, end, window, X.FN_AVG_WITH_SUM_AND_COUNT_OVER_TIME)
+        res = ex.execute(src, psm, valueColumn=1, longValues=long_sum)
+        assert_same(np.asarray(res.values), exp, "operator mirror AvgWithSumAndCountOverTime")
         with pytest.raises(capi.FiloError):
             ctx.query_avg_sum_count(t_sum, ctx.load_series(nch[:3], addrs[:int(nch[:3].sum())], val_col=2), t0, 60000, t0 + 600000, 300000)
     finally:
