@@ -115,6 +115,15 @@ JNIEXPORT void JNICALL Java_filodb_gpu_FiloB200NativeMethods_00024_queryHist(JNI
   put_stats(env, stats, st);
 }
 
+// avg_over_time over a downsample schema: the sum and the count column as two tables (AvgWithSumAndCountOverTimeFuncD / FuncL)
+JNIEXPORT void JNICALL Java_filodb_gpu_FiloB200NativeMethods_00024_queryAvgSumCount(JNIEnv* env, jobject, jlong ctx, jlong sumTable, jlong countTable, jlong startMs, jlong stepMs,
+                                                                                   jlong endMs, jlong windowMs, jlong outValuesAddr, jlongArray stats) {
+  filo_stats st{};
+  const int32_t rc = filo_query_avg_sum_count(C(ctx), T(sumTable), T(countTable), startMs, stepMs, endMs, windowMs, reinterpret_cast<double*>((uintptr_t)outValuesAddr), &st);
+  if (rc != FILO_OK) { throw_filo(env, C(ctx), rc); return; }
+  put_stats(env, stats, st);
+}
+
 // the one-call form for a bare PeriodicSamplesMapper: gather + H2D + kernels + D2H, pipelined in batches
 JNIEXPORT void JNICALL Java_filodb_gpu_FiloB200NativeMethods_00024_scanSeries(JNIEnv* env, jobject, jlong ctx, jlong nSeries, jintArray nChunks, jlongArray chunkInfoAddrs,
                                                                              jint tsCol, jint valCol, jint schemaFlags, jint rangeFn, jlong startMs, jlong stepMs, jlong endMs,

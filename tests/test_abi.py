@@ -153,7 +153,7 @@ def test_jni_shim_exports_the_reference_naming():
     names = sorted(l.split()[-1] for l in syms if " T " in l)
     want = sorted("Java_filodb_gpu_FiloB200NativeMethods_00024_" + m for m in
                   ("ctxCreate", "ctxDestroy", "ctxSetFnArgs", "ctxCheck", "hostRegister", "hostUnregister", "loadSeries", "tableFree", "numWindows",
-                   "query", "queryHist", "scanSeries"))
+                   "query", "queryAvgSumCount", "queryHist", "scanSeries"))
     assert names == want, names
     needed = subprocess.run(["readelf", "-d", so], check=True, capture_output=True, text=True).stdout
     assert "libfilo_b200.so" in needed
