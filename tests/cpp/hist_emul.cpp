@@ -91,8 +91,8 @@ static int run_series(const Series& S, const filo::H2Ctx& X, int max_rows, doubl
 
 static bool same_bits(double a, double b) { uint64_t x, y; std::memcpy(&x, &a, 8); std::memcpy(&y, &b, 8); return x == y || (a != a && b != b); }
 
-int main() {
-  std::mt19937_64 rng(777);
+int main(int argc, char** argv) {
+  std::mt19937_64 rng(argc > 1 ? std::strtoull(argv[1], nullptr, 10) : 777);      // other seeds: other chunk layouts and histories
   long checked = 0, drops = 0, less = 0, empties = 0; int cases = 0;
   for (int cfg = 0; cfg < 24; ++cfg) {
     const int nb = cfg % 3 == 0 ? 20 : (cfg % 3 == 1 ? 8 : 33);

@@ -80,12 +80,12 @@ def test_cpp_operator_mirror_compiles_and_keeps_reference_requirements(tmp_path)
         assert "QueryError -2" in out and "ok=4" in out
 
 
-def _build_and_run_cpp(tmp_path, name, flags=()):
+def _build_and_run_cpp(tmp_path, name, flags=(), args=()):
     import subprocess
     exe = str(tmp_path / name)
     subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", *flags,
                     os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe], check=True)
-    return subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    return subprocess.run([exe, *args], check=True, capture_output=True, text=True).stdout
 
 
 def test_hist_group_decoder_matches_nibblepack_on_cpu(tmp_path):
@@ -98,8 +98,9 @@ def test_hist_scan2_phases_match_oracle_on_cpu(tmp_path):
     """filodb_b200/csrc/hist_phases.h — the phase functions hist_scan2_kernel is made of — run thread id by thread id on the CPU:
     hist rate / increase over SectDelta chunks with resets inside chunks and at chunk starts, regular and jittered timestamps,
     8 / 20 / 33 buckets, several series folded into one partial row; bit-exact against the oracle (tests/cpp/hist_emul.cpp)."""
-    out = _build_and_run_cpp(tmp_path, "hist_emul")
-    assert out.startswith("OK 72 cases") and "bit-exact" in out
+    for seed in ((), ("3",)):                      # default histories, and another draw of chunk layouts / resets
+        out = _build_and_run_cpp(tmp_path, "hist_emul", args=seed)
+        assert out.startswith("OK 72 cases") and "bit-exact" in out
 
 
 def test_tile_kernel_runs_on_the_simt_emulator(tmp_path):
