@@ -435,6 +435,27 @@ def test_over_time_known_answers(oracle):
         [(150000, 1.0), (250000, 3.0), (350000, 5.0), (450000, 7.0)]
 
 
+def test_downsampled_avg_and_count_known_answers(oracle):
+    """WindowIteratorSpec.scala:540-584 ("should calculate query results from downsampled data"): over a downsample schema avg_over_time
+    becomes AvgWithSumAndCountOverTime = sum_over_time(sum column) / sum_over_time(count column) and count_over_time becomes sum_over_time of
+    the count column (RangeFunction.downsampleRangeFunction, RangeFunction.scala:272-279; AvgWithSumAndCountOverTimeFuncD,
+    AggrOverTimeFunctions.scala:820-854).  This is the quotient filo_query_avg_sum_count forms on the device."""
+    o = oracle
+    # (timestamp, min, max, sum, count, avg) rows of the reference test
+    rows = [(100000, 2.0, 5.0, 20.0, 5.0, 2.8), (153000, 1.0, 6.0, 18.0, 3.0, 1.4), (250000, 3.0, 7.0, 21.0, 5.0, 5.0), (270000, 2.0, 10.0, 22.0, 4.0, 6.0),
+            (280000, 1.5, 2.0, 10.0, 6.0, 1.75), (360000, 0.6, 7.0, 23.0, 7.0, 2.0), (430000, 7.0, 10.0, 60.0, 5.0, 8.0), (690000, 1.8, 5.0, 25.0, 7.0, 3.0),
+            (700000, 4.9, 12.0, 80.0, 10.0, 10.0), (710000, 0.1, 3.0, 10.0, 10.0, 1.0)]
+    sums = _store_one(o, [(r[0], r[3]) for r in rows], detect_drops=False)
+    cnts = _store_one(o, [(r[0], r[4]) for r in rows], detect_drops=False)
+    q = (50000, 100000, 750000, 100000)
+    num = sums.query(o.FN_SUM_OVER_TIME, *q)[0]; den = cnts.query(o.FN_SUM_OVER_TIME, *q)[0]
+    with np.errstate(all="ignore"):
+        avg = num / den
+    got = [(q[0] + k * q[1], v) for k, v in enumerate(avg) if not math.isnan(v)]
+    assert got == [(150000, 4.0), (250000, 4.875), (350000, 3.533333333333333), (450000, 6.916666666666667), (750000, 4.2592592592592595)]
+    assert _non_nan(o, cnts, o.FN_SUM_OVER_TIME, *q) == [(150000, 5.0), (250000, 8.0), (350000, 15.0), (450000, 12.0), (750000, 27.0)]
+
+
 def test_last_sample_staleness(oracle):
     # WindowIteratorSpec.scala:325-368 (window 180000) and :370-431 (5 min) and :433-464
     o = oracle
