@@ -251,9 +251,11 @@ FILO_HD inline void h2_decode_rows(int tid, int nthreads, const H2Ctx& X) {
 FILO_HD inline void h2_add_base(int tid, int nthreads, const H2Ctx& X) {
   const H2Ctl* C = X.ctl(); int64_t* cv = X.cv(); const uint16_t* rsec = X.rsec();
   const int rows = C->rows, nb = X.nb, pitch = X.L.pitch;
-  const uint32_t magic = (uint32_t)((0x100000000ull + (uint32_t)nb - 1) / (uint32_t)nb);     // i / nb = (i * magic) >> 32 for i * nb < 2^32 / nb (rows * nb <= 2^16 * 64 here)
+  // i / nb = (i * magic) >> 32 with magic = ceil(2^32 / nb): exact while i * (magic * nb - 2^32) < 2^32, i.e. for every i < 2^26 at nb <= 64
+  // (rows * nb <= 2^16 * 64 here); nb = 1 has no 32-bit magic
+  const uint32_t magic = nb > 1 ? (uint32_t)((0x100000000ull + (uint32_t)nb - 1) / (uint32_t)nb) : 0u;
   for (int i = tid; i < rows * nb; i += nthreads) {
-    const int r = (int)(((uint64_t)(uint32_t)i * magic) >> 32), b = i - r * nb;
+    const int r = nb > 1 ? (int)(((uint64_t)(uint32_t)i * magic) >> 32) : i, b = i - r * nb;
     const int r0 = rsec[r];
     if (r0 != r) cv[(size_t)r * pitch + b] += cv[(size_t)r0 * pitch + b];
   }

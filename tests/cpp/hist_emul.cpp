@@ -94,8 +94,8 @@ static bool same_bits(double a, double b) { uint64_t x, y; std::memcpy(&x, &a, 8
 int main(int argc, char** argv) {
   std::mt19937_64 rng(argc > 1 ? std::strtoull(argv[1], nullptr, 10) : 777);      // other seeds: other chunk layouts and histories
   long checked = 0, drops = 0, less = 0, empties = 0; int cases = 0;
-  for (int cfg = 0; cfg < 24; ++cfg) {
-    const int nb = cfg % 3 == 0 ? 20 : (cfg % 3 == 1 ? 8 : 33);
+  for (int cfg = 0; cfg < 27; ++cfg) {
+    const int nb = cfg >= 24 ? (cfg == 24 ? 1 : cfg == 25 ? 2 : 64) : cfg % 3 == 0 ? 20 : (cfg % 3 == 1 ? 8 : 33);     // the last three: the smallest and the largest bucket counts
     std::vector<double> les; for (int i = 0; i < nb - 1; ++i) les.push_back(2.0 * std::pow(3.0, i)); les.push_back(INFINITY);
     const H::Buckets b = cfg % 2 ? H::Buckets::geometric(2.0, 2.0, nb) : H::Buckets::custom(les.data(), nb);
     const int rows = cfg < 4 ? 480 : 60 + (int)(rng() % 200);

@@ -100,7 +100,7 @@ def test_hist_scan2_phases_match_oracle_on_cpu(tmp_path):
     8 / 20 / 33 buckets, several series folded into one partial row; bit-exact against the oracle (tests/cpp/hist_emul.cpp)."""
     for seed in ((), ("3",)):                      # default histories, and another draw of chunk layouts / resets
         out = _build_and_run_cpp(tmp_path, "hist_emul", args=seed)
-        assert out.startswith("OK 72 cases") and "bit-exact" in out
+        assert out.startswith("OK 81 cases") and "bit-exact" in out
 
 
 def test_tile_kernel_runs_on_the_simt_emulator(tmp_path):
