@@ -499,7 +499,7 @@ int32_t filo_internal_set_hist(filo_ctx* ctx, filo_table* t, const uint8_t* hd) 
     if (ok) {
       const double logBase = std::log(std::pow(2.0, std::pow(2.0, (double)-scale)));
       t->hist_tops[0] = 0.0;
-      for (int i = 1; i < nb; ++i) t->hist_tops[(size_t)i] = std::exp((double)(startIdx + i) * logBase);
+      for (int i = 1; i < nb; ++i) t->hist_tops[(size_t)i] = std::exp((double)(int32_t)((uint32_t)startIdx + (uint32_t)i) * logBase);   // index + 1 in the JVM's wrapping Int arithmetic
       t->hist_exp = true;
     }
   } else ok = false;
