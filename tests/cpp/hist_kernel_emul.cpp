@@ -82,6 +82,9 @@ int main(int argc, char** argv) {
     {16, false, {100, 60}, 0, 0, true, true, filo::FN_SUM, 300000, 15000, 4, 2, 1},            // sum_over_time over cumulative SectDelta vectors
     {12, false, {90, 70}, 0, 41, true, true, filo::FN_RATE, 300000, 15000, 6, 2, 1, 3},        // otel exponential buckets (scale 3) in SectDelta vectors: log-space quantile
     {24, false, {50, 50, 30}, 1500, 0, true, true, filo::FN_INCREASE, 200000, 20000, 5, 5, 1, -1},  // ... scale -1 (base 4)
+    {1, true, {40, 30}, 0, 23, true, true, filo::FN_RATE, 120000, 15000, 4, 2, 1},               // one bucket (no quantile: NaN)
+    {2, false, {40, 30}, 0, 0, true, true, filo::FN_INCREASE, 120000, 15000, 4, 2, 1},           // two buckets
+    {64, true, {30, 25}, 1000, 19, true, true, filo::FN_RATE, 150000, 15000, 3, 3, 1},           // the largest table the device path takes
   };
   for (size_t ci = 0; ci < cfgs.size(); ++ci) {
     const Cfg& c = cfgs[ci];

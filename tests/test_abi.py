@@ -139,7 +139,7 @@ def test_histogram_kernels_run_on_the_simt_emulator(tmp_path):
                     os.path.join(ROOT, "tests", "cpp", "hist_kernel_emul.cpp"), "-o", exe], check=True)
     for seed in ("0", "5"):
         out = subprocess.run([exe, seed], check=True, capture_output=True, text=True).stdout
-        assert "OK 8 cases" in out and "bit-exact" in out, out
+        assert "OK 11 cases" in out and "bit-exact" in out, out
 
 
 def test_jni_shim_exports_the_reference_naming():
